@@ -1,0 +1,173 @@
+/* eph_b200 -- C ABI of the B200-native `fix eph` hot path.
+ *
+ * This is the drop-in boundary: a LAMMPS-side `FixEPH`-compatible host class
+ * (user-eph_b200/fix/fix_eph_b200.cpp) keeps the reference's argument syntax,
+ * file formats and Fix hooks and forwards the per-timestep work to these entry
+ * points.  Each entry point names the reference interface it replaces
+ * (paths relative to the LLNL/USER-EPH checkout).
+ *
+ * Conventions
+ *  - plain C, opaque handle, no exceptions across the boundary;
+ *  - every call returns EPH_B200_OK (0) or a negative error code, and
+ *    eph_b200_last_error(h) gives the message (the host fix forwards it to
+ *    LAMMPS' error->all(), mirroring fix_eph.cpp:64,140,175,182,196);
+ *  - all calls come from the rank's single host thread (LAMMPS calls fix hooks
+ *    from the main thread); work is enqueued on ONE CUDA stream (config.stream
+ *    or a library-owned one);
+ *  - per-atom arrays use LAMMPS layout: x, v, f are [n][3] row-major doubles
+ *    (`&atom->x[0][0]`), type/mask int32, tag int64; ghosts follow locals;
+ *  - pointer arguments are HOST pointers unless the `memspace` argument says
+ *    EPH_B200_DEVICE, in which case they are device pointers of the same
+ *    layout (GPU-resident LAMMPS: KOKKOS / GPU package) and no copy is made;
+ *  - there is NO CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef EPH_B200_H
+#define EPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPH_B200_VERSION 100
+
+enum eph_b200_status {
+  EPH_B200_OK = 0,
+  EPH_B200_ERR_ARG = -1,      /* bad argument / call order                    */
+  EPH_B200_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail)  */
+  EPH_B200_ERR_NODEVICE = -3, /* no usable sm_100 device                       */
+  EPH_B200_ERR_MODEL = -4,    /* friction model not available on the device   */
+  EPH_B200_ERR_STATE = -5     /* numerical guard tripped (see status word)    */
+};
+
+enum eph_b200_memspace { EPH_B200_HOST = 0, EPH_B200_DEVICE = 1 };
+
+/* eph_flag bits -- FixEPH::Flag, fix_eph.h:43-50 */
+enum eph_b200_flag {
+  EPH_B200_FRICTION = 0x01,
+  EPH_B200_RANDOM = 0x02,
+  EPH_B200_FDM = 0x04,
+  EPH_B200_NOINT = 0x08,
+  EPH_B200_NOFRICTION = 0x10,
+  EPH_B200_NORANDOM = 0x20
+};
+
+/* eph_model -- FixEPH::Model, fix_eph.h:53-60.  The device path implements
+ * PRL (4), the model every BASELINE configuration uses. */
+enum eph_b200_model { EPH_B200_MODEL_NONE = 0, EPH_B200_MODEL_PRL = 4 };
+
+/* forward-comm payloads -- FixEPH::FixState, fix_eph.h:35-40 */
+enum eph_b200_state { EPH_B200_STATE_NONE = 0, EPH_B200_STATE_RHO = 1, EPH_B200_STATE_XI = 2, EPH_B200_STATE_WI = 3 };
+
+typedef struct eph_b200_handle eph_b200_handle;
+
+/* Replaces the scalar part of FixEPH::FixEPH (fix_eph.cpp:61-241): what the
+ * constructor parses from the `fix ... eph` command line and LAMMPS state. */
+typedef struct eph_b200_config {
+  int device;             /* CUDA device ordinal of this rank                          */
+  int ntypes;             /* atom->ntypes                                              */
+  const int *type_map;    /* [ntypes] element index in the .beta file per LAMMPS type  */
+  int groupbit;           /* Fix::groupbit                                             */
+  int flags;              /* eph_flag, arg[4]                                          */
+  int model;              /* eph_model, arg[5]                                         */
+  unsigned long long seed;/* arg[3]; keys the counter-based Gaussian stream            */
+  int rank, nranks;       /* comm->me, comm->nprocs                                    */
+  void *stream;           /* cudaStream_t to enqueue on, or NULL for a private stream  */
+} eph_b200_config;
+
+int eph_b200_version(void);
+int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out);
+int eph_b200_destroy(eph_b200_handle *h);
+const char *eph_b200_last_error(const eph_b200_handle *h);
+/* message of a failed create() (no handle exists yet) */
+const char *eph_b200_create_error(void);
+
+/* Replaces EPH_Beta's spline set (eph_beta.h:96-125, :164-198) and
+ * EPH_Spline::operator() (eph_spline.h:134-142).  Coefficients are the
+ * reference's {a,b,c,d} per interval in absolute x, built on the host.
+ *   coeff_rho_r_sq [n_elements][n_rho][4],  coeff_alpha / coeff_beta [n_elements][n_beta][4]  */
+int eph_b200_set_tables(eph_b200_handle *h, int n_elements, int n_rho, double inv_dr_sq, const double *coeff_rho_r_sq,
+                        int n_beta, double inv_drho, const double *coeff_alpha, const double *coeff_beta,
+                        double r_cutoff_sq, double rho_cutoff);
+
+/* Replaces EPH_FDM's constructors and state vectors (eph_fdm.h:28-119, :415-446).
+ * box = {x0,x1,y0,y1,z0,z1}; fields are [nz][ny][nx] (index i + j*nx + k*nx*ny);
+ * flag: 0 constant, 1 dynamic, 2 zero-derivative wall; t_dyn: 1 = C_e, kappa_e follow T_e. */
+int eph_b200_set_grid(eph_b200_handle *h, int nx, int ny, int nz, const double *box, int steps, const double *T_e,
+                      const double *S_e, const double *rho_e, const double *C_e, const double *kappa_e,
+                      const int16_t *flag, const uint16_t *t_dyn);
+/* Temperature dependent parameters (eph_fdm.h:74-104): C_e(T), kappa_e(T) spline
+ * coefficients [n_T][4] and the E_e(T) running-sum table [n_T] (EPH_Linear). */
+int eph_b200_set_grid_tables(eph_b200_handle *h, int n_T, double dT, const double *coeff_C_e_T,
+                             const double *coeff_kappa_e_T, const double *E_e_T);
+/* which: 0 T_e 1 S_e 2 rho_e 3 C_e 4 kappa_e 5 dT_e ; out/in are host arrays of nx*ny*nz doubles */
+int eph_b200_get_grid(eph_b200_handle *h, int which, double *out);
+int eph_b200_put_grid(eph_b200_handle *h, int which, const double *in);
+/* EPH_FDM::get_T_total, eph_fdm.h:189-196 */
+int eph_b200_mean_T(eph_b200_handle *h, double *out);
+/* sub-steps used by the last solve (eph_fdm.h:302-313) */
+int eph_b200_last_substeps(eph_b200_handle *h, int *out);
+
+/* Replaces FixEPH::reset_dt and EPH_FDM::set_dt (fix_eph.cpp:909-916, eph_fdm.h:155-158) */
+int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz);
+
+/* Per-atom data that only changes when LAMMPS re-neighbours (atom->type, mask, tag
+ * for nlocal+nghost atoms) and the ghost->owner map of a single-rank periodic
+ * run (what Comm::forward_comm(Fix*) would realise through
+ * pack/unpack_forward_comm, fix_eph.cpp:951-1009). ghost_owner may be NULL when nghost==0. */
+int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *type, const int *mask,
+                       const int64_t *tag, const int *ghost_owner, int memspace);
+
+/* Replaces FixEPH::init_list + the per-step use of list->numneigh/firstneigh
+ * (fix_eph.cpp:289-291, :437-448).  Call only when neighbor->ago == 0.
+ * Entries may carry LAMMPS' special-bond bits; they are masked with NEIGHMASK. */
+int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *offsets, const int *neigh, int memspace);
+int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *numneigh, int *const *firstneigh);
+
+/* Replaces FixEPH::post_force (fix_eph.cpp:841-907) for model PRL:
+ * xi generation, calculate_environment (:431-466), the three ghost broadcasts,
+ * force_prl (:687-837) and f += f_EPH (+ f_RNG).
+ * x, v: [nlocal+nghost][3]; f: [nlocal][3] read-modify-write.
+ * xi_inject: [nlocal][3] Gaussians to use instead of the built-in counter-based
+ * stream (parity testing), or NULL.  ntimestep keys the built-in stream. */
+int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
+                        long long ntimestep, int memspace);
+
+/* Replaces FixEPH::end_of_step (fix_eph.cpp:350-429): energy bookkeeping,
+ * EPH_FDM::insert_energy (eph_fdm.h:172-179), EPH_FDM::solve (:267-400) and the
+ * 8-column per-atom output.  E_local (host pointer, may be NULL) receives this
+ * rank's energy transfer of the step; passing NULL avoids the host sync. */
+int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace);
+
+/* Replaces the integrator hooks (fix_eph.cpp:305-348). mass_by_type is 1-based [ntypes+1]. */
+int eph_b200_initial_integrate(eph_b200_handle *h, double *x, double *v, const double *f, const double *mass_by_type,
+                               double dtv, double dtf, int memspace);
+int eph_b200_final_integrate(eph_b200_handle *h, double *v, const double *f, const double *mass_by_type, double dtf,
+                             int memspace);
+
+/* FixEPH::array (fix_eph.cpp:406-428): [nlocal][8] = rho, beta(rho), f_EPH xyz, f_RNG xyz */
+int eph_b200_get_peratom(eph_b200_handle *h, double *array8, int memspace);
+/* probes for parity tests; LAMMPS order.
+ * which: 0 rho_i[nlocal+nghost] 1 w_i[nlocal][3] 2 xi_i[nlocal][3] 3 f_EPH[nlocal][3] 4 f_RNG[nlocal][3] */
+int eph_b200_get_probe(eph_b200_handle *h, int which, double *out);
+
+/* Replaces FixEPH::pack_forward_comm / unpack_forward_comm (fix_eph.cpp:951-1009)
+ * for a host transport (LAMMPS' MPI comm): gathers / scatters the payload of
+ * `state` between device-resident per-atom arrays and a host buffer. */
+int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list, double *buf);
+int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf);
+
+/* blocks until everything enqueued so far has finished */
+int eph_b200_synchronize(eph_b200_handle *h);
+/* number of kernels this handle has launched since creation */
+long long eph_b200_launch_count(const eph_b200_handle *h);
+/* device status word: bit0 rho_i > rho_cutoff seen (eph_beta.h:174-180), bit1 T_e clamped at 0 (eph_fdm.h:391-394),
+ * bit2 non-finite force */
+int eph_b200_status_word(eph_b200_handle *h, unsigned *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPH_B200_H */

@@ -1,0 +1,248 @@
+// Generic C driver around a LAMMPS-style fix, compiled once per fix class.
+// The harness (Python via ctypes) plays LAMMPS: it fills the per-atom arrays,
+// hands over a full neighbour list and calls the hooks in Verlet order.  The
+// same entry points exist for the compiled reference fix (prefix `ref_`) and
+// for the product fix (prefix `b200_`), so parity tests issue identical call
+// sequences against both.
+//
+// FixT must derive from LAMMPS_NS::Fix and provide the probe accessors used at
+// the bottom (p_rho, p_w, p_xi, p_feph, p_frng, grid_size, grid_T).
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "lammps_shim.h"
+
+namespace shim_driver {
+
+using namespace LAMMPS_NS;
+
+template <class FixT>
+struct World {
+  LAMMPS lmp;
+  std::unique_ptr<FixT> fix;
+  NeighList list;
+  std::vector<double> xs, vs, fs, mass;
+  std::vector<double *> xr, vr, fr;
+  std::vector<int> type, mask;
+  std::vector<long long> tag;
+  std::vector<int> numneigh, flat;
+  std::vector<int *> firstneigh;
+  std::vector<double> xi;
+  std::string err;
+  int nmax_fix = 0;
+};
+
+template <class W, class F>
+int guarded(W *w, F &&body) {
+  try {
+    body();
+    return 0;
+  } catch (const std::exception &e) {
+    w->err = e.what();
+    return -1;
+  } catch (...) {
+    w->err = "unknown exception";
+    return -2;
+  }
+}
+
+template <class FixT>
+World<FixT> *world_new(long long natoms, int ntypes, const double *boxlo, const double *boxhi, double dt,
+                       const double *mass_by_type) {
+  auto *w = new World<FixT>;
+  w->lmp.atom->natoms = natoms;
+  w->lmp.atom->ntypes = ntypes;
+  for (int d = 0; d < 3; ++d) {
+    w->lmp.domain->boxlo[d] = boxlo[d];
+    w->lmp.domain->boxhi[d] = boxhi[d];
+  }
+  w->lmp.update->dt = dt;
+  w->mass.assign(ntypes + 1, 1.0);
+  for (int t = 1; t <= ntypes; ++t) w->mass[t] = mass_by_type ? mass_by_type[t - 1] : 1.0;
+  w->lmp.atom->mass = w->mass.data();
+  return w;
+}
+
+template <class FixT>
+int world_set_atoms(World<FixT> *w, int nlocal, int nghost, const double *x, const double *v, const double *f,
+                    const int *type, const int *mask, const long long *tag, const int *ghost_owner) {
+  return guarded(w, [&] {
+    size_t n = static_cast<size_t>(nlocal) + nghost;
+    w->xs.assign(x, x + 3 * n);
+    w->vs.assign(v, v + 3 * n);
+    if (f) w->fs.assign(f, f + 3 * n); else w->fs.assign(3 * n, 0.0);
+    w->type.assign(type, type + n);
+    w->mask.assign(mask, mask + n);
+    w->tag.resize(n);
+    for (size_t i = 0; i < n; ++i) w->tag[i] = tag ? tag[i] : static_cast<long long>(i + 1);
+    w->xr.resize(n); w->vr.resize(n); w->fr.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      w->xr[i] = &w->xs[3 * i]; w->vr[i] = &w->vs[3 * i]; w->fr[i] = &w->fs[3 * i];
+    }
+    Atom *a = w->lmp.atom;
+    a->nlocal = nlocal; a->nghost = nghost; a->nmax = static_cast<int>(n);
+    a->x = w->xr.data(); a->v = w->vr.data(); a->f = w->fr.data();
+    a->type = w->type.data(); a->mask = w->mask.data(); a->tag = w->tag.data();
+    w->lmp.comm->ghost_owner.assign(ghost_owner, ghost_owner + nghost);
+    if (w->fix && a->nmax > w->nmax_fix) {   // LAMMPS' grow callback
+      w->fix->grow_arrays(a->nmax);
+      w->nmax_fix = a->nmax;
+    }
+  });
+}
+
+// Update positions / velocities / forces in place (same atom counts).
+template <class FixT>
+int world_update_xvf(World<FixT> *w, const double *x, const double *v, const double *f) {
+  return guarded(w, [&] {
+    if (x) std::copy(x, x + w->xs.size(), w->xs.begin());
+    if (v) std::copy(v, v + w->vs.size(), w->vs.begin());
+    if (f) std::copy(f, f + w->fs.size(), w->fs.begin());
+  });
+}
+
+template <class FixT>
+int world_make_fix(World<FixT> *w, int narg, const char **arg) {
+  return guarded(w, [&] {
+    std::vector<std::string> store(arg, arg + narg);
+    std::vector<char *> argv;
+    for (auto &s : store) argv.push_back(const_cast<char *>(s.c_str()));
+    w->fix.reset(new FixT(&w->lmp, narg, argv.data()));
+    w->nmax_fix = w->lmp.atom->nmax;
+    w->fix->init();
+    w->fix->init_list(0, &w->list);
+  });
+}
+
+// CSR neighbour list: offsets[nlocal+1], flat[offsets[nlocal]]
+template <class FixT>
+int world_set_neighbors(World<FixT> *w, int nlocal, const long long *offsets, const int *flat) {
+  return guarded(w, [&] {
+    w->flat.assign(flat, flat + offsets[nlocal]);
+    w->numneigh.resize(nlocal);
+    w->firstneigh.resize(nlocal);
+    for (int i = 0; i < nlocal; ++i) {
+      w->numneigh[i] = static_cast<int>(offsets[i + 1] - offsets[i]);
+      w->firstneigh[i] = w->flat.data() + offsets[i];
+    }
+    w->list.inum = nlocal;
+    w->list.numneigh = w->numneigh.data();
+    w->list.firstneigh = w->firstneigh.data();
+    w->lmp.neighbor->ago = 0;
+    if (w->fix) w->fix->init_list(0, &w->list);
+  });
+}
+
+// xi for every local atom [nlocal][3]; replayed through the RanMars stand-in
+// in the order the fix consumes it (group atoms, ascending local index).
+template <class FixT>
+int world_set_xi(World<FixT> *w, const double *xi) {
+  return guarded(w, [&] {
+    Atom *a = w->lmp.atom;
+    w->xi.clear();
+    for (int i = 0; i < a->nlocal; ++i)
+      if (a->mask[i] & w->fix->groupbit)
+        for (int d = 0; d < 3; ++d) w->xi.push_back(xi[3 * i + d]);
+    RanMars::inject = w->xi.data();
+    RanMars::inject_len = w->xi.size();
+    RanMars::cursor = 0;
+  });
+}
+
+}  // namespace shim_driver
+
+#define SHIM_DRIVER_DEFINE(P, FixT)                                                                            \
+  const double *LAMMPS_NS::RanMars::inject = nullptr;                                                          \
+  size_t LAMMPS_NS::RanMars::inject_len = 0;                                                                   \
+  size_t LAMMPS_NS::RanMars::cursor = 0;                                                                       \
+  extern "C" {                                                                                                 \
+  typedef shim_driver::World<FixT> P##_world;                                                                  \
+  void *P##_world_new(long long natoms, int ntypes, const double *lo, const double *hi, double dt,             \
+                      const double *mass) {                                                                    \
+    return shim_driver::world_new<FixT>(natoms, ntypes, lo, hi, dt, mass);                                     \
+  }                                                                                                            \
+  void P##_world_free(void *w) { delete static_cast<P##_world *>(w); }                                         \
+  const char *P##_last_error(void *w) { return static_cast<P##_world *>(w)->err.c_str(); }                     \
+  int P##_set_atoms(void *w, int nlocal, int nghost, const double *x, const double *v, const double *f,        \
+                    const int *type, const int *mask, const long long *tag, const int *owner) {                \
+    return shim_driver::world_set_atoms(static_cast<P##_world *>(w), nlocal, nghost, x, v, f, type, mask, tag, \
+                                        owner);                                                                \
+  }                                                                                                            \
+  int P##_update_xvf(void *w, const double *x, const double *v, const double *f) {                             \
+    return shim_driver::world_update_xvf(static_cast<P##_world *>(w), x, v, f);                                \
+  }                                                                                                            \
+  int P##_make_fix(void *w, int narg, const char **arg) {                                                      \
+    return shim_driver::world_make_fix(static_cast<P##_world *>(w), narg, arg);                                \
+  }                                                                                                            \
+  int P##_set_neighbors(void *w, int nlocal, const long long *off, const int *flat) {                          \
+    return shim_driver::world_set_neighbors(static_cast<P##_world *>(w), nlocal, off, flat);                   \
+  }                                                                                                            \
+  int P##_set_xi(void *w, const double *xi) {                                                                  \
+    return shim_driver::world_set_xi(static_cast<P##_world *>(w), xi);                                         \
+  }                                                                                                            \
+  int P##_set_dt(void *w_, double dt) {                                                                        \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->lmp.update->dt = dt; w->fix->reset_dt(); });                       \
+  }                                                                                                            \
+  void P##_set_step(void *w, long long step) { static_cast<P##_world *>(w)->lmp.update->ntimestep = step; }    \
+  int P##_initial_integrate(void *w_) {                                                                        \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->initial_integrate(0); });                                     \
+  }                                                                                                            \
+  int P##_post_force(void *w_) {                                                                               \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->post_force(0); });                                            \
+  }                                                                                                            \
+  int P##_final_integrate(void *w_) {                                                                          \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->final_integrate(); });                                        \
+  }                                                                                                            \
+  int P##_end_of_step(void *w_) {                                                                              \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->end_of_step(); });                                            \
+  }                                                                                                            \
+  int P##_post_run(void *w_) {                                                                                 \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->post_run(); });                                               \
+  }                                                                                                            \
+  int P##_setmask(void *w) { return static_cast<P##_world *>(w)->fix->setmask(); }                             \
+  double P##_compute_vector(void *w, int i) { return static_cast<P##_world *>(w)->fix->compute_vector(i); }    \
+  long long P##_n_forward(void *w) { return static_cast<P##_world *>(w)->lmp.comm->n_forward; }                \
+  double P##_neigh_cutoff(void *w) { return static_cast<P##_world *>(w)->lmp.neighbor->last_request.cutoff; }  \
+  int P##_fix_flags(void *w_, int *out) {                                                                      \
+    auto *f = static_cast<P##_world *>(w_)->fix.get();                                                         \
+    int v[] = {f->vector_flag, f->size_vector, f->global_freq, f->extvector, f->nevery, f->peratom_flag,       \
+               f->size_peratom_cols, f->peratom_freq, f->comm_forward, f->time_integrate,                      \
+               static_cast<P##_world *>(w_)->lmp.comm->ghost_velocity};                                        \
+    for (int i = 0; i < 11; ++i) out[i] = v[i];                                                                \
+    return 11;                                                                                                 \
+  }                                                                                                            \
+  void P##_get_xvf(void *w_, double *x, double *v, double *f) {                                                \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    if (x) std::copy(w->xs.begin(), w->xs.end(), x);                                                           \
+    if (v) std::copy(w->vs.begin(), w->vs.end(), v);                                                           \
+    if (f) std::copy(w->fs.begin(), w->fs.end(), f);                                                           \
+  }                                                                                                            \
+  void P##_get_array(void *w_, double *out) {                                                                  \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    int n = w->lmp.atom->nlocal, c = w->fix->size_peratom_cols;                                                \
+    for (int i = 0; i < n; ++i)                                                                                \
+      for (int k = 0; k < c; ++k) out[(size_t)i * c + k] = w->fix->array_atom[i][k];                           \
+  }                                                                                                            \
+  /* which: 0 rho[ntotal] 1 w[nlocal*3] 2 xi[nlocal*3] 3 f_EPH[nlocal*3] 4 f_RNG[nlocal*3] */                  \
+  int P##_get_probe(void *w_, int which, double *out) {                                                        \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] {                                                                       \
+      size_t nl = w->lmp.atom->nlocal, nt = nl + w->lmp.atom->nghost;                                          \
+      w->fix->probe_copy(which, nl, nt, out);                                                                  \
+    });                                                                                                        \
+  }                                                                                                            \
+  long long P##_grid_size(void *w) { return (long long)static_cast<P##_world *>(w)->fix->grid_size(); }        \
+  int P##_grid_T(void *w_, double *out) {                                                                      \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    return shim_driver::guarded(w, [&] { w->fix->grid_T(out); });                                              \
+  }                                                                                                            \
+  }

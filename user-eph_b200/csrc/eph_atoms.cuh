@@ -1,0 +1,207 @@
+// Streaming per-atom kernels around the sweeps: packing LAMMPS arrays into the
+// gather-friendly records, the per-atom coupling s = alpha(rho)/rho, ghost
+// fills, force accumulation, energy deposition and the integrator hooks.
+#pragma once
+
+#include "eph_device.cuh"
+
+namespace ephb {
+
+// x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits}, v4 {vx,vy,vz,0}
+__global__ void pack_atoms_kernel(int ntotal, const double *__restrict__ x, const double *__restrict__ v,
+                                  const int *__restrict__ type, const int *__restrict__ mask,
+                                  const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
+                                  double4 *__restrict__ v4) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= ntotal) return;
+  unsigned bits = static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask;
+  if (mask[a] & groupbit) bits |= kBitGroup;
+  pos4[a] = make_double4(x[3 * (size_t)a], x[3 * (size_t)a + 1], x[3 * (size_t)a + 2], bits_to_double(bits));
+  v4[a] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+}
+
+struct PrepArgs {
+  int nlocal, ntotal;
+  const int *__restrict__ owner;      // [nghost] local owner of each ghost (single-rank images) or nullptr
+  const long long *__restrict__ tag;  // [ntotal]
+  const double *__restrict__ xi_inject;  // [nlocal][3] or nullptr
+  const double2 *__restrict__ alpha_tab;  // [n_elements][n_beta][2]
+  int n_beta;
+  double inv_drho, rho_cutoff;
+  unsigned long long seed, step;
+  int do_random;
+  double *__restrict__ rho;    // [ntotal]; ghost entries are filled here
+  double *__restrict__ s;      // [ntotal]
+  double4 *__restrict__ pos4;  // validity bit is set here
+  double4 *__restrict__ z4;    // [ntotal] s * xi
+  double *__restrict__ xi;     // [nlocal][3] probe copy
+  unsigned *__restrict__ status;
+};
+
+// After the rho sweep: ghost rho (forward comm RHO, fix_eph.cpp:870-871),
+// s = alpha(rho)/rho with alpha = 0 above rho_cutoff (eph_beta.h:186-198),
+// the rho>0 validity bit, xi (fix_eph.cpp:854-865) and z = s*xi.
+__global__ void prep_coupling_kernel(PrepArgs p) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.ntotal) return;
+  const int src = (a < p.nlocal || p.owner == nullptr) ? a : p.owner[a - p.nlocal];
+  double rho = p.rho[src];
+  if (a >= p.nlocal) p.rho[a] = rho;
+  double4 pa = p.pos4[a];
+  unsigned bits = double_to_bits(pa.w) & ~kBitValid;
+  double s = 0.0;
+  if (rho > 0) {
+    bits |= kBitValid;
+    double alpha = 0.0;
+    if (rho > p.rho_cutoff) atomicOr(p.status, 1u);
+    else alpha = spline_eval(p.alpha_tab + 2 * (size_t)(bits & kElemMask) * p.n_beta, p.inv_drho, rho);
+    s = alpha / rho;
+  }
+  pa.w = bits_to_double(bits);
+  p.pos4[a] = pa;
+  p.s[a] = s;
+  double xi[3] = {0.0, 0.0, 0.0};
+  if (p.do_random && (bits & kBitGroup)) {
+    if (p.xi_inject) {
+      xi[0] = p.xi_inject[3 * (size_t)src]; xi[1] = p.xi_inject[3 * (size_t)src + 1]; xi[2] = p.xi_inject[3 * (size_t)src + 2];
+    } else {
+      xi_stream(p.seed, p.step, p.tag[a], xi);
+    }
+  }
+  p.z4[a] = make_double4(s * xi[0], s * xi[1], s * xi[2], 0.0);
+  if (a < p.nlocal) {
+    p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
+  }
+}
+
+// forward comm WI (fix_eph.cpp:743-744) for single-rank periodic images
+__global__ void ghost_fill4_kernel(int nlocal, int nghost, const int *__restrict__ owner, double4 *__restrict__ arr) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  arr[nlocal + g] = arr[owner[g]];
+}
+
+// f += f_EPH (+ f_RNG) for every local atom, grouped or not (fix_eph.cpp:892-906)
+__global__ void add_forces_kernel(int n3, double *__restrict__ f, const double *__restrict__ f_eph,
+                                  const double *__restrict__ f_rng, int add_friction, int add_random) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n3) return;
+  double v = f[t];
+  if (add_friction) v += f_eph[t];
+  if (add_random) v += f_rng[t];
+  f[t] = v;
+}
+
+struct DepositArgs {
+  int nlocal;
+  const double *__restrict__ x;      // LAMMPS layout
+  const double *__restrict__ v;
+  const double4 *__restrict__ pos4;  // bits (group) from the last post_force
+  const double *__restrict__ f_eph;
+  const double *__restrict__ f_rng;
+  const double *__restrict__ rho;
+  const double2 *__restrict__ beta_tab;
+  int n_beta;
+  double inv_drho, rho_cutoff;
+  double dt, dVdt;
+  int do_friction, do_random;
+  GridGeom grid;
+  double *__restrict__ dT_e;
+  double *__restrict__ E_sum;    // one double, accumulated atomically per block
+  double *__restrict__ array8;   // [nlocal][8]
+};
+
+// FixEPH::end_of_step (fix_eph.cpp:350-429) up to the grid solve: per-atom
+// energy transfer, EPH_FDM::insert_energy (eph_fdm.h:172-179) with one atomic
+// per distinct cell per warp, the energy sum and the 8-column output.
+__global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
+  __shared__ double s_part[8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double dE = 0.0;       // energy handed to the electrons by this atom
+  double contrib = 0.0;  // the same as a power density for its grid cell
+  int cell = -1;
+  if (i < d.nlocal) {
+    const unsigned bits = double_to_bits(d.pos4[i].w);
+    const size_t o = 3 * (size_t)i;
+    double *row = d.array8 + 8 * (size_t)i;
+    if (bits & kBitGroup) {
+      const double vx = d.v[o], vy = d.v[o + 1], vz = d.v[o + 2];
+      const double ex = d.f_eph[o], ey = d.f_eph[o + 1], ez = d.f_eph[o + 2];
+      const double rx = d.f_rng[o], ry = d.f_rng[o + 1], rz = d.f_rng[o + 2];
+      double dEf = 0.0, dEr = 0.0;
+      if (d.do_friction) { dEf -= ex * vx * d.dt; dEf -= ey * vy * d.dt; dEf -= ez * vz * d.dt; }
+      if (d.do_random) { dEr -= rx * vx * d.dt; dEr -= ry * vy * d.dt; dEr -= rz * vz * d.dt; }
+      dE = dEf + dEr;
+      contrib = dEf / d.dVdt + dEr / d.dVdt;  // two insert_energy calls in the reference
+      cell = grid_index(d.grid, d.x[o], d.x[o + 1], d.x[o + 2]);
+      const double rho = d.rho[i];
+      double beta = 0.0;  // eph_beta.h:171-184
+      if (!(rho > d.rho_cutoff))
+        beta = spline_eval(d.beta_tab + 2 * (size_t)(bits & kElemMask) * d.n_beta, d.inv_drho, rho);
+      row[0] = rho; row[1] = beta;
+      row[2] = ex; row[3] = ey; row[4] = ez;
+      row[5] = rx; row[6] = ry; row[7] = rz;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) row[c] = 0.0;
+    }
+  }
+  // warp-aggregated scatter-add: atoms are spatially sorted, so a warp usually
+  // touches one to three cells; each distinct cell costs one fp64 atomic.
+  unsigned remaining = __ballot_sync(0xFFFFFFFFu, cell >= 0);
+  while (remaining) {
+    const int leader = __ffs(remaining) - 1;
+    const int lcell = __shfl_sync(0xFFFFFFFFu, cell, leader);
+    const bool mine = (cell == lcell);
+    const double sum = warp_sum(mine ? contrib : 0.0);
+    if (lane == leader) atomicAdd(&d.dT_e[lcell], sum);
+    remaining &= ~__ballot_sync(0xFFFFFFFFu, mine);
+  }
+  // energy transferred this step (E_local of fix_eph.cpp:357-404)
+  dE = warp_sum(dE);
+  if (lane == 0) s_part[threadIdx.x >> 5] = dE;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0 && t != 0.0) atomicAdd(d.E_sum, t);
+  }
+}
+
+// FixEPH::initial_integrate / final_integrate (fix_eph.cpp:305-348)
+__global__ void integrate_kernel(int nlocal, double *__restrict__ x, double *__restrict__ v,
+                                 const double *__restrict__ f, const int *__restrict__ type,
+                                 const int *__restrict__ mask, const double *__restrict__ mass, int groupbit,
+                                 double dtv, double dtf, int drift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  if (!(mask[i] & groupbit)) return;
+  const double dtfm = dtf / mass[type[i]];
+  const size_t o = 3 * (size_t)i;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double vv = v[o + d] + dtfm * f[o + d];
+    v[o + d] = vv;
+    if (drift) x[o + d] += dtv * vv;
+  }
+}
+
+// FixEPH::pack_forward_comm / unpack_forward_comm (fix_eph.cpp:951-1009) on
+// device-resident arrays; width 1 (rho) or 3 (xi, w).
+__global__ void pack_forward_kernel(int n, const int *__restrict__ list, const double *__restrict__ src, int width,
+                                    int stride, double *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  int k = t / width, c = t - k * width;
+  buf[t] = src[(size_t)list[k] * stride + c];
+}
+__global__ void unpack_forward_kernel(int n, int first, double *__restrict__ dst, int width, int stride,
+                                      const double *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  int k = t / width, c = t - k * width;
+  dst[(size_t)(first + k) * stride + c] = buf[t];
+}
+
+}  // namespace ephb

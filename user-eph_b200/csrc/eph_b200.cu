@@ -1,0 +1,834 @@
+// C ABI of the B200-native `fix eph` hot path (see include/eph_b200.h).
+// Host-side handle, buffer management and kernel orchestration.  There is no
+// CPU fallback: every entry point either enqueues CUDA work or fails.
+#include "eph_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "eph_atoms.cuh"
+#include "eph_device.cuh"
+#include "eph_grid.cuh"
+#include "eph_sweeps.cuh"
+
+using namespace ephb;
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct eph_b200_handle {
+  eph_b200_config cfg{};
+  std::vector<int> type_map;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  std::string err;
+  long long launches = 0;
+
+  // tables
+  int n_el = 0, n_rho = 0, n_beta = 0;
+  double inv_dr_sq = 0, inv_drho = 0, rc2 = 0, rho_cut = 0;
+  DevBuf<double2> rho_tab, alpha_tab, beta_tab;
+  DevBuf<int> d_type_map;
+  bool tables_set = false;
+
+  // time step
+  double dt = 0, boltz = 0, eta = 0;
+  bool dt_set = false;
+
+  // atoms (LAMMPS order)
+  int nlocal = 0, nghost = 0;
+  bool atoms_set = false;
+  DevBuf<int> type, mask, owner;
+  DevBuf<long long> tag;
+  bool has_owner = false;
+  DevBuf<double> x, v, f, xi_in;  // staging for host memspace
+  DevBuf<double> mass;
+
+  // internal per-atom records
+  DevBuf<double4> pos4, v4, z4, u4;
+  DevBuf<double> rho, s, w, xi, f_eph, f_rng, array8;
+  bool forces_valid = false;
+
+  // neighbours
+  DevBuf<long long> off;
+  DevBuf<int> neigh, cneigh, ccount;
+  long long n_entries = 0;
+  bool neigh_set = false;
+  const long long *off_ptr = nullptr;  // device pointers actually used (own or caller's)
+  const int *neigh_ptr = nullptr;
+
+  // grid
+  int nx = 0, ny = 0, nz = 0, steps = 1;
+  long long ncell = 0;
+  double box[6] = {0, 1, 0, 1, 0, 1};
+  double gdx = 1, gdy = 1, gdz = 1, dV = 1;
+  DevBuf<double> T[2], dT_e, S_e, rho_e, C_e, kappa_e;
+  int cur = 0;
+  DevBuf<short> flag;
+  DevBuf<unsigned short> t_dyn;
+  bool grid_set = false, has_tdyn = false, minmax_valid = false;
+  double c_min = 0, rho_min = 0, kappa_max = 0;
+  int n_T = 0;
+  double dT_tab = 0;
+  DevBuf<double2> C_T_tab, K_T_tab;
+  DevBuf<double> E_T_tab;
+  int last_substeps = 0;
+
+  // scalars
+  DevBuf<double> d_scal;              // [0] E_local, [1] T sum
+  DevBuf<unsigned long long> d_mm;    // min/max bits
+  DevBuf<unsigned> d_status;
+  double *h_pinned = nullptr;         // 8 doubles
+};
+
+namespace {
+
+int fail(eph_b200_handle *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define EPH_CUDA(h, call)                                                                                \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(h, EPH_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define EPH_LAUNCH_CHECK(h)                                                                              \
+  do {                                                                                                   \
+    ++(h)->launches;                                                                                     \
+    cudaError_t e_ = cudaGetLastError();                                                                 \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(h, EPH_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+GridGeom grid_geom(const eph_b200_handle *h) {
+  GridGeom g;
+  g.nx = h->nx; g.ny = h->ny; g.nz = h->nz;
+  g.x0 = h->box[0]; g.y0 = h->box[2]; g.z0 = h->box[4];
+  g.dx = h->gdx; g.dy = h->gdy; g.dz = h->gdz;
+  return g;
+}
+
+// copy-or-alias: host memspace stages into `buf`, device memspace uses the caller's pointer
+template <class T>
+int stage_in(eph_b200_handle *h, DevBuf<T> &buf, const T *src, size_t n, int memspace, const T **out) {
+  if (memspace == EPH_B200_DEVICE) {
+    *out = src;
+    return EPH_B200_OK;
+  }
+  EPH_CUDA(h, buf.reserve(n));
+  EPH_CUDA(h, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *out = buf.p;
+  return EPH_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eph_b200_version(void) { return EPH_B200_VERSION; }
+const char *eph_b200_create_error(void) { return g_create_error.c_str(); }
+const char *eph_b200_last_error(const eph_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+long long eph_b200_launch_count(const eph_b200_handle *h) { return h ? h->launches : 0; }
+
+int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
+  if (!cfg || !out) { g_create_error = "eph_b200_create: null argument"; return EPH_B200_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->ntypes < 1 || !cfg->type_map) { g_create_error = "eph_b200_create: ntypes < 1 or no type_map"; return EPH_B200_ERR_ARG; }
+  if (cfg->model != EPH_B200_MODEL_PRL && cfg->model != EPH_B200_MODEL_NONE) {
+    g_create_error = "eph_b200_create: only eph_model 4 (PRL 120, 185501) and 0 run on the device";
+    return EPH_B200_ERR_MODEL;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1) {
+    g_create_error = std::string("eph_b200_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return EPH_B200_ERR_NODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "eph_b200_create: bad device ordinal"; return EPH_B200_ERR_ARG; }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) {
+    g_create_error = std::string("eph_b200_create: ") + cudaGetErrorString(e);
+    return EPH_B200_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "eph_b200_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return EPH_B200_ERR_NODEVICE;
+  }
+  auto *h = new eph_b200_handle;
+  h->cfg = *cfg;
+  h->type_map.assign(cfg->type_map, cfg->type_map + cfg->ntypes);
+  h->cfg.type_map = h->type_map.data();
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (cfg->stream) h->stream = static_cast<cudaStream_t>(cfg->stream);
+  else {
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      g_create_error = std::string("eph_b200_create: ") + cudaGetErrorString(e);
+      delete h;
+      return EPH_B200_ERR_CUDA;
+    }
+    h->own_stream = true;
+  }
+  bool ok = h->d_type_map.reserve(cfg->ntypes) == cudaSuccess && h->d_scal.reserve(8) == cudaSuccess &&
+            h->d_mm.reserve(4) == cudaSuccess && h->d_status.reserve(1) == cudaSuccess &&
+            cudaMallocHost(&h->h_pinned, 8 * sizeof(double)) == cudaSuccess &&
+            cudaMemcpy(h->d_type_map.p, h->type_map.data(), cfg->ntypes * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemset(h->d_status.p, 0, sizeof(unsigned)) == cudaSuccess &&
+            cudaMemset(h->d_scal.p, 0, 8 * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("eph_b200_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    eph_b200_destroy(h);
+    return EPH_B200_ERR_CUDA;
+  }
+  *out = h;
+  return EPH_B200_OK;
+}
+
+int eph_b200_destroy(eph_b200_handle *h) {
+  if (!h) return EPH_B200_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
+  h->type.release(); h->mask.release(); h->owner.release(); h->tag.release();
+  h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release();
+  h->pos4.release(); h->v4.release(); h->z4.release(); h->u4.release();
+  h->rho.release(); h->s.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
+  h->off.release(); h->neigh.release(); h->cneigh.release(); h->ccount.release();
+  h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
+  h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
+  h->d_scal.release(); h->d_mm.release(); h->d_status.release();
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EPH_B200_OK;
+}
+
+int eph_b200_synchronize(eph_b200_handle *h) {
+  if (!h) return EPH_B200_ERR_ARG;
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+int eph_b200_status_word(eph_b200_handle *h, unsigned *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  EPH_CUDA(h, cudaMemcpyAsync(out, h->d_status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_tables(eph_b200_handle *h, int n_elements, int n_rho, double inv_dr_sq, const double *coeff_rho_r_sq,
+                        int n_beta, double inv_drho, const double *coeff_alpha, const double *coeff_beta,
+                        double r_cutoff_sq, double rho_cutoff) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (n_elements < 1 || n_elements > 255 || n_rho < 4 || n_beta < 4 || !coeff_rho_r_sq || !coeff_alpha || !coeff_beta)
+    return fail(h, EPH_B200_ERR_ARG, "set_tables: bad table sizes or null coefficients");
+  for (int t = 0; t < h->cfg.ntypes; ++t)
+    if (h->type_map[t] < 0 || h->type_map[t] >= n_elements)
+      return fail(h, EPH_B200_ERR_ARG, "set_tables: type %d maps to element %d, table has %d", t + 1, h->type_map[t], n_elements);
+  cudaSetDevice(h->cfg.device);
+  size_t nr = (size_t)n_elements * n_rho * 2, nb = (size_t)n_elements * n_beta * 2;
+  EPH_CUDA(h, h->rho_tab.reserve(nr));
+  EPH_CUDA(h, h->alpha_tab.reserve(nb));
+  EPH_CUDA(h, h->beta_tab.reserve(nb));
+  EPH_CUDA(h, cudaMemcpyAsync(h->rho_tab.p, coeff_rho_r_sq, nr * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->alpha_tab.p, coeff_alpha, nb * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->beta_tab.p, coeff_beta, nb * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_el = n_elements; h->n_rho = n_rho; h->n_beta = n_beta;
+  h->inv_dr_sq = inv_dr_sq; h->inv_drho = inv_drho; h->rc2 = r_cutoff_sq; h->rho_cut = rho_cutoff;
+  h->tables_set = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_grid(eph_b200_handle *h, int nx, int ny, int nz, const double *box, int steps, const double *T_e,
+                      const double *S_e, const double *rho_e, const double *C_e, const double *kappa_e,
+                      const int16_t *flag, const uint16_t *t_dyn) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (nx < 1 || ny < 1 || nz < 1) return fail(h, EPH_B200_ERR_ARG, "FixEPH: non-positive grid values");
+  if (!box || !T_e || !rho_e || !C_e || !kappa_e) return fail(h, EPH_B200_ERR_ARG, "set_grid: null field");
+  if (!(box[0] < box[1] && box[2] < box[3] && box[4] < box[5])) return fail(h, EPH_B200_ERR_ARG, "set_grid: empty box");
+  cudaSetDevice(h->cfg.device);
+  long long n = (long long)nx * ny * nz;
+  h->nx = nx; h->ny = ny; h->nz = nz; h->ncell = n; h->steps = steps > 0 ? steps : 1;
+  std::memcpy(h->box, box, sizeof h->box);
+  h->gdx = (box[1] - box[0]) / nx;  // eph_fdm.h:135-139
+  h->gdy = (box[3] - box[2]) / ny;
+  h->gdz = (box[5] - box[4]) / nz;
+  h->dV = h->gdx * h->gdy * h->gdz;
+  EPH_CUDA(h, h->T[0].reserve(n)); EPH_CUDA(h, h->T[1].reserve(n)); EPH_CUDA(h, h->dT_e.reserve(n));
+  EPH_CUDA(h, h->S_e.reserve(n)); EPH_CUDA(h, h->rho_e.reserve(n)); EPH_CUDA(h, h->C_e.reserve(n));
+  EPH_CUDA(h, h->kappa_e.reserve(n)); EPH_CUDA(h, h->flag.reserve(n)); EPH_CUDA(h, h->t_dyn.reserve(n));
+  h->cur = 0;
+  const size_t bytes = n * sizeof(double);
+  EPH_CUDA(h, cudaMemcpyAsync(h->T[0].p, T_e, bytes, cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->dT_e.p, 0, bytes, h->stream));
+  if (S_e) EPH_CUDA(h, cudaMemcpyAsync(h->S_e.p, S_e, bytes, cudaMemcpyHostToDevice, h->stream));
+  else EPH_CUDA(h, cudaMemsetAsync(h->S_e.p, 0, bytes, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->rho_e.p, rho_e, bytes, cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->C_e.p, C_e, bytes, cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->kappa_e.p, kappa_e, bytes, cudaMemcpyHostToDevice, h->stream));
+  std::vector<short> fl(n, 1);
+  std::vector<unsigned short> td(n, 0);
+  if (flag) std::copy(flag, flag + n, fl.begin());
+  h->has_tdyn = false;
+  if (t_dyn) {
+    std::copy(t_dyn, t_dyn + n, td.begin());
+    for (long long i = 0; i < n; ++i) if (td[i]) { h->has_tdyn = true; break; }
+  }
+  EPH_CUDA(h, cudaMemcpyAsync(h->flag.p, fl.data(), n * sizeof(short), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->t_dyn.p, td.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->grid_set = true;
+  h->minmax_valid = false;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_grid_tables(eph_b200_handle *h, int n_T, double dT, const double *coeff_C_e_T,
+                             const double *coeff_kappa_e_T, const double *E_e_T) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (n_T < 4 || !(dT > 0) || !coeff_C_e_T || !coeff_kappa_e_T || !E_e_T) return fail(h, EPH_B200_ERR_ARG, "set_grid_tables: bad table");
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, h->C_T_tab.reserve(2 * (size_t)n_T)); EPH_CUDA(h, h->K_T_tab.reserve(2 * (size_t)n_T)); EPH_CUDA(h, h->E_T_tab.reserve(n_T));
+  EPH_CUDA(h, cudaMemcpyAsync(h->C_T_tab.p, coeff_C_e_T, 4 * (size_t)n_T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->K_T_tab.p, coeff_kappa_e_T, 4 * (size_t)n_T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->E_T_tab.p, E_e_T, (size_t)n_T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_T = n_T; h->dT_tab = dT;
+  return EPH_B200_OK;
+}
+
+static double *grid_field(eph_b200_handle *h, int which) {
+  switch (which) {
+    case 0: return h->T[h->cur].p; case 1: return h->S_e.p; case 2: return h->rho_e.p;
+    case 3: return h->C_e.p; case 4: return h->kappa_e.p; case 5: return h->dT_e.p; default: return nullptr;
+  }
+}
+
+int eph_b200_get_grid(eph_b200_handle *h, int which, double *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "get_grid: no grid");
+  double *p = grid_field(h, which);
+  if (!p) return fail(h, EPH_B200_ERR_ARG, "get_grid: bad field id %d", which);
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, cudaMemcpyAsync(out, p, h->ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+int eph_b200_put_grid(eph_b200_handle *h, int which, const double *in) {
+  if (!h || !in) return EPH_B200_ERR_ARG;
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "put_grid: no grid");
+  double *p = grid_field(h, which);
+  if (!p) return fail(h, EPH_B200_ERR_ARG, "put_grid: bad field id %d", which);
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, cudaMemcpyAsync(p, in, h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->minmax_valid = false;
+  return EPH_B200_OK;
+}
+
+int eph_b200_mean_T(eph_b200_handle *h, double *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "mean_T: no grid");
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p + 1, 0, sizeof(double), h->stream));
+  fdm_sum_kernel<<<std::min(blocks_for(h->ncell, 256), 4 * h->sm_count), 256, 0, h->stream>>>(h->ncell, h->T[h->cur].p, h->d_scal.p + 1);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned + 1, h->d_scal.p + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out = h->h_pinned[1] / (double)h->ncell;
+  return EPH_B200_OK;
+}
+
+int eph_b200_last_substeps(eph_b200_handle *h, int *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  *out = h->last_substeps;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!(dt > 0) || !(boltz > 0)) return fail(h, EPH_B200_ERR_ARG, "set_dt: dt and boltz must be positive");
+  h->dt = dt; h->boltz = boltz;
+  h->eta = std::sqrt(2.0 * boltz / dt);  // eta_factor, fix_eph.cpp:200, :910
+  h->dt_set = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *type, const int *mask,
+                       const int64_t *tag, const int *ghost_owner, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (nlocal < 0 || nghost < 0 || !type || !mask) return fail(h, EPH_B200_ERR_ARG, "set_atoms: bad counts or null arrays");
+  cudaSetDevice(h->cfg.device);
+  const size_t nt = (size_t)nlocal + nghost;
+  const cudaMemcpyKind kind = memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  EPH_CUDA(h, h->type.reserve(nt)); EPH_CUDA(h, h->mask.reserve(nt)); EPH_CUDA(h, h->tag.reserve(nt));
+  EPH_CUDA(h, cudaMemcpyAsync(h->type.p, type, nt * sizeof(int), kind, h->stream));
+  EPH_CUDA(h, cudaMemcpyAsync(h->mask.p, mask, nt * sizeof(int), kind, h->stream));
+  if (tag) EPH_CUDA(h, cudaMemcpyAsync(h->tag.p, tag, nt * sizeof(long long), kind, h->stream));
+  else if (h->cfg.flags & EPH_B200_RANDOM) {
+    // without tags the counter-based stream cannot be keyed; injected xi still works
+    EPH_CUDA(h, cudaMemsetAsync(h->tag.p, 0, nt * sizeof(long long), h->stream));
+  }
+  h->has_owner = false;
+  if (nghost > 0 && ghost_owner) {
+    EPH_CUDA(h, h->owner.reserve(nghost));
+    EPH_CUDA(h, cudaMemcpyAsync(h->owner.p, ghost_owner, (size_t)nghost * sizeof(int), kind, h->stream));
+    h->has_owner = true;
+  }
+  EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->v4.reserve(nt)); EPH_CUDA(h, h->z4.reserve(nt)); EPH_CUDA(h, h->u4.reserve(nt));
+  EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->s.reserve(nt));
+  const size_t nl = std::max<size_t>(nlocal, 1);
+  EPH_CUDA(h, h->w.reserve(3 * nl)); EPH_CUDA(h, h->xi.reserve(3 * nl)); EPH_CUDA(h, h->f_eph.reserve(3 * nl));
+  EPH_CUDA(h, h->f_rng.reserve(3 * nl)); EPH_CUDA(h, h->array8.reserve(8 * nl)); EPH_CUDA(h, h->ccount.reserve(nl));
+  // fresh storage is zero, like the reference constructor (fix_eph.cpp:229-238)
+  EPH_CUDA(h, cudaMemsetAsync(h->rho.p, 0, nt * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->u4.p, 0, nt * sizeof(double4), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->z4.p, 0, nt * sizeof(double4), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->w.p, 0, 3 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->xi.p, 0, 3 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->f_eph.p, 0, 3 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->f_rng.p, 0, 3 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->array8.p, 0, 8 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));  // host source buffers may be reused by the caller
+  h->nlocal = nlocal; h->nghost = nghost;
+  h->atoms_set = true;
+  h->neigh_set = false;
+  h->forces_valid = false;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *offsets, const int *neigh, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: call set_atoms first");
+  if (nlocal != h->nlocal) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: nlocal %d differs from set_atoms (%d)", nlocal, h->nlocal);
+  if (!offsets || (!neigh && nlocal > 0)) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: null list");
+  cudaSetDevice(h->cfg.device);
+  long long total = 0;
+  if (memspace == EPH_B200_DEVICE) {
+    EPH_CUDA(h, cudaMemcpyAsync(&total, offsets + nlocal, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->off_ptr = reinterpret_cast<const long long *>(offsets);
+    h->neigh_ptr = neigh;
+  } else {
+    total = offsets[nlocal];
+    EPH_CUDA(h, h->off.reserve((size_t)nlocal + 1));
+    EPH_CUDA(h, h->neigh.reserve((size_t)std::max<long long>(total, 1)));
+    EPH_CUDA(h, cudaMemcpyAsync(h->off.p, offsets, ((size_t)nlocal + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->neigh.p, neigh, (size_t)total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->off_ptr = h->off.p;
+    h->neigh_ptr = h->neigh.p;
+  }
+  if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
+  EPH_CUDA(h, h->cneigh.reserve((size_t)std::max<long long>(total, 1)));
+  h->n_entries = total;
+  h->neigh_set = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *numneigh, int *const *firstneigh) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!numneigh || (!firstneigh && nlocal > 0)) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: null list");
+  // LAMMPS keeps the list in paged host memory (int **firstneigh); flatten once per
+  // re-neighbouring -- never per step (the legacy port's fix_eph_gpu.cpp:241-271 did).
+  std::vector<long long> off((size_t)nlocal + 1, 0);
+  for (int i = 0; i < nlocal; ++i) off[i + 1] = off[i] + numneigh[i];
+  std::vector<int> flat((size_t)std::max<long long>(off[nlocal], 1));
+  for (int i = 0; i < nlocal; ++i) std::memcpy(flat.data() + off[i], firstneigh[i], sizeof(int) * (size_t)numneigh[i]);
+  return eph_b200_set_neighbors_csr(h, nlocal, reinterpret_cast<const int64_t *>(off.data()), flat.data(), EPH_B200_HOST);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// sweep launch helpers
+// ---------------------------------------------------------------------------
+namespace {
+
+template <class K>
+int resident_grid(eph_b200_handle *h, K kernel, int threads, size_t smem) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return h->sm_count * per_sm;  // persistent CTAs: exactly one resident wave
+}
+
+template <int LANES, bool SMEM, bool MULTI>
+int launch_sweeps(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem) {
+  const int threads = 256;
+  if (which == 0) {
+    auto k = rho_sweep_kernel<LANES, SMEM>;
+    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
+  } else if (which == 1) {
+    auto k = w_rng_sweep_kernel<LANES, SMEM, MULTI>;
+    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
+  } else {
+    auto k = friction_sweep_kernel<LANES, SMEM, MULTI>;
+    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
+  }
+  EPH_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+
+int env_lanes(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  if (!e) return dflt;
+  int v = std::atoi(e);
+  return (v == 8 || v == 16 || v == 32) ? v : dflt;
+}
+
+template <bool SMEM, bool MULTI>
+int launch_sweep_lanes(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, int lanes) {
+  switch (lanes) {
+    case 8: return launch_sweeps<8, SMEM, MULTI>(h, a, which, smem);
+    case 16: return launch_sweeps<16, SMEM, MULTI>(h, a, which, smem);
+    default: return launch_sweeps<32, SMEM, MULTI>(h, a, which, smem);
+  }
+}
+
+int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which) {
+  // the rho(r^2) tables of all elements live in shared memory when they fit
+  const size_t table_bytes = (size_t)a.n_elements * a.n_rho * 2 * sizeof(double2);
+  const bool smem = table_bytes <= (size_t)h->max_smem_optin - 1024;
+  const bool multi = a.n_elements > 1;
+  static const int lanes_rho = env_lanes("EPH_B200_LANES_RHO", 32);
+  static const int lanes_pair = env_lanes("EPH_B200_LANES_PAIR", 16);
+  const int lanes = which == 0 ? lanes_rho : lanes_pair;
+  if (smem) {
+    if (multi) return launch_sweep_lanes<true, true>(h, a, which, table_bytes, lanes);
+    return launch_sweep_lanes<true, false>(h, a, which, table_bytes, lanes);
+  }
+  if (multi) return launch_sweep_lanes<false, true>(h, a, which, 0, lanes);
+  return launch_sweep_lanes<false, false>(h, a, which, 0, lanes);
+}
+
+SweepArgs sweep_args(eph_b200_handle *h) {
+  SweepArgs a{};
+  a.nlocal = h->nlocal; a.n_elements = h->n_el; a.n_rho = h->n_rho;
+  a.inv_dr_sq = h->inv_dr_sq; a.r_cutoff_sq = h->rc2; a.rho_tab = h->rho_tab.p;
+  a.offsets = h->off_ptr; a.neigh = h->neigh_ptr; a.cneigh = h->cneigh.p; a.ccount = h->ccount.p;
+  a.pos4 = h->pos4.p; a.v4 = h->v4.p; a.z4 = h->z4.p; a.u4 = h->u4.p; a.s = h->s.p; a.rho = h->rho.p;
+  a.w = h->w.p; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
+  a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
+  a.grid = grid_geom(h);
+  a.eta_factor = h->eta;
+  a.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
+  a.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
+                        long long ntimestep, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->tables_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_tables not called");
+  if (!h->dt_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_dt not called");
+  if (!h->atoms_set || !h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_atoms / set_neighbors not called");
+  if ((h->cfg.flags & EPH_B200_RANDOM) && !h->grid_set) return fail(h, EPH_B200_ERR_ARG, "post_force: random force needs the T_e grid");
+  if (!x || !v || (!f && h->nlocal > 0)) return fail(h, EPH_B200_ERR_ARG, "post_force: null x, v or f");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal, nt = h->nlocal + h->nghost;
+  if (nl == 0) return EPH_B200_OK;
+  const double *dx = nullptr, *dv = nullptr, *dxi = nullptr;
+  double *df = nullptr;
+  int rc;
+  if ((rc = stage_in(h, h->x, x, 3 * (size_t)nt, memspace, &dx))) return rc;
+  if ((rc = stage_in(h, h->v, v, 3 * (size_t)nt, memspace, &dv))) return rc;
+  const bool add_fric = (h->cfg.flags & EPH_B200_FRICTION) && !(h->cfg.flags & EPH_B200_NOFRICTION);
+  const bool add_rand = (h->cfg.flags & EPH_B200_RANDOM) && !(h->cfg.flags & EPH_B200_NORANDOM);
+  if (memspace == EPH_B200_DEVICE) df = f;
+  else {
+    EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
+    if (add_fric || add_rand) EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    df = h->f.p;
+  }
+  if (xi_inject && (h->cfg.flags & EPH_B200_RANDOM)) {
+    if ((rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &dxi))) return rc;
+  }
+
+  pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
+                                                                 h->cfg.groupbit, h->pos4.p, h->v4.p);
+  EPH_LAUNCH_CHECK(h);
+
+  SweepArgs a = sweep_args(h);
+  if ((rc = launch_sweep(h, a, 0))) return rc;
+
+  PrepArgs p{};
+  p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
+  p.xi_inject = dxi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
+  p.seed = h->cfg.seed; p.step = (unsigned long long)ntimestep; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
+  p.rho = h->rho.p; p.s = h->s.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.xi = h->xi.p; p.status = h->d_status.p;
+  prep_coupling_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(p);
+  EPH_LAUNCH_CHECK(h);
+
+  if (h->cfg.model == EPH_B200_MODEL_PRL) {
+    if ((rc = launch_sweep(h, a, 1))) return rc;
+    if (a.do_friction) {
+      if (h->nghost > 0 && h->has_owner) {
+        ghost_fill4_kernel<<<blocks_for(h->nghost, 256), 256, 0, h->stream>>>(nl, h->nghost, h->owner.p, h->u4.p);
+        EPH_LAUNCH_CHECK(h);
+      }
+      if ((rc = launch_sweep(h, a, 2))) return rc;
+    }
+  }
+  if (add_fric || add_rand) {
+    add_forces_kernel<<<blocks_for(3LL * nl, 256), 256, 0, h->stream>>>(3 * nl, df, h->f_eph.p, h->f_rng.p, add_fric, add_rand);
+    EPH_LAUNCH_CHECK(h);
+    if (memspace != EPH_B200_DEVICE) {
+      EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+  }
+  h->forces_valid = true;
+  return EPH_B200_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// EPH_FDM::solve (eph_fdm.h:267-400).  The sub-step count is decided on the
+// host with the reference's exact double arithmetic and truncating cast from
+// three device-reduced scalars; they are cached while the parameters are constant.
+int grid_solve(eph_b200_handle *h) {
+  const long long n = h->ncell;
+  if (h->has_tdyn) {
+    if (h->n_T < 4) return fail(h, EPH_B200_ERR_ARG, "solve: grid has temperature-dependent cells but no parameter tables");
+    fdm_refresh_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, h->T[h->cur].p, h->t_dyn.p, h->C_T_tab.p, h->K_T_tab.p,
+                                                                   1. / h->dT_tab, h->C_e.p, h->kappa_e.p);
+    EPH_LAUNCH_CHECK(h);
+    h->minmax_valid = false;
+  }
+  if (!h->minmax_valid) {
+    // seed with cell 0 (eph_fdm.h:290-292)
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 0, h->C_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 1, h->rho_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 2, h->kappa_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    fdm_minmax_kernel<<<std::min(blocks_for(n, 256), 4 * h->sm_count), 256, 0, h->stream>>>(
+        n, h->C_e.p, h->rho_e.p, h->kappa_e.p, h->flag.p, h->d_mm.p);
+    EPH_LAUNCH_CHECK(h);
+    EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned + 2, h->d_mm.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->c_min = h->h_pinned[2]; h->rho_min = h->h_pinned[3]; h->kappa_max = h->h_pinned[4];
+    h->minmax_valid = true;
+  }
+  const double dx = h->gdx, dy = h->gdy, dz = h->gdz, dt = h->dt;
+  double inner_dt = dt / h->steps;
+  const double dtdxdydz = inner_dt * (1.0 / dx / dx + 1.0 / dy / dy + 1.0 / dz / dz);
+  const double r = dtdxdydz / h->c_min / h->rho_min * h->kappa_max;
+  unsigned int new_steps = (unsigned int)h->steps;
+  if (r > 0.4) {  // eph_fdm.h:308-313, truncating cast kept
+    inner_dt = 0.4 * inner_dt / r;
+    new_steps = std::max(static_cast<unsigned int>(dt / inner_dt), 1u);
+    inner_dt = dt / new_steps;
+  }
+  h->last_substeps = (int)new_steps;
+
+  GridArgs g{};
+  g.nx = h->nx; g.ny = h->ny; g.nz = h->nz; g.ncell = n;
+  g.dT_e = h->dT_e.p; g.S_e = h->S_e.p; g.rho_e = h->rho_e.p; g.C_e = h->C_e.p; g.kappa_e = h->kappa_e.p;
+  g.flag = h->flag.p; g.t_dyn = h->t_dyn.p;
+  g.E_e_T = h->has_tdyn ? h->E_T_tab.p : nullptr; g.n_T = h->n_T; g.dT = h->dT_tab;
+  g.inv_dx2 = 1.0 / (dx * dx); g.inv_dy2 = 1.0 / (dy * dy); g.inv_dz2 = 1.0 / (dz * dz);
+  g.inner_dt = inner_dt; g.status = h->d_status.p;
+  dim3 block(32, 4, 2);
+  dim3 grid((h->nx + block.x - 1) / block.x, (h->ny + block.y - 1) / block.y, (h->nz + block.z - 1) / block.z);
+  for (unsigned int s = 0; s < new_steps; ++s) {
+    g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
+    g.clear_source = (s + 1 == new_steps) ? 1 : 0;
+    fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+    EPH_LAUNCH_CHECK(h);
+    h->cur = 1 - h->cur;
+  }
+  return EPH_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->forces_valid) return fail(h, EPH_B200_ERR_ARG, "end_of_step: post_force has not run");
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "end_of_step: set_grid not called");
+  if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "end_of_step: null x or v");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  const double *dx = nullptr, *dv = nullptr;
+  int rc;
+  // only the local part is read here
+  if ((rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
+  if ((rc = stage_in(h, h->v, v, 3 * (size_t)nl, memspace, &dv))) return rc;
+  EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
+  if (nl > 0) {
+    DepositArgs d{};
+    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p; d.rho = h->rho.p;
+    d.beta_tab = h->beta_tab.p; d.n_beta = h->n_beta; d.inv_drho = h->inv_drho; d.rho_cutoff = h->rho_cut;
+    d.dt = h->dt; d.dVdt = h->dV * h->dt;
+    d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
+    d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
+    d.grid = grid_geom(h); d.dT_e = h->dT_e.p; d.E_sum = h->d_scal.p; d.array8 = h->array8.p;
+    deposit_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(d);
+    EPH_LAUNCH_CHECK(h);
+  }
+  if (h->cfg.flags & EPH_B200_FDM) {
+    if ((rc = grid_solve(h))) return rc;
+  }
+  if (E_local) {
+    EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    *E_local = h->h_pinned[0];
+  }
+  return EPH_B200_OK;
+}
+
+int eph_b200_initial_integrate(eph_b200_handle *h, double *x, double *v, const double *f, const double *mass_by_type,
+                               double dtv, double dtf, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->cfg.flags & EPH_B200_NOINT) return EPH_B200_OK;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "initial_integrate: set_atoms not called");
+  if (!x || !v || !f || !mass_by_type) return fail(h, EPH_B200_ERR_ARG, "initial_integrate: null argument");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
+  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  double *dx = x, *dv = v;
+  const double *df = f;
+  if (memspace != EPH_B200_DEVICE) {
+    EPH_CUDA(h, h->x.reserve(3 * (size_t)nl)); EPH_CUDA(h, h->v.reserve(3 * (size_t)nl)); EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
+    EPH_CUDA(h, cudaMemcpyAsync(h->x.p, x, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->v.p, v, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dx = h->x.p; dv = h->v.p; df = h->f.p;
+  }
+  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, dx, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
+  EPH_LAUNCH_CHECK(h);
+  if (memspace != EPH_B200_DEVICE) {
+    EPH_CUDA(h, cudaMemcpyAsync(x, h->x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(v, h->v.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+int eph_b200_final_integrate(eph_b200_handle *h, double *v, const double *f, const double *mass_by_type, double dtf,
+                             int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->cfg.flags & EPH_B200_NOINT) return EPH_B200_OK;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "final_integrate: set_atoms not called");
+  if (!v || !f || !mass_by_type) return fail(h, EPH_B200_ERR_ARG, "final_integrate: null argument");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
+  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  double *dv = v;
+  const double *df = f;
+  if (memspace != EPH_B200_DEVICE) {
+    EPH_CUDA(h, h->v.reserve(3 * (size_t)nl)); EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
+    EPH_CUDA(h, cudaMemcpyAsync(h->v.p, v, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dv = h->v.p; df = h->f.p;
+  }
+  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, nullptr, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, 0.0, dtf, 0);
+  EPH_LAUNCH_CHECK(h);
+  if (memspace != EPH_B200_DEVICE) {
+    EPH_CUDA(h, cudaMemcpyAsync(v, h->v.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+int eph_b200_get_peratom(eph_b200_handle *h, double *array8, int memspace) {
+  if (!h || !array8) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "get_peratom: set_atoms not called");
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, cudaMemcpyAsync(array8, h->array8.p, 8 * (size_t)h->nlocal * sizeof(double),
+                              memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+int eph_b200_get_probe(eph_b200_handle *h, int which, double *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "get_probe: set_atoms not called");
+  cudaSetDevice(h->cfg.device);
+  const size_t nl = h->nlocal, nt = nl + h->nghost;
+  const double *src = nullptr;
+  size_t n = 0;
+  switch (which) {
+    case 0: src = h->rho.p; n = nt; break;
+    case 1: src = h->w.p; n = 3 * nl; break;
+    case 2: src = h->xi.p; n = 3 * nl; break;
+    case 3: src = h->f_eph.p; n = 3 * nl; break;
+    case 4: src = h->f_rng.p; n = 3 * nl; break;
+    default: return fail(h, EPH_B200_ERR_ARG, "get_probe: bad id %d", which);
+  }
+  EPH_CUDA(h, cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list, double *buf) {
+  (void)list; (void)buf; (void)n;
+  if (!h) return EPH_B200_ERR_ARG;
+  return fail(h, EPH_B200_ERR_ARG, "pack_forward(state %d): host transport not wired yet", state);
+}
+
+int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf) {
+  (void)first; (void)buf; (void)n;
+  if (!h) return EPH_B200_ERR_ARG;
+  return fail(h, EPH_B200_ERR_ARG, "unpack_forward(state %d): host transport not wired yet", state);
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+"""ctypes binding of the C ABI in include/eph_b200.h (libeph_b200.so).
+
+Array arguments may be numpy arrays (host memspace) or torch CUDA tensors
+(device memspace); the two must not be mixed inside one call.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._paths import lib_path
+
+HOST, DEVICE = 0, 1
+FRICTION, RANDOM, FDM, NOINT, NOFRICTION, NORANDOM = 1, 2, 4, 8, 16, 32
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_i64_p = C.POINTER(C.c_int64)
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("ntypes", C.c_int), ("type_map", c_int_p), ("groupbit", C.c_int),
+                ("flags", C.c_int), ("model", C.c_int), ("seed", C.c_ulonglong), ("rank", C.c_int),
+                ("nranks", C.c_int), ("stream", C.c_void_p)]
+
+
+# every symbol include/eph_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "eph_b200_version": (C.c_int, []),
+    "eph_b200_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "eph_b200_destroy": (C.c_int, [C.c_void_p]),
+    "eph_b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "eph_b200_create_error": (C.c_char_p, []),
+    "eph_b200_set_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_double,
+                                      C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_set_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eph_b200_set_grid_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eph_b200_get_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "eph_b200_put_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "eph_b200_mean_T": (C.c_int, [C.c_void_p, c_double_p]),
+    "eph_b200_last_substeps": (C.c_int, [C.c_void_p, c_int_p]),
+    "eph_b200_set_dt": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_set_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_set_neighbors_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_set_neighbors_lammps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
+    "eph_b200_end_of_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),
+    "eph_b200_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_double, C.c_int]),
+    "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
+    "eph_b200_get_peratom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "eph_b200_pack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_unpack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "eph_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "eph_b200_launch_count": (C.c_longlong, [C.c_void_p]),
+    "eph_b200_status_word": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libeph_b200.so and declare every prototype.  Raises if the library is missing: no fallback."""
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(lib_path("engine"), mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class EphError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    """(address, memspace) of a numpy array or torch tensor; None -> (None, HOST)."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data, HOST
+    # torch tensor
+    if not a.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
+
+
+def _space(*arrs):
+    spaces = {s for _, s in arrs if s is not None}
+    if len(spaces) > 1:
+        raise ValueError("cannot mix host and device arrays in one call")
+    return spaces.pop() if spaces else HOST
+
+
+class Engine:
+    """One eph_b200_handle: the device engine behind FixEPHB200."""
+
+    def __init__(self, type_map, flags, model=4, groupbit=1, seed=12345, device=0, rank=0, nranks=1, stream=None):
+        self.lib = load()
+        tm = np.ascontiguousarray(type_map, dtype=np.int32)
+        cfg = Config(device, len(tm), tm.ctypes.data_as(c_int_p), groupbit, flags, model, seed, rank, nranks,
+                     C.c_void_p(stream) if stream else None)
+        h = C.c_void_p()
+        rc = self.lib.eph_b200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EphError("eph_b200_create failed (%d): %s" % (rc, self.lib.eph_b200_create_error().decode()))
+        self.h = h
+        self.flags = flags
+        self.nlocal = self.nghost = 0
+        self.ncell = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EphError("eph_b200 error %d: %s" % (rc, self.lib.eph_b200_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eph_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- set-up ---------------------------------------------------------------
+    def set_tables(self, n_elements, n_rho, inv_dr_sq, rho_r_sq, n_beta, inv_drho, alpha, beta, r_cutoff_sq, rho_cutoff):
+        rho_r_sq, alpha, beta = (np.ascontiguousarray(t, dtype=np.float64) for t in (rho_r_sq, alpha, beta))
+        self._check(self.lib.eph_b200_set_tables(self.h, n_elements, n_rho, inv_dr_sq, rho_r_sq.ctypes.data, n_beta,
+                                                 inv_drho, alpha.ctypes.data, beta.ctypes.data, r_cutoff_sq, rho_cutoff))
+
+    def set_tables_from(self, tables):
+        """tables: eph_b200.host.BetaTables"""
+        self.set_tables(tables.n_elements, tables.n_rho, tables.inv_dr_sq, tables.table(1), tables.n_beta,
+                        tables.inv_drho, tables.table(2), tables.table(3), tables.r_cutoff_sq, tables.rho_cutoff)
+
+    def set_grid(self, nx, ny, nz, box, T_e, rho_e, C_e, kappa_e, S_e=None, flag=None, t_dyn=None, steps=1):
+        n = nx * ny * nz
+
+        def field(v):
+            a = np.empty(n, dtype=np.float64)
+            a[...] = v
+            return a
+
+        box = np.ascontiguousarray(box, dtype=np.float64)
+        T_e, rho_e, C_e, kappa_e = field(T_e), field(rho_e), field(C_e), field(kappa_e)
+        S_e = field(0.0 if S_e is None else S_e)
+        fl = None if flag is None else np.ascontiguousarray(flag, dtype=np.int16)
+        td = None if t_dyn is None else np.ascontiguousarray(t_dyn, dtype=np.uint16)
+        self._check(self.lib.eph_b200_set_grid(self.h, nx, ny, nz, box.ctypes.data, steps, T_e.ctypes.data, S_e.ctypes.data,
+                                               rho_e.ctypes.data, C_e.ctypes.data, kappa_e.ctypes.data,
+                                               None if fl is None else fl.ctypes.data, None if td is None else td.ctypes.data))
+        self.ncell = n
+
+    def set_grid_tables(self, dT, C_e_T, kappa_e_T, E_e_T):
+        C_e_T, kappa_e_T, E_e_T = (np.ascontiguousarray(t, dtype=np.float64) for t in (C_e_T, kappa_e_T, E_e_T))
+        self._check(self.lib.eph_b200_set_grid_tables(self.h, len(E_e_T), dT, C_e_T.ctypes.data, kappa_e_T.ctypes.data,
+                                                      E_e_T.ctypes.data))
+
+    def get_grid(self, which=0):
+        out = np.empty(self.ncell, dtype=np.float64)
+        self._check(self.lib.eph_b200_get_grid(self.h, which, out.ctypes.data))
+        return out
+
+    def put_grid(self, which, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.size == self.ncell
+        self._check(self.lib.eph_b200_put_grid(self.h, which, v.ctypes.data))
+
+    def mean_T(self):
+        out = C.c_double()
+        self._check(self.lib.eph_b200_mean_T(self.h, C.byref(out)))
+        return out.value
+
+    def last_substeps(self):
+        out = C.c_int()
+        self._check(self.lib.eph_b200_last_substeps(self.h, C.byref(out)))
+        return out.value
+
+    def set_dt(self, dt, boltz=8.617343e-5):
+        self._check(self.lib.eph_b200_set_dt(self.h, dt, boltz))
+
+    def set_atoms(self, nlocal, nghost, type, mask, tag=None, ghost_owner=None):
+        ps = [_ptr(type), _ptr(mask), _ptr(tag), _ptr(ghost_owner)]
+        sp = _space(*ps)
+        self._check(self.lib.eph_b200_set_atoms(self.h, nlocal, nghost, ps[0][0], ps[1][0], ps[2][0], ps[3][0], sp))
+        self.nlocal, self.nghost = nlocal, nghost
+
+    def set_neighbors(self, offsets, neigh):
+        ps = [_ptr(offsets), _ptr(neigh)]
+        self._check(self.lib.eph_b200_set_neighbors_csr(self.h, self.nlocal, ps[0][0], ps[1][0], _space(*ps)))
+        self._keep = (offsets, neigh)  # device memspace aliases the caller's buffers
+
+    # -- per step -------------------------------------------------------------
+    def post_force(self, x, v, f, xi=None, step=0):
+        ps = [_ptr(x), _ptr(v), _ptr(f), _ptr(xi)]
+        self._check(self.lib.eph_b200_post_force(self.h, ps[0][0], ps[1][0], ps[2][0], ps[3][0], step, _space(*ps)))
+
+    def end_of_step(self, x, v, want_energy=True):
+        ps = [_ptr(x), _ptr(v)]
+        e = C.c_double()
+        self._check(self.lib.eph_b200_end_of_step(self.h, ps[0][0], ps[1][0], C.byref(e) if want_energy else None,
+                                                  _space(*ps)))
+        return e.value if want_energy else None
+
+    def initial_integrate(self, x, v, f, mass_by_type, dtv, dtf):
+        m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
+        ps = [_ptr(x), _ptr(v), _ptr(f)]
+        self._check(self.lib.eph_b200_initial_integrate(self.h, ps[0][0], ps[1][0], ps[2][0], m.ctypes.data, dtv, dtf, _space(*ps)))
+
+    def final_integrate(self, v, f, mass_by_type, dtf):
+        m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
+        ps = [_ptr(v), _ptr(f)]
+        self._check(self.lib.eph_b200_final_integrate(self.h, ps[0][0], ps[1][0], m.ctypes.data, dtf, _space(*ps)))
+
+    def peratom(self):
+        out = np.empty((self.nlocal, 8), dtype=np.float64)
+        self._check(self.lib.eph_b200_get_peratom(self.h, out.ctypes.data, HOST))
+        return out
+
+    def probe(self, which):
+        n = self.nlocal + self.nghost if which == 0 else 3 * self.nlocal
+        out = np.empty(n, dtype=np.float64)
+        self._check(self.lib.eph_b200_get_probe(self.h, which, out.ctypes.data))
+        return out if which == 0 else out.reshape(-1, 3)
+
+    def synchronize(self):
+        self._check(self.lib.eph_b200_synchronize(self.h))
+
+    def launch_count(self):
+        return self.lib.eph_b200_launch_count(self.h)
+
+    def status_word(self):
+        out = C.c_uint()
+        self._check(self.lib.eph_b200_status_word(self.h, C.byref(out)))
+        return out.value

@@ -1,0 +1,393 @@
+// fix eph/b200: host side of the B200-native `fix eph`.  Keeps the reference's
+// command syntax, file formats, hook order, outputs and error messages
+// (reference fix_eph.cpp) and forwards the per-timestep work to libeph_b200.
+#include "fix_eph_b200.h"
+
+#include <mpi.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <string>
+
+#include "atom.h"
+#include "comm.h"
+#include "domain.h"
+#include "error.h"
+#include "force.h"
+#include "memory.h"
+#include "neigh_list.h"
+#include "neigh_request.h"
+#include "neighbor.h"
+#include "random_mars.h"
+#include "update.h"
+
+using namespace LAMMPS_NS;
+using namespace FixConst;
+
+/* arguments: identical positions to FixEPH (fix_eph.cpp:36-58)
+ *  3 seed | 4 flags | 5 model | 6 rho_e | 7 C_e | 8 kappa_e | 9 T_e | 10-12 NX NY NZ | 13 T_infile | 14 freq
+ *  15 T_out | 16 beta file | 17.. element per type | then optional keyword pairs */
+FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), dev(nullptr), random(nullptr) {
+  if (narg < 18) error->all(FLERR, "Illegal fix eph command: too few arguments");
+  if (atom->natoms < 1) error->all(FLERR, "fix_eph: error no atoms in simulation");
+  MPI_Comm_rank(world, &myID);
+  MPI_Comm_size(world, &nrPS);
+
+  state = FixState::NONE;
+
+  vector_flag = 1;
+  size_vector = 2;
+  global_freq = 1;
+  extvector = 1;
+  nevery = 1;
+  peratom_flag = 1;
+  size_peratom_cols = 8;
+  peratom_freq = 1;
+  comm_forward = 3;
+  comm->ghost_velocity = 1;
+
+  seed = atoi(arg[3]);
+  random = new RanMars(lmp, seed + myID);
+
+  eph_flag = strtol(arg[4], NULL, 0);
+  if (myID == 0) {
+    std::cout << '\n' << "Flag read: " << arg[4] << " -> " << eph_flag << '\n';
+    if (eph_flag & Flag::FRICTION) std::cout << "Friction evaluation: ON\n";
+    if (eph_flag & Flag::RANDOM) std::cout << "Random evaluation: ON\n";
+    if (eph_flag & Flag::FDM) std::cout << "FDM grid solving: ON\n";
+    if (eph_flag & Flag::NOINT) std::cout << "No integration: ON\n";
+    if (eph_flag & Flag::NOFRICTION) std::cout << "No friction application: ON\n";
+    if (eph_flag & Flag::NORANDOM) std::cout << "No random application: ON\n";
+    std::cout << '\n';
+  }
+  time_integrate = (eph_flag & Flag::NOINT) ? 0 : 1;
+
+  eph_model = atoi(arg[5]);
+  if (myID == 0) std::cout << "\nModel read: " << arg[5] << " -> " << eph_model << " (B200 device path)\n" << std::endl;
+  if (eph_model != Model::PRL && eph_model != Model::NONE)
+    error->all(FLERR, "fix eph/b200: only model 4 (PRL 120, 185501) runs on the device");
+
+  const double v_rho = atof(arg[6]);
+  const double v_Ce = atof(arg[7]);
+  const double v_kappa = atof(arg[8]);
+  const double v_Te = atof(arg[9]);
+  const int nx = atoi(arg[10]);
+  const int ny = atoi(arg[11]);
+  const int nz = atoi(arg[12]);
+
+  try {
+    if (strcmp("NULL", arg[13]) == 0) {
+      if (nx < 1 || ny < 1 || nz < 1) error->all(FLERR, "FixEPH: non-positive grid values");
+      grid = eph_b200::make_uniform_grid(nx, ny, nz, domain->boxlo, domain->boxhi, v_Te, v_Ce, v_rho, v_kappa);
+      strcpy(T_state, "T.restart");
+    } else {
+      grid = eph_b200::load_grid_file(arg[13]);
+      snprintf(T_state, max_file_length, "%s.restart", arg[13]);
+    }
+  } catch (const std::exception &e) {
+    error->all(FLERR, e.what());
+  }
+
+  T_freq = atoi(arg[14]);
+  T_out[0] = '\0';
+  if (T_freq > 0) snprintf(T_out, max_file_length, "%s", arg[15]);
+
+  types = atom->ntypes;
+  if (types > (narg - 17)) error->all(FLERR, "Fix eph: number of types larger than provided in fix");
+
+  try {
+    beta = eph_b200::load_beta_file(arg[16]);
+  } catch (const std::exception &e) {
+    error->all(FLERR, e.what());
+  }
+  if (beta.n_elements < 1) error->all(FLERR, "Fix eph: no elements found in input file");
+  r_cutoff = beta.r_cutoff;
+  r_cutoff_sq = beta.r_cutoff_sq;
+  rho_cutoff = beta.rho_cutoff;
+
+  type_map.assign(types, -1);
+  for (int i = 0; i < types; ++i) {
+    type_map[i] = beta.find(arg[17 + i]);
+    if (type_map[i] < 0) error->all(FLERR, "Fix eph: elements not found in input file");
+  }
+
+  // optional keyword pairs after the element names
+  rng_mars = false;
+  int device = -1;
+  for (int k = 17 + types; k + 1 < narg; k += 2) {
+    if (strcmp(arg[k], "rng") == 0) {
+      if (strcmp(arg[k + 1], "mars") == 0) rng_mars = true;
+      else if (strcmp(arg[k + 1], "philox") == 0) rng_mars = false;
+      else error->all(FLERR, "fix eph/b200: rng must be mars or philox");
+    } else if (strcmp(arg[k], "device") == 0) {
+      device = atoi(arg[k + 1]);
+    }
+    // anything else: extra element names, ignored like the reference does
+  }
+
+  eta_factor = sqrt(2.0 * force->boltz / update->dt);
+  dtv = update->dt;
+  dtf = 0.5 * update->dt * force->ftm2v;
+
+  // the device engine
+  eph_b200_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  if (device < 0) {
+    const char *vis = getenv("EPH_B200_DEVICES_PER_NODE");
+    int per_node = vis ? atoi(vis) : 1;
+    device = per_node > 0 ? myID % per_node : 0;
+  }
+  cfg.device = device;
+  cfg.ntypes = types;
+  cfg.type_map = type_map.data();
+  cfg.groupbit = groupbit;
+  cfg.flags = eph_flag;
+  cfg.model = eph_model;
+  cfg.seed = (unsigned long long)seed;
+  cfg.rank = myID;
+  cfg.nranks = nrPS;
+  cfg.stream = nullptr;
+  if (eph_b200_create(&cfg, &dev) != EPH_B200_OK) error->all(FLERR, eph_b200_create_error());
+
+  {
+    std::vector<double> t_rho = eph_b200::BetaTables::flatten(beta.rho_r_sq);
+    std::vector<double> t_alpha = eph_b200::BetaTables::flatten(beta.alpha);
+    std::vector<double> t_beta = eph_b200::BetaTables::flatten(beta.beta);
+    check(eph_b200_set_tables(dev, beta.n_elements, (int)beta.n_rho, beta.inv_dr_sq(), t_rho.data(), (int)beta.n_beta,
+                              beta.inv_drho(), t_alpha.data(), t_beta.data(), beta.r_cutoff_sq, beta.rho_cutoff),
+          "set_tables");
+  }
+  check(eph_b200_set_grid(dev, (int)grid.nx, (int)grid.ny, (int)grid.nz, grid.box, (int)grid.steps, grid.T_e.data(),
+                          grid.S_e.data(), grid.rho_e.data(), grid.C_e.data(), grid.kappa_e.data(), grid.flag.data(),
+                          grid.t_dyn.data()),
+        "set_grid");
+  if (grid.has_tables)
+    check(eph_b200_set_grid_tables(dev, (int)grid.C_e_T.size(), grid.E_e_T.dx, grid.C_e_T.k.data(), grid.kappa_e_T.k.data(),
+                                   grid.E_e_T.y.data()),
+          "set_grid_tables");
+  check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
+
+  array = nullptr;
+  list = nullptr;
+  n = 0;
+  atoms_epoch = -1;
+  need_upload = true;
+
+  grow_arrays(atom->nmax);
+  atom->add_callback(0);
+  std::fill_n(&(array[0][0]), size_peratom_cols * (size_t)(atom->nlocal + atom->nghost), 0);
+
+  Ee = 0.0;
+}
+
+FixEPHB200::~FixEPHB200() {
+  delete random;
+  atom->delete_callback(id, 0);
+  memory->destroy(array);
+  eph_b200_destroy(dev);
+}
+
+void FixEPHB200::check(int rc, const char *what) {
+  if (rc != EPH_B200_OK) {
+    std::string msg = std::string("fix eph/b200: ") + what + ": " + eph_b200_last_error(dev);
+    error->all(FLERR, msg);
+  }
+}
+
+void FixEPHB200::init() {
+  if (domain->dimension == 2) error->all(FLERR, "Cannot use fix eph with 2d simulation");
+  if (domain->nonperiodic != 0) error->all(FLERR, "Cannot use nonperiodic boundares with fix eph");
+  if (domain->triclinic) error->all(FLERR, "Cannot use fix eph with triclinic box");
+
+  // full neighbour list including ghosts, cut-off r_c (fix_eph.cpp:273-275)
+  int request_style = NeighConst::REQ_FULL | NeighConst::REQ_GHOST;
+  auto req = neighbor->add_request(this, request_style);
+  req->set_cutoff(r_cutoff);
+
+  reset_dt();
+}
+
+void FixEPHB200::init_list(int, NeighList *ptr) {
+  this->list = ptr;
+  need_upload = true;
+}
+
+int FixEPHB200::setmask() {
+  int mask = 0;
+  mask |= POST_FORCE;
+  mask |= END_OF_STEP;
+  mask |= INITIAL_INTEGRATE;
+  mask |= FINAL_INTEGRATE;
+  return mask;
+}
+
+// Velocity-Verlet half steps (fix_eph.cpp:305-348).  x, v, f live in LAMMPS'
+// host arrays here, so these streaming loops stay on the host; the device
+// variants (eph_b200_initial_integrate / final_integrate) serve GPU-resident atoms.
+void FixEPHB200::initial_integrate(int) {
+  if (eph_flag & Flag::NOINT) return;
+  double **x = atom->x, **v = atom->v, **f = atom->f;
+  const double *mass = atom->mass;
+  const int *type = atom->type, *mask = atom->mask;
+  const int nlocal = atom->nlocal;
+  for (int i = 0; i < nlocal; ++i) {
+    if (!(mask[i] & groupbit)) continue;
+    const double dtfm = dtf / mass[type[i]];
+    for (int d = 0; d < 3; ++d) v[i][d] += dtfm * f[i][d];
+    for (int d = 0; d < 3; ++d) x[i][d] += dtv * v[i][d];
+  }
+}
+
+void FixEPHB200::final_integrate() {
+  if (eph_flag & Flag::NOINT) return;
+  double **v = atom->v, **f = atom->f;
+  const double *mass = atom->mass;
+  const int *type = atom->type, *mask = atom->mask;
+  const int nlocal = atom->nlocal;
+  for (int i = 0; i < nlocal; ++i) {
+    if (!(mask[i] & groupbit)) continue;
+    const double dtfm = dtf / mass[type[i]];
+    for (int d = 0; d < 3; ++d) v[i][d] += dtfm * f[i][d];
+  }
+}
+
+// Everything that only changes when LAMMPS re-neighbours: atom types / masks /
+// tags, the ghost->owner map and the neighbour list go to the device once per
+// rebuild, never per step.
+void FixEPHB200::upload_topology() {
+  const int nlocal = atom->nlocal, nghost = atom->nghost;
+  if (nrPS > 1)
+    error->all(FLERR, "fix eph/b200: multi-rank runs exchange ghosts over NCCL (see INTEGRATION.md); "
+                      "the LAMMPS-MPI transport is not wired in this build");
+  // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
+  ghost_owner.assign(nghost, -1);
+  state = FixState::OWNER;
+  comm->forward_comm(this);
+  state = FixState::NONE;
+  for (int g = 0; g < nghost; ++g)
+    if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/b200: ghost atom without a local owner");
+  check(eph_b200_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, reinterpret_cast<const int64_t *>(atom->tag),
+                           ghost_owner.data(), EPH_B200_HOST),
+        "set_atoms");
+  check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
+  atoms_epoch = ((long long)nlocal << 32) | (unsigned)nghost;
+  need_upload = false;
+}
+
+void FixEPHB200::post_force(int) {
+  const int nlocal = atom->nlocal, nghost = atom->nghost;
+  const long long epoch = ((long long)nlocal << 32) | (unsigned)nghost;
+  if (need_upload || neighbor->ago == 0 || epoch != atoms_epoch) upload_topology();
+
+  const double *xi = nullptr;
+  if ((eph_flag & Flag::RANDOM) && rng_mars) {
+    // the reference's stream: three Gaussians per group atom in local order (fix_eph.cpp:854-861)
+    xi_host.assign(3 * (size_t)nlocal, 0.0);
+    const int *mask = atom->mask;
+    for (int i = 0; i < nlocal; ++i)
+      if (mask[i] & groupbit) {
+        xi_host[3 * (size_t)i + 0] = random->gaussian();
+        xi_host[3 * (size_t)i + 1] = random->gaussian();
+        xi_host[3 * (size_t)i + 2] = random->gaussian();
+      }
+    xi = xi_host.data();
+  }
+  if (nlocal + nghost == 0) return;
+  check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
+                            EPH_B200_HOST),
+        "post_force");
+}
+
+void FixEPHB200::end_of_step() {
+  const int nlocal = atom->nlocal;
+  double E_local = 0.0;
+  if (nlocal > 0)
+    check(eph_b200_end_of_step(dev, &atom->x[0][0], &atom->v[0][0], &E_local, EPH_B200_HOST), "end_of_step");
+
+  // heat map (fix_eph.cpp:397-399)
+  if (myID == 0 && T_freq > 0 && (update->ntimestep % T_freq) == 0) {
+    std::vector<double> T(grid.ncell());
+    check(eph_b200_get_grid(dev, 0, T.data()), "get_grid");
+    try {
+      eph_b200::write_heat_map(grid, T, T_out, (int)(update->ntimestep / T_freq));
+    } catch (const std::exception &e) {
+      error->all(FLERR, e.what());
+    }
+  }
+
+  MPI_Allreduce(MPI_IN_PLACE, &E_local, 1, MPI_DOUBLE, MPI_SUM, world);
+  Ee += E_local;
+
+  if (nlocal > 0) check(eph_b200_get_peratom(dev, &array[0][0], EPH_B200_HOST), "get_peratom");
+}
+
+void FixEPHB200::reset_dt() {
+  eta_factor = sqrt(2.0 * force->boltz / update->dt);
+  dtv = update->dt;
+  dtf = 0.5 * update->dt * force->ftm2v;
+  check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
+}
+
+void FixEPHB200::grow_arrays(int ngrow) {
+  n = ngrow;
+  memory->grow(array, ngrow, size_peratom_cols, "eph:array");
+  array_atom = array;
+}
+
+double FixEPHB200::compute_vector(int i) {
+  if (i == 0) return Ee;
+  if (i == 1) {
+    double T = 0.0;
+    check(eph_b200_mean_T(dev, &T), "mean_T");
+    return T;
+  }
+  return Ee;
+}
+
+int FixEPHB200::pack_forward_comm(int n, int *list, double *data, int, int *) {
+  int m = 0;
+  if (state == FixState::OWNER) {
+    const int nlocal = atom->nlocal;
+    // LAMMPS forwards ghosts of ghosts in later swaps: resolve through the part already known
+    for (int i = 0; i < n; ++i) {
+      const int src = list[i];
+      data[m++] = static_cast<double>(src < nlocal ? src : ghost_owner[src - nlocal]);
+    }
+  }
+  return m;
+}
+
+void FixEPHB200::unpack_forward_comm(int n, int first, double *data) {
+  if (state == FixState::OWNER) {
+    const int nlocal = atom->nlocal;
+    for (int i = 0; i < n; ++i) ghost_owner[first + i - nlocal] = static_cast<int>(data[i]);
+  }
+}
+
+double FixEPHB200::memory_usage() {
+  return (double)n * size_peratom_cols * sizeof(double);
+}
+
+// final grid state, readable as T_infile of a later run (fix_eph.cpp:1019-1021)
+void FixEPHB200::post_run() {
+  if (myID != 0) return;
+  std::vector<double> T(grid.ncell());
+  check(eph_b200_get_grid(dev, 0, T.data()), "get_grid");
+  // temperature-dependent cells carry their last C_e / kappa_e in the reference's restart
+  check(eph_b200_get_grid(dev, 3, grid.C_e.data()), "get_grid");
+  check(eph_b200_get_grid(dev, 4, grid.kappa_e.data()), "get_grid");
+  try {
+    eph_b200::write_restart(grid, T, T_state);
+  } catch (const std::exception &e) {
+    error->all(FLERR, e.what());
+  }
+}
+
+void FixEPHB200::probe_copy(int which, size_t, size_t, double *out) {
+  check(eph_b200_get_probe(dev, which, out), "get_probe");
+}
+
+void FixEPHB200::grid_T(double *out) { check(eph_b200_get_grid(dev, 0, out), "get_grid"); }

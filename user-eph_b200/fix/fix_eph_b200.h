@@ -1,0 +1,105 @@
+/* fix eph/b200 -- B200-native drop-in for `fix eph` (LLNL/USER-EPH).
+ *
+ * Same command line as the reference fix (fix_eph.cpp:36-58):
+ *   fix ID group eph/b200 seed flags model rho_e C_e kappa_e T_e NX NY NZ T_infile freq T_out beta_file elem...
+ * optionally followed by keyword pairs the reference does not have:
+ *   rng mars|philox   source of the Gaussians xi_i (default philox: counter-based, generated on the device and keyed
+ *                     on atom tags, so no XI ghost exchange is needed; mars: LAMMPS' RanMars on the host in the
+ *                     reference's order, fix_eph.cpp:854-861, uploaded every step)
+ *   device N          CUDA device ordinal (default: rank modulo visible devices)
+ * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
+ * (f_ID[1], f_ID[2], 8 per-atom columns); all per-timestep work is done by libeph_b200 (include/eph_b200.h).
+ * Build with -DEPH_B200_REPLACE_FIX_EPH to register under the name `eph` itself.
+ */
+#ifdef FIX_CLASS
+#ifdef EPH_B200_REPLACE_FIX_EPH
+FixStyle(eph,FixEPHB200)
+#else
+FixStyle(eph/b200,FixEPHB200)
+#endif
+#else
+
+#ifndef LMP_FIX_EPH_B200_H
+#define LMP_FIX_EPH_B200_H
+
+#include <string>
+#include <vector>
+
+#include "fix.h"
+
+#include "eph_b200.h"
+#include "eph_grid_io.h"
+#include "eph_tables.h"
+
+namespace LAMMPS_NS {
+
+class FixEPHB200 : public Fix {
+ public:
+  // same enumerations as FixEPH (fix_eph.h:35-60)
+  enum class FixState : unsigned int { NONE, RHO, XI, WI, OWNER };
+  enum Flag : int { FRICTION = 0x01, RANDOM = 0x02, FDM = 0x04, NOINT = 0x08, NOFRICTION = 0x10, NORANDOM = 0x20 };
+  enum Model : int { TESTING = -1, NONE = 0, TTM = 1, PRB = 2, PRLCM = 3, PRL = 4 };
+
+  FixEPHB200(class LAMMPS *, int, char **);
+  ~FixEPHB200() override;
+
+  void init() override;
+  void init_list(int id, class NeighList *ptr) override;
+  int setmask() override;
+  void initial_integrate(int) override;
+  void post_force(int) override;
+  void final_integrate() override;
+  void end_of_step() override;
+  void reset_dt() override;
+  void grow_arrays(int) override;
+  double compute_vector(int) override;
+  double memory_usage() override;
+  void post_run() override;
+  int pack_forward_comm(int, int *, double *, int, int *) override;
+  void unpack_forward_comm(int, int, double *) override;
+
+  // read-only views used by the test driver (tests/lammps_shim/fix_driver.h)
+  void probe_copy(int which, size_t nlocal, size_t ntotal, double *out);
+  size_t grid_size() const { return grid.ncell(); }
+  void grid_T(double *out);
+
+ protected:
+  static constexpr size_t max_file_length = 256;
+
+  int myID, nrPS;
+  FixState state;
+  int eph_flag, eph_model;
+  int types;
+  std::vector<int> type_map;
+
+  eph_b200::BetaTables beta;   // host copy of the tables (parsed from arg[16])
+  eph_b200::GridState grid;    // host description of the FDM grid (parameters, file names)
+  eph_b200_handle *dev;        // the device engine
+
+  double dtv, dtf;
+  double r_cutoff, r_cutoff_sq, rho_cutoff;
+  int T_freq;
+  char T_out[max_file_length];
+  char T_state[max_file_length];
+  double eta_factor;
+  int seed;
+  class RanMars *random;
+  bool rng_mars;
+  class NeighList *list;
+  double Ee;
+  size_t n;
+
+  double **array;               // [nmax][8] per-atom output (array_atom)
+  std::vector<double> xi_host;  // rng mars: Gaussians of this step
+  std::vector<int> ghost_owner; // local owner of each ghost (single rank)
+  std::vector<double> owner_buf;
+  long long atoms_epoch;        // (nlocal,nghost) signature of the last upload
+  bool need_upload;
+
+  void upload_topology();
+  void check(int rc, const char *what);
+};
+
+}  // namespace LAMMPS_NS
+#endif
+#endif
