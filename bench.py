@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- `fix eph` hot path throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's own CPU fix
+
+Workload: fcc Ni, n^3 unit cells (n = 100 -> 4 000 000 atoms), a = 3.52 A, N(0, 0.05 A)
+displacements, Maxwell velocities at 600 K plus one 10 keV primary knock-on atom, dt = 1e-4 ps, flags 7
+(friction + random + FDM), model 4, FDM grid 64^3, full neighbour list at r_c + 2 A = 7 A.  One step = post_force
++ end_of_step.  `value` is timed with all inputs resident in HBM; `e2e` goes through the same C ABI with pinned
+HOST buffers (x, v, f up and f down every step, the neighbour list re-uploaded every 10 steps as a re-neighbouring
+LAMMPS run would).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
+sys.path.insert(0, ROOT)
+
+BETA_FILE = os.path.join(ROOT, "tests", "golden", "Ni_trunc.beta")
+METRIC = "fix eph atom-steps/s (Ni 4M atoms)"
+UNIT = "atom-steps/s"
+REBUILD_EVERY = 10
+DT = 1e-4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=100, help="fcc unit cells per box edge (100 -> 4M atoms)")
+    ap.add_argument("--grid", type=int, default=64, help="FDM grid points per edge")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fdm-bench", action="store_true")
+    ap.add_argument("--cpu-cells", type=int, default=16, help="edge of each CPU-baseline replica (16 -> 16 384 atoms)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------
+def build_workload(cells, brick=None):
+    from eph_b200 import harness as H
+    s = H.make_system(cells, brick=brick)
+    # the primary knock-on atom of config C3: 10 keV along (0.835, 0.544, 0.082) (Tests/MD_Run/run.lmp:69-73)
+    if brick is None or brick[0] == 0:
+        pka = 0
+        s["v"][pka] = 1813.0 * np.array([0.835115, 0.543981, 0.081652])
+        s["v"][s["nlocal"]:][s["ghost_owner"] == pka] = s["v"][pka]
+    return s
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append(line.strip())
+            if self.stop_flag:
+                break
+        p.kill()
+
+    def summary(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [t.strip() for t in r.split(",")]
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own fix (compiled, unmodified) or the oracle port, as independent replicas
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    cells, steps, seed, use_ref = args
+    sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
+    sys.path.insert(0, ROOT)
+    from eph_b200 import harness as H
+    s = H.make_system(cells, pos_seed=1234 + seed, vel_seed=101 + seed)
+    xi = np.random.default_rng(seed).normal(size=(s["nlocal"], 3))
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    g = 4
+    if use_ref:
+        from oracle import reference as R
+        devnull = os.open(os.devnull, os.O_WRONLY)   # the reference prints a banner per fix
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            drv = R.fix_driver(s, H.fix_args(7, BETA_FILE, ["Ni"], grid=(g, g, g)), dt=DT)
+        finally:
+            os.dup2(saved, 1)
+        drv.set_xi(xi); drv.post_force(); drv.end_of_step()          # untimed first step
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            drv.set_xi(xi)
+            drv.post_force()
+            drv.end_of_step()
+        return s["nlocal"] * steps, time.perf_counter() - t0
+    from oracle import oracle as O
+    fx = O.Fix(s, O.Beta(path=BETA_FILE), O.FDM(g, g, g, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=DT)
+    fx.post_force(xi); fx.end_of_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fx.post_force(xi)
+        fx.end_of_step()
+    return s["nlocal"] * steps, time.perf_counter() - t0
+
+
+def cpu_baseline(cells, steps, procs=None):
+    """Aggregate atom-steps/s of `procs` concurrent single-rank replicas (the reference has no threads and MPI is
+    not installed, so replicas stand in for ranks)."""
+    import multiprocessing as mp
+    from oracle import reference as R
+    use_ref = R.available()
+    procs = procs or max(1, (os.cpu_count() or 1))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(cells, steps, k, use_ref) for k in range(procs)])
+    wall = time.perf_counter() - t0
+    work = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    return {"value": work / tmax, "unit": UNIT, "cores": procs, "kind": "reference" if use_ref else "port",
+            "sample": "%d concurrent single-rank replicas of %d Ni atoms (n=%d), %d timed steps each, grid 4^3, flags 7, "
+                      "model 4; slowest replica %.2f s, wall %.1f s" % (procs, 4 * cells ** 3, cells, steps, tmax, wall)}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    base = None
+    for k in range(a.warmup + a.steps):
+        base = cpu_baseline(a.cpu_cells, 1)
+        if k >= a.warmup:
+            per_step.append(base["value"])
+    value = float(np.mean(per_step))
+    natoms = 4 * a.cells ** 3
+    base["value"] = value
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": 1e3 * natoms / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": workload_config(a, natoms), "cpu_baseline": base,
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference CPU fix on the host cores; each step is a bounded sample (all cores, one replica of "
+                   "%d atoms per core); ms_per_step is the time the full %d-atom workload would need at that rate"
+                   % (4 * a.cpu_cells ** 3, natoms)}
+    print(json.dumps(out))
+
+
+def workload_config(a, natoms):
+    return {"workload": "C3: Ni fcc %d^3 cells = %d atoms, one 10 keV PKA, flags 7 (friction+random+FDM), model 4, "
+                        "FDM grid %d^3, dt 1e-4 ps, full list at 7 A" % (a.cells, natoms, a.grid),
+            "atoms": natoms, "fdm_grid": [a.grid] * 3, "beta_file": "tests/golden/Ni_trunc.beta",
+            "l2": "inputs (neighbour list + per-atom arrays) far larger than the 126 MB L2; no flush needed",
+            "parallelism": "spatial bricks, one rank per GPU"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from eph_b200 import host, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != a.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d" % (a.gpus, world))
+    if world > 1:
+        raise SystemExit("bench.py: the multi-GPU path is not wired yet in this build")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    s = build_workload(a.cells)
+    nl, ng = s["nlocal"], s["nghost"]
+    natoms = s["natoms"]
+    n_nb = float(s["offsets"][-1]) / nl
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = lib.Engine([0], flags=7, seed=12345, device=local, stream=stream)
+    eng.set_tables_from(host.BetaTables(path=BETA_FILE))
+    eng.set_grid(a.grid, a.grid, a.grid, box, 300.0, 1.0, 3.5e-6, 0.1248)
+    eng.set_dt(DT)
+    t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
+    d_type, d_mask, d_tag, d_owner = t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64), t(s["ghost_owner"], torch.int32)
+    d_off, d_neigh = t(s["offsets"], torch.int64), t(s["neigh"], torch.int32)
+    d_x, d_v = t(s["x"], torch.float64), t(s["v"], torch.float64)
+    d_f = torch.zeros((nl, 3), dtype=torch.float64, device=dev)
+    eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
+    eng.set_neighbors(d_off, d_neigh)
+
+    def step_resident(k):
+        eng.post_force(d_x, d_v, d_f, None, k)
+        eng.end_of_step(d_x, d_v, want_energy=False)
+
+    for k in range(a.warmup):
+        step_resident(k)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(a.steps):
+        step_resident(a.warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    ktimes = eng.kernel_times()
+    eng.set_profiling(False)
+    clocks = sampler.summary()
+    ms_per_step = ms / a.steps
+    value = natoms * a.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (SURVEY.md 8d per-sweep algorithmic bytes) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg = {"rho_sweep": 36 + 4 * n_nb, "w_rng_sweep": 84 + 4 * n_nb, "friction_sweep": 180 + 4 * n_nb}
+    per_kernel = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in ktimes.items()}
+    dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["ms_avg"], default=None)
+    roofline = None
+    if dom:
+        ach = alg[dom] * nl / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_atom": alg[dom], "kernel_ms": per_kernel[dom]["ms_avg"],
+                    "step": {"algorithmic_bytes_per_atom_step": 420 + 12 * n_nb,
+                             "achieved": (420 + 12 * n_nb) * value / 1e9, "frac": (420 + 12 * n_nb) * value / 1e9 / peak},
+                    "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in per_kernel.items()}}
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        h_x, h_v = pin(s["x"]), pin(s["v"])
+        h_f = torch.zeros((nl, 3), dtype=torch.float64).pin_memory()
+        h_off, h_neigh = pin(s["offsets"]), pin(s["neigh"])
+        h_type, h_mask, h_tag, h_owner = pin(s["type"]), pin(s["mask"]), pin(s["tag"]), pin(s["ghost_owner"])
+        nx, nv, nf = h_x.numpy(), h_v.numpy(), h_f.numpy()
+
+        def reneighbor():
+            eng.set_atoms(nl, ng, h_type.numpy(), h_mask.numpy(), h_tag.numpy(), h_owner.numpy())
+            eng.set_neighbors(h_off.numpy(), h_neigh.numpy())
+
+        def step_e2e(k):
+            if k % REBUILD_EVERY == 0:
+                reneighbor()
+            eng.post_force(nx, nv, nf, None, k)         # x, v, f up; f down
+            return eng.end_of_step(nx, nv)              # x, v (locals) up; E_local down
+
+        reneighbor()
+        for k in range(1, min(a.warmup, 3) + 1):
+            step_e2e(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(a.steps):
+            step_e2e(k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+        nt = nl + ng
+        rebuilds = len([k for k in range(a.steps) if k % REBUILD_EVERY == 0])
+        list_bytes = (h_off.numel() * 8 + h_neigh.numel() * 4 + nt * (4 + 4 + 8) + ng * 4) * rebuilds / a.steps
+        h2d = 2 * nt * 24 + nl * 24 + 2 * nl * 24 + list_bytes
+        d2h = nl * 24 + 8
+        e2e = {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
+               "note": "pinned host x, v, f through eph_b200_post_force/end_of_step (HOST memspace); neighbour list "
+                       "re-uploaded every %d steps (amortised in h2d_bytes_per_step)" % REBUILD_EVERY}
+        # back to the resident set-up for anything that follows
+        eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
+        eng.set_neighbors(d_off, d_neigh)
+
+    # ---- FDM micro-benchmark: Mcell-updates/s of the stencil on a 256^3 grid with 13 sub-steps (TB_Bench fine grid) ----
+    fdm = None
+    if not a.no_fdm_bench:
+        fdm = fdm_bench(lib, host, stream, local, peak)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts=ng),
+           "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
+    if not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.cpu_steps)
+    print(json.dumps(out))
+
+
+def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):
+    import torch
+    L = 56.32 * n / 128.0
+    eng = lib.Engine([0], flags=7, device=local, stream=stream)
+    eng.set_tables_from(host.BetaTables(path=BETA_FILE))
+    eng.set_grid(n, n, n, [0, L, 0, L, 0, L], 300.0, 1.0, 3.5e-6, 0.01248)    # TB_Bench 03_Grid_Fine parameters
+    eng.set_dt(DT)
+    x = np.array([[1.0, 1.0, 1.0]]); z = np.zeros((1, 3))
+    eng.set_atoms(1, 0, np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1], dtype=np.int64))
+    eng.set_neighbors(np.array([0, 0], dtype=np.int64), np.array([0], dtype=np.int32))
+    dx, dv, df = (torch.as_tensor(t, device=torch.device("cuda", local)) for t in (x, z, z.copy()))
+    eng.post_force(dx, dv, df, None, 0)
+    for _ in range(2):
+        eng.end_of_step(dx, dv, want_energy=False)
+    sub = eng.last_substeps()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    eng.set_profiling(True)
+    e0.record()
+    for _ in range(solves):
+        eng.end_of_step(dx, dv, want_energy=False)
+    e1.record()
+    torch.cuda.synchronize()
+    kt = eng.kernel_times().get("fdm_substep", (0.0, 1))
+    ms = e0.elapsed_time(e1)
+    cells = n ** 3
+    rate = cells * sub * solves / (ms * 1e-3)
+    k_ms = kt[0] / max(kt[1], 1)
+    ach = 60.0 * cells / (k_ms * 1e-3) / 1e9
+    eng.close()
+    return {"metric": "FDM Mcell-updates/s", "value": rate / 1e6, "unit": "Mcell-updates/s", "grid": [n] * 3, "substeps": sub,
+            "solves": solves, "ms_per_solve": ms / solves,
+            "roofline": {"bound": "hbm", "kernel": "fdm_substep", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_cell_update": 60, "kernel_ms": k_ms}}
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

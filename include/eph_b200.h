@@ -159,6 +159,11 @@ int eph_b200_get_probe(eph_b200_handle *h, int which, double *out);
 int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list, double *buf);
 int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf);
 
+/* Per-kernel device timing with CUDA events on the launch stream (benchmarks).  kernel_times returns the number of
+ * distinct kernels seen since profiling was switched on and fills up to `max` entries (total ms, launches). */
+int eph_b200_set_profiling(eph_b200_handle *h, int on);
+int eph_b200_kernel_times(eph_b200_handle *h, int max, const char **names, double *ms, long long *counts);
+
 /* blocks until everything enqueued so far has finished */
 int eph_b200_synchronize(eph_b200_handle *h);
 /* number of kernels this handle has launched since creation */

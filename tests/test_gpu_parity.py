@@ -1,0 +1,364 @@
+"""Parity of the CUDA path against the oracle on the same seeded inputs, through the C ABI
+(eph_b200.lib.Engine) and through the FixEPHB200 host class.  Bar (BASELINE.json north_star):
+rho, beta, forces and T_e grids within 1e-10 relative; force errors are scaled by the largest
+reference magnitude because per-atom friction is a cancelling sum."""
+import os
+
+import numpy as np
+import pytest
+
+from eph_b200 import harness as H
+from eph_b200 import host, lib
+from oracle import oracle as O
+
+import traj
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def make_engine(beta_path, flags, grid, box, type_map=(0,), groupbit=1, dt=1e-4, grid_file=None, seed=12345):
+    eng = lib.Engine(list(type_map), flags=flags, groupbit=groupbit, seed=seed)
+    eng.set_tables_from(host.BetaTables(path=beta_path))
+    if grid_file is not None:
+        host.GridFile(grid_file).apply(eng)
+    else:
+        eng.set_grid(grid[0], grid[1], grid[2], box, 300.0, 1.0, 3.5e-6, 0.1248)
+    eng.set_dt(dt)
+    return eng
+
+
+def attach(eng, s, device=False):
+    if device:
+        import torch
+        d = torch.device("cuda", 0)
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=d)
+        eng.set_atoms(s["nlocal"], s["nghost"], t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64),
+                      t(s["ghost_owner"], torch.int32))
+        eng.set_neighbors(t(s["offsets"], torch.int64), t(s["neigh"], torch.int32))
+    else:
+        eng.set_atoms(s["nlocal"], s["nghost"], np.ascontiguousarray(s["type"], dtype=np.int32),
+                      np.ascontiguousarray(s["mask"], dtype=np.int32), np.ascontiguousarray(s["tag"], dtype=np.int64),
+                      np.ascontiguousarray(s["ghost_owner"], dtype=np.int32))
+        eng.set_neighbors(np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32))
+
+
+def compare(recs, refs, nl, keys=("f", "array", "T", "w", "x", "v")):
+    for k, (a, b) in enumerate(zip(recs, refs)):
+        for key in keys:
+            err = H.error_metrics(a[key], b[key])
+            assert err < TOL, (key, k, err)
+        assert H.error_metrics(a["rho"][:nl], b["rho"][:nl]) < TOL
+        assert abs(a["Ee"] - b["Ee"]) <= TOL * max(abs(b["Ee"]), 1e-300), (a["Ee"], b["Ee"])
+        assert abs(a["Tmean"] - b["Tmean"]) <= TOL * abs(b["Tmean"])
+
+
+def box6(s):
+    return [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+
+
+@pytest.mark.parametrize("flags", [1, 3, 7, 2 | 4, 7 | 16, 7 | 32])
+@pytest.mark.parametrize("device", [False, True])
+def test_engine_matches_oracle_flags(sys500, synth_beta_1, flags, device):
+    s = sys500
+    rng = np.random.default_rng(31)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(3)]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(3, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), flags, dt=1e-4)
+    refs = traj.run_oracle(fx, s, xis, [58.71])
+    eng = make_engine(synth_beta_1, flags, (3, 2, 2), box6(s))
+    attach(eng, s, device)
+    recs = traj.run_engine(eng, s, xis, [58.71], 1e-4, device=device)
+    compare(recs, refs, s["nlocal"])
+    for a, b in zip(recs, refs):
+        assert H.error_metrics(a["f_eph"], b["f_eph"]) < TOL and H.error_metrics(a["f_rng"], b["f_rng"]) < TOL
+    assert eng.launch_count() > 0
+
+
+@pytest.mark.parametrize("lanes", ["8", "16", "32"])
+def test_engine_lane_widths(sys500, synth_beta_1, lanes, monkeypatch):
+    """every sub-warp width of the sweeps gives the same answer"""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, os, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import test_gpu_parity as T, traj
+        from eph_b200 import harness as H
+        from oracle import oracle as O
+        s = H.make_system(5)
+        xis = [np.random.default_rng(3).normal(size=(s["nlocal"], 3))]
+        fx = O.Fix(s, O.Beta(path=%r), O.FDM(2, 2, 2, T.box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
+        refs = traj.run_oracle(fx, s, xis, [58.71])
+        eng = T.make_engine(%r, 7, (2, 2, 2), T.box6(s)); T.attach(eng, s)
+        T.compare(traj.run_engine(eng, s, xis, [58.71], 1e-4), refs, s["nlocal"])
+        print("ok")
+    """) % (os.path.join(os.path.dirname(GOLDEN), "..", "user-eph_b200"), os.path.join(os.path.dirname(GOLDEN), ".."),
+            os.path.dirname(GOLDEN), synth_beta_1, synth_beta_1)
+    env = dict(os.environ, EPH_B200_LANES_RHO=lanes, EPH_B200_LANES_PAIR=lanes)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_engine_multi_element_and_group(synth_beta_4):
+    s = H.make_system(4, ntypes=3, group_fraction=0.5, pos_seed=5)
+    rng = np.random.default_rng(32)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(2)]
+    mass = [55.85, 58.71, 52.0]
+    fx = O.Fix(s, O.Beta(path=synth_beta_4), O.FDM(2, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, groupbit=2,
+               type_map=[3, 0, 2], dt=1e-4)
+    refs = traj.run_oracle(fx, s, xis, mass)
+    eng = make_engine(synth_beta_4, 7, (2, 2, 2), box6(s), type_map=[3, 0, 2], groupbit=2)
+    attach(eng, s)
+    compare(traj.run_engine(eng, s, xis, mass, 1e-4), refs, s["nlocal"])
+
+
+def test_rho_above_cutoff_gives_zero_coupling(tmp_path):
+    """the `beta set to zero` branch (eph_beta.h:174-180; reference deck Tests/EPH_Beta_zero)"""
+    knots = H.synthetic_knots(1, n_beta=41, drho=0.01)      # rho_cutoff = 0.4, below the lattice's site density
+    p = str(H.write_beta_file(tmp_path / "low.beta", knots))
+    s = H.make_system(4, sigma=0.08)
+    xi = [np.random.default_rng(33).normal(size=(s["nlocal"], 3))]
+    ob = O.Beta(path=p)
+    fx = O.Fix(s, ob, O.FDM(1, 1, 1, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
+    refs = traj.run_oracle(fx, s, xi, [58.71])
+    assert (refs[0]["rho"][: s["nlocal"]] > ob.rho_cutoff).any()
+    eng = make_engine(p, 7, (1, 1, 1), box6(s))
+    attach(eng, s)
+    compare(traj.run_engine(eng, s, xi, [58.71], 1e-4), refs, s["nlocal"])
+    assert eng.status_word() & 1
+
+
+def test_builtin_gaussian_stream_matches_its_definition(sys500, synth_beta_1):
+    """xi from the built-in counter-based stream == the stream's CPU definition fed through the injection port"""
+    s = sys500
+    eng = make_engine(synth_beta_1, 7, (2, 2, 2), box6(s), seed=777)
+    attach(eng, s)
+    recs = traj.run_engine(eng, s, [None, None], [58.71], 1e-4)
+    tags = s["tag"][: s["nlocal"]]
+    xis = [O.xi_stream(777, step, tags) for step in (1, 2)]
+    for r, xi in zip(recs, xis):
+        assert np.max(np.abs(r["xi"] - xi)) < 1e-13
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(2, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
+    compare(recs, traj.run_oracle(fx, s, xis, [58.71]), s["nlocal"])
+    allxi = np.concatenate([r["xi"].ravel() for r in recs])
+    assert abs(allxi.mean()) < 0.1 and abs(allxi.std() - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("name", ["caseA_example1", "caseB_grid", "caseC_alloy_group"])
+def test_engine_matches_committed_golden_vectors(name, ni_trunc_beta):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = traj.system_from_golden(g)
+    dt = float(g["dt"])
+    if name == "caseA_example1":
+        eng, mass = make_engine(ni_trunc_beta, 3, (1, 1, 1), box6(s), dt=dt), [58.71]
+    elif name == "caseB_grid":
+        eng, mass = make_engine(ni_trunc_beta, 7, None, None, dt=dt, grid_file=os.path.join(GOLDEN, "caseB_grid.in")), [58.71]
+    else:
+        eng = make_engine(os.path.join(GOLDEN, "synth2.beta"), 7, (2, 2, 2), box6(s), type_map=[1, 0], groupbit=2, dt=dt)
+        mass = [58.93, 58.71]
+    attach(eng, s)
+    recs = traj.run_engine(eng, s, list(g["xi"]), mass, dt)
+    refs = [dict((k, g["out_" + k][i]) for k in ("f", "array", "T", "w", "x", "v", "rho", "Ee", "Tmean")) for i in range(len(recs))]
+    compare(recs, refs, s["nlocal"])
+
+
+@pytest.mark.parametrize("name", ["caseA_example1", "caseB_grid", "caseC_alloy_group"])
+def test_fix_b200_matches_committed_golden_vectors(name):
+    """FixEPHB200 in the LAMMPS stand-in, same command line as the reference fix, rng mars = injected stream"""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = traj.system_from_golden(g)
+    s["natoms"] = s["nlocal"]
+    dt = float(g["dt"])
+    cwd = os.getcwd()
+    os.chdir(GOLDEN)
+    try:
+        if name == "caseA_example1":
+            drv = host.FixDriver(s, H.fix_args(3, "Ni_trunc.beta", ["Ni"], grid=(1, 1, 1), style="eph/b200", extra=["rng", "mars"]), dt=dt)
+        elif name == "caseB_grid":
+            drv = host.FixDriver(s, H.fix_args(7, "Ni_trunc.beta", ["Ni"], T_infile="caseB_grid.in", style="eph/b200", extra=["rng", "mars"]), dt=dt)
+        else:
+            drv = host.FixDriver(s, H.fix_args(7, "synth2.beta", ["Co", "Ni"], grid=(2, 2, 2), group="bit1", style="eph/b200",
+                                               extra=["rng", "mars"]), dt=dt, mass=[58.93, 58.71])
+    finally:
+        os.chdir(cwd)
+    recs = traj.run_fix_driver(drv, s, list(g["xi"]))
+    refs = [dict((k, g["out_" + k][i]) for k in ("f", "array", "T", "w", "x", "v", "rho", "Ee", "Tmean")) for i in range(len(recs))]
+    compare(recs, refs, s["nlocal"])
+    fl = drv.fix_flags()
+    assert fl["size_peratom_cols"] == 8 and fl["comm_forward"] == 3 and fl["ghost_velocity"] == 1 and fl["size_vector"] == 2
+    assert drv.neigh_cutoff() == 5.0
+
+
+def _fdm_case(shape, rng, walls, constant, tdyn_tables=None):
+    nx, ny, nz = shape
+    n = nx * ny * nz
+    fl = np.ones(n, dtype=np.int16)
+    if walls:
+        fl[rng.random(n) < 0.15] = 2
+    if constant:
+        fl[rng.random(n) < 0.1] = 0
+    return dict(T=300 + 100 * rng.random(n), kap=0.1248 * (0.5 + rng.random(n)), Ce=3.5e-6 * (0.5 + rng.random(n)),
+                S=1e-3 * rng.random(n), rho=1.0 + 0.2 * rng.random(n), fl=fl)
+
+
+@pytest.mark.parametrize("shape,walls,constant", [((8, 1, 1), False, False), ((5, 4, 3), True, True), ((1, 1, 1), False, False),
+                                                   ((33, 9, 5), True, False), ((64, 64, 64), False, False)])
+def test_grid_solve_matches_oracle(synth_beta_1, shape, walls, constant):
+    """EPH_FDM::solve alone: energy deposited by a handful of atoms, several solves, with and without sub-stepping"""
+    rng = np.random.default_rng(41)
+    box = [0.0, 17.6, -1.0, 16.6, 2.0, 19.6]
+    c = _fdm_case(shape, rng, walls, constant)
+    o = O.FDM(*shape, box, 300.0, 3.5e-6, 1.0, 0.1248)
+    for which, key in ((0, "T"), (1, "S"), (2, "rho"), (3, "Ce"), (4, "kap")):
+        o.field(which)[:] = c[key]
+    o.flags()[0][:] = c["fl"]
+    eng = lib.Engine([0], flags=7)
+    eng.set_tables_from(host.BetaTables(path=synth_beta_1))
+    eng.set_grid(*shape, box, c["T"], c["rho"], c["Ce"], c["kap"], S_e=c["S"], flag=c["fl"])
+    for dt in (1e-4, 5e-3):
+        o.set_dt(dt)
+        eng.set_dt(dt)
+        for _ in range(3):
+            src = 1e-2 * rng.normal(size=o.ntotal)
+            o.field(5)[:] = src
+            eng.put_grid(5, src)
+            o.solve()
+            _solve_only(eng)
+            assert H.error_metrics(eng.get_grid(0), o.field(0)) < TOL
+            assert np.all(eng.get_grid(5) == 0.0)
+        assert abs(eng.mean_T() - o.T_total()) < TOL * o.T_total()
+    assert eng.last_substeps() > 1
+
+
+def _solve_only(eng):
+    """run end_of_step with no atoms contributing: a one-atom system outside the fix group"""
+    if not getattr(eng, "_dummy", False):
+        x = np.array([[1.0, 1.0, 3.0]]); z = np.zeros((1, 3))
+        eng.set_atoms(1, 0, np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1], dtype=np.int64))
+        eng.set_neighbors(np.array([0, 0], dtype=np.int64), np.array([0], dtype=np.int32))
+        eng._xz = (x, z)
+        eng._dummy = True
+    x, z = eng._xz
+    eng.post_force(x, z, z.copy(), None, 0)
+    eng.end_of_step(x, z)
+
+
+def test_grid_temperature_dependent_cells(synth_beta_1, tmp_path):
+    rng = np.random.default_rng(42)
+    nT, dT = 401, 25.0
+    Tt = np.arange(nT) * dT
+    par = H.write_parameter_file(tmp_path / "par.data", dT, 3.5e-6 * (1 + Tt / 3000.0), 0.1248 * (1 + Tt / 5000.0))
+    nx, ny, nz = 6, 5, 4
+    n = nx * ny * nz
+    grid = H.write_grid_file(tmp_path / "T.in", nx, ny, nz, [0, 10, 0, 9, 0, 8], 300 + 2000 * rng.random(n), 0.0, 1.0, 3.5e-6, 0.1248, 1,
+                             (rng.random(n) < 0.5).astype(int), steps=3, parameter_file=str(par))
+    o = O.FDM(path=grid)
+    eng = lib.Engine([0], flags=7)
+    eng.set_tables_from(host.BetaTables(path=synth_beta_1))
+    host.GridFile(grid).apply(eng)
+    o.set_dt(2e-4)
+    eng.set_dt(2e-4)
+    for _ in range(4):
+        src = 1e-2 * rng.normal(size=n)
+        o.field(5)[:] = src
+        eng.put_grid(5, src)
+        o.solve()
+        _solve_only(eng)
+        assert H.error_metrics(eng.get_grid(0), o.field(0)) < TOL
+        assert H.error_metrics(eng.get_grid(3), o.field(3)) < TOL and H.error_metrics(eng.get_grid(4), o.field(4)) < TOL
+
+
+def test_empty_and_ragged_inputs(synth_beta_1):
+    eng = make_engine(synth_beta_1, 7, (2, 2, 2), [0, 10, 0, 10, 0, 10])
+    z = np.zeros((0, 3))
+    eng.set_atoms(0, 0, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64))
+    eng.set_neighbors(np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int32))
+    eng.post_force(z, z, z.copy(), None, 1)            # no atoms: nothing to do, no error
+    # ragged: atoms with empty rows, isolated atoms (rho = 0 -> skipped everywhere, fix_eph.cpp:709)
+    x = np.array([[1.0, 1, 1], [2.5, 1, 1], [9.0, 9, 9], [1.0, 3.2, 1]])
+    v = np.random.default_rng(1).normal(size=(4, 3))
+    off = np.array([0, 2, 4, 4, 6], dtype=np.int64)
+    ne = np.array([1, 3, 0, 3, 0, 1], dtype=np.int32)
+    s = dict(nlocal=4, nghost=0, x=x, v=v, f=np.zeros_like(x), type=np.ones(4, dtype=np.int32), mask=np.ones(4, dtype=np.int32),
+             tag=np.arange(1, 5), ghost_owner=np.zeros(0, dtype=np.int32), offsets=off, neigh=ne, box=np.array([10.0, 10, 10]), ntypes=1)
+    xi = [np.random.default_rng(2).normal(size=(4, 3))]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(2, 2, 2, [0, 10, 0, 10, 0, 10], 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
+    refs = traj.run_oracle(fx, s, xi, [58.71])
+    attach(eng, s)
+    recs = traj.run_engine(eng, s, xi, [58.71], 1e-4)
+    compare(recs, refs, 4)
+    assert np.all(recs[0]["array"][2] == 0.0)          # the isolated atom: rho = 0, no forces
+    # call-order errors are reported, not ignored
+    e2 = lib.Engine([0], flags=7)
+    with pytest.raises(lib.EphError, match="set_tables"):
+        e2.post_force(x, v, np.zeros_like(x), None, 0)
+
+
+def test_size_independent_properties_at_scale(synth_beta_1):
+    """n = 24 (55 296 atoms, 7.5 M list entries): properties that need no oracle run --
+    momentum conservation of the pair forces, linearity in v and xi, energy bookkeeping."""
+    s = H.make_system(24)
+    nl = s["nlocal"]
+    eng = make_engine(synth_beta_1, 7 | 16 | 32, (8, 8, 8), box6(s))   # forces computed but not applied
+    attach(eng, s)
+    rng = np.random.default_rng(51)
+    xi = rng.normal(size=(nl, 3))
+    x, v = s["x"], s["v"]
+    f = np.zeros((nl, 3))
+    eng.post_force(x, v, f, xi, 1)
+    assert np.all(f == 0.0)
+    fe, fr, rho = eng.probe(3), eng.probe(4), eng.probe(0)
+    assert np.all(rho[:nl] > 0) and np.allclose(rho[nl:], rho[s["ghost_owner"]], rtol=0, atol=0)
+    # every pair term is antisymmetric: the total friction and random force vanish
+    assert np.max(np.abs(fe.sum(axis=0))) < 1e-9 * np.abs(fe).max() * np.sqrt(nl)
+    assert np.max(np.abs(fr.sum(axis=0))) < 1e-9 * np.abs(fr).max() * np.sqrt(nl)
+    # friction is linear in v, the random force linear in xi
+    eng.post_force(x, 2.0 * v, f, -3.0 * xi, 1)
+    assert H.error_metrics(eng.probe(3), 2.0 * fe) < 1e-12 and H.error_metrics(eng.probe(4), -3.0 * fr) < 1e-12
+    # friction dissipates: -f_EPH . v >= 0 summed over atoms; energy bookkeeping matches the deposited source
+    eng.post_force(x, v, f, xi, 1)
+    T0 = eng.get_grid(0)
+    E = eng.end_of_step(x, v)
+    fe, fr = eng.probe(3), eng.probe(4)
+    E_ref = -np.sum((fe + fr) * v[:nl]) * 1e-4
+    assert abs(E - E_ref) < 1e-10 * max(abs(E_ref), np.abs(fe * v[:nl]).sum() * 1e-4)
+    assert -np.sum(fe * v[:nl]) > 0
+    # grid energy: sum(C_e rho_e dT) dV equals the energy handed over (periodic grid, uniform parameters)
+    dV = np.prod(s["box"] / 8)
+    dE_grid = np.sum(eng.get_grid(0) - T0) * 3.5e-6 * 1.0 * dV
+    assert abs(dE_grid - E) < 1e-8 * abs(E)
+    arr = eng.peratom()
+    assert np.array_equal(arr[:, 0], rho[:nl]) and np.array_equal(arr[:, 2:5], fe) and np.array_equal(arr[:, 5:8], fr)
+
+
+def test_fluctuation_dissipation_statistics(synth_beta_1):
+    """<f_RNG f_RNG^T> over noise realisations equals 2 k_B T_e B / dt with f_EPH = -B v
+    (the random force is built from the same W as the friction: PRL 120, 185501)."""
+    s = H.make_system(6)
+    nl = s["nlocal"]
+    dt, Te = 1e-4, 300.0
+    eng = make_engine(synth_beta_1, 7 | 16 | 32, (1, 1, 1), box6(s), dt=dt, seed=4242)
+    attach(eng, s)
+    x = s["x"]
+    f = np.zeros((nl, 3))
+    # B column for (atom a, direction d): friction response to a unit velocity of one atom and its images
+    a = 17
+    B = np.zeros((3, 3))
+    for d in range(3):
+        v = np.zeros_like(x)
+        v[a, d] = 1.0
+        v[nl:][s["ghost_owner"] == a, d] = 1.0
+        eng.post_force(x, v, f, None, 0)
+        B[:, d] = -eng.probe(3)[a]
+    # sample the random force on atom a over many steps of the built-in stream
+    nsamp = 4000
+    acc = np.zeros((3, 3))
+    v0 = np.zeros_like(x)
+    for step in range(nsamp):
+        eng.post_force(x, v0, f, None, step + 1)
+        fr = eng.probe(4)[a]
+        acc += np.outer(fr, fr)
+    cov = acc / nsamp
+    want = 2.0 * H.KB * Te * B / dt
+    assert np.allclose(B, B.T, rtol=1e-9, atol=1e-12 * np.abs(B).max())
+    assert np.max(np.abs(cov - want)) < 0.12 * np.max(np.abs(want))

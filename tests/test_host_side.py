@@ -1,0 +1,164 @@
+"""Host side of the product (C++ under user-eph_b200/fix): table construction, file grammars,
+the C-ABI library's symbols, and the loud failure without a GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from eph_b200 import harness as H
+from eph_b200 import host, lib
+from oracle import oracle as O
+
+from conftest import REFERENCE, ROOT, gpu_available
+
+
+def test_product_tables_match_oracle_bit_exact(synth_beta_4, ni_trunc_beta):
+    for path in (synth_beta_4, ni_trunc_beta):
+        pb, ob = host.BetaTables(path=path), O.Beta(path=path)
+        assert (pb.n_elements, pb.n_rho, pb.n_beta) == (ob.n_elements, ob.n_rho, ob.n_beta)
+        for a in ("r_cutoff", "r_cutoff_sq", "rho_cutoff", "inv_dr", "inv_dr_sq", "inv_drho"):
+            assert getattr(pb, a) == getattr(ob, a), a
+        for kind in range(4):
+            assert np.array_equal(pb.table(kind), ob.table(kind)), kind
+    assert [host.BetaTables(path=synth_beta_4).name(e) for e in range(4)] == ["Ni", "Co", "Cr", "Fe"]
+
+
+@pytest.mark.parametrize("rel", ["Data/Ni/Ni_PRB2019.beta", "Data/NiCoCrFe/NiCoCrFe_PRB2019.beta", "Examples/Beta/Ni.beta",
+                                 "Data/Si/Si_PRB2021_constant.beta"])
+def test_product_tables_match_reference_on_shipped_files(ref, rel):
+    path = os.path.join(REFERENCE, rel)
+    if not os.path.exists(path):
+        pytest.skip("reference data tree not present")
+    pb, rb = host.BetaTables(path=path), ref.beta_tables(path)
+    for kind in range(4):
+        assert np.array_equal(pb.table(kind), rb.table(kind)), kind
+    assert pb.rho_cutoff == rb.rho_cutoff and pb.inv_dr_sq == rb.inv_dr_sq
+
+
+def test_spline_builder_matches_oracle():
+    rng = np.random.default_rng(21)
+    for n in (5, 6, 64, 1001):
+        y = rng.normal(size=n)
+        assert np.array_equal(host.spline_build(0.37, y), O.spline_build(0.37, y))
+    y = np.array([0, 0, 0, 0, 1, 1, 1, 1, 5, 5, 0, 0, 0, 0.0])
+    assert np.array_equal(host.spline_build(1.0, y), O.spline_build(1.0, y))
+
+
+def test_knots_and_file_paths_agree(tmp_path):
+    knots = H.synthetic_knots(2, n_rho=301, n_beta=801, drho=0.02)
+    p = H.write_beta_file(tmp_path / "k.beta", knots)
+    a, b = host.BetaTables(path=p), host.BetaTables(knots=knots)
+    for kind in range(4):
+        assert np.array_equal(a.table(kind), b.table(kind))
+
+
+def test_missing_beta_file_is_an_error(tmp_path):
+    with pytest.raises(RuntimeError):
+        host.BetaTables(path=tmp_path / "nope.beta")
+
+
+def test_grid_file_grammar_and_writers(tmp_path):
+    rng = np.random.default_rng(22)
+    nT, dT = 101, 50.0
+    par = H.write_parameter_file(tmp_path / "par.data", dT, 3.5e-6 * (1 + np.arange(nT) / 50.0), 0.1 + 0.001 * np.arange(nT))
+    nx, ny, nz = 3, 4, 2
+    n = nx * ny * nz
+    fl = rng.integers(0, 3, n)
+    td = rng.integers(0, 2, n)
+    path = H.write_grid_file(tmp_path / "T.in", nx, ny, nz, [0, 3, -1, 3, 2, 4], 300 + rng.random(n), rng.random(n), 1 + rng.random(n),
+                             3.5e-6 * (1 + rng.random(n)), 0.1 * (1 + rng.random(n)), fl, td, steps=5, parameter_file=str(par))
+    g, o = host.GridFile(path), O.FDM(path=path)
+    assert (g.nx, g.ny, g.nz, g.steps, g.n_T) == (nx, ny, nz, 5, nT)
+    for which in range(5):
+        assert np.array_equal(g.field(which), o.field(which))
+    assert np.array_equal(g.flags()[0], o.flags()[0]) and np.array_equal(g.flags()[1], o.flags()[1])
+    # writers are byte-compatible with the reference grammar (as restated in the oracle)
+    g.write_heat_map(g.field(0), tmp_path / "prod_T", 3)
+    o.save_temperature(tmp_path / "orc_T", 3)
+    assert open(tmp_path / "prod_T_000003").read() == open(tmp_path / "orc_T_000003").read()
+    g.write_restart(g.field(0), tmp_path / "prod.restart")
+    o.save_state(tmp_path / "orc.restart")
+    assert open(tmp_path / "prod.restart").read() == open(tmp_path / "orc.restart").read()
+    # and a restart file can be read back as a grid file
+    g2 = host.GridFile(tmp_path / "prod.restart")
+    assert (g2.nx, g2.ny, g2.nz, g2.steps) == (nx, ny, nz, 5)
+
+
+def test_reference_example_grid_files_parse(has_reference_tree):
+    if not has_reference_tree:
+        pytest.skip("reference tree not present")
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REFERENCE, "Examples/Example_6"))   # T.in names Parameters.data relative to the run directory
+    try:
+        g, o = host.GridFile("T.in"), O.FDM(path="T.in")
+    finally:
+        os.chdir(cwd)
+    assert (g.nx, g.ny, g.nz) == (9, 9, 9) and g.n_T == 1001
+    for which in range(5):
+        assert np.array_equal(g.field(which), o.field(which))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "eph_b200.h")).read()
+    declared = set(re.findall(r"\b(eph_b200_[A-Za-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    L = lib.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert declared == set(lib.SYMBOLS), declared ^ set(lib.SYMBOLS)
+    assert lib.load().eph_b200_version() == 100
+
+
+def test_no_cpu_fallback_create_fails_loudly_without_gpu():
+    if gpu_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(lib.EphError) as e:
+        lib.Engine([0], flags=7)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_bad_config_is_rejected_before_touching_the_device():
+    L = lib.load()
+    h = C.c_void_p()
+    tm = (C.c_int * 1)(0)
+    cfg = lib.Config(0, 1, tm, 1, 7, 2, 1, 0, 1, None)   # model 2 (PRB) is not available on the device
+    assert L.eph_b200_create(C.byref(cfg), C.byref(h)) == -4
+    assert b"model" in L.eph_b200_create_error()
+    cfg = lib.Config(0, 0, tm, 1, 7, 4, 1, 0, 1, None)
+    assert L.eph_b200_create(C.byref(cfg), C.byref(h)) == -1
+
+
+def test_fix_b200_without_gpu_reports_through_lammps_error(sys500, synth_beta_1):
+    """Same constructor checks and messages as the reference (fix_eph.cpp:64, :175, :196); then a loud device error."""
+    s = sys500
+    with pytest.raises(host.FixError, match="too few arguments"):
+        host.FixDriver(s, ["fx", "all", "eph", 1, 7, 4])
+    with pytest.raises(host.FixError, match="elements not found"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Xx"]))
+    with pytest.raises(host.FixError, match="only model 4"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], model=2))
+    with pytest.raises(host.FixError, match="non-positive grid"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], grid=(0, 1, 1)))
+    if not gpu_available():
+        with pytest.raises(host.FixError, match="no CUDA device|CUDA"):
+            host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"]))
+
+
+def test_harness_neighbor_list_is_a_full_list(sys500):
+    s = sys500
+    off, ne, x = s["offsets"], s["neigh"], s["x"]
+    assert s["nlocal"] == 500 and off[-1] == len(ne)
+    nn = np.diff(off)
+    assert 120 < nn.mean() < 150          # N_nb ~ 135 at r_c + skin = 7 A (SURVEY.md conventions)
+    i = 17
+    d = np.linalg.norm(x - x[i], axis=1)
+    want = np.nonzero((d < 7.0) & (np.arange(len(x)) != i))[0]
+    assert np.array_equal(np.sort(ne[off[i]:off[i + 1]]), want)
+    # in-cutoff pairs: 54 for perfect fcc Ni at r_c = 5 A; the 4th shell (4.978 A) straddles the cut-off once displaced
+    nc = np.mean([(np.linalg.norm(x[ne[off[k]:off[k + 1]]] - x[k], axis=1) < 5.0).sum() for k in range(50)])
+    assert 45 < nc < 55
+    # ghosts are images of their owners
+    sh = x[s["nlocal"]:] - x[s["ghost_owner"]]
+    assert np.allclose(np.abs(sh / s["box"]).round(), np.abs(sh / s["box"]), atol=1e-12)

@@ -1,0 +1,121 @@
+"""Shared driver of short `fix eph` trajectories for golden generation and parity tests.
+
+One step = what LAMMPS' Verlet loop does around the fix with a
+zero pair force: f := 0, initial_integrate, ghost x/v refresh, post_force,
+final_integrate, ghost v refresh, end_of_step."""
+import numpy as np
+
+
+class GhostSync:
+    def __init__(self, system):
+        self.nl = system["nlocal"]
+        self.owner = np.asarray(system["ghost_owner"])
+        x = np.asarray(system["x"])
+        self.shift = x[self.nl:] - x[self.owner]
+
+    def __call__(self, x, v):
+        x[self.nl:] = x[self.owner] + self.shift
+        v[self.nl:] = v[self.owner]
+
+
+def run_fix_driver(drv, system, xis, dt=None):
+    """drv: eph_b200.host.FixDriver (reference or product).  xis: list of per-step xi [nlocal][3] or None.
+    Returns per-step records."""
+    sync = GhostSync(system)
+    out = []
+    for step, xi in enumerate(xis, start=1):
+        drv.set_step(step)
+        x, v, f = drv.xvf()
+        f[:] = 0.0
+        drv.update(f=f)
+        drv.initial_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(x=x, v=v)
+        if xi is not None:
+            drv.set_xi(xi)
+        drv.post_force()
+        drv.final_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(v=v)
+        drv.end_of_step()
+        x, v, f = drv.xvf()
+        out.append(dict(x=x[: sync.nl].copy(), v=v[: sync.nl].copy(), f=f[: sync.nl].copy(), array=drv.array().copy(),
+                        T=drv.grid_T().copy(), Ee=drv.compute_vector(0), Tmean=drv.compute_vector(1),
+                        w=drv.probe(1).copy(), rho=drv.probe(0).copy()))
+    return out
+
+
+def system_from_golden(g):
+    """Rebuild the harness system dict (incl. the neighbour list) from a golden file's stored inputs."""
+    from eph_b200 import harness as H
+    nl, ng = int(g["nlocal"]), int(g["nghost"])
+    x = np.ascontiguousarray(g["x"])
+    offsets, neigh = H.neighbor_list(x, nl, 7.0)
+    return dict(n=int(g["n"]), natoms=nl, box=np.asarray(g["box"]), nlocal=nl, nghost=ng, x=x, v=np.ascontiguousarray(g["v"]),
+                f=np.zeros_like(x), type=np.ascontiguousarray(g["type"]), mask=np.ascontiguousarray(g["mask"]),
+                tag=np.ascontiguousarray(g["tag"]), ghost_owner=np.ascontiguousarray(g["ghost_owner"]), offsets=offsets,
+                neigh=neigh, ntypes=int(np.max(g["type"])))
+
+
+def run_oracle(fix, system, xis, mass):
+    """fix: oracle.oracle.Fix.  Same step sequence as run_fix_driver."""
+    sync = GhostSync(system)
+    nl = sync.nl
+    out = []
+    for xi in xis:
+        fix.f[:] = 0.0
+        fix.initial_integrate(mass)
+        sync(fix.x, fix.v)
+        fix.post_force(xi)
+        fix.final_integrate(mass)
+        sync(fix.x, fix.v)
+        fix.end_of_step()
+        out.append(dict(x=fix.x[:nl].copy(), v=fix.v[:nl].copy(), f=fix.f[:nl].copy(), array=np.array(fix.ptr(5)),
+                        T=np.array(fix.fdm.field(0)), Ee=fix.Ee(), Tmean=fix.fdm.T_total(), w=np.array(fix.ptr(1)),
+                        rho=np.array(fix.ptr(0)), f_eph=np.array(fix.ptr(3)), f_rng=np.array(fix.ptr(4))))
+    return out
+
+
+def run_engine(eng, system, xis, mass, dt, device=False, ftm2v=1.0 / 1.0364269e-4):
+    """eng: eph_b200.lib.Engine with tables/grid/dt/atoms/neighbours set.  Drives the C ABI directly, with
+    host (numpy) or device (torch) arrays.  `mass` is per type (1-based list without the leading slot)."""
+    sync = GhostSync(system)
+    nl = sync.nl
+    m = np.concatenate([[0.0], np.atleast_1d(mass)])
+    x = np.ascontiguousarray(system["x"], dtype=np.float64).copy()
+    v = np.ascontiguousarray(system["v"], dtype=np.float64).copy()
+    f = np.zeros((nl, 3))
+    if device:
+        import torch
+        dev = torch.device("cuda", 0)
+        owner = torch.as_tensor(sync.owner, device=dev, dtype=torch.long)
+        shift = torch.as_tensor(sync.shift, device=dev)
+        x, v, f = (torch.as_tensor(t, device=dev) for t in (x, v, f))
+
+        def gsync():
+            x[nl:] = x[owner] + shift
+            v[nl:] = v[owner]
+    else:
+        def gsync():
+            sync(x, v)
+    out = []
+    Ee = 0.0
+    for step, xi in enumerate(xis, start=1):
+        f[...] = 0.0
+        eng.initial_integrate(x, v, f, m, dt, 0.5 * dt * ftm2v)
+        gsync()
+        xi_arg = xi
+        if device and xi is not None:
+            import torch
+            xi_arg = torch.as_tensor(np.ascontiguousarray(xi), device=x.device)
+        eng.post_force(x, v, f, xi_arg, step)
+        eng.final_integrate(v, f, m, 0.5 * dt * ftm2v)
+        gsync()
+        Ee += eng.end_of_step(x, v)
+        tonp = (lambda t: t.cpu().numpy()) if device else (lambda t: t.copy())
+        out.append(dict(x=tonp(x[:nl]), v=tonp(v[:nl]), f=tonp(f[:nl]), array=eng.peratom(), T=eng.get_grid(0), Ee=Ee,
+                        Tmean=eng.mean_T(), w=eng.probe(1), rho=eng.probe(0), f_eph=eng.probe(3), f_rng=eng.probe(4),
+                        xi=eng.probe(2)))
+    return out

@@ -57,6 +57,14 @@ struct eph_b200_handle {
   std::string err;
   long long launches = 0;
 
+  // optional per-kernel timing with CUDA events on the launch stream
+  bool profiling = false;
+  struct KernelStat { const char *name; double ms = 0; long long count = 0; };
+  std::vector<KernelStat> kstats;
+  struct Pending { int stat; cudaEvent_t beg, end; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+
   // tables
   int n_el = 0, n_rho = 0, n_beta = 0;
   double inv_dr_sq = 0, inv_drho = 0, rc2 = 0, rho_cut = 0;
@@ -124,6 +132,59 @@ int fail(eph_b200_handle *h, int code, const char *fmt, ...) {
   va_end(ap);
   if (h) h->err = buf;
   return code;
+}
+
+int stat_index(eph_b200_handle *h, const char *name) {
+  for (size_t i = 0; i < h->kstats.size(); ++i)
+    if (std::strcmp(h->kstats[i].name, name) == 0) return (int)i;
+  eph_b200_handle::KernelStat st;
+  st.name = name;
+  h->kstats.push_back(st);
+  return (int)h->kstats.size() - 1;
+}
+
+cudaEvent_t take_event(eph_b200_handle *h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// RAII bracket around one kernel launch: two events on the launch stream when profiling is on
+struct KernelTimer {
+  eph_b200_handle *h;
+  int idx = -1;
+  cudaEvent_t beg = nullptr;
+  KernelTimer(eph_b200_handle *h_, const char *name) : h(h_) {
+    if (!h->profiling) return;
+    idx = stat_index(h, name);
+    beg = take_event(h);
+    cudaEventRecord(beg, h->stream);
+  }
+  ~KernelTimer() {
+    if (idx < 0) return;
+    cudaEvent_t end = take_event(h);
+    cudaEventRecord(end, h->stream);
+    h->pending.push_back({idx, beg, end});
+  }
+};
+
+void drain_timers(eph_b200_handle *h) {
+  for (auto &p : h->pending) {
+    cudaEventSynchronize(p.end);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.beg, p.end) == cudaSuccess) {
+      h->kstats[p.stat].ms += ms;
+      h->kstats[p.stat].count += 1;
+    }
+    h->event_pool.push_back(p.beg);
+    h->event_pool.push_back(p.end);
+  }
+  h->pending.clear();
 }
 
 #define EPH_CUDA(h, call)                                                                                \
@@ -240,10 +301,35 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
   h->d_scal.release(); h->d_mm.release(); h->d_status.release();
+  drain_timers(h);
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return EPH_B200_OK;
+}
+
+int eph_b200_set_profiling(eph_b200_handle *h, int on) {
+  if (!h) return EPH_B200_ERR_ARG;
+  drain_timers(h);
+  h->profiling = on != 0;
+  if (on) for (auto &k : h->kstats) { k.ms = 0; k.count = 0; }
+  return EPH_B200_OK;
+}
+
+int eph_b200_kernel_times(eph_b200_handle *h, int max, const char **names, double *ms, long long *counts) {
+  if (!h) return EPH_B200_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  drain_timers(h);
+  int n = 0;
+  for (auto &k : h->kstats) {
+    if (n >= max) break;
+    if (names) names[n] = k.name;
+    if (ms) ms[n] = k.ms;
+    if (counts) counts[n] = k.count;
+    ++n;
+  }
+  return n;
 }
 
 int eph_b200_synchronize(eph_b200_handle *h) {
@@ -499,6 +585,7 @@ int resident_grid(eph_b200_handle *h, K kernel, int threads, size_t smem) {
 template <int LANES, bool SMEM, bool MULTI>
 int launch_sweeps(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem) {
   const int threads = 256;
+  KernelTimer kt(h, which == 0 ? "rho_sweep" : which == 1 ? "w_rng_sweep" : "friction_sweep");
   if (which == 0) {
     auto k = rho_sweep_kernel<LANES, SMEM>;
     if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -595,8 +682,11 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
     if ((rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &dxi))) return rc;
   }
 
-  pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
-                                                                 h->cfg.groupbit, h->pos4.p, h->v4.p);
+  {
+    KernelTimer kt(h, "pack_atoms");
+    pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
+                                                                   h->cfg.groupbit, h->pos4.p, h->v4.p);
+  }
   EPH_LAUNCH_CHECK(h);
 
   SweepArgs a = sweep_args(h);
@@ -607,21 +697,30 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
   p.xi_inject = dxi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
   p.seed = h->cfg.seed; p.step = (unsigned long long)ntimestep; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
   p.rho = h->rho.p; p.s = h->s.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.xi = h->xi.p; p.status = h->d_status.p;
-  prep_coupling_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(p);
+  {
+    KernelTimer kt(h, "prep_coupling");
+    prep_coupling_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(p);
+  }
   EPH_LAUNCH_CHECK(h);
 
   if (h->cfg.model == EPH_B200_MODEL_PRL) {
     if ((rc = launch_sweep(h, a, 1))) return rc;
     if (a.do_friction) {
       if (h->nghost > 0 && h->has_owner) {
-        ghost_fill4_kernel<<<blocks_for(h->nghost, 256), 256, 0, h->stream>>>(nl, h->nghost, h->owner.p, h->u4.p);
+        {
+          KernelTimer kt(h, "ghost_fill_u");
+          ghost_fill4_kernel<<<blocks_for(h->nghost, 256), 256, 0, h->stream>>>(nl, h->nghost, h->owner.p, h->u4.p);
+        }
         EPH_LAUNCH_CHECK(h);
       }
       if ((rc = launch_sweep(h, a, 2))) return rc;
     }
   }
   if (add_fric || add_rand) {
-    add_forces_kernel<<<blocks_for(3LL * nl, 256), 256, 0, h->stream>>>(3 * nl, df, h->f_eph.p, h->f_rng.p, add_fric, add_rand);
+    {
+      KernelTimer kt(h, "add_forces");
+      add_forces_kernel<<<blocks_for(3LL * nl, 256), 256, 0, h->stream>>>(3 * nl, df, h->f_eph.p, h->f_rng.p, add_fric, add_rand);
+    }
     EPH_LAUNCH_CHECK(h);
     if (memspace != EPH_B200_DEVICE) {
       EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -685,7 +784,10 @@ int grid_solve(eph_b200_handle *h) {
   for (unsigned int s = 0; s < new_steps; ++s) {
     g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
     g.clear_source = (s + 1 == new_steps) ? 1 : 0;
-    fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+    {
+      KernelTimer kt(h, "fdm_substep");
+      fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+    }
     EPH_LAUNCH_CHECK(h);
     h->cur = 1 - h->cur;
   }
@@ -717,7 +819,10 @@ int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, d
     d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
     d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
     d.grid = grid_geom(h); d.dT_e = h->dT_e.p; d.E_sum = h->d_scal.p; d.array8 = h->array8.p;
-    deposit_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(d);
+    {
+      KernelTimer kt(h, "deposit");
+      deposit_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(d);
+    }
     EPH_LAUNCH_CHECK(h);
   }
   if (h->cfg.flags & EPH_B200_FDM) {

@@ -52,6 +52,8 @@ SYMBOLS = {
     "eph_b200_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "eph_b200_pack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "eph_b200_unpack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "eph_b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "eph_b200_kernel_times": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_double_p, C.POINTER(C.c_longlong)]),
     "eph_b200_synchronize": (C.c_int, [C.c_void_p]),
     "eph_b200_launch_count": (C.c_longlong, [C.c_void_p]),
     "eph_b200_status_word": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint)]),
@@ -230,6 +232,17 @@ class Engine:
         out = np.empty(n, dtype=np.float64)
         self._check(self.lib.eph_b200_get_probe(self.h, which, out.ctypes.data))
         return out if which == 0 else out.reshape(-1, 3)
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.eph_b200_set_profiling(self.h, int(on)))
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} measured with CUDA events on the launch stream since set_profiling(True)"""
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        cnt = (C.c_longlong * 32)()
+        n = self.lib.eph_b200_kernel_times(self.h, 32, names, ms, cnt)
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(n)}
 
     def synchronize(self):
         self._check(self.lib.eph_b200_synchronize(self.h))
