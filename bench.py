@@ -225,7 +225,11 @@ def run_b200(a):
     n_nb = float(s["offsets"][-1]) / nl
     box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated stream shared by torch and the engine, so torch's CUDA events bracket the engine's kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     eng = lib.Engine([0], flags=7, seed=12345, device=local, stream=stream)
     eng.set_tables_from(host.BetaTables(path=BETA_FILE))
     eng.set_grid(a.grid, a.grid, a.grid, box, 300.0, 1.0, 3.5e-6, 0.1248)

@@ -114,14 +114,15 @@ def test_engine_multi_element_and_group(synth_beta_4):
 
 def test_rho_above_cutoff_gives_zero_coupling(tmp_path):
     """the `beta set to zero` branch (eph_beta.h:174-180; reference deck Tests/EPH_Beta_zero)"""
-    knots = H.synthetic_knots(1, n_beta=41, drho=0.01)      # rho_cutoff = 0.4, below the lattice's site density
+    knots = H.synthetic_knots(1, n_beta=11, drho=0.01)      # rho_cutoff = 0.1, inside the lattice's site-density spread
     p = str(H.write_beta_file(tmp_path / "low.beta", knots))
     s = H.make_system(4, sigma=0.08)
     xi = [np.random.default_rng(33).normal(size=(s["nlocal"], 3))]
     ob = O.Beta(path=p)
     fx = O.Fix(s, ob, O.FDM(1, 1, 1, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
     refs = traj.run_oracle(fx, s, xi, [58.71])
-    assert (refs[0]["rho"][: s["nlocal"]] > ob.rho_cutoff).any()
+    above = refs[0]["rho"][: s["nlocal"]] > ob.rho_cutoff
+    assert above.any() and not above.all()
     eng = make_engine(p, 7, (1, 1, 1), box6(s))
     attach(eng, s)
     compare(traj.run_engine(eng, s, xi, [58.71], 1e-4), refs, s["nlocal"])
