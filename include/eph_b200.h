@@ -113,6 +113,14 @@ int eph_b200_last_substeps(eph_b200_handle *h, int *out);
 /* Replaces FixEPH::reset_dt and EPH_FDM::set_dt (fix_eph.cpp:909-916, eph_fdm.h:155-158) */
 int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz);
 
+/* LAMMPS' neighbor->skin and the skin of the device-side inner list (two-level Verlet list: the sweeps walk a
+ * list cut at r_c + inner_skin that the device rebuilds from LAMMPS' list; a device-side displacement check falls
+ * back to LAMMPS' list whenever the inner one could be incomplete, so results never depend on this setting).
+ * inner_skin = 0 disables the inner list, negative keeps the current value (default 0.4 A, or EPH_B200_INNER_SKIN). */
+int eph_b200_set_skin(eph_b200_handle *h, double skin, double inner_skin);
+/* how often the inner list was (re)built and how many steps saw it invalidated */
+int eph_b200_list_stats(eph_b200_handle *h, long long *inner_builds, long long *fallback_steps);
+
 /* Per-atom data that only changes when LAMMPS re-neighbours (atom->type, mask, tag
  * for nlocal+nghost atoms) and the ghost->owner map of a single-rank periodic
  * run (what Comm::forward_comm(Fix*) would realise through

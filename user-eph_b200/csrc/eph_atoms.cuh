@@ -7,17 +7,49 @@
 
 namespace ephb {
 
-// x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits}, v4 {vx,vy,vz,0}
-__global__ void pack_atoms_kernel(int ntotal, const double *__restrict__ x, const double *__restrict__ v,
+// Device-side bookkeeping of the two-level Verlet list (see eph_sweeps.cuh).
+struct ListState {
+  unsigned inner_invalid;   // != 0: the inner list must not be used (some atom moved more than inner_skin/2)
+  unsigned pad;
+  unsigned long long disp0_sq_bits;  // max squared displacement since LAMMPS built its list (double bits, >= 0)
+};
+
+// x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits}, v4 {vx,vy,vz,0}; with track != 0 also the displacement
+// checks that guard the inner list: against xref (positions when the inner list was built) and against xref0
+// (positions when LAMMPS built its list).
+__global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const double *__restrict__ x, const double *__restrict__ v,
                                   const int *__restrict__ type, const int *__restrict__ mask,
                                   const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
-                                  double4 *__restrict__ v4) {
-  int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= ntotal) return;
-  unsigned bits = static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask;
-  if (mask[a] & groupbit) bits |= kBitGroup;
-  pos4[a] = make_double4(x[3 * (size_t)a], x[3 * (size_t)a + 1], x[3 * (size_t)a + 2], bits_to_double(bits));
-  v4[a] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+                                  double4 *__restrict__ v4, int track, const double4 *__restrict__ xref,
+                                  const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st) {
+  __shared__ double s_max[8];
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  double d0 = 0.0;
+  if (a < ntotal) {
+    unsigned bits = static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask;
+    if (mask[a] & groupbit) bits |= kBitGroup;
+    const double px = x[3 * (size_t)a], py = x[3 * (size_t)a + 1], pz = x[3 * (size_t)a + 2];
+    pos4[a] = make_double4(px, py, pz, bits_to_double(bits));
+    v4[a] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+    if (track) {
+      const double4 r = xref[a], r0 = xref0[a];
+      const double dx = px - r.x, dy = py - r.y, dz = pz - r.z;
+      if (dx * dx + dy * dy + dz * dz > half_skin_sq) st->inner_invalid = 1u;
+      const double ex = px - r0.x, ey = py - r0.y, ez = pz - r0.z;
+      d0 = ex * ex + ey * ey + ez * ez;
+    }
+  }
+  if (track) {  // block-wide max of the displacement since LAMMPS' build, one atomic per block
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d0 = fmax(d0, __shfl_xor_sync(0xFFFFFFFFu, d0, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = d0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = s_max[0];
+      for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, s_max[k]);
+      atomicMax(&st->disp0_sq_bits, (unsigned long long)__double_as_longlong(m));
+    }
+  }
 }
 
 struct PrepArgs {
@@ -36,6 +68,10 @@ struct PrepArgs {
   double4 *__restrict__ z4;    // [ntotal] s * xi
   double *__restrict__ xi;     // [nlocal][3] probe copy
   unsigned *__restrict__ status;
+  // the step that (re)built the inner list validates it here (stream order: after the rho sweep)
+  int built_inner;
+  double skin, inner_skin;
+  ListState *__restrict__ list_state;
 };
 
 // After the rho sweep: ghost rho (forward comm RHO, fix_eph.cpp:870-871),
@@ -44,6 +80,12 @@ struct PrepArgs {
 __global__ void prep_coupling_kernel(PrepArgs p) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.ntotal) return;
+  if (a == 0 && p.built_inner) {
+    // an inner list built now from LAMMPS' list is complete only if r_c + inner_skin + 2 D <= r_c + skin,
+    // D = largest displacement since LAMMPS built its list
+    const double d0 = sqrt(__longlong_as_double((long long)p.list_state->disp0_sq_bits));
+    p.list_state->inner_invalid = (2.0 * d0 + p.inner_skin <= p.skin) ? 0u : 1u;
+  }
   const int src = (a < p.nlocal || p.owner == nullptr) ? a : p.owner[a - p.nlocal];
   double rho = p.rho[src];
   if (a >= p.nlocal) p.rho[a] = rho;

@@ -98,6 +98,22 @@ struct eph_b200_handle {
   const long long *off_ptr = nullptr;  // device pointers actually used (own or caller's)
   const int *neigh_ptr = nullptr;
 
+  // two-level Verlet list: inner list with a small skin, rebuilt on the device from LAMMPS' list
+  DevBuf<int> ineigh, icount;
+  DevBuf<double4> xref, xref0;          // positions at the last inner build / at LAMMPS' build
+  DevBuf<ListState> lstate;
+  double skin = -1.0;                    // LAMMPS' neighbor->skin (unknown: inner list only valid from LAMMPS' build)
+  double inner_skin = 0.4;
+  bool inner_enabled = true;
+  bool fresh_neighbors = false;          // set_neighbors since the last post_force
+  bool have_inner = false;               // an inner list (and xref) exists
+  bool inner_gave_up = false;            // rebuild was refused by the device-side check: use LAMMPS' list until it changes
+  bool rebuilt_last_step = false;
+  unsigned *h_flag = nullptr;            // pinned mirror of lstate.inner_invalid
+  cudaEvent_t flag_event = nullptr;
+  bool flag_pending = false;
+  long long inner_builds = 0, inner_fallback_steps = 0;
+
   // grid
   int nx = 0, ny = 0, nz = 0, steps = 1;
   long long ncell = 0;
@@ -262,6 +278,10 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
   h->cfg = *cfg;
   h->type_map.assign(cfg->type_map, cfg->type_map + cfg->ntypes);
   h->cfg.type_map = h->type_map.data();
+  if (const char *e = std::getenv("EPH_B200_INNER_SKIN")) {
+    h->inner_skin = std::atof(e);
+    h->inner_enabled = h->inner_skin > 0.0;
+  }
   h->sm_count = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cfg->stream) h->stream = static_cast<cudaStream_t>(cfg->stream);
@@ -274,6 +294,9 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
     h->own_stream = true;
   }
   bool ok = h->d_type_map.reserve(cfg->ntypes) == cudaSuccess && h->d_scal.reserve(8) == cudaSuccess &&
+            h->lstate.reserve(1) == cudaSuccess && cudaMemset(h->lstate.p, 0, sizeof(ListState)) == cudaSuccess &&
+            cudaMallocHost(&h->h_flag, sizeof(unsigned)) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->flag_event, cudaEventDisableTiming) == cudaSuccess &&
             h->d_mm.reserve(4) == cudaSuccess && h->d_status.reserve(1) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 8 * sizeof(double)) == cudaSuccess &&
             cudaMemcpy(h->d_type_map.p, h->type_map.data(), cfg->ntypes * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -303,6 +326,9 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->d_scal.release(); h->d_mm.release(); h->d_status.release();
   drain_timers(h);
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  h->ineigh.release(); h->icount.release(); h->xref.release(); h->xref0.release(); h->lstate.release();
+  if (h->h_flag) cudaFreeHost(h->h_flag);
+  if (h->flag_event) cudaEventDestroy(h->flag_event);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -484,6 +510,24 @@ int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz) {
   return EPH_B200_OK;
 }
 
+int eph_b200_set_skin(eph_b200_handle *h, double skin, double inner_skin) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (skin < 0.0) return fail(h, EPH_B200_ERR_ARG, "set_skin: negative skin");
+  h->skin = skin;
+  if (inner_skin >= 0.0) h->inner_skin = inner_skin;   // negative: keep the current setting
+  h->inner_enabled = h->inner_skin > 0.0 && h->inner_skin <= skin;
+  h->have_inner = false;
+  h->fresh_neighbors = h->neigh_set;   // rebuild the inner list at the next post_force
+  return EPH_B200_OK;
+}
+
+int eph_b200_list_stats(eph_b200_handle *h, long long *inner_builds, long long *fallback_steps) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (inner_builds) *inner_builds = h->inner_builds;
+  if (fallback_steps) *fallback_steps = h->inner_fallback_steps;
+  return EPH_B200_OK;
+}
+
 int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *type, const int *mask,
                        const int64_t *tag, const int *ghost_owner, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
@@ -507,6 +551,8 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   }
   EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->v4.reserve(nt)); EPH_CUDA(h, h->z4.reserve(nt)); EPH_CUDA(h, h->u4.reserve(nt));
   EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->s.reserve(nt));
+  EPH_CUDA(h, h->xref.reserve(nt)); EPH_CUDA(h, h->xref0.reserve(nt)); EPH_CUDA(h, h->icount.reserve(std::max<size_t>(nlocal, 1)));
+  h->have_inner = false;
   const size_t nl = std::max<size_t>(nlocal, 1);
   EPH_CUDA(h, h->w.reserve(3 * nl)); EPH_CUDA(h, h->xi.reserve(3 * nl)); EPH_CUDA(h, h->f_eph.reserve(3 * nl));
   EPH_CUDA(h, h->f_rng.reserve(3 * nl)); EPH_CUDA(h, h->array8.reserve(8 * nl)); EPH_CUDA(h, h->ccount.reserve(nl));
@@ -551,6 +597,12 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
   EPH_CUDA(h, h->cneigh.reserve((size_t)std::max<long long>(total, 1)));
+  if (h->inner_enabled) EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(total, 1)));
+  EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
+  h->fresh_neighbors = true;
+  h->have_inner = false;
+  h->inner_gave_up = false;
+  h->flag_pending = false;
   h->n_entries = total;
   h->neigh_set = true;
   return EPH_B200_OK;
@@ -582,64 +634,77 @@ int resident_grid(eph_b200_handle *h, K kernel, int threads, size_t smem) {
   return h->sm_count * per_sm;  // persistent CTAs: exactly one resident wave
 }
 
-template <int LANES, bool SMEM, bool MULTI>
-int launch_sweeps(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem) {
+template <int LANES, int TAB, bool MULTI>
+int launch_sweeps(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, bool build) {
   const int threads = 256;
-  KernelTimer kt(h, which == 0 ? "rho_sweep" : which == 1 ? "w_rng_sweep" : "friction_sweep");
-  if (which == 0) {
-    auto k = rho_sweep_kernel<LANES, SMEM>;
-    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  KernelTimer kt(h, which == 0 ? (build ? "rho_sweep_build" : "rho_sweep") : which == 1 ? "w_rng_sweep" : "friction_sweep");
+  if (which == 0 && build) {
+    auto k = rho_sweep_kernel<LANES, TAB, true>;
+    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
+  } else if (which == 0) {
+    auto k = rho_sweep_kernel<LANES, TAB, false>;
+    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   } else if (which == 1) {
-    auto k = w_rng_sweep_kernel<LANES, SMEM, MULTI>;
-    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto k = w_rng_sweep_kernel<LANES, TAB, MULTI>;
+    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   } else {
-    auto k = friction_sweep_kernel<LANES, SMEM, MULTI>;
-    if (SMEM) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto k = friction_sweep_kernel<LANES, TAB, MULTI>;
+    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   }
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
 
-int env_lanes(const char *name, int dflt) {
+int env_int(const char *name, int dflt) {
   const char *e = std::getenv(name);
-  if (!e) return dflt;
-  int v = std::atoi(e);
+  return e ? std::atoi(e) : dflt;
+}
+
+int env_lanes(const char *name, int dflt) {
+  int v = env_int(name, dflt);
   return (v == 8 || v == 16 || v == 32) ? v : dflt;
 }
 
-template <bool SMEM, bool MULTI>
-int launch_sweep_lanes(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, int lanes) {
+template <int TAB, bool MULTI>
+int launch_sweep_lanes(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, int lanes, bool build) {
   switch (lanes) {
-    case 8: return launch_sweeps<8, SMEM, MULTI>(h, a, which, smem);
-    case 16: return launch_sweeps<16, SMEM, MULTI>(h, a, which, smem);
-    default: return launch_sweeps<32, SMEM, MULTI>(h, a, which, smem);
+    case 8: return launch_sweeps<8, TAB, MULTI>(h, a, which, smem, build);
+    case 16: return launch_sweeps<16, TAB, MULTI>(h, a, which, smem, build);
+    default: return launch_sweeps<32, TAB, MULTI>(h, a, which, smem, build);
   }
 }
 
-int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which) {
-  // the rho(r^2) tables of all elements live in shared memory when they fit
+int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false) {
+  // rho(r^2) tables of all elements: staged in shared memory when they fit (EPH_B200_TABLE=1), or read with
+  // 256-bit loads through L1 (EPH_B200_TABLE=0)
   const size_t table_bytes = (size_t)a.n_elements * a.n_rho * 2 * sizeof(double2);
-  const bool smem = table_bytes <= (size_t)h->max_smem_optin - 1024;
+  static const int table_mode = env_int("EPH_B200_TABLE", 1);
+  const bool smem = table_mode == 1 && table_bytes <= (size_t)h->max_smem_optin - 1024;
   const bool multi = a.n_elements > 1;
   static const int lanes_rho = env_lanes("EPH_B200_LANES_RHO", 32);
   static const int lanes_pair = env_lanes("EPH_B200_LANES_PAIR", 16);
   const int lanes = which == 0 ? lanes_rho : lanes_pair;
   if (smem) {
-    if (multi) return launch_sweep_lanes<true, true>(h, a, which, table_bytes, lanes);
-    return launch_sweep_lanes<true, false>(h, a, which, table_bytes, lanes);
+    if (multi) return launch_sweep_lanes<1, true>(h, a, which, table_bytes, lanes, build);
+    return launch_sweep_lanes<1, false>(h, a, which, table_bytes, lanes, build);
   }
-  if (multi) return launch_sweep_lanes<false, true>(h, a, which, 0, lanes);
-  return launch_sweep_lanes<false, false>(h, a, which, 0, lanes);
+  if (multi) return launch_sweep_lanes<0, true>(h, a, which, 0, lanes, build);
+  return launch_sweep_lanes<0, false>(h, a, which, 0, lanes, build);
 }
 
 SweepArgs sweep_args(eph_b200_handle *h) {
   SweepArgs a{};
   a.nlocal = h->nlocal; a.n_elements = h->n_el; a.n_rho = h->n_rho;
-  a.inv_dr_sq = h->inv_dr_sq; a.r_cutoff_sq = h->rc2; a.rho_tab = h->rho_tab.p;
+  a.inv_dr_sq = h->inv_dr_sq; a.r_cutoff_sq = h->rc2; a.rho_tab4 = reinterpret_cast<const double4 *>(h->rho_tab.p);
+  const double r_in = std::sqrt(h->rc2) + h->inner_skin;
+  a.r_inner_sq = r_in * r_in;
   a.offsets = h->off_ptr; a.neigh = h->neigh_ptr; a.cneigh = h->cneigh.p; a.ccount = h->ccount.p;
+  a.ineigh = h->ineigh.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
+  a.use_inner = 0;
   a.pos4 = h->pos4.p; a.v4 = h->v4.p; a.z4 = h->z4.p; a.u4 = h->u4.p; a.s = h->s.p; a.rho = h->rho.p;
   a.w = h->w.p; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
   a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
@@ -682,26 +747,59 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
     if ((rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &dxi))) return rc;
   }
 
+  // ---- two-level list policy (host side; correctness is guarded by the device flag, not by this) ----
+  bool build = false;
+  if (h->inner_enabled) {
+    if (h->flag_pending && cudaEventQuery(h->flag_event) == cudaSuccess) {
+      h->flag_pending = false;
+      if (*h->h_flag != 0u) {
+        if (h->rebuilt_last_step) h->inner_gave_up = true;   // the device refused the rebuilt list: stop trying
+        else build = !h->inner_gave_up;
+        ++h->inner_fallback_steps;
+      }
+    }
+    if (h->fresh_neighbors) build = true;
+  }
+  const bool track = h->inner_enabled && h->have_inner;
   {
     KernelTimer kt(h, "pack_atoms");
+    const double half = 0.5 * h->inner_skin;
     pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
-                                                                   h->cfg.groupbit, h->pos4.p, h->v4.p);
+                                                                   h->cfg.groupbit, h->pos4.p, h->v4.p, track ? 1 : 0,
+                                                                   h->xref.p, h->xref0.p, half * half, h->lstate.p);
   }
   EPH_LAUNCH_CHECK(h);
 
   SweepArgs a = sweep_args(h);
-  if ((rc = launch_sweep(h, a, 0))) return rc;
+  a.use_inner = (h->inner_enabled && h->have_inner && !build) ? 1 : 0;
+  if ((rc = launch_sweep(h, a, 0, build))) return rc;
+  if (build) {
+    EPH_CUDA(h, cudaMemcpyAsync(h->xref.p, h->pos4.p, (size_t)nt * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->fresh_neighbors)
+      EPH_CUDA(h, cudaMemcpyAsync(h->xref0.p, h->pos4.p, (size_t)nt * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
+    h->have_inner = true;
+    ++h->inner_builds;
+  }
+  h->rebuilt_last_step = build && !h->fresh_neighbors;
+  h->fresh_neighbors = false;
 
   PrepArgs p{};
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
   p.xi_inject = dxi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
   p.seed = h->cfg.seed; p.step = (unsigned long long)ntimestep; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
   p.rho = h->rho.p; p.s = h->s.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.xi = h->xi.p; p.status = h->d_status.p;
+  p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
+  p.list_state = h->lstate.p;
   {
     KernelTimer kt(h, "prep_coupling");
     prep_coupling_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(p);
   }
   EPH_LAUNCH_CHECK(h);
+  if (h->inner_enabled && !h->flag_pending) {
+    EPH_CUDA(h, cudaMemcpyAsync(h->h_flag, &h->lstate.p->inner_invalid, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaEventRecord(h->flag_event, h->stream));
+    h->flag_pending = true;
+  }
 
   if (h->cfg.model == EPH_B200_MODEL_PRL) {
     if ((rc = launch_sweep(h, a, 1))) return rc;

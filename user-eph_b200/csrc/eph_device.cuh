@@ -19,6 +19,14 @@ __device__ __forceinline__ double bits_to_double(unsigned lo) {
 }
 __device__ __forceinline__ unsigned double_to_bits(double w) { return static_cast<unsigned>(__double2loint(w)); }
 
+// One 256-bit load (LDG.E.256 on sm_100a) of a 32-byte record through the
+// read-only path: a gathered record costs one L1TEX request instead of two.
+__device__ __forceinline__ double4 ld256(const double4 *p) {
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
 // Sub-warp groups: LANES consecutive lanes cooperate on one atom.
 template <int LANES>
 __device__ __forceinline__ constexpr unsigned lanes_bits() {

@@ -40,6 +40,8 @@ SYMBOLS = {
     "eph_b200_mean_T": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_last_substeps": (C.c_int, [C.c_void_p, c_int_p]),
     "eph_b200_set_dt": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_set_skin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_list_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "eph_b200_set_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_neighbors_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_neighbors_lammps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -188,6 +190,14 @@ class Engine:
 
     def set_dt(self, dt, boltz=8.617343e-5):
         self._check(self.lib.eph_b200_set_dt(self.h, dt, boltz))
+
+    def set_skin(self, skin, inner_skin=-1.0):
+        self._check(self.lib.eph_b200_set_skin(self.h, skin, inner_skin))
+
+    def list_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._check(self.lib.eph_b200_list_stats(self.h, C.byref(a), C.byref(b)))
+        return {"inner_builds": a.value, "fallback_steps": b.value}
 
     def set_atoms(self, nlocal, nghost, type, mask, tag=None, ghost_owner=None):
         ps = [_ptr(type), _ptr(mask), _ptr(tag), _ptr(ghost_owner)]

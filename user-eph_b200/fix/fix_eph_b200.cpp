@@ -169,6 +169,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
                                    grid.E_e_T.y.data()),
           "set_grid_tables");
   check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
+  check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
 
   array = nullptr;
   list = nullptr;
