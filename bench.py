@@ -277,7 +277,9 @@ def run_b200(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    alg = {"rho_sweep": 36 + 4 * n_nb, "w_rng_sweep": 84 + 4 * n_nb, "friction_sweep": 180 + 4 * n_nb}
+    # rho sweep 36+4N, w sweep 84+4N, f sweep 180+4N bytes per atom.  density_sweep does the work of the
+    # reference's rho AND w sweeps, force_sweep that of its f sweep (friction + random).
+    alg = {"density_sweep": (36 + 4 * n_nb) + (84 + 4 * n_nb), "force_sweep": 180 + 4 * n_nb}
     per_kernel = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in ktimes.items()}
     dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["ms_avg"], default=None)
     roofline = None

@@ -8,9 +8,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cells = sys.argv[1] if len(sys.argv) > 1 else "64"
-variants = []
-for table, inner, lr, lp in itertools.product(["1", "0"], ["0.4", "0"], ["32", "16"], ["16", "8", "32"]):
-    variants.append(dict(EPH_B200_TABLE=table, EPH_B200_INNER_SKIN=inner, EPH_B200_LANES_RHO=lr, EPH_B200_LANES_PAIR=lp))
+variants = [
+    dict(),
+    dict(EPH_B200_LANES_DENSITY="4", EPH_B200_LANES_FORCE="4"),
+    dict(EPH_B200_LANES_DENSITY="16", EPH_B200_LANES_FORCE="8"),
+    dict(EPH_B200_LANES_DENSITY="8", EPH_B200_LANES_FORCE="4"),
+    dict(EPH_B200_LANES_DENSITY="8", EPH_B200_LANES_FORCE="16"),
+    dict(EPH_B200_TABLE="0"),
+    dict(EPH_B200_INNER_SKIN="0"),
+    dict(EPH_B200_INNER_SKIN="0.3"),
+]
 if len(sys.argv) > 2:
     variants = variants[: int(sys.argv[2])]
 for v in variants:

@@ -63,9 +63,12 @@ struct PrepArgs {
   unsigned long long seed, step;
   int do_random;
   double *__restrict__ rho;    // [ntotal]; ghost entries are filled here
-  double *__restrict__ s;      // [ntotal]
+  const double4 *__restrict__ W4;  // [nlocal] (or [ntotal] after an exchange) pair sums of the density pass
+  int ghost_W_present;         // ghosts' W4 entries were filled by an exchange (multi-rank)
   double4 *__restrict__ pos4;  // validity bit is set here
   double4 *__restrict__ z4;    // [ntotal] s * xi
+  double4 *__restrict__ u4;    // [ntotal] s * w
+  double *__restrict__ w;      // [nlocal][3] w_i (probe / forward-comm payload)
   double *__restrict__ xi;     // [nlocal][3] probe copy
   unsigned *__restrict__ status;
   // the step that (re)built the inner list validates it here (stream order: after the rho sweep)
@@ -74,9 +77,10 @@ struct PrepArgs {
   ListState *__restrict__ list_state;
 };
 
-// After the rho sweep: ghost rho (forward comm RHO, fix_eph.cpp:870-871),
-// s = alpha(rho)/rho with alpha = 0 above rho_cutoff (eph_beta.h:186-198),
-// the rho>0 validity bit, xi (fix_eph.cpp:854-865) and z = s*xi.
+// Between the two passes, for locals and ghosts alike: ghost rho and W come from the owner (the reference's
+// forward comms RHO and WI, fix_eph.cpp:870-871, :743-744, as one step), s = alpha(rho)/rho with alpha = 0
+// above rho_cutoff (eph_beta.h:186-198), the rho>0 validity bit, w = s W, u = s w, xi (fix_eph.cpp:854-865)
+// and z = s xi.
 __global__ void prep_coupling_kernel(PrepArgs p) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.ntotal) return;
@@ -89,6 +93,7 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   const int src = (a < p.nlocal || p.owner == nullptr) ? a : p.owner[a - p.nlocal];
   double rho = p.rho[src];
   if (a >= p.nlocal) p.rho[a] = rho;
+  const double4 W = (src < p.nlocal || p.ghost_W_present) ? p.W4[src] : make_double4(0, 0, 0, 0);
   double4 pa = p.pos4[a];
   unsigned bits = double_to_bits(pa.w) & ~kBitValid;
   double s = 0.0;
@@ -101,7 +106,11 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   }
   pa.w = bits_to_double(bits);
   p.pos4[a] = pa;
-  p.s[a] = s;
+  const double wx = s * W.x, wy = s * W.y, wz = s * W.z;   // w_i = alpha_i/rho_i * sum (prescaler of fix_eph.cpp:727)
+  p.u4[a] = make_double4(s * wx, s * wy, s * wz, 0.0);
+  if (a < p.nlocal) {
+    p.w[3 * (size_t)a] = wx; p.w[3 * (size_t)a + 1] = wy; p.w[3 * (size_t)a + 2] = wz;
+  }
   double xi[3] = {0.0, 0.0, 0.0};
   if (p.do_random && (bits & kBitGroup)) {
     if (p.xi_inject) {
@@ -114,24 +123,6 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   if (a < p.nlocal) {
     p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
   }
-}
-
-// forward comm WI (fix_eph.cpp:743-744) for single-rank periodic images
-__global__ void ghost_fill4_kernel(int nlocal, int nghost, const int *__restrict__ owner, double4 *__restrict__ arr) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nghost) return;
-  arr[nlocal + g] = arr[owner[g]];
-}
-
-// f += f_EPH (+ f_RNG) for every local atom, grouped or not (fix_eph.cpp:892-906)
-__global__ void add_forces_kernel(int n3, double *__restrict__ f, const double *__restrict__ f_eph,
-                                  const double *__restrict__ f_rng, int add_friction, int add_random) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n3) return;
-  double v = f[t];
-  if (add_friction) v += f_eph[t];
-  if (add_random) v += f_rng[t];
-  f[t] = v;
 }
 
 struct DepositArgs {

@@ -86,8 +86,8 @@ struct eph_b200_handle {
   DevBuf<double> mass;
 
   // internal per-atom records
-  DevBuf<double4> pos4, v4, z4, u4;
-  DevBuf<double> rho, s, w, xi, f_eph, f_rng, array8;
+  DevBuf<double4> pos4, v4, z4, u4, W4;
+  DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
   bool forces_valid = false;
 
   // neighbours
@@ -318,8 +318,8 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->tag.release();
   h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release();
-  h->pos4.release(); h->v4.release(); h->z4.release(); h->u4.release();
-  h->rho.release(); h->s.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
+  h->pos4.release(); h->v4.release(); h->z4.release(); h->u4.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
+  h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
   h->off.release(); h->neigh.release(); h->cneigh.release(); h->ccount.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -550,7 +550,7 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
     h->has_owner = true;
   }
   EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->v4.reserve(nt)); EPH_CUDA(h, h->z4.reserve(nt)); EPH_CUDA(h, h->u4.reserve(nt));
-  EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->s.reserve(nt));
+  EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->W4.reserve(nt));
   EPH_CUDA(h, h->xref.reserve(nt)); EPH_CUDA(h, h->xref0.reserve(nt)); EPH_CUDA(h, h->icount.reserve(std::max<size_t>(nlocal, 1)));
   h->have_inner = false;
   const size_t nl = std::max<size_t>(nlocal, 1);
@@ -597,6 +597,8 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
   EPH_CUDA(h, h->cneigh.reserve((size_t)std::max<long long>(total, 1)));
+  EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(total, 1)));
+  if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(total, 1)));
   if (h->inner_enabled) EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(total, 1)));
   EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
   h->fresh_neighbors = true;
@@ -635,26 +637,28 @@ int resident_grid(eph_b200_handle *h, K kernel, int threads, size_t smem) {
 }
 
 template <int LANES, int TAB, bool MULTI>
-int launch_sweeps(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, bool build) {
+int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool build) {
   const int threads = 256;
-  KernelTimer kt(h, which == 0 ? (build ? "rho_sweep_build" : "rho_sweep") : which == 1 ? "w_rng_sweep" : "friction_sweep");
-  if (which == 0 && build) {
-    auto k = rho_sweep_kernel<LANES, TAB, true>;
-    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
-  } else if (which == 0) {
-    auto k = rho_sweep_kernel<LANES, TAB, false>;
-    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
-  } else if (which == 1) {
-    auto k = w_rng_sweep_kernel<LANES, TAB, MULTI>;
+  KernelTimer kt(h, build ? "density_sweep_build" : "density_sweep");
+  if (build) {
+    auto k = density_sweep_kernel<LANES, TAB, true, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   } else {
-    auto k = friction_sweep_kernel<LANES, TAB, MULTI>;
+    auto k = density_sweep_kernel<LANES, TAB, false, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   }
+  EPH_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+
+template <int LANES, bool MULTI>
+int launch_force(eph_b200_handle *h, const SweepArgs &a) {
+  const int threads = 256;
+  KernelTimer kt(h, "force_sweep");
+  auto k = force_sweep_kernel<LANES, MULTI>;
+  k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
@@ -666,34 +670,43 @@ int env_int(const char *name, int dflt) {
 
 int env_lanes(const char *name, int dflt) {
   int v = env_int(name, dflt);
-  return (v == 8 || v == 16 || v == 32) ? v : dflt;
+  return (v == 4 || v == 8 || v == 16 || v == 32) ? v : dflt;
 }
 
 template <int TAB, bool MULTI>
-int launch_sweep_lanes(eph_b200_handle *h, const SweepArgs &a, int which, size_t smem, int lanes, bool build) {
+int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, int lanes, bool build) {
   switch (lanes) {
-    case 8: return launch_sweeps<8, TAB, MULTI>(h, a, which, smem, build);
-    case 16: return launch_sweeps<16, TAB, MULTI>(h, a, which, smem, build);
-    default: return launch_sweeps<32, TAB, MULTI>(h, a, which, smem, build);
+    case 4: return launch_density<4, TAB, MULTI>(h, a, smem, build);
+    case 8: return launch_density<8, TAB, MULTI>(h, a, smem, build);
+    case 16: return launch_density<16, TAB, MULTI>(h, a, smem, build);
+    default: return launch_density<32, TAB, MULTI>(h, a, smem, build);
   }
 }
 
+// which: 0 density pass (optionally rebuilding the inner list), 1 force pass
 int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false) {
-  // rho(r^2) tables of all elements: staged in shared memory when they fit (EPH_B200_TABLE=1), or read with
-  // 256-bit loads through L1 (EPH_B200_TABLE=0)
+  const bool multi = a.n_elements > 1;
+  static const int lanes_density = env_lanes("EPH_B200_LANES_DENSITY", 8);
+  static const int lanes_force = env_lanes("EPH_B200_LANES_FORCE", 8);
+  if (which == 1) {
+    switch (lanes_force) {
+      case 4: return multi ? launch_force<4, true>(h, a) : launch_force<4, false>(h, a);
+      case 16: return multi ? launch_force<16, true>(h, a) : launch_force<16, false>(h, a);
+      case 32: return multi ? launch_force<32, true>(h, a) : launch_force<32, false>(h, a);
+      default: return multi ? launch_force<8, true>(h, a) : launch_force<8, false>(h, a);
+    }
+  }
+  // rho(r^2) tables of all elements: staged in shared memory when they fit (EPH_B200_TABLE=1, default), or read
+  // with 256-bit loads through L1 (EPH_B200_TABLE=0)
   const size_t table_bytes = (size_t)a.n_elements * a.n_rho * 2 * sizeof(double2);
   static const int table_mode = env_int("EPH_B200_TABLE", 1);
   const bool smem = table_mode == 1 && table_bytes <= (size_t)h->max_smem_optin - 1024;
-  const bool multi = a.n_elements > 1;
-  static const int lanes_rho = env_lanes("EPH_B200_LANES_RHO", 32);
-  static const int lanes_pair = env_lanes("EPH_B200_LANES_PAIR", 16);
-  const int lanes = which == 0 ? lanes_rho : lanes_pair;
   if (smem) {
-    if (multi) return launch_sweep_lanes<1, true>(h, a, which, table_bytes, lanes, build);
-    return launch_sweep_lanes<1, false>(h, a, which, table_bytes, lanes, build);
+    if (multi) return launch_density_lanes<1, true>(h, a, table_bytes, lanes_density, build);
+    return launch_density_lanes<1, false>(h, a, table_bytes, lanes_density, build);
   }
-  if (multi) return launch_sweep_lanes<0, true>(h, a, which, 0, lanes, build);
-  return launch_sweep_lanes<0, false>(h, a, which, 0, lanes, build);
+  if (multi) return launch_density_lanes<0, true>(h, a, 0, lanes_density, build);
+  return launch_density_lanes<0, false>(h, a, 0, lanes_density, build);
 }
 
 SweepArgs sweep_args(eph_b200_handle *h) {
@@ -705,8 +718,9 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   a.offsets = h->off_ptr; a.neigh = h->neigh_ptr; a.cneigh = h->cneigh.p; a.ccount = h->ccount.p;
   a.ineigh = h->ineigh.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
   a.use_inner = 0;
-  a.pos4 = h->pos4.p; a.v4 = h->v4.p; a.z4 = h->z4.p; a.u4 = h->u4.p; a.s = h->s.p; a.rho = h->rho.p;
-  a.w = h->w.p; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
+  a.pos4 = h->pos4.p; a.v4 = h->v4.p; a.z4 = h->z4.p; a.u4 = h->u4.p; a.W4 = h->W4.p; a.rho = h->rho.p;
+  a.gpair = h->gpair.p; a.gpair_i = h->gpair_i.p;
+  a.f = nullptr; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
   a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
   a.grid = grid_geom(h);
   a.eta_factor = h->eta;
@@ -787,7 +801,8 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
   p.xi_inject = dxi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
   p.seed = h->cfg.seed; p.step = (unsigned long long)ntimestep; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
-  p.rho = h->rho.p; p.s = h->s.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.xi = h->xi.p; p.status = h->d_status.p;
+  p.rho = h->rho.p; p.W4 = h->W4.p; p.ghost_W_present = 0; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.u4 = h->u4.p;
+  p.w = h->w.p; p.xi = h->xi.p; p.status = h->d_status.p;
   p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
   p.list_state = h->lstate.p;
   {
@@ -801,26 +816,12 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
     h->flag_pending = true;
   }
 
-  if (h->cfg.model == EPH_B200_MODEL_PRL) {
+  if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
+    a.f = (add_fric || add_rand) ? df : nullptr;
+    a.add_friction = add_fric ? 1 : 0;
+    a.add_random = add_rand ? 1 : 0;
     if ((rc = launch_sweep(h, a, 1))) return rc;
-    if (a.do_friction) {
-      if (h->nghost > 0 && h->has_owner) {
-        {
-          KernelTimer kt(h, "ghost_fill_u");
-          ghost_fill4_kernel<<<blocks_for(h->nghost, 256), 256, 0, h->stream>>>(nl, h->nghost, h->owner.p, h->u4.p);
-        }
-        EPH_LAUNCH_CHECK(h);
-      }
-      if ((rc = launch_sweep(h, a, 2))) return rc;
-    }
-  }
-  if (add_fric || add_rand) {
-    {
-      KernelTimer kt(h, "add_forces");
-      add_forces_kernel<<<blocks_for(3LL * nl, 256), 256, 0, h->stream>>>(3 * nl, df, h->f_eph.p, h->f_rng.p, add_fric, add_rand);
-    }
-    EPH_LAUNCH_CHECK(h);
-    if (memspace != EPH_B200_DEVICE) {
+    if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
       EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       EPH_CUDA(h, cudaStreamSynchronize(h->stream));
     }
