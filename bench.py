@@ -206,66 +206,89 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     from eph_b200 import host, lib
+    from eph_b200 import parallel as P
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != a.gpus:
-        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d" % (a.gpus, world))
-    if world > 1:
-        raise SystemExit("bench.py: the multi-GPU path is not wired yet in this build")
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE %d (launch N > 1 with torch.distributed.run)" % (a.gpus, world))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D = dist if world > 1 else None
 
-    s = build_workload(a.cells)
+    grid = P.brick_grid(world)
+    s = build_workload(a.cells, brick=(rank, grid) if world > 1 else None)
+    if world == 1:
+        s["grid"] = (1, 1, 1)
     nl, ng = s["nlocal"], s["nghost"]
     natoms = s["natoms"]
     n_nb = float(s["offsets"][-1]) / nl
     box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    plan = P.ExchangePlan(s, rank, world, D)
 
     # a dedicated stream shared by torch and the engine, so torch's CUDA events bracket the engine's kernels
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    eng = lib.Engine([0], flags=7, seed=12345, device=local, stream=stream)
+    eng = lib.Engine([0], flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
     eng.set_tables_from(host.BetaTables(path=BETA_FILE))
     eng.set_grid(a.grid, a.grid, a.grid, box, 300.0, 1.0, 3.5e-6, 0.1248)
     eng.set_dt(DT)
+    eng.set_skin(2.0)
     t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
-    d_type, d_mask, d_tag, d_owner = t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64), t(s["ghost_owner"], torch.int32)
+    d_type, d_mask, d_tag, d_owner = t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64), t(plan.self_owner, torch.int32)
     d_off, d_neigh = t(s["offsets"], torch.int64), t(s["neigh"], torch.int32)
     d_x, d_v = t(s["x"], torch.float64), t(s["v"], torch.float64)
     d_f = torch.zeros((nl, 3), dtype=torch.float64, device=dev)
+    d_src = torch.zeros(a.grid ** 3, dtype=torch.float64, device=dev)
     eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
     eng.set_neighbors(d_off, d_neigh)
+    eng.bind_grid_source(d_src)
+    exch = P.GhostExchange(plan, D, dev)
 
     def step_resident(k):
-        eng.post_force(d_x, d_v, d_f, None, k)
-        eng.end_of_step(d_x, d_v, want_energy=False)
+        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src)
+
+    def timed(fn, steps, first):
+        """barrier + synchronize on both sides, device time via CUDA events, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if D:
+            D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(steps):
+            fn(first + k)
+        e1.record()
+        if D:
+            D.barrier()
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        wall = 1e3 * (time.perf_counter() - t0)
+        if D:
+            tt = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+            D.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms, wall = float(tt[0]), float(tt[1])
+        return ms, wall
 
     for k in range(a.warmup):
         step_resident(k)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
     eng.set_profiling(True)
     l0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for k in range(a.steps):
-        step_resident(a.warmup + k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms, _ = timed(step_resident, a.steps, a.warmup)
     launches = eng.launch_count() - l0
     ktimes = eng.kernel_times()
     eng.set_profiling(False)
-    clocks = sampler.summary()
+    clocks = sampler.summary() if rank == 0 else None
     ms_per_step = ms / a.steps
     value = natoms * a.steps / (ms * 1e-3)
 
@@ -285,11 +308,12 @@ def run_b200(a):
     roofline = None
     if dom:
         ach = alg[dom] * nl / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9
+        b_step = 420 + 12 * n_nb
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_atom": alg[dom], "kernel_ms": per_kernel[dom]["ms_avg"],
-                    "step": {"algorithmic_bytes_per_atom_step": 420 + 12 * n_nb,
-                             "achieved": (420 + 12 * n_nb) * value / 1e9, "frac": (420 + 12 * n_nb) * value / 1e9 / peak},
+                    "step": {"algorithmic_bytes_per_atom_step": b_step, "achieved": b_step * value / 1e9 / world,
+                             "frac": b_step * value / 1e9 / world / peak, "note": "whole step, per GPU"},
                     "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in per_kernel.items()}}
 
     # ---- end to end through the C ABI with pinned host buffers ----
@@ -299,7 +323,7 @@ def run_b200(a):
         h_x, h_v = pin(s["x"]), pin(s["v"])
         h_f = torch.zeros((nl, 3), dtype=torch.float64).pin_memory()
         h_off, h_neigh = pin(s["offsets"]), pin(s["neigh"])
-        h_type, h_mask, h_tag, h_owner = pin(s["type"]), pin(s["mask"]), pin(s["tag"]), pin(s["ghost_owner"])
+        h_type, h_mask, h_tag, h_owner = pin(s["type"]), pin(s["mask"]), pin(s["tag"]), pin(plan.self_owner)
         nx, nv, nf = h_x.numpy(), h_v.numpy(), h_f.numpy()
 
         def reneighbor():
@@ -309,45 +333,49 @@ def run_b200(a):
         def step_e2e(k):
             if k % REBUILD_EVERY == 0:
                 reneighbor()
-            eng.post_force(nx, nv, nf, None, k)         # x, v, f up; f down
-            return eng.end_of_step(nx, nv)              # x, v (locals) up; E_local down
+            eng.post_force_begin(nx, nv, None, k)       # x, v up
+            exch(eng)
+            eng.post_force_end(nf)                      # f up, f down
+            eng.end_of_step_begin(nx, nv)               # x, v (locals) up
+            if D:
+                D.all_reduce(d_src)
+            return eng.end_of_step_end(True)            # E_local down
 
         reneighbor()
         for k in range(1, min(a.warmup, 3) + 1):
             step_e2e(k)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e0.record()
-        for k in range(a.steps):
-            step_e2e(k)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+        ms_dev, ms_wall = timed(step_e2e, a.steps, 0)
+        ms_e = max(ms_dev, ms_wall)
         nt = nl + ng
         rebuilds = len([k for k in range(a.steps) if k % REBUILD_EVERY == 0])
         list_bytes = (h_off.numel() * 8 + h_neigh.numel() * 4 + nt * (4 + 4 + 8) + ng * 4) * rebuilds / a.steps
         h2d = 2 * nt * 24 + nl * 24 + 2 * nl * 24 + list_bytes
         d2h = nl * 24 + 8
-        e2e = {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e / a.steps,
-               "note": "pinned host x, v, f through eph_b200_post_force/end_of_step (HOST memspace); neighbour list "
-                       "re-uploaded every %d steps (amortised in h2d_bytes_per_step)" % REBUILD_EVERY}
-        # back to the resident set-up for anything that follows
+        e2e = {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
+               "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps,
+               "note": "pinned host x, v, f through the C ABI (HOST memspace); neighbour list re-uploaded every %d steps "
+                       "(amortised in h2d_bytes_per_step); bytes summed over ranks" % REBUILD_EVERY}
         eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
         eng.set_neighbors(d_off, d_neigh)
 
     # ---- FDM micro-benchmark: Mcell-updates/s of the stencil on a 256^3 grid with 13 sub-steps (TB_Bench fine grid) ----
     fdm = None
-    if not a.no_fdm_bench:
+    if not a.no_fdm_bench and rank == 0 and world == 1:
         fdm = fdm_bench(lib, host, stream, local, peak)
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts=ng),
-           "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
-    if not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.cpu_steps)
-    print(json.dumps(out))
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid),
+                              exchange_bytes_per_step_rank0=exch.bytes_per_step(), list_stats=eng.list_stats()),
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
+        if not a.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.cpu_steps)
+        print(json.dumps(out), flush=True)
+    if D:
+        D.barrier()
+        dist.destroy_process_group()
 
 
 def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):

@@ -143,6 +143,27 @@ int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *num
 int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
                         long long ntimestep, int memspace);
 
+/* post_force in two halves for multi-rank runs.  begin: xi, the density pass (rho_i and the pair sums W_i of owned
+ * atoms).  Then ONE ghost exchange moves {rho, Wx, Wy, Wz} from owners to ghosts -- it replaces the reference's
+ * forward comms RHO and WI (fix_eph.cpp:870-871, :743-744); XI (:863-864) needs no exchange because ghosts regenerate
+ * the owner's Gaussians from the atom tag.  end: per-atom coupling, the force pass, f += f_EPH (+ f_RNG).
+ * pack/unpack move the payload between the engine and caller-owned DEVICE buffers of n*4 doubles (the transport is
+ * NCCL or peer memory, e.g. torch.distributed); ghosts with ghost_owner[g] >= 0 in set_atoms are images of this
+ * rank's own atoms and are filled internally, ghosts with ghost_owner[g] < 0 must be covered by unpack. */
+int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double *v, const double *xi_inject,
+                              long long ntimestep, int memspace);
+int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index_dev, double *buf_dev);
+int eph_b200_unpack_ghost_payload(eph_b200_handle *h, int n, const int *recv_index_dev, const double *buf_dev);
+int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace);
+
+/* end_of_step in two halves for multi-rank runs: begin deposits this rank's energy into the grid source term, the
+ * caller all-reduces that array over ranks (the reference's MPI_Allreduce, eph_fdm.h:481), end solves the grid on
+ * every rank (no broadcast needed).  bind_grid_source makes the engine use a caller-owned DEVICE array of
+ * nx*ny*nz doubles as the source term so the transport can reduce it in place. */
+int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double *v, int memspace);
+int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local);
+int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev);
+
 /* Replaces FixEPH::end_of_step (fix_eph.cpp:350-429): energy bookkeeping,
  * EPH_FDM::insert_energy (eph_fdm.h:172-179), EPH_FDM::solve (:267-400) and the
  * 8-column per-atom output.  E_local (host pointer, may be NULL) receives this

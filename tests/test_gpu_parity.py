@@ -304,6 +304,84 @@ def test_inner_list_invalidation_and_rebuild(synth_beta_1, skin):
     assert st["inner_builds"] >= (2 if skin else 1)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
+    """The multi-rank path on one GPU: `world` engines, one per spatial brick, driven through the two halves of
+    post_force / end_of_step with the ghost payload and the grid source term moved between them exactly as
+    torch.distributed would (eph_b200.parallel); the result must equal the single-rank oracle on the whole box."""
+    import torch
+    from eph_b200 import parallel as P
+    dev = torch.device("cuda", 0)
+    n, seed, dt = 6, 4711, 1e-4
+    whole = H.make_system(n)
+    grid = P.brick_grid(world)
+    systems = [H.make_system(n, brick=(r, grid)) for r in range(world)]
+    plans = P.ExchangePlan.build_all(systems)
+    gshape = (3, 2, 2)
+    box = box6(whole)
+    engines, state = [], []
+    t = lambda a, ty: torch.as_tensor(np.ascontiguousarray(a), dtype=ty, device=dev)
+    for r, (s, plan) in enumerate(zip(systems, plans)):
+        eng = lib.Engine([0], flags=7, seed=seed, rank=r, nranks=world)
+        eng.set_tables_from(host.BetaTables(path=synth_beta_1))
+        eng.set_grid(*gshape, box, 300.0, 1.0, 3.5e-6, 0.1248)
+        eng.set_dt(dt)
+        eng.set_atoms(s["nlocal"], s["nghost"], t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64),
+                      t(plan.self_owner, torch.int32))
+        eng.set_neighbors(t(s["offsets"], torch.int64), t(s["neigh"], torch.int32))
+        src = torch.zeros(int(np.prod(gshape)), dtype=torch.float64, device=dev)
+        eng.bind_grid_source(src)
+        engines.append(eng)
+        state.append(dict(x=t(s["x"], torch.float64), v=t(s["v"], torch.float64),
+                          f=torch.zeros((s["nlocal"], 3), dtype=torch.float64, device=dev), src=src,
+                          send=t(plan.flat_send_index(), torch.int32), recv=t(plan.flat_recv_index(), torch.int32)))
+    # oracle on the whole box with the same counter-based Gaussians
+    fx = O.Fix(whole, O.Beta(path=synth_beta_1), O.FDM(*gshape, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=dt)
+    for step in (1, 2):
+        xi = O.xi_stream(seed, step, whole["tag"][: whole["nlocal"]])
+        fx.f[:] = 0.0
+        fx.post_force(xi)
+        fx.end_of_step()
+        for eng, st in zip(engines, state):
+            st["f"].zero_()
+            eng.post_force_begin(st["x"], st["v"], None, step)
+        # the exchange: all_to_all of {rho, W} rows, done here by plain copies between the engines' buffers
+        bufs = []
+        for eng, st in zip(engines, state):
+            b = torch.empty((max(st["send"].numel(), 1), 4), dtype=torch.float64, device=dev)
+            if st["send"].numel():
+                eng.pack_ghost_payload(st["send"], b)
+            bufs.append(b)
+        for r, (eng, st, plan) in enumerate(zip(engines, state, plans)):
+            parts = []
+            for q in range(world):   # what rank q sends to r sits in q's buffer after what q sends to ranks < r
+                off = sum(plans[q].send_counts[:r])
+                parts.append(bufs[q][off: off + plans[q].send_counts[r]])
+            rb = torch.cat(parts) if parts else torch.empty((0, 4), dtype=torch.float64, device=dev)
+            assert rb.shape[0] == st["recv"].numel()
+            if st["recv"].numel():
+                eng.unpack_ghost_payload(st["recv"], rb.contiguous())
+        total = torch.zeros_like(state[0]["src"])
+        for eng, st in zip(engines, state):
+            eng.post_force_end(st["f"])
+            eng.end_of_step_begin(st["x"], st["v"])
+            total += st["src"]
+        E = 0.0
+        for eng, st in zip(engines, state):
+            st["src"].copy_(total)          # all-reduce of the source term
+            E += eng.end_of_step_end(True)
+        # compare per atom by tag
+        ref_f, ref_rho = fx.f[: whole["nlocal"]], np.array(fx.ptr(0))[: whole["nlocal"]]
+        order = np.argsort(whole["tag"][: whole["nlocal"]])
+        for eng, st, s in zip(engines, state, systems):
+            idx = order[np.searchsorted(whole["tag"][: whole["nlocal"]][order], s["tag"][: s["nlocal"]])]
+            assert H.error_metrics(st["f"].cpu().numpy(), ref_f[idx], floor=np.abs(ref_f).max()) < TOL
+            assert H.error_metrics(eng.probe(0)[: s["nlocal"]], ref_rho[idx]) < TOL
+            assert H.error_metrics(eng.get_grid(0), fx.fdm.field(0)) < TOL
+        assert abs(E - (fx.Ee() if step == 1 else fx.Ee() - E_prev)) < 1e-9 * abs(E)
+        E_prev = fx.Ee()
+
+
 def test_empty_and_ragged_inputs(synth_beta_1):
     eng = make_engine(synth_beta_1, 7, (2, 2, 2), [0, 10, 0, 10, 0, 10])
     z = np.zeros((0, 3))

@@ -64,7 +64,6 @@ struct PrepArgs {
   int do_random;
   double *__restrict__ rho;    // [ntotal]; ghost entries are filled here
   const double4 *__restrict__ W4;  // [nlocal] (or [ntotal] after an exchange) pair sums of the density pass
-  int ghost_W_present;         // ghosts' W4 entries were filled by an exchange (multi-rank)
   double4 *__restrict__ pos4;  // validity bit is set here
   double4 *__restrict__ z4;    // [ntotal] s * xi
   double4 *__restrict__ u4;    // [ntotal] s * w
@@ -90,10 +89,16 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
     const double d0 = sqrt(__longlong_as_double((long long)p.list_state->disp0_sq_bits));
     p.list_state->inner_invalid = (2.0 * d0 + p.inner_skin <= p.skin) ? 0u : 1u;
   }
-  const int src = (a < p.nlocal || p.owner == nullptr) ? a : p.owner[a - p.nlocal];
+  // ghosts: owner >= 0 is a local atom of this rank (periodic image); owner < 0 means the owner lives on another
+  // rank and the exchange already wrote {rho, W} into the ghost's own slot
+  int src = a;
+  if (a >= p.nlocal && p.owner != nullptr) {
+    const int o = p.owner[a - p.nlocal];
+    if (o >= 0) src = o;
+  }
   double rho = p.rho[src];
   if (a >= p.nlocal) p.rho[a] = rho;
-  const double4 W = (src < p.nlocal || p.ghost_W_present) ? p.W4[src] : make_double4(0, 0, 0, 0);
+  const double4 W = p.W4[src];
   double4 pa = p.pos4[a];
   unsigned bits = double_to_bits(pa.w) & ~kBitValid;
   double s = 0.0;
@@ -123,6 +128,27 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   if (a < p.nlocal) {
     p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
   }
+}
+
+// The one ghost exchange of a step: {rho, Wx, Wy, Wz} of the listed owned atoms into a send buffer, and from a
+// receive buffer into the listed (ghost) slots.  Device buffers: the transport is NCCL (or peer memory), not the host.
+__global__ void pack_payload_kernel(int n, const int *__restrict__ index, const double *__restrict__ rho,
+                                    const double4 *__restrict__ W4, double4 *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int a = index[t];
+  const double4 W = W4[a];
+  buf[t] = make_double4(rho[a], W.x, W.y, W.z);
+}
+__global__ void unpack_payload_kernel(int n, const int *__restrict__ index, double *__restrict__ rho,
+                                      double4 *__restrict__ W4, const double4 *__restrict__ buf, int ntotal) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int a = index[t];
+  if (a < 0 || a >= ntotal) return;
+  const double4 b = buf[t];
+  rho[a] = b.x;
+  W4[a] = make_double4(b.y, b.z, b.w, 0.0);
 }
 
 struct DepositArgs {

@@ -89,6 +89,12 @@ struct eph_b200_handle {
   DevBuf<double4> pos4, v4, z4, u4, W4;
   DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
   bool forces_valid = false;
+  // state between post_force_begin and post_force_end
+  bool pf_open = false, pf_build = false;
+  const double *pf_xi = nullptr;
+  long long pf_step = 0;
+  bool eos_open = false;
+  double *dT_e_ext = nullptr;   // caller-owned grid source term (multi-rank: all-reduced between the two end_of_step halves)
 
   // neighbours
   DevBuf<long long> off;
@@ -455,7 +461,7 @@ int eph_b200_set_grid_tables(eph_b200_handle *h, int n_T, double dT, const doubl
 static double *grid_field(eph_b200_handle *h, int which) {
   switch (which) {
     case 0: return h->T[h->cur].p; case 1: return h->S_e.p; case 2: return h->rho_e.p;
-    case 3: return h->C_e.p; case 4: return h->kappa_e.p; case 5: return h->dT_e.p; default: return nullptr;
+    case 3: return h->C_e.p; case 4: return h->kappa_e.p; case 5: return h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; default: return nullptr;
   }
 }
 
@@ -687,13 +693,13 @@ int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, in
 int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false) {
   const bool multi = a.n_elements > 1;
   static const int lanes_density = env_lanes("EPH_B200_LANES_DENSITY", 8);
-  static const int lanes_force = env_lanes("EPH_B200_LANES_FORCE", 8);
+  static const int lanes_force = env_lanes("EPH_B200_LANES_FORCE", 4);
   if (which == 1) {
     switch (lanes_force) {
-      case 4: return multi ? launch_force<4, true>(h, a) : launch_force<4, false>(h, a);
+      case 8: return multi ? launch_force<8, true>(h, a) : launch_force<8, false>(h, a);
       case 16: return multi ? launch_force<16, true>(h, a) : launch_force<16, false>(h, a);
       case 32: return multi ? launch_force<32, true>(h, a) : launch_force<32, false>(h, a);
-      default: return multi ? launch_force<8, true>(h, a) : launch_force<8, false>(h, a);
+      default: return multi ? launch_force<4, true>(h, a) : launch_force<4, false>(h, a);
     }
   }
   // rho(r^2) tables of all elements: staged in shared memory when they fit (EPH_B200_TABLE=1, default), or read
@@ -733,30 +739,22 @@ SweepArgs sweep_args(eph_b200_handle *h) {
 
 extern "C" {
 
-int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
-                        long long ntimestep, int memspace) {
+int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double *v, const double *xi_inject,
+                              long long ntimestep, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->tables_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_tables not called");
   if (!h->dt_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_dt not called");
   if (!h->atoms_set || !h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "post_force: set_atoms / set_neighbors not called");
   if ((h->cfg.flags & EPH_B200_RANDOM) && !h->grid_set) return fail(h, EPH_B200_ERR_ARG, "post_force: random force needs the T_e grid");
-  if (!x || !v || (!f && h->nlocal > 0)) return fail(h, EPH_B200_ERR_ARG, "post_force: null x, v or f");
+  if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "post_force: null x or v");
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal, nt = h->nlocal + h->nghost;
-  if (nl == 0) return EPH_B200_OK;
+  h->pf_open = false;
+  if (nl == 0) { h->pf_open = true; return EPH_B200_OK; }
   const double *dx = nullptr, *dv = nullptr, *dxi = nullptr;
-  double *df = nullptr;
   int rc;
   if ((rc = stage_in(h, h->x, x, 3 * (size_t)nt, memspace, &dx))) return rc;
   if ((rc = stage_in(h, h->v, v, 3 * (size_t)nt, memspace, &dv))) return rc;
-  const bool add_fric = (h->cfg.flags & EPH_B200_FRICTION) && !(h->cfg.flags & EPH_B200_NOFRICTION);
-  const bool add_rand = (h->cfg.flags & EPH_B200_RANDOM) && !(h->cfg.flags & EPH_B200_NORANDOM);
-  if (memspace == EPH_B200_DEVICE) df = f;
-  else {
-    EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
-    if (add_fric || add_rand) EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    df = h->f.p;
-  }
   if (xi_inject && (h->cfg.flags & EPH_B200_RANDOM)) {
     if ((rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &dxi))) return rc;
   }
@@ -796,12 +794,37 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
   }
   h->rebuilt_last_step = build && !h->fresh_neighbors;
   h->fresh_neighbors = false;
+  h->pf_build = build;
+  h->pf_xi = dxi;
+  h->pf_step = ntimestep;
+  h->pf_open = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->pf_open) return fail(h, EPH_B200_ERR_ARG, "post_force_end without post_force_begin");
+  h->pf_open = false;
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal, nt = h->nlocal + h->nghost;
+  if (nl == 0) return EPH_B200_OK;
+  if (!f) return fail(h, EPH_B200_ERR_ARG, "post_force: null f");
+  int rc;
+  const bool add_fric = (h->cfg.flags & EPH_B200_FRICTION) && !(h->cfg.flags & EPH_B200_NOFRICTION);
+  const bool add_rand = (h->cfg.flags & EPH_B200_RANDOM) && !(h->cfg.flags & EPH_B200_NORANDOM);
+  double *df = f;
+  if (memspace != EPH_B200_DEVICE) {
+    EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
+    if (add_fric || add_rand) EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    df = h->f.p;
+  }
+  const bool build = h->pf_build;
 
   PrepArgs p{};
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
-  p.xi_inject = dxi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
-  p.seed = h->cfg.seed; p.step = (unsigned long long)ntimestep; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
-  p.rho = h->rho.p; p.W4 = h->W4.p; p.ghost_W_present = 0; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.u4 = h->u4.p;
+  p.xi_inject = h->pf_xi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
+  p.seed = h->cfg.seed; p.step = (unsigned long long)h->pf_step; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
+  p.rho = h->rho.p; p.W4 = h->W4.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.u4 = h->u4.p;
   p.w = h->w.p; p.xi = h->xi.p; p.status = h->d_status.p;
   p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
   p.list_state = h->lstate.p;
@@ -816,6 +839,7 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
     h->flag_pending = true;
   }
 
+  SweepArgs a = sweep_args(h);
   if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
     a.f = (add_fric || add_rand) ? df : nullptr;
     a.add_friction = add_fric ? 1 : 0;
@@ -827,6 +851,42 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
     }
   }
   h->forces_valid = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
+                        long long ntimestep, int memspace) {
+  if (h && !f && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "post_force: null x, v or f");
+  int rc = eph_b200_post_force_begin(h, x, v, xi_inject, ntimestep, memspace);
+  if (rc) return rc;
+  return eph_b200_post_force_end(h, f, memspace);
+}
+
+// Ghost payload of the one exchange a step needs: {rho, Wx, Wy, Wz} per atom, device buffers.
+int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index_dev, double *buf_dev) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (n < 0 || (n > 0 && (!send_index_dev || !buf_dev))) return fail(h, EPH_B200_ERR_ARG, "pack_ghost_payload: bad arguments");
+  if (n == 0) return EPH_B200_OK;
+  cudaSetDevice(h->cfg.device);
+  {
+    KernelTimer kt(h, "pack_payload");
+    pack_payload_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, send_index_dev, h->rho.p, h->W4.p, reinterpret_cast<double4 *>(buf_dev));
+  }
+  EPH_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+
+int eph_b200_unpack_ghost_payload(eph_b200_handle *h, int n, const int *recv_index_dev, const double *buf_dev) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (n < 0 || (n > 0 && (!recv_index_dev || !buf_dev))) return fail(h, EPH_B200_ERR_ARG, "unpack_ghost_payload: bad arguments");
+  if (n == 0) return EPH_B200_OK;
+  cudaSetDevice(h->cfg.device);
+  {
+    KernelTimer kt(h, "unpack_payload");
+    unpack_payload_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, recv_index_dev, h->rho.p, h->W4.p,
+                                                                      reinterpret_cast<const double4 *>(buf_dev), h->nlocal + h->nghost);
+  }
+  EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
 
@@ -873,7 +933,7 @@ int grid_solve(eph_b200_handle *h) {
 
   GridArgs g{};
   g.nx = h->nx; g.ny = h->ny; g.nz = h->nz; g.ncell = n;
-  g.dT_e = h->dT_e.p; g.S_e = h->S_e.p; g.rho_e = h->rho_e.p; g.C_e = h->C_e.p; g.kappa_e = h->kappa_e.p;
+  g.dT_e = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; g.S_e = h->S_e.p; g.rho_e = h->rho_e.p; g.C_e = h->C_e.p; g.kappa_e = h->kappa_e.p;
   g.flag = h->flag.p; g.t_dyn = h->t_dyn.p;
   g.E_e_T = h->has_tdyn ? h->E_T_tab.p : nullptr; g.n_T = h->n_T; g.dT = h->dT_tab;
   g.inv_dx2 = 1.0 / (dx * dx); g.inv_dy2 = 1.0 / (dy * dy); g.inv_dz2 = 1.0 / (dz * dz);
@@ -897,7 +957,7 @@ int grid_solve(eph_b200_handle *h) {
 
 extern "C" {
 
-int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace) {
+int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double *v, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->forces_valid) return fail(h, EPH_B200_ERR_ARG, "end_of_step: post_force has not run");
   if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "end_of_step: set_grid not called");
@@ -917,13 +977,23 @@ int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, d
     d.dt = h->dt; d.dVdt = h->dV * h->dt;
     d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
     d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
-    d.grid = grid_geom(h); d.dT_e = h->dT_e.p; d.E_sum = h->d_scal.p; d.array8 = h->array8.p;
+    d.grid = grid_geom(h); d.dT_e = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; d.E_sum = h->d_scal.p; d.array8 = h->array8.p;
     {
       KernelTimer kt(h, "deposit");
       deposit_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(d);
     }
     EPH_LAUNCH_CHECK(h);
   }
+  h->eos_open = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->eos_open) return fail(h, EPH_B200_ERR_ARG, "end_of_step_end without end_of_step_begin");
+  h->eos_open = false;
+  cudaSetDevice(h->cfg.device);
+  int rc;
   if (h->cfg.flags & EPH_B200_FDM) {
     if ((rc = grid_solve(h))) return rc;
   }
@@ -932,6 +1002,19 @@ int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, d
     EPH_CUDA(h, cudaStreamSynchronize(h->stream));
     *E_local = h->h_pinned[0];
   }
+  return EPH_B200_OK;
+}
+
+int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace) {
+  int rc = eph_b200_end_of_step_begin(h, x, v, memspace);
+  if (rc) return rc;
+  return eph_b200_end_of_step_end(h, E_local);
+}
+
+int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "bind_grid_source: set_grid not called");
+  h->dT_e_ext = dT_e_dev;   // nullptr: back to the library-owned array
   return EPH_B200_OK;
 }
 

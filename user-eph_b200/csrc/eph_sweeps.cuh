@@ -29,6 +29,14 @@
 
 #include "eph_device.cuh"
 
+// resident CTAs per SM the sweeps are compiled for (registers: 64 -> 4 CTAs of 256 threads; asking for more spills)
+#ifndef EPH_MINB_DENSITY
+#define EPH_MINB_DENSITY 4
+#endif
+#ifndef EPH_MINB_FORCE
+#define EPH_MINB_FORCE 4
+#endif
+
 namespace ephb {
 
 struct SweepArgs {
@@ -104,7 +112,7 @@ __device__ __forceinline__ RhoTable<TAB> stage_tables(const SweepArgs &a, double
 // BUILD = this launch also (re)builds the inner list from LAMMPS' list.
 // MULTI = more than one element: two table look-ups per pair.
 template <int LANES, int TAB, bool BUILD, bool MULTI>
-__global__ void __launch_bounds__(256) density_sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(SweepArgs a) {
   extern __shared__ double2 s_tab[];
   const RhoTable<TAB> tab = stage_tables<TAB>(a, s_tab);
   const int lane = threadIdx.x & 31;
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(256) density_sweep_kernel(SweepArgs a) {
 
 // f_EPH_i and f_RNG_i from the cached in-cutoff pairs; no table look-up, no reciprocal, no distance test.
 template <int LANES, bool MULTI>
-__global__ void __launch_bounds__(256) force_sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepArgs a) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES - 1);
   const unsigned gmask = group_mask<LANES>(lane);

@@ -47,6 +47,13 @@ SYMBOLS = {
     "eph_b200_set_neighbors_lammps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "eph_b200_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
     "eph_b200_end_of_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),
+    "eph_b200_post_force_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
+    "eph_b200_pack_ghost_payload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_unpack_ghost_payload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_post_force_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_end_of_step_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_end_of_step_end": (C.c_int, [C.c_void_p, c_double_p]),
+    "eph_b200_bind_grid_source": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_double, C.c_int]),
     "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
@@ -214,6 +221,34 @@ class Engine:
     def post_force(self, x, v, f, xi=None, step=0):
         ps = [_ptr(x), _ptr(v), _ptr(f), _ptr(xi)]
         self._check(self.lib.eph_b200_post_force(self.h, ps[0][0], ps[1][0], ps[2][0], ps[3][0], step, _space(*ps)))
+
+    # multi-rank halves (device tensors)
+    def post_force_begin(self, x, v, xi=None, step=0):
+        ps = [_ptr(x), _ptr(v), _ptr(xi)]
+        self._check(self.lib.eph_b200_post_force_begin(self.h, ps[0][0], ps[1][0], ps[2][0], step, _space(*ps)))
+
+    def pack_ghost_payload(self, index, buf):
+        self._check(self.lib.eph_b200_pack_ghost_payload(self.h, index.numel(), index.data_ptr(), buf.data_ptr()))
+
+    def unpack_ghost_payload(self, index, buf):
+        self._check(self.lib.eph_b200_unpack_ghost_payload(self.h, index.numel(), index.data_ptr(), buf.data_ptr()))
+
+    def post_force_end(self, f):
+        p = _ptr(f)
+        self._check(self.lib.eph_b200_post_force_end(self.h, p[0], p[1]))
+
+    def end_of_step_begin(self, x, v):
+        ps = [_ptr(x), _ptr(v)]
+        self._check(self.lib.eph_b200_end_of_step_begin(self.h, ps[0][0], ps[1][0], _space(*ps)))
+
+    def end_of_step_end(self, want_energy=True):
+        e = C.c_double()
+        self._check(self.lib.eph_b200_end_of_step_end(self.h, C.byref(e) if want_energy else None))
+        return e.value if want_energy else None
+
+    def bind_grid_source(self, tensor):
+        self._check(self.lib.eph_b200_bind_grid_source(self.h, tensor.data_ptr() if tensor is not None else None))
+        self._src = tensor
 
     def end_of_step(self, x, v, want_energy=True):
         ps = [_ptr(x), _ptr(v)]
