@@ -312,6 +312,9 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
     import torch
     from eph_b200 import parallel as P
     dev = torch.device("cuda", 0)
+    # one stream for torch and all engines, so the copies that stand in for NCCL are ordered with the kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
     n, seed, dt = 6, 4711, 1e-4
     whole = H.make_system(n)
     grid = P.brick_grid(world)
@@ -322,7 +325,7 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
     engines, state = [], []
     t = lambda a, ty: torch.as_tensor(np.ascontiguousarray(a), dtype=ty, device=dev)
     for r, (s, plan) in enumerate(zip(systems, plans)):
-        eng = lib.Engine([0], flags=7, seed=seed, rank=r, nranks=world)
+        eng = lib.Engine([0], flags=7, seed=seed, rank=r, nranks=world, stream=tstream.cuda_stream)
         eng.set_tables_from(host.BetaTables(path=synth_beta_1))
         eng.set_grid(*gshape, box, 300.0, 1.0, 3.5e-6, 0.1248)
         eng.set_dt(dt)
@@ -380,6 +383,8 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
             assert H.error_metrics(eng.get_grid(0), fx.fdm.field(0)) < TOL
         assert abs(E - (fx.Ee() if step == 1 else fx.Ee() - E_prev)) < 1e-9 * abs(E)
         E_prev = fx.Ee()
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
 
 
 def test_empty_and_ragged_inputs(synth_beta_1):
