@@ -203,7 +203,8 @@ def _fdm_case(shape, rng, walls, constant, tdyn_tables=None):
 
 
 @pytest.mark.parametrize("shape,walls,constant", [((8, 1, 1), False, False), ((5, 4, 3), True, True), ((1, 1, 1), False, False),
-                                                   ((33, 9, 5), True, False), ((64, 64, 64), False, False)])
+                                                   ((33, 9, 5), True, False), ((64, 64, 64), False, False),
+                                                   ((32, 6, 5), True, True), ((48, 16, 12), True, False), ((16, 4, 4), False, False)])
 def test_grid_solve_matches_oracle(synth_beta_1, shape, walls, constant):
     """EPH_FDM::solve alone: energy deposited by a handful of atoms, several solves, with and without sub-stepping"""
     rng = np.random.default_rng(41)
@@ -244,12 +245,13 @@ def _solve_only(eng):
     eng.end_of_step(x, z)
 
 
-def test_grid_temperature_dependent_cells(synth_beta_1, tmp_path):
+@pytest.mark.parametrize("shape", [(6, 5, 4), (32, 5, 4)])   # generic kernel / TMA-tiled kernel
+def test_grid_temperature_dependent_cells(synth_beta_1, tmp_path, shape):
     rng = np.random.default_rng(42)
     nT, dT = 401, 25.0
     Tt = np.arange(nT) * dT
     par = H.write_parameter_file(tmp_path / "par.data", dT, 3.5e-6 * (1 + Tt / 3000.0), 0.1248 * (1 + Tt / 5000.0))
-    nx, ny, nz = 6, 5, 4
+    nx, ny, nz = shape
     n = nx * ny * nz
     grid = H.write_grid_file(tmp_path / "T.in", nx, ny, nz, [0, 10, 0, 9, 0, 8], 300 + 2000 * rng.random(n), 0.0, 1.0, 3.5e-6, 0.1248, 1,
                              (rng.random(n) < 0.5).astype(int), steps=3, parameter_file=str(par))

@@ -16,6 +16,7 @@
 #include "eph_atoms.cuh"
 #include "eph_device.cuh"
 #include "eph_grid.cuh"
+#include "eph_grid_tma.cuh"
 #include "eph_sweeps.cuh"
 
 using namespace ephb;
@@ -136,6 +137,9 @@ struct eph_b200_handle {
   DevBuf<double2> C_T_tab, K_T_tab;
   DevBuf<double> E_T_tab;
   int last_substeps = 0;
+  // TMA path of the stencil: tensor maps over T_e (both buffers) and kappa_e; needs 16-byte row strides (nx even)
+  bool tma_ok = false, has_walls = false;
+  CUtensorMap map_T[2], map_K;
 
   // scalars
   DevBuf<double> d_scal;              // [0] E_local, [1] T sum
@@ -245,6 +249,27 @@ int stage_in(eph_b200_handle *h, DevBuf<T> &buf, const T *src, size_t n, int mem
   EPH_CUDA(h, cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
   *out = buf.p;
   return EPH_B200_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D fp64 tensor map over an [nz][ny][nx] field with a (kBX, kBY, kBZ) box; out-of-range elements read as zero
+bool encode_grid_map(CUtensorMap *map, double *base, int nx, int ny, int nz) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+  cuuint64_t strides[2] = {(cuuint64_t)nx * sizeof(double), (cuuint64_t)nx * ny * sizeof(double)};
+  cuuint32_t box[3] = {(cuuint32_t)kBX, (cuuint32_t)kBY, (cuuint32_t)kBZ};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -439,6 +464,14 @@ int eph_b200_set_grid(eph_b200_handle *h, int nx, int ny, int nz, const double *
   EPH_CUDA(h, cudaMemcpyAsync(h->flag.p, fl.data(), n * sizeof(short), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaMemcpyAsync(h->t_dyn.p, td.data(), n * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->has_walls = false;
+  for (long long i = 0; i < n; ++i) if (fl[i] == 2) { h->has_walls = true; break; }
+  // the TMA needs 16-byte global strides (nx even); tiny grids gain nothing from tiles
+  static const bool tma_off = std::getenv("EPH_B200_NO_TMA") != nullptr;
+  h->tma_ok = !tma_off && (nx % 2 == 0) && nx >= 16 && (long long)ny * nz >= 16 &&
+              encode_grid_map(&h->map_T[0], h->T[0].p, nx, ny, nz) && encode_grid_map(&h->map_T[1], h->T[1].p, nx, ny, nz) &&
+              encode_grid_map(&h->map_K, h->kappa_e.p, nx, ny, nz);
+  if (h->tma_ok) cudaFuncSetAttribute(fdm_substep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
   h->grid_set = true;
   h->minmax_valid = false;
   return EPH_B200_OK;
@@ -940,12 +973,20 @@ int grid_solve(eph_b200_handle *h) {
   g.inner_dt = inner_dt; g.status = h->d_status.p;
   dim3 block(32, 4, 2);
   dim3 grid((h->nx + block.x - 1) / block.x, (h->ny + block.y - 1) / block.y, (h->nz + block.z - 1) / block.z);
+  dim3 tgrid((h->nx + kTX - 1) / kTX, (h->ny + kTY - 1) / kTY, (h->nz + kTZ - 1) / kTZ);
   for (unsigned int s = 0; s < new_steps; ++s) {
     g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
     g.clear_source = (s + 1 == new_steps) ? 1 : 0;
     {
       KernelTimer kt(h, "fdm_substep");
-      fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+      if (h->tma_ok) {
+        GridTmaArgs ta;
+        ta.g = g;
+        ta.has_walls = h->has_walls ? 1 : 0;
+        fdm_substep_tma_kernel<<<tgrid, 256, kTmaSmemBytes, h->stream>>>(h->map_T[h->cur], h->map_K, ta);
+      } else {
+        fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+      }
     }
     EPH_LAUNCH_CHECK(h);
     h->cur = 1 - h->cur;

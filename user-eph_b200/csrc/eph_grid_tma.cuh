@@ -1,0 +1,140 @@
+// TMA-tiled form of the FDM sub-step (reference eph_fdm.h:319-395) for sm_100a.
+//
+// One CTA owns a TX x TY x TZ tile of cells.  The T_e and kappa_e boxes with a one-cell halo are brought into shared
+// memory by the Tensor Memory Accelerator (cp.async.bulk.tensor.3d, one elected thread, completion on an mbarrier);
+// the TMA zero-fills whatever lies outside the grid, and the threads of tiles that touch the periodic boundary patch
+// those halo cells with the wrapped values.  All stencil neighbours are then read from shared memory, the five
+// single-use fields (dT_e, S_e, rho_e, C_e, flags) stream in with coalesced loads, T_e streams out.
+// Algorithmic traffic: 60 bytes per cell-update; the halo adds (34*10*10)/(32*8*8) - 1 = 66 % to the
+// T_e and kappa_e reads, which L2 absorbs.
+#pragma once
+
+#include <cuda.h>
+
+#include "eph_grid.cuh"
+
+namespace ephb {
+
+constexpr int kTX = 32, kTY = 8, kTZ = 8;
+constexpr int kBX = kTX + 2, kBY = kTY + 2, kBZ = kTZ + 2;
+constexpr int kBoxCells = kBX * kBY * kBZ;
+constexpr int kBoxBytes = (kBoxCells * 8 + 127) / 128 * 128;
+constexpr int kTmaSmemBytes = 2 * kBoxBytes + kBoxCells * 2;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+struct GridTmaArgs {
+  GridArgs g;
+  int has_walls;   // some cell has flag == 2: the wall substitution needs the neighbours' flags
+};
+
+__global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_constant__ CUtensorMap map_T,
+                                                              const __grid_constant__ CUtensorMap map_K, GridTmaArgs ta) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  double *sT = reinterpret_cast<double *>(tma_smem);                 // kBoxBytes each, 128-byte aligned
+  double *sK = reinterpret_cast<double *>(tma_smem + kBoxBytes);
+  short *sF = reinterpret_cast<short *>(tma_smem + 2 * kBoxBytes);
+  __shared__ __align__(8) unsigned long long bar;
+  const GridArgs &g = ta.g;
+  const int ox = blockIdx.x * kTX, oy = blockIdx.y * kTY, oz = blockIdx.z * kTZ;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&bar)),
+                 "r"(static_cast<unsigned>(2 * kBoxCells * sizeof(double))) : "memory");
+    tma_load_3d(sT, &map_T, ox - 1, oy - 1, oz - 1, &bar);
+    tma_load_3d(sK, &map_K, ox - 1, oy - 1, oz - 1, &bar);
+  }
+  const long long sy = g.nx, sz = (long long)g.nx * g.ny;
+  // flags of the box (2 bytes per cell, periodic wrap applied directly) while the TMA is in flight
+  if (ta.has_walls) {
+    for (int c = tid; c < kBoxCells; c += blockDim.x) {
+      const int bx = c % kBX, by = (c / kBX) % kBY, bz = c / (kBX * kBY);
+      int gx = ox - 1 + bx, gy = oy - 1 + by, gz = oz - 1 + bz;
+      gx = gx < 0 ? gx + g.nx : (gx >= g.nx ? gx - g.nx : gx);
+      gy = gy < 0 ? gy + g.ny : (gy >= g.ny ? gy - g.ny : gy);
+      gz = gz < 0 ? gz + g.nz : (gz >= g.nz ? gz - g.nz : gz);
+      const bool ok = gx >= 0 && gx < g.nx && gy >= 0 && gy < g.ny && gz >= 0 && gz < g.nz;
+      sF[c] = ok ? g.flag[gx + gy * sy + gz * sz] : (short)1;
+    }
+  }
+  {  // wait for both boxes
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    }
+  }
+  // periodic wrap: halo cells outside the grid were zero-filled by the TMA
+  const bool edge = ox == 0 || oy == 0 || oz == 0 || ox + kTX >= g.nx || oy + kTY >= g.ny || oz + kTZ >= g.nz;
+  if (edge) {
+    for (int c = tid; c < kBoxCells; c += blockDim.x) {
+      const int bx = c % kBX, by = (c / kBX) % kBY, bz = c / (kBX * kBY);
+      int gx = ox - 1 + bx, gy = oy - 1 + by, gz = oz - 1 + bz;
+      if (gx >= 0 && gx < g.nx && gy >= 0 && gy < g.ny && gz >= 0 && gz < g.nz) continue;
+      gx = gx < 0 ? gx + g.nx : (gx >= g.nx ? gx - g.nx : gx);
+      gy = gy < 0 ? gy + g.ny : (gy >= g.ny ? gy - g.ny : gy);
+      gz = gz < 0 ? gz + g.nz : (gz >= g.nz ? gz - g.nz : gz);
+      if (gx < 0 || gx >= g.nx || gy < 0 || gy >= g.ny || gz < 0 || gz >= g.nz) continue;  // beyond one period: unused cells
+      const long long r = gx + gy * sy + gz * sz;
+      sT[c] = g.T_in[r];
+      sK[c] = g.kappa_e[r];
+    }
+  }
+  __syncthreads();
+
+  const int tx = tid & 31, ty = tid >> 5;   // 32 x 8 threads, each marching over the tile's TZ planes
+  const int i = ox + tx, j = oy + ty;
+  if (i >= g.nx || j >= g.ny) return;
+  for (int tz = 0; tz < kTZ; ++tz) {
+    const int k = oz + tz;
+    if (k >= g.nz) break;
+    const long long r = i + j * sy + k * sz;
+    const int c = (tx + 1) + (ty + 1) * kBX + (tz + 1) * kBX * kBY;
+    const short fr = g.flag[r];
+    double T = sT[c];
+    if (fr == 1) {  // only DYNAMIC cells change; walls (2) and constant cells (0) keep T
+      const double kr = sK[c];
+      double ddT = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int stride = d == 0 ? 1 : (d == 1 ? kBX : kBX * kBY);
+        const double inv = d == 0 ? g.inv_dx2 : (d == 1 ? g.inv_dy2 : g.inv_dz2);
+        int p = c - stride, q = c + stride;
+        if (ta.has_walls) {  // zero-derivative wall substitution, eph_fdm.h:336-337
+          if (sF[q] == 2) q = c; else if (sF[p] == 2) p = c;
+        }
+        const double Tq = sT[q], Tp = sT[p];
+        ddT += (sK[q] - sK[p]) * (Tq - Tp) * inv * 0.25;
+        ddT += kr * ((Tq + Tp - 2.0 * T) * inv);
+      }
+      const double src = ddT + g.dT_e[r] + g.S_e[r];
+      const double rho = g.rho_e[r];
+      if (g.E_e_T != nullptr && g.t_dyn[r] == 1) {
+        double E = linear_eval(g.E_e_T, g.n_T, g.dT, T);
+        E += src / rho * g.inner_dt;
+        T = linear_reverse(g.E_e_T, g.n_T, g.dT, E);
+      } else {
+        T += src / (rho * g.C_e[r]) * g.inner_dt;
+      }
+    }
+    if (T < 0.0) {
+      T = 0.0;
+      atomicOr(g.status, 2u);
+    }
+    g.T_out[r] = T;
+    if (g.clear_source) g.dT_e[r] = 0.0;
+  }
+}
+
+}  // namespace ephb
