@@ -408,10 +408,14 @@ def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):
     k_ms = kt[0] / max(kt[1], 1)
     ach = 60.0 * cells / (k_ms * 1e-3) / 1e9
     eng.close()
+    # the grid of this benchmark has constant coefficients, so the engine takes its constant-coefficient TMA kernel, which
+    # really moves 24 B per cell-update (T_e in/out, dT_e in); `achieved` uses the 60 B of the general path
+    actual = 24.0 * cells / (k_ms * 1e-3) / 1e9
     return {"metric": "FDM Mcell-updates/s", "value": rate / 1e6, "unit": "Mcell-updates/s", "grid": [n] * 3, "substeps": sub,
             "solves": solves, "ms_per_solve": ms / solves,
-            "roofline": {"bound": "hbm", "kernel": "fdm_substep", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "algorithmic_bytes_per_cell_update": 60, "kernel_ms": k_ms}}
+            "roofline": {"bound": "hbm", "kernel": "fdm_substep (constant-coefficient TMA path)", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_cell_update": 60, "kernel_ms": k_ms,
+                         "actual_bytes_per_cell_update": 24, "actual_gbs": actual, "actual_frac": actual / peak}}
 
 
 def main():

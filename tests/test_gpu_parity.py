@@ -232,6 +232,32 @@ def test_grid_solve_matches_oracle(synth_beta_1, shape, walls, constant):
     assert eng.last_substeps() > 1
 
 
+@pytest.mark.parametrize("shape", [(32, 16, 8), (64, 4, 4), (16, 4, 5), (40, 9, 7)])
+def test_grid_uniform_fast_path_matches_oracle(synth_beta_1, shape):
+    """`NX NY NZ NULL` grids (all cells dynamic, identical parameters) take the constant-coefficient TMA kernel"""
+    rng = np.random.default_rng(43)
+    box = [0.0, 35.2, 0.0, 17.6, -3.0, 14.6]
+    o = O.FDM(*shape, box, 300.0, 3.5e-6, 1.0, 0.1248)
+    eng = lib.Engine([0], flags=7)
+    eng.set_tables_from(host.BetaTables(path=synth_beta_1))
+    eng.set_grid(*shape, box, 300.0, 1.0, 3.5e-6, 0.1248)
+    T0 = 300 + 200 * rng.random(o.ntotal)
+    o.field(0)[:] = T0
+    eng.put_grid(0, T0)                      # T_e is state, not a parameter: the fast path stays on
+    for dt in (1e-4, 2e-3):
+        o.set_dt(dt)
+        eng.set_dt(dt)
+        for _ in range(3):
+            src = 1e-2 * rng.normal(size=o.ntotal)
+            o.field(5)[:] = src
+            eng.put_grid(5, src)
+            o.solve()
+            _solve_only(eng)
+            assert H.error_metrics(eng.get_grid(0), o.field(0)) < TOL
+            assert np.all(eng.get_grid(5) == 0.0)
+    assert eng.last_substeps() > 1
+
+
 def _solve_only(eng):
     """run end_of_step with no atoms contributing: a one-atom system outside the fix group"""
     if not getattr(eng, "_dummy", False):

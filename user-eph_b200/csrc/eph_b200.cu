@@ -139,7 +139,11 @@ struct eph_b200_handle {
   int last_substeps = 0;
   // TMA path of the stencil: tensor maps over T_e (both buffers) and kappa_e; needs 16-byte row strides (nx even)
   bool tma_ok = false, has_walls = false;
-  CUtensorMap map_T[2], map_K;
+  CUtensorMap map_T[2], map_K, map_S;
+  // constant-coefficient fast path: all cells dynamic with identical parameters
+  bool uniform = false;
+  double u_kappa = 0, u_S = 0, u_rho = 0, u_C = 0;
+  double *map_S_base = nullptr;
 
   // scalars
   DevBuf<double> d_scal;              // [0] E_local, [1] T sum
@@ -256,7 +260,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 3-D fp64 tensor map over an [nz][ny][nx] field with a (kBX, kBY, kBZ) box; out-of-range elements read as zero
-bool encode_grid_map(CUtensorMap *map, double *base, int nx, int ny, int nz) {
+bool encode_grid_map(CUtensorMap *map, double *base, int nx, int ny, int nz, int bx = kBX, int by = kBY, int bz = kBZ) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -266,7 +270,7 @@ bool encode_grid_map(CUtensorMap *map, double *base, int nx, int ny, int nz) {
   }
   cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
   cuuint64_t strides[2] = {(cuuint64_t)nx * sizeof(double), (cuuint64_t)nx * ny * sizeof(double)};
-  cuuint32_t box[3] = {(cuuint32_t)kBX, (cuuint32_t)kBY, (cuuint32_t)kBZ};
+  cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -472,6 +476,13 @@ int eph_b200_set_grid(eph_b200_handle *h, int nx, int ny, int nz, const double *
               encode_grid_map(&h->map_T[0], h->T[0].p, nx, ny, nz) && encode_grid_map(&h->map_T[1], h->T[1].p, nx, ny, nz) &&
               encode_grid_map(&h->map_K, h->kappa_e.p, nx, ny, nz);
   if (h->tma_ok) cudaFuncSetAttribute(fdm_substep_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes);
+  // constant-coefficient grid?  (what the `NX NY NZ NULL` constructor creates)
+  h->uniform = !h->has_tdyn && !h->has_walls;
+  for (long long i = 0; i < n && h->uniform; ++i)
+    h->uniform = fl[i] == 1 && rho_e[i] == rho_e[0] && C_e[i] == C_e[0] && kappa_e[i] == kappa_e[0] && (S_e ? S_e[i] == S_e[0] : true);
+  h->u_kappa = kappa_e[0]; h->u_rho = rho_e[0]; h->u_C = C_e[0]; h->u_S = S_e ? S_e[0] : 0.0;
+  h->map_S_base = nullptr;
+  if (h->uniform && h->tma_ok) cudaFuncSetAttribute(fdm_uniform_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUniSmemBytes);
   h->grid_set = true;
   h->minmax_valid = false;
   return EPH_B200_OK;
@@ -517,6 +528,7 @@ int eph_b200_put_grid(eph_b200_handle *h, int which, const double *in) {
   cudaSetDevice(h->cfg.device);
   EPH_CUDA(h, cudaMemcpyAsync(p, in, h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (which >= 1 && which <= 4) h->uniform = false;   // parameters changed cell by cell: general kernel from now on
   h->minmax_valid = false;
   return EPH_B200_OK;
 }
@@ -979,7 +991,18 @@ int grid_solve(eph_b200_handle *h) {
     g.clear_source = (s + 1 == new_steps) ? 1 : 0;
     {
       KernelTimer kt(h, "fdm_substep");
-      if (h->tma_ok) {
+      if (h->tma_ok && h->uniform) {
+        if (h->map_S_base != g.dT_e) {   // the source array may be caller-owned (bind_grid_source)
+          if (!encode_grid_map(&h->map_S, g.dT_e, h->nx, h->ny, h->nz, kTX, kTY, kTZ)) return fail(h, EPH_B200_ERR_CUDA, "solve: cannot encode the source tensor map");
+          h->map_S_base = g.dT_e;
+        }
+        GridUniformArgs u;
+        u.nx = h->nx; u.ny = h->ny; u.nz = h->nz; u.T_in = g.T_in; u.T_out = g.T_out; u.dT_e = g.dT_e;
+        u.kappa = h->u_kappa; u.S = h->u_S; u.rho = h->u_rho; u.C = h->u_C;
+        u.inv_dx2 = g.inv_dx2; u.inv_dy2 = g.inv_dy2; u.inv_dz2 = g.inv_dz2; u.inner_dt = g.inner_dt;
+        u.clear_source = g.clear_source; u.status = g.status;
+        fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, h->stream>>>(h->map_T[h->cur], h->map_S, u);
+      } else if (h->tma_ok) {
         GridTmaArgs ta;
         ta.g = g;
         ta.has_walls = h->has_walls ? 1 : 0;
