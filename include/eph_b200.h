@@ -184,7 +184,10 @@ int eph_b200_get_probe(eph_b200_handle *h, int which, double *out);
 
 /* Replaces FixEPH::pack_forward_comm / unpack_forward_comm (fix_eph.cpp:951-1009)
  * for a host transport (LAMMPS' MPI comm): gathers / scatters the payload of
- * `state` between device-resident per-atom arrays and a host buffer. */
+ * `state` between device-resident per-atom arrays and a host buffer, between
+ * post_force_begin and post_force_end.  RHO: rho (1 double per atom); WI: the
+ * pair sums W of the density pass (3 doubles; the receiver forms w itself);
+ * XI: injected Gaussians (3 doubles).  pack returns the number of doubles written. */
 int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list, double *buf);
 int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf);
 

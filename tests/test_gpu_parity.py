@@ -163,9 +163,11 @@ def test_engine_matches_committed_golden_vectors(name, ni_trunc_beta):
     compare(recs, refs, s["nlocal"])
 
 
+@pytest.mark.parametrize("comm", ["device", "lammps"])
 @pytest.mark.parametrize("name", ["caseA_example1", "caseB_grid", "caseC_alloy_group"])
-def test_fix_b200_matches_committed_golden_vectors(name):
-    """FixEPHB200 in the LAMMPS stand-in, same command line as the reference fix, rng mars = injected stream"""
+def test_fix_b200_matches_committed_golden_vectors(name, comm):
+    """FixEPHB200 in the LAMMPS stand-in, same command line as the reference fix, rng mars = injected stream;
+    ghost values either through the engine's owner map or through Comm::forward_comm(Fix*) like the reference"""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     s = traj.system_from_golden(g)
     s["natoms"] = s["nlocal"]
@@ -174,12 +176,12 @@ def test_fix_b200_matches_committed_golden_vectors(name):
     os.chdir(GOLDEN)
     try:
         if name == "caseA_example1":
-            drv = host.FixDriver(s, H.fix_args(3, "Ni_trunc.beta", ["Ni"], grid=(1, 1, 1), style="eph/b200", extra=["rng", "mars"]), dt=dt)
+            drv = host.FixDriver(s, H.fix_args(3, "Ni_trunc.beta", ["Ni"], grid=(1, 1, 1), style="eph/b200", extra=["rng", "mars", "comm", comm]), dt=dt)
         elif name == "caseB_grid":
-            drv = host.FixDriver(s, H.fix_args(7, "Ni_trunc.beta", ["Ni"], T_infile="caseB_grid.in", style="eph/b200", extra=["rng", "mars"]), dt=dt)
+            drv = host.FixDriver(s, H.fix_args(7, "Ni_trunc.beta", ["Ni"], T_infile="caseB_grid.in", style="eph/b200", extra=["rng", "mars", "comm", comm]), dt=dt)
         else:
             drv = host.FixDriver(s, H.fix_args(7, "synth2.beta", ["Co", "Ni"], grid=(2, 2, 2), group="bit1", style="eph/b200",
-                                               extra=["rng", "mars"]), dt=dt, mass=[58.93, 58.71])
+                                               extra=["rng", "mars", "comm", comm]), dt=dt, mass=[58.93, 58.71])
     finally:
         os.chdir(cwd)
     recs = traj.run_fix_driver(drv, s, list(g["xi"]))
@@ -188,6 +190,8 @@ def test_fix_b200_matches_committed_golden_vectors(name):
     fl = drv.fix_flags()
     assert fl["size_peratom_cols"] == 8 and fl["comm_forward"] == 3 and fl["ghost_velocity"] == 1 and fl["size_vector"] == 2
     assert drv.neigh_cutoff() == 5.0
+    if comm == "lammps":      # XI, RHO and (with friction) WI broadcasts per step, as in the reference
+        assert drv.n_forward() >= 3 * len(recs)
 
 
 def _fdm_case(shape, rng, walls, constant, tdyn_tables=None):

@@ -68,7 +68,7 @@ struct PrepArgs {
   double4 *__restrict__ z4;    // [ntotal] s * xi
   double4 *__restrict__ u4;    // [ntotal] s * w
   double *__restrict__ w;      // [nlocal][3] w_i (probe / forward-comm payload)
-  double *__restrict__ xi;     // [nlocal][3] probe copy
+  double *__restrict__ xi;     // [ntotal][3] xi_i (probe / XI forward-comm slots)
   unsigned *__restrict__ status;
   // the step that (re)built the inner list validates it here (stream order: after the rho sweep)
   int built_inner;
@@ -119,7 +119,10 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   double xi[3] = {0.0, 0.0, 0.0};
   if (p.do_random && (bits & kBitGroup)) {
     if (p.xi_inject) {
-      xi[0] = p.xi_inject[3 * (size_t)src]; xi[1] = p.xi_inject[3 * (size_t)src + 1]; xi[2] = p.xi_inject[3 * (size_t)src + 2];
+      // injected stream: locals and own images read the caller's array; ghosts owned elsewhere read the slot the XI
+      // forward comm filled (fix_eph.cpp:863-864)
+      const double *q = src < p.nlocal ? p.xi_inject + 3 * (size_t)src : p.xi + 3 * (size_t)a;
+      xi[0] = q[0]; xi[1] = q[1]; xi[2] = q[2];
     } else {
       xi_stream(p.seed, p.step, p.tag[a], xi);
     }

@@ -84,6 +84,8 @@ struct eph_b200_handle {
   DevBuf<long long> tag;
   bool has_owner = false;
   DevBuf<double> x, v, f, xi_in;  // staging for host memspace
+  DevBuf<int> comm_idx;           // forward-comm scratch (host transport)
+  DevBuf<double> comm_buf;
   DevBuf<double> mass;
 
   // internal per-atom records
@@ -352,7 +354,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   cudaStreamSynchronize(h->stream);
   h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->tag.release();
-  h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release();
+  h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release(); h->comm_idx.release(); h->comm_buf.release();
   h->pos4.release(); h->v4.release(); h->z4.release(); h->u4.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
   h->off.release(); h->neigh.release(); h->cneigh.release(); h->ccount.release();
@@ -605,14 +607,14 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   EPH_CUDA(h, h->xref.reserve(nt)); EPH_CUDA(h, h->xref0.reserve(nt)); EPH_CUDA(h, h->icount.reserve(std::max<size_t>(nlocal, 1)));
   h->have_inner = false;
   const size_t nl = std::max<size_t>(nlocal, 1);
-  EPH_CUDA(h, h->w.reserve(3 * nl)); EPH_CUDA(h, h->xi.reserve(3 * nl)); EPH_CUDA(h, h->f_eph.reserve(3 * nl));
+  EPH_CUDA(h, h->w.reserve(3 * nl)); EPH_CUDA(h, h->xi.reserve(3 * std::max<size_t>(nt, 1))); EPH_CUDA(h, h->f_eph.reserve(3 * nl));
   EPH_CUDA(h, h->f_rng.reserve(3 * nl)); EPH_CUDA(h, h->array8.reserve(8 * nl)); EPH_CUDA(h, h->ccount.reserve(nl));
   // fresh storage is zero, like the reference constructor (fix_eph.cpp:229-238)
   EPH_CUDA(h, cudaMemsetAsync(h->rho.p, 0, nt * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->u4.p, 0, nt * sizeof(double4), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->z4.p, 0, nt * sizeof(double4), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->w.p, 0, 3 * nl * sizeof(double), h->stream));
-  EPH_CUDA(h, cudaMemsetAsync(h->xi.p, 0, 3 * nl * sizeof(double), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->xi.p, 0, 3 * std::max<size_t>(nt, 1) * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->f_eph.p, 0, 3 * nl * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->f_rng.p, 0, 3 * nl * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->array8.p, 0, 8 * nl * sizeof(double), h->stream));
@@ -839,6 +841,7 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   }
   h->rebuilt_last_step = build && !h->fresh_neighbors;
   h->fresh_neighbors = false;
+  if (dxi) EPH_CUDA(h, cudaMemcpyAsync(h->xi.p, dxi, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   h->pf_build = build;
   h->pf_xi = dxi;
   h->pf_step = ntimestep;
@@ -1170,16 +1173,49 @@ int eph_b200_get_probe(eph_b200_handle *h, int which, double *out) {
   return EPH_B200_OK;
 }
 
+// Host transport (LAMMPS' own MPI comm): payload of `state` between device-resident arrays and a host buffer.
+// RHO: rho (1 double); WI: the pair sums W of the density pass (3 doubles; the receiver forms w = s W itself);
+// XI: the injected Gaussians (3 doubles).  Valid between post_force_begin and post_force_end.
+static int forward_source(eph_b200_handle *h, int state, double **base, int *width, int *stride) {
+  switch (state) {
+    case EPH_B200_STATE_RHO: *base = h->rho.p; *width = 1; *stride = 1; return 0;
+    case EPH_B200_STATE_WI: *base = reinterpret_cast<double *>(h->W4.p); *width = 3; *stride = 4; return 0;
+    case EPH_B200_STATE_XI: *base = h->xi.p; *width = 3; *stride = 3; return 0;
+    default: return -1;
+  }
+}
+
 int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list, double *buf) {
-  (void)list; (void)buf; (void)n;
   if (!h) return EPH_B200_ERR_ARG;
-  return fail(h, EPH_B200_ERR_ARG, "pack_forward(state %d): host transport not wired yet", state);
+  if (!h->pf_open) return fail(h, EPH_B200_ERR_ARG, "pack_forward: only valid between post_force_begin and post_force_end");
+  double *base; int width, stride;
+  if (forward_source(h, state, &base, &width, &stride)) return fail(h, EPH_B200_ERR_ARG, "pack_forward: bad state %d", state);
+  if (n <= 0) return EPH_B200_OK;
+  if (!list || !buf) return fail(h, EPH_B200_ERR_ARG, "pack_forward: null list or buffer");
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, h->comm_idx.reserve(n)); EPH_CUDA(h, h->comm_buf.reserve((size_t)n * width));
+  EPH_CUDA(h, cudaMemcpyAsync(h->comm_idx.p, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  pack_forward_kernel<<<blocks_for((long long)n * width, 256), 256, 0, h->stream>>>(n, h->comm_idx.p, base, width, stride, h->comm_buf.p);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cudaMemcpyAsync(buf, h->comm_buf.p, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return n * width;
 }
 
 int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf) {
-  (void)first; (void)buf; (void)n;
   if (!h) return EPH_B200_ERR_ARG;
-  return fail(h, EPH_B200_ERR_ARG, "unpack_forward(state %d): host transport not wired yet", state);
+  if (!h->pf_open) return fail(h, EPH_B200_ERR_ARG, "unpack_forward: only valid between post_force_begin and post_force_end");
+  double *base; int width, stride;
+  if (forward_source(h, state, &base, &width, &stride)) return fail(h, EPH_B200_ERR_ARG, "unpack_forward: bad state %d", state);
+  if (n <= 0) return EPH_B200_OK;
+  if (!buf || first < 0 || first + n > h->nlocal + h->nghost) return fail(h, EPH_B200_ERR_ARG, "unpack_forward: bad range");
+  cudaSetDevice(h->cfg.device);
+  EPH_CUDA(h, h->comm_buf.reserve((size_t)n * width));
+  EPH_CUDA(h, cudaMemcpyAsync(h->comm_buf.p, buf, (size_t)n * width * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  unpack_forward_kernel<<<blocks_for((long long)n * width, 256), 256, 0, h->stream>>>(n, first, base, width, stride, h->comm_buf.p);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));   // the caller may reuse its buffer
+  return EPH_B200_OK;
 }
 
 }  // extern "C"

@@ -116,6 +116,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
 
   // optional keyword pairs after the element names
   rng_mars = false;
+  comm_lammps = nrPS > 1;
   int device = -1;
   for (int k = 17 + types; k + 1 < narg; k += 2) {
     if (strcmp(arg[k], "rng") == 0) {
@@ -124,6 +125,10 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
       else error->all(FLERR, "fix eph/b200: rng must be mars or philox");
     } else if (strcmp(arg[k], "device") == 0) {
       device = atoi(arg[k + 1]);
+    } else if (strcmp(arg[k], "comm") == 0) {
+      if (strcmp(arg[k + 1], "lammps") == 0) comm_lammps = true;
+      else if (strcmp(arg[k + 1], "device") == 0) comm_lammps = false;
+      else error->all(FLERR, "fix eph/b200: comm must be device or lammps");
     }
     // anything else: extra element names, ignored like the reference does
   }
@@ -260,16 +265,17 @@ void FixEPHB200::final_integrate() {
 // rebuild, never per step.
 void FixEPHB200::upload_topology() {
   const int nlocal = atom->nlocal, nghost = atom->nghost;
-  if (nrPS > 1)
-    error->all(FLERR, "fix eph/b200: multi-rank runs exchange ghosts over NCCL (see INTEGRATION.md); "
-                      "the LAMMPS-MPI transport is not wired in this build");
-  // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
+  if (nrPS > 1 && !comm_lammps)
+    error->all(FLERR, "fix eph/b200: comm device needs a single rank; use comm lammps (or the NCCL halves, INTEGRATION.md)");
   ghost_owner.assign(nghost, -1);
-  state = FixState::OWNER;
-  comm->forward_comm(this);
-  state = FixState::NONE;
-  for (int g = 0; g < nghost; ++g)
-    if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/b200: ghost atom without a local owner");
+  if (!comm_lammps) {
+    // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
+    state = FixState::OWNER;
+    comm->forward_comm(this);
+    state = FixState::NONE;
+    for (int g = 0; g < nghost; ++g)
+      if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/b200: ghost atom without a local owner");
+  }
   check(eph_b200_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, reinterpret_cast<const int64_t *>(atom->tag),
                            ghost_owner.data(), EPH_B200_HOST),
         "set_atoms");
@@ -297,9 +303,19 @@ void FixEPHB200::post_force(int) {
     xi = xi_host.data();
   }
   if (nlocal + nghost == 0) return;
-  check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
-                            EPH_B200_HOST),
-        "post_force");
+  if (!comm_lammps) {
+    check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
+                              EPH_B200_HOST),
+          "post_force");
+    return;
+  }
+  // the reference's transport: ghosts get xi, rho and the w sums through Comm::forward_comm(Fix*) (fix_eph.cpp:863-871, :743-744)
+  check(eph_b200_post_force_begin(dev, &atom->x[0][0], &atom->v[0][0], xi, update->ntimestep, EPH_B200_HOST), "post_force");
+  if (xi) { state = FixState::XI; comm->forward_comm(this); }
+  state = FixState::RHO; comm->forward_comm(this);
+  if (eph_flag & Flag::FRICTION) { state = FixState::WI; comm->forward_comm(this); }
+  state = FixState::NONE;
+  check(eph_b200_post_force_end(dev, nlocal ? &atom->f[0][0] : nullptr, EPH_B200_HOST), "post_force");
 }
 
 void FixEPHB200::end_of_step() {
@@ -357,6 +373,13 @@ int FixEPHB200::pack_forward_comm(int n, int *list, double *data, int, int *) {
       const int src = list[i];
       data[m++] = static_cast<double>(src < nlocal ? src : ghost_owner[src - nlocal]);
     }
+    return m;
+  }
+  const int st = state == FixState::RHO ? EPH_B200_STATE_RHO : state == FixState::WI ? EPH_B200_STATE_WI
+               : state == FixState::XI ? EPH_B200_STATE_XI : EPH_B200_STATE_NONE;
+  if (st != EPH_B200_STATE_NONE) {
+    m = eph_b200_pack_forward(dev, st, n, list, data);
+    if (m < 0) check(m, "pack_forward");
   }
   return m;
 }
@@ -365,7 +388,11 @@ void FixEPHB200::unpack_forward_comm(int n, int first, double *data) {
   if (state == FixState::OWNER) {
     const int nlocal = atom->nlocal;
     for (int i = 0; i < n; ++i) ghost_owner[first + i - nlocal] = static_cast<int>(data[i]);
+    return;
   }
+  const int st = state == FixState::RHO ? EPH_B200_STATE_RHO : state == FixState::WI ? EPH_B200_STATE_WI
+               : state == FixState::XI ? EPH_B200_STATE_XI : EPH_B200_STATE_NONE;
+  if (st != EPH_B200_STATE_NONE) check(eph_b200_unpack_forward(dev, st, n, first, data), "unpack_forward");
 }
 
 double FixEPHB200::memory_usage() {

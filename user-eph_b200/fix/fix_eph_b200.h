@@ -7,6 +7,8 @@
  *                     on atom tags, so no XI ghost exchange is needed; mars: LAMMPS' RanMars on the host in the
  *                     reference's order, fix_eph.cpp:854-861, uploaded every step)
  *   device N          CUDA device ordinal (default: rank modulo visible devices)
+ *   comm device|lammps ghost values through the engine's own owner map (single rank, default) or through LAMMPS'
+ *                     Comm::forward_comm(Fix*) with host buffers, as the reference does (default for several ranks)
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
  * (f_ID[1], f_ID[2], 8 per-atom columns); all per-timestep work is done by libeph_b200 (include/eph_b200.h).
  * Build with -DEPH_B200_REPLACE_FIX_EPH to register under the name `eph` itself.
@@ -85,6 +87,7 @@ class FixEPHB200 : public Fix {
   int seed;
   class RanMars *random;
   bool rng_mars;
+  bool comm_lammps;
   class NeighList *list;
   double Ee;
   size_t n;
