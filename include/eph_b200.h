@@ -134,6 +134,12 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
 int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *offsets, const int *neigh, int memspace);
 int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *numneigh, int *const *firstneigh);
 
+/* Alternative to uploading LAMMPS' list: build the same full list (rows of local atoms over locals and ghosts,
+ * pairs closer than cutoff = r_c + neighbor->skin) on the device from the positions x [nlocal+nghost][3].  Call when
+ * neighbor->ago == 0, after set_atoms.  get_neighbors reads the list in use back (offsets [nlocal+1], neigh). */
+int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff, int memspace);
+int eph_b200_get_neighbors(eph_b200_handle *h, int64_t *offsets, int *neigh, long long *n_entries);
+
 /* Replaces FixEPH::post_force (fix_eph.cpp:841-907) for model PRL:
  * xi generation, calculate_environment (:431-466), the three ghost broadcasts,
  * force_prl (:687-837) and f += f_EPH (+ f_RNG).
@@ -167,7 +173,9 @@ int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev);
 /* Replaces FixEPH::end_of_step (fix_eph.cpp:350-429): energy bookkeeping,
  * EPH_FDM::insert_energy (eph_fdm.h:172-179), EPH_FDM::solve (:267-400) and the
  * 8-column per-atom output.  E_local (host pointer, may be NULL) receives this
- * rank's energy transfer of the step; passing NULL avoids the host sync. */
+ * rank's energy transfer of the step; passing NULL avoids the host sync.
+ * x may be NULL: the positions of the last post_force are used (the Verlet loop
+ * does not move atoms between post_force and end_of_step), saving their upload. */
 int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace);
 
 /* Replaces the integrator hooks (fix_eph.cpp:305-348). mass_by_type is 1-based [ntypes+1]. */

@@ -419,6 +419,42 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
 
 
+def test_device_built_neighbor_list(synth_beta_1):
+    """eph_b200_build_neighbors: same pair set as the host list (LAMMPS' REQ_FULL semantics) and same results"""
+    s = H.make_system(7, sigma=0.08)
+    nl = s["nlocal"]
+    eng = make_engine(synth_beta_1, 7, (2, 2, 2), box6(s))
+    eng.set_atoms(nl, s["nghost"], np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
+                  np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(s["ghost_owner"], dtype=np.int32))
+    eng.build_neighbors(s["x"], 7.0)
+    off, ne = eng.get_neighbors()
+    assert np.array_equal(off, s["offsets"])          # same row lengths ...
+    for i in range(0, nl, 37):                         # ... and the same members
+        assert np.array_equal(np.sort(ne[off[i]:off[i + 1]]), np.sort(s["neigh"][s["offsets"][i]:s["offsets"][i + 1]]))
+    xi = [np.random.default_rng(71).normal(size=(nl, 3)) for _ in range(2)]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(2, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=1e-4)
+    compare(traj.run_engine(eng, s, xi, [58.71], 1e-4), traj.run_oracle(fx, s, xi, [58.71]), nl)
+    # device pointers, and the fix keyword
+    import torch
+    eng.build_neighbors(torch.as_tensor(s["x"], device="cuda"), 7.0)
+    off2, ne2 = eng.get_neighbors()
+    assert np.array_equal(off2, off) and np.array_equal(ne2, ne)
+    g = np.load(os.path.join(GOLDEN, "caseA_example1.npz"))
+    sg = traj.system_from_golden(g)
+    sg["natoms"] = sg["nlocal"]
+    cwd = os.getcwd()
+    os.chdir(GOLDEN)
+    try:
+        drv = host.FixDriver(sg, H.fix_args(3, "Ni_trunc.beta", ["Ni"], grid=(1, 1, 1), style="eph/b200",
+                                            extra=["rng", "mars", "neigh", "device"]), dt=float(g["dt"]))
+    finally:
+        os.chdir(cwd)
+    recs = traj.run_fix_driver(drv, sg, list(g["xi"]))
+    refs = [dict((k, g["out_" + k][i]) for k in ("f", "array", "T", "w", "x", "v", "rho", "Ee", "Tmean")) for i in range(len(recs))]
+    compare(recs, refs, sg["nlocal"])
+    assert drv.neigh_cutoff() == 0.0                   # no list was requested from LAMMPS
+
+
 def test_empty_and_ragged_inputs(synth_beta_1):
     eng = make_engine(synth_beta_1, 7, (2, 2, 2), [0, 10, 0, 10, 0, 10])
     z = np.zeros((0, 3))

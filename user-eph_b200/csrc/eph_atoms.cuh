@@ -156,7 +156,7 @@ __global__ void unpack_payload_kernel(int n, const int *__restrict__ index, doub
 
 struct DepositArgs {
   int nlocal;
-  const double *__restrict__ x;      // LAMMPS layout
+  const double *__restrict__ x;      // LAMMPS layout, or nullptr: positions unchanged since post_force (use pos4)
   const double *__restrict__ v;
   const double4 *__restrict__ pos4;  // bits (group) from the last post_force
   const double *__restrict__ f_eph;
@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
       if (d.do_random) { dEr -= rx * vx * d.dt; dEr -= ry * vy * d.dt; dEr -= rz * vz * d.dt; }
       dE = dEf + dEr;
       contrib = dEf / d.dVdt + dEr / d.dVdt;  // two insert_energy calls in the reference
-      cell = grid_index(d.grid, d.x[o], d.x[o + 1], d.x[o + 2]);
+      if (d.x != nullptr) cell = grid_index(d.grid, d.x[o], d.x[o + 1], d.x[o + 2]);
+      else {
+        const double4 p4 = d.pos4[i];
+        cell = grid_index(d.grid, p4.x, p4.y, p4.z);
+      }
       const double rho = d.rho[i];
       double beta = 0.0;  // eph_beta.h:171-184
       if (!(rho > d.rho_cutoff))

@@ -4,6 +4,7 @@
 #include "eph_b200.h"
 
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -17,6 +18,7 @@
 #include "eph_device.cuh"
 #include "eph_grid.cuh"
 #include "eph_grid_tma.cuh"
+#include "eph_neigh.cuh"
 #include "eph_sweeps.cuh"
 
 using namespace ephb;
@@ -107,6 +109,13 @@ struct eph_b200_handle {
   const long long *off_ptr = nullptr;  // device pointers actually used (own or caller's)
   const int *neigh_ptr = nullptr;
 
+  // device-side neighbour list construction (eph_b200_build_neighbors)
+  DevBuf<int> nb_cell, nb_atom, nb_cell_s, nb_atom_s, nb_start, nb_end;
+  DevBuf<double4> nb_xs;
+  DevBuf<long long> nb_counts;
+  DevBuf<unsigned char> nb_tmp;
+  DevBuf<double> nb_box;
+
   // two-level Verlet list: inner list with a small skin, rebuilt on the device from LAMMPS' list
   DevBuf<int> ineigh, icount;
   DevBuf<double4> xref, xref0;          // positions at the last inner build / at LAMMPS' build
@@ -121,6 +130,9 @@ struct eph_b200_handle {
   unsigned *h_flag = nullptr;            // pinned mirror of lstate.inner_invalid
   cudaEvent_t flag_event = nullptr;
   bool flag_pending = false;
+  cudaStream_t copy_stream = nullptr;    // host memspace: f goes up while the density pass runs
+  cudaEvent_t f_event = nullptr;
+  bool f_prefetched = false;
   long long inner_builds = 0, inner_fallback_steps = 0;
 
   // grid
@@ -334,6 +346,8 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
             h->lstate.reserve(1) == cudaSuccess && cudaMemset(h->lstate.p, 0, sizeof(ListState)) == cudaSuccess &&
             cudaMallocHost(&h->h_flag, sizeof(unsigned)) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->flag_event, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->f_event, cudaEventDisableTiming) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             h->d_mm.reserve(4) == cudaSuccess && h->d_status.reserve(1) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 8 * sizeof(double)) == cudaSuccess &&
             cudaMemcpy(h->d_type_map.p, h->type_map.data(), cfg->ntypes * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -363,9 +377,13 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->d_scal.release(); h->d_mm.release(); h->d_status.release();
   drain_timers(h);
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  h->nb_cell.release(); h->nb_atom.release(); h->nb_cell_s.release(); h->nb_atom_s.release(); h->nb_start.release();
+  h->nb_end.release(); h->nb_xs.release(); h->nb_counts.release(); h->nb_tmp.release(); h->nb_box.release();
   h->ineigh.release(); h->icount.release(); h->xref.release(); h->xref0.release(); h->lstate.release();
   if (h->h_flag) cudaFreeHost(h->h_flag);
   if (h->flag_event) cudaEventDestroy(h->flag_event);
+  if (h->f_event) cudaEventDestroy(h->f_event);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -663,6 +681,89 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
   return EPH_B200_OK;
 }
 
+// Builds the full list on the device from the positions: rows of local atoms over all atoms closer than `cutoff`
+// (r_c + skin).  Same pair set as LAMMPS' REQ_FULL list, so the fix need not request (and LAMMPS need not build and
+// the host need not upload) that list at all.
+int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: call set_atoms first");
+  if (!x || !(cutoff > 0.0)) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: null positions or bad cut-off");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal, nt = h->nlocal + h->nghost;
+  if (nl == 0) {
+    const long long zero = 0;
+    return eph_b200_set_neighbors_csr(h, 0, reinterpret_cast<const int64_t *>(&zero), nullptr, EPH_B200_HOST);
+  }
+  const double *dx = nullptr;
+  int rc;
+  if ((rc = stage_in(h, h->x, x, 3 * (size_t)nt, memspace, &dx))) return rc;
+  KernelTimer kt(h, "build_neighbors");
+  // bounding box of locals + ghosts
+  EPH_CUDA(h, h->nb_box.reserve(6));
+  const double init[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+  double box[6];
+  EPH_CUDA(h, cudaMemcpyAsync(h->nb_box.p, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  bbox_kernel<<<std::min(blocks_for(nt, 256), 8 * h->sm_count), 256, 0, h->stream>>>(nt, dx, h->nb_box.p);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cudaMemcpyAsync(box, h->nb_box.p, sizeof box, cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  CellGrid g;
+  long long ncell = 1;
+  for (int d = 0; d < 3; ++d) {
+    const double len = std::max(box[3 + d] - box[d], 1e-9);
+    g.nb[d] = std::max(1, (int)std::floor(len / (0.5 * cutoff)));   // cells of at least cutoff/2: +-2 cells cover the cut-off
+    g.lo[d] = box[d];
+    g.inv[d] = g.nb[d] / (len * (1.0 + 1e-12));
+    ncell *= g.nb[d];
+  }
+  if (ncell > 500000000LL) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: %lld cells (box far larger than the atoms?)", ncell);
+  EPH_CUDA(h, h->nb_cell.reserve(nt)); EPH_CUDA(h, h->nb_atom.reserve(nt)); EPH_CUDA(h, h->nb_cell_s.reserve(nt));
+  EPH_CUDA(h, h->nb_atom_s.reserve(nt)); EPH_CUDA(h, h->nb_xs.reserve(nt)); EPH_CUDA(h, h->nb_start.reserve(ncell));
+  EPH_CUDA(h, h->nb_end.reserve(ncell)); EPH_CUDA(h, h->nb_counts.reserve((size_t)nl + 1)); EPH_CUDA(h, h->off.reserve((size_t)nl + 1));
+  cell_id_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, g, h->nb_cell.p, h->nb_atom.p);
+  EPH_LAUNCH_CHECK(h);
+  int bits = 1;
+  while ((1LL << bits) < ncell) ++bits;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->nb_cell.p, h->nb_cell_s.p, h->nb_atom.p, h->nb_atom_s.p, nt, 0, bits, h->stream);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->nb_counts.p, h->off.p, nl + 1, h->stream);
+  EPH_CUDA(h, h->nb_tmp.reserve(std::max(tmp_bytes, scan_bytes)));
+  EPH_CUDA(h, cub::DeviceRadixSort::SortPairs(h->nb_tmp.p, tmp_bytes, h->nb_cell.p, h->nb_cell_s.p, h->nb_atom.p, h->nb_atom_s.p, nt, 0, bits, h->stream));
+  ++h->launches;
+  EPH_CUDA(h, cudaMemsetAsync(h->nb_start.p, 0, (size_t)ncell * sizeof(int), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->nb_end.p, 0, (size_t)ncell * sizeof(int), h->stream));
+  cell_ranges_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, h->nb_cell_s.p, h->nb_atom_s.p, dx, h->nb_xs.p, h->nb_start.p, h->nb_end.p);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cudaMemsetAsync(h->nb_counts.p + nl, 0, sizeof(long long), h->stream));
+  neighbor_pass_kernel<false><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                          h->nb_counts.p, nullptr, nullptr);
+  EPH_LAUNCH_CHECK(h);
+  EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->nb_counts.p, h->off.p, nl + 1, h->stream));
+  ++h->launches;
+  long long total = 0;
+  EPH_CUDA(h, cudaMemcpyAsync(&total, h->off.p + nl, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  EPH_CUDA(h, h->neigh.reserve((size_t)std::max<long long>(total, 1)));
+  neighbor_pass_kernel<true><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                         nullptr, h->off.p, h->neigh.p);
+  EPH_LAUNCH_CHECK(h);
+  // hand the device-resident CSR to the common path (aliases our own buffers: no copy)
+  return eph_b200_set_neighbors_csr(h, nl, reinterpret_cast<const int64_t *>(h->off.p), h->neigh.p, EPH_B200_DEVICE);
+}
+
+// read-back of the list currently in use (tests, diagnostics): offsets[nlocal+1]; neigh may be NULL to query the size
+int eph_b200_get_neighbors(eph_b200_handle *h, int64_t *offsets, int *neigh, long long *n_entries) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "get_neighbors: no list");
+  cudaSetDevice(h->cfg.device);
+  if (n_entries) *n_entries = h->n_entries;
+  if (offsets) EPH_CUDA(h, cudaMemcpyAsync(offsets, h->off_ptr, ((size_t)h->nlocal + 1) * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  if (neigh && h->n_entries > 0) EPH_CUDA(h, cudaMemcpyAsync(neigh, h->neigh_ptr, (size_t)h->n_entries * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
 int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *numneigh, int *const *firstneigh) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!numneigh || (!firstneigh && nlocal > 0)) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: null list");
@@ -863,9 +964,11 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   double *df = f;
   if (memspace != EPH_B200_DEVICE) {
     EPH_CUDA(h, h->f.reserve(3 * (size_t)nl));
-    if (add_fric || add_rand) EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->f_prefetched) EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));   // uploaded behind the density pass
+    else if (add_fric || add_rand) EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     df = h->f.p;
   }
+  h->f_prefetched = false;
   const bool build = h->pf_build;
 
   PrepArgs p{};
@@ -907,6 +1010,17 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
   if (h && !f && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "post_force: null x, v or f");
   int rc = eph_b200_post_force_begin(h, x, v, xi_inject, ntimestep, memspace);
   if (rc) return rc;
+  if (memspace != EPH_B200_DEVICE && h->nlocal > 0 && h->pf_open) {
+    // f is only needed by the force pass: send it up on the copy stream while the density pass runs
+    const bool add = ((h->cfg.flags & EPH_B200_FRICTION) && !(h->cfg.flags & EPH_B200_NOFRICTION)) ||
+                     ((h->cfg.flags & EPH_B200_RANDOM) && !(h->cfg.flags & EPH_B200_NORANDOM));
+    if (add) {
+      EPH_CUDA(h, h->f.reserve(3 * (size_t)h->nlocal));
+      EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)h->nlocal * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      EPH_CUDA(h, cudaEventRecord(h->f_event, h->copy_stream));
+      h->f_prefetched = true;
+    }
+  }
   return eph_b200_post_force_end(h, f, memspace);
 }
 
@@ -1028,13 +1142,14 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->forces_valid) return fail(h, EPH_B200_ERR_ARG, "end_of_step: post_force has not run");
   if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "end_of_step: set_grid not called");
-  if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "end_of_step: null x or v");
+  if (!v) return fail(h, EPH_B200_ERR_ARG, "end_of_step: null v");
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal;
   const double *dx = nullptr, *dv = nullptr;
   int rc;
-  // only the local part is read here
-  if ((rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
+  // only the local part is read here; x == NULL: positions are those of the last post_force (Verlet does not move
+  // atoms between post_force and end_of_step), so nothing is uploaded for them
+  if (x && (rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
   if ((rc = stage_in(h, h->v, v, 3 * (size_t)nl, memspace, &dv))) return rc;
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {

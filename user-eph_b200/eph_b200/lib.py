@@ -45,6 +45,8 @@ SYMBOLS = {
     "eph_b200_set_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_neighbors_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_neighbors_lammps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_build_neighbors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
+    "eph_b200_get_neighbors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_longlong)]),
     "eph_b200_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
     "eph_b200_end_of_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),
     "eph_b200_post_force_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
@@ -216,6 +218,19 @@ class Engine:
         ps = [_ptr(offsets), _ptr(neigh)]
         self._check(self.lib.eph_b200_set_neighbors_csr(self.h, self.nlocal, ps[0][0], ps[1][0], _space(*ps)))
         self._keep = (offsets, neigh)  # device memspace aliases the caller's buffers
+
+    def build_neighbors(self, x, cutoff):
+        """full list built on the device from positions (instead of uploading LAMMPS' list)"""
+        p = _ptr(x)
+        self._check(self.lib.eph_b200_build_neighbors(self.h, p[0], cutoff, p[1]))
+
+    def get_neighbors(self):
+        n = C.c_longlong()
+        self._check(self.lib.eph_b200_get_neighbors(self.h, None, None, C.byref(n)))
+        off = np.empty(self.nlocal + 1, dtype=np.int64)
+        ne = np.empty(max(n.value, 1), dtype=np.int32)
+        self._check(self.lib.eph_b200_get_neighbors(self.h, off.ctypes.data, ne.ctypes.data, None))
+        return off, ne[: n.value]
 
     # -- per step -------------------------------------------------------------
     def post_force(self, x, v, f, xi=None, step=0):

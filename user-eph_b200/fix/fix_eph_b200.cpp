@@ -117,6 +117,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
   // optional keyword pairs after the element names
   rng_mars = false;
   comm_lammps = nrPS > 1;
+  neigh_device = false;
   int device = -1;
   for (int k = 17 + types; k + 1 < narg; k += 2) {
     if (strcmp(arg[k], "rng") == 0) {
@@ -125,6 +126,10 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
       else error->all(FLERR, "fix eph/b200: rng must be mars or philox");
     } else if (strcmp(arg[k], "device") == 0) {
       device = atoi(arg[k + 1]);
+    } else if (strcmp(arg[k], "neigh") == 0) {
+      if (strcmp(arg[k + 1], "device") == 0) neigh_device = true;
+      else if (strcmp(arg[k + 1], "lammps") == 0) neigh_device = false;
+      else error->all(FLERR, "fix eph/b200: neigh must be device or lammps");
     } else if (strcmp(arg[k], "comm") == 0) {
       if (strcmp(arg[k + 1], "lammps") == 0) comm_lammps = true;
       else if (strcmp(arg[k + 1], "device") == 0) comm_lammps = false;
@@ -208,10 +213,13 @@ void FixEPHB200::init() {
   if (domain->nonperiodic != 0) error->all(FLERR, "Cannot use nonperiodic boundares with fix eph");
   if (domain->triclinic) error->all(FLERR, "Cannot use fix eph with triclinic box");
 
-  // full neighbour list including ghosts, cut-off r_c (fix_eph.cpp:273-275)
-  int request_style = NeighConst::REQ_FULL | NeighConst::REQ_GHOST;
-  auto req = neighbor->add_request(this, request_style);
-  req->set_cutoff(r_cutoff);
+  // full neighbour list including ghosts, cut-off r_c (fix_eph.cpp:273-275); with `neigh device` the engine builds
+  // the same list from the positions and LAMMPS need not build (nor the host upload) a second full list for this fix
+  if (!neigh_device) {
+    int request_style = NeighConst::REQ_FULL | NeighConst::REQ_GHOST;
+    auto req = neighbor->add_request(this, request_style);
+    req->set_cutoff(r_cutoff);
+  }
 
   reset_dt();
 }
@@ -279,7 +287,8 @@ void FixEPHB200::upload_topology() {
   check(eph_b200_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, reinterpret_cast<const int64_t *>(atom->tag),
                            ghost_owner.data(), EPH_B200_HOST),
         "set_atoms");
-  check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
+  if (neigh_device) check(eph_b200_build_neighbors(dev, &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
+  else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
   atoms_epoch = ((long long)nlocal << 32) | (unsigned)nghost;
   need_upload = false;
 }

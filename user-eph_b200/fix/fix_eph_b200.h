@@ -7,6 +7,8 @@
  *                     on atom tags, so no XI ghost exchange is needed; mars: LAMMPS' RanMars on the host in the
  *                     reference's order, fix_eph.cpp:854-861, uploaded every step)
  *   device N          CUDA device ordinal (default: rank modulo visible devices)
+ *   neigh lammps|device the full neighbour list comes from LAMMPS (uploaded when it is rebuilt; default) or is built
+ *                     on the device from the positions (LAMMPS then builds no list for this fix)
  *   comm device|lammps ghost values through the engine's own owner map (single rank, default) or through LAMMPS'
  *                     Comm::forward_comm(Fix*) with host buffers, as the reference does (default for several ranks)
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
@@ -88,6 +90,7 @@ class FixEPHB200 : public Fix {
   class RanMars *random;
   bool rng_mars;
   bool comm_lammps;
+  bool neigh_device;
   class NeighList *list;
   double Ee;
   size_t n;
