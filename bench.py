@@ -249,9 +249,13 @@ def run_b200(a):
     eng.set_neighbors(d_off, d_neigh)
     eng.bind_grid_source(d_src)
     exch = P.GhostExchange(plan, D, dev)
+    gstream = None
+    if D:   # grid all-reduce + solve on a second stream: they overlap the next step's density pass
+        gstream = torch.cuda.Stream(device=dev)
+        eng.set_grid_stream(gstream.cuda_stream)
 
     def step_resident(k):
-        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src)
+        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src, grid_stream=gstream)
 
     def timed(fn, steps, first):
         """barrier + synchronize on both sides, device time via CUDA events, max over ranks"""
@@ -345,7 +349,8 @@ def run_b200(a):
                     exch(eng)
                     eng.post_force_end(nf)                  # f up, f down
                     eng.end_of_step_begin(None, nv)         # v (locals) up; positions are those of post_force
-                    D.all_reduce(d_src)
+                    with torch.cuda.stream(gstream):
+                        D.all_reduce(d_src)
                     return eng.end_of_step_end(True)        # E_local down
                 eng.post_force(nx, nv, nf, None, k)         # x, v, f up (f behind the density pass), f down
                 return eng.end_of_step(None, nv)            # v up, E_local down

@@ -169,6 +169,11 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace);
 int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double *v, int memspace);
 int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local);
 int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev);
+/* Optional second CUDA stream for the grid.  When set, end_of_step_begin makes that stream wait for the deposit,
+ * end_of_step_end enqueues the solve on it, and the engine's main stream waits for the solve only where it needs
+ * T_e or dT_e again (the force pass, the next deposit, grid read-backs).  A caller that issues its all-reduce of the
+ * source term on the same stream thus overlaps all-reduce + solve with the next step's density pass. */
+int eph_b200_set_grid_stream(eph_b200_handle *h, void *stream);
 
 /* Replaces FixEPH::end_of_step (fix_eph.cpp:350-429): energy bookkeeping,
  * EPH_FDM::insert_energy (eph_fdm.h:172-179), EPH_FDM::solve (:267-400) and the

@@ -346,6 +346,7 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
     dev = torch.device("cuda", 0)
     # one stream for torch and all engines, so the copies that stand in for NCCL are ordered with the kernels
     tstream = torch.cuda.Stream(device=dev)
+    gstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     n, seed, dt = 6, 4711, 1e-4
     whole = H.make_system(n)
@@ -366,6 +367,7 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
         eng.set_neighbors(t(s["offsets"], torch.int64), t(s["neigh"], torch.int32))
         src = torch.zeros(int(np.prod(gshape)), dtype=torch.float64, device=dev)
         eng.bind_grid_source(src)
+        eng.set_grid_stream(gstream.cuda_stream)     # source all-reduce + solve on a second stream
         engines.append(eng)
         state.append(dict(x=t(s["x"], torch.float64), v=t(s["v"], torch.float64),
                           f=torch.zeros((s["nlocal"], 3), dtype=torch.float64, device=dev), src=src,
@@ -396,14 +398,17 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
             assert rb.shape[0] == st["recv"].numel()
             if st["recv"].numel():
                 eng.unpack_ghost_payload(st["recv"], rb.contiguous())
-        total = torch.zeros_like(state[0]["src"])
         for eng, st in zip(engines, state):
             eng.post_force_end(st["f"])
             eng.end_of_step_begin(st["x"], st["v"])
-            total += st["src"]
+        with torch.cuda.stream(gstream):    # all-reduce of the source term, on the grid stream like dist.all_reduce would be
+            total = torch.zeros_like(state[0]["src"])
+            for st in state:
+                total += st["src"]
+            for st in state:
+                st["src"].copy_(total)
         E = 0.0
         for eng, st in zip(engines, state):
-            st["src"].copy_(total)          # all-reduce of the source term
             E += eng.end_of_step_end(True)
         # compare per atom by tag
         ref_f, ref_rho = fx.f[: whole["nlocal"]], np.array(fx.ptr(0))[: whole["nlocal"]]

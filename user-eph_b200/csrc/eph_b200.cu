@@ -99,6 +99,10 @@ struct eph_b200_handle {
   const double *pf_xi = nullptr;
   long long pf_step = 0;
   bool eos_open = false;
+  // optional second stream for the grid: the source all-reduce and the solve overlap the next step's density pass
+  cudaStream_t grid_stream = nullptr;
+  cudaEvent_t ev_deposit = nullptr, ev_solved = nullptr;
+  bool solve_pending = false;
   double *dT_e_ext = nullptr;   // caller-owned grid source term (multi-rank: all-reduced between the two end_of_step halves)
 
   // neighbours
@@ -203,16 +207,17 @@ struct KernelTimer {
   eph_b200_handle *h;
   int idx = -1;
   cudaEvent_t beg = nullptr;
-  KernelTimer(eph_b200_handle *h_, const char *name) : h(h_) {
+  cudaStream_t st;
+  KernelTimer(eph_b200_handle *h_, const char *name, cudaStream_t st_ = nullptr) : h(h_), st(st_ ? st_ : h_->stream) {
     if (!h->profiling) return;
     idx = stat_index(h, name);
     beg = take_event(h);
-    cudaEventRecord(beg, h->stream);
+    cudaEventRecord(beg, st);
   }
   ~KernelTimer() {
     if (idx < 0) return;
     cudaEvent_t end = take_event(h);
-    cudaEventRecord(end, h->stream);
+    cudaEventRecord(end, st);
     h->pending.push_back({idx, beg, end});
   }
 };
@@ -245,6 +250,14 @@ void drain_timers(eph_b200_handle *h) {
     if (e_ != cudaSuccess)                                                                               \
       return fail(h, EPH_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// the main stream must not read T_e / write dT_e before a solve running on the grid stream has finished
+inline void join_grid_stream(eph_b200_handle *h) {
+  if (h->solve_pending) {
+    cudaStreamWaitEvent(h->stream, h->ev_solved, 0);
+    h->solve_pending = false;
+  }
+}
 
 inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
@@ -347,6 +360,8 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
             cudaMallocHost(&h->h_flag, sizeof(unsigned)) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->flag_event, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->f_event, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_deposit, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             h->d_mm.reserve(4) == cudaSuccess && h->d_status.reserve(1) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 8 * sizeof(double)) == cudaSuccess &&
@@ -383,6 +398,8 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (h->h_flag) cudaFreeHost(h->h_flag);
   if (h->flag_event) cudaEventDestroy(h->flag_event);
   if (h->f_event) cudaEventDestroy(h->f_event);
+  if (h->ev_deposit) cudaEventDestroy(h->ev_deposit);
+  if (h->ev_solved) cudaEventDestroy(h->ev_solved);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -416,6 +433,7 @@ int eph_b200_kernel_times(eph_b200_handle *h, int max, const char **names, doubl
 int eph_b200_synchronize(eph_b200_handle *h) {
   if (!h) return EPH_B200_ERR_ARG;
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->grid_stream) EPH_CUDA(h, cudaStreamSynchronize(h->grid_stream));
   return EPH_B200_OK;
 }
 
@@ -535,6 +553,7 @@ int eph_b200_get_grid(eph_b200_handle *h, int which, double *out) {
   double *p = grid_field(h, which);
   if (!p) return fail(h, EPH_B200_ERR_ARG, "get_grid: bad field id %d", which);
   cudaSetDevice(h->cfg.device);
+  join_grid_stream(h);
   EPH_CUDA(h, cudaMemcpyAsync(out, p, h->ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
   return EPH_B200_OK;
@@ -546,6 +565,7 @@ int eph_b200_put_grid(eph_b200_handle *h, int which, const double *in) {
   double *p = grid_field(h, which);
   if (!p) return fail(h, EPH_B200_ERR_ARG, "put_grid: bad field id %d", which);
   cudaSetDevice(h->cfg.device);
+  join_grid_stream(h);
   EPH_CUDA(h, cudaMemcpyAsync(p, in, h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
   if (which >= 1 && which <= 4) h->uniform = false;   // parameters changed cell by cell: general kernel from now on
@@ -557,6 +577,7 @@ int eph_b200_mean_T(eph_b200_handle *h, double *out) {
   if (!h || !out) return EPH_B200_ERR_ARG;
   if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "mean_T: no grid");
   cudaSetDevice(h->cfg.device);
+  join_grid_stream(h);
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p + 1, 0, sizeof(double), h->stream));
   fdm_sum_kernel<<<std::min(blocks_for(h->ncell, 256), 4 * h->sm_count), 256, 0, h->stream>>>(h->ncell, h->T[h->cur].p, h->d_scal.p + 1);
   EPH_LAUNCH_CHECK(h);
@@ -970,6 +991,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   }
   h->f_prefetched = false;
   const bool build = h->pf_build;
+  join_grid_stream(h);   // the force pass reads T_e
 
   PrepArgs p{};
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
@@ -1059,25 +1081,25 @@ namespace {
 // EPH_FDM::solve (eph_fdm.h:267-400).  The sub-step count is decided on the
 // host with the reference's exact double arithmetic and truncating cast from
 // three device-reduced scalars; they are cached while the parameters are constant.
-int grid_solve(eph_b200_handle *h) {
+int grid_solve(eph_b200_handle *h, cudaStream_t st) {
   const long long n = h->ncell;
   if (h->has_tdyn) {
     if (h->n_T < 4) return fail(h, EPH_B200_ERR_ARG, "solve: grid has temperature-dependent cells but no parameter tables");
-    fdm_refresh_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, h->T[h->cur].p, h->t_dyn.p, h->C_T_tab.p, h->K_T_tab.p,
+    fdm_refresh_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, h->T[h->cur].p, h->t_dyn.p, h->C_T_tab.p, h->K_T_tab.p,
                                                                    1. / h->dT_tab, h->C_e.p, h->kappa_e.p);
     EPH_LAUNCH_CHECK(h);
     h->minmax_valid = false;
   }
   if (!h->minmax_valid) {
     // seed with cell 0 (eph_fdm.h:290-292)
-    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 0, h->C_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 1, h->rho_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 2, h->kappa_e.p, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    fdm_minmax_kernel<<<std::min(blocks_for(n, 256), 4 * h->sm_count), 256, 0, h->stream>>>(
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 0, h->C_e.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 1, h->rho_e.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    EPH_CUDA(h, cudaMemcpyAsync(h->d_mm.p + 2, h->kappa_e.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    fdm_minmax_kernel<<<std::min(blocks_for(n, 256), 4 * h->sm_count), 256, 0, st>>>(
         n, h->C_e.p, h->rho_e.p, h->kappa_e.p, h->flag.p, h->d_mm.p);
     EPH_LAUNCH_CHECK(h);
-    EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned + 2, h->d_mm.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned + 2, h->d_mm.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EPH_CUDA(h, cudaStreamSynchronize(st));
     h->c_min = h->h_pinned[2]; h->rho_min = h->h_pinned[3]; h->kappa_max = h->h_pinned[4];
     h->minmax_valid = true;
   }
@@ -1107,7 +1129,7 @@ int grid_solve(eph_b200_handle *h) {
     g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
     g.clear_source = (s + 1 == new_steps) ? 1 : 0;
     {
-      KernelTimer kt(h, "fdm_substep");
+      KernelTimer kt(h, "fdm_substep", st);
       if (h->tma_ok && h->uniform) {
         if (h->map_S_base != g.dT_e) {   // the source array may be caller-owned (bind_grid_source)
           if (!encode_grid_map(&h->map_S, g.dT_e, h->nx, h->ny, h->nz, kTX, kTY, kTZ)) return fail(h, EPH_B200_ERR_CUDA, "solve: cannot encode the source tensor map");
@@ -1118,14 +1140,14 @@ int grid_solve(eph_b200_handle *h) {
         u.kappa = h->u_kappa; u.S = h->u_S; u.rho = h->u_rho; u.C = h->u_C;
         u.inv_dx2 = g.inv_dx2; u.inv_dy2 = g.inv_dy2; u.inv_dz2 = g.inv_dz2; u.inner_dt = g.inner_dt;
         u.clear_source = g.clear_source; u.status = g.status;
-        fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, h->stream>>>(h->map_T[h->cur], h->map_S, u);
+        fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, st>>>(h->map_T[h->cur], h->map_S, u);
       } else if (h->tma_ok) {
         GridTmaArgs ta;
         ta.g = g;
         ta.has_walls = h->has_walls ? 1 : 0;
-        fdm_substep_tma_kernel<<<tgrid, 256, kTmaSmemBytes, h->stream>>>(h->map_T[h->cur], h->map_K, ta);
+        fdm_substep_tma_kernel<<<tgrid, 256, kTmaSmemBytes, st>>>(h->map_T[h->cur], h->map_K, ta);
       } else {
-        fdm_substep_kernel<<<grid, block, 0, h->stream>>>(g);
+        fdm_substep_kernel<<<grid, block, 0, st>>>(g);
       }
     }
     EPH_LAUNCH_CHECK(h);
@@ -1151,6 +1173,7 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   // atoms between post_force and end_of_step), so nothing is uploaded for them
   if (x && (rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
   if ((rc = stage_in(h, h->v, v, 3 * (size_t)nl, memspace, &dv))) return rc;
+  join_grid_stream(h);   // the previous solve clears dT_e
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {
     DepositArgs d{};
@@ -1166,6 +1189,10 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
     }
     EPH_LAUNCH_CHECK(h);
   }
+  if (h->grid_stream) {   // whatever runs next on the grid stream (the caller's all-reduce, the solve) comes after the deposit
+    EPH_CUDA(h, cudaEventRecord(h->ev_deposit, h->stream));
+    EPH_CUDA(h, cudaStreamWaitEvent(h->grid_stream, h->ev_deposit, 0));
+  }
   h->eos_open = true;
   return EPH_B200_OK;
 }
@@ -1176,8 +1203,13 @@ int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local) {
   h->eos_open = false;
   cudaSetDevice(h->cfg.device);
   int rc;
+  cudaStream_t st = h->grid_stream ? h->grid_stream : h->stream;
   if (h->cfg.flags & EPH_B200_FDM) {
-    if ((rc = grid_solve(h))) return rc;
+    if ((rc = grid_solve(h, st))) return rc;
+  }
+  if (h->grid_stream) {
+    EPH_CUDA(h, cudaEventRecord(h->ev_solved, h->grid_stream));
+    h->solve_pending = true;
   }
   if (E_local) {
     EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1191,6 +1223,15 @@ int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, d
   int rc = eph_b200_end_of_step_begin(h, x, v, memspace);
   if (rc) return rc;
   return eph_b200_end_of_step_end(h, E_local);
+}
+
+int eph_b200_set_grid_stream(eph_b200_handle *h, void *stream) {
+  if (!h) return EPH_B200_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  join_grid_stream(h);
+  if (h->grid_stream) cudaStreamSynchronize(h->grid_stream);
+  h->grid_stream = static_cast<cudaStream_t>(stream);
+  return EPH_B200_OK;
 }
 
 int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev) {

@@ -56,6 +56,7 @@ SYMBOLS = {
     "eph_b200_end_of_step_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_end_of_step_end": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_bind_grid_source": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eph_b200_set_grid_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_double, C.c_int]),
     "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
@@ -264,6 +265,9 @@ class Engine:
     def bind_grid_source(self, tensor):
         self._check(self.lib.eph_b200_bind_grid_source(self.h, tensor.data_ptr() if tensor is not None else None))
         self._src = tensor
+
+    def set_grid_stream(self, stream):
+        self._check(self.lib.eph_b200_set_grid_stream(self.h, C.c_void_p(stream) if stream else None))
 
     def end_of_step(self, x, v, want_energy=True):
         ps = [_ptr(x), _ptr(v)]

@@ -132,12 +132,20 @@ class GhostExchange:
         return 32 * (self.send_idx.numel() + self.recv_idx.numel())
 
 
-def distributed_step(engine, exchange, dist, x, v, f, step, dT_e, want_energy=False):
-    """One `fix eph` step on one rank of a multi-GPU run (device tensors)."""
+def distributed_step(engine, exchange, dist, x, v, f, step, dT_e, want_energy=False, grid_stream=None):
+    """One `fix eph` step on one rank of a multi-GPU run (device tensors).
+
+    grid_stream: a torch.cuda.Stream registered with engine.set_grid_stream(); the all-reduce of the source term and
+    the grid solve then run on it and overlap the next step's density pass."""
     engine.post_force_begin(x, v, None, step)
     exchange(engine)
     engine.post_force_end(f)
     engine.end_of_step_begin(x, v)
     if dist is not None and dist.get_world_size() > 1:
-        dist.all_reduce(dT_e)      # the reference's MPI_Allreduce of the grid source term (eph_fdm.h:481)
+        if grid_stream is not None:
+            import torch
+            with torch.cuda.stream(grid_stream):
+                dist.all_reduce(dT_e)
+        else:
+            dist.all_reduce(dT_e)      # the reference's MPI_Allreduce of the grid source term (eph_fdm.h:481)
     return engine.end_of_step_end(want_energy)
