@@ -14,13 +14,14 @@ struct ListState {
   unsigned long long disp0_sq_bits;  // max squared displacement since LAMMPS built its list (double bits, >= 0)
 };
 
-// x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits}, v4 {vx,vy,vz,0}; with track != 0 also the displacement
+// x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits} and the density-pass record pv {x,y,z,bits | vx,vy,vz,0}
+// (eph_sweeps.cuh); with track != 0 also the displacement
 // checks that guard the inner list: against xref (positions when the inner list was built) and against xref0
 // (positions when LAMMPS built its list).
 __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const double *__restrict__ x, const double *__restrict__ v,
                                   const int *__restrict__ type, const int *__restrict__ mask,
                                   const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
-                                  double4 *__restrict__ v4, int track, const double4 *__restrict__ xref,
+                                  double4 *__restrict__ pv, int track, const double4 *__restrict__ xref,
                                   const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st) {
   __shared__ double s_max[8];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,8 +30,10 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
     unsigned bits = static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask;
     if (mask[a] & groupbit) bits |= kBitGroup;
     const double px = x[3 * (size_t)a], py = x[3 * (size_t)a + 1], pz = x[3 * (size_t)a + 2];
-    pos4[a] = make_double4(px, py, pz, bits_to_double(bits));
-    v4[a] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+    const double4 p4 = make_double4(px, py, pz, bits_to_double(bits));
+    pos4[a] = p4;
+    pv[2 * (size_t)a] = p4;
+    pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
     if (track) {
       const double4 r = xref[a], r0 = xref0[a];
       const double dx = px - r.x, dy = py - r.y, dz = pz - r.z;
@@ -64,9 +67,8 @@ struct PrepArgs {
   int do_random;
   double *__restrict__ rho;    // [ntotal]; ghost entries are filled here
   const double4 *__restrict__ W4;  // [nlocal] (or [ntotal] after an exchange) pair sums of the density pass
-  double4 *__restrict__ pos4;  // validity bit is set here
-  double4 *__restrict__ z4;    // [ntotal] s * xi
-  double4 *__restrict__ u4;    // [ntotal] s * w
+  const double4 *__restrict__ pos4;  // [ntotal] x, y, z, bits of pack_atoms
+  double4 *__restrict__ puz;   // [ntotal][3] force-pass record {x,y,z,bits+valid | u = s*w, z = s*xi} (eph_sweeps.cuh)
   double *__restrict__ w;      // [nlocal][3] w_i (probe / forward-comm payload)
   double *__restrict__ xi;     // [ntotal][3] xi_i (probe / XI forward-comm slots)
   unsigned *__restrict__ status;
@@ -110,9 +112,7 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
     s = alpha / rho;
   }
   pa.w = bits_to_double(bits);
-  p.pos4[a] = pa;
   const double wx = s * W.x, wy = s * W.y, wz = s * W.z;   // w_i = alpha_i/rho_i * sum (prescaler of fix_eph.cpp:727)
-  p.u4[a] = make_double4(s * wx, s * wy, s * wz, 0.0);
   if (a < p.nlocal) {
     p.w[3 * (size_t)a] = wx; p.w[3 * (size_t)a + 1] = wy; p.w[3 * (size_t)a + 2] = wz;
   }
@@ -127,7 +127,10 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
       xi_stream(p.seed, p.step, p.tag[a], xi);
     }
   }
-  p.z4[a] = make_double4(s * xi[0], s * xi[1], s * xi[2], 0.0);
+  double4 *rec = p.puz + 3 * (size_t)a;
+  rec[0] = pa;
+  rec[1] = make_double4(s * wx, s * wy, s * wz, s * xi[0]);
+  rec[2] = make_double4(s * xi[1], s * xi[2], 0.0, 0.0);
   if (a < p.nlocal) {
     p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
   }

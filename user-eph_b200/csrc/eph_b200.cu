@@ -91,7 +91,7 @@ struct eph_b200_handle {
   DevBuf<double> mass;
 
   // internal per-atom records
-  DevBuf<double4> pos4, v4, z4, u4, W4;
+  DevBuf<double4> pos4, pv, puz, W4;
   DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
   bool forces_valid = false;
   // state between post_force_begin and post_force_end
@@ -107,7 +107,7 @@ struct eph_b200_handle {
 
   // neighbours
   DevBuf<long long> off;
-  DevBuf<int> neigh, cneigh, ccount;
+  DevBuf<int> neigh;
   long long n_entries = 0;
   bool neigh_set = false;
   const long long *off_ptr = nullptr;  // device pointers actually used (own or caller's)
@@ -384,9 +384,9 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->tag.release();
   h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release(); h->comm_idx.release(); h->comm_buf.release();
-  h->pos4.release(); h->v4.release(); h->z4.release(); h->u4.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
+  h->pos4.release(); h->pv.release(); h->puz.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
-  h->off.release(); h->neigh.release(); h->cneigh.release(); h->ccount.release();
+  h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
   h->d_scal.release(); h->d_mm.release(); h->d_status.release();
@@ -641,17 +641,16 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
     EPH_CUDA(h, cudaMemcpyAsync(h->owner.p, ghost_owner, (size_t)nghost * sizeof(int), kind, h->stream));
     h->has_owner = true;
   }
-  EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->v4.reserve(nt)); EPH_CUDA(h, h->z4.reserve(nt)); EPH_CUDA(h, h->u4.reserve(nt));
+  EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->pv.reserve(2 * nt)); EPH_CUDA(h, h->puz.reserve(3 * nt));
   EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->W4.reserve(nt));
   EPH_CUDA(h, h->xref.reserve(nt)); EPH_CUDA(h, h->xref0.reserve(nt)); EPH_CUDA(h, h->icount.reserve(std::max<size_t>(nlocal, 1)));
   h->have_inner = false;
   const size_t nl = std::max<size_t>(nlocal, 1);
   EPH_CUDA(h, h->w.reserve(3 * nl)); EPH_CUDA(h, h->xi.reserve(3 * std::max<size_t>(nt, 1))); EPH_CUDA(h, h->f_eph.reserve(3 * nl));
-  EPH_CUDA(h, h->f_rng.reserve(3 * nl)); EPH_CUDA(h, h->array8.reserve(8 * nl)); EPH_CUDA(h, h->ccount.reserve(nl));
+  EPH_CUDA(h, h->f_rng.reserve(3 * nl)); EPH_CUDA(h, h->array8.reserve(8 * nl));
   // fresh storage is zero, like the reference constructor (fix_eph.cpp:229-238)
   EPH_CUDA(h, cudaMemsetAsync(h->rho.p, 0, nt * sizeof(double), h->stream));
-  EPH_CUDA(h, cudaMemsetAsync(h->u4.p, 0, nt * sizeof(double4), h->stream));
-  EPH_CUDA(h, cudaMemsetAsync(h->z4.p, 0, nt * sizeof(double4), h->stream));
+  EPH_CUDA(h, cudaMemsetAsync(h->puz.p, 0, 3 * nt * sizeof(double4), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->w.p, 0, 3 * nl * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->xi.p, 0, 3 * std::max<size_t>(nt, 1) * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->f_eph.p, 0, 3 * nl * sizeof(double), h->stream));
@@ -688,7 +687,6 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
     h->neigh_ptr = h->neigh.p;
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
-  EPH_CUDA(h, h->cneigh.reserve((size_t)std::max<long long>(total, 1)));
   EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(total, 1)));
   if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(total, 1)));
   if (h->inner_enabled) EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(total, 1)));
@@ -811,12 +809,31 @@ int resident_grid(eph_b200_handle *h, K kernel, int threads, size_t smem) {
   return h->sm_count * per_sm;  // persistent CTAs: exactly one resident wave
 }
 
+int env_int(const char *name, int dflt) {
+  const char *e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+bool pipelined_density() {
+  static const int v = env_int("EPH_B200_PIPE", 0);
+  return v != 0;
+}
+
+bool pipelined_force() {
+  static const int v = env_int("EPH_B200_PIPE_FORCE", 0);
+  return v != 0;
+}
+
 template <int LANES, int TAB, bool MULTI>
 int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool build) {
   const int threads = 256;
   KernelTimer kt(h, build ? "density_sweep_build" : "density_sweep");
   if (build) {
     auto k = density_sweep_kernel<LANES, TAB, true, MULTI>;
+    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
+  } else if (pipelined_density() && a.do_friction) {
+    auto k = density_sweep_pipe_kernel<LANES, TAB, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   } else {
@@ -832,15 +849,15 @@ template <int LANES, bool MULTI>
 int launch_force(eph_b200_handle *h, const SweepArgs &a) {
   const int threads = 256;
   KernelTimer kt(h, "force_sweep");
-  auto k = force_sweep_kernel<LANES, MULTI>;
-  k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
+  if (pipelined_force()) {
+    auto k = force_sweep_pipe_kernel<LANES, MULTI>;
+    k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
+  } else {
+    auto k = force_sweep_kernel<LANES, MULTI>;
+    k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
+  }
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
-}
-
-int env_int(const char *name, int dflt) {
-  const char *e = std::getenv(name);
-  return e ? std::atoi(e) : dflt;
 }
 
 int env_lanes(const char *name, int dflt) {
@@ -890,10 +907,10 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   a.inv_dr_sq = h->inv_dr_sq; a.r_cutoff_sq = h->rc2; a.rho_tab4 = reinterpret_cast<const double4 *>(h->rho_tab.p);
   const double r_in = std::sqrt(h->rc2) + h->inner_skin;
   a.r_inner_sq = r_in * r_in;
-  a.offsets = h->off_ptr; a.neigh = h->neigh_ptr; a.cneigh = h->cneigh.p; a.ccount = h->ccount.p;
+  a.offsets = h->off_ptr; a.neigh = h->neigh_ptr;
   a.ineigh = h->ineigh.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
   a.use_inner = 0;
-  a.pos4 = h->pos4.p; a.v4 = h->v4.p; a.z4 = h->z4.p; a.u4 = h->u4.p; a.W4 = h->W4.p; a.rho = h->rho.p;
+  a.pv = h->pv.p; a.puz = h->puz.p; a.W4 = h->W4.p; a.rho = h->rho.p;
   a.gpair = h->gpair.p; a.gpair_i = h->gpair_i.p;
   a.f = nullptr; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
   a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
@@ -946,7 +963,7 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
     KernelTimer kt(h, "pack_atoms");
     const double half = 0.5 * h->inner_skin;
     pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
-                                                                   h->cfg.groupbit, h->pos4.p, h->v4.p, track ? 1 : 0,
+                                                                   h->cfg.groupbit, h->pos4.p, h->pv.p, track ? 1 : 0,
                                                                    h->xref.p, h->xref0.p, half * half, h->lstate.p);
   }
   EPH_LAUNCH_CHECK(h);
@@ -997,7 +1014,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
   p.xi_inject = h->pf_xi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
   p.seed = h->cfg.seed; p.step = (unsigned long long)h->pf_step; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
-  p.rho = h->rho.p; p.W4 = h->W4.p; p.pos4 = h->pos4.p; p.z4 = h->z4.p; p.u4 = h->u4.p;
+  p.rho = h->rho.p; p.W4 = h->W4.p; p.pos4 = h->pos4.p; p.puz = h->puz.p;
   p.w = h->w.p; p.xi = h->xi.p; p.status = h->d_status.p;
   p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
   p.list_state = h->lstate.p;
@@ -1015,6 +1032,8 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   SweepArgs a = sweep_args(h);
   if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
     a.f = (add_fric || add_rand) ? df : nullptr;
+    // walk the list whose slots this step's density pass filled with pair weights
+    a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
     a.add_friction = add_fric ? 1 : 0;
     a.add_random = add_rand ? 1 : 0;
     if ((rc = launch_sweep(h, a, 1))) return rc;

@@ -27,6 +27,12 @@ __device__ __forceinline__ double4 ld256(const double4 *p) {
   return r;
 }
 
+// Streams that are read or written exactly once per pass (list indices, pair weights): evict-first hints keep
+// them from displacing the gathered per-atom records in L1/L2.
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+
 // Sub-warp groups: LANES consecutive lanes cooperate on one atom.
 template <int LANES>
 __device__ __forceinline__ constexpr unsigned lanes_bits() {

@@ -5,8 +5,8 @@
 //
 //   density_sweep   rho_i = sum_j rho^{t_j}(r^2)                      (fix_eph.cpp:450-461)
 //                   W_i   = sum_j g_ij (e.(v_i - v_j)) e              (the sum of :713-739 without its prefactor)
-//                   + this step's in-cutoff pair list and the pair weights g_ij = rho^{t_j}(r^2)/r^2
-//   force_sweep     f_EPH_i (fix_eph.cpp:758-785) and f_RNG_i (:802-833) from the cached pairs
+//                   + the pair weights g_ij = rho^{t_j}(r^2)/r^2 of every walked list slot (0 beyond the cut-off)
+//   force_sweep     f_EPH_i (fix_eph.cpp:758-785) and f_RNG_i (:802-833) from the cached pair weights
 //
 // Algebra: with the per-atom scalar s = alpha(rho)/rho,
 //   w_i = s_i W_i, u = s w, z = s xi, and every pair term of the two forces is
@@ -17,14 +17,23 @@
 // evaluated once per atom instead of once per pair.
 //
 // ncu (profiles/r1_*) shows these kernels bound by L1TEX wavefronts -- about one
-// wavefront per distinct 32-byte sector a warp instruction touches -- so the
-// data path is organised around sectors: every per-atom record is one aligned
-// sector fetched with ONE 256-bit load; LANES lanes share an atom so that the
-// atoms of a warp (spatial neighbours) hit common sectors; the density pass
-// walks a two-level Verlet list (inner list with a small skin, rebuilt on the
-// device from LAMMPS' list and guarded by a device-side displacement check);
-// the spline look-up and the reciprocal are done once per pair per step and
-// cached (8 bytes per pair, streamed) instead of being redone by every pass.
+// wavefront per distinct 32-byte sector a warp instruction touches -- and, below
+// that roof, by the latency of dependent loads.  The data path is organised
+// around both:
+//   * everything a pass needs about atom j sits in ONE record of consecutive
+//     sectors ({pos,bits | v} for the density pass, {pos,bits | u,z} for the
+//     force pass), fetched with back-to-back 256-bit loads: one exposed latency
+//     per list slot instead of one per array;
+//   * the list index (and, in the force pass, the pair weight) of the next
+//     slot is fetched one iteration ahead, so the gather never waits for the
+//     index stream;
+//   * LANES lanes share an atom so that the atoms of a warp (spatial
+//     neighbours) hit common sectors;
+//   * the density pass walks a two-level Verlet list (inner list with a small
+//     skin, rebuilt on the device from LAMMPS' list and guarded by a
+//     device-side displacement check);
+//   * the spline look-up and the reciprocal are done once per pair per step and
+//     cached (8 bytes per walked slot, streamed with evict-first hints).
 #pragma once
 
 #include "eph_device.cuh"
@@ -39,6 +48,12 @@
 
 namespace ephb {
 
+// Per-atom gather records (32-byte sectors, consecutive in memory).
+//   density pass: pv[2a] = {x, y, z, bits}, pv[2a+1] = {vx, vy, vz, 0}
+//   force pass:   puz[3a] = {x, y, z, bits}, puz[3a+1] = {ux, uy, uz, zx}, puz[3a+2] = {zy, zz, 0, 0}
+constexpr int kPvStride = 2;
+constexpr int kPuzStride = 3;
+
 struct SweepArgs {
   int nlocal;
   int n_elements;
@@ -52,15 +67,12 @@ struct SweepArgs {
   int *__restrict__ ineigh;               // inner list, same row starts
   int *__restrict__ icount;               // [nlocal] inner-list lengths
   const unsigned *__restrict__ inner_invalid;  // device flag: != 0 -> inner list must not be used
-  int use_inner;                          // an inner list exists
-  int *__restrict__ cneigh;               // this step's in-cutoff pairs, same row starts
-  int *__restrict__ ccount;               // [nlocal] in-cutoff pairs per atom
-  double *__restrict__ gpair;             // rho^{t_j}(r^2)/r^2 per in-cutoff pair, same indexing as cneigh
+  int use_inner;                          // density pass: an inner list exists
+  int walk_mode;                          // force pass: 0 LAMMPS' list, 1 inner list unless the device flag is set, 2 inner list
+  double *__restrict__ gpair;             // rho^{t_j}(r^2)/r^2 per walked slot (0 beyond r_c)
   double *__restrict__ gpair_i;           // rho^{t_i}(r^2)/r^2 (only when there is more than one element)
-  const double4 *__restrict__ pos4;       // [ntotal] x,y,z,bits
-  const double4 *__restrict__ v4;         // [ntotal] velocity
-  const double4 *__restrict__ z4;         // [ntotal] s * xi
-  const double4 *__restrict__ u4;         // [ntotal] s * w
+  const double4 *__restrict__ pv;         // [ntotal][2] density-pass records
+  const double4 *__restrict__ puz;        // [ntotal][3] force-pass records
   double4 *__restrict__ W4;               // [nlocal] sum_j g (e.(v_i - v_j)) e
   double *__restrict__ rho;               // [ntotal]
   double *__restrict__ f;                 // [nlocal][3] LAMMPS force array (read-modify-write) or nullptr
@@ -126,52 +138,62 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
   for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
-    const double4 pi = ld256(a.pos4 + i);
+    const double4 pi = ld256(a.pv + kPvStride * (size_t)i);
     const unsigned bi = double_to_bits(pi.w);
     double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
-    int count = 0, icnt = 0;
+    int icnt = 0;
     if (bi & kBitGroup) {  // atoms outside the fix group keep rho = 0 (fix_eph.cpp:442-445) and w = 0 (:704)
-      const double4 vi = a.do_friction ? ld256(a.v4 + i) : make_double4(0, 0, 0, 0);
+      const double4 vi = a.do_friction ? ld256(a.pv + kPvStride * (size_t)i + 1) : make_double4(0, 0, 0, 0);
       const int off_i = (bi & kElemMask) * a.n_rho;
       const long long beg = a.offsets[i];
       const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
+      const int *__restrict__ row = list + beg;
+      int jn = sub < nn ? ld_stream(row + sub) : 0;   // the index stream runs one slot ahead of the gathers
       for (int k0 = 0; k0 < nn; k0 += LANES) {
         const int k = k0 + sub;
+        const bool have = k < nn;
+        const int j = jn & kNeighMask;
+        if (k + LANES < nn) jn = ld_stream(row + k + LANES);
         bool in = false, in_inner = false;
-        int j = 0;
-        double r2 = 1.0, ex = 0.0, ey = 0.0, ez = 0.0;
-        unsigned bj = 0;
-        if (k < nn) {
-          j = list[beg + k] & kNeighMask;
-          const double4 pj = ld256(a.pos4 + j);
-          ex = pj.x - pi.x; ey = pj.y - pi.y; ez = pj.z - pi.z;
-          r2 = ex * ex + ey * ey + ez * ez;
-          bj = double_to_bits(pj.w);
+        double g = 0.0, gi = 0.0;
+        if (have) {
+          const double4 *rec = a.pv + kPvStride * (size_t)j;
+          const double4 pj = ld256(rec);
+          double4 vj = make_double4(0, 0, 0, 0);
+          // inner list: 5 of 6 slots are inside the cut-off, so v_j is fetched together with the position
+          // (one latency per slot); LAMMPS' list (3 of 8 inside): only after the distance test
+          if (inner && a.do_friction) vj = ld256(rec + 1);
+          const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+          const double r2 = ex * ex + ey * ey + ez * ez;
           in = r2 < a.r_cutoff_sq;  // strict '<' as in fix_eph.cpp:457, :724
           if (BUILD) in_inner = r2 < a.r_inner_sq;
+          if (in) {
+            const unsigned bj = double_to_bits(pj.w);
+            const double rho_j = tab.eval(MULTI ? (bj & kElemMask) * a.n_rho : off_i, a.inv_dr_sq, r2);
+            const double rinv = fast_rcp(r2);
+            g = rho_j * rinv;
+            rho += rho_j;
+            if (MULTI) gi = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
+            if (a.do_friction) {  // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
+              if (!inner) vj = ld256(rec + 1);
+              const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));
+              wx += d * ex; wy += d * ey; wz += d * ez;
+            }
+          }
         }
         if (BUILD) {
           const unsigned bal = (__ballot_sync(gmask, in_inner) >> gshift) & lanes_bits<LANES>();
-          if (in_inner) a.ineigh[beg + icnt + __popc(bal & below)] = j;
-          icnt += __popc(bal);
-        }
-        const unsigned bal = (__ballot_sync(gmask, in) >> gshift) & lanes_bits<LANES>();
-        if (in) {
-          const long long slot = beg + count + __popc(bal & below);
-          const double rho_j = tab.eval(MULTI ? (bj & kElemMask) * a.n_rho : off_i, a.inv_dr_sq, r2);
-          const double rinv = fast_rcp(r2);
-          const double g = rho_j * rinv;
-          rho += rho_j;
-          a.cneigh[slot] = j;
-          a.gpair[slot] = g;
-          if (MULTI) a.gpair_i[slot] = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
-          if (a.do_friction) {  // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
-            const double4 vj = ld256(a.v4 + j);
-            const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));
-            wx += d * ex; wy += d * ey; wz += d * ez;
+          if (in_inner) {
+            const long long slot = beg + icnt + __popc(bal & below);
+            a.ineigh[slot] = j;
+            st_stream(a.gpair + slot, g);
+            if (MULTI) st_stream(a.gpair_i + slot, gi);
           }
+          icnt += __popc(bal);
+        } else if (have) {
+          st_stream(a.gpair + beg + k, g);
+          if (MULTI) st_stream(a.gpair_i + beg + k, gi);
         }
-        count += __popc(bal);
       }
       rho = group_sum<LANES>(rho, gmask);
       if (a.do_friction) {
@@ -180,14 +202,84 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
     }
     if (sub == 0) {
       a.rho[i] = rho;
-      a.ccount[i] = count;
       a.W4[i] = make_double4(wx, wy, wz, 0.0);
       if (BUILD) a.icount[i] = icnt;
     }
   }
 }
 
-// f_EPH_i and f_RNG_i from the cached in-cutoff pairs; no table look-up, no reciprocal, no distance test.
+// Software-pipelined density pass (no inner-list rebuild): the records of slot k+LANES are requested before
+// slot k is evaluated, the index stream runs two slots ahead.  More registers, fewer resident warps, but two
+// gathers in flight per lane.
+#ifndef EPH_MINB_DENSITY_PIPE
+#define EPH_MINB_DENSITY_PIPE 3
+#endif
+template <int LANES, int TAB, bool MULTI>
+__global__ void __launch_bounds__(256, EPH_MINB_DENSITY_PIPE) density_sweep_pipe_kernel(SweepArgs a) {
+  extern __shared__ double2 s_tab[];
+  const RhoTable<TAB> tab = stage_tables<TAB>(a, s_tab);
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LANES - 1);
+  const unsigned gmask = group_mask<LANES>(lane);
+  const int groups_per_block = blockDim.x / LANES;
+  const int group_in_block = threadIdx.x / LANES;
+  const bool inner = a.use_inner && (*a.inner_invalid == 0u);
+  const int *__restrict__ list = inner ? a.ineigh : a.neigh;
+
+  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
+    const double4 pi = ld256(a.pv + kPvStride * (size_t)i);
+    const unsigned bi = double_to_bits(pi.w);
+    double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
+    if (bi & kBitGroup) {
+      const double4 vi = ld256(a.pv + kPvStride * (size_t)i + 1);
+      const int off_i = (bi & kElemMask) * a.n_rho;
+      const long long beg = a.offsets[i];
+      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
+      const int *__restrict__ row = list + beg;
+      int j1 = 0;
+      double4 pj = make_double4(0, 0, 0, 0), vj = pj;
+      if (sub < nn) {
+        const int j0 = ld_stream(row + sub) & kNeighMask;
+        if (sub + LANES < nn) j1 = ld_stream(row + sub + LANES) & kNeighMask;
+        pj = ld256(a.pv + kPvStride * (size_t)j0);
+        vj = ld256(a.pv + kPvStride * (size_t)j0 + 1);
+      }
+      for (int k = sub; k < nn; k += LANES) {
+        double4 pn = make_double4(0, 0, 0, 0), vn = pn;
+        int j2 = 0;
+        if (k + LANES < nn) {
+          pn = ld256(a.pv + kPvStride * (size_t)j1);
+          vn = ld256(a.pv + kPvStride * (size_t)j1 + 1);
+          if (k + 2 * LANES < nn) j2 = ld_stream(row + k + 2 * LANES) & kNeighMask;
+        }
+        const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+        const double r2 = ex * ex + ey * ey + ez * ez;
+        double g = 0.0, gi = 0.0;
+        if (r2 < a.r_cutoff_sq) {  // strict '<' as in fix_eph.cpp:457, :724
+          const unsigned bj = double_to_bits(pj.w);
+          const double rho_j = tab.eval(MULTI ? (bj & kElemMask) * a.n_rho : off_i, a.inv_dr_sq, r2);
+          const double rinv = fast_rcp(r2);
+          g = rho_j * rinv;
+          rho += rho_j;
+          if (MULTI) gi = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
+          const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));
+          wx += d * ex; wy += d * ey; wz += d * ez;
+        }
+        st_stream(a.gpair + beg + k, g);
+        if (MULTI) st_stream(a.gpair_i + beg + k, gi);
+        pj = pn; vj = vn; j1 = j2;
+      }
+      rho = group_sum<LANES>(rho, gmask);
+      wx = group_sum<LANES>(wx, gmask); wy = group_sum<LANES>(wy, gmask); wz = group_sum<LANES>(wz, gmask);
+    }
+    if (sub == 0) {
+      a.rho[i] = rho;
+      a.W4[i] = make_double4(wx, wy, wz, 0.0);
+    }
+  }
+}
+
+// f_EPH_i and f_RNG_i from the cached pair weights; no table look-up, no reciprocal, no distance test.
 template <int LANES, bool MULTI>
 __global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepArgs a) {
   const int lane = threadIdx.x & 31;
@@ -195,36 +287,57 @@ __global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepA
   const unsigned gmask = group_mask<LANES>(lane);
   const int groups_per_block = blockDim.x / LANES;
   const int group_in_block = threadIdx.x / LANES;
+  // the list whose slots the density pass of this step filled
+  const bool inner = a.walk_mode == 2 || (a.walk_mode == 1 && *a.inner_invalid == 0u);
+  const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
   for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
-    const double4 pi = ld256(a.pos4 + i);
+    const double4 *ri = a.puz + kPuzStride * (size_t)i;
+    const double4 pi = ld256(ri);
     const unsigned bi = double_to_bits(pi.w);
     double fx = 0, fy = 0, fz = 0, rx = 0, ry = 0, rz = 0;
     // group atoms with rho_i > 0 only (fix_eph.cpp:749-754, :793-798)
     const bool active = (bi & kBitGroup) && (bi & kBitValid);
     if (active) {
-      const double4 ui = a.do_friction ? ld256(a.u4 + i) : make_double4(0, 0, 0, 0);
-      const double4 zi = a.do_random ? ld256(a.z4 + i) : make_double4(0, 0, 0, 0);
+      const double4 qi = ld256(ri + 1), si = ld256(ri + 2);
+      const double uix = qi.x, uiy = qi.y, uiz = qi.z, zix = qi.w, ziy = si.x, ziz = si.y;
       const long long beg = a.offsets[i];
-      const int nn = a.ccount[i];
+      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
+      const int *__restrict__ row = list + beg;
+      const double *__restrict__ grow = a.gpair + beg;
+      const double *__restrict__ girow = MULTI ? a.gpair_i + beg : nullptr;
+      int jn = 0;
+      double gjn = 0.0, gin = 0.0;
+      if (sub < nn) {
+        jn = ld_stream(row + sub);
+        gjn = ld_stream(grow + sub);
+        if (MULTI) gin = ld_stream(girow + sub);
+      }
       for (int k = sub; k < nn; k += LANES) {
-        const int j = a.cneigh[beg + k];
-        const double gj = a.gpair[beg + k];
-        const double gi = MULTI ? a.gpair_i[beg + k] : gj;
-        const double4 pj = ld256(a.pos4 + j);
+        const int j = jn & kNeighMask;
+        const double gj = gjn;
+        const double gi = MULTI ? gin : gjn;
+        if (k + LANES < nn) {
+          jn = ld_stream(row + k + LANES);
+          gjn = ld_stream(grow + k + LANES);
+          if (MULTI) gin = ld_stream(girow + k + LANES);
+        }
+        if (gj == 0.0 && gi == 0.0) continue;  // beyond the cut-off (fix_eph.cpp:768, :811) or a vanishing pair weight
+        const double4 *rj = a.puz + kPuzStride * (size_t)j;
+        const double4 pj = ld256(rj), qj = ld256(rj + 1);
+        double4 sj = make_double4(0, 0, 0, 0);
+        if (a.do_random) sj = ld256(rj + 2);
         if (!(double_to_bits(pj.w) & kBitValid)) continue;  // rho_j > 0 required, fix_eph.cpp:768, :811
         const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
         if (a.do_friction) {
-          const double4 uj = ld256(a.u4 + j);
-          const double di = ex * ui.x + ey * ui.y + ez * ui.z;
-          const double dj = ex * uj.x + ey * uj.y + ez * uj.z;
+          const double di = ex * uix + ey * uiy + ez * uiz;
+          const double dj = ex * qj.x + ey * qj.y + ez * qj.z;
           const double g = gj * di - gi * dj;
           fx -= g * ex; fy -= g * ey; fz -= g * ez;  // friction is negative, fix_eph.cpp:781-784
         }
         if (a.do_random) {
-          const double4 zj = ld256(a.z4 + j);
-          const double di = ex * zi.x + ey * zi.y + ez * zi.z;
-          const double dj = ex * zj.x + ey * zj.y + ez * zj.z;
+          const double di = ex * zix + ey * ziy + ez * ziz;
+          const double dj = ex * qj.w + ey * sj.x + ez * sj.y;
           const double g = gj * di - gi * dj;
           rx += g * ex; ry += g * ey; rz += g * ez;  // fix_eph.cpp:823-826
         }
@@ -243,6 +356,109 @@ __global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepA
       if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
       if (a.do_random) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
       // f += f_EPH (+ f_RNG) for every local atom, grouped or not (fix_eph.cpp:892-906)
+      if (a.f != nullptr) {
+        double ax = 0, ay = 0, az = 0;
+        if (a.add_friction) { ax += fx; ay += fy; az += fz; }
+        if (a.add_random) { ax += rx; ay += ry; az += rz; }
+        a.f[o] += ax; a.f[o + 1] += ay; a.f[o + 2] += az;
+      }
+    }
+  }
+}
+
+// Software-pipelined force pass: the records of slot k+LANES are requested before slot k is evaluated; indices and
+// pair weights run two slots ahead.
+#ifndef EPH_MINB_FORCE_PIPE
+#define EPH_MINB_FORCE_PIPE 2
+#endif
+template <int LANES, bool MULTI>
+__global__ void __launch_bounds__(256, EPH_MINB_FORCE_PIPE) force_sweep_pipe_kernel(SweepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LANES - 1);
+  const unsigned gmask = group_mask<LANES>(lane);
+  const int groups_per_block = blockDim.x / LANES;
+  const int group_in_block = threadIdx.x / LANES;
+  const bool inner = a.walk_mode == 2 || (a.walk_mode == 1 && *a.inner_invalid == 0u);
+  const int *__restrict__ list = inner ? a.ineigh : a.neigh;
+
+  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
+    const double4 *ri = a.puz + kPuzStride * (size_t)i;
+    const double4 pi = ld256(ri);
+    const unsigned bi = double_to_bits(pi.w);
+    double fx = 0, fy = 0, fz = 0, rx = 0, ry = 0, rz = 0;
+    const bool active = (bi & kBitGroup) && (bi & kBitValid);
+    if (active) {
+      const double4 qi = ld256(ri + 1), si = ld256(ri + 2);
+      const double uix = qi.x, uiy = qi.y, uiz = qi.z, zix = qi.w, ziy = si.x, ziz = si.y;
+      const long long beg = a.offsets[i];
+      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
+      const int *__restrict__ row = list + beg;
+      const double *__restrict__ grow = a.gpair + beg;
+      const double *__restrict__ girow = MULTI ? a.gpair_i + beg : nullptr;
+      const double4 zero4 = make_double4(0, 0, 0, 0);
+      double gj = 0.0, gi = 0.0, g1 = 0.0, gi1 = 0.0;
+      int j1 = 0;
+      double4 pj = zero4, qj = zero4, sj = zero4;
+      if (sub < nn) {
+        const int j0 = ld_stream(row + sub) & kNeighMask;
+        gj = ld_stream(grow + sub);
+        gi = MULTI ? ld_stream(girow + sub) : gj;
+        if (sub + LANES < nn) {
+          j1 = ld_stream(row + sub + LANES) & kNeighMask;
+          g1 = ld_stream(grow + sub + LANES);
+          gi1 = MULTI ? ld_stream(girow + sub + LANES) : g1;
+        }
+        if (gj != 0.0 || gi != 0.0) {
+          const double4 *rj = a.puz + kPuzStride * (size_t)j0;
+          pj = ld256(rj); qj = ld256(rj + 1); sj = ld256(rj + 2);
+        }
+      }
+      for (int k = sub; k < nn; k += LANES) {
+        double4 pn = zero4, qn = zero4, sn = zero4;
+        int j2 = 0;
+        double g2 = 0.0, gi2 = 0.0;
+        if (k + LANES < nn) {
+          if (g1 != 0.0 || gi1 != 0.0) {
+            const double4 *rj = a.puz + kPuzStride * (size_t)j1;
+            pn = ld256(rj); qn = ld256(rj + 1); sn = ld256(rj + 2);
+          }
+          if (k + 2 * LANES < nn) {
+            j2 = ld_stream(row + k + 2 * LANES) & kNeighMask;
+            g2 = ld_stream(grow + k + 2 * LANES);
+            gi2 = MULTI ? ld_stream(girow + k + 2 * LANES) : g2;
+          }
+        }
+        // zero weights: beyond the cut-off; validity bit: rho_j > 0 required (fix_eph.cpp:768, :811)
+        if ((gj != 0.0 || gi != 0.0) && (double_to_bits(pj.w) & kBitValid)) {
+          const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+          if (a.do_friction) {
+            const double di = ex * uix + ey * uiy + ez * uiz;
+            const double dj = ex * qj.x + ey * qj.y + ez * qj.z;
+            const double g = gj * di - gi * dj;
+            fx -= g * ex; fy -= g * ey; fz -= g * ez;
+          }
+          if (a.do_random) {
+            const double di = ex * zix + ey * ziy + ez * ziz;
+            const double dj = ex * qj.w + ey * sj.x + ez * sj.y;
+            const double g = gj * di - gi * dj;
+            rx += g * ex; ry += g * ey; rz += g * ez;
+          }
+        }
+        pj = pn; qj = qn; sj = sn; gj = g1; gi = gi1; j1 = j2; g1 = g2; gi1 = gi2;
+      }
+      fx = group_sum<LANES>(fx, gmask); fy = group_sum<LANES>(fy, gmask); fz = group_sum<LANES>(fz, gmask);
+      rx = group_sum<LANES>(rx, gmask); ry = group_sum<LANES>(ry, gmask); rz = group_sum<LANES>(rz, gmask);
+    }
+    if (sub == 0) {
+      double var = 0.0;
+      if (active && a.do_random) {
+        const double Te = a.T_e[grid_index(a.grid, pi.x, pi.y, pi.z)];
+        var = a.eta_factor * sqrt(Te);
+      }
+      rx *= var; ry *= var; rz *= var;
+      const size_t o = 3 * (size_t)i;
+      if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
+      if (a.do_random) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
       if (a.f != nullptr) {
         double ax = 0, ay = 0, az = 0;
         if (a.add_friction) { ax += fx; ay += fy; az += fz; }

@@ -13,6 +13,9 @@ _LIBS = {
 
 
 def lib_path(name):
+    # EPH_B200_ENGINE_LIB: development aid for A/B timing of two builds of the engine on the same box
+    if name == "engine" and os.environ.get("EPH_B200_ENGINE_LIB"):
+        return os.environ["EPH_B200_ENGINE_LIB"]
     return _LIBS[name]
 
 
