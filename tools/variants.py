@@ -9,16 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cells = sys.argv[1] if len(sys.argv) > 1 else "64"
 variants = [
-    dict(EPH_B200_ENGINE_LIB=os.path.join(ROOT, "tools", "ab", "libeph_b200_v4.so")),
     dict(),
-    dict(EPH_B200_PIPE="1"),
-    dict(EPH_B200_PIPE_FORCE="1"),
-    dict(EPH_B200_PIPE="1", EPH_B200_PIPE_FORCE="1"),
-    dict(EPH_B200_LANES_DENSITY="4"),
-    dict(EPH_B200_LANES_DENSITY="4", EPH_B200_PIPE="1"),
-    dict(EPH_B200_LANES_FORCE="8"),
-    dict(EPH_B200_LANES_FORCE="8", EPH_B200_PIPE_FORCE="1"),
-    dict(EPH_B200_LANES_DENSITY="16", EPH_B200_PIPE="1"),
+    dict(EPH_B200_SPEC_V="0"),
+    dict(EPH_B200_TABLE="0"),
+    dict(EPH_B200_TABLE="0", EPH_B200_SPEC_V="0"),
 ]
 if len(sys.argv) > 2:
     variants = variants[: int(sys.argv[2])]

@@ -122,6 +122,8 @@ struct eph_b200_handle {
 
   // two-level Verlet list: inner list with a small skin, rebuilt on the device from LAMMPS' list
   DevBuf<int> ineigh, icount;
+  DevBuf<long long> tile_caps, tile_off;  // warp-tiled layout of the inner list (eph_sweeps.cuh)
+  int lanes = 4;                          // lanes per atom in both sweeps (fixes the tile shape)
   DevBuf<double4> xref, xref0;          // positions at the last inner build / at LAMMPS' build
   DevBuf<ListState> lstate;
   double skin = -1.0;                    // LAMMPS' neighbor->skin (unknown: inner list only valid from LAMMPS' build)
@@ -344,6 +346,10 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
     h->inner_skin = std::atof(e);
     h->inner_enabled = h->inner_skin > 0.0;
   }
+  if (const char *e = std::getenv("EPH_B200_LANES")) {   // tuning knob: lanes per atom in the sweeps
+    const int v = std::atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->lanes = v;
+  }
   h->sm_count = prop.multiProcessorCount;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (cfg->stream) h->stream = static_cast<cudaStream_t>(cfg->stream);
@@ -394,7 +400,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   for (auto e : h->event_pool) cudaEventDestroy(e);
   h->nb_cell.release(); h->nb_atom.release(); h->nb_cell_s.release(); h->nb_atom_s.release(); h->nb_start.release();
   h->nb_end.release(); h->nb_xs.release(); h->nb_counts.release(); h->nb_tmp.release(); h->nb_box.release();
-  h->ineigh.release(); h->icount.release(); h->xref.release(); h->xref0.release(); h->lstate.release();
+  h->ineigh.release(); h->icount.release(); h->tile_caps.release(); h->tile_off.release(); h->xref.release(); h->xref0.release(); h->lstate.release();
   if (h->h_flag) cudaFreeHost(h->h_flag);
   if (h->flag_event) cudaEventDestroy(h->flag_event);
   if (h->f_event) cudaEventDestroy(h->f_event);
@@ -687,9 +693,27 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
     h->neigh_ptr = h->neigh.p;
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
-  EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(total, 1)));
-  if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(total, 1)));
-  if (h->inner_enabled) EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(total, 1)));
+  long long slots = total;   // pair-weight slots: CSR rows of LAMMPS' list or, usually larger, the tiles of the inner list
+  if (h->inner_enabled && nlocal > 0) {
+    const int tile_atoms = 32 / h->lanes;
+    const int ntiles = (nlocal + tile_atoms - 1) / tile_atoms;
+    EPH_CUDA(h, h->tile_caps.reserve((size_t)ntiles + 1));
+    EPH_CUDA(h, h->tile_off.reserve((size_t)ntiles + 1));
+    tile_caps_kernel<<<blocks_for(ntiles + 1, 256), 256, 0, h->stream>>>(nlocal, h->off_ptr, tile_atoms, h->lanes, ntiles, h->tile_caps.p);
+    EPH_LAUNCH_CHECK(h);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->tile_caps.p, h->tile_off.p, ntiles + 1, h->stream);
+    EPH_CUDA(h, h->nb_tmp.reserve(scan_bytes));
+    EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->tile_caps.p, h->tile_off.p, ntiles + 1, h->stream));
+    ++h->launches;
+    long long tiled = 0;
+    EPH_CUDA(h, cudaMemcpyAsync(&tiled, h->tile_off.p + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(tiled, 1)));
+    slots = std::max(slots, tiled);
+  }
+  EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(slots, 1)));
+  if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(slots, 1)));
   EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
   h->fresh_neighbors = true;
   h->have_inner = false;
@@ -814,26 +838,12 @@ int env_int(const char *name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 
-bool pipelined_density() {
-  static const int v = env_int("EPH_B200_PIPE", 0);
-  return v != 0;
-}
-
-bool pipelined_force() {
-  static const int v = env_int("EPH_B200_PIPE_FORCE", 0);
-  return v != 0;
-}
-
 template <int LANES, int TAB, bool MULTI>
 int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool build) {
   const int threads = 256;
   KernelTimer kt(h, build ? "density_sweep_build" : "density_sweep");
   if (build) {
     auto k = density_sweep_kernel<LANES, TAB, true, MULTI>;
-    if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
-  } else if (pipelined_density() && a.do_friction) {
-    auto k = density_sweep_pipe_kernel<LANES, TAB, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<resident_grid(h, k, threads, smem), threads, smem, h->stream>>>(a);
   } else {
@@ -847,58 +857,50 @@ int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool bui
 
 template <int LANES, bool MULTI>
 int launch_force(eph_b200_handle *h, const SweepArgs &a) {
-  const int threads = 256;
+  const int threads = EPH_THREADS_FORCE;
   KernelTimer kt(h, "force_sweep");
-  if (pipelined_force()) {
-    auto k = force_sweep_pipe_kernel<LANES, MULTI>;
-    k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
-  } else {
-    auto k = force_sweep_kernel<LANES, MULTI>;
-    k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
-  }
+  auto k = force_sweep_kernel<LANES, MULTI>;
+  k<<<resident_grid(h, k, threads, 0), threads, 0, h->stream>>>(a);
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
-}
-
-int env_lanes(const char *name, int dflt) {
-  int v = env_int(name, dflt);
-  return (v == 4 || v == 8 || v == 16 || v == 32) ? v : dflt;
 }
 
 template <int TAB, bool MULTI>
 int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, int lanes, bool build) {
   switch (lanes) {
-    case 4: return launch_density<4, TAB, MULTI>(h, a, smem, build);
+    case 1: return launch_density<1, TAB, MULTI>(h, a, smem, build);
+    case 2: return launch_density<2, TAB, MULTI>(h, a, smem, build);
     case 8: return launch_density<8, TAB, MULTI>(h, a, smem, build);
     case 16: return launch_density<16, TAB, MULTI>(h, a, smem, build);
-    default: return launch_density<32, TAB, MULTI>(h, a, smem, build);
+    default: return launch_density<4, TAB, MULTI>(h, a, smem, build);
   }
 }
 
-// which: 0 density pass (optionally rebuilding the inner list), 1 force pass
+// which: 0 density pass (optionally rebuilding the inner list), 1 force pass.  Both passes use the same number of
+// lanes per atom: it fixes the tile shape of the inner list and of the pair weights.
 int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false) {
   const bool multi = a.n_elements > 1;
-  static const int lanes_density = env_lanes("EPH_B200_LANES_DENSITY", 8);
-  static const int lanes_force = env_lanes("EPH_B200_LANES_FORCE", 4);
   if (which == 1) {
-    switch (lanes_force) {
+    switch (h->lanes) {
+      case 1: return multi ? launch_force<1, true>(h, a) : launch_force<1, false>(h, a);
+      case 2: return multi ? launch_force<2, true>(h, a) : launch_force<2, false>(h, a);
       case 8: return multi ? launch_force<8, true>(h, a) : launch_force<8, false>(h, a);
       case 16: return multi ? launch_force<16, true>(h, a) : launch_force<16, false>(h, a);
-      case 32: return multi ? launch_force<32, true>(h, a) : launch_force<32, false>(h, a);
       default: return multi ? launch_force<4, true>(h, a) : launch_force<4, false>(h, a);
     }
   }
-  // rho(r^2) tables of all elements: staged in shared memory when they fit (EPH_B200_TABLE=1, default), or read
-  // with 256-bit loads through L1 (EPH_B200_TABLE=0)
+  // rho(r^2) tables of all elements: read with 256-bit loads through L1 (default; measured 3 % faster than the
+  // shared-memory copy, whose bank conflicts cost more data-pipe wavefronts than the cached sectors, and it keeps
+  // 4 CTAs per SM for multi-element tables), or staged in shared memory when they fit (EPH_B200_TABLE=1)
   const size_t table_bytes = (size_t)a.n_elements * a.n_rho * 2 * sizeof(double2);
-  static const int table_mode = env_int("EPH_B200_TABLE", 1);
+  static const int table_mode = env_int("EPH_B200_TABLE", 0);
   const bool smem = table_mode == 1 && table_bytes <= (size_t)h->max_smem_optin - 1024;
   if (smem) {
-    if (multi) return launch_density_lanes<1, true>(h, a, table_bytes, lanes_density, build);
-    return launch_density_lanes<1, false>(h, a, table_bytes, lanes_density, build);
+    if (multi) return launch_density_lanes<1, true>(h, a, table_bytes, h->lanes, build);
+    return launch_density_lanes<1, false>(h, a, table_bytes, h->lanes, build);
   }
-  if (multi) return launch_density_lanes<0, true>(h, a, 0, lanes_density, build);
-  return launch_density_lanes<0, false>(h, a, 0, lanes_density, build);
+  if (multi) return launch_density_lanes<0, true>(h, a, 0, h->lanes, build);
+  return launch_density_lanes<0, false>(h, a, 0, h->lanes, build);
 }
 
 SweepArgs sweep_args(eph_b200_handle *h) {
@@ -908,8 +910,10 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   const double r_in = std::sqrt(h->rc2) + h->inner_skin;
   a.r_inner_sq = r_in * r_in;
   a.offsets = h->off_ptr; a.neigh = h->neigh_ptr;
-  a.ineigh = h->ineigh.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
+  a.ineigh = h->ineigh.p; a.tile_off = h->tile_off.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
   a.use_inner = 0;
+  static const int spec_v = env_int("EPH_B200_SPEC_V", 1);
+  a.spec_v = spec_v;
   a.pv = h->pv.p; a.puz = h->puz.p; a.W4 = h->W4.p; a.rho = h->rho.p;
   a.gpair = h->gpair.p; a.gpair_i = h->gpair_i.p;
   a.f = nullptr; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;

@@ -27,6 +27,13 @@ __device__ __forceinline__ double4 ld256(const double4 *p) {
   return r;
 }
 
+// First half of a 32-byte record (LDG.128 through the read-only path).
+__device__ __forceinline__ double2 ld128(const double4 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
 // Streams that are read or written exactly once per pass (list indices, pair weights): evict-first hints keep
 // them from displacing the gathered per-atom records in L1/L2.
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }

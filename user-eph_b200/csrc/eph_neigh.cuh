@@ -7,6 +7,21 @@
 
 namespace ephb {
 
+// Capacity of every warp tile of the inner list (eph_sweeps.cuh): 32 entries per iteration, as many iterations as
+// the longest LAMMPS row of the tile needs (the inner list is a subset of LAMMPS' list).  caps[ntiles] = 0 closes the scan.
+__global__ void tile_caps_kernel(int nlocal, const long long *__restrict__ offsets, int tile_atoms, int lanes,
+                                 int ntiles, long long *__restrict__ caps) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > ntiles) return;
+  long long longest = 0;
+  if (w < ntiles)
+    for (int a = 0; a < tile_atoms; ++a) {
+      const int i = w * tile_atoms + a;
+      if (i < nlocal) longest = max(longest, offsets[i + 1] - offsets[i]);
+    }
+  caps[w] = 32 * ((longest + lanes - 1) / lanes);
+}
+
 struct CellGrid {
   double lo[3];
   double inv[3];   // cells per length

@@ -32,6 +32,10 @@
 //   * the density pass walks a two-level Verlet list (inner list with a small
 //     skin, rebuilt on the device from LAMMPS' list and guarded by a
 //     device-side displacement check);
+//   * the inner list and the pair weights are stored warp-tiled: slot t of the
+//     32/LANES atoms a warp works on is one run of 32 consecutive entries, so
+//     the index and weight streams cost one 128-byte line per warp and
+//     iteration instead of one sector per atom;
 //   * the spline look-up and the reciprocal are done once per pair per step and
 //     cached (8 bytes per walked slot, streamed with evict-first hints).
 #pragma once
@@ -42,8 +46,13 @@
 #ifndef EPH_MINB_DENSITY
 #define EPH_MINB_DENSITY 4
 #endif
+// force pass: 72 registers hold the working set without spills (spill traffic goes through the same L1 data pipe
+// the gathers saturate) -> CTAs of 128 threads, 7 per SM (28 resident warps)
+#ifndef EPH_THREADS_FORCE
+#define EPH_THREADS_FORCE 128
+#endif
 #ifndef EPH_MINB_FORCE
-#define EPH_MINB_FORCE 4
+#define EPH_MINB_FORCE 7
 #endif
 
 namespace ephb {
@@ -64,12 +73,14 @@ struct SweepArgs {
   const double4 *__restrict__ rho_tab4;   // [n_elements][n_rho] {a,b,c,d} (global copy)
   const long long *__restrict__ offsets;  // CSR row starts of LAMMPS' list
   const int *__restrict__ neigh;          // LAMMPS' list (raw entries)
-  int *__restrict__ ineigh;               // inner list, same row starts
+  int *__restrict__ ineigh;               // inner list, warp-tiled (see tile_slot)
+  const long long *__restrict__ tile_off; // [ceil(nlocal / (32/LANES)) + 1] first entry of every tile (multiples of 32)
   int *__restrict__ icount;               // [nlocal] inner-list lengths
   const unsigned *__restrict__ inner_invalid;  // device flag: != 0 -> inner list must not be used
   int use_inner;                          // density pass: an inner list exists
+  int spec_v;                             // density pass: fetch v_j together with the position when walking the inner list
   int walk_mode;                          // force pass: 0 LAMMPS' list, 1 inner list unless the device flag is set, 2 inner list
-  double *__restrict__ gpair;             // rho^{t_j}(r^2)/r^2 per walked slot (0 beyond r_c)
+  double *__restrict__ gpair;             // rho^{t_j}(r^2)/r^2 per walked slot (0 beyond r_c), indexed like the walked list
   double *__restrict__ gpair_i;           // rho^{t_i}(r^2)/r^2 (only when there is more than one element)
   const double4 *__restrict__ pv;         // [ntotal][2] density-pass records
   const double4 *__restrict__ puz;        // [ntotal][3] force-pass records
@@ -121,6 +132,22 @@ __device__ __forceinline__ RhoTable<TAB> stage_tables(const SweepArgs &a, double
   return t;
 }
 
+// Where the slots of one atom live.  LAMMPS' list: CSR row, the group's LANES lanes read LANES consecutive entries
+// per iteration.  Inner list: the tile of the 32/LANES atoms a warp works on; iteration t of the whole warp is the
+// run [tile_off + 32 t, tile_off + 32 t + 32), lane l reads entry l of it.
+struct RowWalk {
+  long long first;  // entry of (iteration 0, this lane)
+  int stride;       // entries between iterations
+};
+template <int LANES>
+__device__ __forceinline__ RowWalk walk_csr(const SweepArgs &a, int i, int sub) {
+  return RowWalk{a.offsets[i] + sub, LANES};
+}
+template <int LANES>
+__device__ __forceinline__ RowWalk walk_tile(const SweepArgs &a, int i, int lane) {
+  return RowWalk{a.tile_off[i / (32 / LANES)] + lane, 32};
+}
+
 // BUILD = this launch also (re)builds the inner list from LAMMPS' list.
 // MULTI = more than one element: two table look-ups per pair.
 template <int LANES, int TAB, bool BUILD, bool MULTI>
@@ -135,6 +162,7 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   const int groups_per_block = blockDim.x / LANES;
   const int group_in_block = threadIdx.x / LANES;
   const bool inner = !BUILD && a.use_inner && (*a.inner_invalid == 0u);
+  const bool spec = inner && a.spec_v;
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
   for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
@@ -145,15 +173,20 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
     if (bi & kBitGroup) {  // atoms outside the fix group keep rho = 0 (fix_eph.cpp:442-445) and w = 0 (:704)
       const double4 vi = a.do_friction ? ld256(a.pv + kPvStride * (size_t)i + 1) : make_double4(0, 0, 0, 0);
       const int off_i = (bi & kElemMask) * a.n_rho;
-      const long long beg = a.offsets[i];
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
-      const int *__restrict__ row = list + beg;
-      int jn = sub < nn ? ld_stream(row + sub) : 0;   // the index stream runs one slot ahead of the gathers
-      for (int k0 = 0; k0 < nn; k0 += LANES) {
+      const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
+      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
+      const long long tile0 = BUILD ? a.tile_off[i / (32 / LANES)] + gshift : 0;   // this atom's lanes of tile iteration 0
+      const int *__restrict__ lp = list + rw.first;
+      double *__restrict__ gp = a.gpair + rw.first;
+      double *__restrict__ gip = MULTI ? a.gpair_i + rw.first : nullptr;
+      int slot = 0;
+      int jn = sub < nn ? ld_stream(lp) : 0;   // the index stream runs one slot ahead of the gathers
+#pragma unroll 2
+      for (int k0 = 0; k0 < nn; k0 += LANES, slot += rw.stride) {
         const int k = k0 + sub;
         const bool have = k < nn;
         const int j = jn & kNeighMask;
-        if (k + LANES < nn) jn = ld_stream(row + k + LANES);
+        if (k + LANES < nn) jn = ld_stream(lp + slot + rw.stride);
         bool in = false, in_inner = false;
         double g = 0.0, gi = 0.0;
         if (have) {
@@ -162,7 +195,7 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
           double4 vj = make_double4(0, 0, 0, 0);
           // inner list: 5 of 6 slots are inside the cut-off, so v_j is fetched together with the position
           // (one latency per slot); LAMMPS' list (3 of 8 inside): only after the distance test
-          if (inner && a.do_friction) vj = ld256(rec + 1);
+          if (spec && a.do_friction) vj = ld256(rec + 1);
           const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
           const double r2 = ex * ex + ey * ey + ez * ez;
           in = r2 < a.r_cutoff_sq;  // strict '<' as in fix_eph.cpp:457, :724
@@ -175,7 +208,7 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
             rho += rho_j;
             if (MULTI) gi = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
             if (a.do_friction) {  // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
-              if (!inner) vj = ld256(rec + 1);
+              if (!spec) vj = ld256(rec + 1);
               const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));
               wx += d * ex; wy += d * ey; wz += d * ez;
             }
@@ -184,15 +217,16 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
         if (BUILD) {
           const unsigned bal = (__ballot_sync(gmask, in_inner) >> gshift) & lanes_bits<LANES>();
           if (in_inner) {
-            const long long slot = beg + icnt + __popc(bal & below);
-            a.ineigh[slot] = j;
-            st_stream(a.gpair + slot, g);
-            if (MULTI) st_stream(a.gpair_i + slot, gi);
+            const int c = icnt + __popc(bal & below);   // position in this atom's inner list
+            const long long dst = tile0 + (long long)(c / LANES) * 32 + (c & (LANES - 1));
+            a.ineigh[dst] = j;
+            st_stream(a.gpair + dst, g);
+            if (MULTI) st_stream(a.gpair_i + dst, gi);
           }
           icnt += __popc(bal);
         } else if (have) {
-          st_stream(a.gpair + beg + k, g);
-          if (MULTI) st_stream(a.gpair_i + beg + k, gi);
+          st_stream(gp + slot, g);
+          if (MULTI) st_stream(gip + slot, gi);
         }
       }
       rho = group_sum<LANES>(rho, gmask);
@@ -208,80 +242,9 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   }
 }
 
-// Software-pipelined density pass (no inner-list rebuild): the records of slot k+LANES are requested before
-// slot k is evaluated, the index stream runs two slots ahead.  More registers, fewer resident warps, but two
-// gathers in flight per lane.
-#ifndef EPH_MINB_DENSITY_PIPE
-#define EPH_MINB_DENSITY_PIPE 3
-#endif
-template <int LANES, int TAB, bool MULTI>
-__global__ void __launch_bounds__(256, EPH_MINB_DENSITY_PIPE) density_sweep_pipe_kernel(SweepArgs a) {
-  extern __shared__ double2 s_tab[];
-  const RhoTable<TAB> tab = stage_tables<TAB>(a, s_tab);
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & (LANES - 1);
-  const unsigned gmask = group_mask<LANES>(lane);
-  const int groups_per_block = blockDim.x / LANES;
-  const int group_in_block = threadIdx.x / LANES;
-  const bool inner = a.use_inner && (*a.inner_invalid == 0u);
-  const int *__restrict__ list = inner ? a.ineigh : a.neigh;
-
-  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
-    const double4 pi = ld256(a.pv + kPvStride * (size_t)i);
-    const unsigned bi = double_to_bits(pi.w);
-    double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
-    if (bi & kBitGroup) {
-      const double4 vi = ld256(a.pv + kPvStride * (size_t)i + 1);
-      const int off_i = (bi & kElemMask) * a.n_rho;
-      const long long beg = a.offsets[i];
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
-      const int *__restrict__ row = list + beg;
-      int j1 = 0;
-      double4 pj = make_double4(0, 0, 0, 0), vj = pj;
-      if (sub < nn) {
-        const int j0 = ld_stream(row + sub) & kNeighMask;
-        if (sub + LANES < nn) j1 = ld_stream(row + sub + LANES) & kNeighMask;
-        pj = ld256(a.pv + kPvStride * (size_t)j0);
-        vj = ld256(a.pv + kPvStride * (size_t)j0 + 1);
-      }
-      for (int k = sub; k < nn; k += LANES) {
-        double4 pn = make_double4(0, 0, 0, 0), vn = pn;
-        int j2 = 0;
-        if (k + LANES < nn) {
-          pn = ld256(a.pv + kPvStride * (size_t)j1);
-          vn = ld256(a.pv + kPvStride * (size_t)j1 + 1);
-          if (k + 2 * LANES < nn) j2 = ld_stream(row + k + 2 * LANES) & kNeighMask;
-        }
-        const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
-        const double r2 = ex * ex + ey * ey + ez * ez;
-        double g = 0.0, gi = 0.0;
-        if (r2 < a.r_cutoff_sq) {  // strict '<' as in fix_eph.cpp:457, :724
-          const unsigned bj = double_to_bits(pj.w);
-          const double rho_j = tab.eval(MULTI ? (bj & kElemMask) * a.n_rho : off_i, a.inv_dr_sq, r2);
-          const double rinv = fast_rcp(r2);
-          g = rho_j * rinv;
-          rho += rho_j;
-          if (MULTI) gi = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
-          const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));
-          wx += d * ex; wy += d * ey; wz += d * ez;
-        }
-        st_stream(a.gpair + beg + k, g);
-        if (MULTI) st_stream(a.gpair_i + beg + k, gi);
-        pj = pn; vj = vn; j1 = j2;
-      }
-      rho = group_sum<LANES>(rho, gmask);
-      wx = group_sum<LANES>(wx, gmask); wy = group_sum<LANES>(wy, gmask); wz = group_sum<LANES>(wz, gmask);
-    }
-    if (sub == 0) {
-      a.rho[i] = rho;
-      a.W4[i] = make_double4(wx, wy, wz, 0.0);
-    }
-  }
-}
-
 // f_EPH_i and f_RNG_i from the cached pair weights; no table look-up, no reciprocal, no distance test.
 template <int LANES, bool MULTI>
-__global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_sweep_kernel(SweepArgs a) {
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES - 1);
   const unsigned gmask = group_mask<LANES>(lane);
@@ -299,34 +262,37 @@ __global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepA
     // group atoms with rho_i > 0 only (fix_eph.cpp:749-754, :793-798)
     const bool active = (bi & kBitGroup) && (bi & kBitValid);
     if (active) {
-      const double4 qi = ld256(ri + 1), si = ld256(ri + 2);
+      const double4 qi = ld256(ri + 1);
+      const double2 si = ld128(ri + 2);
       const double uix = qi.x, uiy = qi.y, uiz = qi.z, zix = qi.w, ziy = si.x, ziz = si.y;
-      const long long beg = a.offsets[i];
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
-      const int *__restrict__ row = list + beg;
-      const double *__restrict__ grow = a.gpair + beg;
-      const double *__restrict__ girow = MULTI ? a.gpair_i + beg : nullptr;
+      const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
+      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
+      const int *__restrict__ lp = list + rw.first;
+      const double *__restrict__ gp = a.gpair + rw.first;
+      const double *__restrict__ gip = MULTI ? a.gpair_i + rw.first : nullptr;
+      int slot = 0;
       int jn = 0;
       double gjn = 0.0, gin = 0.0;
       if (sub < nn) {
-        jn = ld_stream(row + sub);
-        gjn = ld_stream(grow + sub);
-        if (MULTI) gin = ld_stream(girow + sub);
+        jn = ld_stream(lp);
+        gjn = ld_stream(gp);
+        if (MULTI) gin = ld_stream(gip);
       }
-      for (int k = sub; k < nn; k += LANES) {
+#pragma unroll 1
+      for (int k = sub; k < nn; k += LANES, slot += rw.stride) {
         const int j = jn & kNeighMask;
         const double gj = gjn;
         const double gi = MULTI ? gin : gjn;
         if (k + LANES < nn) {
-          jn = ld_stream(row + k + LANES);
-          gjn = ld_stream(grow + k + LANES);
-          if (MULTI) gin = ld_stream(girow + k + LANES);
+          jn = ld_stream(lp + slot + rw.stride);
+          gjn = ld_stream(gp + slot + rw.stride);
+          if (MULTI) gin = ld_stream(gip + slot + rw.stride);
         }
         if (gj == 0.0 && gi == 0.0) continue;  // beyond the cut-off (fix_eph.cpp:768, :811) or a vanishing pair weight
         const double4 *rj = a.puz + kPuzStride * (size_t)j;
         const double4 pj = ld256(rj), qj = ld256(rj + 1);
-        double4 sj = make_double4(0, 0, 0, 0);
-        if (a.do_random) sj = ld256(rj + 2);
+        double2 sj = make_double2(0, 0);
+        if (a.do_random) sj = ld128(rj + 2);
         if (!(double_to_bits(pj.w) & kBitValid)) continue;  // rho_j > 0 required, fix_eph.cpp:768, :811
         const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
         if (a.do_friction) {
@@ -356,109 +322,6 @@ __global__ void __launch_bounds__(256, EPH_MINB_FORCE) force_sweep_kernel(SweepA
       if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
       if (a.do_random) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
       // f += f_EPH (+ f_RNG) for every local atom, grouped or not (fix_eph.cpp:892-906)
-      if (a.f != nullptr) {
-        double ax = 0, ay = 0, az = 0;
-        if (a.add_friction) { ax += fx; ay += fy; az += fz; }
-        if (a.add_random) { ax += rx; ay += ry; az += rz; }
-        a.f[o] += ax; a.f[o + 1] += ay; a.f[o + 2] += az;
-      }
-    }
-  }
-}
-
-// Software-pipelined force pass: the records of slot k+LANES are requested before slot k is evaluated; indices and
-// pair weights run two slots ahead.
-#ifndef EPH_MINB_FORCE_PIPE
-#define EPH_MINB_FORCE_PIPE 2
-#endif
-template <int LANES, bool MULTI>
-__global__ void __launch_bounds__(256, EPH_MINB_FORCE_PIPE) force_sweep_pipe_kernel(SweepArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & (LANES - 1);
-  const unsigned gmask = group_mask<LANES>(lane);
-  const int groups_per_block = blockDim.x / LANES;
-  const int group_in_block = threadIdx.x / LANES;
-  const bool inner = a.walk_mode == 2 || (a.walk_mode == 1 && *a.inner_invalid == 0u);
-  const int *__restrict__ list = inner ? a.ineigh : a.neigh;
-
-  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
-    const double4 *ri = a.puz + kPuzStride * (size_t)i;
-    const double4 pi = ld256(ri);
-    const unsigned bi = double_to_bits(pi.w);
-    double fx = 0, fy = 0, fz = 0, rx = 0, ry = 0, rz = 0;
-    const bool active = (bi & kBitGroup) && (bi & kBitValid);
-    if (active) {
-      const double4 qi = ld256(ri + 1), si = ld256(ri + 2);
-      const double uix = qi.x, uiy = qi.y, uiz = qi.z, zix = qi.w, ziy = si.x, ziz = si.y;
-      const long long beg = a.offsets[i];
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - beg);
-      const int *__restrict__ row = list + beg;
-      const double *__restrict__ grow = a.gpair + beg;
-      const double *__restrict__ girow = MULTI ? a.gpair_i + beg : nullptr;
-      const double4 zero4 = make_double4(0, 0, 0, 0);
-      double gj = 0.0, gi = 0.0, g1 = 0.0, gi1 = 0.0;
-      int j1 = 0;
-      double4 pj = zero4, qj = zero4, sj = zero4;
-      if (sub < nn) {
-        const int j0 = ld_stream(row + sub) & kNeighMask;
-        gj = ld_stream(grow + sub);
-        gi = MULTI ? ld_stream(girow + sub) : gj;
-        if (sub + LANES < nn) {
-          j1 = ld_stream(row + sub + LANES) & kNeighMask;
-          g1 = ld_stream(grow + sub + LANES);
-          gi1 = MULTI ? ld_stream(girow + sub + LANES) : g1;
-        }
-        if (gj != 0.0 || gi != 0.0) {
-          const double4 *rj = a.puz + kPuzStride * (size_t)j0;
-          pj = ld256(rj); qj = ld256(rj + 1); sj = ld256(rj + 2);
-        }
-      }
-      for (int k = sub; k < nn; k += LANES) {
-        double4 pn = zero4, qn = zero4, sn = zero4;
-        int j2 = 0;
-        double g2 = 0.0, gi2 = 0.0;
-        if (k + LANES < nn) {
-          if (g1 != 0.0 || gi1 != 0.0) {
-            const double4 *rj = a.puz + kPuzStride * (size_t)j1;
-            pn = ld256(rj); qn = ld256(rj + 1); sn = ld256(rj + 2);
-          }
-          if (k + 2 * LANES < nn) {
-            j2 = ld_stream(row + k + 2 * LANES) & kNeighMask;
-            g2 = ld_stream(grow + k + 2 * LANES);
-            gi2 = MULTI ? ld_stream(girow + k + 2 * LANES) : g2;
-          }
-        }
-        // zero weights: beyond the cut-off; validity bit: rho_j > 0 required (fix_eph.cpp:768, :811)
-        if ((gj != 0.0 || gi != 0.0) && (double_to_bits(pj.w) & kBitValid)) {
-          const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
-          if (a.do_friction) {
-            const double di = ex * uix + ey * uiy + ez * uiz;
-            const double dj = ex * qj.x + ey * qj.y + ez * qj.z;
-            const double g = gj * di - gi * dj;
-            fx -= g * ex; fy -= g * ey; fz -= g * ez;
-          }
-          if (a.do_random) {
-            const double di = ex * zix + ey * ziy + ez * ziz;
-            const double dj = ex * qj.w + ey * sj.x + ez * sj.y;
-            const double g = gj * di - gi * dj;
-            rx += g * ex; ry += g * ey; rz += g * ez;
-          }
-        }
-        pj = pn; qj = qn; sj = sn; gj = g1; gi = gi1; j1 = j2; g1 = g2; gi1 = gi2;
-      }
-      fx = group_sum<LANES>(fx, gmask); fy = group_sum<LANES>(fy, gmask); fz = group_sum<LANES>(fz, gmask);
-      rx = group_sum<LANES>(rx, gmask); ry = group_sum<LANES>(ry, gmask); rz = group_sum<LANES>(rz, gmask);
-    }
-    if (sub == 0) {
-      double var = 0.0;
-      if (active && a.do_random) {
-        const double Te = a.T_e[grid_index(a.grid, pi.x, pi.y, pi.z)];
-        var = a.eta_factor * sqrt(Te);
-      }
-      rx *= var; ry *= var; rz *= var;
-      const size_t o = 3 * (size_t)i;
-      if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
-      if (a.do_random) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
       if (a.f != nullptr) {
         double ax = 0, ay = 0, az = 0;
         if (a.add_friction) { ax += fx; ay += fy; az += fz; }
