@@ -174,6 +174,14 @@ int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev);
  * T_e or dT_e again (the force pass, the next deposit, grid read-backs).  A caller that issues its all-reduce of the
  * source term on the same stream thus overlaps all-reduce + solve with the next step's density pass. */
 int eph_b200_set_grid_stream(eph_b200_handle *h, void *stream);
+/* Optional communication stream and boundary-first density pass (multi-rank overlap of the one ghost exchange a step
+ * needs; the reference serialises its forward comms, fix_eph.cpp:743-744, :863-871, with the sweeps).
+ * set_boundary_atoms names the owned atoms other ranks hold as ghosts (local indices, after set_atoms): the density
+ * pass then sweeps the tiles holding them first.  With a communication stream set, pack_ghost_payload and
+ * unpack_ghost_payload run on it -- pack waits only for those boundary tiles, post_force_end waits for unpack -- so a
+ * caller that issues its all-to-all on the same stream hides the exchange behind the sweep of the interior tiles. */
+int eph_b200_set_comm_stream(eph_b200_handle *h, void *stream);
+int eph_b200_set_boundary_atoms(eph_b200_handle *h, int n, const int *index, int memspace);
 
 /* Replaces FixEPH::end_of_step (fix_eph.cpp:350-429): energy bookkeeping,
  * EPH_FDM::insert_energy (eph_fdm.h:172-179), EPH_FDM::solve (:267-400) and the

@@ -336,8 +336,8 @@ def test_inner_list_invalidation_and_rebuild(synth_beta_1, skin):
     assert st["inner_builds"] >= (2 if skin else 1)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
+@pytest.mark.parametrize("world,overlap", [(2, False), (4, False), (2, True), (4, True)])
+def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world, overlap):
     """The multi-rank path on one GPU: `world` engines, one per spatial brick, driven through the two halves of
     post_force / end_of_step with the ghost payload and the grid source term moved between them exactly as
     torch.distributed would (eph_b200.parallel); the result must equal the single-rank oracle on the whole box."""
@@ -347,6 +347,9 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
     # one stream for torch and all engines, so the copies that stand in for NCCL are ordered with the kernels
     tstream = torch.cuda.Stream(device=dev)
     gstream = torch.cuda.Stream(device=dev)
+    # overlap: the exchange runs on a communication stream behind the boundary tiles of the density pass
+    # (eph_b200_set_comm_stream / eph_b200_set_boundary_atoms) while the main stream sweeps the interior tiles
+    cstream = torch.cuda.Stream(device=dev) if overlap else tstream
     torch.cuda.set_stream(tstream)
     n, seed, dt = 6, 4711, 1e-4
     whole = H.make_system(n)
@@ -368,6 +371,9 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
         src = torch.zeros(int(np.prod(gshape)), dtype=torch.float64, device=dev)
         eng.bind_grid_source(src)
         eng.set_grid_stream(gstream.cuda_stream)     # source all-reduce + solve on a second stream
+        if overlap:
+            eng.set_comm_stream(cstream.cuda_stream)
+            eng.set_boundary_atoms(t(plan.flat_send_index(), torch.int32))
         engines.append(eng)
         state.append(dict(x=t(s["x"], torch.float64), v=t(s["v"], torch.float64),
                           f=torch.zeros((s["nlocal"], 3), dtype=torch.float64, device=dev), src=src,
@@ -383,21 +389,22 @@ def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world):
             st["f"].zero_()
             eng.post_force_begin(st["x"], st["v"], None, step)
         # the exchange: all_to_all of {rho, W} rows, done here by plain copies between the engines' buffers
-        bufs = []
-        for eng, st in zip(engines, state):
-            b = torch.empty((max(st["send"].numel(), 1), 4), dtype=torch.float64, device=dev)
-            if st["send"].numel():
-                eng.pack_ghost_payload(st["send"], b)
-            bufs.append(b)
-        for r, (eng, st, plan) in enumerate(zip(engines, state, plans)):
-            parts = []
-            for q in range(world):   # what rank q sends to r sits in q's buffer after what q sends to ranks < r
-                off = sum(plans[q].send_counts[:r])
-                parts.append(bufs[q][off: off + plans[q].send_counts[r]])
-            rb = torch.cat(parts) if parts else torch.empty((0, 4), dtype=torch.float64, device=dev)
-            assert rb.shape[0] == st["recv"].numel()
-            if st["recv"].numel():
-                eng.unpack_ghost_payload(st["recv"], rb.contiguous())
+        with torch.cuda.stream(cstream):
+            bufs = []
+            for eng, st in zip(engines, state):
+                b = torch.empty((max(st["send"].numel(), 1), 4), dtype=torch.float64, device=dev)
+                if st["send"].numel():
+                    eng.pack_ghost_payload(st["send"], b)
+                bufs.append(b)
+            for r, (eng, st, plan) in enumerate(zip(engines, state, plans)):
+                parts = []
+                for q in range(world):   # what rank q sends to r sits in q's buffer after what q sends to ranks < r
+                    off = sum(plans[q].send_counts[:r])
+                    parts.append(bufs[q][off: off + plans[q].send_counts[r]])
+                rb = torch.cat(parts) if parts else torch.empty((0, 4), dtype=torch.float64, device=dev)
+                assert rb.shape[0] == st["recv"].numel()
+                if st["recv"].numel():
+                    eng.unpack_ghost_payload(st["recv"], rb.contiguous())
         for eng, st in zip(engines, state):
             eng.post_force_end(st["f"])
             eng.end_of_step_begin(st["x"], st["v"])

@@ -164,21 +164,17 @@ struct DepositArgs {
   const double4 *__restrict__ pos4;  // bits (group) from the last post_force
   const double *__restrict__ f_eph;
   const double *__restrict__ f_rng;
-  const double *__restrict__ rho;
-  const double2 *__restrict__ beta_tab;
-  int n_beta;
-  double inv_drho, rho_cutoff;
   double dt, dVdt;
   int do_friction, do_random;
   GridGeom grid;
   double *__restrict__ dT_e;
   double *__restrict__ E_sum;    // one double, accumulated atomically per block
-  double *__restrict__ array8;   // [nlocal][8]
 };
 
 // FixEPH::end_of_step (fix_eph.cpp:350-429) up to the grid solve: per-atom
 // energy transfer, EPH_FDM::insert_energy (eph_fdm.h:172-179) with one atomic
-// per distinct cell per warp, the energy sum and the 8-column output.
+// per distinct cell per warp, and the energy sum.  The 8-column per-atom output is
+// produced on demand (peratom_kernel): nothing downstream of the step reads it on the device.
 __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
   __shared__ double s_part[8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,7 +185,6 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
   if (i < d.nlocal) {
     const unsigned bits = double_to_bits(d.pos4[i].w);
     const size_t o = 3 * (size_t)i;
-    double *row = d.array8 + 8 * (size_t)i;
     if (bits & kBitGroup) {
       const double vx = d.v[o], vy = d.v[o + 1], vz = d.v[o + 2];
       const double ex = d.f_eph[o], ey = d.f_eph[o + 1], ez = d.f_eph[o + 2];
@@ -204,16 +199,6 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
         const double4 p4 = d.pos4[i];
         cell = grid_index(d.grid, p4.x, p4.y, p4.z);
       }
-      const double rho = d.rho[i];
-      double beta = 0.0;  // eph_beta.h:171-184
-      if (!(rho > d.rho_cutoff))
-        beta = spline_eval(d.beta_tab + 2 * (size_t)(bits & kElemMask) * d.n_beta, d.inv_drho, rho);
-      row[0] = rho; row[1] = beta;
-      row[2] = ex; row[3] = ey; row[4] = ez;
-      row[5] = rx; row[6] = ry; row[7] = rz;
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) row[c] = 0.0;
     }
   }
   // warp-aggregated scatter-add: atoms are spatially sorted, so a warp usually
@@ -236,6 +221,29 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
     t = warp_sum(t);
     if (threadIdx.x == 0 && t != 0.0) atomicAdd(d.E_sum, t);
   }
+}
+
+// Per-atom output of the fix (fix_eph.cpp:406-428): rho_i, beta(rho_i), f_EPH, f_RNG; zeros outside the group.
+// Materialised when the caller asks for it (eph_b200_get_peratom) from the arrays the step left on the device.
+__global__ void __launch_bounds__(256) peratom_kernel(int nlocal, const double4 *__restrict__ pos4, const double *__restrict__ rho_i,
+                                                      const double *__restrict__ f_eph, const double *__restrict__ f_rng,
+                                                      const double2 *__restrict__ beta_tab, int n_beta, double inv_drho,
+                                                      double rho_cutoff, double *__restrict__ array8) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlocal) return;
+  const unsigned bits = double_to_bits(pos4[i].w);
+  double4 lo = make_double4(0, 0, 0, 0), hi = lo;
+  if (bits & kBitGroup) {
+    const size_t o = 3 * (size_t)i;
+    const double rho = rho_i[i];
+    double beta = 0.0;  // eph_beta.h:171-184
+    if (!(rho > rho_cutoff)) beta = spline_eval(beta_tab + 2 * (size_t)(bits & kElemMask) * n_beta, inv_drho, rho);
+    lo = make_double4(rho, beta, f_eph[o], f_eph[o + 1]);
+    hi = make_double4(f_eph[o + 2], f_rng[o], f_rng[o + 1], f_rng[o + 2]);
+  }
+  double4 *row = reinterpret_cast<double4 *>(array8 + 8 * (size_t)i);
+  row[0] = lo;
+  row[1] = hi;
 }
 
 // FixEPH::initial_integrate / final_integrate (fix_eph.cpp:305-348)

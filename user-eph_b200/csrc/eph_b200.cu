@@ -94,6 +94,7 @@ struct eph_b200_handle {
   DevBuf<double4> pos4, pv, puz, W4;
   DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
   bool forces_valid = false;
+  bool peratom_valid = false;   // an end_of_step has run: the per-atom output (fix_eph.cpp:406-428) can be materialised
   // state between post_force_begin and post_force_end
   bool pf_open = false, pf_build = false;
   const double *pf_xi = nullptr;
@@ -103,6 +104,14 @@ struct eph_b200_handle {
   cudaStream_t grid_stream = nullptr;
   cudaEvent_t ev_deposit = nullptr, ev_solved = nullptr;
   bool solve_pending = false;
+  // optional communication stream + boundary-first density pass: the ghost exchange of a step (pack, the caller's
+  // all-to-all, unpack) runs on it behind the boundary tiles while the main stream still sweeps the interior tiles
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_boundary = nullptr, ev_unpacked = nullptr;
+  bool unpack_pending = false, boundary_recorded = false;
+  DevBuf<int> tile_flag, tile_scan, work_first, work_rest;
+  int n_first = 0, n_rest = 0;          // tiles in the two work lists
+  bool split_ready = false;
   double *dT_e_ext = nullptr;   // caller-owned grid source term (multi-rank: all-reduced between the two end_of_step halves)
 
   // neighbours
@@ -368,6 +377,8 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
             cudaEventCreateWithFlags(&h->f_event, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_deposit, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_boundary, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             h->d_mm.reserve(4) == cudaSuccess && h->d_status.reserve(1) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 8 * sizeof(double)) == cudaSuccess &&
@@ -406,6 +417,9 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (h->f_event) cudaEventDestroy(h->f_event);
   if (h->ev_deposit) cudaEventDestroy(h->ev_deposit);
   if (h->ev_solved) cudaEventDestroy(h->ev_solved);
+  if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
+  if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
+  h->tile_flag.release(); h->tile_scan.release(); h->work_first.release(); h->work_rest.release();
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -665,6 +679,8 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));  // host source buffers may be reused by the caller
   h->nlocal = nlocal; h->nghost = nghost;
   h->atoms_set = true;
+  h->peratom_valid = false;
+  h->split_ready = false;   // the boundary work lists name atoms of the previous registration
   h->neigh_set = false;
   h->forces_valid = false;
   return EPH_B200_OK;
@@ -839,9 +855,9 @@ int env_int(const char *name, int dflt) {
 }
 
 template <int LANES, int TAB, bool MULTI>
-int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool build) {
+int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool build, const char *name) {
   const int threads = 256;
-  KernelTimer kt(h, build ? "density_sweep_build" : "density_sweep");
+  KernelTimer kt(h, name ? name : (build ? "density_sweep_build" : "density_sweep"));
   if (build) {
     auto k = density_sweep_kernel<LANES, TAB, true, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -866,19 +882,19 @@ int launch_force(eph_b200_handle *h, const SweepArgs &a) {
 }
 
 template <int TAB, bool MULTI>
-int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, int lanes, bool build) {
+int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, int lanes, bool build, const char *name) {
   switch (lanes) {
-    case 1: return launch_density<1, TAB, MULTI>(h, a, smem, build);
-    case 2: return launch_density<2, TAB, MULTI>(h, a, smem, build);
-    case 8: return launch_density<8, TAB, MULTI>(h, a, smem, build);
-    case 16: return launch_density<16, TAB, MULTI>(h, a, smem, build);
-    default: return launch_density<4, TAB, MULTI>(h, a, smem, build);
+    case 1: return launch_density<1, TAB, MULTI>(h, a, smem, build, name);
+    case 2: return launch_density<2, TAB, MULTI>(h, a, smem, build, name);
+    case 8: return launch_density<8, TAB, MULTI>(h, a, smem, build, name);
+    case 16: return launch_density<16, TAB, MULTI>(h, a, smem, build, name);
+    default: return launch_density<4, TAB, MULTI>(h, a, smem, build, name);
   }
 }
 
 // which: 0 density pass (optionally rebuilding the inner list), 1 force pass.  Both passes use the same number of
 // lanes per atom: it fixes the tile shape of the inner list and of the pair weights.
-int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false) {
+int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false, const char *name = nullptr) {
   const bool multi = a.n_elements > 1;
   if (which == 1) {
     switch (h->lanes) {
@@ -896,11 +912,11 @@ int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build =
   static const int table_mode = env_int("EPH_B200_TABLE", 0);
   const bool smem = table_mode == 1 && table_bytes <= (size_t)h->max_smem_optin - 1024;
   if (smem) {
-    if (multi) return launch_density_lanes<1, true>(h, a, table_bytes, h->lanes, build);
-    return launch_density_lanes<1, false>(h, a, table_bytes, h->lanes, build);
+    if (multi) return launch_density_lanes<1, true>(h, a, table_bytes, h->lanes, build, name);
+    return launch_density_lanes<1, false>(h, a, table_bytes, h->lanes, build, name);
   }
-  if (multi) return launch_density_lanes<0, true>(h, a, 0, h->lanes, build);
-  return launch_density_lanes<0, false>(h, a, 0, h->lanes, build);
+  if (multi) return launch_density_lanes<0, true>(h, a, 0, h->lanes, build, name);
+  return launch_density_lanes<0, false>(h, a, 0, h->lanes, build, name);
 }
 
 SweepArgs sweep_args(eph_b200_handle *h) {
@@ -974,7 +990,23 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
 
   SweepArgs a = sweep_args(h);
   a.use_inner = (h->inner_enabled && h->have_inner && !build) ? 1 : 0;
-  if ((rc = launch_sweep(h, a, 0, build))) return rc;
+  const int tile_atoms = 32 / h->lanes;
+  if (h->comm_stream && h->split_ready && h->n_first > 0) {
+    // boundary tiles first: once they are done the exchange can start on the communication stream while this
+    // stream sweeps the interior tiles
+    a.work = h->work_first.p; a.n_work = h->n_first * tile_atoms;
+    if ((rc = launch_sweep(h, a, 0, build, "density_sweep_boundary"))) return rc;
+    EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
+    if (h->n_rest > 0) {
+      a.work = h->work_rest.p; a.n_work = h->n_rest * tile_atoms;
+      if ((rc = launch_sweep(h, a, 0, build))) return rc;
+    }
+  } else {
+    a.work = nullptr; a.n_work = nl;
+    if ((rc = launch_sweep(h, a, 0, build))) return rc;
+    if (h->comm_stream) EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
+  }
+  h->boundary_recorded = h->comm_stream != nullptr;
   if (build) {
     EPH_CUDA(h, cudaMemcpyAsync(h->xref.p, h->pos4.p, (size_t)nt * sizeof(double4), cudaMemcpyDeviceToDevice, h->stream));
     if (h->fresh_neighbors)
@@ -1013,6 +1045,11 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   h->f_prefetched = false;
   const bool build = h->pf_build;
   join_grid_stream(h);   // the force pass reads T_e
+  if (h->unpack_pending) {
+    EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_unpacked, 0));
+    h->unpack_pending = false;
+  }
+  h->boundary_recorded = false;
 
   PrepArgs p{};
   p.nlocal = nl; p.ntotal = nt; p.owner = h->has_owner ? h->owner.p : nullptr; p.tag = h->tag.p;
@@ -1075,9 +1112,14 @@ int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index
   if (n < 0 || (n > 0 && (!send_index_dev || !buf_dev))) return fail(h, EPH_B200_ERR_ARG, "pack_ghost_payload: bad arguments");
   if (n == 0) return EPH_B200_OK;
   cudaSetDevice(h->cfg.device);
+  cudaStream_t st = h->stream;
+  if (h->comm_stream) {   // starts as soon as the boundary tiles of the density pass are done
+    st = h->comm_stream;
+    if (h->boundary_recorded) EPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_boundary, 0));
+  }
   {
-    KernelTimer kt(h, "pack_payload");
-    pack_payload_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, send_index_dev, h->rho.p, h->W4.p, reinterpret_cast<double4 *>(buf_dev));
+    KernelTimer kt(h, "pack_payload", st);
+    pack_payload_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, send_index_dev, h->rho.p, h->W4.p, reinterpret_cast<double4 *>(buf_dev));
   }
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
@@ -1088,12 +1130,17 @@ int eph_b200_unpack_ghost_payload(eph_b200_handle *h, int n, const int *recv_ind
   if (n < 0 || (n > 0 && (!recv_index_dev || !buf_dev))) return fail(h, EPH_B200_ERR_ARG, "unpack_ghost_payload: bad arguments");
   if (n == 0) return EPH_B200_OK;
   cudaSetDevice(h->cfg.device);
+  cudaStream_t st = h->comm_stream ? h->comm_stream : h->stream;
   {
-    KernelTimer kt(h, "unpack_payload");
-    unpack_payload_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, recv_index_dev, h->rho.p, h->W4.p,
-                                                                      reinterpret_cast<const double4 *>(buf_dev), h->nlocal + h->nghost);
+    KernelTimer kt(h, "unpack_payload", st);
+    unpack_payload_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, recv_index_dev, h->rho.p, h->W4.p,
+                                                               reinterpret_cast<const double4 *>(buf_dev), h->nlocal + h->nghost);
   }
   EPH_LAUNCH_CHECK(h);
+  if (h->comm_stream) {   // post_force_end waits for the ghosts' {rho, W}
+    EPH_CUDA(h, cudaEventRecord(h->ev_unpacked, st));
+    h->unpack_pending = true;
+  }
   return EPH_B200_OK;
 }
 
@@ -1200,12 +1247,11 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {
     DepositArgs d{};
-    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p; d.rho = h->rho.p;
-    d.beta_tab = h->beta_tab.p; d.n_beta = h->n_beta; d.inv_drho = h->inv_drho; d.rho_cutoff = h->rho_cut;
+    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p;
     d.dt = h->dt; d.dVdt = h->dV * h->dt;
     d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
     d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
-    d.grid = grid_geom(h); d.dT_e = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; d.E_sum = h->d_scal.p; d.array8 = h->array8.p;
+    d.grid = grid_geom(h); d.dT_e = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; d.E_sum = h->d_scal.p;
     {
       KernelTimer kt(h, "deposit");
       deposit_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(d);
@@ -1217,6 +1263,7 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
     EPH_CUDA(h, cudaStreamWaitEvent(h->grid_stream, h->ev_deposit, 0));
   }
   h->eos_open = true;
+  h->peratom_valid = true;
   return EPH_B200_OK;
 }
 
@@ -1254,6 +1301,54 @@ int eph_b200_set_grid_stream(eph_b200_handle *h, void *stream) {
   join_grid_stream(h);
   if (h->grid_stream) cudaStreamSynchronize(h->grid_stream);
   h->grid_stream = static_cast<cudaStream_t>(stream);
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_comm_stream(eph_b200_handle *h, void *stream) {
+  if (!h) return EPH_B200_ERR_ARG;
+  cudaSetDevice(h->cfg.device);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  cudaStreamSynchronize(h->stream);
+  h->comm_stream = static_cast<cudaStream_t>(stream);
+  h->unpack_pending = false;
+  h->boundary_recorded = false;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_boundary_atoms(eph_b200_handle *h, int n, const int *index, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "set_boundary_atoms: call set_atoms first");
+  if (n < 0 || (n > 0 && !index)) return fail(h, EPH_B200_ERR_ARG, "set_boundary_atoms: bad arguments");
+  cudaSetDevice(h->cfg.device);
+  h->split_ready = false;
+  h->n_first = h->n_rest = 0;
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  const int tile_atoms = 32 / h->lanes;
+  const int ntiles = (nl + tile_atoms - 1) / tile_atoms;
+  const int *didx = nullptr;
+  int rc;
+  if (n > 0 && (rc = stage_in(h, h->comm_idx, index, (size_t)n, memspace, &didx))) return rc;
+  EPH_CUDA(h, h->tile_flag.reserve((size_t)ntiles + 1)); EPH_CUDA(h, h->tile_scan.reserve((size_t)ntiles + 1));
+  EPH_CUDA(h, h->work_first.reserve(ntiles)); EPH_CUDA(h, h->work_rest.reserve(ntiles));
+  EPH_CUDA(h, cudaMemsetAsync(h->tile_flag.p, 0, ((size_t)ntiles + 1) * sizeof(int), h->stream));
+  if (n > 0) {
+    tile_mark_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, didx, tile_atoms, nl, h->tile_flag.p);
+    EPH_LAUNCH_CHECK(h);
+  }
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, h->tile_flag.p, h->tile_scan.p, ntiles + 1, h->stream);
+  EPH_CUDA(h, h->nb_tmp.reserve(scan_bytes));
+  EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->tile_flag.p, h->tile_scan.p, ntiles + 1, h->stream));
+  ++h->launches;
+  tile_split_kernel<<<blocks_for(ntiles, 256), 256, 0, h->stream>>>(ntiles, h->tile_flag.p, h->tile_scan.p, h->work_first.p, h->work_rest.p);
+  EPH_LAUNCH_CHECK(h);
+  int first = 0;
+  EPH_CUDA(h, cudaMemcpyAsync(&first, h->tile_scan.p + ntiles, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_first = first;
+  h->n_rest = ntiles - first;
+  h->split_ready = true;
   return EPH_B200_OK;
 }
 
@@ -1326,8 +1421,21 @@ int eph_b200_get_peratom(eph_b200_handle *h, double *array8, int memspace) {
   if (!h || !array8) return EPH_B200_ERR_ARG;
   if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "get_peratom: set_atoms not called");
   cudaSetDevice(h->cfg.device);
-  EPH_CUDA(h, cudaMemcpyAsync(array8, h->array8.p, 8 * (size_t)h->nlocal * sizeof(double),
-                              memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  // the 8 columns are not written every step (64 bytes per atom nobody reads on the device): they are formed here
+  // from rho_i, f_EPH and f_RNG of the last step; before the first end_of_step they are zero like the reference's
+  double *dst = memspace == EPH_B200_DEVICE ? array8 : h->array8.p;
+  if (!h->peratom_valid) {
+    EPH_CUDA(h, cudaMemsetAsync(dst, 0, 8 * (size_t)nl * sizeof(double), h->stream));
+  } else {
+    KernelTimer kt(h, "peratom");
+    peratom_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->pos4.p, h->rho.p, h->f_eph.p, h->f_rng.p, h->beta_tab.p,
+                                                              h->n_beta, h->inv_drho, h->rho_cut, dst);
+    EPH_LAUNCH_CHECK(h);
+  }
+  if (memspace != EPH_B200_DEVICE)
+    EPH_CUDA(h, cudaMemcpyAsync(array8, h->array8.p, 8 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
   return EPH_B200_OK;
 }

@@ -22,6 +22,22 @@ __global__ void tile_caps_kernel(int nlocal, const long long *__restrict__ offse
   caps[w] = 32 * ((longest + lanes - 1) / lanes);
 }
 
+// Boundary-first ordering of the density pass (multi-rank overlap): tiles that hold an atom some other rank needs as a
+// ghost are flagged, then split into two ordered work lists with an exclusive scan of the flags.
+__global__ void tile_mark_kernel(int n, const int *__restrict__ index, int tile_atoms, int nlocal, int *__restrict__ flag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int a = index[t];
+  if (a >= 0 && a < nlocal) flag[a / tile_atoms] = 1;
+}
+__global__ void tile_split_kernel(int ntiles, const int *__restrict__ flag, const int *__restrict__ scan,
+                                  int *__restrict__ first, int *__restrict__ rest) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  if (flag[t]) first[scan[t]] = t;
+  else rest[t - scan[t]] = t;
+}
+
 struct CellGrid {
   double lo[3];
   double inv[3];   // cells per length

@@ -77,6 +77,8 @@ struct SweepArgs {
   const long long *__restrict__ tile_off; // [ceil(nlocal / (32/LANES)) + 1] first entry of every tile (multiples of 32)
   int *__restrict__ icount;               // [nlocal] inner-list lengths
   const unsigned *__restrict__ inner_invalid;  // device flag: != 0 -> inner list must not be used
+  const int *__restrict__ work;           // density pass: tiles to process in this launch (nullptr: all, in order)
+  int n_work;                             // density pass: atoms covered by this launch (tiles * 32/LANES, or nlocal)
   int use_inner;                          // density pass: an inner list exists
   int spec_v;                             // density pass: fetch v_j together with the position when walking the inner list
   int walk_mode;                          // force pass: 0 LAMMPS' list, 1 inner list unless the device flag is set, 2 inner list
@@ -165,7 +167,10 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   const bool spec = inner && a.spec_v;
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
-  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
+  for (int w = blockIdx.x * groups_per_block + group_in_block; w < a.n_work; w += gridDim.x * groups_per_block) {
+    // a work list names whole tiles (the warp's 32/LANES atoms), so the lane <-> tile-slot mapping is unchanged
+    const int i = a.work ? a.work[w / (32 / LANES)] * (32 / LANES) + (w & (32 / LANES - 1)) : w;
+    if (i >= a.nlocal) continue;
     const double4 pi = ld256(a.pv + kPvStride * (size_t)i);
     const unsigned bi = double_to_bits(pi.w);
     double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;

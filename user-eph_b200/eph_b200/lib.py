@@ -57,6 +57,8 @@ SYMBOLS = {
     "eph_b200_end_of_step_end": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_bind_grid_source": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_set_grid_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eph_b200_set_comm_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eph_b200_set_boundary_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "eph_b200_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_double, C.c_int]),
     "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
@@ -268,6 +270,14 @@ class Engine:
 
     def set_grid_stream(self, stream):
         self._check(self.lib.eph_b200_set_grid_stream(self.h, C.c_void_p(stream) if stream else None))
+
+    def set_comm_stream(self, stream):
+        self._check(self.lib.eph_b200_set_comm_stream(self.h, C.c_void_p(stream) if stream else None))
+
+    def set_boundary_atoms(self, index):
+        """index: int32 local indices (numpy or device tensor) of the owned atoms other ranks hold as ghosts"""
+        p = _ptr(index)
+        self._check(self.lib.eph_b200_set_boundary_atoms(self.h, len(index), p[0], p[1]))
 
     def end_of_step(self, x, v, want_energy=True):
         ps = [_ptr(x), _ptr(v)]

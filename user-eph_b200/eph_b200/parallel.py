@@ -106,11 +106,16 @@ def _alltoall_lists(lists, dist):
 
 
 class GhostExchange:
-    """Device-side exchange for an Engine: pack -> all_to_all over NCCL -> unpack."""
+    """Device-side exchange for an Engine: pack -> all_to_all over NCCL -> unpack.
 
-    def __init__(self, plan, dist, device):
+    comm_stream: a torch.cuda.Stream registered with engine.set_comm_stream(); pack, the all-to-all and unpack then
+    run on it, behind the boundary tiles of the density pass (engine.set_boundary_atoms(self.send_idx)), and overlap
+    the sweep of the interior tiles on the engine's main stream."""
+
+    def __init__(self, plan, dist, device, comm_stream=None):
         import torch
         self.plan, self.dist = plan, dist
+        self.comm_stream = comm_stream
         self.send_idx = torch.as_tensor(plan.flat_send_index(), dtype=torch.int32, device=device)
         self.recv_idx = torch.as_tensor(plan.flat_recv_index(), dtype=torch.int32, device=device)
         self.send_buf = torch.empty((max(self.send_idx.numel(), 1), 4), dtype=torch.float64, device=device)
@@ -123,8 +128,14 @@ class GhostExchange:
         if ns:
             engine.pack_ghost_payload(self.send_idx, self.send_buf)
         if self.plan.world > 1:
-            self.dist.all_to_all_single(self.recv_buf.view(-1)[: 4 * nr], self.send_buf.view(-1)[: 4 * ns],
-                                        output_split_sizes=self.in_splits, input_split_sizes=self.out_splits)
+            if self.comm_stream is not None:
+                import torch
+                with torch.cuda.stream(self.comm_stream):
+                    self.dist.all_to_all_single(self.recv_buf.view(-1)[: 4 * nr], self.send_buf.view(-1)[: 4 * ns],
+                                                output_split_sizes=self.in_splits, input_split_sizes=self.out_splits)
+            else:
+                self.dist.all_to_all_single(self.recv_buf.view(-1)[: 4 * nr], self.send_buf.view(-1)[: 4 * ns],
+                                            output_split_sizes=self.in_splits, input_split_sizes=self.out_splits)
         if nr:
             engine.unpack_ghost_payload(self.recv_idx, self.recv_buf)
 
