@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-fdm-bench", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
     ap.add_argument("--cpu-cells", type=int, default=16, help="edge of each CPU-baseline replica (16 -> 16 384 atoms)")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=100, help="timed steps of every CPU-baseline replica (about 10 s of work per core)")
     return ap.parse_args()
 
 
@@ -175,7 +175,7 @@ def run_reference_arm(a):
     per_step = []
     base = None
     for k in range(a.warmup + a.steps):
-        base = cpu_baseline(a.cpu_cells, 1)
+        base = cpu_baseline(a.cpu_cells, 10)
         if k >= a.warmup:
             per_step.append(base["value"])
     value = float(np.mean(per_step))
@@ -322,8 +322,17 @@ def run_b200(a):
     if dom:
         ach = alg[dom] * nl / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9
         b_step = 420 + 12 * n_nb
+        # DRAM bytes per launch of the same kernel on the same workload from the committed ncu capture (tools/ncu_traffic.py)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_4M.json")))
+            if tj["atoms"] == nl and dom in tj["kernels"]:
+                traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], "profiles/r1_traffic_4M.json (%s)" % tj["report"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": alg[dom] * nl, "peak_source": peak_src,
                     "algorithmic_bytes_per_atom": alg[dom], "kernel_ms": per_kernel[dom]["ms_avg"],
                     "step": {"algorithmic_bytes_per_atom_step": b_step, "achieved": b_step * value / 1e9 / world,
                              "frac": b_step * value / 1e9 / world / peak, "note": "whole step, per GPU"},
