@@ -109,8 +109,11 @@ struct eph_b200_handle {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_boundary = nullptr, ev_unpacked = nullptr;
   bool unpack_pending = false, boundary_recorded = false;
-  DevBuf<int> tile_flag, tile_scan, work_first, work_rest;
-  int n_first = 0, n_rest = 0;          // tiles in the two work lists
+  DevBuf<int> tile_flag, tile_scan, work_all;   // work_all: boundary tiles, then interior tiles
+  int n_first = 0, n_rest = 0;          // boundary / interior tiles
+  DevBuf<unsigned> done_counter;        // finished boundary tiles (monotonic, wraps; compared cyclically)
+  unsigned boundary_target = 0;         // counter value at which this step's boundary tiles are all done
+  bool boundary_by_counter = false;     // this step's pack waits on the counter (one launch) instead of an event (two)
   bool split_ready = false;
   double *dT_e_ext = nullptr;   // caller-owned grid source term (multi-rank: all-reduced between the two end_of_step halves)
 
@@ -293,6 +296,22 @@ int stage_in(eph_b200_handle *h, DevBuf<T> &buf, const T *src, size_t n, int mem
   return EPH_B200_OK;
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point query (no -lcuda at link time); nullptr if unavailable
+typedef CUresult (*StreamWaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValueFn stream_wait_value() {
+  static StreamWaitValueFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char *off = std::getenv("EPH_B200_NO_WAIT_VALUE");
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (!(off && off[0] == '1') && cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+      fn = reinterpret_cast<StreamWaitValueFn>(p);
+  }
+  return fn;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -419,7 +438,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (h->ev_solved) cudaEventDestroy(h->ev_solved);
   if (h->ev_boundary) cudaEventDestroy(h->ev_boundary);
   if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
-  h->tile_flag.release(); h->tile_scan.release(); h->work_first.release(); h->work_rest.release();
+  h->tile_flag.release(); h->tile_scan.release(); h->work_all.release(); h->done_counter.release();
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -991,18 +1010,27 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   SweepArgs a = sweep_args(h);
   a.use_inner = (h->inner_enabled && h->have_inner && !build) ? 1 : 0;
   const int tile_atoms = 32 / h->lanes;
-  if (h->comm_stream && h->split_ready && h->n_first > 0) {
-    // boundary tiles first: once they are done the exchange can start on the communication stream while this
-    // stream sweeps the interior tiles
-    a.work = h->work_first.p; a.n_work = h->n_first * tile_atoms;
+  a.work = nullptr; a.n_work = nl; a.n_boundary = 0; a.done_counter = nullptr;
+  h->boundary_by_counter = false;
+  if (h->comm_stream && h->split_ready && h->n_first > 0 && stream_wait_value() != nullptr) {
+    // ONE launch over the reordered tiles, boundary tiles first; each finished boundary tile bumps a counter the
+    // communication stream waits on (stream memory operation), so the exchange starts while this launch is still
+    // sweeping the interior tiles
+    a.work = h->work_all.p; a.n_work = (h->n_first + h->n_rest) * tile_atoms;
+    a.n_boundary = h->n_first * tile_atoms; a.done_counter = h->done_counter.p;
+    h->boundary_target += (unsigned)h->n_first;
+    h->boundary_by_counter = true;
+    if ((rc = launch_sweep(h, a, 0, build))) return rc;
+  } else if (h->comm_stream && h->split_ready && h->n_first > 0) {
+    // no stream memory operations: two launches with an event between them
+    a.work = h->work_all.p; a.n_work = h->n_first * tile_atoms;
     if ((rc = launch_sweep(h, a, 0, build, "density_sweep_boundary"))) return rc;
     EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
     if (h->n_rest > 0) {
-      a.work = h->work_rest.p; a.n_work = h->n_rest * tile_atoms;
+      a.work = h->work_all.p + h->n_first; a.n_work = h->n_rest * tile_atoms;
       if ((rc = launch_sweep(h, a, 0, build))) return rc;
     }
   } else {
-    a.work = nullptr; a.n_work = nl;
     if ((rc = launch_sweep(h, a, 0, build))) return rc;
     if (h->comm_stream) EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
   }
@@ -1115,7 +1143,12 @@ int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index
   cudaStream_t st = h->stream;
   if (h->comm_stream) {   // starts as soon as the boundary tiles of the density pass are done
     st = h->comm_stream;
-    if (h->boundary_recorded) EPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_boundary, 0));
+    if (h->boundary_recorded && h->boundary_by_counter) {
+      if (stream_wait_value()(st, (CUdeviceptr)h->done_counter.p, h->boundary_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(h, EPH_B200_ERR_CUDA, "pack_ghost_payload: cuStreamWaitValue32 failed");
+    } else if (h->boundary_recorded) {
+      EPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_boundary, 0));
+    }
   }
   {
     KernelTimer kt(h, "pack_payload", st);
@@ -1330,7 +1363,12 @@ int eph_b200_set_boundary_atoms(eph_b200_handle *h, int n, const int *index, int
   int rc;
   if (n > 0 && (rc = stage_in(h, h->comm_idx, index, (size_t)n, memspace, &didx))) return rc;
   EPH_CUDA(h, h->tile_flag.reserve((size_t)ntiles + 1)); EPH_CUDA(h, h->tile_scan.reserve((size_t)ntiles + 1));
-  EPH_CUDA(h, h->work_first.reserve(ntiles)); EPH_CUDA(h, h->work_rest.reserve(ntiles));
+  EPH_CUDA(h, h->work_all.reserve(ntiles));
+  if (!h->done_counter.p) {
+    EPH_CUDA(h, h->done_counter.reserve(1));
+    EPH_CUDA(h, cudaMemsetAsync(h->done_counter.p, 0, sizeof(unsigned), h->stream));
+    h->boundary_target = 0;
+  }
   EPH_CUDA(h, cudaMemsetAsync(h->tile_flag.p, 0, ((size_t)ntiles + 1) * sizeof(int), h->stream));
   if (n > 0) {
     tile_mark_kernel<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, didx, tile_atoms, nl, h->tile_flag.p);
@@ -1341,7 +1379,7 @@ int eph_b200_set_boundary_atoms(eph_b200_handle *h, int n, const int *index, int
   EPH_CUDA(h, h->nb_tmp.reserve(scan_bytes));
   EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->tile_flag.p, h->tile_scan.p, ntiles + 1, h->stream));
   ++h->launches;
-  tile_split_kernel<<<blocks_for(ntiles, 256), 256, 0, h->stream>>>(ntiles, h->tile_flag.p, h->tile_scan.p, h->work_first.p, h->work_rest.p);
+  tile_split_kernel<<<blocks_for(ntiles, 256), 256, 0, h->stream>>>(ntiles, h->tile_flag.p, h->tile_scan.p, h->work_all.p);
   EPH_LAUNCH_CHECK(h);
   int first = 0;
   EPH_CUDA(h, cudaMemcpyAsync(&first, h->tile_scan.p + ntiles, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

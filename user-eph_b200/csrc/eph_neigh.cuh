@@ -31,11 +31,11 @@ __global__ void tile_mark_kernel(int n, const int *__restrict__ index, int tile_
   if (a >= 0 && a < nlocal) flag[a / tile_atoms] = 1;
 }
 __global__ void tile_split_kernel(int ntiles, const int *__restrict__ flag, const int *__restrict__ scan,
-                                  int *__restrict__ first, int *__restrict__ rest) {
+                                  int *__restrict__ work /* boundary tiles, then interior tiles */) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
-  if (flag[t]) first[scan[t]] = t;
-  else rest[t - scan[t]] = t;
+  if (flag[t]) work[scan[t]] = t;
+  else work[scan[ntiles] + t - scan[t]] = t;
 }
 
 struct CellGrid {

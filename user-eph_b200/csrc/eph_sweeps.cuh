@@ -79,6 +79,8 @@ struct SweepArgs {
   const unsigned *__restrict__ inner_invalid;  // device flag: != 0 -> inner list must not be used
   const int *__restrict__ work;           // density pass: tiles to process in this launch (nullptr: all, in order)
   int n_work;                             // density pass: atoms covered by this launch (tiles * 32/LANES, or nlocal)
+  int n_boundary;                         // density pass: the first n_boundary work atoms are boundary tiles ...
+  unsigned *__restrict__ done_counter;    // ... each finished boundary tile adds 1 here (the exchange waits on it)
   int use_inner;                          // density pass: an inner list exists
   int spec_v;                             // density pass: fetch v_j together with the position when walking the inner list
   int walk_mode;                          // force pass: 0 LAMMPS' list, 1 inner list unless the device flag is set, 2 inner list
@@ -170,12 +172,13 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   for (int w = blockIdx.x * groups_per_block + group_in_block; w < a.n_work; w += gridDim.x * groups_per_block) {
     // a work list names whole tiles (the warp's 32/LANES atoms), so the lane <-> tile-slot mapping is unchanged
     const int i = a.work ? a.work[w / (32 / LANES)] * (32 / LANES) + (w & (32 / LANES - 1)) : w;
-    if (i >= a.nlocal) continue;
-    const double4 pi = ld256(a.pv + kPvStride * (size_t)i);
+    const bool real = i < a.nlocal;   // the last tile may be partial
+    double4 pi = make_double4(0, 0, 0, 0);
+    if (real) pi = ld256(a.pv + kPvStride * (size_t)i);
     const unsigned bi = double_to_bits(pi.w);
     double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
     int icnt = 0;
-    if (bi & kBitGroup) {  // atoms outside the fix group keep rho = 0 (fix_eph.cpp:442-445) and w = 0 (:704)
+    if (real && (bi & kBitGroup)) {  // atoms outside the fix group keep rho = 0 (fix_eph.cpp:442-445) and w = 0 (:704)
       const double4 vi = a.do_friction ? ld256(a.pv + kPvStride * (size_t)i + 1) : make_double4(0, 0, 0, 0);
       const int off_i = (bi & kElemMask) * a.n_rho;
       const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
@@ -239,10 +242,19 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
         wx = group_sum<LANES>(wx, gmask); wy = group_sum<LANES>(wy, gmask); wz = group_sum<LANES>(wz, gmask);
       }
     }
-    if (sub == 0) {
+    if (real && sub == 0) {
       a.rho[i] = rho;
       a.W4[i] = make_double4(wx, wy, wz, 0.0);
       if (BUILD) a.icount[i] = icnt;
+    }
+    // boundary tiles come first in the work list; when the last of them is done the ghost exchange may start
+    // (the communication stream waits for the counter with a stream memory operation)
+    if (a.done_counter != nullptr && w < a.n_boundary) {   // warp-uniform: a warp owns exactly one tile
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(a.done_counter, 1u);
+      }
     }
   }
 }
