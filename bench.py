@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
+    ap.add_argument("--elements", type=int, default=1, help="config C4: this many elements (types uniform random), synthetic "
+                    "multi-element .beta file written on the fly; the default 1 is the Ni workload of the headline metric")
     ap.add_argument("--cpu-cells", type=int, default=16, help="edge of each CPU-baseline replica (16 -> 16 384 atoms)")
     ap.add_argument("--cpu-steps", type=int, default=100, help="timed steps of every CPU-baseline replica (about 10 s of work per core)")
     return ap.parse_args()
@@ -52,9 +54,9 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
-def build_workload(cells, brick=None):
+def build_workload(cells, brick=None, elements=1):
     from eph_b200 import harness as H
-    s = H.make_system(cells, brick=brick)
+    s = H.make_system(cells, brick=brick, ntypes=elements)
     # the primary knock-on atom of config C3: 10 keV along (0.835, 0.544, 0.082) (Tests/MD_Run/run.lmp:69-73)
     if brick is None or brick[0] == 0:
         pka = 0
@@ -193,9 +195,12 @@ def run_reference_arm(a):
 
 
 def workload_config(a, natoms):
-    return {"workload": "C3: Ni fcc %d^3 cells = %d atoms, one 10 keV PKA, flags 7 (friction+random+FDM), model 4, "
-                        "FDM grid %d^3, dt 1e-4 ps, full list at 7 A" % (a.cells, natoms, a.grid),
-            "atoms": natoms, "fdm_grid": [a.grid] * 3, "beta_file": "tests/golden/Ni_trunc.beta",
+    multi = getattr(a, "elements", 1) > 1
+    name = ("C4: %d-element fcc alloy (types uniform random, synthetic .beta tables)" % a.elements) if multi else "C3: Ni fcc"
+    return {"workload": "%s %d^3 cells = %d atoms, one 10 keV PKA, flags 7 (friction+random+FDM), model 4, "
+                        "FDM grid %d^3, dt 1e-4 ps, full list at 7 A" % (name, a.cells, natoms, a.grid),
+            "atoms": natoms, "fdm_grid": [a.grid] * 3,
+            "beta_file": "synthetic (eph_b200.harness.synthetic_knots)" if multi else "tests/golden/Ni_trunc.beta",
             "l2": "inputs (neighbour list + per-atom arrays) far larger than the 126 MB L2; no flush needed",
             "parallelism": "spatial bricks, one rank per GPU"}
 
@@ -221,7 +226,7 @@ def run_b200(a):
     D = dist if world > 1 else None
 
     grid = P.brick_grid(world)
-    s = build_workload(a.cells, brick=(rank, grid) if world > 1 else None)
+    s = build_workload(a.cells, brick=(rank, grid) if world > 1 else None, elements=a.elements)
     if world == 1:
         s["grid"] = (1, 1, 1)
     nl, ng = s["nlocal"], s["nghost"]
@@ -235,8 +240,14 @@ def run_b200(a):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    eng = lib.Engine([0], flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
-    eng.set_tables_from(host.BetaTables(path=BETA_FILE))
+    beta_file = BETA_FILE
+    if a.elements > 1:   # C4: multi-element tables (two look-ups per pair, second pair-weight stream)
+        import tempfile
+        from eph_b200 import harness as H
+        beta_file = os.path.join(tempfile.mkdtemp(prefix="eph_bench_"), "synthetic_%d.beta" % a.elements)
+        H.write_beta_file(beta_file, H.synthetic_knots(n_elements=a.elements))
+    eng = lib.Engine(list(range(a.elements)), flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
+    eng.set_tables_from(host.BetaTables(path=beta_file))
     eng.set_grid(a.grid, a.grid, a.grid, box, 300.0, 1.0, 3.5e-6, 0.1248)
     eng.set_dt(DT)
     eng.set_skin(2.0)
