@@ -54,9 +54,10 @@ enum eph_b200_flag {
   EPH_B200_NORANDOM = 0x20
 };
 
-/* eph_model -- FixEPH::Model, fix_eph.h:53-60.  The device path implements
- * PRL (4), the model every BASELINE configuration uses. */
-enum eph_b200_model { EPH_B200_MODEL_NONE = 0, EPH_B200_MODEL_PRL = 4 };
+/* eph_model -- FixEPH::Model, fix_eph.h:53-60.  PRL (4) is the model every BASELINE configuration uses; TTM (1,
+ * fix_eph.cpp:468-503) and PRB (2, :505-568) are the reference's uncorrelated legacy models (PRB additionally needs
+ * eph_b200_set_rho_r_table).  PRLCM (3) is rejected: the reference reads out of bounds there (fix_eph.cpp:601). */
+enum eph_b200_model { EPH_B200_MODEL_NONE = 0, EPH_B200_MODEL_TTM = 1, EPH_B200_MODEL_PRB = 2, EPH_B200_MODEL_PRL = 4 };
 
 /* forward-comm payloads -- FixEPH::FixState, fix_eph.h:35-40 */
 enum eph_b200_state { EPH_B200_STATE_NONE = 0, EPH_B200_STATE_RHO = 1, EPH_B200_STATE_XI = 2, EPH_B200_STATE_WI = 3 };
@@ -91,6 +92,9 @@ const char *eph_b200_create_error(void);
 int eph_b200_set_tables(eph_b200_handle *h, int n_elements, int n_rho, double inv_dr_sq, const double *coeff_rho_r_sq,
                         int n_beta, double inv_drho, const double *coeff_alpha, const double *coeff_beta,
                         double r_cutoff_sq, double rho_cutoff);
+/* rho(r) splines in r (eph_beta.h:157-162; knots spaced dr, [n_elements][n_rho][4]) for eph_model 2 (PRB), the one
+ * place the reference evaluates them per step (fix_eph.cpp:530).  Call after set_tables. */
+int eph_b200_set_rho_r_table(eph_b200_handle *h, int n_elements, int n_rho, double inv_dr, const double *coeff_rho_r);
 
 /* Replaces EPH_FDM's constructors and state vectors (eph_fdm.h:28-119, :415-446).
  * box = {x0,x1,y0,y1,z0,z1}; fields are [nz][ny][nx] (index i + j*nx + k*nx*ny);

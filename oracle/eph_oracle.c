@@ -229,6 +229,10 @@ void orc_beta_free(orc_beta *b) {
 double orc_beta_rho_r_sq(const orc_beta *b, int e, double r_sq) {
   return orc_spline_eval(b->rho_r_sq + 4 * b->n_rho * e, b->inv_dr_sq, r_sq);
 }
+/* eph_beta.h:157-162: rho(r) of the legacy models (no cut-off test under NDEBUG) */
+double orc_beta_rho_r(const orc_beta *b, int e, double r) {
+  return orc_spline_eval(b->rho_r + 4 * b->n_rho * e, b->inv_dr, r);
+}
 /* eph_beta.h:186-198: zero above rho_cutoff */
 double orc_beta_alpha(const orc_beta *b, int e, double rho) {
   if (rho > b->rho_cutoff) return 0.;
@@ -719,6 +723,66 @@ void orc_force_prl(orc_fix *fx, const orc_atoms *a) { /* fix_eph.cpp:687-837 */
   }
 }
 
+/* Random force shared by the two legacy models: f_RNG_i = eta_factor alpha(rho_i) sqrt(T_e(x_i)) xi_i for every group
+ * atom (fix_eph.cpp:490-502 and :554-567 are the same loop). */
+static void random_uncorrelated(orc_fix *fx, const orc_atoms *a) {
+  const double *x = a->x;
+  int i;
+  for (i = 0; i != a->nlocal; ++i) {
+    double v_Te, var;
+    if (!(a->mask[i] & fx->groupbit)) continue;
+    v_Te = orc_fdm_get_T(fx->fdm, x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2]);
+    var = fx->eta_factor * orc_beta_alpha(fx->beta, fx->type_map[a->type[i] - 1], fx->rho_i[i]) * sqrt(v_Te);
+    fx->f_RNG[3 * (size_t)i + 0] = var * fx->xi_i[3 * (size_t)i + 0];
+    fx->f_RNG[3 * (size_t)i + 1] = var * fx->xi_i[3 * (size_t)i + 1];
+    fx->f_RNG[3 * (size_t)i + 2] = var * fx->xi_i[3 * (size_t)i + 2];
+  }
+}
+
+void orc_force_ttm(orc_fix *fx, const orc_atoms *a) { /* fix_eph.cpp:468-503 */
+  const double *v = a->v;
+  int i;
+  if (fx->flags & ORC_FRICTION)
+    for (i = 0; i != a->nlocal; ++i) {
+      double var;
+      if (!(a->mask[i] & fx->groupbit)) continue;
+      var = -orc_beta_beta(fx->beta, fx->type_map[a->type[i] - 1], fx->rho_i[i]);
+      fx->f_EPH[3 * (size_t)i + 0] = var * v[3 * (size_t)i + 0];
+      fx->f_EPH[3 * (size_t)i + 1] = var * v[3 * (size_t)i + 1];
+      fx->f_EPH[3 * (size_t)i + 2] = var * v[3 * (size_t)i + 2];
+    }
+  if (fx->flags & ORC_RANDOM) random_uncorrelated(fx, a);
+}
+
+void orc_force_prb(orc_fix *fx, const orc_atoms *a) { /* fix_eph.cpp:505-568 */
+  const orc_beta *b = fx->beta;
+  const double rc2 = b->r_cutoff_sq;
+  const double *x = a->x, *v = a->v;
+  int i;
+  if (fx->flags & ORC_FRICTION)
+    for (i = 0; i != a->nlocal; ++i) {
+      long long j;
+      double *f = fx->f_EPH + 3 * (size_t)i, var;
+      if (!(a->mask[i] & fx->groupbit)) continue;
+      if (!(fx->rho_i[i] > 0)) continue;
+      f[0] = v[3 * (size_t)i + 0]; f[1] = v[3 * (size_t)i + 1]; f[2] = v[3 * (size_t)i + 2];
+      for (j = a->offsets[i]; j != a->offsets[i + 1]; ++j) {
+        int jj = a->neigh[j] & NEIGHMASK;
+        int jtype = a->type[jj];
+        double r_sq = dist_sq(x + 3 * (size_t)jj, x + 3 * (size_t)i);
+        if (r_sq < rc2) { /* the element index is jtype - 1, NOT type_map[jtype - 1] (:530) */
+          var = orc_beta_rho_r(b, jtype - 1, sqrt(r_sq)) / fx->rho_i[i];
+          f[0] -= var * v[3 * (size_t)jj + 0];
+          f[1] -= var * v[3 * (size_t)jj + 1];
+          f[2] -= var * v[3 * (size_t)jj + 2];
+        }
+      }
+      var = orc_beta_beta(b, fx->type_map[a->type[i] - 1], fx->rho_i[i]);
+      f[0] *= var; f[1] *= var; f[2] *= var;
+    }
+  if (fx->flags & ORC_RANDOM) random_uncorrelated(fx, a);
+}
+
 void orc_post_force(orc_fix *fx, const orc_atoms *a, const double *xi) { /* fix_eph.cpp:841-907 */
   size_t nl = (size_t)a->nlocal, i;
   fix_resize(fx, nl + a->nghost);
@@ -737,7 +801,9 @@ void orc_post_force(orc_fix *fx, const orc_atoms *a, const double *xi) { /* fix_
   }
   orc_calculate_environment(fx, a); /* :868 */
   ghost_fill(a, fx->rho_i, 1);      /* :870-871 */
-  if (fx->model == 4) orc_force_prl(fx, a);
+  if (fx->model == 1) orc_force_ttm(fx, a);       /* switch(eph_model), :877-890; PRLCM (3) is not restated: the */
+  else if (fx->model == 2) orc_force_prb(fx, a);  /* reference indexes its table with jtype - i there (:601)      */
+  else if (fx->model == 4) orc_force_prl(fx, a);
   if ((fx->flags & ORC_FRICTION) && !(fx->flags & ORC_NOFRICTION)) /* :892-898 */
     for (i = 0; i < 3 * nl; ++i) a->f[i] += fx->f_EPH[i];
   if ((fx->flags & ORC_RANDOM) && !(fx->flags & ORC_NORANDOM)) /* :900-906 */

@@ -50,6 +50,7 @@ orc_beta *orc_beta_from_knots(int n_elements, size_t n_rho, double dr, size_t n_
                               const double *rho_knots, const double *beta_knots);
 void orc_beta_free(orc_beta *b);
 double orc_beta_rho_r_sq(const orc_beta *b, int e, double r_sq);
+double orc_beta_rho_r(const orc_beta *b, int e, double r);
 double orc_beta_alpha(const orc_beta *b, int e, double rho);
 double orc_beta_beta(const orc_beta *b, int e, double rho);
 /* plain accessors for ctypes */
@@ -125,6 +126,8 @@ typedef struct orc_atoms {
 
 void orc_calculate_environment(orc_fix *fx, const orc_atoms *a);
 void orc_force_prl(orc_fix *fx, const orc_atoms *a);
+void orc_force_ttm(orc_fix *fx, const orc_atoms *a);   /* model 1, fix_eph.cpp:468-503 */
+void orc_force_prb(orc_fix *fx, const orc_atoms *a);   /* model 2, fix_eph.cpp:505-568 */
 /* xi: [nlocal][3] Gaussians for every local atom (only group atoms are used) or NULL when RANDOM is off */
 void orc_post_force(orc_fix *fx, const orc_atoms *a, const double *xi);
 void orc_end_of_step(orc_fix *fx, const orc_atoms *a);

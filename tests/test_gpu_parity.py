@@ -18,8 +18,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
-def make_engine(beta_path, flags, grid, box, type_map=(0,), groupbit=1, dt=1e-4, grid_file=None, seed=12345):
-    eng = lib.Engine(list(type_map), flags=flags, groupbit=groupbit, seed=seed)
+def make_engine(beta_path, flags, grid, box, type_map=(0,), groupbit=1, dt=1e-4, grid_file=None, seed=12345, model=4):
+    eng = lib.Engine(list(type_map), flags=flags, model=model, groupbit=groupbit, seed=seed)
     eng.set_tables_from(host.BetaTables(path=beta_path))
     if grid_file is not None:
         host.GridFile(grid_file).apply(eng)
@@ -97,6 +97,39 @@ def test_engine_lane_widths(sys500, synth_beta_1, lanes, monkeypatch):
     env = dict(os.environ, EPH_B200_LANES=lanes, EPH_B200_TABLE="0" if lanes == "16" else "1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("model", [1, 2])
+@pytest.mark.parametrize("flags", [1, 2 | 4, 7])
+def test_engine_legacy_models_match_oracle(sys500, synth_beta_1, model, flags):
+    """TTM (fix_eph.cpp:468-503) and PRB (:505-568) on the device against the restatement (itself bit-exact against the
+    compiled reference, test_oracle_vs_reference.py::test_fix_legacy_models_bit_exact)."""
+    s = sys500
+    rng = np.random.default_rng(33)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(3)]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(3, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), flags, model=model, dt=1e-4)
+    refs = traj.run_oracle(fx, s, xis, [58.71])
+    eng = make_engine(synth_beta_1, flags, (3, 2, 2), box6(s), model=model)
+    attach(eng, s)
+    recs = traj.run_engine(eng, s, xis, [58.71], 1e-4)
+    compare(recs, refs, s["nlocal"])
+    for a, b in zip(recs, refs):
+        assert H.error_metrics(a["f_eph"], b["f_eph"]) < TOL and H.error_metrics(a["f_rng"], b["f_rng"]) < TOL
+    assert np.abs(refs[-1]["f"]).max() > 0
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_engine_legacy_models_multi_element_and_group(synth_beta_4, model):
+    s = H.make_system(4, ntypes=3, group_fraction=0.5, pos_seed=5)
+    rng = np.random.default_rng(34)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(2)]
+    mass = [55.85, 58.71, 52.0]
+    fx = O.Fix(s, O.Beta(path=synth_beta_4), O.FDM(2, 2, 2, box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, model=model, groupbit=2,
+               type_map=[3, 0, 2], dt=1e-4)
+    refs = traj.run_oracle(fx, s, xis, mass)
+    eng = make_engine(synth_beta_4, 7, (2, 2, 2), box6(s), type_map=[3, 0, 2], groupbit=2, model=model)
+    attach(eng, s)
+    compare(traj.run_engine(eng, s, xis, mass, 1e-4), refs, s["nlocal"])
 
 
 def test_engine_multi_element_and_group(synth_beta_4):

@@ -123,7 +123,7 @@ def test_bad_config_is_rejected_before_touching_the_device():
     L = lib.load()
     h = C.c_void_p()
     tm = (C.c_int * 1)(0)
-    cfg = lib.Config(0, 1, tm, 1, 7, 2, 1, 0, 1, None)   # model 2 (PRB) is not available on the device
+    cfg = lib.Config(0, 1, tm, 1, 7, 3, 1, 0, 1, None)   # model 3 (PRLCM) is not offered (reference bug, fix_eph.cpp:601)
     assert L.eph_b200_create(C.byref(cfg), C.byref(h)) == -4
     assert b"model" in L.eph_b200_create_error()
     cfg = lib.Config(0, 0, tm, 1, 7, 4, 1, 0, 1, None)
@@ -137,8 +137,10 @@ def test_fix_b200_without_gpu_reports_through_lammps_error(sys500, synth_beta_1)
         host.FixDriver(s, ["fx", "all", "eph", 1, 7, 4])
     with pytest.raises(host.FixError, match="elements not found"):
         host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Xx"]))
-    with pytest.raises(host.FixError, match="only model 4"):
-        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], model=2))
+    with pytest.raises(host.FixError, match="model 3 .PRLCM. is not offered"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], model=3))
+    with pytest.raises(host.FixError, match="unknown model"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], model=9))
     with pytest.raises(host.FixError, match="non-positive grid"):
         host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], grid=(0, 1, 1)))
     if not gpu_available():

@@ -163,6 +163,42 @@ def test_fix_hot_path_bit_exact(ref, sys500, synth_beta_1, flags):
         assert ra["Ee"] == rb["Ee"]
 
 
+@pytest.mark.parametrize("model", [1, 2])
+@pytest.mark.parametrize("flags", [1, 2 | 4, 7])
+def test_fix_legacy_models_bit_exact(ref, sys500, synth_beta_1, model, flags):
+    """TTM (1, fix_eph.cpp:468-503) and PRB (2, :505-568)."""
+    s = sys500
+    rng = np.random.default_rng(15)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(2)]
+    drv = ref.fix_driver(s, H.fix_args(flags, synth_beta_1, ["Ni"], model=model, grid=(3, 2, 2)), dt=1e-4)
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(3, 2, 2, box, 300.0, 3.5e-6, 1.0, 0.1248), flags, model=model, dt=1e-4)
+    a = traj.run_fix_driver(drv, s, xis)
+    b = traj.run_oracle(fx, s, xis, [58.71])
+    for ra, rb in zip(a, b):
+        for k in ("x", "v", "f", "array", "T", "w"):
+            assert np.array_equal(ra[k], rb[k]), k
+        assert ra["Ee"] == rb["Ee"]
+    assert np.abs(b[-1]["f"]).max() > 0
+
+
+@pytest.mark.parametrize("model", [1, 2])
+def test_fix_legacy_models_multi_element_bit_exact(ref, synth_beta_4, model):
+    s = H.make_system(4, ntypes=3, group_fraction=0.5, pos_seed=5)
+    rng = np.random.default_rng(16)
+    xis = [rng.normal(size=(s["nlocal"], 3)) for _ in range(2)]
+    drv = ref.fix_driver(s, H.fix_args(7, synth_beta_4, ["Fe", "Ni", "Cr"], model=model, grid=(2, 2, 2), group="bit1"),
+                         dt=1e-4, mass=[55.85, 58.71, 52.0])
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    fx = O.Fix(s, O.Beta(path=synth_beta_4), O.FDM(2, 2, 2, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, model=model, groupbit=2,
+               type_map=[3, 0, 2], dt=1e-4)
+    a = traj.run_fix_driver(drv, s, xis)
+    b = traj.run_oracle(fx, s, xis, [55.85, 58.71, 52.0])
+    for ra, rb in zip(a, b):
+        for k in ("f", "array", "T", "w"):
+            assert np.array_equal(ra[k], rb[k]), k
+
+
 def test_fix_multi_element_group_bit_exact(ref, synth_beta_4):
     s = H.make_system(4, ntypes=3, group_fraction=0.5, pos_seed=5)
     rng = np.random.default_rng(14)

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   double d0 = 0.0;
   if (a < ntotal) {
-    unsigned bits = static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask;
+    unsigned bits = (static_cast<unsigned>(type_map[type[a] - 1]) & kElemMask) |
+                    ((static_cast<unsigned>(type[a] - 1) & 0xFFu) << kTypeShift);
     if (mask[a] & groupbit) bits |= kBitGroup;
     const double px = x[3 * (size_t)a], py = x[3 * (size_t)a + 1], pz = x[3 * (size_t)a + 2];
     const double4 p4 = make_double4(px, py, pz, bits_to_double(bits));

@@ -20,6 +20,7 @@
 #include "eph_grid_tma.cuh"
 #include "eph_neigh.cuh"
 #include "eph_sweeps.cuh"
+#include "eph_legacy.cuh"
 
 using namespace ephb;
 
@@ -72,6 +73,9 @@ struct eph_b200_handle {
   int n_el = 0, n_rho = 0, n_beta = 0;
   double inv_dr_sq = 0, inv_drho = 0, rc2 = 0, rho_cut = 0;
   DevBuf<double2> rho_tab, alpha_tab, beta_tab;
+  DevBuf<double2> rho_r_tab;   // rho(r) splines in r: eph_model 2 only
+  double inv_dr = 0;
+  bool rho_r_set = false;
   DevBuf<int> d_type_map;
   bool tables_set = false;
 
@@ -346,8 +350,10 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
   if (!cfg || !out) { g_create_error = "eph_b200_create: null argument"; return EPH_B200_ERR_ARG; }
   *out = nullptr;
   if (cfg->ntypes < 1 || !cfg->type_map) { g_create_error = "eph_b200_create: ntypes < 1 or no type_map"; return EPH_B200_ERR_ARG; }
-  if (cfg->model != EPH_B200_MODEL_PRL && cfg->model != EPH_B200_MODEL_NONE) {
-    g_create_error = "eph_b200_create: only eph_model 4 (PRL 120, 185501) and 0 run on the device";
+  if (cfg->model != EPH_B200_MODEL_PRL && cfg->model != EPH_B200_MODEL_NONE && cfg->model != EPH_B200_MODEL_TTM &&
+      cfg->model != EPH_B200_MODEL_PRB) {
+    g_create_error = "eph_b200_create: eph_model must be 4 (PRL 120, 185501), 1 (TTM), 2 (PRB) or 0; model 3 reads out of "
+                     "bounds in the reference (fix_eph.cpp:601) and is not offered";
     return EPH_B200_ERR_MODEL;
   }
   int ndev = 0;
@@ -417,7 +423,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (!h) return EPH_B200_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
+  h->rho_tab.release(); h->rho_r_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->d_type_map.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->tag.release();
   h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release(); h->comm_idx.release(); h->comm_buf.release();
   h->pos4.release(); h->pv.release(); h->puz.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
@@ -504,6 +510,23 @@ int eph_b200_set_tables(eph_b200_handle *h, int n_elements, int n_rho, double in
   h->n_el = n_elements; h->n_rho = n_rho; h->n_beta = n_beta;
   h->inv_dr_sq = inv_dr_sq; h->inv_drho = inv_drho; h->rc2 = r_cutoff_sq; h->rho_cut = rho_cutoff;
   h->tables_set = true;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_rho_r_table(eph_b200_handle *h, int n_elements, int n_rho, double inv_dr, const double *coeff_rho_r) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->tables_set) return fail(h, EPH_B200_ERR_ARG, "set_rho_r_table: call set_tables first");
+  if (n_elements != h->n_el || n_rho != h->n_rho || !coeff_rho_r || !(inv_dr > 0.0))
+    return fail(h, EPH_B200_ERR_ARG, "set_rho_r_table: sizes differ from set_tables or null coefficients");
+  if (h->cfg.ntypes > n_elements)   // the reference indexes rho(r) with type - 1 (fix_eph.cpp:530)
+    return fail(h, EPH_B200_ERR_ARG, "set_rho_r_table: model 2 indexes rho(r) with the atom type: %d types, %d elements", h->cfg.ntypes, n_elements);
+  cudaSetDevice(h->cfg.device);
+  const size_t nr = (size_t)n_elements * n_rho * 2;
+  EPH_CUDA(h, h->rho_r_tab.reserve(nr));
+  EPH_CUDA(h, cudaMemcpyAsync(h->rho_r_tab.p, coeff_rho_r, nr * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->inv_dr = inv_dr;
+  h->rho_r_set = true;
   return EPH_B200_OK;
 }
 
@@ -955,7 +978,8 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
   a.grid = grid_geom(h);
   a.eta_factor = h->eta;
-  a.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
+  // the pair sums W (and with them w, u) belong to model PRL; the legacy models leave w_i zero like the reference
+  a.do_friction = ((h->cfg.flags & EPH_B200_FRICTION) && h->cfg.model == EPH_B200_MODEL_PRL) ? 1 : 0;
   a.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
   return a;
 }
@@ -1099,7 +1123,40 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   }
 
   SweepArgs a = sweep_args(h);
-  if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
+  if (h->cfg.model == EPH_B200_MODEL_TTM || h->cfg.model == EPH_B200_MODEL_PRB) {
+    const bool fric = (h->cfg.flags & EPH_B200_FRICTION) != 0, rnd = (h->cfg.flags & EPH_B200_RANDOM) != 0;
+    if (fric || rnd) {
+      if (h->cfg.model == EPH_B200_MODEL_PRB && fric) {
+        if (!h->rho_r_set) return fail(h, EPH_B200_ERR_ARG, "post_force: eph_model 2 needs eph_b200_set_rho_r_table");
+        a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
+        KernelTimer kt(h, "prb_sweep");
+        switch (h->lanes) {
+          case 1: prb_sweep_kernel<1><<<h->sm_count * 8, 256, 0, h->stream>>>(a, h->rho_r_tab.p, h->inv_dr); break;
+          case 2: prb_sweep_kernel<2><<<h->sm_count * 8, 256, 0, h->stream>>>(a, h->rho_r_tab.p, h->inv_dr); break;
+          case 8: prb_sweep_kernel<8><<<h->sm_count * 8, 256, 0, h->stream>>>(a, h->rho_r_tab.p, h->inv_dr); break;
+          case 16: prb_sweep_kernel<16><<<h->sm_count * 8, 256, 0, h->stream>>>(a, h->rho_r_tab.p, h->inv_dr); break;
+          default: prb_sweep_kernel<4><<<h->sm_count * 8, 256, 0, h->stream>>>(a, h->rho_r_tab.p, h->inv_dr); break;
+        }
+        EPH_LAUNCH_CHECK(h);
+      }
+      LegacyArgs q{};
+      q.nlocal = nl; q.model = h->cfg.model; q.pv = h->pv.p; q.rho = h->rho.p; q.S4 = h->W4.p; q.xi = h->xi.p;
+      q.alpha_tab = h->alpha_tab.p; q.beta_tab = h->beta_tab.p; q.n_beta = h->n_beta; q.inv_drho = h->inv_drho;
+      q.rho_cutoff = h->rho_cut; q.T_e = h->grid_set ? h->T[h->cur].p : nullptr; q.grid = grid_geom(h);
+      q.eta_factor = h->eta; q.do_friction = fric ? 1 : 0; q.do_random = rnd ? 1 : 0;
+      q.add_friction = add_fric ? 1 : 0; q.add_random = add_rand ? 1 : 0;
+      q.f = (add_fric || add_rand) ? df : nullptr; q.f_eph = h->f_eph.p; q.f_rng = h->f_rng.p;
+      {
+        KernelTimer kt(h, "legacy_force");
+        legacy_force_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(q);
+      }
+      EPH_LAUNCH_CHECK(h);
+      if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
+        EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+      }
+    }
+  } else if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
     a.f = (add_fric || add_rand) ? df : nullptr;
     // walk the list whose slots this step's density pass filled with pair weights
     a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);

@@ -13,6 +13,7 @@ constexpr int kNeighMask = 0x1FFFFFFF;  // LAMMPS NEIGHMASK (reference fix_eph.c
 constexpr unsigned kElemMask = 0xFFu;    // element index in the .beta file (type_map[type-1])
 constexpr unsigned kBitGroup = 1u << 8;  // mask & groupbit
 constexpr unsigned kBitValid = 1u << 9;  // rho_j > 0 (reference fix_eph.cpp:768, :811)
+constexpr int kTypeShift = 16;           // bits 16..23: LAMMPS type - 1 (the legacy PRB model indexes rho(r) with it)
 
 __device__ __forceinline__ double bits_to_double(unsigned lo) {
   return __hiloint2double(0, static_cast<int>(lo));

@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
             const double rinv = fast_rcp(r2);
             g = rho_j * rinv;
             rho += rho_j;
-            if (MULTI) gi = tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
+            // the second look-up is only needed when the two atoms are different elements
+            if (MULTI) gi = ((bj & kElemMask) * a.n_rho == off_i) ? g : tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
             if (a.do_friction) {  // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
               if (!spec) vj = ld256(rec + 1);
               const double d = g * (ex * (vi.x - vj.x) + ey * (vi.y - vj.y) + ez * (vi.z - vj.z));

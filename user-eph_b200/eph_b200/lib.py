@@ -32,6 +32,7 @@ SYMBOLS = {
     "eph_b200_create_error": (C.c_char_p, []),
     "eph_b200_set_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_double,
                                       C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_set_rho_r_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
     "eph_b200_set_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eph_b200_set_grid_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -128,6 +129,7 @@ class Engine:
             raise EphError("eph_b200_create failed (%d): %s" % (rc, self.lib.eph_b200_create_error().decode()))
         self.h = h
         self.flags = flags
+        self.model = model
         self.nlocal = self.nghost = 0
         self.ncell = 0
 
@@ -156,6 +158,10 @@ class Engine:
         """tables: eph_b200.host.BetaTables"""
         self.set_tables(tables.n_elements, tables.n_rho, tables.inv_dr_sq, tables.table(1), tables.n_beta,
                         tables.inv_drho, tables.table(2), tables.table(3), tables.r_cutoff_sq, tables.rho_cutoff)
+        if self.model == 2:   # PRB evaluates rho(r) per pair (fix_eph.cpp:530)
+            t = np.ascontiguousarray(tables.table(0), dtype=np.float64)
+            self._check(self.lib.eph_b200_set_rho_r_table(self.h, tables.n_elements, tables.n_rho, C.c_double(tables.inv_dr),
+                                                          t.ctypes.data))
 
     def set_grid(self, nx, ny, nz, box, T_e, rho_e, C_e, kappa_e, S_e=None, flag=None, t_dyn=None, steps=1):
         n = nx * ny * nz

@@ -67,8 +67,11 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
 
   eph_model = atoi(arg[5]);
   if (myID == 0) std::cout << "\nModel read: " << arg[5] << " -> " << eph_model << " (B200 device path)\n" << std::endl;
-  if (eph_model != Model::PRL && eph_model != Model::NONE)
-    error->all(FLERR, "fix eph/b200: only model 4 (PRL 120, 185501) runs on the device");
+  if (eph_model == Model::PRLCM)
+    error->all(FLERR, "fix eph/b200: model 3 (PRLCM) is not offered: the reference indexes its rho(r) table with jtype - i "
+                      "there (fix_eph.cpp:601)");
+  if (eph_model != Model::PRL && eph_model != Model::NONE && eph_model != Model::TTM && eph_model != Model::PRB)
+    error->all(FLERR, "fix eph/b200: unknown model (1 TTM, 2 PRB, 4 PRL run on the device)");
 
   const double v_rho = atof(arg[6]);
   const double v_Ce = atof(arg[7]);
@@ -169,6 +172,11 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
     check(eph_b200_set_tables(dev, beta.n_elements, (int)beta.n_rho, beta.inv_dr_sq(), t_rho.data(), (int)beta.n_beta,
                               beta.inv_drho(), t_alpha.data(), t_beta.data(), beta.r_cutoff_sq, beta.rho_cutoff),
           "set_tables");
+    if (eph_model == Model::PRB) {   // the one model that evaluates rho(r) per step (fix_eph.cpp:530)
+      std::vector<double> t_rho_r = eph_b200::BetaTables::flatten(beta.rho_r);
+      check(eph_b200_set_rho_r_table(dev, beta.n_elements, (int)beta.n_rho, beta.rho_r.at(0).inv_dx, t_rho_r.data()),
+            "set_rho_r_table");
+    }
   }
   check(eph_b200_set_grid(dev, (int)grid.nx, (int)grid.ny, (int)grid.nz, grid.box, (int)grid.steps, grid.T_e.data(),
                           grid.S_e.data(), grid.rho_e.data(), grid.C_e.data(), grid.kappa_e.data(), grid.flag.data(),
