@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
+    ap.add_argument("--weak", action="store_true", help="weak scaling (supplementary): --cells^3 unit cells and --grid^3 grid "
+                    "cells PER GPU (config C5 at 8 GPUs: 32 M atoms); the default is strong scaling of the named 4 M-atom box")
     ap.add_argument("--elements", type=int, default=1, help="config C4: this many elements (types uniform random), synthetic "
                     "multi-element .beta file written on the fly; the default 1 is the Ni workload of the headline metric")
     ap.add_argument("--cpu-cells", type=int, default=16, help="edge of each CPU-baseline replica (16 -> 16 384 atoms)")
@@ -196,6 +198,11 @@ def run_reference_arm(a):
 
 def workload_config(a, natoms):
     multi = getattr(a, "elements", 1) > 1
+    if getattr(a, "weak", False) and a.gpus > 1:
+        return {"workload": "C5-style weak scaling: Ni fcc, %d^3 cells (= %d atoms) and a %d^3 grid per GPU, %d atoms in all, "
+                            "flags 7, model 4, dt 1e-4 ps, full list at 7 A" % (a.cells, 4 * a.cells ** 3, a.grid, natoms),
+                "atoms": natoms, "fdm_grid_per_gpu": [a.grid] * 3, "beta_file": "tests/golden/Ni_trunc.beta",
+                "l2": "inputs far larger than the 126 MB L2; no flush needed", "parallelism": "spatial bricks, one rank per GPU"}
     name = ("C4: %d-element fcc alloy (types uniform random, synthetic .beta tables)" % a.elements) if multi else "C3: Ni fcc"
     return {"workload": "%s %d^3 cells = %d atoms, one 10 keV PKA, flags 7 (friction+random+FDM), model 4, "
                         "FDM grid %d^3, dt 1e-4 ps, full list at 7 A" % (name, a.cells, natoms, a.grid),
@@ -222,11 +229,15 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True    # NCCL's own stream: same reason as the side streams below
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     D = dist if world > 1 else None
 
     grid = P.brick_grid(world)
-    s = build_workload(a.cells, brick=(rank, grid) if world > 1 else None, elements=a.elements)
+    cells = tuple(a.cells * g for g in grid) if (a.weak and world > 1) else a.cells
+    gridn = tuple(a.grid * g for g in grid) if (a.weak and world > 1) else (a.grid,) * 3
+    s = build_workload(cells, brick=(rank, grid) if world > 1 else None, elements=a.elements)
     if world == 1:
         s["grid"] = (1, 1, 1)
     nl, ng = s["nlocal"], s["nghost"]
@@ -248,7 +259,7 @@ def run_b200(a):
         H.write_beta_file(beta_file, H.synthetic_knots(n_elements=a.elements))
     eng = lib.Engine(list(range(a.elements)), flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
     eng.set_tables_from(host.BetaTables(path=beta_file))
-    eng.set_grid(a.grid, a.grid, a.grid, box, 300.0, 1.0, 3.5e-6, 0.1248)
+    eng.set_grid(gridn[0], gridn[1], gridn[2], box, 300.0, 1.0, 3.5e-6, 0.1248)
     eng.set_dt(DT)
     eng.set_skin(2.0)
     t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
@@ -256,16 +267,17 @@ def run_b200(a):
     d_off, d_neigh = t(s["offsets"], torch.int64), t(s["neigh"], torch.int32)
     d_x, d_v = t(s["x"], torch.float64), t(s["v"], torch.float64)
     d_f = torch.zeros((nl, 3), dtype=torch.float64, device=dev)
-    d_src = torch.zeros(a.grid ** 3, dtype=torch.float64, device=dev)
+    d_src = torch.zeros(gridn[0] * gridn[1] * gridn[2], dtype=torch.float64, device=dev)
     eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
     eng.set_neighbors(d_off, d_neigh)
     eng.bind_grid_source(d_src)
     gstream = cstream = None
     if D:   # grid all-reduce + solve on a second stream: they overlap the next step's density pass
-        gstream = torch.cuda.Stream(device=dev)
+        # both side streams have high priority: their small kernels take the SM slots the sweeps' CTAs free up
+        gstream = torch.cuda.Stream(device=dev, priority=-1)
         eng.set_grid_stream(gstream.cuda_stream)
         if not a.no_overlap:   # ghost exchange on a third stream, behind the boundary tiles of the density pass
-            cstream = torch.cuda.Stream(device=dev)
+            cstream = torch.cuda.Stream(device=dev, priority=-1)
             eng.set_comm_stream(cstream.cuda_stream)
     exch = P.GhostExchange(plan, D, dev, comm_stream=cstream)
     if cstream is not None:
@@ -416,7 +428,7 @@ def run_b200(a):
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if a.weak else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid),
                               exchange_bytes_per_step_rank0=exch.bytes_per_step(), list_stats=eng.list_stats()),

@@ -10,9 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cells = sys.argv[1] if len(sys.argv) > 1 else "64"
 variants = [
     dict(),
-    dict(EPH_B200_SPEC_V="0"),
-    dict(EPH_B200_TABLE="0"),
-    dict(EPH_B200_TABLE="0", EPH_B200_SPEC_V="0"),
+    dict(EPH_B200_PERSISTENT="1"),
 ]
 if len(sys.argv) > 2:
     variants = variants[: int(sys.argv[2])]
