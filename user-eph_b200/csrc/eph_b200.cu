@@ -886,16 +886,15 @@ namespace {
 
 int env_int(const char *name, int dflt);
 
-// Grid of a sweep over `items` atoms with `per_cta` atoms per CTA pass.  Single stream: persistent, one resident wave
-// of CTAs striding over the atoms (3 % faster at 4 M atoms).  With a communication or grid stream registered: many
-// short-lived CTAs instead, because a resident wave fills every register file and would keep the side streams'
-// kernels (pack/unpack, NCCL, the grid solve) out until its tail -- the overlap would exist on paper only.
-// EPH_B200_PERSISTENT=1/0 overrides.
+// Grid of a sweep over `items` atoms with `per_cta` atoms per CTA pass: persistent, one resident wave of CTAs
+// striding over the atoms.  Measured alternative (EPH_B200_PERSISTENT=0: many short-lived CTAs, so that the kernels of
+// the communication and grid streams -- pack/unpack, NCCL, the grid solve -- can take SM slots while a sweep is
+// running instead of waiting for its tail): 3 % slower on one GPU and 2.5 % slower on 8 GPUs, where the NCCL kernels
+// then spin on SMs the sweep could use (profiles/r1_v10_bench_4M_8gpu*.json).  Kept as a switch, not the default.
 template <class K>
 int sweep_grid(eph_b200_handle *h, K kernel, int threads, size_t smem, long long items, int per_cta) {
   static const int forced = env_int("EPH_B200_PERSISTENT", -1);
-  const bool side_streams = h->comm_stream != nullptr || h->grid_stream != nullptr;
-  const bool persistent = forced >= 0 ? forced != 0 : (smem > 0 || !side_streams);
+  const bool persistent = forced >= 0 ? forced != 0 : true;
   const long long passes = std::max<long long>(1, (items + per_cta - 1) / per_cta);
   if (!persistent) return (int)std::min<long long>((passes + 3) / 4, 1 << 22);   // four passes per CTA: short-lived CTAs
   int per_sm = 1;
