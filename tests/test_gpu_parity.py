@@ -564,6 +564,81 @@ def test_size_independent_properties_at_scale(synth_beta_1):
     assert np.array_equal(arr[:, 0], rho[:nl]) and np.array_equal(arr[:, 2:5], fe) and np.array_equal(arr[:, 5:8], fr)
 
 
+def test_full_size_box_properties_and_sampled_parity(ni_trunc_beta):
+    """BASELINE's full size (config C3: n = 100, 4 000 000 atoms, 5.4e8 list entries, the bench's .beta file).  The C
+    oracle needs minutes per step there, so parity is checked two ways: size-independent properties over all atoms
+    (momentum conservation, energy bookkeeping against the grid) and an independent numpy evaluation of rho_i, f_EPH_i
+    and f_RNG_i for a sample of atoms -- straight from the definitions (fix_eph.cpp:450-461, :713-739, :758-785,
+    :802-833) with the oracle's spline tables, including the neighbours' rho_j and w_j."""
+    s = H.make_system(100)
+    nl, x, v = s["nlocal"], s["x"], s["v"]
+    off, ne, owner = s["offsets"], s["neigh"], s["ghost_owner"]
+    dt, Te = 1e-4, 300.0
+    eng = make_engine(ni_trunc_beta, 7 | 16 | 32, (64, 64, 64), box6(s), dt=dt)
+    attach(eng, s)
+    rng = np.random.default_rng(61)
+    xi = rng.normal(size=(nl, 3))
+    f = np.zeros((nl, 3))
+    eng.post_force(x, v, f, xi, 1)
+    T0 = eng.get_grid(0)
+    E = eng.end_of_step(x, v)
+    fe, fr, rho = eng.probe(3), eng.probe(4), eng.probe(0)
+    assert np.all(rho[:nl] > 0)
+    # properties over all 4 M atoms
+    assert np.max(np.abs(fe.sum(axis=0))) < 1e-9 * np.abs(fe).max() * np.sqrt(nl)
+    assert np.max(np.abs(fr.sum(axis=0))) < 1e-9 * np.abs(fr).max() * np.sqrt(nl)
+    E_ref = -np.sum((fe + fr) * v[:nl]) * dt
+    assert abs(E - E_ref) < 1e-10 * max(abs(E_ref), np.abs(fe * v[:nl]).sum() * dt)
+    dV = np.prod(s["box"] / 64)
+    assert abs(np.sum(eng.get_grid(0) - T0) * 3.5e-6 * 1.0 * dV - E) < 1e-8 * abs(E)
+
+    # sampled parity against the definitions
+    ob = O.Beta(path=ni_trunc_beta)
+    t_rho, t_alpha = ob.table(1)[0], ob.table(2)[0]
+    rc2 = ob.r_cutoff_sq
+
+    def spline(tab, inv_dx, xs):
+        k = (xs * inv_dx).astype(np.int64)
+        a, b, c, d = tab[k, 0], tab[k, 1], tab[k, 2], tab[k, 3]
+        return a + xs * (b + xs * (c + xs * d))
+
+    def home(j):                      # a ghost carries its owner's rho, w and xi
+        return j if j < nl else int(owner[j - nl])
+
+    cache = {}
+
+    def site(i):                      # rho_i, s_i = alpha/rho, W_i of a local atom, from its own list
+        if i not in cache:
+            jj = ne[off[i]:off[i + 1]] & 0x1FFFFFFF
+            e = x[jj] - x[i]
+            r2 = np.einsum("ij,ij->i", e, e)
+            m = r2 < rc2
+            e, r2, jj = e[m], r2[m], jj[m]
+            rj = spline(t_rho, ob.inv_dr_sq, r2)
+            r_i = rj.sum()
+            g = rj / r2
+            W = ((g * np.einsum("ij,ij->i", e, v[i] - v[jj]))[:, None] * e).sum(axis=0)
+            al = 0.0 if r_i > ob.rho_cutoff else float(spline(t_alpha, ob.inv_drho, np.array([r_i]))[0])
+            cache[i] = (r_i, al / r_i, W, e, g, jj)
+        return cache[i]
+
+    eta = np.sqrt(2.0 * H.KB / dt)
+    sample = rng.choice(nl, 16, replace=False)
+    for i in sample:
+        r_i, s_i, W_i, e, g, jj = site(int(i))
+        u_i, z_i = s_i * s_i * W_i, s_i * xi[i]
+        fe_i, fr_i = np.zeros(3), np.zeros(3)
+        for k, j in enumerate(jj):
+            r_j, s_j, W_j = site(home(int(j)))[:3]
+            u_j, z_j = s_j * s_j * W_j, s_j * xi[home(int(j))]
+            fe_i -= g[k] * (e[k] @ u_i - e[k] @ u_j) * e[k]
+            fr_i += g[k] * (e[k] @ z_i - e[k] @ z_j) * e[k]
+        fr_i *= eta * np.sqrt(Te)
+        assert abs(rho[i] - r_i) < TOL * r_i
+        assert np.max(np.abs(fe[i] - fe_i)) < TOL * np.abs(fe).max(), (i, fe[i], fe_i)
+        assert np.max(np.abs(fr[i] - fr_i)) < TOL * np.abs(fr).max(), (i, fr[i], fr_i)
+
+
 def test_fluctuation_dissipation_statistics(synth_beta_1):
     """<f_RNG f_RNG^T> over noise realisations equals 2 k_B T_e B / dt with f_EPH = -B v
     (the random force is built from the same W as the friction: PRL 120, 185501)."""
