@@ -37,7 +37,25 @@ struct GridTmaArgs {
   int has_walls;   // some cell has flag == 2: the wall substitution needs the neighbours' flags
 };
 
-__global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_constant__ CUtensorMap map_T,
+// The single-use fields of kBatch z-planes of one thread's (i, j) column: fetched together (more bytes in flight per
+// thread), and one batch ahead of the stencil so that their latency overlaps the TMA's and the previous batch's math.
+constexpr int kBatch = 2;
+struct PlaneBatch {
+  double dT[kBatch], S[kBatch], rho[kBatch], C[kBatch];
+  int fl[kBatch], td[kBatch];
+};
+
+__device__ __forceinline__ void load_batch(PlaneBatch &b, const GridArgs &g, int i, int j, int k0, long long sy, long long sz) {
+#pragma unroll
+  for (int q = 0; q < kBatch; ++q) {
+    const long long r = i + j * sy + (long long)min(k0 + q, g.nz - 1) * sz;
+    b.fl[q] = g.flag[r];
+    b.dT[q] = g.dT_e[r]; b.S[q] = g.S_e[r]; b.rho[q] = g.rho_e[r]; b.C[q] = g.C_e[r];
+    b.td[q] = g.E_e_T != nullptr ? g.t_dyn[r] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) fdm_substep_tma_kernel(const __grid_constant__ CUtensorMap map_T,
                                                               const __grid_constant__ CUtensorMap map_K, GridTmaArgs ta) {
   extern __shared__ __align__(128) unsigned char tma_smem[];
   double *sT = reinterpret_cast<double *>(tma_smem);                 // kBoxBytes each, 128-byte aligned
@@ -72,6 +90,11 @@ __global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_const
       sF[c] = ok ? g.flag[gx + gy * sy + gz * sz] : (short)1;
     }
   }
+  const int tx = tid & 31, ty = tid >> 5;   // 32 x 8 threads, each marching over the tile's TZ planes
+  const int i = ox + tx, j = oy + ty;
+  const bool inside = i < g.nx && j < g.ny;
+  PlaneBatch cur;
+  if (inside) load_batch(cur, g, i, j, oz, sy, sz);   // in flight together with the two TMA boxes
   {  // wait for both boxes
     unsigned done = 0;
     while (!done) {
@@ -97,23 +120,11 @@ __global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_const
   }
   __syncthreads();
 
-  const int tx = tid & 31, ty = tid >> 5;   // 32 x 8 threads, each marching over the tile's TZ planes
-  const int i = ox + tx, j = oy + ty;
-  if (i >= g.nx || j >= g.ny) return;
-  constexpr int kBatch = 4;   // single-use fields of kBatch planes are fetched together: more bytes in flight per thread
+  if (!inside) return;
 #pragma unroll
   for (int t0 = 0; t0 < kTZ; t0 += kBatch) {
-    double dTs[kBatch], Ss[kBatch], rhos[kBatch], Cs[kBatch];
-    short fl[kBatch];
-    unsigned short td[kBatch];
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int k = oz + t0 + b;
-      const long long r = i + j * sy + (long long)min(k, g.nz - 1) * sz;
-      fl[b] = g.flag[r];
-      dTs[b] = g.dT_e[r]; Ss[b] = g.S_e[r]; rhos[b] = g.rho_e[r]; Cs[b] = g.C_e[r];
-      td[b] = g.E_e_T != nullptr ? g.t_dyn[r] : (unsigned short)0;
-    }
+    PlaneBatch nxt;
+    if (t0 + kBatch < kTZ) load_batch(nxt, g, i, j, oz + t0 + kBatch, sy, sz);   // next batch ahead of this batch's math
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
       const int tz = t0 + b, k = oz + tz;
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_const
       const long long r = i + j * sy + k * sz;
       const int c = (tx + kHX) + (ty + 1) * kBX + (tz + 1) * kBX * kBY;
       double T = sT[c];
-      if (fl[b] == 1) {  // only DYNAMIC cells change; walls (2) and constant cells (0) keep T
+      if (cur.fl[b] == 1) {  // only DYNAMIC cells change; walls (2) and constant cells (0) keep T
         const double kr = sK[c];
         double ddT = 0.0;
 #pragma unroll
@@ -136,13 +147,13 @@ __global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_const
           ddT += (sK[q] - sK[p]) * (Tq - Tp) * inv * 0.25;
           ddT += kr * ((Tq + Tp - 2.0 * T) * inv);
         }
-        const double src = ddT + dTs[b] + Ss[b];
-        if (td[b] == 1) {
+        const double src = ddT + cur.dT[b] + cur.S[b];
+        if (cur.td[b] == 1) {
           double E = linear_eval(g.E_e_T, g.n_T, g.dT, T);
-          E += src / rhos[b] * g.inner_dt;
+          E += src / cur.rho[b] * g.inner_dt;
           T = linear_reverse(g.E_e_T, g.n_T, g.dT, E);
         } else {
-          T += src / (rhos[b] * Cs[b]) * g.inner_dt;
+          T += src / (cur.rho[b] * cur.C[b]) * g.inner_dt;
         }
       }
       if (T < 0.0) {
@@ -152,6 +163,7 @@ __global__ void __launch_bounds__(256) fdm_substep_tma_kernel(const __grid_const
       g.T_out[r] = T;
       if (g.clear_source) g.dT_e[r] = 0.0;
     }
+    if (t0 + kBatch < kTZ) cur = nxt;
   }
 }
 
