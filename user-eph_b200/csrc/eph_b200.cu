@@ -1309,6 +1309,7 @@ int grid_solve(eph_b200_handle *h, cudaStream_t st) {
         GridUniformArgs u;
         u.nx = h->nx; u.ny = h->ny; u.nz = h->nz; u.T_in = g.T_in; u.T_out = g.T_out; u.dT_e = g.dT_e;
         u.kappa = h->u_kappa; u.S = h->u_S; u.rho = h->u_rho; u.C = h->u_C;
+        u.inv_rho_C = 1.0 / (h->u_rho * h->u_C);
         u.inv_dx2 = g.inv_dx2; u.inv_dy2 = g.inv_dy2; u.inv_dz2 = g.inv_dz2; u.inner_dt = g.inner_dt;
         u.clear_source = g.clear_source; u.status = g.status;
         fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, st>>>(h->map_T[h->cur], h->map_S, u);

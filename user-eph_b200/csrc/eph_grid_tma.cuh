@@ -32,6 +32,23 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
                :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+// The CTA waits for a TMA transaction with ONE polling warp (256 threads spinning on try_wait cost the
+// constant-coefficient kernel a large share of its issue slots, ncu); the other warps sleep in __syncthreads and then
+// observe the completed phase themselves with a single non-blocking test_wait, which is their own acquire of the
+// data the TMA wrote.
+__device__ __forceinline__ void cta_wait_tma(unsigned long long *bar, unsigned parity, int tid) {
+  if (tid < 32) {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+  }
+  __syncthreads();
+  asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1; }"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 struct GridTmaArgs {
   GridArgs g;
   int has_walls;   // some cell has flag == 2: the wall substitution needs the neighbours' flags
@@ -95,13 +112,7 @@ __global__ void __launch_bounds__(256, 3) fdm_substep_tma_kernel(const __grid_co
   const bool inside = i < g.nx && j < g.ny;
   PlaneBatch cur;
   if (inside) load_batch(cur, g, i, j, oz, sy, sz);   // in flight together with the two TMA boxes
-  {  // wait for both boxes
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
-    }
-  }
+  cta_wait_tma(&bar, 0u, tid);   // both boxes have landed
   // periodic wrap: halo cells outside the grid were zero-filled by the TMA
   const bool edge = ox == 0 || oy == 0 || oz == 0 || ox + kTX >= g.nx || oy + kTY >= g.ny || oz + kTZ >= g.nz;
   if (edge) {
@@ -170,13 +181,16 @@ __global__ void __launch_bounds__(256, 3) fdm_substep_tma_kernel(const __grid_co
 // Constant-coefficient fast path: every cell DYNAMIC with the same rho_e, C_e, kappa_e and S_e (what `fix eph ... NX NY NZ
 // NULL ...` creates, reference eph_fdm.h:28-46, :143-153).  kappa differences vanish identically, the parameters are
 // scalars, and a cell-update moves 24 bytes (T_e in/out, dT_e in) instead of 60.  Both the T_e box (with halo) and the
-// dT_e tile arrive by TMA; arithmetic order is that of the general kernel, so results are bit-identical to it.
+// dT_e tile arrive by TMA; arithmetic order is that of the general kernel.  The one division per cell has a constant
+// denominator: it is done as q = x * (1/d), q += fma(-d, q, x) * (1/d) (correctly rounded but for rare ties; the
+// generic fp64 division subroutine was 35 % of this issue-bound kernel's instructions, ncu).
 struct GridUniformArgs {
   int nx, ny, nz;
   const double *__restrict__ T_in;   // for the periodic halo patch
   double *__restrict__ T_out;
   double *__restrict__ dT_e;
   double kappa, S, rho, C;
+  double inv_rho_C;                  // 1 / (rho * C), correctly rounded on the host
   double inv_dx2, inv_dy2, inv_dz2, inner_dt;
   int clear_source;
   unsigned *__restrict__ status;
@@ -204,13 +218,7 @@ __global__ void __launch_bounds__(256) fdm_uniform_tma_kernel(const __grid_const
     tma_load_3d(sT, &map_T, ox - kHX, oy - 1, oz - 1, &bar);
     tma_load_3d(sS, &map_S, ox, oy, oz, &bar);
   }
-  {
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                   : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
-    }
-  }
+  cta_wait_tma(&bar, 0u, tid);
   const long long sy = g.nx, sz = (long long)g.nx * g.ny;
   const bool edge = ox == 0 || oy == 0 || oz == 0 || ox + kTX >= g.nx || oy + kTY >= g.ny || oz + kTZ >= g.nz;
   if (edge) {
@@ -229,26 +237,31 @@ __global__ void __launch_bounds__(256) fdm_uniform_tma_kernel(const __grid_const
   const int tx = tid & 31, ty = tid >> 5;
   const int i = ox + tx, j = oy + ty;
   if (i >= g.nx || j >= g.ny) return;
-  const double prescaler = g.rho * g.C;
+  const double prescaler = g.rho * g.C, inv = g.inv_rho_C;
   int c = (tx + kHX) + (ty + 1) * kBX + kBX * kBY;
   double Tm = sT[c - kBX * kBY], T = sT[c];
+  const long long r0 = i + j * sy + (long long)oz * sz;
+  double *__restrict__ out = g.T_out + r0;
+  double *__restrict__ src = g.dT_e + r0;
+  const double *__restrict__ sSp = sS + tx + ty * kTX;
 #pragma unroll
   for (int tz = 0; tz < kTZ; ++tz, c += kBX * kBY) {
-    const int k = oz + tz;
     const double Tn = sT[c + kBX * kBY];
-    if (k < g.nz) {
-      const long long r = i + j * sy + k * sz;
+    if (oz + tz < g.nz) {
       double ddT = 0.0;
       ddT += g.kappa * ((sT[c + 1] + sT[c - 1] - 2.0 * T) * g.inv_dx2);
       ddT += g.kappa * ((sT[c + kBX] + sT[c - kBX] - 2.0 * T) * g.inv_dy2);
       ddT += g.kappa * ((Tn + Tm - 2.0 * T) * g.inv_dz2);
-      double Tnew = T + (ddT + sS[tx + ty * kTX + tz * kTX * kTY] + g.S) / prescaler * g.inner_dt;
+      const double x = ddT + sSp[tz * kTX * kTY] + g.S;
+      double q = x * inv;                       // x / prescaler
+      q = fma(fma(-prescaler, q, x), inv, q);
+      double Tnew = T + q * g.inner_dt;
       if (Tnew < 0.0) {
         Tnew = 0.0;
         atomicOr(g.status, 2u);
       }
-      g.T_out[r] = Tnew;
-      if (g.clear_source) g.dT_e[r] = 0.0;
+      out[tz * sz] = Tnew;
+      if (g.clear_source) src[tz * sz] = 0.0;
     }
     Tm = T;
     T = Tn;
