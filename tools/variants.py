@@ -10,12 +10,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cells = sys.argv[1] if len(sys.argv) > 1 else "64"
 variants = [
     dict(),
-    dict(EPH_B200_LANES="8"),
-    dict(EPH_B200_LANES="2"),
-    dict(EPH_B200_TABLE="1"),
-    dict(EPH_B200_SPEC_V="0"),
-    dict(EPH_B200_INNER_SKIN="0.3"),
-    dict(EPH_B200_PERSISTENT="0"),
 ]
 if len(sys.argv) > 2:
     variants = variants[: int(sys.argv[2])]

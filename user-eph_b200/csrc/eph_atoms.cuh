@@ -69,7 +69,12 @@ struct PrepArgs {
   double *__restrict__ rho;    // [ntotal]; ghost entries are filled here
   const double4 *__restrict__ W4;  // [nlocal] (or [ntotal] after an exchange) pair sums of the density pass
   const double4 *__restrict__ pos4;  // [ntotal] x, y, z, bits of pack_atoms
-  double4 *__restrict__ puz;   // [ntotal][3] force-pass record {x,y,z,bits+valid | u = s*w, z = s*xi} (eph_sweeps.cuh)
+  double4 *__restrict__ puz;   // [ntotal][3] force-pass record {x,y,z,bits+valid | u = s*w, z = s*xi | var, cell} (eph_sweeps.cuh)
+  const double *__restrict__ T_e;   // grid temperatures (nullptr: no grid) ...
+  GridGeom grid;                    // ... and geometry: the grid cell of every local atom (EPH_FDM::get_index,
+  double eta_factor;                // eph_fdm.h:494-509: six fp64 divisions) is worked out ONCE per step here, with
+                                    // all lanes busy, and stored with eta_factor * sqrt(T_e(cell)) (fix_eph.cpp:829-833)
+                                    // in the atom's record for the force pass and the deposition
   double *__restrict__ w;      // [nlocal][3] w_i (probe / forward-comm payload)
   double *__restrict__ xi;     // [ntotal][3] xi_i (probe / XI forward-comm slots)
   unsigned *__restrict__ status;
@@ -128,10 +133,16 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
       xi_stream(p.seed, p.step, p.tag[a], xi);
     }
   }
+  double var = 0.0;
+  int cell = 0;
+  if (a < p.nlocal && p.T_e != nullptr) {
+    cell = grid_index(p.grid, pa.x, pa.y, pa.z);
+    if (p.do_random) var = p.eta_factor * sqrt(p.T_e[cell]);
+  }
   double4 *rec = p.puz + 3 * (size_t)a;
   rec[0] = pa;
   rec[1] = make_double4(s * wx, s * wy, s * wz, s * xi[0]);
-  rec[2] = make_double4(s * xi[1], s * xi[2], 0.0, 0.0);
+  rec[2] = make_double4(s * xi[1], s * xi[2], var, bits_to_double(static_cast<unsigned>(cell)));
   if (a < p.nlocal) {
     p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
   }
@@ -163,6 +174,7 @@ struct DepositArgs {
   const double *__restrict__ x;      // LAMMPS layout, or nullptr: positions unchanged since post_force (use pos4)
   const double *__restrict__ v;
   const double4 *__restrict__ pos4;  // bits (group) from the last post_force
+  const double4 *__restrict__ puz;   // force-pass records: puz[3i+2].w carries the atom's grid cell of the last post_force
   const double *__restrict__ f_eph;
   const double *__restrict__ f_rng;
   double dt, dVdt;
@@ -196,10 +208,7 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
       dE = dEf + dEr;
       contrib = dEf / d.dVdt + dEr / d.dVdt;  // two insert_energy calls in the reference
       if (d.x != nullptr) cell = grid_index(d.grid, d.x[o], d.x[o + 1], d.x[o + 2]);
-      else {
-        const double4 p4 = d.pos4[i];
-        cell = grid_index(d.grid, p4.x, p4.y, p4.z);
-      }
+      else cell = static_cast<int>(double_to_bits(d.puz[3 * (size_t)i + 2].w));   // positions unchanged since post_force
     }
   }
   // warp-aggregated scatter-add: atoms are spatially sorted, so a warp usually

@@ -1119,6 +1119,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   p.xi_inject = h->pf_xi; p.alpha_tab = h->alpha_tab.p; p.n_beta = h->n_beta; p.inv_drho = h->inv_drho; p.rho_cutoff = h->rho_cut;
   p.seed = h->cfg.seed; p.step = (unsigned long long)h->pf_step; p.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;
   p.rho = h->rho.p; p.W4 = h->W4.p; p.pos4 = h->pos4.p; p.puz = h->puz.p;
+  p.T_e = h->grid_set ? h->T[h->cur].p : nullptr; p.grid = grid_geom(h); p.eta_factor = h->eta;
   p.w = h->w.p; p.xi = h->xi.p; p.status = h->d_status.p;
   p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
   p.list_state = h->lstate.p;
@@ -1349,7 +1350,7 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {
     DepositArgs d{};
-    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p;
+    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.puz = h->puz.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p;
     d.dt = h->dt; d.dVdt = h->dV * h->dt;
     d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
     d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;

@@ -127,9 +127,12 @@ struct GridGeom {
 };
 
 __device__ __forceinline__ int wrap_cell(double x, double x0, double dx, int n) {
-  int l = static_cast<int>(floor((x - x0) / dx));
-  int p = static_cast<int>(floor(static_cast<double>(l) / n));
-  return l - p * n;
+  const int l = static_cast<int>(floor((x - x0) / dx));
+  if (l >= 0 && l < n) return l;   // inside the grid: the second floor is zero
+  // l - floor(double(l) / n) * n of the reference is the non-negative remainder; in integers, without a second
+  // fp64 division
+  const int m = l % n;
+  return m < 0 ? m + n : m;
 }
 
 __device__ __forceinline__ int grid_index(const GridGeom &g, double x, double y, double z) {

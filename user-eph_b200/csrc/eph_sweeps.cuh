@@ -59,7 +59,8 @@ namespace ephb {
 
 // Per-atom gather records (32-byte sectors, consecutive in memory).
 //   density pass: pv[2a] = {x, y, z, bits}, pv[2a+1] = {vx, vy, vz, 0}
-//   force pass:   puz[3a] = {x, y, z, bits}, puz[3a+1] = {ux, uy, uz, zx}, puz[3a+2] = {zy, zz, 0, 0}
+//   force pass:   puz[3a] = {x, y, z, bits}, puz[3a+1] = {ux, uy, uz, zx}, puz[3a+2] = {zy, zz, var, cell}
+//                 (var = eta_factor sqrt(T_e(cell of a)) and the cell index, local atoms only, from prep_coupling)
 constexpr int kPvStride = 2;
 constexpr int kPuzStride = 3;
 
@@ -331,10 +332,8 @@ __global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_sweep
     }
     if (sub == 0) {
       double var = 0.0;
-      if (active && a.do_random) {  // fix_eph.cpp:829-833: nearest-cell T_e, eta_factor = sqrt(2 k_B / dt)
-        const double Te = a.T_e[grid_index(a.grid, pi.x, pi.y, pi.z)];
-        var = a.eta_factor * sqrt(Te);
-      }
+      // fix_eph.cpp:829-833: eta_factor sqrt(T_e(nearest cell)), worked out once per atom by prep_coupling
+      if (active && a.do_random) var = __ldg(reinterpret_cast<const double *>(ri + 2) + 2);
       rx *= var; ry *= var; rz *= var;
       const size_t o = 3 * (size_t)i;
       if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
