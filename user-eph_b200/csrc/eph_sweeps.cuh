@@ -174,16 +174,21 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
     // a work list names whole tiles (the warp's 32/LANES atoms), so the lane <-> tile-slot mapping is unchanged
     const int i = a.work ? a.work[w / (32 / LANES)] * (32 / LANES) + (w & (32 / LANES - 1)) : w;
     const bool real = i < a.nlocal;   // the last tile may be partial
-    double4 pi = make_double4(0, 0, 0, 0);
-    if (real) pi = ld256(a.pv + kPvStride * (size_t)i);
+    // the whole header of the atom is requested at once, not behind the record that says whether it is in the group
+    double4 pi = make_double4(0, 0, 0, 0), vi = pi;
+    RowWalk rw{0, 0};
+    int nn = 0;
+    if (real) {
+      pi = ld256(a.pv + kPvStride * (size_t)i);
+      if (a.do_friction) vi = ld256(a.pv + kPvStride * (size_t)i + 1);
+      rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
+      nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
+    }
     const unsigned bi = double_to_bits(pi.w);
     double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
     int icnt = 0;
     if (real && (bi & kBitGroup)) {  // atoms outside the fix group keep rho = 0 (fix_eph.cpp:442-445) and w = 0 (:704)
-      const double4 vi = a.do_friction ? ld256(a.pv + kPvStride * (size_t)i + 1) : make_double4(0, 0, 0, 0);
       const int off_i = (bi & kElemMask) * a.n_rho;
-      const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
       const long long tile0 = BUILD ? a.tile_off[i / (32 / LANES)] + gshift : 0;   // this atom's lanes of tile iteration 0
       const int *__restrict__ lp = list + rw.first;
       double *__restrict__ gp = a.gpair + rw.first;
@@ -274,18 +279,20 @@ __global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_sweep
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
   for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
+    // the whole header of the atom is requested at once (the pass is bound by the latency of dependent loads: the
+    // row description must not wait for the record that says whether the atom takes part)
     const double4 *ri = a.puz + kPuzStride * (size_t)i;
     const double4 pi = ld256(ri);
+    const double4 qi = ld256(ri + 1);
+    const double2 si = ld128(ri + 2);
+    const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
+    const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
     const unsigned bi = double_to_bits(pi.w);
     double fx = 0, fy = 0, fz = 0, rx = 0, ry = 0, rz = 0;
     // group atoms with rho_i > 0 only (fix_eph.cpp:749-754, :793-798)
     const bool active = (bi & kBitGroup) && (bi & kBitValid);
     if (active) {
-      const double4 qi = ld256(ri + 1);
-      const double2 si = ld128(ri + 2);
       const double uix = qi.x, uiy = qi.y, uiz = qi.z, zix = qi.w, ziy = si.x, ziz = si.y;
-      const RowWalk rw = inner ? walk_tile<LANES>(a, i, lane) : walk_csr<LANES>(a, i, sub);
-      const int nn = inner ? a.icount[i] : static_cast<int>(a.offsets[i + 1] - a.offsets[i]);
       const int *__restrict__ lp = list + rw.first;
       const double *__restrict__ gp = a.gpair + rw.first;
       const double *__restrict__ gip = MULTI ? a.gpair_i + rw.first : nullptr;
