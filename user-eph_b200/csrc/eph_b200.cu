@@ -929,7 +929,7 @@ int launch_force(eph_b200_handle *h, const SweepArgs &a) {
   const int threads = EPH_THREADS_FORCE;
   KernelTimer kt(h, "force_sweep");
   auto k = force_sweep_kernel<LANES, MULTI>;
-  k<<<sweep_grid(h, k, threads, 0, a.nlocal, threads / LANES), threads, 0, h->stream>>>(a);
+  k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a);
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
@@ -981,6 +981,7 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   a.offsets = h->off_ptr; a.neigh = h->neigh_ptr;
   a.ineigh = h->ineigh.p; a.tile_off = h->tile_off.p; a.icount = h->icount.p; a.inner_invalid = &h->lstate.p->inner_invalid;
   a.use_inner = 0;
+  a.i_begin = 0; a.i_end = h->nlocal;
   static const int spec_v = env_int("EPH_B200_SPEC_V", 1);
   a.spec_v = spec_v;
   a.pv = h->pv.p; a.puz = h->puz.p; a.W4 = h->W4.p; a.rho = h->rho.p;
@@ -1174,10 +1175,26 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
     a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
     a.add_friction = add_fric ? 1 : 0;
     a.add_random = add_rand ? 1 : 0;
-    if ((rc = launch_sweep(h, a, 1))) return rc;
     if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
-      EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      // host memspace: the force pass runs in a few launches over consecutive atom ranges and every finished range of
+      // f goes back to the host on the copy stream while the next range is still being swept
+      static const int chunks_env = env_int("EPH_B200_F_CHUNKS", 4);
+      const int chunks = std::max(1, std::min(chunks_env, nl / 32768 + 1));
+      const int per = ((nl + chunks - 1) / chunks + 255) / 256 * 256;   // multiple of the tile and CTA pass sizes
+      for (int i0 = 0; i0 < nl; i0 += per) {
+        const int i1 = std::min(nl, i0 + per);
+        a.i_begin = i0; a.i_end = i1;
+        if ((rc = launch_sweep(h, a, 1))) return rc;
+        EPH_CUDA(h, cudaEventRecord(h->f_event, h->stream));
+        EPH_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->f_event, 0));
+        EPH_CUDA(h, cudaMemcpyAsync(f + 3 * (size_t)i0, h->f.p + 3 * (size_t)i0, 3 * (size_t)(i1 - i0) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->copy_stream));
+      }
+      EPH_CUDA(h, cudaStreamSynchronize(h->copy_stream));
       EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    } else {
+      a.i_begin = 0; a.i_end = nl;
+      if ((rc = launch_sweep(h, a, 1))) return rc;
     }
   }
   h->forces_valid = true;

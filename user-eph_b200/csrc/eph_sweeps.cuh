@@ -85,6 +85,7 @@ struct SweepArgs {
   int use_inner;                          // density pass: an inner list exists
   int spec_v;                             // density pass: fetch v_j together with the position when walking the inner list
   int walk_mode;                          // force pass: 0 LAMMPS' list, 1 inner list unless the device flag is set, 2 inner list
+  int i_begin, i_end;                     // force pass: atoms [i_begin, i_end) of this launch (i_begin a multiple of 32)
   double *__restrict__ gpair;             // rho^{t_j}(r^2)/r^2 per walked slot (0 beyond r_c), indexed like the walked list
   double *__restrict__ gpair_i;           // rho^{t_i}(r^2)/r^2 (only when there is more than one element)
   const double4 *__restrict__ pv;         // [ntotal][2] density-pass records
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_sweep
   const bool inner = a.walk_mode == 2 || (a.walk_mode == 1 && *a.inner_invalid == 0u);
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
-  for (int i = blockIdx.x * groups_per_block + group_in_block; i < a.nlocal; i += gridDim.x * groups_per_block) {
+  for (int i = a.i_begin + blockIdx.x * groups_per_block + group_in_block; i < a.i_end; i += gridDim.x * groups_per_block) {
     // the whole header of the atom is requested at once (the pass is bound by the latency of dependent loads: the
     // row description must not wait for the record that says whether the atom takes part)
     const double4 *ri = a.puz + kPuzStride * (size_t)i;
