@@ -987,9 +987,6 @@ SweepArgs sweep_args(eph_b200_handle *h) {
   a.pv = h->pv.p; a.puz = h->puz.p; a.W4 = h->W4.p; a.rho = h->rho.p;
   a.gpair = h->gpair.p; a.gpair_i = h->gpair_i.p;
   a.f = nullptr; a.f_eph = h->f_eph.p; a.f_rng = h->f_rng.p;
-  a.T_e = h->grid_set ? h->T[h->cur].p : nullptr;
-  a.grid = grid_geom(h);
-  a.eta_factor = h->eta;
   // the pair sums W (and with them w, u) belong to model PRL; the legacy models leave w_i zero like the reference
   a.do_friction = ((h->cfg.flags & EPH_B200_FRICTION) && h->cfg.model == EPH_B200_MODEL_PRL) ? 1 : 0;
   a.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;

@@ -95,9 +95,6 @@ struct SweepArgs {
   double *__restrict__ f;                 // [nlocal][3] LAMMPS force array (read-modify-write) or nullptr
   double *__restrict__ f_eph;             // [nlocal][3]
   double *__restrict__ f_rng;             // [nlocal][3]
-  const double *__restrict__ T_e;         // grid temperatures
-  GridGeom grid;
-  double eta_factor;
   int do_friction, do_random, add_friction, add_random;
 };
 
