@@ -15,13 +15,13 @@ struct ListState {
 };
 
 // x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits} and the density-pass record pv {x,y,z,bits | vx,vy,vz,0}
-// (eph_sweeps.cuh); with track != 0 also the displacement
-// checks that guard the inner list: against xref (positions when the inner list was built) and against xref0
-// (positions when LAMMPS built its list).
+// (eph_sweeps.cuh); with track != 0 also the displacement check that guards the inner list (against xref, the
+// positions when the inner list was built) and, with track0 != 0 -- only in a step that rebuilds the inner list from
+// a LAMMPS list that is not fresh --, the largest displacement since LAMMPS built its list (against xref0).
 __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const double *__restrict__ x, const double *__restrict__ v,
                                   const int *__restrict__ type, const int *__restrict__ mask,
                                   const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
-                                  double4 *__restrict__ pv, int track, const double4 *__restrict__ xref,
+                                  double4 *__restrict__ pv, int track, int track0, const double4 *__restrict__ xref,
                                   const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st) {
   __shared__ double s_max[8];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,14 +36,17 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
     pv[2 * (size_t)a] = p4;
     pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
     if (track) {
-      const double4 r = xref[a], r0 = xref0[a];
+      const double4 r = xref[a];
       const double dx = px - r.x, dy = py - r.y, dz = pz - r.z;
       if (dx * dx + dy * dy + dz * dz > half_skin_sq) st->inner_invalid = 1u;
+    }
+    if (track0) {
+      const double4 r0 = xref0[a];
       const double ex = px - r0.x, ey = py - r0.y, ez = pz - r0.z;
       d0 = ex * ex + ey * ey + ez * ez;
     }
   }
-  if (track) {  // block-wide max of the displacement since LAMMPS' build, one atomic per block
+  if (track0) {  // block-wide max of the displacement since LAMMPS' build, one atomic per block
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d0 = fmax(d0, __shfl_xor_sync(0xFFFFFFFFu, d0, o));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = d0;
@@ -174,7 +177,6 @@ struct DepositArgs {
   const double *__restrict__ x;      // LAMMPS layout, or nullptr: positions unchanged since post_force (use pos4)
   const double *__restrict__ v;
   const double4 *__restrict__ pos4;  // bits (group) from the last post_force
-  const double4 *__restrict__ puz;   // force-pass records: puz[3i+2].w carries the atom's grid cell of the last post_force
   const double *__restrict__ f_eph;
   const double *__restrict__ f_rng;
   double dt, dVdt;
@@ -208,7 +210,10 @@ __global__ void __launch_bounds__(256) deposit_kernel(DepositArgs d) {
       dE = dEf + dEr;
       contrib = dEf / d.dVdt + dEr / d.dVdt;  // two insert_energy calls in the reference
       if (d.x != nullptr) cell = grid_index(d.grid, d.x[o], d.x[o + 1], d.x[o + 2]);
-      else cell = static_cast<int>(double_to_bits(d.puz[3 * (size_t)i + 2].w));   // positions unchanged since post_force
+      else {   // positions unchanged since post_force (recomputing from the packed position is cheaper than reading the
+        const double4 p4 = d.pos4[i];   // cell cached in the 96-byte-stride force record: measured)
+        cell = grid_index(d.grid, p4.x, p4.y, p4.z);
+      }
     }
   }
   // warp-aggregated scatter-add: atoms are spatially sorted, so a warp usually

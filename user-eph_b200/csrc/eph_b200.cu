@@ -1031,12 +1031,17 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
     if (h->fresh_neighbors) build = true;
   }
   const bool track = h->inner_enabled && h->have_inner;
+  // the displacement since LAMMPS built its list only matters when the inner list is rebuilt from that (aged) list:
+  // the new inner list is complete iff r_c + inner_skin + 2 D(now) <= r_c + skin (prep_coupling decides on the device)
+  const bool track0 = track && build && !h->fresh_neighbors;
+  if (track0)
+    EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->disp0_sq_bits, 0, sizeof(unsigned long long), h->stream));
   {
     KernelTimer kt(h, "pack_atoms");
     const double half = 0.5 * h->inner_skin;
     pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
                                                                    h->cfg.groupbit, h->pos4.p, h->pv.p, track ? 1 : 0,
-                                                                   h->xref.p, h->xref0.p, half * half, h->lstate.p);
+                                                                   track0 ? 1 : 0, h->xref.p, h->xref0.p, half * half, h->lstate.p);
   }
   EPH_LAUNCH_CHECK(h);
 
@@ -1364,7 +1369,7 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {
     DepositArgs d{};
-    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.puz = h->puz.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p;
+    d.nlocal = nl; d.x = dx; d.v = dv; d.pos4 = h->pos4.p; d.f_eph = h->f_eph.p; d.f_rng = h->f_rng.p;
     d.dt = h->dt; d.dVdt = h->dV * h->dt;
     d.do_friction = (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0;
     d.do_random = (h->cfg.flags & EPH_B200_RANDOM) ? 1 : 0;

@@ -151,7 +151,7 @@ def distributed_step(engine, exchange, dist, x, v, f, step, dT_e, want_energy=Fa
     engine.post_force_begin(x, v, None, step)
     exchange(engine)
     engine.post_force_end(f)
-    engine.end_of_step_begin(x, v)
+    engine.end_of_step_begin(None, v)   # positions are those of post_force (Verlet does not move atoms in between)
     if dist is not None and dist.get_world_size() > 1:
         if grid_stream is not None:
             import torch
