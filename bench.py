@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
+    ap.add_argument("--side-stream-priority", type=int, default=0, help="CUDA priority of the grid/communication streams "
+                    "and of NCCL's stream (0 default; -1 high was measured 12 %% slower at 2 GPUs: the all-reduce kernel "
+                    "then takes SM slots from the density pass while it waits for its peer)")
     ap.add_argument("--weak", action="store_true", help="weak scaling (supplementary): --cells^3 unit cells and --grid^3 grid "
                     "cells PER GPU (config C5 at 8 GPUs: 32 M atoms); the default is strong scaling of the named 4 M-atom box")
     ap.add_argument("--elements", type=int, default=1, help="config C4: this many elements (types uniform random), synthetic "
@@ -230,7 +233,7 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True    # NCCL's own stream: same reason as the side streams below
+        opts.is_high_priority_stream = a.side_stream_priority < 0    # NCCL's own stream: like the side streams below
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     D = dist if world > 1 else None
 
@@ -273,11 +276,11 @@ def run_b200(a):
     eng.bind_grid_source(d_src)
     gstream = cstream = None
     if D:   # grid all-reduce + solve on a second stream: they overlap the next step's density pass
-        # both side streams have high priority: their small kernels take the SM slots the sweeps' CTAs free up
-        gstream = torch.cuda.Stream(device=dev, priority=-1)
+        # side streams at default priority (see --side-stream-priority)
+        gstream = torch.cuda.Stream(device=dev, priority=a.side_stream_priority)
         eng.set_grid_stream(gstream.cuda_stream)
         if not a.no_overlap:   # ghost exchange on a third stream, behind the boundary tiles of the density pass
-            cstream = torch.cuda.Stream(device=dev, priority=-1)
+            cstream = torch.cuda.Stream(device=dev, priority=a.side_stream_priority)
             eng.set_comm_stream(cstream.cuda_stream)
     exch = P.GhostExchange(plan, D, dev, comm_stream=cstream)
     if cstream is not None:
