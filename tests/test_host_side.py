@@ -164,3 +164,17 @@ def test_harness_neighbor_list_is_a_full_list(sys500):
     # ghosts are images of their owners
     sh = x[s["nlocal"]:] - x[s["ghost_owner"]]
     assert np.allclose(np.abs(sh / s["box"]).round(), np.abs(sh / s["box"]), atol=1e-12)
+
+
+def test_bench_and_entry_points_parse_without_a_gpu():
+    """bench.py's argument surface (the driver's contract flags) and the graft entry module import on a CPU-only box."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in out.stdout
+    import importlib
+    sys.path.insert(0, ROOT)
+    g = importlib.import_module("__graft_entry__")
+    assert callable(g.build) and callable(g.smoke)

@@ -46,12 +46,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, cells=6):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         grid = P.brick_grid(world)
-        s = H.make_system(6, brick=(rank, grid))
+        s = H.make_system(cells, brick=(rank, grid))
         plan = P.ExchangePlan(s, rank, world, dist)
         nl, ng = s["nlocal"], s["nghost"]
         # payload = a function of the atom tag; after the exchange every ghost must hold its owner's payload
@@ -67,9 +67,9 @@ def _worker(rank, world, port, q):
         gt = s["tag"][nl:].astype(np.float64)
         ok = np.array_equal(pay[nl:], np.stack([gt, 2 * gt, -gt, np.sqrt(gt)], axis=1))
         # grid all-reduce: each rank deposits its own atoms, the sum must equal the whole-box deposit
-        cells = np.minimum((s["x"][:nl] / (s["box"] / 4)).astype(int), 3)
+        cell = np.minimum((s["x"][:nl] / (s["box"] / 4)).astype(int), 3)
         hist = np.zeros(64)
-        np.add.at(hist, cells[:, 0] + 4 * cells[:, 1] + 16 * cells[:, 2], 1.0)
+        np.add.at(hist, cell[:, 0] + 4 * cell[:, 1] + 16 * cell[:, 2], 1.0)
         t = torch.as_tensor(hist)
         dist.all_reduce(t)
         q.put((rank, bool(ok), float(t.sum()), int((~own).sum()), int(own.sum())))
@@ -77,18 +77,19 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_exchange_plan_two_gloo_ranks():
+@pytest.mark.parametrize("cells", [6, (10, 5, 5)])   # cubic box (strong scaling); 5^3 cells per rank (bench.py --weak)
+def test_exchange_plan_two_gloo_ranks(cells):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, cells)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
     for p in procs:
         p.join(60)
-    natoms = 4 * 6 ** 3
+    natoms = 4 * (cells ** 3 if np.isscalar(cells) else int(np.prod(cells)))
     for rank, ok, total, remote, own in res:
         assert ok, "ghost payload mismatch on rank %d" % rank
         assert total == natoms
