@@ -143,6 +143,10 @@ def test_fix_b200_without_gpu_reports_through_lammps_error(sys500, synth_beta_1)
         host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], model=9))
     with pytest.raises(host.FixError, match="non-positive grid"):
         host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], grid=(0, 1, 1)))
+    for extra, msg in ((["peratom", -1], "peratom must be >= 0"), (["rng", "mt"], "rng must be mars or philox"),
+                       (["neigh", "host"], "neigh must be device or lammps"), (["comm", "mpi"], "comm must be device or lammps")):
+        with pytest.raises(host.FixError, match=msg):
+            host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], style="eph/b200", extra=extra))
     if not gpu_available():
         with pytest.raises(host.FixError, match="no CUDA device|CUDA"):
             host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"]))

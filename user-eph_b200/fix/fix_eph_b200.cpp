@@ -121,6 +121,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
   rng_mars = false;
   comm_lammps = nrPS > 1;
   neigh_device = false;
+  peratom_every = 1;
   int device = -1;
   for (int k = 17 + types; k + 1 < narg; k += 2) {
     if (strcmp(arg[k], "rng") == 0) {
@@ -133,6 +134,11 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
       if (strcmp(arg[k + 1], "device") == 0) neigh_device = true;
       else if (strcmp(arg[k + 1], "lammps") == 0) neigh_device = false;
       else error->all(FLERR, "fix eph/b200: neigh must be device or lammps");
+    } else if (strcmp(arg[k], "peratom") == 0) {
+      // the 8 per-atom columns live on the device; bringing them to array_atom costs 64 bytes per atom over PCIe, so
+      // the cadence is the user's: every N-th step (default 1 = the reference's behaviour, 0 = never)
+      peratom_every = atoi(arg[k + 1]);
+      if (peratom_every < 0) error->all(FLERR, "fix eph/b200: peratom must be >= 0");
     } else if (strcmp(arg[k], "comm") == 0) {
       if (strcmp(arg[k + 1], "lammps") == 0) comm_lammps = true;
       else if (strcmp(arg[k + 1], "device") == 0) comm_lammps = false;
@@ -355,7 +361,8 @@ void FixEPHB200::end_of_step() {
   MPI_Allreduce(MPI_IN_PLACE, &E_local, 1, MPI_DOUBLE, MPI_SUM, world);
   Ee += E_local;
 
-  if (nlocal > 0) check(eph_b200_get_peratom(dev, &array[0][0], EPH_B200_HOST), "get_peratom");
+  if (nlocal > 0 && peratom_every > 0 && update->ntimestep % peratom_every == 0)
+    check(eph_b200_get_peratom(dev, &array[0][0], EPH_B200_HOST), "get_peratom");
 }
 
 void FixEPHB200::reset_dt() {

@@ -91,6 +91,7 @@ class FixEPHB200 : public Fix {
   bool rng_mars;
   bool comm_lammps;
   bool neigh_device;
+  int peratom_every;            // keyword `peratom N`: array_atom is refreshed every N-th step (0: never)
   class NeighList *list;
   double Ee;
   size_t n;
