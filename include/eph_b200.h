@@ -120,7 +120,9 @@ int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz);
 /* LAMMPS' neighbor->skin and the skin of the device-side inner list (two-level Verlet list: the sweeps walk a
  * list cut at r_c + inner_skin that the device rebuilds from LAMMPS' list; a device-side displacement check falls
  * back to LAMMPS' list whenever the inner one could be incomplete, so results never depend on this setting).
- * inner_skin = 0 disables the inner list, negative keeps the current value (default 0.4 A, or EPH_B200_INNER_SKIN). */
+ * inner_skin = 0 disables the inner list, negative keeps the current value (default 0.4 A, or EPH_B200_INNER_SKIN).
+ * Call it before set_neighbors: with a list already registered the sweeps walk LAMMPS' list until the next
+ * set_neighbors applies the new setting (the age of the registered list is unknown to the engine). */
 int eph_b200_set_skin(eph_b200_handle *h, double skin, double inner_skin);
 /* how often the inner list was (re)built and how many steps saw it invalidated */
 int eph_b200_list_stats(eph_b200_handle *h, long long *inner_builds, long long *fallback_steps);

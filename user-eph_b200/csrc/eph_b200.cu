@@ -145,6 +145,7 @@ struct eph_b200_handle {
   double skin = -1.0;                    // LAMMPS' neighbor->skin (unknown: inner list only valid from LAMMPS' build)
   double inner_skin = 0.4;
   bool inner_enabled = true;
+  bool inner_wanted = true;              // the setting the next set_neighbors applies (set_skin with a list registered)
   bool fresh_neighbors = false;          // set_neighbors since the last post_force
   bool have_inner = false;               // an inner list (and xref) exists
   bool inner_gave_up = false;            // rebuild was refused by the device-side check: use LAMMPS' list until it changes
@@ -378,7 +379,7 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
   h->cfg.type_map = h->type_map.data();
   if (const char *e = std::getenv("EPH_B200_INNER_SKIN")) {
     h->inner_skin = std::atof(e);
-    h->inner_enabled = h->inner_skin > 0.0;
+    h->inner_enabled = h->inner_wanted = h->inner_skin > 0.0;
   }
   if (const char *e = std::getenv("EPH_B200_LANES")) {   // tuning knob: lanes per atom in the sweeps
     const int v = std::atoi(e);
@@ -669,9 +670,11 @@ int eph_b200_set_skin(eph_b200_handle *h, double skin, double inner_skin) {
   if (skin < 0.0) return fail(h, EPH_B200_ERR_ARG, "set_skin: negative skin");
   h->skin = skin;
   if (inner_skin >= 0.0) h->inner_skin = inner_skin;   // negative: keep the current setting
-  h->inner_enabled = h->inner_skin > 0.0 && h->inner_skin <= skin;
+  h->inner_wanted = h->inner_skin > 0.0 && h->inner_skin <= skin;
   h->have_inner = false;
-  h->fresh_neighbors = h->neigh_set;   // rebuild the inner list at the next post_force
+  // with a list registered its age is unknown here and its tile storage was sized under the previous setting: the
+  // sweeps walk LAMMPS' list until the next set_neighbors applies the new one
+  h->inner_enabled = h->neigh_set ? false : h->inner_wanted;
   return EPH_B200_OK;
 }
 
@@ -751,6 +754,7 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
     h->neigh_ptr = h->neigh.p;
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
+  h->inner_enabled = h->inner_wanted;
   long long slots = total;   // pair-weight slots: CSR rows of LAMMPS' list or, usually larger, the tiles of the inner list
   if (h->inner_enabled && nlocal > 0) {
     const int tile_atoms = 32 / h->lanes;
