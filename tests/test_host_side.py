@@ -147,9 +147,54 @@ def test_fix_b200_without_gpu_reports_through_lammps_error(sys500, synth_beta_1)
                        (["neigh", "host"], "neigh must be device or lammps"), (["comm", "mpi"], "comm must be device or lammps")):
         with pytest.raises(host.FixError, match=msg):
             host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], style="eph/b200", extra=extra))
+    # decks list more element names than atom types (`Ni.beta Ni Ni`): a keyword is found behind any number of extras
+    with pytest.raises(host.FixError, match="peratom must be >= 0"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni", "Ni"], style="eph/b200", extra=["peratom", -1]))
+    with pytest.raises(host.FixError, match="keyword without a value"):
+        host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni", "Ni", "Ni"], style="eph/b200", extra=["rng"]))
     if not gpu_available():
         with pytest.raises(host.FixError, match="no CUDA device|CUDA"):
             host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"]))
+
+
+def _deck_fix_lines():
+    """every `fix ... eph ...` command of the reference's examples, tests and benchmarks (model 4 decks)"""
+    out = []
+    if not os.path.isdir(REFERENCE):
+        return out
+    seen = set()
+    for top in ("Examples", "Tests", "TB_Bench"):
+        for dirpath, _, files in os.walk(os.path.join(REFERENCE, top)):
+            for fn in files:
+                if not fn.endswith(".lmp"):
+                    continue
+                for line in open(os.path.join(dirpath, fn), errors="replace"):
+                    w = line.split()
+                    if len(w) > 18 and w[0] == "fix" and w[3] in ("eph", "eph/gpu") and tuple(w[4:]) not in seen:
+                        seen.add(tuple(w[4:]))
+                        out.append((os.path.relpath(dirpath, REFERENCE), w))
+    return out
+
+
+@pytest.mark.parametrize("deck", _deck_fix_lines(), ids=lambda d: d[0].replace("/", "_"))
+def test_reference_decks_are_accepted_up_to_the_device(deck, sys500):
+    """Drop-in check of the command line: each distinct `fix eph` line the reference ships is parsed by FixEPHB200 in
+    the deck's own directory (beta file, grid file) and fails -- on a box without a GPU -- only at eph_b200_create."""
+    rel, w = deck
+    beta = os.path.join(REFERENCE, rel, w[17])
+    if not os.path.exists(beta):
+        pytest.skip("deck needs %s, which the reference does not ship" % w[17])
+    args = ["fx", "all", "eph/b200"] + w[4:]
+    cwd = os.getcwd()
+    os.chdir(os.path.join(REFERENCE, rel))
+    try:
+        if gpu_available():
+            host.FixDriver(sys500, args).close()
+        else:
+            with pytest.raises(host.FixError, match="no CUDA device|CUDA"):
+                host.FixDriver(sys500, args)
+    finally:
+        os.chdir(cwd)
 
 
 def test_harness_neighbor_list_is_a_full_list(sys500):

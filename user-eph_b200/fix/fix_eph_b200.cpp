@@ -123,28 +123,35 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
   neigh_device = false;
   peratom_every = 1;
   int device = -1;
-  for (int k = 17 + types; k + 1 < narg; k += 2) {
+  // token by token: decks list more element names than atom types (e.g. `Ni.beta Ni Ni` with one type); like the
+  // reference those extras are skipped, and a keyword is recognised wherever it stands
+  for (int k = 17 + types; k < narg; ++k) {
+    const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "neigh") == 0 ||
+                            strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0;
+    if (!is_keyword) continue;   // an extra element name
+    if (k + 1 >= narg) error->all(FLERR, "fix eph/b200: keyword without a value");
+    const char *val = arg[k + 1];
     if (strcmp(arg[k], "rng") == 0) {
-      if (strcmp(arg[k + 1], "mars") == 0) rng_mars = true;
-      else if (strcmp(arg[k + 1], "philox") == 0) rng_mars = false;
+      if (strcmp(val, "mars") == 0) rng_mars = true;
+      else if (strcmp(val, "philox") == 0) rng_mars = false;
       else error->all(FLERR, "fix eph/b200: rng must be mars or philox");
     } else if (strcmp(arg[k], "device") == 0) {
-      device = atoi(arg[k + 1]);
+      device = atoi(val);
     } else if (strcmp(arg[k], "neigh") == 0) {
-      if (strcmp(arg[k + 1], "device") == 0) neigh_device = true;
-      else if (strcmp(arg[k + 1], "lammps") == 0) neigh_device = false;
+      if (strcmp(val, "device") == 0) neigh_device = true;
+      else if (strcmp(val, "lammps") == 0) neigh_device = false;
       else error->all(FLERR, "fix eph/b200: neigh must be device or lammps");
     } else if (strcmp(arg[k], "peratom") == 0) {
       // the 8 per-atom columns live on the device; bringing them to array_atom costs 64 bytes per atom over PCIe, so
       // the cadence is the user's: every N-th step (default 1 = the reference's behaviour, 0 = never)
-      peratom_every = atoi(arg[k + 1]);
+      peratom_every = atoi(val);
       if (peratom_every < 0) error->all(FLERR, "fix eph/b200: peratom must be >= 0");
-    } else if (strcmp(arg[k], "comm") == 0) {
-      if (strcmp(arg[k + 1], "lammps") == 0) comm_lammps = true;
-      else if (strcmp(arg[k + 1], "device") == 0) comm_lammps = false;
+    } else {   // comm
+      if (strcmp(val, "lammps") == 0) comm_lammps = true;
+      else if (strcmp(val, "device") == 0) comm_lammps = false;
       else error->all(FLERR, "fix eph/b200: comm must be device or lammps");
     }
-    // anything else: extra element names, ignored like the reference does
+    ++k;
   }
 
   eta_factor = sqrt(2.0 * force->boltz / update->dt);
