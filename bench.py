@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
+    ap.add_argument("--sharded-grid", action="store_true", help="multi-GPU: every rank advances only its z-slab of the FDM grid "
+                    "(halo planes between sub-steps, all-gather at the end) instead of solving the whole grid redundantly; "
+                    "needs --grid divisible by --gpus")
     ap.add_argument("--side-stream-priority", type=int, default=0, help="CUDA priority of the grid/communication streams "
                     "and of NCCL's stream (0 default; -1 high was measured 12 %% slower at 2 GPUs: the all-reduce kernel "
                     "then takes SM slots from the density pass while it waits for its peer)")
@@ -286,8 +289,10 @@ def run_b200(a):
     if cstream is not None:
         eng.set_boundary_atoms(exch.send_idx)
 
+    sharded = bool(D) and a.sharded_grid and P.grid_slab(gridn[2], rank, world) is not None
+
     def step_resident(k):
-        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src, grid_stream=gstream)
+        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src, grid_stream=gstream, sharded_grid=sharded)
 
     def timed(fn, steps, first):
         """barrier + synchronize on both sides, device time via CUDA events, max over ranks"""
@@ -433,7 +438,7 @@ def run_b200(a):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if a.weak else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid),
+               "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid), grid_solve="z-slabs + halo planes + all-gather" if sharded else "whole grid on every rank",
                               exchange_bytes_per_step_rank0=exch.bytes_per_step(), list_stats=eng.list_stats()),
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
         if not a.no_cpu_baseline and world == 1:

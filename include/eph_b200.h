@@ -175,6 +175,22 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace);
 int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double *v, int memspace);
 int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local);
 int eph_b200_bind_grid_source(eph_b200_handle *h, double *dT_e_dev);
+/* Sharded grid solve (multi-rank alternative to the redundant solve above; replaces MPI_Allreduce + rank-0 solve +
+ * MPI_Bcast of eph_fdm.h:481-491 with all-reduce + slab solve with halo planes + all-gather).  Every rank keeps the
+ * whole grid in memory and updates only its slab of z-planes [z_begin, z_end); the stencil reads the two neighbouring
+ * planes (periodic in z) from the same full-size array, so between two sub-steps the caller copies those planes from
+ * the ranks that own them into its own T_e array in place (ncclSend/ncclRecv on grid_device_ptr(h, 0, ...), which
+ * follows the double buffer: query it after every sub-step), and after the last sub-step all-gathers the slabs.
+ *   end_of_step_begin; all-reduce of the source term; grid_plan_substeps(&n);
+ *   n x { grid_substep(z_begin, z_end); halo exchange (not after the last one) }; all-gather of T_e;
+ *   end_of_step_end_external
+ * plan_substeps refreshes temperature-dependent cells and returns the reference's sub-step count (eph_fdm.h:290-313;
+ * 0 without flag 4); the last planned sub-step also clears the source term on all planes.  Work is enqueued on the
+ * grid stream when one is set.  grid_device_ptr: which as in get_grid (0 T_e, current buffer; 5 source term). */
+int eph_b200_grid_plan_substeps(eph_b200_handle *h, int *n_substeps);
+int eph_b200_grid_substep(eph_b200_handle *h, int z_begin, int z_end);
+int eph_b200_end_of_step_end_external(eph_b200_handle *h, double *E_local);
+int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr);
 /* Optional second CUDA stream for the grid.  When set, end_of_step_begin makes that stream wait for the deposit,
  * end_of_step_end enqueues the solve on it, and the engine's main stream waits for the solve only where it needs
  * T_e or dT_e again (the force pass, the next deposit, grid read-backs).  A caller that issues its all-reduce of the

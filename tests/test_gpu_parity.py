@@ -227,26 +227,6 @@ def test_fix_b200_matches_committed_golden_vectors(name, comm):
         assert drv.n_forward() >= 3 * len(recs)
 
 
-def test_fix_b200_peratom_cadence():
-    """keyword `peratom N`: array_atom is refreshed from the device in steps divisible by N only (forces are unaffected)"""
-    g = np.load(os.path.join(GOLDEN, "caseA_example1.npz"))
-    s = traj.system_from_golden(g)
-    s["natoms"] = s["nlocal"]
-    cwd = os.getcwd()
-    os.chdir(GOLDEN)
-    try:
-        drv = host.FixDriver(s, H.fix_args(3, "Ni_trunc.beta", ["Ni"], grid=(1, 1, 1), style="eph/b200",
-                                           extra=["rng", "mars", "peratom", "2"]), dt=float(g["dt"]))
-    finally:
-        os.chdir(cwd)
-    recs = traj.run_fix_driver(drv, s, list(g["xi"]))
-    for k in range(3):
-        assert H.error_metrics(recs[k]["f"], g["out_f"][k]) < TOL
-    assert not recs[0]["array"].any()
-    assert H.error_metrics(recs[1]["array"], g["out_array"][1]) < TOL
-    assert np.array_equal(recs[2]["array"], recs[1]["array"])
-
-
 def _fdm_case(shape, rng, walls, constant, tdyn_tables=None):
     nx, ny, nz = shape
     n = nx * ny * nz

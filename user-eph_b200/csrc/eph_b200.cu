@@ -174,6 +174,9 @@ struct eph_b200_handle {
   DevBuf<double2> C_T_tab, K_T_tab;
   DevBuf<double> E_T_tab;
   int last_substeps = 0;
+  double plan_inner_dt = 0;              // sub-step length of the last grid_plan
+  bool plan_open = false;                // grid_plan_substeps called, sub-steps of this solve still to come
+  int plan_done = 0;                     // sub-steps of the open plan already run
   // TMA path of the stencil: tensor maps over T_e (both buffers) and kappa_e; needs 16-byte row strides (nx even)
   bool tma_ok = false, has_walls = false;
   CUtensorMap map_T[2], map_K, map_S;
@@ -1273,10 +1276,11 @@ int eph_b200_unpack_ghost_payload(eph_b200_handle *h, int n, const int *recv_ind
 
 namespace {
 
-// EPH_FDM::solve (eph_fdm.h:267-400).  The sub-step count is decided on the
-// host with the reference's exact double arithmetic and truncating cast from
-// three device-reduced scalars; they are cached while the parameters are constant.
-int grid_solve(eph_b200_handle *h, cudaStream_t st) {
+// EPH_FDM::solve (eph_fdm.h:267-400) in two parts so that a multi-rank caller can put a halo exchange between the
+// sub-steps.  grid_plan: refresh of temperature-dependent cells and the sub-step count, decided on the host with the
+// reference's exact double arithmetic and truncating cast from three device-reduced scalars (cached while the
+// parameters are constant).  grid_substep: one explicit sub-step over the planes [z_begin, z_end).
+int grid_plan(eph_b200_handle *h, cudaStream_t st) {
   const long long n = h->ncell;
   if (h->has_tdyn) {
     if (h->n_T < 4) return fail(h, EPH_B200_ERR_ARG, "solve: grid has temperature-dependent cells but no parameter tables");
@@ -1309,46 +1313,62 @@ int grid_solve(eph_b200_handle *h, cudaStream_t st) {
     inner_dt = dt / new_steps;
   }
   h->last_substeps = (int)new_steps;
+  h->plan_inner_dt = inner_dt;
+  return EPH_B200_OK;
+}
 
+int grid_substep(eph_b200_handle *h, cudaStream_t st, int z_begin, int z_end, bool clear_source) {
+  const long long n = h->ncell;
+  const double dx = h->gdx, dy = h->gdy, dz = h->gdz;
   GridArgs g{};
   g.nx = h->nx; g.ny = h->ny; g.nz = h->nz; g.ncell = n;
   g.dT_e = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p; g.S_e = h->S_e.p; g.rho_e = h->rho_e.p; g.C_e = h->C_e.p; g.kappa_e = h->kappa_e.p;
   g.flag = h->flag.p; g.t_dyn = h->t_dyn.p;
   g.E_e_T = h->has_tdyn ? h->E_T_tab.p : nullptr; g.n_T = h->n_T; g.dT = h->dT_tab;
   g.inv_dx2 = 1.0 / (dx * dx); g.inv_dy2 = 1.0 / (dy * dy); g.inv_dz2 = 1.0 / (dz * dz);
-  g.inner_dt = inner_dt; g.status = h->d_status.p;
+  g.inner_dt = h->plan_inner_dt; g.status = h->d_status.p;
+  g.z_begin = z_begin; g.z_end = z_end;
+  const int nzs = z_end - z_begin;
   dim3 block(32, 4, 2);
-  dim3 grid((h->nx + block.x - 1) / block.x, (h->ny + block.y - 1) / block.y, (h->nz + block.z - 1) / block.z);
-  dim3 tgrid((h->nx + kTX - 1) / kTX, (h->ny + kTY - 1) / kTY, (h->nz + kTZ - 1) / kTZ);
-  for (unsigned int s = 0; s < new_steps; ++s) {
-    g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
-    g.clear_source = (s + 1 == new_steps) ? 1 : 0;
-    {
-      KernelTimer kt(h, "fdm_substep", st);
-      if (h->tma_ok && h->uniform) {
-        if (h->map_S_base != g.dT_e) {   // the source array may be caller-owned (bind_grid_source)
-          if (!encode_grid_map(&h->map_S, g.dT_e, h->nx, h->ny, h->nz, kTX, kTY, kTZ)) return fail(h, EPH_B200_ERR_CUDA, "solve: cannot encode the source tensor map");
-          h->map_S_base = g.dT_e;
-        }
-        GridUniformArgs u;
-        u.nx = h->nx; u.ny = h->ny; u.nz = h->nz; u.T_in = g.T_in; u.T_out = g.T_out; u.dT_e = g.dT_e;
-        u.kappa = h->u_kappa; u.S = h->u_S; u.rho = h->u_rho; u.C = h->u_C;
-        u.inv_rho_C = 1.0 / (h->u_rho * h->u_C);
-        u.inv_dx2 = g.inv_dx2; u.inv_dy2 = g.inv_dy2; u.inv_dz2 = g.inv_dz2; u.inner_dt = g.inner_dt;
-        u.clear_source = g.clear_source; u.status = g.status;
-        fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, st>>>(h->map_T[h->cur], h->map_S, u);
-      } else if (h->tma_ok) {
-        GridTmaArgs ta;
-        ta.g = g;
-        ta.has_walls = h->has_walls ? 1 : 0;
-        fdm_substep_tma_kernel<<<tgrid, 256, kTmaSmemBytes, st>>>(h->map_T[h->cur], h->map_K, ta);
-      } else {
-        fdm_substep_kernel<<<grid, block, 0, st>>>(g);
+  dim3 grid((h->nx + block.x - 1) / block.x, (h->ny + block.y - 1) / block.y, (nzs + block.z - 1) / block.z);
+  dim3 tgrid((h->nx + kTX - 1) / kTX, (h->ny + kTY - 1) / kTY, (nzs + kTZ - 1) / kTZ);
+  g.T_in = h->T[h->cur].p; g.T_out = h->T[1 - h->cur].p;
+  g.clear_source = clear_source ? 1 : 0;
+  {
+    KernelTimer kt(h, "fdm_substep", st);
+    if (h->tma_ok && h->uniform) {
+      if (h->map_S_base != g.dT_e) {   // the source array may be caller-owned (bind_grid_source)
+        if (!encode_grid_map(&h->map_S, g.dT_e, h->nx, h->ny, h->nz, kTX, kTY, kTZ)) return fail(h, EPH_B200_ERR_CUDA, "solve: cannot encode the source tensor map");
+        h->map_S_base = g.dT_e;
       }
+      GridUniformArgs u;
+      u.nx = h->nx; u.ny = h->ny; u.nz = h->nz; u.T_in = g.T_in; u.T_out = g.T_out; u.dT_e = g.dT_e;
+      u.kappa = h->u_kappa; u.S = h->u_S; u.rho = h->u_rho; u.C = h->u_C;
+      u.inv_rho_C = 1.0 / (h->u_rho * h->u_C);
+      u.inv_dx2 = g.inv_dx2; u.inv_dy2 = g.inv_dy2; u.inv_dz2 = g.inv_dz2; u.inner_dt = g.inner_dt;
+      u.clear_source = g.clear_source; u.status = g.status;
+      u.z_begin = z_begin; u.z_end = z_end;
+      fdm_uniform_tma_kernel<<<tgrid, 256, kUniSmemBytes, st>>>(h->map_T[h->cur], h->map_S, u);
+    } else if (h->tma_ok) {
+      GridTmaArgs ta;
+      ta.g = g;
+      ta.has_walls = h->has_walls ? 1 : 0;
+      fdm_substep_tma_kernel<<<tgrid, 256, kTmaSmemBytes, st>>>(h->map_T[h->cur], h->map_K, ta);
+    } else {
+      fdm_substep_kernel<<<grid, block, 0, st>>>(g);
     }
-    EPH_LAUNCH_CHECK(h);
-    h->cur = 1 - h->cur;
   }
+  EPH_LAUNCH_CHECK(h);
+  h->cur = 1 - h->cur;
+  return EPH_B200_OK;
+}
+
+int grid_solve(eph_b200_handle *h, cudaStream_t st) {
+  int rc = grid_plan(h, st);
+  if (rc) return rc;
+  const int new_steps = h->last_substeps;
+  for (int s = 0; s < new_steps; ++s)
+    if ((rc = grid_substep(h, st, 0, h->nz, s + 1 == new_steps))) return rc;
   return EPH_B200_OK;
 }
 
@@ -1393,14 +1413,15 @@ int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double
   return EPH_B200_OK;
 }
 
-int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local) {
+static int end_of_step_finish(eph_b200_handle *h, double *E_local, bool solve) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->eos_open) return fail(h, EPH_B200_ERR_ARG, "end_of_step_end without end_of_step_begin");
   h->eos_open = false;
+  h->plan_open = false;
   cudaSetDevice(h->cfg.device);
   int rc;
   cudaStream_t st = h->grid_stream ? h->grid_stream : h->stream;
-  if (h->cfg.flags & EPH_B200_FDM) {
+  if (solve && (h->cfg.flags & EPH_B200_FDM)) {
     if ((rc = grid_solve(h, st))) return rc;
   }
   if (h->grid_stream) {
@@ -1412,6 +1433,57 @@ int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local) {
     EPH_CUDA(h, cudaStreamSynchronize(h->stream));
     *E_local = h->h_pinned[0];
   }
+  return EPH_B200_OK;
+}
+
+int eph_b200_end_of_step_end(eph_b200_handle *h, double *E_local) { return end_of_step_finish(h, E_local, true); }
+
+// ---- sharded grid solve: the caller drives the sub-steps of one solve and exchanges halo planes between them ----
+int eph_b200_grid_plan_substeps(eph_b200_handle *h, int *n_substeps) {
+  if (!h || !n_substeps) return EPH_B200_ERR_ARG;
+  if (!h->eos_open) return fail(h, EPH_B200_ERR_ARG, "grid_plan_substeps: only valid between end_of_step_begin and end_of_step_end_external");
+  *n_substeps = 0;
+  h->plan_open = false;
+  if (!(h->cfg.flags & EPH_B200_FDM)) return EPH_B200_OK;   // the reference does not solve without flag 4 (fix_eph.cpp:392-394)
+  cudaSetDevice(h->cfg.device);
+  int rc = grid_plan(h, h->grid_stream ? h->grid_stream : h->stream);
+  if (rc) return rc;
+  *n_substeps = h->last_substeps;
+  h->plan_open = true;
+  h->plan_done = 0;
+  return EPH_B200_OK;
+}
+
+int eph_b200_grid_substep(eph_b200_handle *h, int z_begin, int z_end) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->plan_open || h->plan_done >= h->last_substeps) return fail(h, EPH_B200_ERR_ARG, "grid_substep: no sub-step of a planned solve is due");
+  if (z_begin < 0 || z_end > h->nz || z_begin >= z_end) return fail(h, EPH_B200_ERR_ARG, "grid_substep: bad plane range [%d, %d) of %d", z_begin, z_end, h->nz);
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = h->grid_stream ? h->grid_stream : h->stream;
+  const bool last = h->plan_done + 1 == h->last_substeps;
+  int rc = grid_substep(h, st, z_begin, z_end, last);
+  if (rc) return rc;
+  if (last) {   // the source term is consumed: the kernel cleared this rank's slab, the other planes are cleared here
+    double *src = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p;
+    const size_t plane = (size_t)h->nx * h->ny;
+    if (z_begin > 0) EPH_CUDA(h, cudaMemsetAsync(src, 0, (size_t)z_begin * plane * sizeof(double), st));
+    if (z_end < h->nz) EPH_CUDA(h, cudaMemsetAsync(src + (size_t)z_end * plane, 0, (size_t)(h->nz - z_end) * plane * sizeof(double), st));
+  }
+  ++h->plan_done;
+  return EPH_B200_OK;
+}
+
+int eph_b200_end_of_step_end_external(eph_b200_handle *h, double *E_local) {
+  if (h && h->plan_open && h->plan_done != h->last_substeps)
+    return fail(h, EPH_B200_ERR_ARG, "end_of_step_end_external: %d of %d planned sub-steps run", h->plan_done, h->last_substeps);
+  return end_of_step_finish(h, E_local, false);
+}
+
+int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr) {
+  if (!h || !ptr) return EPH_B200_ERR_ARG;
+  if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "grid_device_ptr: no grid");
+  *ptr = grid_field(h, which);
+  if (!*ptr) return fail(h, EPH_B200_ERR_ARG, "grid_device_ptr: bad field id %d", which);
   return EPH_B200_OK;
 }
 

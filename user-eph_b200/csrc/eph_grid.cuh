@@ -26,6 +26,9 @@ struct GridArgs {
   double inner_dt;
   int clear_source;  // last sub-step: zero dT_e (sync_after, eph_fdm.h:484-487)
   unsigned *__restrict__ status;
+  // planes [z_begin, z_end) are updated by this launch (the whole grid, or one rank's slab of a sharded solve:
+  // neighbours are still read with the periodic wrap of the full grid, the halo planes being current in T_in)
+  int z_begin, z_end;
 };
 
 // EPH_Linear::operator() and reverse_lookup (reference eph_linear.h:40-62)
@@ -58,8 +61,8 @@ __device__ __forceinline__ double linear_reverse(const double *__restrict__ y, i
 __global__ void __launch_bounds__(256) fdm_substep_kernel(GridArgs g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  const int k = blockIdx.z * blockDim.z + threadIdx.z;
-  if (i >= g.nx || j >= g.ny || k >= g.nz) return;
+  const int k = g.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
+  if (i >= g.nx || j >= g.ny || k >= g.z_end) return;
   const long long sx = 1, sy = g.nx, sz = (long long)g.nx * g.ny;
   const long long r = i + j * sy + k * sz;
   const short fr = g.flag[r];

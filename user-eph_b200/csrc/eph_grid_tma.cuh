@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256, 3) fdm_substep_tma_kernel(const __grid_co
   short *sF = reinterpret_cast<short *>(tma_smem + 2 * kBoxBytes);
   unsigned long long &bar = *reinterpret_cast<unsigned long long *>(tma_smem + 2 * kBoxBytes + kFlagBytes);
   const GridArgs &g = ta.g;
-  const int ox = blockIdx.x * kTX, oy = blockIdx.y * kTY, oz = blockIdx.z * kTZ;
+  const int ox = blockIdx.x * kTX, oy = blockIdx.y * kTY, oz = g.z_begin + blockIdx.z * kTZ;
   const int tid = threadIdx.x;
 
   if (tid == 0) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256, 3) fdm_substep_tma_kernel(const __grid_co
 #pragma unroll
     for (int b = 0; b < kBatch; ++b) {
       const int tz = t0 + b, k = oz + tz;
-      if (k >= g.nz) break;
+      if (k >= g.z_end) break;
       const long long r = i + j * sy + k * sz;
       const int c = (tx + kHX) + (ty + 1) * kBX + (tz + 1) * kBX * kBY;
       double T = sT[c];
@@ -194,6 +194,7 @@ struct GridUniformArgs {
   double inv_dx2, inv_dy2, inv_dz2, inner_dt;
   int clear_source;
   unsigned *__restrict__ status;
+  int z_begin, z_end;                // planes updated by this launch (GridArgs)
 };
 
 constexpr int kTileBytes = kTX * kTY * kTZ * 8;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256) fdm_uniform_tma_kernel(const __grid_const
   double *sT = reinterpret_cast<double *>(tma_smem);
   double *sS = reinterpret_cast<double *>(tma_smem + kBoxBytes);
   unsigned long long &bar = *reinterpret_cast<unsigned long long *>(tma_smem + kBoxBytes + kTileBytes);
-  const int ox = blockIdx.x * kTX, oy = blockIdx.y * kTY, oz = blockIdx.z * kTZ;
+  const int ox = blockIdx.x * kTX, oy = blockIdx.y * kTY, oz = g.z_begin + blockIdx.z * kTZ;
   const int tid = threadIdx.x;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(256) fdm_uniform_tma_kernel(const __grid_const
 #pragma unroll
   for (int tz = 0; tz < kTZ; ++tz, c += kBX * kBY) {
     const double Tn = sT[c + kBX * kBY];
-    if (oz + tz < g.nz) {
+    if (oz + tz < g.z_end) {
       double ddT = 0.0;
       ddT += g.kappa * ((sT[c + 1] + sT[c - 1] - 2.0 * T) * g.inv_dx2);
       ddT += g.kappa * ((sT[c + kBX] + sT[c - kBX] - 2.0 * T) * g.inv_dy2);

@@ -57,6 +57,10 @@ SYMBOLS = {
     "eph_b200_end_of_step_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_end_of_step_end": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_bind_grid_source": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "eph_b200_grid_plan_substeps": (C.c_int, [C.c_void_p, c_int_p]),
+    "eph_b200_grid_substep": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "eph_b200_end_of_step_end_external": (C.c_int, [C.c_void_p, c_double_p]),
+    "eph_b200_grid_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "eph_b200_set_grid_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_set_comm_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_set_boundary_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -113,6 +117,14 @@ def _space(*arrs):
     if len(spaces) > 1:
         raise ValueError("cannot mix host and device arrays in one call")
     return spaces.pop() if spaces else HOST
+
+
+class _DeviceArray:
+    """fp64 device memory owned by the engine, exposed through the CUDA array interface (zero-copy torch views)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
 
 
 class Engine:
@@ -180,6 +192,7 @@ class Engine:
                                                rho_e.ctypes.data, C_e.ctypes.data, kappa_e.ctypes.data,
                                                None if fl is None else fl.ctypes.data, None if td is None else td.ctypes.data))
         self.ncell = n
+        self.grid_shape = (nx, ny, nz)
 
     def set_grid_tables(self, dT, C_e_T, kappa_e_T, E_e_T):
         C_e_T, kappa_e_T, E_e_T = (np.ascontiguousarray(t, dtype=np.float64) for t in (C_e_T, kappa_e_T, E_e_T))
@@ -265,10 +278,33 @@ class Engine:
         ps = [_ptr(x), _ptr(v)]
         self._check(self.lib.eph_b200_end_of_step_begin(self.h, ps[0][0], ps[1][0], _space(*ps)))
 
-    def end_of_step_end(self, want_energy=True):
+    def end_of_step_end(self, want_energy=True, external=False):
+        """external: the caller has run the grid solve itself (sharded solve), only the bookkeeping is left"""
         e = C.c_double()
-        self._check(self.lib.eph_b200_end_of_step_end(self.h, C.byref(e) if want_energy else None))
+        fn = self.lib.eph_b200_end_of_step_end_external if external else self.lib.eph_b200_end_of_step_end
+        self._check(fn(self.h, C.byref(e) if want_energy else None))
         return e.value if want_energy else None
+
+    # sharded grid solve (eph_b200.parallel.sharded_grid_solve drives these between end_of_step_begin and
+    # end_of_step_end(external=True))
+    def grid_plan_substeps(self):
+        n = C.c_int()
+        self._check(self.lib.eph_b200_grid_plan_substeps(self.h, C.byref(n)))
+        return n.value
+
+    def grid_substep(self, z_begin, z_end):
+        self._check(self.lib.eph_b200_grid_substep(self.h, z_begin, z_end))
+
+    def grid_tensor(self, which=0):
+        """torch view (no copy) of a grid field in device memory; for T_e (which = 0) it names the CURRENT buffer of the
+        double-buffered solve, so ask again after every sub-step"""
+        import torch
+        p = C.c_void_p()
+        self._check(self.lib.eph_b200_grid_device_ptr(self.h, which, C.byref(p)))
+        views = self.__dict__.setdefault("_grid_views", {})
+        if p.value not in views:
+            views[p.value] = torch.as_tensor(_DeviceArray(p.value, self.ncell), device=torch.device("cuda", torch.cuda.current_device()))
+        return views[p.value]
 
     def bind_grid_source(self, tensor):
         self._check(self.lib.eph_b200_bind_grid_source(self.h, tensor.data_ptr() if tensor is not None else None))

@@ -143,16 +143,76 @@ class GhostExchange:
         return 32 * (self.send_idx.numel() + self.recv_idx.numel())
 
 
-def distributed_step(engine, exchange, dist, x, v, f, step, dT_e, want_energy=False, grid_stream=None):
+def grid_slab(nz, rank, world):
+    """z-planes [z0, z1) of the grid that `rank` updates in a sharded solve (equal slabs; None if nz does not divide)"""
+    if world < 1 or nz % world:
+        return None
+    per = nz // world
+    return rank * per, (rank + 1) * per
+
+
+def sharded_grid_solve(engine, dist, rank, world):
+    """EPH_FDM::solve (eph_fdm.h:267-400) with the grid sharded in z-slabs over the ranks: what the reference does as
+    MPI_Allreduce + solve on rank 0 + MPI_Bcast (eph_fdm.h:481-491) becomes all-reduce (done by the caller) + slab
+    sub-steps with one halo plane pair exchanged between sub-steps + all-gather of the slabs.
+
+    engine: anything with grid_shape, grid_plan_substeps(), grid_substep(z0, z1) and grid_tensor(0) (the whole T_e
+    field in the memory of this rank, current buffer; flat, z slowest).  Call between end_of_step_begin and
+    end_of_step_end(external=True), on the stream the grid work is to run on.  Returns the number of sub-steps."""
+    import torch
+    nx, ny, nz = engine.grid_shape
+    slab = grid_slab(nz, rank, world)
+    if slab is None:
+        raise ValueError("sharded grid solve needs nz (%d) divisible by the number of ranks (%d)" % (nz, world))
+    z0, z1 = slab
+    plane = nx * ny
+    n = engine.grid_plan_substeps()
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    for s in range(n):
+        engine.grid_substep(z0, z1)
+        if world == 1 or s == n - 1:
+            continue
+        # halo planes for the next sub-step, written in place at their global position (periodic in z).  Posting
+        # order matters when prev == nxt (two ranks): sends go "bottom plane to prev, top plane to next", receives
+        # "from next into the plane above the slab, from prev into the plane below", which pairs up on both sides.
+        T = engine.grid_tensor(0).view(nz, plane)
+        zlo, zhi = (z0 - 1) % nz, z1 % nz
+        ops = [dist.P2POp(dist.isend, T[z0], prev), dist.P2POp(dist.isend, T[z1 - 1], nxt),
+               dist.P2POp(dist.irecv, T[zhi], nxt), dist.P2POp(dist.irecv, T[zlo], prev)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if world > 1 and n > 0:
+        T = engine.grid_tensor(0).view(world, (z1 - z0) * plane)
+        mine = T[rank].clone()
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(T.view(-1), mine)
+        else:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            for r, p in enumerate(parts):
+                T[r].copy_(p)
+    return n
+
+
+def distributed_step(engine, exchange, dist, x, v, f, step, dT_e, want_energy=False, grid_stream=None, sharded_grid=False):
     """One `fix eph` step on one rank of a multi-GPU run (device tensors).
 
     grid_stream: a torch.cuda.Stream registered with engine.set_grid_stream(); the all-reduce of the source term and
-    the grid solve then run on it and overlap the next step's density pass."""
+    the grid solve then run on it and overlap the next step's density pass.
+    sharded_grid: every rank advances only its z-slab of the grid (sharded_grid_solve) instead of the whole grid."""
     engine.post_force_begin(x, v, None, step)
     exchange(engine)
     engine.post_force_end(f)
     engine.end_of_step_begin(None, v)   # positions are those of post_force (Verlet does not move atoms in between)
-    if dist is not None and dist.get_world_size() > 1:
+    multi = dist is not None and dist.get_world_size() > 1
+    if multi and sharded_grid:
+        import contextlib
+        import torch
+        with (torch.cuda.stream(grid_stream) if grid_stream is not None else contextlib.nullcontext()):
+            dist.all_reduce(dT_e)
+            sharded_grid_solve(engine, dist, dist.get_rank(), dist.get_world_size())
+        return engine.end_of_step_end(want_energy, external=True)
+    if multi:
         if grid_stream is not None:
             import torch
             with torch.cuda.stream(grid_stream):
