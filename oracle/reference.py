@@ -143,3 +143,58 @@ def fix_driver(system, fix_args, dt=1e-4, mass=None):
     sys.path.insert(0, os.path.join(os.path.dirname(HERE), "user-eph_b200"))
     from eph_b200.host import FixDriver
     return FixDriver(system, fix_args, dt=dt, lib=load(), prefix="ref", mass=mass)
+
+
+# ---------------------------------------------------------------------------
+# the unmodified `fix eph/atomic` (oracle/_ref/libeph_atomic_ref.so, oracle/ref/ref_atomic_driver.cpp)
+# ---------------------------------------------------------------------------
+PATH_ATOMIC = os.path.join(HERE, "_ref", "libeph_atomic_ref.so")
+_alib = None
+
+
+def atomic_available():
+    return os.path.exists(PATH_ATOMIC)
+
+
+def load_atomic():
+    global _alib
+    if _alib is None:
+        L = C.CDLL(PATH_ATOMIC)
+        L.refa_kappa_load.restype = C.c_void_p
+        _alib = L
+    return _alib
+
+
+def atomic_fix_driver(system, fix_args, dt=1e-4, mass=None):
+    """The unmodified FixEPHAtomic inside the LAMMPS stand-in."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "user-eph_b200"))
+    from eph_b200.host import FixDriver
+    return FixDriver(system, fix_args, dt=dt, lib=load_atomic(), prefix="refa", mass=mass)
+
+
+class Kappa:
+    """The reference's EPH_kappa tables (eph_kappa.h) at full precision."""
+
+    def __init__(self, path):
+        L = load_atomic()
+        self.h = L.refa_kappa_load(str(path).encode())
+        if not self.h:
+            raise RuntimeError("reference: cannot load kappa file %r" % (path,))
+        dims = (C.c_longlong * 4)()
+        scal = (C.c_double * 5)()
+        L.refa_kappa_info(C.c_void_p(self.h), dims, scal)
+        self.n_elements, self.n_pairs, self.n_r, self.n_T = (int(d) for d in dims)
+        self.r_cutoff, self.r_cutoff_sq, self.T_max, self.inv_dr_sq, self.dT = (float(v) for v in scal)
+
+    def table(self, kind, e=0):
+        """0 rho(r) [n_r][4], 1 rho(r^2) [n_r][4], 2 E(T) [n_T], 3 K(T) of slot e [n_T]"""
+        out = np.empty((self.n_r, 4)) if kind < 2 else np.empty(self.n_T)
+        load_atomic().refa_kappa_table(C.c_void_p(self.h), kind, e, _p(out))
+        return out
+
+    def __del__(self):
+        try:
+            load_atomic().refa_kappa_free(C.c_void_p(self.h))
+        except Exception:
+            pass

@@ -278,6 +278,10 @@ class Fix : protected Pointers {
   virtual double memory_usage() { return 0.0; }
   virtual int pack_forward_comm(int, int *, double *, int, int *) { return 0; }
   virtual void unpack_forward_comm(int, int, double *) {}
+  // atom migration callbacks (fix eph/atomic carries its per-atom electronic energy along, fix_eph_atomic.cpp:939-955)
+  virtual int pack_exchange(int, double *) { return 0; }
+  virtual int unpack_exchange(int, double *) { return 0; }
+  virtual void copy_arrays(int, int, int) {}
 };
 
 // One "swap": every ghost receives the value of its owner through the fix's own

@@ -210,6 +210,55 @@ def fix_args(flags, beta_file, elements, model=4, seed=12345, rho_e=1.0, C_e=3.5
              grid[2], T_infile, T_freq, T_out, beta_file] + list(elements) + list(extra))
 
 
+# ---------------------------------------------------------------------------
+# `fix eph/atomic` (reference fix_eph_atomic.cpp, eph_kappa.h): synthetic `.kappa` parametrisation
+# ---------------------------------------------------------------------------
+def synthetic_kappa(n_elements=1, n_r=1001, r_cutoff=4.5, n_T=2001, dT=1.0):
+    """Locality rho_a(r), heat capacity C(T) and conductivity K(T) knots from + - * / only (bit-reproducible text)."""
+    dr = r_cutoff / (n_r - 1)
+    r = np.arange(n_r, dtype=np.float64) * dr
+    T = np.arange(n_T, dtype=np.float64) * dT
+    n_pairs = (n_elements + 1) * (n_elements - 1) // 2 if n_elements > 1 else 1   # eph_kappa.h:76
+    rho_k = np.empty((n_elements, n_r))
+    C_k = np.empty((n_elements, n_T))
+    K_k = np.empty((n_pairs, n_T))
+    for e in range(n_elements):
+        t = 1.0 - r / r_cutoff
+        t = np.where(t > 0.0, t, 0.0)
+        rho_k[e] = (1.0 + 0.1 * e) * t * t * t / (1.0 + r * r / 4.0)
+        C_k[e] = (1.0e-5 + 1.0e-6 * e) * (1.0 + T / 1000.0)
+    for p in range(n_pairs):
+        K_k[p] = (0.02 + 0.002 * p) * (1.0 + T / 1000.0)
+    return n_elements, n_r, dr, r_cutoff, n_T, dT, T[-1], rho_k, C_k, K_k
+
+
+def write_kappa_file(path, knots, names=None, Z=None):
+    """Write knots in the `.kappa` grammar the reference reads (eph_kappa.h:53-151)."""
+    n_el, n_r, dr, rc, n_T, dT, T_max, rho_k, C_k, K_k = knots
+    names = names or ["Ni", "Co", "Cr", "Fe", "Al", "Cu"][:n_el]
+    Z = Z or [28, 27, 24, 26, 13, 29][:n_el]
+    with open(path, "w") as f:
+        f.write("# synthetic per-atom electronic properties, written by eph_b200.harness\n# rho_a(r), C(T), K(T)\n#\n")
+        f.write("%d %s\n" % (n_el, " ".join(names)))
+        f.write("%d %.17g %.17g %d %.17g %.17g\n" % (n_r, dr, rc, n_T, dT, T_max))
+        for e in range(n_el):
+            f.write("%d\n" % Z[e])
+            f.write("\n".join("%.17e" % v for v in rho_k[e]))
+            f.write("\n")
+            f.write("\n".join("%.17e" % v for v in C_k[e]))
+            f.write("\n")
+        for p in range(len(K_k)):
+            f.write("\n".join("%.17e" % v for v in K_k[p]))
+            f.write("\n")
+    return path
+
+
+def atomic_fix_args(flags, beta_file, kappa_file, elements, seed=12345, T_e=300.0, T_infile="NULL", inner_loops=0,
+                    T_out="NULL", group="all", style="eph/atomic"):
+    """The `fix ID group eph/atomic ...` argument vector (reference fix_eph_atomic.cpp:39-56)."""
+    return ["fx", group, style, seed, flags, repr(T_e), T_infile, inner_loops, T_out, beta_file, kappa_file] + list(elements)
+
+
 def error_metrics(got, ref, floor=0.0):
     """max |got-ref| / max |ref|  (forces are cancelling sums, so errors are scaled by the largest reference magnitude)"""
     got, ref = np.asarray(got), np.asarray(ref)

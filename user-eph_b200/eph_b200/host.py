@@ -228,15 +228,23 @@ class FixDriver:
         return x, v, f
 
     def array(self):
-        out = np.empty((self.nlocal, 8))
+        out = np.empty((self.nlocal, self.fix_flags()["size_peratom_cols"]))
         self._fn("get_array")(C.c_void_p(self.w), C.c_void_p(out.ctypes.data))
         return out
 
     def probe(self, which):
-        n = self.nlocal + self.nghost if which == 0 else 3 * self.nlocal
+        """0 rho[nt] 1 w 2 xi 3 f_EPH 4 f_RNG [nl][3]; `fix eph/atomic` adds 5 rho_a[nt] 6 E_a[nt] 7 dE_a[nl] 8 T_a[nl]"""
+        nt = self.nlocal + self.nghost
+        n = nt if which in (0, 5, 6) else self.nlocal if which in (7, 8) else 3 * self.nlocal
         out = np.empty(n)
         self._ck(self._fn("get_probe")(C.c_void_p(self.w), which, C.c_void_p(out.ctypes.data)))
-        return out if which == 0 else out.reshape(-1, 3)
+        return out.reshape(-1, 3) if which in (1, 2, 3, 4) else out
+
+    def set_energy(self, E):
+        """`fix eph/atomic` only: overwrite the per-atom electronic energies of the local atoms"""
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        assert len(E) == self.nlocal
+        self._ck(self._fn("set_energy")(C.c_void_p(self.w), C.c_void_p(E.ctypes.data)))
 
     def grid_T(self):
         out = np.empty(self._fn("grid_size")(C.c_void_p(self.w)))
