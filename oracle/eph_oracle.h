@@ -140,6 +140,55 @@ size_t orc_sizeof_atoms(void);
 double *orc_fix_ptr(orc_fix *fx, int which /*0 rho 1 w 2 xi 3 f_EPH 4 f_RNG 5 array*/);
 double orc_fix_Ee(const orc_fix *fx);
 
+/* ---- `fix eph/atomic`: EPH_kappa (eph_kappa.h) and FixEPHAtomic (fix_eph_atomic.cpp);
+ *      restated in eph_oracle_atomic.c ---- */
+typedef struct orc_kappa {
+  int n_elements, n_pairs;
+  size_t n_r, n_T;
+  double r_cutoff, r_cutoff_sq, T_max, dT, inv_dr, inv_dr_sq;
+  char names[16][16];
+  int number[16];
+  double *rho_r;    /* [n_elements][n_r][4] */
+  double *rho_r_sq; /* [n_elements][n_r][4] */
+  double *E_T;      /* [n_elements][n_T] running sum of C(T) dT (EPH_Linear y) */
+  double *K_T;      /* [n_pairs][n_T] (EPH_Linear y) */
+} orc_kappa;
+
+orc_kappa *orc_kappa_load(const char *file);
+void orc_kappa_free(orc_kappa *k);
+void orc_kappa_info(const orc_kappa *k, long long *dims /*4*/, double *scal /*5*/);
+const double *orc_kappa_table(const orc_kappa *k, int kind /*0 rho(r) 1 rho(r^2) 2 E(T) 3 K(T)*/, int e);
+
+typedef struct orc_afix {
+  int flags, groupbit, ntypes, inner_loops;
+  int type_map_beta[16], type_map_kappa[16];
+  double dt, boltz, ftm2v, eta_factor;
+  const orc_beta *beta;
+  const orc_kappa *kappa;
+  double Ee, Te;
+  size_t cap;
+  double *rho_i, *w_i, *xi_i, *f_EPH, *f_RNG, *array /*[n][12]*/;
+  double *rho_a_i, *E_a_i /*[n][2]*/, *dE_a_i, *T_a_i;
+} orc_afix;
+
+/* `a` supplies nlocal/nghost/type/mask for the constructor's per-atom initialisation (fix_eph_atomic.cpp:212-257) */
+orc_afix *orc_afix_new(int flags, int groupbit, int ntypes, const int *type_map_beta, const int *type_map_kappa, double dt,
+                       double boltz, double ftm2v, int inner_loops, double T_init, const orc_beta *beta,
+                       const orc_kappa *kappa, const orc_atoms *a);
+void orc_afix_free(orc_afix *fx);
+void orc_afix_set_dt(orc_afix *fx, double dt);
+void orc_atomic_calculate_environment(orc_afix *fx, const orc_atoms *a);
+void orc_atomic_force_prl(orc_afix *fx, const orc_atoms *a);
+void orc_atomic_heat_solve(orc_afix *fx, const orc_atoms *a);
+void orc_atomic_post_force(orc_afix *fx, const orc_atoms *a, const double *xi);
+void orc_atomic_end_of_step(orc_afix *fx, const orc_atoms *a);
+void orc_atomic_initial_integrate(orc_afix *fx, const orc_atoms *a, const double *mass_by_type);
+void orc_atomic_final_integrate(orc_afix *fx, const orc_atoms *a, const double *mass_by_type);
+/* which: 0 rho 1 w 2 xi 3 f_EPH 4 f_RNG 5 rho_a 6 E_a[n][2] 7 dE_a 8 T_a 9 array[n][12] */
+double *orc_afix_ptr(orc_afix *fx, int which);
+double orc_afix_Ee(const orc_afix *fx);
+double orc_afix_Te(const orc_afix *fx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,10 +23,11 @@ def load():
             build()
         L = C.CDLL(path)
         for n in ("orc_beta_load", "orc_beta_from_knots", "orc_fdm_new", "orc_fdm_from_file", "orc_fix_new",
-                  "orc_beta_table", "orc_fdm_field", "orc_fdm_flags", "orc_fdm_tdyn", "orc_fix_ptr"):
+                  "orc_beta_table", "orc_fdm_field", "orc_fdm_flags", "orc_fdm_tdyn", "orc_fix_ptr", "orc_kappa_load",
+                  "orc_kappa_table", "orc_afix_new", "orc_afix_ptr"):
             getattr(L, n).restype = C.c_void_p
         for n in ("orc_spline_eval", "orc_linear_eval", "orc_linear_reverse", "orc_beta_rho_r_sq", "orc_beta_alpha",
-                  "orc_beta_beta", "orc_fdm_get_T", "orc_fdm_T_total", "orc_fix_Ee"):
+                  "orc_beta_beta", "orc_fdm_get_T", "orc_fdm_T_total", "orc_fix_Ee", "orc_afix_Ee", "orc_afix_Te"):
             getattr(L, n).restype = C.c_double
         L.orc_fdm_index.restype = C.c_size_t
         L.orc_sizeof_atoms.restype = C.c_size_t
@@ -207,6 +208,99 @@ class Fix:
     def __del__(self):
         try:
             load().orc_fix_free(C.c_void_p(self.h))
+        except Exception:
+            pass
+
+
+class Kappa:
+    """Restated EPH_kappa tables (eph_kappa.h)."""
+
+    def __init__(self, path):
+        L = load()
+        self.h = L.orc_kappa_load(str(path).encode())
+        if not self.h:
+            raise RuntimeError("oracle: cannot load kappa file %r" % (path,))
+        dims = (C.c_longlong * 4)()
+        scal = (C.c_double * 5)()
+        L.orc_kappa_info(C.c_void_p(self.h), dims, scal)
+        self.n_elements, self.n_pairs, self.n_r, self.n_T = (int(d) for d in dims)
+        self.r_cutoff, self.r_cutoff_sq, self.T_max, self.inv_dr_sq, self.dT = (float(v) for v in scal)
+
+    def table(self, kind, e=0):
+        """0 rho(r) [n_r][4], 1 rho(r^2) [n_r][4], 2 E(T) [n_T], 3 K(T) of slot e [n_T]"""
+        shape = (self.n_r, 4) if kind < 2 else (self.n_T,)
+        ptr = load().orc_kappa_table(C.c_void_p(self.h), kind, e)
+        return np.array(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=shape))
+
+    def __del__(self):
+        try:
+            load().orc_kappa_free(C.c_void_p(self.h))
+        except Exception:
+            pass
+
+
+class AtomicFix(Fix):
+    """The restated FixEPHAtomic hot path on one rank (periodic ghost images), eph_oracle_atomic.c."""
+
+    def __init__(self, system, beta, kappa, flags, groupbit=1, type_map_beta=None, type_map_kappa=None, dt=1e-4,
+                 boltz=8.617343e-5, ftm2v=1.0 / 1.0364269e-4, inner_loops=0, T_init=300.0):
+        L = load()
+        self.sys, self.beta, self.kappa = system, beta, kappa
+        ntypes = int(system.get("ntypes", 1))
+        tb = np.ascontiguousarray(type_map_beta if type_map_beta is not None else list(range(ntypes)), dtype=np.int32)
+        tk = np.ascontiguousarray(type_map_kappa if type_map_kappa is not None else list(range(ntypes)), dtype=np.int32)
+        s = system
+        self.nlocal, self.nghost = s["nlocal"], s["nghost"]
+        self.x = np.ascontiguousarray(s["x"], dtype=np.float64).copy()
+        self.v = np.ascontiguousarray(s["v"], dtype=np.float64).copy()
+        self.f = np.ascontiguousarray(s["f"], dtype=np.float64).copy()
+        self.type = np.ascontiguousarray(s["type"], dtype=np.int32)
+        self.mask = np.ascontiguousarray(s["mask"], dtype=np.int32)
+        self.owner = np.ascontiguousarray(s["ghost_owner"], dtype=np.int32)
+        self.offsets = np.ascontiguousarray(s["offsets"], dtype=np.int64)
+        self.neigh = np.ascontiguousarray(s["neigh"], dtype=np.int32)
+        self.atoms = C.create_string_buffer(L.orc_sizeof_atoms())
+        self._fill()
+        self.h = L.orc_afix_new(flags, groupbit, ntypes, _p(tb), _p(tk), C.c_double(dt), C.c_double(boltz), C.c_double(ftm2v),
+                                inner_loops, C.c_double(T_init), C.c_void_p(beta.h), C.c_void_p(kappa.h), self.atoms)
+
+    def set_dt(self, dt): load().orc_afix_set_dt(C.c_void_p(self.h), C.c_double(dt))
+
+    def post_force(self, xi=None):
+        xi = None if xi is None else np.ascontiguousarray(xi, dtype=np.float64)
+        load().orc_atomic_post_force(C.c_void_p(self.h), self.atoms, _p(xi))
+
+    def end_of_step(self): load().orc_atomic_end_of_step(C.c_void_p(self.h), self.atoms)
+
+    def initial_integrate(self, mass):
+        m = np.ascontiguousarray(np.concatenate([[0.0], np.atleast_1d(mass)]), dtype=np.float64)
+        load().orc_atomic_initial_integrate(C.c_void_p(self.h), self.atoms, _p(m))
+
+    def final_integrate(self, mass):
+        m = np.ascontiguousarray(np.concatenate([[0.0], np.atleast_1d(mass)]), dtype=np.float64)
+        load().orc_atomic_final_integrate(C.c_void_p(self.h), self.atoms, _p(m))
+
+    def Ee(self): return load().orc_afix_Ee(C.c_void_p(self.h))
+    def Te(self): return load().orc_afix_Te(C.c_void_p(self.h))
+
+    def ptr(self, which):
+        """0 rho[nt] 1 w 2 xi 3 f_EPH 4 f_RNG [nl][3] 5 rho_a[nt] 6 E_a[nt] 7 dE_a[nl] 8 T_a[nl] 9 array[nl][12]"""
+        nl, nt = self.nlocal, self.nlocal + self.nghost
+        shape = {0: (nt,), 1: (nt, 3), 2: (nt, 3), 3: (nt, 3), 4: (nt, 3), 5: (nt,), 6: (nt, 2), 7: (nt,), 8: (nt,), 9: (nt, 12)}[which]
+        p = load().orc_afix_ptr(C.c_void_p(self.h), which)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=shape)
+        if which in (0, 5):
+            return a
+        if which == 6:
+            return a[:, 0]
+        return a[:nl]
+
+    def set_energy(self, E):
+        self.ptr(6)[: self.nlocal] = E
+
+    def __del__(self):
+        try:
+            load().orc_afix_free(C.c_void_p(self.h))
         except Exception:
             pass
 

@@ -1,0 +1,97 @@
+"""`fix eph/atomic`: pins the C restatement (oracle/eph_oracle_atomic.c) bit for bit against the
+UNMODIFIED reference fix_eph_atomic.cpp / eph_kappa.h compiled into oracle/_ref/libeph_atomic_ref.so, and against the
+committed golden vectors generated from it (tests/golden/make_golden_atomic.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from eph_b200 import harness as H
+from oracle import oracle as O
+
+import traj
+from conftest import GOLDEN, REFERENCE
+
+KAPPA = os.path.join(GOLDEN, "synth1.kappa")
+BETA = os.path.join(GOLDEN, "Ni_trunc.beta")
+KEYS = ("f", "array", "Ee", "Te", "rho", "w", "f_eph", "f_rng", "rho_a", "E", "dE", "x", "v")
+
+
+@pytest.fixture(scope="module")
+def refa():
+    from oracle import reference
+    if not reference.atomic_available():
+        pytest.skip("oracle/_ref/libeph_atomic_ref.so not built (needs /root/reference at build time)")
+    return reference
+
+
+@pytest.mark.parametrize("path", [KAPPA, os.path.join(REFERENCE, "Tests/EPH_kappa/Cu.kappa"),
+                                  os.path.join(REFERENCE, "Tests/EPH_atomic_run/heat_diffusion/Ni.kappa")])
+def test_kappa_tables_bit_exact(refa, path):
+    if not os.path.exists(path):
+        pytest.skip("reference data tree not present")
+    kr, ko = refa.Kappa(path), O.Kappa(path)
+    for a in ("n_elements", "n_pairs", "n_r", "n_T", "r_cutoff", "r_cutoff_sq", "T_max", "inv_dr_sq", "dT"):
+        assert getattr(kr, a) == getattr(ko, a), a
+    for kind in range(4):
+        assert np.array_equal(kr.table(kind), ko.table(kind)), kind
+    if path.endswith("Cu.kappa"):   # the one expectation of the reference's Tests/EPH_kappa/test.cpp:17
+        assert kr.n_elements == 1
+
+
+CASES = [(7, 0, None), (7, 3, None), (1, 0, None), (2, 0, None), (3, 0, None), (5, 2, None), (6, 1, None),
+         (7 + 16, 2, None), (7 + 32, 2, None), (7 + 8, 1, None), (7, 2, 0.7)]
+
+
+@pytest.mark.parametrize("flags,loops,group_fraction", CASES)
+def test_atomic_trajectory_bit_exact(refa, flags, loops, group_fraction):
+    s = H.make_system(3, group_fraction=group_fraction)
+    group, gb = ("bit1", 2) if group_fraction else ("all", 1)
+    drv = refa.atomic_fix_driver(s, H.atomic_fix_args(flags, BETA, KAPPA, ["Ni"], inner_loops=loops, group=group))
+    fx = O.AtomicFix(s, O.Beta(path=BETA), O.Kappa(KAPPA), flags, groupbit=gb, inner_loops=loops)
+    assert drv.fix_flags()["size_peratom_cols"] == 12 and drv.neigh_cutoff() == 5.0
+    xis = [np.random.default_rng(i).normal(size=(s["nlocal"], 3)) if flags & 2 else None for i in range(3)]
+    a = traj.run_atomic_fix_driver(drv, s, xis)
+    b = traj.run_atomic_oracle(fx, s, xis, [58.71])
+    in_group = (s["mask"][: s["nlocal"]] & gb) != 0
+    for step, (ra, rb) in enumerate(zip(a, b)):
+        for k in ra:
+            if k == "T":   # T_a_i of atoms outside the group is never written by the reference (uninitialised storage)
+                assert np.array_equal(ra[k][in_group], rb[k][in_group]), (step, k)
+            else:
+                assert np.array_equal(np.asarray(ra[k]), np.asarray(rb[k])), (step, k)
+    if flags & 4 and flags & 3:
+        assert a[-1]["Ee"] != a[0]["Ee"]          # the electronic energy moved
+
+
+def test_atomic_heat_diffusion_from_gradient_bit_exact(refa):
+    """heat_solve alone (flags 4): an energy gradient relaxes, the group's total energy is conserved to rounding
+    except for what the one-sided clamp at zero adds"""
+    s = H.make_system(3)
+    drv = refa.atomic_fix_driver(s, H.atomic_fix_args(4, BETA, KAPPA, ["Ni"], inner_loops=4))
+    fx = O.AtomicFix(s, O.Beta(path=BETA), O.Kappa(KAPPA), 4, inner_loops=4)
+    E0 = drv.probe(6)[: s["nlocal"]] * (1.0 + 0.8 * np.sin(2 * np.pi * s["x"][: s["nlocal"], 0] / s["box"][0]))
+    drv.set_energy(E0)
+    fx.set_energy(E0)
+    a = traj.run_atomic_fix_driver(drv, s, [None] * 4)
+    b = traj.run_atomic_oracle(fx, s, [None] * 4, [58.71])
+    for ra, rb in zip(a, b):
+        for k in ("E", "T", "Ee", "Te", "array"):
+            assert np.array_equal(np.asarray(ra[k]), np.asarray(rb[k])), k
+    assert np.std(a[-1]["T"]) < np.std(a[0]["T"])
+    assert abs(a[-1]["Ee"] - np.sum(E0)) < 1e-3 * np.sum(E0)
+
+
+@pytest.mark.parametrize("name", ["atomic_caseA", "atomic_caseB_group"])
+def test_atomic_oracle_matches_committed_golden_vectors(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = traj.system_from_golden(g)
+    gb = int(g["groupbit"])
+    fx = O.AtomicFix(s, O.Beta(path=BETA), O.Kappa(KAPPA), int(g["flags"]), groupbit=gb, inner_loops=int(g["inner_loops"]),
+                     dt=float(g["dt"]))
+    if "E0" in g.files:
+        fx.set_energy(g["E0"])
+    recs = traj.run_atomic_oracle(fx, s, list(g["xi"]), [58.71])
+    for k in KEYS:
+        got = np.array([r[k] for r in recs])
+        assert np.array_equal(got, g["out_" + k]), k

@@ -119,3 +119,55 @@ def run_engine(eng, system, xis, mass, dt, device=False, ftm2v=1.0 / 1.0364269e-
                         Tmean=eng.mean_T(), w=eng.probe(1), rho=eng.probe(0), f_eph=eng.probe(3), f_rng=eng.probe(4),
                         xi=eng.probe(2)))
     return out
+
+
+# ---------------------------------------------------------------------------
+# `fix eph/atomic`: the same Verlet sequence, with the per-atom electronic state in the records
+# ---------------------------------------------------------------------------
+def run_atomic_fix_driver(drv, system, xis):
+    sync = GhostSync(system)
+    nl = sync.nl
+    out = []
+    for step, xi in enumerate(xis, start=1):
+        drv.set_step(step)
+        x, v, f = drv.xvf()
+        f[:] = 0.0
+        drv.update(f=f)
+        drv.initial_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(x=x, v=v)
+        if xi is not None:
+            drv.set_xi(xi)
+        drv.post_force()
+        drv.final_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(v=v)
+        drv.end_of_step()
+        x, v, f = drv.xvf()
+        out.append(dict(x=x[:nl].copy(), v=v[:nl].copy(), f=f[:nl].copy(), array=drv.array().copy(), Ee=drv.compute_vector(0),
+                        Te=drv.compute_vector(1), rho=drv.probe(0).copy(), w=drv.probe(1).copy(), f_eph=drv.probe(3).copy(),
+                        f_rng=drv.probe(4).copy(), rho_a=drv.probe(5).copy(), E=drv.probe(6)[:nl].copy(),
+                        dE=drv.probe(7).copy(), T=drv.probe(8).copy()))
+    return out
+
+
+def run_atomic_oracle(fix, system, xis, mass):
+    """fix: oracle.oracle.AtomicFix"""
+    sync = GhostSync(system)
+    nl = sync.nl
+    out = []
+    for xi in xis:
+        fix.f[:] = 0.0
+        fix.initial_integrate(mass)
+        sync(fix.x, fix.v)
+        fix.post_force(xi)
+        fix.final_integrate(mass)
+        sync(fix.x, fix.v)
+        fix.end_of_step()
+        out.append(dict(x=fix.x[:nl].copy(), v=fix.v[:nl].copy(), f=fix.f[:nl].copy(), array=np.array(fix.ptr(9)), Ee=fix.Ee(),
+                        Te=fix.Te(), rho=np.array(fix.ptr(0)), w=np.array(fix.ptr(1)), f_eph=np.array(fix.ptr(3)),
+                        f_rng=np.array(fix.ptr(4)), rho_a=np.array(fix.ptr(5)), E=np.array(fix.ptr(6)[:nl]),
+                        dE=np.array(fix.ptr(7)), T=np.array(fix.ptr(8))))
+    return out
