@@ -1,0 +1,135 @@
+"""Parity cases of the `fix eph/atomic` device path against the oracle, shared by the `-m gpu` tests (the CUDA build on
+a B200) and tests/test_atomic_emulated.py (the same source compiled for the host, tests/emul).  Every function takes
+`make_engine(type_map_beta, type_map_kappa, flags, **kw)` returning an eph_b200.atomic.AtomicEngine, and where the host
+class is involved `make_fix(system, args)` returning a FixDriver of FixEPHAtomicB200."""
+import os
+
+import numpy as np
+
+from eph_b200 import harness as H
+from eph_b200 import host
+from oracle import oracle as O
+
+import traj
+from conftest import GOLDEN
+
+KAPPA = os.path.join(GOLDEN, "synth1.kappa")
+BETA = os.path.join(GOLDEN, "Ni_trunc.beta")
+TOL = 1e-10   # north star: relative, forces and energies scaled by the largest reference magnitude
+KEYS = ("f", "array", "rho", "w", "f_eph", "f_rng", "rho_a", "E", "dE", "T", "x", "v")
+
+
+def setup_engine(eng, s, beta_path, kappa_tables, dt=1e-4, T_init=300.0):
+    eng.set_tables_from(host.BetaTables(path=beta_path), kappa_tables)
+    eng.set_dt(dt)
+    eng.set_atoms(s["nlocal"], s["nghost"], np.ascontiguousarray(s["type"], dtype=np.int32),
+                  np.ascontiguousarray(s["mask"], dtype=np.int32), np.ascontiguousarray(s["tag"], dtype=np.int64),
+                  np.ascontiguousarray(s["ghost_owner"], dtype=np.int32))
+    eng.set_neighbors(np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32))
+    eng.init_energy(T_init)
+    return eng
+
+
+def compare(recs, refs, in_group=None):
+    worst = 0.0
+    for step, (a, b) in enumerate(zip(recs, refs)):
+        for k in KEYS:
+            got, ref = np.asarray(a[k]), np.asarray(b[k])
+            if k == "T" and in_group is not None:
+                got, ref = got[in_group], ref[in_group]
+            assert np.all(np.isfinite(got)), (step, k)
+            err = H.error_metrics(got, ref)
+            assert err < TOL, (step, k, err)
+            worst = max(worst, err)
+        for k in ("Ee", "Te"):
+            assert abs(a[k] - b[k]) <= TOL * abs(b[k]), (step, k, a[k], b[k])
+    return worst
+
+
+def trajectory_case(make_engine, kappa_tables, flags, loops, group_fraction=None, n=3, steps=3, ntypes=1, beta=BETA,
+                    names=("Ni",)):
+    s = H.make_system(n, group_fraction=group_fraction, ntypes=ntypes)
+    gb = 2 if group_fraction else 1
+    tm = list(range(ntypes)) if len(names) > 1 else [0] * ntypes
+    eng = setup_engine(make_engine(tm, [0] * ntypes, flags, groupbit=gb, inner_loops=loops), s, beta, kappa_tables)
+    fx = O.AtomicFix(s, O.Beta(path=beta), O.Kappa(KAPPA), flags, groupbit=gb, inner_loops=loops, type_map_beta=tm,
+                     type_map_kappa=[0] * ntypes)
+    # the constructor's sums (fix_eph_atomic.cpp:223-253)
+    Ee0, Te0 = eng.summary()
+    assert abs(Ee0 - fx.Ee()) <= TOL * abs(fx.Ee()) and abs(Te0 - fx.Te()) <= TOL * abs(fx.Te())
+    xis = [np.random.default_rng(10 + i).normal(size=(s["nlocal"], 3)) if flags & 2 else None for i in range(steps)]
+    mass = [58.71] * ntypes
+    recs = traj.run_atomic_engine(eng, s, xis, mass, 1e-4, groupbit=gb, noint=bool(flags & 8))
+    refs = traj.run_atomic_oracle(fx, s, xis, mass)
+    in_group = (s["mask"][: s["nlocal"]] & gb) != 0
+    worst = compare(recs, refs, in_group)
+    assert eng.launch_count() > 0
+    return worst
+
+
+def gradient_case(make_engine, kappa_tables):
+    """heat diffusion alone (flags 4) from an energy gradient, 4 inner loops"""
+    s = H.make_system(3)
+    eng = setup_engine(make_engine([0], [0], 4, inner_loops=4), s, BETA, kappa_tables)
+    fx = O.AtomicFix(s, O.Beta(path=BETA), O.Kappa(KAPPA), 4, inner_loops=4)
+    E0 = np.array(fx.ptr(6)[: s["nlocal"]]) * (1.0 + 0.8 * np.sin(2 * np.pi * s["x"][: s["nlocal"], 0] / s["box"][0]))
+    eng.set_energy(np.ascontiguousarray(E0))
+    fx.set_energy(E0)
+    recs = traj.run_atomic_engine(eng, s, [None] * 4, [58.71], 1e-4)
+    refs = traj.run_atomic_oracle(fx, s, [None] * 4, [58.71])
+    compare(recs, refs)
+    assert np.std(recs[-1]["T"]) < np.std(recs[0]["T"])
+
+
+def golden_engine_case(make_engine, kappa_tables, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = traj.system_from_golden(g)
+    gb = int(g["groupbit"])
+    eng = setup_engine(make_engine([0], [0], int(g["flags"]), groupbit=gb, inner_loops=int(g["inner_loops"])), s, BETA,
+                       kappa_tables, dt=float(g["dt"]))
+    if "E0" in g.files:
+        eng.set_energy(np.ascontiguousarray(g["E0"]))
+    recs = traj.run_atomic_engine(eng, s, list(g["xi"]), [58.71], float(g["dt"]), groupbit=gb)
+    for k in ("f", "array", "rho", "w", "f_eph", "f_rng", "rho_a", "E", "dE", "x", "v"):
+        got = np.array([r[k] for r in recs])
+        assert H.error_metrics(got, g["out_" + k]) < TOL, k
+    for k in ("Ee", "Te"):
+        got = np.array([r[k] for r in recs])
+        assert np.all(np.abs(got - g["out_" + k]) <= TOL * np.abs(g["out_" + k])), k
+
+
+def golden_fix_case(make_fix, name):
+    """the committed golden vectors through FixEPHAtomicB200 (constructor syntax, hooks, outputs)"""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    s = traj.system_from_golden(g)
+    group = "bit1" if int(g["groupbit"]) == 2 else "all"
+    args = H.atomic_fix_args(int(g["flags"]), BETA, KAPPA, ["Ni"], inner_loops=int(g["inner_loops"]), group=group,
+                             style="eph/atomic/b200") + ["rng", "mars"]
+    drv = make_fix(s, args)
+    fl = drv.fix_flags()
+    assert fl["size_peratom_cols"] == 12 and fl["comm_forward"] == 3 and fl["ghost_velocity"] == 1 and drv.neigh_cutoff() == 5.0
+    if "E0" in g.files:
+        drv.set_energy(np.ascontiguousarray(g["E0"]))
+    recs = traj.run_atomic_fix_driver(drv, s, list(g["xi"]))
+    for k in ("f", "array", "rho", "w", "f_eph", "f_rng", "rho_a", "E", "dE", "x", "v"):
+        got = np.array([r[k] for r in recs])
+        assert H.error_metrics(got, g["out_" + k]) < TOL, k
+    for k in ("Ee", "Te"):
+        got = np.array([r[k] for r in recs])
+        assert np.all(np.abs(got - g["out_" + k]) <= TOL * np.abs(g["out_" + k])), k
+
+
+def philox_case(make_engine, kappa_tables):
+    """built-in Gaussian stream: xi of a step is the pinned Philox definition keyed on (seed, tag, step), and the run
+    equals one with that stream injected"""
+    s = H.make_system(3)
+    a = setup_engine(make_engine([0], [0], 7, seed=777, inner_loops=1), s, BETA, kappa_tables)
+    b = setup_engine(make_engine([0], [0], 7, seed=777, inner_loops=1), s, BETA, kappa_tables)
+    tags = np.ascontiguousarray(s["tag"][: s["nlocal"]], dtype=np.int64)
+    xis = [O.xi_stream(777, step, tags) for step in (1, 2)]
+    ra = traj.run_atomic_engine(a, s, [None, None], [58.71], 1e-4)   # None with RANDOM set -> built-in stream
+    rb = traj.run_atomic_engine(b, s, xis, [58.71], 1e-4)
+    for x, y, xi in zip(ra, rb, xis):
+        assert H.error_metrics(x["xi"], xi) < 1e-13
+        for k in ("f", "E", "dE", "f_rng"):
+            assert H.error_metrics(x[k], y[k]) < 1e-12, k

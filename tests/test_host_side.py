@@ -227,3 +227,56 @@ def test_bench_and_entry_points_parse_without_a_gpu():
     sys.path.insert(0, ROOT)
     g = importlib.import_module("__graft_entry__")
     assert callable(g.build) and callable(g.smoke)
+
+
+# ---- `fix eph/atomic` boundary (include/eph_b200_atomic.h) ----
+def test_atomic_library_exports_every_declared_symbol():
+    from eph_b200 import atomic as A
+    hdr = open(os.path.join(ROOT, "include", "eph_b200_atomic.h")).read()
+    declared = set(re.findall(r"\b(eph_b200_atomic_[A-Za-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    L = A.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert declared == set(A.SYMBOLS), declared ^ set(A.SYMBOLS)
+
+
+def test_atomic_no_cpu_fallback_and_argument_errors():
+    from eph_b200 import atomic as A
+    from eph_b200 import harness as H
+    if not gpu_available():
+        with pytest.raises(lib.EphError) as e:
+            A.AtomicEngine([0], [0], 7)
+        assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+    # the host class parses the reference's command line up to the creation of the device engine
+    s = H.make_system(2)
+    kappa = os.path.join(ROOT, "tests", "golden", "synth1.kappa")
+    beta = os.path.join(ROOT, "tests", "golden", "Ni_trunc.beta")
+    good = H.atomic_fix_args(7, beta, kappa, ["Ni"], style="eph/atomic/b200")
+    for bad, msg in ((good[:11], "too few arguments"), (good[:-1] + ["Xx"], "elements not found"),
+                     (good[:9] + ["/nonexistent.beta"] + good[10:], "cannot open beta file"),
+                     (good[:10] + ["/nonexistent.kappa"] + good[11:], "cannot open kappa file"),
+                     (good + ["rng", "bad"], "rng must be")):
+        with pytest.raises(host.FixError) as e:
+            A.fix_driver(s, bad)
+        assert msg in str(e.value), (msg, str(e.value))
+    if not gpu_available():
+        with pytest.raises(host.FixError) as e:
+            A.fix_driver(s, good)
+        assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_atomic_kappa_tables_match_oracle_bit_for_bit():
+    from eph_b200 import atomic as A
+    from oracle import oracle as O
+    path = os.path.join(ROOT, "tests", "golden", "synth1.kappa")
+    kp, ko = A.KappaTables(path), O.Kappa(path)
+    for a in ("n_elements", "n_pairs", "n_r", "n_T", "r_cutoff", "r_cutoff_sq", "T_max", "inv_dr_sq", "dT"):
+        assert getattr(kp, a) == getattr(ko, a), a
+    for kind in range(4):
+        assert np.array_equal(kp.table(kind), ko.table(kind)), kind
+    assert kp.name(0) == "Ni"
+    q = np.linspace(0.0, 900.0, 37)
+    assert np.array_equal(kp.linear(0, q), O.linear_eval(ko.dT, ko.table(2), q))
+    E = O.linear_eval(ko.dT, ko.table(2), q)
+    assert np.array_equal(kp.linear(0, E, reverse=True), O.linear_eval(ko.dT, ko.table(2), E, reverse=True))

@@ -171,3 +171,31 @@ def run_atomic_oracle(fix, system, xis, mass):
                         f_rng=np.array(fix.ptr(4)), rho_a=np.array(fix.ptr(5)), E=np.array(fix.ptr(6)[:nl]),
                         dE=np.array(fix.ptr(7)), T=np.array(fix.ptr(8))))
     return out
+
+
+def run_atomic_engine(eng, system, xis, mass, dt, groupbit=1, noint=False, ftm2v=1.0 / 1.0364269e-4):
+    """eng: eph_b200.atomic.AtomicEngine with tables/dt/atoms/neighbours/energies set.  Drives the C ABI with host
+    arrays; the velocity-Verlet half steps are the host loops of FixEPHAtomicB200."""
+    sync = GhostSync(system)
+    nl = sync.nl
+    x = np.ascontiguousarray(system["x"], dtype=np.float64).copy()
+    v = np.ascontiguousarray(system["v"], dtype=np.float64).copy()
+    f = np.zeros((nl, 3))
+    g = (np.asarray(system["mask"][:nl]) & groupbit) != 0
+    dtfm = (0.5 * dt * ftm2v / np.atleast_1d(mass)[np.asarray(system["type"][:nl]) - 1])[:, None]
+    out = []
+    for step, xi in enumerate(xis, start=1):
+        f[...] = 0.0
+        if not noint:
+            v[:nl][g] += (dtfm * f)[g]
+            x[:nl][g] += dt * v[:nl][g]
+        sync(x, v)
+        eng.post_force(x, v, f, None if xi is None else np.ascontiguousarray(xi), step)
+        if not noint:
+            v[:nl][g] += (dtfm * f)[g]
+        sync(x, v)
+        Ee, Te = eng.end_of_step()
+        out.append(dict(x=x[:nl].copy(), v=v[:nl].copy(), f=f.copy(), array=eng.peratom(), Ee=Ee, Te=Te, rho=eng.probe(0),
+                        w=eng.probe(1), f_eph=eng.probe(3), f_rng=eng.probe(4), rho_a=eng.probe(5), E=eng.probe(6)[:nl],
+                        dE=eng.probe(7), T=eng.probe(8), xi=eng.probe(2)))
+    return out

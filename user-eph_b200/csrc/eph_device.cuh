@@ -23,16 +23,24 @@ __device__ __forceinline__ unsigned double_to_bits(double w) { return static_cas
 // One 256-bit load (LDG.E.256 on sm_100a) of a 32-byte record through the
 // read-only path: a gathered record costs one L1TEX request instead of two.
 __device__ __forceinline__ double4 ld256(const double4 *p) {
+#ifdef EPHA_HOST_EMULATION   // tests/emul: this header compiled for the host (test infrastructure only)
+  return *p;
+#else
   double4 r;
   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
+#endif
 }
 
 // First half of a 32-byte record (LDG.128 through the read-only path).
 __device__ __forceinline__ double2 ld128(const double4 *p) {
+#ifdef EPHA_HOST_EMULATION
+  return double2{p->x, p->y};
+#else
   double2 r;
   asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
+#endif
 }
 
 // Streams that are read or written exactly once per pass (list indices, pair weights): evict-first hints keep
@@ -76,6 +84,9 @@ __device__ __forceinline__ double spline_eval(const double2 *__restrict__ tab, d
 // 1/x to full double precision without the slow-path branches of the generic
 // division (x is a squared distance: finite, positive, far from the range ends).
 __device__ __forceinline__ double fast_rcp(double x) {
+#ifdef EPHA_HOST_EMULATION
+  return 1.0 / x;
+#else
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   // rcp.approx.f64 is good to ~2^-23; two Newton steps square that twice.
@@ -84,6 +95,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   return y;
+#endif
 }
 
 // Philox4x32-10, identical to the definition pinned in oracle/eph_oracle.c.
