@@ -117,6 +117,17 @@ int eph_b200_last_substeps(eph_b200_handle *h, int *out);
 /* Replaces FixEPH::reset_dt and EPH_FDM::set_dt (fix_eph.cpp:909-916, eph_fdm.h:155-158) */
 int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz);
 
+/* `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): eph_model 4 with an exponential memory kernel of time constant
+ * tau0 (its arg[5]) on both forces, f <- f_prev (1 - zeta) + zeta f_new, zeta = 1 - exp(-dt / tau0) (:190, :563-569,
+ * :619-625, :686), applied to group atoms with rho_i > 0; the filtered forces are what is added to f, deposited into the
+ * grid and reported per atom.  tau0 <= 0 switches the filter off.  get/set_colour_state move the filter's per-atom state
+ * (f_dis, f_sto: [nlocal][3] each), which migrates with the atoms (pack_exchange / unpack_exchange / copy_arrays,
+ * :793-825): new storage starts from zero, set_atoms keeps the values of a registration of the same size, and a caller
+ * whose atoms were re-ordered registers them again after set_atoms. */
+int eph_b200_set_colour(eph_b200_handle *h, double tau0);
+int eph_b200_get_colour_state(eph_b200_handle *h, double *f_dis, double *f_sto, int memspace);
+int eph_b200_set_colour_state(eph_b200_handle *h, const double *f_dis, const double *f_sto, int memspace);
+
 /* LAMMPS' neighbor->skin and the skin of the device-side inner list (two-level Verlet list: the sweeps walk a
  * list cut at r_c + inner_skin that the device rebuilds from LAMMPS' list; a device-side displacement check falls
  * back to LAMMPS' list whenever the inner one could be incomplete, so results never depend on this setting).

@@ -581,12 +581,14 @@ orc_fix *orc_fix_new(int flags, int model, int groupbit, int ntypes, const int *
 
 void orc_fix_free(orc_fix *fx) {
   if (!fx) return;
-  free(fx->rho_i); free(fx->w_i); free(fx->xi_i); free(fx->f_EPH); free(fx->f_RNG); free(fx->array); free(fx);
+  free(fx->rho_i); free(fx->w_i); free(fx->xi_i); free(fx->f_EPH); free(fx->f_RNG); free(fx->array);
+  free(fx->f_dis_i); free(fx->f_sto_i); free(fx);
 }
 
 void orc_fix_set_dt(orc_fix *fx, double dt) { /* fix_eph.cpp:909-916 */
   fx->dt = dt;
   fx->eta_factor = sqrt(2.0 * fx->boltz / dt);
+  if (fx->coloured) fx->zeta_factor = 1.0 - exp(-dt / fx->tau0); /* fix_eph_coloured_exp.cpp:686 */
   if (fx->fdm) orc_fdm_set_dt(fx->fdm, dt);
 }
 
@@ -595,8 +597,17 @@ static void fix_resize(orc_fix *fx, size_t n) { /* grow_arrays, fix_eph.cpp:918-
 #define GROW(p, w) do { p = (double *)realloc(p, sizeof(double) * (w) * n); \
     memset(p + (w) * fx->cap, 0, sizeof(double) * (w) * (n - fx->cap)); } while (0)
   GROW(fx->rho_i, 1); GROW(fx->w_i, 3); GROW(fx->xi_i, 3); GROW(fx->f_EPH, 3); GROW(fx->f_RNG, 3); GROW(fx->array, 8);
+  GROW(fx->f_dis_i, 3); GROW(fx->f_sto_i, 3);
 #undef GROW
   fx->cap = n;
+}
+
+/* `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): the same path with an exponential memory kernel on both forces,
+ * zeta_factor = 1 - exp(-dt / tau0) (:190, :686); tau0 <= 0 switches it off */
+void orc_fix_set_colour(orc_fix *fx, double tau0) {
+  fx->tau0 = tau0;
+  fx->coloured = tau0 > 0.0;
+  fx->zeta_factor = fx->coloured ? 1.0 - exp(-fx->dt / tau0) : 0.0;
 }
 
 static double dist_sq(const double *x, const double *y) { /* fix_eph.h:174-181 */
@@ -688,6 +699,14 @@ void orc_force_prl(orc_fix *fx, const orc_atoms *a) { /* fix_eph.cpp:687-837 */
         fx->f_EPH[3 * (size_t)i + 1] -= dvar * e_ij[1];
         fx->f_EPH[3 * (size_t)i + 2] -= dvar * e_ij[2];
       }
+      if (fx->coloured) { /* fix_eph_coloured_exp.cpp:563-569 */
+        int d;
+        for (d = 0; d < 3; ++d) {
+          double *fd = fx->f_dis_i + 3 * (size_t)i + d;
+          *fd = *fd * (1. - fx->zeta_factor) + fx->zeta_factor * fx->f_EPH[3 * (size_t)i + d];
+          fx->f_EPH[3 * (size_t)i + d] = *fd;
+        }
+      }
     }
   }
   if (fx->flags & ORC_RANDOM) { /* :791-836 */
@@ -719,6 +738,14 @@ void orc_force_prl(orc_fix *fx, const orc_atoms *a) { /* fix_eph.cpp:687-837 */
       fx->f_RNG[3 * (size_t)i + 0] *= var;
       fx->f_RNG[3 * (size_t)i + 1] *= var;
       fx->f_RNG[3 * (size_t)i + 2] *= var;
+      if (fx->coloured) { /* fix_eph_coloured_exp.cpp:619-625 */
+        int d;
+        for (d = 0; d < 3; ++d) {
+          double *fs = fx->f_sto_i + 3 * (size_t)i + d;
+          *fs = *fs * (1. - fx->zeta_factor) + fx->zeta_factor * fx->f_RNG[3 * (size_t)i + d];
+          fx->f_RNG[3 * (size_t)i + d] = *fs;
+        }
+      }
     }
   }
 }
@@ -882,7 +909,8 @@ size_t orc_sizeof_atoms(void) { return sizeof(orc_atoms); }
 double *orc_fix_ptr(orc_fix *fx, int which) {
   switch (which) {
     case 0: return fx->rho_i; case 1: return fx->w_i; case 2: return fx->xi_i;
-    case 3: return fx->f_EPH; case 4: return fx->f_RNG; default: return fx->array;
+    case 3: return fx->f_EPH; case 4: return fx->f_RNG; case 6: return fx->f_dis_i; case 7: return fx->f_sto_i;
+    default: return fx->array;
   }
 }
 double orc_fix_Ee(const orc_fix *fx) { return fx->Ee; }

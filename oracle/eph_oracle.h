@@ -108,12 +108,17 @@ typedef struct orc_fix {
   /* per-atom state, sized by orc_fix_resize */
   size_t cap;
   double *rho_i, *w_i, *xi_i, *f_EPH, *f_RNG, *array;
+  /* fix eph/coloured/exp (fix_eph_coloured_exp.cpp): exponential memory kernel on both forces */
+  int coloured;
+  double tau0, zeta_factor;
+  double *f_dis_i, *f_sto_i; /* [n][3] filtered friction / random force, carried from step to step */
 } orc_fix;
 
 orc_fix *orc_fix_new(int flags, int model, int groupbit, int ntypes, const int *type_map, double dt, double boltz,
                      double ftm2v, const orc_beta *beta, orc_fdm *fdm);
 void orc_fix_free(orc_fix *fx);
 void orc_fix_set_dt(orc_fix *fx, double dt);
+void orc_fix_set_colour(orc_fix *fx, double tau0);
 
 typedef struct orc_atoms {
   int nlocal, nghost;
@@ -137,7 +142,7 @@ void orc_final_integrate(orc_fix *fx, const orc_atoms *a, const double *mass_by_
 void orc_atoms_fill(orc_atoms *a, int nlocal, int nghost, double *x, double *v, double *f, const int *type,
                     const int *mask, const int *ghost_owner, const long long *offsets, const int *neigh);
 size_t orc_sizeof_atoms(void);
-double *orc_fix_ptr(orc_fix *fx, int which /*0 rho 1 w 2 xi 3 f_EPH 4 f_RNG 5 array*/);
+double *orc_fix_ptr(orc_fix *fx, int which /*0 rho 1 w 2 xi 3 f_EPH 4 f_RNG 5 array 6 f_dis 7 f_sto*/);
 double orc_fix_Ee(const orc_fix *fx);
 
 /* ---- `fix eph/atomic`: EPH_kappa (eph_kappa.h) and FixEPHAtomic (fix_eph_atomic.cpp);

@@ -182,6 +182,10 @@ class Fix:
 
     def set_dt(self, dt): load().orc_fix_set_dt(C.c_void_p(self.h), C.c_double(dt))
 
+    def set_colour(self, tau0):
+        """`fix eph/coloured/exp`: exponential memory kernel with time constant tau0 on both forces"""
+        load().orc_fix_set_colour(C.c_void_p(self.h), C.c_double(tau0))
+
     def post_force(self, xi=None):
         xi = None if xi is None else np.ascontiguousarray(xi, dtype=np.float64)
         load().orc_post_force(C.c_void_p(self.h), self.atoms, _p(xi))
@@ -200,7 +204,7 @@ class Fix:
 
     def ptr(self, which):
         nl, nt = self.nlocal, self.nlocal + self.nghost
-        shape = {0: (nt,), 1: (nt, 3), 2: (nt, 3), 3: (nt, 3), 4: (nt, 3), 5: (nt, 8)}[which]
+        shape = {0: (nt,), 1: (nt, 3), 2: (nt, 3), 3: (nt, 3), 4: (nt, 3), 5: (nt, 8), 6: (nt, 3), 7: (nt, 3)}[which]
         p = load().orc_fix_ptr(C.c_void_p(self.h), which)
         a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=shape)
         return a if which == 0 else a[:nl]

@@ -198,3 +198,25 @@ class Kappa:
             load_atomic().refa_kappa_free(C.c_void_p(self.h))
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------
+# the unmodified `fix eph/coloured/exp` (oracle/_ref/libeph_coloured_ref.so, oracle/ref/ref_coloured_driver.cpp)
+# ---------------------------------------------------------------------------
+PATH_COLOURED = os.path.join(HERE, "_ref", "libeph_coloured_ref.so")
+_clib = None
+
+
+def coloured_available():
+    return os.path.exists(PATH_COLOURED)
+
+
+def coloured_fix_driver(system, fix_args, dt=1e-4, mass=None):
+    """The unmodified FixEPHColouredExp inside the LAMMPS stand-in; probes 5 / 6 are f_dis / f_sto [nlocal][3]."""
+    global _clib
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "user-eph_b200"))
+    from eph_b200.host import FixDriver
+    if _clib is None:
+        _clib = C.CDLL(PATH_COLOURED)
+    return FixDriver(system, fix_args, dt=dt, lib=_clib, prefix="refc", mass=mass)

@@ -250,6 +250,7 @@ class Fix : protected Pointers {
   int vector_flag = 0, size_vector = 0, global_freq = 0, extvector = 0, nevery = 1;
   int peratom_flag = 0, size_peratom_cols = 0, peratom_freq = 0;
   int comm_forward = 0, time_integrate = 0;
+  int maxexchange = 0;   // doubles per atom in pack_exchange (fix eph/coloured/exp carries its two filtered forces)
   double **array_atom = nullptr;
   double *vector_atom = nullptr;
 

@@ -280,3 +280,17 @@ def test_atomic_kappa_tables_match_oracle_bit_for_bit():
     assert np.array_equal(kp.linear(0, q), O.linear_eval(ko.dT, ko.table(2), q))
     E = O.linear_eval(ko.dT, ko.table(2), q)
     assert np.array_equal(kp.linear(0, E, reverse=True), O.linear_eval(ko.dT, ko.table(2), E, reverse=True))
+
+
+def test_coloured_fix_command_line_without_a_gpu(sys500, ni_trunc_beta):
+    """`fix eph/coloured/exp/b200`: same argument positions as the reference fork, arg[5] = tau0 (fix_eph_coloured_exp.cpp:43)"""
+    good = H.fix_args(7, ni_trunc_beta, ["Ni"], model="5e-4", grid=(2, 2, 2), style="eph/coloured/exp/b200")
+    with pytest.raises(host.FixError, match="tau0 must be positive"):
+        host.FixDriver(sys500, H.fix_args(7, ni_trunc_beta, ["Ni"], model="0", grid=(2, 2, 2), style="eph/coloured/exp/b200"))
+    with pytest.raises(host.FixError, match="too few arguments"):
+        host.FixDriver(sys500, good[:17])
+    if gpu_available():
+        host.FixDriver(sys500, good).close()
+    else:
+        with pytest.raises(host.FixError, match="no CUDA device|CUDA"):
+            host.FixDriver(sys500, good)

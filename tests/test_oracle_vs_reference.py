@@ -272,3 +272,53 @@ def test_reference_fdm_golden_files_loose(test):
             assert len(gold) == n
             err = np.max(np.abs(o.field(0) - gold[:, 3]) / np.abs(gold[:, 3]))
             assert err < 2e-3, (i, err)
+
+
+# ---- `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): model 4 with an exponential memory kernel on both forces ----
+@pytest.fixture(scope="module")
+def refc():
+    from oracle import reference
+    if not reference.coloured_available():
+        pytest.skip("oracle/_ref/libeph_coloured_ref.so not built (needs /root/reference at build time)")
+    return reference
+
+
+@pytest.mark.parametrize("flags,group_fraction", [(7, None), (3, None), (1, None), (2, None), (7 + 16, None), (7 + 32, None), (7, 0.6)])
+def test_coloured_exp_trajectory_bit_exact(refc, ni_trunc_beta, flags, group_fraction):
+    s = H.make_system(3, group_fraction=group_fraction)
+    group, gb = ("bit1", 2) if group_fraction else ("all", 1)
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    tau0 = 5e-4
+    drv = refc.coloured_fix_driver(s, H.fix_args(flags, ni_trunc_beta, ["Ni"], model=repr(tau0), grid=(2, 2, 2), group=group,
+                                                 style="eph/coloured/exp"))
+    fx = O.Fix(s, O.Beta(path=ni_trunc_beta), O.FDM(2, 2, 2, box, 300.0, 3.5e-6, 1.0, 0.1248), flags, groupbit=gb, dt=1e-4)
+    fx.set_colour(tau0)
+    xis = [np.random.default_rng(i).normal(size=(s["nlocal"], 3)) if flags & 2 else None for i in range(4)]
+    recs = traj.run_fix_driver(drv, s, xis, vec3_probes=dict(f_dis=5, f_sto=6))
+    refs = traj.run_oracle(fx, s, xis, [58.71])
+    for step, (a, b) in enumerate(zip(recs, refs)):
+        for k in ("x", "v", "f", "array", "T", "Ee", "Tmean", "w", "rho", "f_dis", "f_sto"):
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (step, k)
+    # the filter has memory: the first step carries zeta times the unfiltered force
+    if flags & 1:
+        assert np.abs(recs[0]["f_dis"]).max() > 0
+    # a time-step change refreshes zeta (fix_eph_coloured_exp.cpp:686)
+    drv.set_dt(2e-4)
+    fx.set_dt(2e-4)
+    a = traj.run_fix_driver(drv, s, xis[:1], vec3_probes=dict(f_dis=5, f_sto=6))[0]
+    b = traj.run_oracle(fx, s, xis[:1], [58.71])[0]
+    for k in ("f", "f_dis", "f_sto"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_coloured_oracle_matches_committed_golden_vectors(ni_trunc_beta):
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "coloured_case.npz"))
+    s = traj.system_from_golden(g)
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    fx = O.Fix(s, O.Beta(path=ni_trunc_beta), O.FDM(2, 2, 2, box, 300.0, 3.5e-6, 1.0, 0.1248), int(g["flags"]),
+               groupbit=int(g["groupbit"]), dt=float(g["dt"]))
+    fx.set_colour(float(g["tau0"]))
+    recs = traj.run_oracle(fx, s, list(g["xi"]), [58.71])
+    for k in ("f", "array", "T", "Ee", "Tmean", "w", "rho", "x", "v", "f_dis", "f_sto"):
+        assert np.array_equal(np.array([r[k] for r in recs]), g["out_" + k]), k

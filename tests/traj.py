@@ -18,8 +18,9 @@ class GhostSync:
         v[self.nl:] = v[self.owner]
 
 
-def run_fix_driver(drv, system, xis, dt=None):
+def run_fix_driver(drv, system, xis, dt=None, vec3_probes=None):
     """drv: eph_b200.host.FixDriver (reference or product).  xis: list of per-step xi [nlocal][3] or None.
+    vec3_probes: {record key: probe id} of additional [nlocal][3] probes (fix eph/coloured/exp: f_dis 5, f_sto 6).
     Returns per-step records."""
     sync = GhostSync(system)
     out = []
@@ -44,6 +45,8 @@ def run_fix_driver(drv, system, xis, dt=None):
         out.append(dict(x=x[: sync.nl].copy(), v=v[: sync.nl].copy(), f=f[: sync.nl].copy(), array=drv.array().copy(),
                         T=drv.grid_T().copy(), Ee=drv.compute_vector(0), Tmean=drv.compute_vector(1),
                         w=drv.probe(1).copy(), rho=drv.probe(0).copy()))
+        for key, which in (vec3_probes or {}).items():
+            out[-1][key] = drv.probe(which, vec3=True).copy()
     return out
 
 
@@ -74,11 +77,12 @@ def run_oracle(fix, system, xis, mass):
         fix.end_of_step()
         out.append(dict(x=fix.x[:nl].copy(), v=fix.v[:nl].copy(), f=fix.f[:nl].copy(), array=np.array(fix.ptr(5)),
                         T=np.array(fix.fdm.field(0)), Ee=fix.Ee(), Tmean=fix.fdm.T_total(), w=np.array(fix.ptr(1)),
-                        rho=np.array(fix.ptr(0)), f_eph=np.array(fix.ptr(3)), f_rng=np.array(fix.ptr(4))))
+                        rho=np.array(fix.ptr(0)), f_eph=np.array(fix.ptr(3)), f_rng=np.array(fix.ptr(4)),
+                        f_dis=np.array(fix.ptr(6)), f_sto=np.array(fix.ptr(7))))
     return out
 
 
-def run_engine(eng, system, xis, mass, dt, device=False, ftm2v=1.0 / 1.0364269e-4):
+def run_engine(eng, system, xis, mass, dt, device=False, ftm2v=1.0 / 1.0364269e-4, coloured=False):
     """eng: eph_b200.lib.Engine with tables/grid/dt/atoms/neighbours set.  Drives the C ABI directly, with
     host (numpy) or device (torch) arrays.  `mass` is per type (1-based list without the leading slot)."""
     sync = GhostSync(system)
@@ -118,6 +122,8 @@ def run_engine(eng, system, xis, mass, dt, device=False, ftm2v=1.0 / 1.0364269e-
         out.append(dict(x=tonp(x[:nl]), v=tonp(v[:nl]), f=tonp(f[:nl]), array=eng.peratom(), T=eng.get_grid(0), Ee=Ee,
                         Tmean=eng.mean_T(), w=eng.probe(1), rho=eng.probe(0), f_eph=eng.probe(3), f_rng=eng.probe(4),
                         xi=eng.probe(2)))
+        if coloured:
+            out[-1]["f_dis"], out[-1]["f_sto"] = eng.colour_state()
     return out
 
 

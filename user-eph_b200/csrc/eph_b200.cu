@@ -97,6 +97,11 @@ struct eph_b200_handle {
   // internal per-atom records
   DevBuf<double4> pos4, pv, puz, W4;
   DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
+  // `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): exponential memory kernel on both forces; the filtered forces of
+  // the previous step are per-atom state (f_dis, f_sto [nlocal][3])
+  bool coloured = false;
+  double tau0 = 0.0, zeta = 0.0;
+  DevBuf<double> f_dis, f_sto;
   bool forces_valid = false;
   bool peratom_valid = false;   // an end_of_step has run: the per-atom output (fix_eph.cpp:406-428) can be materialised
   // state between post_force_begin and post_force_end
@@ -432,6 +437,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->mass.release(); h->comm_idx.release(); h->comm_buf.release();
   h->pos4.release(); h->pv.release(); h->puz.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
+  h->f_dis.release(); h->f_sto.release();
   h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -664,7 +670,58 @@ int eph_b200_set_dt(eph_b200_handle *h, double dt, double boltz) {
   if (!(dt > 0) || !(boltz > 0)) return fail(h, EPH_B200_ERR_ARG, "set_dt: dt and boltz must be positive");
   h->dt = dt; h->boltz = boltz;
   h->eta = std::sqrt(2.0 * boltz / dt);  // eta_factor, fix_eph.cpp:200, :910
+  if (h->coloured) h->zeta = 1.0 - std::exp(-dt / h->tau0);   // zeta_factor, fix_eph_coloured_exp.cpp:686
   h->dt_set = true;
+  return EPH_B200_OK;
+}
+
+// `fix eph/coloured/exp`: f_EPH and f_RNG of model 4 pass through f <- f_prev (1 - zeta) + zeta f_new with
+// zeta = 1 - exp(-dt / tau0) (fix_eph_coloured_exp.cpp:190, :563-569, :619-625); tau0 <= 0 switches the filter off.
+int eph_b200_set_colour(eph_b200_handle *h, double tau0) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (tau0 > 0.0 && h->cfg.model != EPH_B200_MODEL_PRL) return fail(h, EPH_B200_ERR_MODEL, "set_colour: the memory kernel belongs to eph_model 4");
+  cudaSetDevice(h->cfg.device);
+  h->coloured = tau0 > 0.0;
+  h->tau0 = tau0;
+  h->zeta = (h->coloured && h->dt_set) ? 1.0 - std::exp(-h->dt / tau0) : 0.0;
+  if (h->coloured && h->atoms_set) {
+    const size_t n3 = 3 * std::max<size_t>(h->nlocal, 1);
+    if (h->f_dis.cap < n3 || h->f_sto.cap < n3) {
+      EPH_CUDA(h, h->f_dis.reserve(n3)); EPH_CUDA(h, h->f_sto.reserve(n3));
+      EPH_CUDA(h, cudaMemsetAsync(h->f_dis.p, 0, h->f_dis.cap * sizeof(double), h->stream));
+      EPH_CUDA(h, cudaMemsetAsync(h->f_sto.p, 0, h->f_sto.cap * sizeof(double), h->stream));
+    }
+  }
+  return EPH_B200_OK;
+}
+
+// the filter's per-atom state [nlocal][3] each: it migrates with the atoms (pack_exchange / copy_arrays,
+// fix_eph_coloured_exp.cpp:793-825), so the host fix reads it back after every step and re-registers it after set_atoms
+int eph_b200_get_colour_state(eph_b200_handle *h, double *f_dis, double *f_sto, int memspace) {
+  if (!h || !f_dis || !f_sto) return EPH_B200_ERR_ARG;
+  if (!h->coloured || !h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "get_colour_state: set_colour and set_atoms first");
+  cudaSetDevice(h->cfg.device);
+  const size_t bytes = 3 * (size_t)h->nlocal * sizeof(double);
+  const cudaMemcpyKind kind = memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (bytes) {
+    EPH_CUDA(h, cudaMemcpyAsync(f_dis, h->f_dis.p, bytes, kind, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(f_sto, h->f_sto.p, bytes, kind, h->stream));
+    if (memspace != EPH_B200_DEVICE) EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_colour_state(eph_b200_handle *h, const double *f_dis, const double *f_sto, int memspace) {
+  if (!h || !f_dis || !f_sto) return EPH_B200_ERR_ARG;
+  if (!h->coloured || !h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "set_colour_state: set_colour and set_atoms first");
+  cudaSetDevice(h->cfg.device);
+  const size_t bytes = 3 * (size_t)h->nlocal * sizeof(double);
+  const cudaMemcpyKind kind = memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (bytes) {
+    EPH_CUDA(h, cudaMemcpyAsync(h->f_dis.p, f_dis, bytes, kind, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->f_sto.p, f_sto, bytes, kind, h->stream));
+    if (memspace != EPH_B200_DEVICE) EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return EPH_B200_OK;
 }
 
@@ -724,6 +781,11 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   EPH_CUDA(h, cudaMemsetAsync(h->f_eph.p, 0, 3 * nl * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->f_rng.p, 0, 3 * nl * sizeof(double), h->stream));
   EPH_CUDA(h, cudaMemsetAsync(h->array8.p, 0, 8 * nl * sizeof(double), h->stream));
+  if (h->coloured && (h->f_dis.cap < 3 * nl || h->f_sto.cap < 3 * nl)) {   // new filter storage starts from zero (fix_eph_coloured_exp.cpp:229-230)
+    EPH_CUDA(h, h->f_dis.reserve(3 * nl)); EPH_CUDA(h, h->f_sto.reserve(3 * nl));
+    EPH_CUDA(h, cudaMemsetAsync(h->f_dis.p, 0, h->f_dis.cap * sizeof(double), h->stream));
+    EPH_CUDA(h, cudaMemsetAsync(h->f_sto.p, 0, h->f_sto.cap * sizeof(double), h->stream));
+  }
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));  // host source buffers may be reused by the caller
   h->nlocal = nlocal; h->nghost = nghost;
   h->atoms_set = true;
@@ -1184,7 +1246,28 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
     a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
     a.add_friction = add_fric ? 1 : 0;
     a.add_random = add_rand ? 1 : 0;
-    if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
+    if (h->coloured) {
+      // fix eph/coloured/exp: the force pass only forms f_EPH / f_RNG; the memory kernel filters them and the filtered
+      // forces are what goes into f (fix_eph_coloured_exp.cpp:563-569, :619-625, :664-678)
+      a.f = nullptr;
+      a.i_begin = 0; a.i_end = nl;
+      if ((rc = launch_sweep(h, a, 1))) return rc;
+      ColourArgs c{};
+      c.nlocal = nl; c.pos4 = h->pos4.p; c.rho = h->rho.p; c.zeta = h->zeta;
+      c.do_friction = a.do_friction; c.do_random = a.do_random;
+      c.add_friction = add_fric ? 1 : 0; c.add_random = add_rand ? 1 : 0;
+      c.f_eph = h->f_eph.p; c.f_rng = h->f_rng.p; c.f_dis = h->f_dis.p; c.f_sto = h->f_sto.p;
+      c.f = (add_fric || add_rand) ? df : nullptr;
+      {
+        KernelTimer kt(h, "colour_filter");
+        colour_filter_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(c);
+      }
+      EPH_LAUNCH_CHECK(h);
+      if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
+        EPH_CUDA(h, cudaMemcpyAsync(f, h->f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+      }
+    } else if ((add_fric || add_rand) && memspace != EPH_B200_DEVICE) {
       // host memspace: the force pass runs in a few launches over consecutive atom ranges and every finished range of
       // f goes back to the host on the copy stream while the next range is still being swept
       static const int chunks_env = env_int("EPH_B200_F_CHUNKS", 4);

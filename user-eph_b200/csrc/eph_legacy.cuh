@@ -106,4 +106,46 @@ __global__ void __launch_bounds__(256) legacy_force_kernel(LegacyArgs p) {
   }
 }
 
+// `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): exponential memory kernel on the forces of model 4.  For group atoms
+// with rho_i > 0 (the only ones the reference's loops reach, :486, :531, :585)
+//   f_dis_i <- f_dis_i (1 - zeta) + zeta f_EPH_i,  f_EPH_i <- f_dis_i     (:563-569, when FRICTION is set)
+//   f_sto_i <- f_sto_i (1 - zeta) + zeta f_RNG_i,  f_RNG_i <- f_sto_i     (:619-625, when RANDOM is set)
+// then f += f_EPH (+ f_RNG) for every local atom (:664-678).  The force pass ran with its own `f +=` switched off.
+struct ColourArgs {
+  int nlocal;
+  const double4 *__restrict__ pos4;   // {x, y, z, bits}
+  const double *__restrict__ rho;
+  double zeta;
+  int do_friction, do_random, add_friction, add_random;
+  double *__restrict__ f_eph, *__restrict__ f_rng, *__restrict__ f_dis, *__restrict__ f_sto;
+  double *__restrict__ f;             // LAMMPS force array (read-modify-write) or nullptr
+};
+
+__global__ void __launch_bounds__(256) colour_filter_kernel(ColourArgs p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.nlocal) return;
+  const bool active = (double_to_bits(p.pos4[i].w) & kBitGroup) && p.rho[i] > 0;
+  const size_t o = 3 * (size_t)i;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double fe = p.f_eph[o + d], fr = p.f_rng[o + d];
+    if (active && p.do_friction) {
+      fe = p.f_dis[o + d] * (1. - p.zeta) + p.zeta * fe;
+      p.f_dis[o + d] = fe;
+      p.f_eph[o + d] = fe;
+    }
+    if (active && p.do_random) {
+      fr = p.f_sto[o + d] * (1. - p.zeta) + p.zeta * fr;
+      p.f_sto[o + d] = fr;
+      p.f_rng[o + d] = fr;
+    }
+    if (p.f != nullptr) {
+      double a = 0.0;
+      if (p.add_friction) a += fe;
+      if (p.add_random) a += fr;
+      p.f[o + d] += a;
+    }
+  }
+}
+
 }  // namespace ephb

@@ -232,13 +232,16 @@ class FixDriver:
         self._fn("get_array")(C.c_void_p(self.w), C.c_void_p(out.ctypes.data))
         return out
 
-    def probe(self, which):
-        """0 rho[nt] 1 w 2 xi 3 f_EPH 4 f_RNG [nl][3]; `fix eph/atomic` adds 5 rho_a[nt] 6 E_a[nt] 7 dE_a[nl] 8 T_a[nl]"""
+    def probe(self, which, vec3=None):
+        """0 rho[nt] 1 w 2 xi 3 f_EPH 4 f_RNG [nl][3]; `fix eph/atomic` adds 5 rho_a[nt] 6 E_a[nt] 7 dE_a[nl] 8 T_a[nl];
+        `fix eph/coloured/exp` adds 5 f_dis 6 f_sto [nl][3] (pass vec3=True)"""
         nt = self.nlocal + self.nghost
-        n = nt if which in (0, 5, 6) else self.nlocal if which in (7, 8) else 3 * self.nlocal
+        if vec3 is None:
+            vec3 = which in (1, 2, 3, 4)
+        n = 3 * self.nlocal if vec3 else nt if which in (0, 5, 6) else self.nlocal
         out = np.empty(n)
         self._ck(self._fn("get_probe")(C.c_void_p(self.w), which, C.c_void_p(out.ctypes.data)))
-        return out.reshape(-1, 3) if which in (1, 2, 3, 4) else out
+        return out.reshape(-1, 3) if vec3 else out
 
     def set_energy(self, E):
         """`fix eph/atomic` only: overwrite the per-atom electronic energies of the local atoms"""

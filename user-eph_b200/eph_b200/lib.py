@@ -41,6 +41,9 @@ SYMBOLS = {
     "eph_b200_mean_T": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_last_substeps": (C.c_int, [C.c_void_p, c_int_p]),
     "eph_b200_set_dt": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "eph_b200_set_colour": (C.c_int, [C.c_void_p, C.c_double]),
+    "eph_b200_get_colour_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_set_colour_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_skin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "eph_b200_list_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "eph_b200_set_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -221,6 +224,19 @@ class Engine:
 
     def set_dt(self, dt, boltz=8.617343e-5):
         self._check(self.lib.eph_b200_set_dt(self.h, dt, boltz))
+
+    def set_colour(self, tau0):
+        """`fix eph/coloured/exp`: exponential memory kernel with time constant tau0 on both forces (0: off)"""
+        self._check(self.lib.eph_b200_set_colour(self.h, tau0))
+
+    def colour_state(self):
+        fd, fs = np.empty((self.nlocal, 3)), np.empty((self.nlocal, 3))
+        self._check(self.lib.eph_b200_get_colour_state(self.h, fd.ctypes.data, fs.ctypes.data, HOST))
+        return fd, fs
+
+    def set_colour_state(self, f_dis, f_sto):
+        ps = [_ptr(f_dis), _ptr(f_sto)]
+        self._check(self.lib.eph_b200_set_colour_state(self.h, ps[0][0], ps[1][0], _space(*ps)))
 
     def set_skin(self, skin, inner_skin=-1.0):
         self._check(self.lib.eph_b200_set_skin(self.h, skin, inner_skin))

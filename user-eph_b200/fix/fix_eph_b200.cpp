@@ -5,6 +5,7 @@
 
 #include <mpi.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -30,8 +31,10 @@ using namespace FixConst;
 /* arguments: identical positions to FixEPH (fix_eph.cpp:36-58)
  *  3 seed | 4 flags | 5 model | 6 rho_e | 7 C_e | 8 kappa_e | 9 T_e | 10-12 NX NY NZ | 13 T_infile | 14 freq
  *  15 T_out | 16 beta file | 17.. element per type | then optional keyword pairs */
-FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg), dev(nullptr), random(nullptr) {
+FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
+    : Fix(lmp, narg, arg), dev(nullptr), random(nullptr), coloured(false), tau0(0.0), f_sto_i(nullptr), f_dis_i(nullptr) {
   if (narg < 18) error->all(FLERR, "Illegal fix eph command: too few arguments");
+  coloured = strstr(arg[2], "coloured") != nullptr;   // fix eph/coloured/exp: arg[5] is tau0 (fix_eph_coloured_exp.cpp:43)
   if (atom->natoms < 1) error->all(FLERR, "fix_eph: error no atoms in simulation");
   MPI_Comm_rank(world, &myID);
   MPI_Comm_size(world, &nrPS);
@@ -65,8 +68,16 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
   }
   time_integrate = (eph_flag & Flag::NOINT) ? 0 : 1;
 
-  eph_model = atoi(arg[5]);
-  if (myID == 0) std::cout << "\nModel read: " << arg[5] << " -> " << eph_model << " (B200 device path)\n" << std::endl;
+  if (coloured) {
+    tau0 = atof(arg[5]);
+    if (!(tau0 > 0.0)) error->all(FLERR, "fix eph/coloured/exp/b200: tau0 must be positive");
+    eph_model = Model::PRL;
+    maxexchange = 6;
+    if (myID == 0) std::cout << "\nColoured noise, exponential kernel: tau0 = " << tau0 << " (B200 device path)\n" << std::endl;
+  } else {
+    eph_model = atoi(arg[5]);
+    if (myID == 0) std::cout << "\nModel read: " << arg[5] << " -> " << eph_model << " (B200 device path)\n" << std::endl;
+  }
   if (eph_model == Model::PRLCM)
     error->all(FLERR, "fix eph/b200: model 3 (PRLCM) is not offered: the reference indexes its rho(r) table with jtype - i "
                       "there (fix_eph.cpp:601)");
@@ -201,6 +212,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
           "set_grid_tables");
   check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
   check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
+  if (coloured) check(eph_b200_set_colour(dev, tau0), "set_colour");
 
   array = nullptr;
   list = nullptr;
@@ -211,6 +223,10 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg) : Fix(lmp, narg, arg),
   grow_arrays(atom->nmax);
   atom->add_callback(0);
   std::fill_n(&(array[0][0]), size_peratom_cols * (size_t)(atom->nlocal + atom->nghost), 0);
+  if (coloured) {   // fix_eph_coloured_exp.cpp:229-230
+    std::fill_n(&(f_sto_i[0][0]), 3 * (size_t)(atom->nlocal + atom->nghost), 0.);
+    std::fill_n(&(f_dis_i[0][0]), 3 * (size_t)(atom->nlocal + atom->nghost), 0.);
+  }
 
   Ee = 0.0;
 }
@@ -219,6 +235,8 @@ FixEPHB200::~FixEPHB200() {
   delete random;
   atom->delete_callback(id, 0);
   memory->destroy(array);
+  memory->destroy(f_sto_i);
+  memory->destroy(f_dis_i);
   eph_b200_destroy(dev);
 }
 
@@ -310,6 +328,8 @@ void FixEPHB200::upload_topology() {
         "set_atoms");
   if (neigh_device) check(eph_b200_build_neighbors(dev, &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
   else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
+  // the memory kernel's state in the atoms' present order (LAMMPS may have sorted or migrated them)
+  if (coloured && nlocal > 0) check(eph_b200_set_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "set_colour_state");
   atoms_epoch = ((long long)nlocal << 32) | (unsigned)nghost;
   need_upload = false;
 }
@@ -337,6 +357,7 @@ void FixEPHB200::post_force(int) {
     check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
                               EPH_B200_HOST),
           "post_force");
+    if (coloured && nlocal > 0) check(eph_b200_get_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "get_colour_state");
     return;
   }
   // the reference's transport: ghosts get xi, rho and the w sums through Comm::forward_comm(Fix*) (fix_eph.cpp:863-871, :743-744)
@@ -346,6 +367,7 @@ void FixEPHB200::post_force(int) {
   if (eph_flag & Flag::FRICTION) { state = FixState::WI; comm->forward_comm(this); }
   state = FixState::NONE;
   check(eph_b200_post_force_end(dev, nlocal ? &atom->f[0][0] : nullptr, EPH_B200_HOST), "post_force");
+  if (coloured && nlocal > 0) check(eph_b200_get_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "get_colour_state");
 }
 
 void FixEPHB200::end_of_step() {
@@ -376,13 +398,41 @@ void FixEPHB200::reset_dt() {
   eta_factor = sqrt(2.0 * force->boltz / update->dt);
   dtv = update->dt;
   dtf = 0.5 * update->dt * force->ftm2v;
-  check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
+  check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");   // also refreshes the filter's zeta factor
 }
 
 void FixEPHB200::grow_arrays(int ngrow) {
   n = ngrow;
   memory->grow(array, ngrow, size_peratom_cols, "eph:array");
   array_atom = array;
+  if (coloured) {
+    memory->grow(f_sto_i, ngrow, 3, "eph:f_sto_i");
+    memory->grow(f_dis_i, ngrow, 3, "eph:f_dis_i");
+  }
+}
+
+// fix eph/coloured/exp: the filtered forces of the last step migrate with their atom (fix_eph_coloured_exp.cpp:793-825)
+int FixEPHB200::pack_exchange(int i, double *buf) {
+  if (!coloured) return 0;
+  int m = 0;
+  for (int d = 0; d < 3; ++d) buf[m++] = f_sto_i[i][d];
+  for (int d = 0; d < 3; ++d) buf[m++] = f_dis_i[i][d];
+  return m;
+}
+
+int FixEPHB200::unpack_exchange(int nlocal, double *buf) {
+  if (!coloured) return 0;
+  int m = 0;
+  for (int d = 0; d < 3; ++d) f_sto_i[nlocal][d] = buf[m++];
+  for (int d = 0; d < 3; ++d) f_dis_i[nlocal][d] = buf[m++];
+  need_upload = true;
+  return m;
+}
+
+void FixEPHB200::copy_arrays(int i, int j, int) {
+  if (!coloured) return;
+  for (int d = 0; d < 3; ++d) { f_sto_i[j][d] = f_sto_i[i][d]; f_dis_i[j][d] = f_dis_i[i][d]; }
+  need_upload = true;
 }
 
 double FixEPHB200::compute_vector(int i) {
@@ -427,7 +477,7 @@ void FixEPHB200::unpack_forward_comm(int n, int first, double *data) {
 }
 
 double FixEPHB200::memory_usage() {
-  return (double)n * size_peratom_cols * sizeof(double);
+  return (double)n * (size_peratom_cols + (coloured ? 6 : 0)) * sizeof(double);
 }
 
 // final grid state, readable as T_infile of a later run (fix_eph.cpp:1019-1021)
@@ -445,7 +495,12 @@ void FixEPHB200::post_run() {
   }
 }
 
-void FixEPHB200::probe_copy(int which, size_t, size_t, double *out) {
+void FixEPHB200::probe_copy(int which, size_t nlocal, size_t, double *out) {
+  if (coloured && (which == 5 || which == 6)) {   // the filter state as the host holds it: 5 f_dis, 6 f_sto
+    double **src = which == 5 ? f_dis_i : f_sto_i;
+    std::copy(&src[0][0], &src[0][0] + 3 * nlocal, out);
+    return;
+  }
   check(eph_b200_get_probe(dev, which, out), "get_probe");
 }
 

@@ -14,12 +14,19 @@
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
  * (f_ID[1], f_ID[2], 8 per-atom columns); all per-timestep work is done by libeph_b200 (include/eph_b200.h).
  * Build with -DEPH_B200_REPLACE_FIX_EPH to register under the name `eph` itself.
+ *
+ * The same class serves `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp), the reference's fork of model 4 with an
+ * exponential memory kernel on both forces: under a style name containing "coloured" arg[5] is the time constant tau0
+ * instead of the model number (fix_eph_coloured_exp.cpp:43), the filter runs on the device (eph_b200_set_colour) and
+ * its per-atom state (f_dis, f_sto) migrates with the atoms through pack_exchange / unpack_exchange / copy_arrays.
  */
 #ifdef FIX_CLASS
 #ifdef EPH_B200_REPLACE_FIX_EPH
 FixStyle(eph,FixEPHB200)
+FixStyle(eph/coloured/exp,FixEPHB200)
 #else
 FixStyle(eph/b200,FixEPHB200)
+FixStyle(eph/coloured/exp/b200,FixEPHB200)
 #endif
 #else
 
@@ -61,6 +68,9 @@ class FixEPHB200 : public Fix {
   void post_run() override;
   int pack_forward_comm(int, int *, double *, int, int *) override;
   void unpack_forward_comm(int, int, double *) override;
+  int pack_exchange(int, double *) override;
+  int unpack_exchange(int, double *) override;
+  void copy_arrays(int, int, int) override;
 
   // read-only views used by the test driver (tests/lammps_shim/fix_driver.h)
   void probe_copy(int which, size_t nlocal, size_t ntotal, double *out);
@@ -96,6 +106,9 @@ class FixEPHB200 : public Fix {
   double Ee;
   size_t n;
 
+  bool coloured;                // style eph/coloured/exp: exponential memory kernel on both forces
+  double tau0;
+  double **f_sto_i, **f_dis_i;  // coloured: filtered random / friction force of the last step, [nmax][3], migrate with the atoms
   double **array;               // [nmax][8] per-atom output (array_atom)
   std::vector<double> xi_host;  // rng mars: Gaussians of this step
   std::vector<int> ghost_owner; // local owner of each ghost (single rank)
