@@ -133,3 +133,39 @@ def philox_case(make_engine, kappa_tables):
         assert H.error_metrics(x["xi"], xi) < 1e-13
         for k in ("f", "E", "dE", "f_rng"):
             assert H.error_metrics(x[k], y[k]) < 1e-12, k
+
+
+def properties_case(make_engine, kappa_tables, n, steps=2, loops=2):
+    """Size-independent properties of the path (no oracle needed, any box size): the pair forces are antisymmetric, so
+    both forces sum to zero over the box; the energy ledger returns exactly the work the two forces do on the atoms,
+    sum_i dE_i = -dt sum_i (f_EPH_i + f_RNG_i).v_i; heat diffusion only moves energy between atoms; rho, rho_a > 0."""
+    s = H.make_system(n)
+    nl = s["nlocal"]
+    eng = setup_engine(make_engine([0], [0], 7, inner_loops=loops), s, BETA, kappa_tables)
+    sync = traj.GhostSync(s)
+    x = np.ascontiguousarray(s["x"]).copy()
+    v = np.ascontiguousarray(s["v"]).copy()
+    dt = 1e-4
+    E_prev = eng.get_energy()
+    for step in range(1, steps + 1):
+        f = np.zeros((nl, 3))
+        xi = np.random.default_rng(100 + step).normal(size=(nl, 3))
+        eng.post_force(x, v, f, xi, step)
+        f_eph, f_rng, dE, rho, rho_a = eng.probe(3), eng.probe(4), eng.probe(7), eng.probe(0), eng.probe(5)
+        assert np.all(rho[:nl] > 0) and np.all(rho_a[:nl] > 0)
+        assert np.array_equal(rho[nl:], rho[sync.owner]) and np.array_equal(rho_a[nl:], rho_a[sync.owner])
+        assert H.error_metrics(f, f_eph + f_rng) < 1e-14
+        for force in (f_eph, f_rng):
+            assert np.max(np.abs(force.sum(axis=0))) < 1e-10 * np.abs(force).sum()
+        work = -dt * np.einsum("ij,ij->", f_eph + f_rng, v[:nl])
+        assert abs(dE.sum() - work) < 1e-10 * np.abs(dE).sum(), (dE.sum(), work)
+        Ee, Te = eng.end_of_step()
+        E = eng.get_energy()
+        assert np.all(E >= 0)
+        assert abs(Ee - E.sum()) < 1e-12 * E.sum()
+        assert abs(E.sum() - (E_prev.sum() + dE.sum())) < 1e-10 * E.sum()      # diffusion conserves, nothing was clamped
+        assert abs(Te - eng.probe(8).mean()) < 1e-12 * Te
+        E_prev = E
+        v[:nl] += 0.5 * dt * H.FTM2V / 58.71 * f       # keep the state moving between the steps
+        x[:nl] += dt * v[:nl]
+        sync(x, v)

@@ -69,3 +69,7 @@ def test_emulated_fix_matches_committed_golden_vectors(make_fix, name):
 
 def test_emulated_builtin_gaussian_stream(make_engine, kappa_tables):
     cases.philox_case(make_engine, kappa_tables)
+
+
+def test_emulated_size_independent_properties(make_engine, kappa_tables):
+    cases.properties_case(make_engine, kappa_tables, 4)
