@@ -6,9 +6,10 @@
  * is its drop-in boundary, with the conventions of eph_b200.h: plain C, opaque handle, EPH_B200_OK or a negative
  * eph_b200_status, one CUDA stream, LAMMPS array layouts, host or device pointers (`memspace`), NO CPU fallback.
  *
- * Scope: one rank per box.  Ghost atoms are periodic images of the rank's own atoms and take their owner's values
- * through the ghost_owner map (what Comm::forward_comm(Fix*) realises through pack/unpack_forward_comm,
- * fix_eph_atomic.cpp:849-927, on one rank).  Every entry point names the reference lines it replaces.
+ * Ghost atoms take their owner's values either through the ghost_owner map inside the engine (one rank per box: every
+ * ghost is a periodic image of one of the rank's own atoms) or through the caller's transport in a phase-split step
+ * (set_comm_mode; what Comm::forward_comm(Fix*) realises through pack/unpack_forward_comm, fix_eph_atomic.cpp:849-927).
+ * Every entry point names the reference lines it replaces.
  */
 #ifndef EPH_B200_ATOMIC_H
 #define EPH_B200_ATOMIC_H
@@ -83,6 +84,24 @@ int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const
 int eph_b200_atomic_end_of_step(eph_b200_atomic_handle *h, double *Ee, double *Te);
 /* only the sums (constructor, fix_eph_atomic.cpp:223-253) */
 int eph_b200_atomic_summary(eph_b200_atomic_handle *h, double *Ee, double *Te);
+
+/* Ghost transport by the caller (LAMMPS' Comm::forward_comm(Fix*) with host buffers, i.e. several ranks per box): after
+ * set_comm_mode(h, 1) set_atoms needs no owner map and a step is driven in phases, with the reference's forward comms
+ * (fix_eph_atomic.cpp:803-825, :549-550, :720-721) issued by the caller through pack_forward / unpack_forward
+ * (FixEPHAtomic::pack_forward_comm / unpack_forward_comm, :849-927; state 1 RHO {rho, rho_a}, 2 XI, 3 WI, 4 EI):
+ *   post_force_begin;  comm EI, XI (flag RANDOM), RHO;  post_force_mid;  comm WI (flag FRICTION);  post_force_end;
+ *   heat_loops() x { heat_begin;  comm EI;  heat_end };  summary (this rank's energy sum and mean temperature).
+ * pack_forward returns the number of doubles written or a negative status. */
+int eph_b200_atomic_set_comm_mode(eph_b200_atomic_handle *h, int external);
+int eph_b200_atomic_post_force_begin(eph_b200_atomic_handle *h, const double *x, const double *v, const double *xi_inject,
+                                     long long ntimestep, int memspace);
+int eph_b200_atomic_post_force_mid(eph_b200_atomic_handle *h);
+int eph_b200_atomic_post_force_end(eph_b200_atomic_handle *h, double *f, int memspace);
+int eph_b200_atomic_heat_loops(const eph_b200_atomic_handle *h);
+int eph_b200_atomic_heat_begin(eph_b200_atomic_handle *h);
+int eph_b200_atomic_heat_end(eph_b200_atomic_handle *h);
+int eph_b200_atomic_pack_forward(eph_b200_atomic_handle *h, int state, int n, const int *list, double *buf);
+int eph_b200_atomic_unpack_forward(eph_b200_atomic_handle *h, int state, int n, int first, const double *buf);
 
 /* FixEPHAtomic::populate_array (fix_eph_atomic.cpp:401-435): [nlocal][12] = rho, beta(rho), f_EPH xyz, f_RNG xyz,
  * rho_a, E, dE, T (zeros for atoms outside the group) */

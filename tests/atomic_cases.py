@@ -98,14 +98,16 @@ def golden_engine_case(make_engine, kappa_tables, name):
         assert np.all(np.abs(got - g["out_" + k]) <= TOL * np.abs(g["out_" + k])), k
 
 
-def golden_fix_case(make_fix, name):
-    """the committed golden vectors through FixEPHAtomicB200 (constructor syntax, hooks, outputs)"""
+def golden_fix_case(make_fix, name, comm="device"):
+    """the committed golden vectors through FixEPHAtomicB200 (constructor syntax, hooks, outputs); comm = "lammps" sends
+    the ghost values through Comm::forward_comm(Fix*) and the fix's pack/unpack callbacks like the reference"""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     s = traj.system_from_golden(g)
     group = "bit1" if int(g["groupbit"]) == 2 else "all"
     args = H.atomic_fix_args(int(g["flags"]), BETA, KAPPA, ["Ni"], inner_loops=int(g["inner_loops"]), group=group,
-                             style="eph/atomic/b200") + ["rng", "mars"]
+                             style="eph/atomic/b200") + ["rng", "mars", "comm", comm]
     drv = make_fix(s, args)
+    n0 = drv.n_forward()
     fl = drv.fix_flags()
     assert fl["size_peratom_cols"] == 12 and fl["comm_forward"] == 3 and fl["ghost_velocity"] == 1 and drv.neigh_cutoff() == 5.0
     if "E0" in g.files:
@@ -117,6 +119,12 @@ def golden_fix_case(make_fix, name):
     for k in ("Ee", "Te"):
         got = np.array([r[k] for r in recs])
         assert np.all(np.abs(got - g["out_" + k]) <= TOL * np.abs(g["out_" + k])), k
+    # forward comms: the reference's per step (EI, XI, RHO, WI and one EI per heat loop, fix_eph_atomic.cpp:803-825,
+    # :549-550, :720-721) with comm lammps; with comm device only the owner map, once per registration (the stand-in's
+    # list always counts as fresh, neighbor->ago == 0, so that is once per step here)
+    loops = max(int(g["inner_loops"]), 1)
+    want = len(recs) * (4 + loops) if comm == "lammps" else len(recs)
+    assert drv.n_forward() - n0 == want, (drv.n_forward() - n0, want)
 
 
 def philox_case(make_engine, kappa_tables):

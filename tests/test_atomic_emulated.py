@@ -62,9 +62,10 @@ def test_emulated_engine_matches_committed_golden_vectors(make_engine, kappa_tab
     cases.golden_engine_case(make_engine, kappa_tables, name)
 
 
+@pytest.mark.parametrize("comm", ["device", "lammps"])
 @pytest.mark.parametrize("name", ["atomic_caseA", "atomic_caseB_group"])
-def test_emulated_fix_matches_committed_golden_vectors(make_fix, name):
-    cases.golden_fix_case(make_fix, name)
+def test_emulated_fix_matches_committed_golden_vectors(make_fix, name, comm):
+    cases.golden_fix_case(make_fix, name, comm)
 
 
 def test_emulated_builtin_gaussian_stream(make_engine, kappa_tables):

@@ -49,9 +49,10 @@ def test_atomic_engine_matches_committed_golden_vectors(make_engine, kappa_table
     cases.golden_engine_case(make_engine, kappa_tables, name)
 
 
+@pytest.mark.parametrize("comm", ["device", "lammps"])
 @pytest.mark.parametrize("name", ["atomic_caseA", "atomic_caseB_group"])
-def test_fix_atomic_b200_matches_committed_golden_vectors(name):
-    cases.golden_fix_case(lambda s, args: A.fix_driver(s, args), name)
+def test_fix_atomic_b200_matches_committed_golden_vectors(name, comm):
+    cases.golden_fix_case(lambda s, args: A.fix_driver(s, args), name, comm)
 
 
 def test_atomic_engine_builtin_gaussian_stream(make_engine, kappa_tables):

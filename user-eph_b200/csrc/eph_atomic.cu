@@ -112,6 +112,24 @@ __global__ void __launch_bounds__(256) ghost_fill_kernel(int nlocal, int nghost,
   if (a2) a2[nlocal + g] = a2[o];
 }
 
+// forward-comm payload of state RHO: {rho, rho_a} per atom (fix_eph_atomic.cpp:855-859, :893-897)
+__global__ void __launch_bounds__(256) gather_kernel(int n, const int *__restrict__ list, int width, const double *__restrict__ a0,
+                                                     const double *__restrict__ a1, double *__restrict__ buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const size_t src = list[k];
+  if (a1 != nullptr) { buf[2 * (size_t)k] = a0[src]; buf[2 * (size_t)k + 1] = a1[src]; }   // two scalars, interleaved
+  else for (int d = 0; d < width; ++d) buf[(size_t)width * k + d] = a0[(size_t)width * src + d];
+}
+
+__global__ void __launch_bounds__(256) scatter_pair_kernel(int n, int first, const double *__restrict__ buf, double *__restrict__ a0,
+                                                           double *__restrict__ a1) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  a0[first + k] = buf[2 * (size_t)k];
+  a1[first + k] = buf[2 * (size_t)k + 1];
+}
+
 // xi_i for the group's local atoms (fix_eph_atomic.cpp:808-816): injected, or the counter-based stream keyed on the tag
 __global__ void __launch_bounds__(256) xi_kernel(int nlocal, const int *__restrict__ mask, int groupbit, int do_random,
                                                  const double *__restrict__ inject, const long long *__restrict__ tag,
@@ -229,7 +247,8 @@ __global__ void __launch_bounds__(256) prep_kernel(int nlocal, int nt, const int
                                                    double4 *__restrict__ q) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nt) return;
-  const int src = a < nlocal ? a : owner[a - nlocal];
+  // owner == nullptr: the transport (LAMMPS' forward comm) has already filled the ghost rows of w and xi
+  const int src = (a < nlocal || owner == nullptr) ? a : owner[a - nlocal];
   const double4 c = cp[a];
   const size_t o = 3 * (size_t)src;
   q[2 * (size_t)a] = make_double4(c.x * w[o], c.x * w[o + 1], c.x * w[o + 2], c.z);
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(256) heat_prep_kernel(int nlocal, int nt, cons
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= nt) return;
   double e;
-  if (a < nlocal) e = E[a];
+  if (a < nlocal || owner == nullptr) e = E[a];   // owner == nullptr: ghost energies came through the transport
   else { e = E[owner[a - nlocal]]; E[a] = e; }
   const unsigned ek = (double_to_bits(rec[2 * (size_t)a].w) >> kKappaShift) & 0xFFu;
   const double T = lin_reverse(t.E_T + (size_t)ek * t.n_T, t.n_T, t.dT, e);
@@ -491,6 +510,11 @@ struct eph_b200_atomic_handle {
   const long long *tag_p = nullptr, *off_p = nullptr;
   const int *neigh_p = nullptr;
   DevBuf<double> x, v, f, xi_in, stage;
+  // external ghost transport (LAMMPS' Comm::forward_comm(Fix*) with host buffers): no owner map, phase-split calls
+  bool external_comm = false;
+  int phase = 0;                 // 0 idle, 1 after post_force_begin, 2 after post_force_mid
+  DevBuf<int> comm_idx;
+  DevBuf<double> comm_buf;
   DevBuf<double4> rec, cp, q, hk;
   DevBuf<double> rho, rho_a, E, E1, dE, T_a, w, xi, f_eph, f_rng, array12, scal;
   double *h_pinned = nullptr;
@@ -642,7 +666,7 @@ int eph_b200_atomic_destroy(eph_b200_atomic_handle *h) {
   cudaStreamSynchronize(h->stream);
   h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->rhoa_tab.release(); h->E_T.release(); h->K_T.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->d_tmb.release(); h->d_tmk.release(); h->tag.release();
-  h->off.release(); h->neigh.release(); h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->stage.release();
+  h->off.release(); h->neigh.release(); h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->stage.release(); h->comm_idx.release(); h->comm_buf.release();
   h->rec.release(); h->cp.release(); h->q.release(); h->hk.release();
   h->rho.release(); h->rho_a.release(); h->E.release(); h->E1.release(); h->dE.release(); h->T_a.release(); h->w.release();
   h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array12.release(); h->scal.release();
@@ -724,16 +748,18 @@ int eph_b200_atomic_set_dt(eph_b200_atomic_handle *h, double dt, double boltz) {
 int eph_b200_atomic_set_atoms(eph_b200_atomic_handle *h, int nlocal, int nghost, const int *type, const int *mask,
                               const int64_t *tag, const int *ghost_owner, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
-  if (nlocal < 0 || nghost < 0 || !type || !mask || !tag || (nghost > 0 && !ghost_owner))
-    return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: bad counts or null arrays (every ghost needs an owner on this rank)");
+  if (nlocal < 0 || nghost < 0 || !type || !mask || !tag)
+    return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: bad counts or null arrays");
+  if (nghost > 0 && !ghost_owner && !h->external_comm)
+    return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: every ghost needs an owner on this rank (or set_comm_mode(external))");
   cudaSetDevice(h->cfg.device);
   const size_t nt = (size_t)nlocal + nghost;
   if (memspace == EPH_B200_HOST) {
     for (size_t i = 0; i < nt; ++i)
       if (type[i] < 1 || type[i] > h->cfg.ntypes) return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: atom %zu has type %d", i, type[i]);
-    for (int g = 0; g < nghost; ++g)
+    for (int g = 0; g < nghost && ghost_owner && !h->external_comm; ++g)
       if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal)
-        return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: ghost %d has no owner on this rank (one rank per box)", g);
+        return fail(h, EPH_B200_ERR_ARG, "atomic_set_atoms: ghost %d has no owner on this rank", g);
   }
   int rc;
   const long long *tag_ll = reinterpret_cast<const long long *>(tag);
@@ -742,19 +768,20 @@ int eph_b200_atomic_set_atoms(eph_b200_atomic_handle *h, int nlocal, int nghost,
   if ((rc = stage_in(h, h->tag, tag_ll, nt, memspace, &h->tag_p)) != EPH_B200_OK) return rc;
   // the owner map is always copied: it is read by later calls
   EPHA_CUDA(h, h->owner.reserve(std::max<size_t>(nghost, 1)));
-  if (nghost) EPHA_CUDA(h, cudaMemcpyAsync(h->owner.p, ghost_owner, (size_t)nghost * sizeof(int),
+  if (nghost && ghost_owner) EPHA_CUDA(h, cudaMemcpyAsync(h->owner.p, ghost_owner, (size_t)nghost * sizeof(int),
                                            memspace == EPH_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
   const size_t n1 = std::max<size_t>(nt, 1), nl1 = std::max<size_t>(nlocal, 1);
   EPHA_CUDA(h, h->rec.reserve(2 * n1)); EPHA_CUDA(h, h->cp.reserve(n1)); EPHA_CUDA(h, h->q.reserve(2 * n1)); EPHA_CUDA(h, h->hk.reserve(n1));
   EPHA_CUDA(h, h->rho.reserve(n1)); EPHA_CUDA(h, h->rho_a.reserve(n1)); EPHA_CUDA(h, h->E.reserve(n1));
   EPHA_CUDA(h, h->E1.reserve(nl1)); EPHA_CUDA(h, h->dE.reserve(nl1)); EPHA_CUDA(h, h->T_a.reserve(nl1));
-  EPHA_CUDA(h, h->w.reserve(3 * nl1)); EPHA_CUDA(h, h->xi.reserve(3 * nl1)); EPHA_CUDA(h, h->f_eph.reserve(3 * nl1));
+  EPHA_CUDA(h, h->w.reserve(3 * n1)); EPHA_CUDA(h, h->xi.reserve(3 * n1)); EPHA_CUDA(h, h->f_eph.reserve(3 * nl1));
   EPHA_CUDA(h, h->f_rng.reserve(3 * nl1)); EPHA_CUDA(h, h->array12.reserve(12 * nl1));
   EPHA_CUDA(h, cudaStreamSynchronize(h->stream));   // host arrays may be reused by the caller
   h->nlocal = nlocal; h->nghost = nghost;
   h->atoms_set = true;
   h->neigh_set = false;
   h->packed = false;
+  h->phase = 0;
   return EPH_B200_OK;
 }
 
@@ -820,8 +847,17 @@ int eph_b200_atomic_get_energy(eph_b200_atomic_handle *h, double *E, int memspac
   return EPH_B200_OK;
 }
 
-int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
-                               long long ntimestep, int memspace) {
+int eph_b200_atomic_set_comm_mode(eph_b200_atomic_handle *h, int external) {
+  if (!h) return EPH_B200_ERR_ARG;
+  h->external_comm = external != 0;
+  h->phase = 0;
+  return EPH_B200_OK;
+}
+
+// post_force in three parts; between them the ghost rows are filled either internally through the owner map
+// (eph_b200_atomic_post_force) or by the caller's transport through pack/unpack_forward (LAMMPS' forward comm).
+int eph_b200_atomic_post_force_begin(eph_b200_atomic_handle *h, const double *x, const double *v, const double *xi_inject,
+                                     long long ntimestep, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
   int rc = ready(h, "atomic_post_force");
   if (rc != EPH_B200_OK) return rc;
@@ -829,43 +865,65 @@ int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const
   if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "atomic_post_force: null x or v");
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal, ng = h->nghost, nt = nl + ng;
+  h->phase = 1;
   if (nt == 0) return EPH_B200_OK;
-  const int flags = h->cfg.flags;
-  const bool do_friction = (flags & EPH_B200_FRICTION) != 0, do_random = (flags & EPH_B200_RANDOM) != 0;
+  const bool do_random = (h->cfg.flags & EPH_B200_RANDOM) != 0;
   const double *xd, *vd, *xid = nullptr;
   if ((rc = stage_in(h, h->x, x, 3 * (size_t)nt, memspace, &xd)) != EPH_B200_OK) return rc;
   if ((rc = stage_in(h, h->v, v, 3 * (size_t)nt, memspace, &vd)) != EPH_B200_OK) return rc;
   if (xi_inject && do_random && (rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &xid)) != EPH_B200_OK) return rc;
-  double *fd = f;
-  if (f && memspace == EPH_B200_HOST) {
-    EPHA_CUDA(h, h->f.reserve(3 * (size_t)std::max(nl, 1)));
-    EPHA_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    fd = h->f.p;
-  }
   cudaStream_t st = h->stream;
   EPHA_LAUNCH(pack_kernel, blocks_for(nt, 256), 256, st, nt, xd, vd, h->type_p, h->mask_p, h->d_tmb.p, h->d_tmk.p, h->cfg.groupbit, h->rec.p);
   EPHA_LAUNCH_CHECK(h);
   h->packed = true;
   if (nl > 0) {
     EPHA_LAUNCH(xi_kernel, blocks_for(nl, 256), 256, st, nl, h->mask_p, h->cfg.groupbit, do_random ? 1 : 0, xid, h->tag_p, h->cfg.seed,
-                                                   (unsigned long long)ntimestep, h->xi.p);
+                (unsigned long long)ntimestep, h->xi.p);
     EPHA_LAUNCH_CHECK(h);
     const SweepArgs sa = sweep_args(h);
     EPHA_LAUNCH(env_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->rho.p, h->rho_a.p);
     EPHA_LAUNCH_CHECK(h);
   }
-  if (ng > 0) {   // the EI and RHO forward comms (:803-804, :824-825)
-    EPHA_LAUNCH(ghost_fill_kernel, blocks_for(ng, 256), 256, st, nl, ng, h->owner.p, h->rho.p, h->rho_a.p, h->E.p);
-    EPHA_LAUNCH_CHECK(h);
-  }
+  return EPH_B200_OK;
+}
+
+// needs rho, rho_a and E of the ghosts (forward comms RHO and EI, fix_eph_atomic.cpp:803-804, :824-825)
+int eph_b200_atomic_post_force_mid(eph_b200_atomic_handle *h) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->phase != 1) return fail(h, EPH_B200_ERR_ARG, "atomic_post_force_mid without post_force_begin");
+  cudaSetDevice(h->cfg.device);
+  h->phase = 2;
+  const int nl = h->nlocal, nt = nl + h->nghost;
+  if (nt == 0) return EPH_B200_OK;
+  cudaStream_t st = h->stream;
   EPHA_LAUNCH(coupling_kernel, blocks_for(nt, 256), 256, st, nt, h->rec.p, h->rho.p, h->E.p, h->t, h->cp.p);
   EPHA_LAUNCH_CHECK(h);
   if (nl > 0) {
     const SweepArgs sa = sweep_args(h);
-    EPHA_LAUNCH(w_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->cp.p, do_friction ? 1 : 0, h->w.p);
+    EPHA_LAUNCH(w_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->cp.p, (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0, h->w.p);
     EPHA_LAUNCH_CHECK(h);
   }
-  EPHA_LAUNCH(prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->owner.p, h->cp.p, h->w.p, h->xi.p, h->q.p);
+  return EPH_B200_OK;
+}
+
+// needs w and xi of the ghosts (forward comms WI and XI, :549-550, :818-819): through the owner map, or already in place
+int eph_b200_atomic_post_force_end(eph_b200_atomic_handle *h, double *f, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->phase != 2) return fail(h, EPH_B200_ERR_ARG, "atomic_post_force_end without post_force_mid");
+  cudaSetDevice(h->cfg.device);
+  h->phase = 0;
+  const int nl = h->nlocal, nt = nl + h->nghost;
+  if (nt == 0) return EPH_B200_OK;
+  const int flags = h->cfg.flags;
+  const bool do_friction = (flags & EPH_B200_FRICTION) != 0, do_random = (flags & EPH_B200_RANDOM) != 0;
+  cudaStream_t st = h->stream;
+  double *fd = f;
+  if (f && memspace == EPH_B200_HOST) {
+    EPHA_CUDA(h, h->f.reserve(3 * (size_t)std::max(nl, 1)));
+    EPHA_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, st));
+    fd = h->f.p;
+  }
+  EPHA_LAUNCH(prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->external_comm ? nullptr : h->owner.p, h->cp.p, h->w.p, h->xi.p, h->q.p);
   EPHA_LAUNCH_CHECK(h);
   if (nl > 0) {
     ForceArgs p;
@@ -889,6 +947,67 @@ int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const
   return EPH_B200_OK;
 }
 
+int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const double *v, double *f, const double *xi_inject,
+                               long long ntimestep, int memspace) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->external_comm) return fail(h, EPH_B200_ERR_ARG, "atomic_post_force: external comm mode uses post_force_begin / mid / end");
+  int rc = eph_b200_atomic_post_force_begin(h, x, v, xi_inject, ntimestep, memspace);
+  if (rc != EPH_B200_OK) return rc;
+  if (h->nghost > 0) {   // the EI and RHO forward comms (:803-804, :824-825) through the owner map
+    EPHA_LAUNCH(ghost_fill_kernel, blocks_for(h->nghost, 256), 256, h->stream, h->nlocal, h->nghost, h->owner.p, h->rho.p, h->rho_a.p, h->E.p);
+    EPHA_LAUNCH_CHECK(h);
+  }
+  if ((rc = eph_b200_atomic_post_force_mid(h)) != EPH_B200_OK) return rc;
+  return eph_b200_atomic_post_force_end(h, f, memspace);   // prep reads the ghosts' w and xi from their owners
+}
+
+// Comm::forward_comm(Fix*) with host buffers: FixEPHAtomic::pack_forward_comm / unpack_forward_comm
+// (fix_eph_atomic.cpp:849-927).  state: 1 RHO {rho, rho_a}, 2 XI, 3 WI (3 doubles), 4 EI (1 double).
+int eph_b200_atomic_pack_forward(eph_b200_atomic_handle *h, int state, int n, const int *list, double *buf) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set || n < 0 || (n > 0 && (!list || !buf))) return fail(h, EPH_B200_ERR_ARG, "atomic_pack_forward: bad arguments");
+  const int width = state == 1 ? 2 : state == 4 ? 1 : (state == 2 || state == 3) ? 3 : 0;
+  if (width == 0) return fail(h, EPH_B200_ERR_ARG, "atomic_pack_forward: unknown state %d", state);
+  if (n == 0) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = h->stream;
+  EPHA_CUDA(h, h->comm_idx.reserve(n));
+  EPHA_CUDA(h, h->comm_buf.reserve((size_t)width * n));
+  EPHA_CUDA(h, cudaMemcpyAsync(h->comm_idx.p, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  const double *a0 = state == 1 ? h->rho.p : state == 2 ? h->xi.p : state == 3 ? h->w.p : h->E.p;
+  const double *a1 = state == 1 ? h->rho_a.p : nullptr;
+  EPHA_LAUNCH(gather_kernel, blocks_for(n, 256), 256, st, n, h->comm_idx.p, width, a0, a1, h->comm_buf.p);
+  EPHA_LAUNCH_CHECK(h);
+  EPHA_CUDA(h, cudaMemcpyAsync(buf, h->comm_buf.p, (size_t)width * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  EPHA_CUDA(h, cudaStreamSynchronize(st));
+  return width * n;
+}
+
+int eph_b200_atomic_unpack_forward(eph_b200_atomic_handle *h, int state, int n, int first, const double *buf) {
+  if (!h) return EPH_B200_ERR_ARG;
+  const long long nt = (long long)h->nlocal + h->nghost;
+  if (!h->atoms_set || n < 0 || first < 0 || (long long)first + n > nt || (n > 0 && !buf))
+    return fail(h, EPH_B200_ERR_ARG, "atomic_unpack_forward: bad arguments");
+  if (n == 0) return EPH_B200_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t st = h->stream;
+  if (state == 1) {
+    EPHA_CUDA(h, h->comm_buf.reserve(2 * (size_t)n));
+    EPHA_CUDA(h, cudaMemcpyAsync(h->comm_buf.p, buf, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    EPHA_LAUNCH(scatter_pair_kernel, blocks_for(n, 256), 256, st, n, first, h->comm_buf.p, h->rho.p, h->rho_a.p);
+    EPHA_LAUNCH_CHECK(h);
+  } else if (state == 2 || state == 3) {   // rows [first, first + n) are contiguous
+    double *dst = (state == 2 ? h->xi.p : h->w.p) + 3 * (size_t)first;
+    EPHA_CUDA(h, cudaMemcpyAsync(dst, buf, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else if (state == 4) {
+    EPHA_CUDA(h, cudaMemcpyAsync(h->E.p + first, buf, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    return fail(h, EPH_B200_ERR_ARG, "atomic_unpack_forward: unknown state %d", state);
+  }
+  EPHA_CUDA(h, cudaStreamSynchronize(st));   // the caller's buffer is reused for the next swap
+  return EPH_B200_OK;
+}
+
 int eph_b200_atomic_summary(eph_b200_atomic_handle *h, double *Ee, double *Te) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->kappa_set || !h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "atomic_summary: kappa tables and atoms first");
@@ -896,29 +1015,60 @@ int eph_b200_atomic_summary(eph_b200_atomic_handle *h, double *Ee, double *Te) {
   return run_summary(h, Ee, Te);
 }
 
+// heat_solve (fix_eph_atomic.cpp:681-787) loop by loop: heat_begin adds the loop's share of the ledger (:705-718), then
+// the ghosts' energies are refreshed (forward comm EI, :720-721: internally, or by the caller), heat_end diffuses (:725-785)
+int eph_b200_atomic_heat_loops(const eph_b200_atomic_handle *h) {
+  if (!h || !(h->cfg.flags & EPH_B200_FDM)) return 0;
+  return h->cfg.inner_loops > 0 ? h->cfg.inner_loops : 1;   // :695-699
+}
+
+int eph_b200_atomic_heat_begin(eph_b200_atomic_handle *h) {
+  if (!h) return EPH_B200_ERR_ARG;
+  int rc = ready(h, "atomic_heat_begin");
+  if (rc != EPH_B200_OK) return rc;
+  if (!h->packed || !h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "atomic_heat_begin: no post_force since the atoms were registered");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  const double scaling = 1.0 / static_cast<double>(eph_b200_atomic_heat_loops(h) > 0 ? eph_b200_atomic_heat_loops(h) : 1);
+  EPHA_LAUNCH(heat_add_kernel, blocks_for(nl, 256), 256, h->stream, nl, h->rec.p, h->dE.p, scaling, h->E.p);
+  EPHA_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+
+int eph_b200_atomic_heat_end(eph_b200_atomic_handle *h) {
+  if (!h) return EPH_B200_ERR_ARG;
+  int rc = ready(h, "atomic_heat_end");
+  if (rc != EPH_B200_OK) return rc;
+  if (!h->packed || !h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "atomic_heat_end: no post_force since the atoms were registered");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal, nt = nl + h->nghost;
+  if (nl == 0) return EPH_B200_OK;
+  cudaStream_t st = h->stream;
+  const int loops = eph_b200_atomic_heat_loops(h) > 0 ? eph_b200_atomic_heat_loops(h) : 1;
+  const double dt_loop = h->dt * (1.0 / static_cast<double>(loops));
+  const SweepArgs sa = sweep_args(h);
+  EPHA_LAUNCH(heat_prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->external_comm ? nullptr : h->owner.p, h->rec.p, h->rho_a.p, h->t,
+              h->E.p, h->hk.p);
+  EPHA_LAUNCH_CHECK(h);
+  EPHA_LAUNCH(heat_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->hk.p, h->E.p, dt_loop, h->E1.p);
+  EPHA_LAUNCH_CHECK(h);
+  EPHA_CUDA(h, cudaMemcpyAsync(h->E.p, h->E1.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));   // :783-785
+  return EPH_B200_OK;
+}
+
 int eph_b200_atomic_end_of_step(eph_b200_atomic_handle *h, double *Ee, double *Te) {
   if (!h) return EPH_B200_ERR_ARG;
   int rc = ready(h, "atomic_end_of_step");
   if (rc != EPH_B200_OK) return rc;
+  if (h->external_comm && eph_b200_atomic_heat_loops(h) > 0)
+    return fail(h, EPH_B200_ERR_ARG, "atomic_end_of_step: external comm mode uses heat_begin / heat_end per loop, then summary");
   cudaSetDevice(h->cfg.device);
-  const int nl = h->nlocal, nt = nl + h->nghost;
-  cudaStream_t st = h->stream;
-  if ((h->cfg.flags & EPH_B200_FDM) && nl > 0) {   // Flag::HEAT -> heat_solve, fix_eph_atomic.cpp:370, :681-787
-    if (!h->packed || !h->neigh_set) return fail(h, EPH_B200_ERR_ARG, "atomic_end_of_step: no post_force since the atoms were registered");
-    const int loops = h->cfg.inner_loops > 0 ? h->cfg.inner_loops : 1;   // :695-699
-    const double scaling = 1.0 / static_cast<double>(loops);
-    const double dt_loop = h->dt * scaling;
-    const SweepArgs sa = sweep_args(h);
-    for (int it = 0; it < loops; ++it) {
-      EPHA_LAUNCH(heat_add_kernel, blocks_for(nl, 256), 256, st, nl, h->rec.p, h->dE.p, scaling, h->E.p);
-      EPHA_LAUNCH_CHECK(h);
-      EPHA_LAUNCH(heat_prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->owner.p, h->rec.p, h->rho_a.p, h->t, h->E.p, h->hk.p);
-      EPHA_LAUNCH_CHECK(h);
-      EPHA_LAUNCH(heat_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->hk.p, h->E.p, dt_loop, h->E1.p);
-      EPHA_LAUNCH_CHECK(h);
-      EPHA_CUDA(h, cudaMemcpyAsync(h->E.p, h->E1.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));   // :783-785
+  if (h->nlocal > 0)
+    for (int it = 0; it < eph_b200_atomic_heat_loops(h); ++it) {   // Flag::HEAT -> heat_solve, fix_eph_atomic.cpp:370
+      if ((rc = eph_b200_atomic_heat_begin(h)) != EPH_B200_OK) return rc;
+      if ((rc = eph_b200_atomic_heat_end(h)) != EPH_B200_OK) return rc;     // heat_prep copies the owners' energies to the ghosts
     }
-  }
   return run_summary(h, Ee, Te);
 }
 

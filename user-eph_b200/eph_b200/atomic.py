@@ -36,6 +36,15 @@ SYMBOLS = {
     "eph_b200_atomic_set_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_atomic_get_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_atomic_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
+    "eph_b200_atomic_set_comm_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "eph_b200_atomic_post_force_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
+    "eph_b200_atomic_post_force_mid": (C.c_int, [C.c_void_p]),
+    "eph_b200_atomic_post_force_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_atomic_heat_loops": (C.c_int, [C.c_void_p]),
+    "eph_b200_atomic_heat_begin": (C.c_int, [C.c_void_p]),
+    "eph_b200_atomic_heat_end": (C.c_int, [C.c_void_p]),
+    "eph_b200_atomic_pack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "eph_b200_atomic_unpack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eph_b200_atomic_end_of_step": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "eph_b200_atomic_summary": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "eph_b200_atomic_get_peratom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -35,7 +35,6 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
   if (atom->natoms < 1) error->all(FLERR, "fix_eph_atomic: error no atoms in simulation");
   MPI_Comm_rank(world, &myID);
   MPI_Comm_size(world, &nrPS);
-  if (nrPS > 1) error->all(FLERR, "fix eph/atomic/b200: runs on one rank per box (ghosts must be images of the rank's own atoms)");
 
   state = FixState::NONE;
   vector_flag = 1;
@@ -92,9 +91,10 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
   }
 
   rng_mars = false;
+  comm_lammps = nrPS > 1;
   int device = 0;
   for (int k = n_elem + types; k < narg; ++k) {
-    const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0;
+    const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "comm") == 0;
     if (!is_keyword) continue;   // an extra element name (the reference's decks list more names than types)
     if (k + 1 >= narg) error->all(FLERR, "fix eph/atomic/b200: keyword without a value");
     const char *val = arg[k + 1];
@@ -102,11 +102,17 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
       if (strcmp(val, "mars") == 0) rng_mars = true;
       else if (strcmp(val, "philox") == 0) rng_mars = false;
       else error->all(FLERR, "fix eph/atomic/b200: rng must be mars or philox");
+    } else if (strcmp(arg[k], "comm") == 0) {
+      if (strcmp(val, "lammps") == 0) comm_lammps = true;
+      else if (strcmp(val, "device") == 0) comm_lammps = false;
+      else error->all(FLERR, "fix eph/atomic/b200: comm must be device or lammps");
     } else {
       device = atoi(val);
     }
     ++k;
   }
+  if (nrPS > 1 && !comm_lammps)
+    error->all(FLERR, "fix eph/atomic/b200: comm device needs one rank per box (ghosts must be images of the rank's own atoms); use comm lammps");
 
   dtv = update->dt;
   dtf = 0.5 * update->dt * force->ftm2v;
@@ -168,6 +174,7 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
           "set_kappa_tables");
   }
   check(eph_b200_atomic_set_dt(dev, update->dt, force->boltz), "set_dt");
+  check(eph_b200_atomic_set_comm_mode(dev, comm_lammps ? 1 : 0), "set_comm_mode");
 }
 
 FixEPHAtomicB200::~FixEPHAtomicB200() {
@@ -243,13 +250,13 @@ void FixEPHAtomicB200::final_integrate() {
 void FixEPHAtomicB200::upload_topology() {
   const int nlocal = atom->nlocal, nghost = atom->nghost;
   ghost_owner.assign(nghost, -1);
-  state = FixState::OWNER;   // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
-  comm->forward_comm(this);
-  state = FixState::NONE;
-  for (int g = 0; g < nghost; ++g)
-    if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/atomic/b200: ghost atom without a local owner");
+  if (!comm_lammps) {
+    forward(FixState::OWNER);   // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
+    for (int g = 0; g < nghost; ++g)
+      if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/atomic/b200: ghost atom without a local owner");
+  }
   check(eph_b200_atomic_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, reinterpret_cast<const int64_t *>(atom->tag),
-                                  ghost_owner.data(), EPH_B200_HOST),
+                                  comm_lammps ? nullptr : ghost_owner.data(), EPH_B200_HOST),
         "set_atoms");
   if (!list) error->all(FLERR, "fix eph/atomic/b200: no neighbour list");
   csr_offsets.assign((size_t)nlocal + 1, 0);
@@ -279,18 +286,55 @@ void FixEPHAtomicB200::post_force(int) {
       }
     xi = xi_host.data();
   }
-  if (nlocal + nghost == 0) return;
-  check(eph_b200_atomic_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
-                                   EPH_B200_HOST),
-        "post_force");
+  if (!comm_lammps) {
+    if (nlocal + nghost == 0) return;
+    check(eph_b200_atomic_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
+                                     EPH_B200_HOST),
+          "post_force");
+    return;
+  }
+  // the reference's transport and order of forward comms (fix_eph_atomic.cpp:803-825, :549-550); every rank takes part
+  // in every comm, with or without atoms
+  double dummy[3] = {0, 0, 0};
+  const double *xp = (nlocal + nghost) ? &atom->x[0][0] : dummy, *vp = (nlocal + nghost) ? &atom->v[0][0] : dummy;
+  check(eph_b200_atomic_post_force_begin(dev, xp, vp, xi, update->ntimestep, EPH_B200_HOST), "post_force");
+  forward(FixState::EI);
+  if (eph_flag & Flag::RANDOM) forward(FixState::XI);
+  forward(FixState::RHO);
+  check(eph_b200_atomic_post_force_mid(dev), "post_force");
+  if (eph_flag & Flag::FRICTION) forward(FixState::WI);
+  check(eph_b200_atomic_post_force_end(dev, nlocal ? &atom->f[0][0] : nullptr, EPH_B200_HOST), "post_force");
+}
+
+void FixEPHAtomicB200::forward(FixState st) {
+  state = st;
+  comm->forward_comm(this);
+  state = FixState::NONE;
 }
 
 void FixEPHAtomicB200::end_of_step() {
   const int nlocal = atom->nlocal;
   double E = 0.0, T = 0.0;
-  check(eph_b200_atomic_end_of_step(dev, &E, &T), "end_of_step");
+  if (!comm_lammps) {
+    check(eph_b200_atomic_end_of_step(dev, &E, &T), "end_of_step");
+  } else {
+    const int loops = eph_b200_atomic_heat_loops(dev);   // heat_solve with the EI forward comm of every loop (:720-721)
+    for (int it = 0; it < loops; ++it) {
+      check(eph_b200_atomic_heat_begin(dev), "heat_begin");
+      forward(FixState::EI);
+      check(eph_b200_atomic_heat_end(dev), "heat_end");
+    }
+    check(eph_b200_atomic_summary(dev, &E, &T), "summary");
+  }
+  // the reference's reductions (fix_eph_atomic.cpp:382-397): energies add up, temperatures are averaged over the ranks
+  // that hold group atoms (T comes back as NaN from a rank without any)
+  int proc_counter = (T == T) ? 1 : 0;
+  if (!proc_counter) T = 0.0;
+  MPI_Allreduce(MPI_IN_PLACE, &E, 1, MPI_DOUBLE, MPI_SUM, world);
+  MPI_Allreduce(MPI_IN_PLACE, &T, 1, MPI_DOUBLE, MPI_SUM, world);
+  MPI_Allreduce(MPI_IN_PLACE, &proc_counter, 1, MPI_INT, MPI_SUM, world);
   Ee = E;
-  Te = T;
+  Te = T / static_cast<double>(proc_counter);
   if (nlocal > 0) {
     check(eph_b200_atomic_get_energy(dev, E_a_i, EPH_B200_HOST), "get_energy");   // E_a_i travels with the atoms on the host
     check(eph_b200_atomic_get_peratom(dev, &array[0][0], EPH_B200_HOST), "get_peratom");
@@ -315,6 +359,12 @@ double FixEPHAtomicB200::compute_vector(int i) {   // fix_eph_atomic.cpp:839-847
   return Ee;
 }
 
+// FixEPHAtomic::pack_forward_comm / unpack_forward_comm (fix_eph_atomic.cpp:849-927): the payloads live on the device
+static int abi_state(FixEPHAtomicB200::FixState st) {
+  using S = FixEPHAtomicB200::FixState;
+  return st == S::RHO ? 1 : st == S::XI ? 2 : st == S::WI ? 3 : st == S::EI ? 4 : 0;
+}
+
 int FixEPHAtomicB200::pack_forward_comm(int n, int *list, double *data, int, int *) {
   int m = 0;
   if (state == FixState::OWNER) {
@@ -323,6 +373,9 @@ int FixEPHAtomicB200::pack_forward_comm(int n, int *list, double *data, int, int
       const int src = list[i];
       data[m++] = static_cast<double>(src < nlocal ? src : ghost_owner[src - nlocal]);
     }
+  } else if (abi_state(state)) {
+    m = eph_b200_atomic_pack_forward(dev, abi_state(state), n, list, data);
+    if (m < 0) check(m, "pack_forward");
   }
   return m;
 }
@@ -331,6 +384,8 @@ void FixEPHAtomicB200::unpack_forward_comm(int n, int first, double *data) {
   if (state == FixState::OWNER) {
     const int nlocal = atom->nlocal;
     for (int i = 0; i < n; ++i) ghost_owner[first + i - nlocal] = static_cast<int>(data[i]);
+  } else if (abi_state(state)) {
+    check(eph_b200_atomic_unpack_forward(dev, abi_state(state), n, first, data), "unpack_forward");
   }
 }
 

@@ -6,10 +6,12 @@
  *   rng mars|philox   source of the Gaussians xi_i (default philox: counter-based on the device, keyed on atom tags;
  *                     mars: LAMMPS' RanMars on the host in the reference's order, :808-816, uploaded every step)
  *   device N          CUDA device ordinal (default 0)
+ *   comm device|lammps ghost values through the engine's own owner map (one rank per box, default there) or through LAMMPS'
+ *                     Comm::forward_comm(Fix*) with host buffers in the reference's order (default for several ranks)
  * The same hooks are registered (:301-311), the same outputs produced (f_ID[1] = electronic energy of the group,
  * f_ID[2] = its mean temperature, 12 per-atom columns) and the per-atom electronic energy migrates with its atom
  * (copy_arrays / pack_exchange / unpack_exchange, :939-955).  All per-timestep work is done by libeph_b200
- * (include/eph_b200_atomic.h).  One rank per box: ghosts are periodic images of the rank's own atoms.
+ * (include/eph_b200_atomic.h).
  * Build with -DEPH_B200_REPLACE_FIX_EPH to register under the name `eph/atomic` itself.
  */
 #ifdef FIX_CLASS
@@ -37,7 +39,7 @@ namespace LAMMPS_NS {
 
 class FixEPHAtomicB200 : public Fix {
  public:
-  enum class FixState : unsigned int { NONE, OWNER };
+  enum class FixState : unsigned int { NONE, RHO, XI, WI, EI, OWNER };   // fix_eph_atomic.h:35-41 + the owner map
   // FixEPHAtomic::Flag (fix_eph_atomic.h:44-51)
   enum Flag : int { FRICTION = 0x01, RANDOM = 0x02, HEAT = 0x04, NOINT = 0x08, NOFRICTION = 0x10, NORANDOM = 0x20 };
 
@@ -84,6 +86,7 @@ class FixEPHAtomicB200 : public Fix {
   int seed;
   class RanMars *random;
   bool rng_mars;
+  bool comm_lammps;
   class NeighList *list;
   double Ee, Te;
   size_t n;
@@ -99,6 +102,7 @@ class FixEPHAtomicB200 : public Fix {
   bool need_upload;
 
   void upload_topology();
+  void forward(FixState st);
   void check(int rc, const char *what);
 };
 
