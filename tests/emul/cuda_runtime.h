@@ -1,50 +1,45 @@
 // TEST INFRASTRUCTURE -- never part of the product, never loaded by it.
 //
-// A serial stand-in for the slice of the CUDA runtime and device intrinsics that user-eph_b200/csrc/eph_atomic.cu uses,
-// so that the CPU test suite can compile THAT VERY SOURCE for the host (tests/emul/Makefile, -DEPHA_HOST_EMULATION,
-// this directory first on the include path so that <cuda_runtime.h> resolves here) and check the kernels' logic and
-// the C-ABI orchestration against the oracle in a container without a GPU.  Semantics: device memory is host memory,
-// streams are immediate, a kernel launch runs its threads one after the other (the kernels of that file use no shared
-// memory and no block-level synchronisation), one lane per atom (kLanes = 1), cross-lane shuffles see no other lane.
-// What this cannot check -- real sub-warp shuffles, memory ordering, launch configuration limits -- is covered by the
-// `-m gpu` tests on a B200.
+// Host stand-in for the slice of the CUDA runtime, driver types and device intrinsics that the product's sources under
+// user-eph_b200/csrc use, so that the CPU test suite can compile THOSE VERY SOURCES for the host (tests/emul/Makefile:
+// cu2cpp.py rewrites the launch syntax, this directory comes first on the include path so that <cuda_runtime.h> and
+// <cub/cub.cuh> resolve here) and check kernels and orchestration against the oracle in a container without a GPU.
+// Device memory is host memory, streams and events are immediate, kernels run under the lock-step SIMT stand-in of
+// simt.h (real sub-warp shuffles, ballots, block barriers, shared memory).  Not modelled: TMA / mbarrier (the tensor-map
+// encoder reports failure, so the engine takes its plain stencil path), memory ordering, timing.  What this cannot
+// check is covered by the `-m gpu` tests on a B200.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+
+#include "simt.h"
+
+#define EPHA_HOST_EMULATION 1
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__ static
+#define __align__(n) alignas(n)
 
 struct double2 { double x, y; };
-struct double4 { double x, y, z, w; };
+struct alignas(32) double4 { double x, y, z, w; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
-struct uint3_emul { unsigned x = 0, y = 0, z = 0; };
-namespace epha_emul {
-inline thread_local uint3_emul threadIdx_, blockIdx_, blockDim_, gridDim_;
-template <class F>
-void launch(int grid, int block, F &&body) {
-  gridDim_.x = (unsigned)grid;
-  blockDim_.x = (unsigned)block;
-  for (int b = 0; b < grid; ++b)
-    for (int t = 0; t < block; ++t) {
-      blockIdx_.x = (unsigned)b;
-      threadIdx_.x = (unsigned)t;
-      body();
-    }
-}
-}  // namespace epha_emul
-#define threadIdx epha_emul::threadIdx_
-#define blockIdx epha_emul::blockIdx_
-#define blockDim epha_emul::blockDim_
-#define gridDim epha_emul::gridDim_
+using std::max;
+using std::min;
 
 // ---- device intrinsics ----
 inline double __hiloint2double(int hi, int lo) {
@@ -58,21 +53,39 @@ inline int __double2loint(double d) {
   std::memcpy(&u, &d, 8);
   return (int)(uint32_t)u;
 }
+inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
+inline double __longlong_as_double(long long u) { double d; std::memcpy(&d, &u, 8); return d; }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <class T> inline T __ldcs(const T *p) { return *p; }
+template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
-// no other lane exists in the serial stand-in: a shuffle contributes nothing to a sum
-inline double __shfl_xor_sync(unsigned, double, int) { return 0.0; }
-inline double atomicAdd(double *p, double v) { const double old = *p; *p = old + v; return old; }
+inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+
+// single host thread: atomics are plain read-modify-writes
+template <class T> inline T atomicAdd(T *p, T v) { const T old = *p; *p = old + v; return old; }
+template <class T> inline T atomicMax(T *p, T v) { const T old = *p; if (v > old) *p = v; return old; }
+template <class T> inline T atomicMin(T *p, T v) { const T old = *p; if (v < old) *p = v; return old; }
+template <class T> inline T atomicOr(T *p, T v) { const T old = *p; *p = old | v; return old; }
+template <class T> inline T atomicCAS(T *p, T cmp, T v) { const T old = *p; if (old == cmp) *p = v; return old; }
+template <class T> inline T atomicExch(T *p, T v) { const T old = *p; *p = v; return old; }
 
 // ---- runtime ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600, cudaErrorNotSupported = 801 };
 typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum { cudaStreamNonBlocking = 1 };
-struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 4; };
-inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated error"; }
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEnableDefault = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+struct cudaDeviceProp {
+  int major = 10, minor = 0, multiProcessorCount = 2;
+  size_t sharedMemPerBlockOptin = 227 * 1024;
+};
+inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -81,17 +94,51 @@ inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
+// no driver behind this: the engine falls back where it asks for an entry point (tensor maps, stream memory operations)
+inline cudaError_t cudaGetDriverEntryPoint(const char *, void **p, unsigned long long, cudaDriverEntryPointQueryResult *q = nullptr) {
+  *p = nullptr;
+  if (q) *q = cudaDriverEntryPointSymbolNotFound;
+  return cudaErrorNotSupported;
+}
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) {
-  // poison fresh storage so that reads of unwritten device memory show up as NaNs in the tests
-  *p = static_cast<T *>(std::malloc(n ? n : 1));
+  // fresh storage is poisoned so that reads of unwritten device memory show up as NaNs / wild indices in the tests
+  *p = static_cast<T *>(std::aligned_alloc(256, (n + 255) / 256 * 256 + 256));
   if (!*p) return cudaErrorMemoryAllocation;
   std::memset(*p, 0xFF, n);
   return cudaSuccess;
 }
-template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = static_cast<T *>(std::malloc(n ? n : 1)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) {
+  *p = static_cast<T *>(std::malloc(n ? n : 1));
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+
+// ---- driver types named by the engine (never used: no entry point is ever handed out) ----
+typedef int CUresult;
+enum { CUDA_SUCCESS = 0 };
+typedef void *CUstream;
+typedef unsigned long long CUdeviceptr;
+typedef uint32_t cuuint32_t;
+typedef uint64_t cuuint64_t;
+struct alignas(64) CUtensorMap { unsigned char opaque[128]; };
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT64 = 10 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0 };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+enum { CU_STREAM_WAIT_VALUE_GEQ = 0 };

@@ -18,7 +18,7 @@ EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
 
 @pytest.fixture(scope="module")
 def emul():
-    subprocess.check_call(["make", "-C", EMUL], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", EMUL, "libeph_atomic_emul.so"], stdout=subprocess.DEVNULL)
     # one self-contained library (engine + host class), loaded privately: see tests/emul/Makefile
     L = A.declare(C.CDLL(os.path.join(EMUL, "libeph_atomic_emul.so")))
     return L, L

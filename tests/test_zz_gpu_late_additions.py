@@ -46,10 +46,27 @@ def _dummy_atom(eng):
     return x, z
 
 
+def _views(engs, nz, plane):
+    """the engines' current T_e buffers as [nz][plane] torch views of device memory (tests/test_engine_emulated.py
+    swaps in numpy views of the host build's memory)"""
+    import torch
+    for e in engs:
+        e.synchronize()
+    out = [e.grid_tensor(0).view(nz, plane) for e in engs]
+    torch.cuda.synchronize()
+    return out
+
+
+def _copy(dst, src):
+    if hasattr(dst, "copy_"):
+        dst.copy_(src)
+    else:
+        dst[...] = src
+
+
 def _solve_sharded(engs, xz, shape):
     """what eph_b200.parallel.sharded_grid_solve does over NCCL, with the ranks' engines in one process: slab sub-steps,
     halo planes copied between the engines' T_e arrays, slabs gathered at the end"""
-    import torch
     W = len(engs)
     nx, ny, nz = shape
     plane = nx * ny
@@ -63,9 +80,15 @@ def _solve_sharded(engs, xz, shape):
     n = ns[0]
 
     def views():
-        for e in engs:
-            e.synchronize()
-        return [e.grid_tensor(0).view(nz, plane) for e in engs]
+        return _views(engs, nz, plane)
+
+    def sync():
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+        except ImportError:
+            pass
 
     for s in range(n):
         for e, (z0, z1) in zip(engs, slabs):
@@ -74,16 +97,16 @@ def _solve_sharded(engs, xz, shape):
             Ts = views()
             for r, (z0, z1) in enumerate(slabs):
                 zlo, zhi = (z0 - 1) % nz, z1 % nz
-                Ts[r][zlo].copy_(Ts[(r - 1) % W][zlo])
-                Ts[r][zhi].copy_(Ts[(r + 1) % W][zhi])
-            torch.cuda.synchronize()
+                _copy(Ts[r][zlo], Ts[(r - 1) % W][zlo])
+                _copy(Ts[r][zhi], Ts[(r + 1) % W][zhi])
+            sync()
     if W > 1 and n > 0:
         Ts = views()
         for r in range(W):
             for q, (z0, z1) in enumerate(slabs):
                 if q != r:
-                    Ts[r][z0:z1].copy_(Ts[q][z0:z1])
-        torch.cuda.synchronize()
+                    _copy(Ts[r][z0:z1], Ts[q][z0:z1])
+        sync()
     for e in engs:
         e.end_of_step_end(True, external=True)
     return n

@@ -18,24 +18,9 @@
 
 using namespace ephb;
 
-// One place for the launch syntax.  tests/emul/ compiles this very file for the host (EPHA_HOST_EMULATION: a serial
-// SIMT stand-in, one lane per atom) so that the CPU test suite can check the kernels' logic and the orchestration
-// against the oracle before they ever reach a GPU; that build is test infrastructure and never part of the product.
-#ifdef EPHA_HOST_EMULATION
-#define EPHA_LAUNCH(kern, grid, block, stream, ...) epha_emul::launch((grid), (block), [&] { kern(__VA_ARGS__); })
-#define EPHA_WARP_LEADER true
-#else
-#define EPHA_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
-#define EPHA_WARP_LEADER ((threadIdx.x & 31) == 0)
-#endif
-
 namespace epha {
 
-#ifdef EPHA_HOST_EMULATION
-constexpr int kLanes = 1;
-#else
 constexpr int kLanes = 8;          // lanes per atom in the list sweeps
-#endif
 constexpr int kKappaShift = 16;    // bits 16..23 of the record's bit word: element index in the .kappa file
 
 // EPH_Linear::reverse_lookup (eph_linear.h:50-60): std::upper_bound over the knots, then the inverse of the segment.
@@ -416,7 +401,7 @@ __global__ void __launch_bounds__(256) summary_kernel(int nlocal, const int *__r
     c = 1.0;
   }
   e = warp_sum(e); T = warp_sum(T); c = warp_sum(c);
-  if (EPHA_WARP_LEADER && c != 0.0) {
+  if ((threadIdx.x & 31) == 0 && c != 0.0) {
     atomicAdd(scal + 0, e);
     atomicAdd(scal + 1, T);
     atomicAdd(scal + 2, c);
@@ -585,8 +570,7 @@ int run_summary(eph_b200_atomic_handle *h, double *Ee, double *Te) {
   const int nl = h->nlocal;
   EPHA_CUDA(h, cudaMemsetAsync(h->scal.p, 0, 4 * sizeof(double), h->stream));
   if (nl > 0) {
-    EPHA_LAUNCH(summary_kernel, blocks_for(nl, 256), 256, h->stream, nl, h->type_p, h->mask_p, h->d_tmk.p, h->cfg.groupbit, h->t, h->E.p,
-                                                               h->T_a.p, h->scal.p);
+    summary_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->type_p, h->mask_p, h->d_tmk.p, h->cfg.groupbit, h->t, h->E.p, h->T_a.p, h->scal.p);
     EPHA_LAUNCH_CHECK(h);
   }
   if (Ee || Te) {
@@ -816,8 +800,7 @@ int eph_b200_atomic_init_energy(eph_b200_atomic_handle *h, double T_init) {
   if (!h->kappa_set || !h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "atomic_init_energy: kappa tables and atoms first");
   cudaSetDevice(h->cfg.device);
   if (h->nlocal > 0) {
-    EPHA_LAUNCH(init_energy_kernel, blocks_for(h->nlocal, 256), 256, h->stream, h->nlocal, h->type_p, h->mask_p, h->d_tmk.p, h->cfg.groupbit,
-                                                                          h->t, T_init, h->E.p);
+    init_energy_kernel<<<blocks_for(h->nlocal, 256), 256, 0, h->stream>>>(h->nlocal, h->type_p, h->mask_p, h->d_tmk.p, h->cfg.groupbit, h->t, T_init, h->E.p);
     EPHA_LAUNCH_CHECK(h);
   }
   return EPH_B200_OK;
@@ -873,15 +856,14 @@ int eph_b200_atomic_post_force_begin(eph_b200_atomic_handle *h, const double *x,
   if ((rc = stage_in(h, h->v, v, 3 * (size_t)nt, memspace, &vd)) != EPH_B200_OK) return rc;
   if (xi_inject && do_random && (rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, memspace, &xid)) != EPH_B200_OK) return rc;
   cudaStream_t st = h->stream;
-  EPHA_LAUNCH(pack_kernel, blocks_for(nt, 256), 256, st, nt, xd, vd, h->type_p, h->mask_p, h->d_tmb.p, h->d_tmk.p, h->cfg.groupbit, h->rec.p);
+  pack_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(nt, xd, vd, h->type_p, h->mask_p, h->d_tmb.p, h->d_tmk.p, h->cfg.groupbit, h->rec.p);
   EPHA_LAUNCH_CHECK(h);
   h->packed = true;
   if (nl > 0) {
-    EPHA_LAUNCH(xi_kernel, blocks_for(nl, 256), 256, st, nl, h->mask_p, h->cfg.groupbit, do_random ? 1 : 0, xid, h->tag_p, h->cfg.seed,
-                (unsigned long long)ntimestep, h->xi.p);
+    xi_kernel<<<blocks_for(nl, 256), 256, 0, st>>>(nl, h->mask_p, h->cfg.groupbit, do_random ? 1 : 0, xid, h->tag_p, h->cfg.seed, (unsigned long long)ntimestep, h->xi.p);
     EPHA_LAUNCH_CHECK(h);
     const SweepArgs sa = sweep_args(h);
-    EPHA_LAUNCH(env_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->rho.p, h->rho_a.p);
+    env_kernel<kLanes><<<sweep_blocks(h), 256, 0, st>>>(sa, h->rho.p, h->rho_a.p);
     EPHA_LAUNCH_CHECK(h);
   }
   return EPH_B200_OK;
@@ -896,11 +878,11 @@ int eph_b200_atomic_post_force_mid(eph_b200_atomic_handle *h) {
   const int nl = h->nlocal, nt = nl + h->nghost;
   if (nt == 0) return EPH_B200_OK;
   cudaStream_t st = h->stream;
-  EPHA_LAUNCH(coupling_kernel, blocks_for(nt, 256), 256, st, nt, h->rec.p, h->rho.p, h->E.p, h->t, h->cp.p);
+  coupling_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(nt, h->rec.p, h->rho.p, h->E.p, h->t, h->cp.p);
   EPHA_LAUNCH_CHECK(h);
   if (nl > 0) {
     const SweepArgs sa = sweep_args(h);
-    EPHA_LAUNCH(w_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->cp.p, (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0, h->w.p);
+    w_kernel<kLanes><<<sweep_blocks(h), 256, 0, st>>>(sa, h->cp.p, (h->cfg.flags & EPH_B200_FRICTION) ? 1 : 0, h->w.p);
     EPHA_LAUNCH_CHECK(h);
   }
   return EPH_B200_OK;
@@ -923,7 +905,7 @@ int eph_b200_atomic_post_force_end(eph_b200_atomic_handle *h, double *f, int mem
     EPHA_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, st));
     fd = h->f.p;
   }
-  EPHA_LAUNCH(prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->external_comm ? nullptr : h->owner.p, h->cp.p, h->w.p, h->xi.p, h->q.p);
+  prep_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(nl, nt, h->external_comm ? nullptr : h->owner.p, h->cp.p, h->w.p, h->xi.p, h->q.p);
   EPHA_LAUNCH_CHECK(h);
   if (nl > 0) {
     ForceArgs p;
@@ -937,7 +919,7 @@ int eph_b200_atomic_post_force_end(eph_b200_atomic_handle *h, double *f, int mem
     p.f = fd;
     p.f_eph = h->f_eph.p; p.f_rng = h->f_rng.p; p.dE = h->dE.p;
     const SweepArgs sa = sweep_args(h);
-    EPHA_LAUNCH(force_kernel<kLanes>, sweep_blocks(h), 256, st, sa, p);
+    force_kernel<kLanes><<<sweep_blocks(h), 256, 0, st>>>(sa, p);
     EPHA_LAUNCH_CHECK(h);
   }
   if (f && memspace == EPH_B200_HOST) {
@@ -954,7 +936,7 @@ int eph_b200_atomic_post_force(eph_b200_atomic_handle *h, const double *x, const
   int rc = eph_b200_atomic_post_force_begin(h, x, v, xi_inject, ntimestep, memspace);
   if (rc != EPH_B200_OK) return rc;
   if (h->nghost > 0) {   // the EI and RHO forward comms (:803-804, :824-825) through the owner map
-    EPHA_LAUNCH(ghost_fill_kernel, blocks_for(h->nghost, 256), 256, h->stream, h->nlocal, h->nghost, h->owner.p, h->rho.p, h->rho_a.p, h->E.p);
+    ghost_fill_kernel<<<blocks_for(h->nghost, 256), 256, 0, h->stream>>>(h->nlocal, h->nghost, h->owner.p, h->rho.p, h->rho_a.p, h->E.p);
     EPHA_LAUNCH_CHECK(h);
   }
   if ((rc = eph_b200_atomic_post_force_mid(h)) != EPH_B200_OK) return rc;
@@ -976,7 +958,7 @@ int eph_b200_atomic_pack_forward(eph_b200_atomic_handle *h, int state, int n, co
   EPHA_CUDA(h, cudaMemcpyAsync(h->comm_idx.p, list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   const double *a0 = state == 1 ? h->rho.p : state == 2 ? h->xi.p : state == 3 ? h->w.p : h->E.p;
   const double *a1 = state == 1 ? h->rho_a.p : nullptr;
-  EPHA_LAUNCH(gather_kernel, blocks_for(n, 256), 256, st, n, h->comm_idx.p, width, a0, a1, h->comm_buf.p);
+  gather_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, h->comm_idx.p, width, a0, a1, h->comm_buf.p);
   EPHA_LAUNCH_CHECK(h);
   EPHA_CUDA(h, cudaMemcpyAsync(buf, h->comm_buf.p, (size_t)width * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   EPHA_CUDA(h, cudaStreamSynchronize(st));
@@ -994,7 +976,7 @@ int eph_b200_atomic_unpack_forward(eph_b200_atomic_handle *h, int state, int n, 
   if (state == 1) {
     EPHA_CUDA(h, h->comm_buf.reserve(2 * (size_t)n));
     EPHA_CUDA(h, cudaMemcpyAsync(h->comm_buf.p, buf, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-    EPHA_LAUNCH(scatter_pair_kernel, blocks_for(n, 256), 256, st, n, first, h->comm_buf.p, h->rho.p, h->rho_a.p);
+    scatter_pair_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, first, h->comm_buf.p, h->rho.p, h->rho_a.p);
     EPHA_LAUNCH_CHECK(h);
   } else if (state == 2 || state == 3) {   // rows [first, first + n) are contiguous
     double *dst = (state == 2 ? h->xi.p : h->w.p) + 3 * (size_t)first;
@@ -1031,7 +1013,7 @@ int eph_b200_atomic_heat_begin(eph_b200_atomic_handle *h) {
   const int nl = h->nlocal;
   if (nl == 0) return EPH_B200_OK;
   const double scaling = 1.0 / static_cast<double>(eph_b200_atomic_heat_loops(h) > 0 ? eph_b200_atomic_heat_loops(h) : 1);
-  EPHA_LAUNCH(heat_add_kernel, blocks_for(nl, 256), 256, h->stream, nl, h->rec.p, h->dE.p, scaling, h->E.p);
+  heat_add_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->rec.p, h->dE.p, scaling, h->E.p);
   EPHA_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
@@ -1048,10 +1030,9 @@ int eph_b200_atomic_heat_end(eph_b200_atomic_handle *h) {
   const int loops = eph_b200_atomic_heat_loops(h) > 0 ? eph_b200_atomic_heat_loops(h) : 1;
   const double dt_loop = h->dt * (1.0 / static_cast<double>(loops));
   const SweepArgs sa = sweep_args(h);
-  EPHA_LAUNCH(heat_prep_kernel, blocks_for(nt, 256), 256, st, nl, nt, h->external_comm ? nullptr : h->owner.p, h->rec.p, h->rho_a.p, h->t,
-              h->E.p, h->hk.p);
+  heat_prep_kernel<<<blocks_for(nt, 256), 256, 0, st>>>(nl, nt, h->external_comm ? nullptr : h->owner.p, h->rec.p, h->rho_a.p, h->t, h->E.p, h->hk.p);
   EPHA_LAUNCH_CHECK(h);
-  EPHA_LAUNCH(heat_kernel<kLanes>, sweep_blocks(h), 256, st, sa, h->hk.p, h->E.p, dt_loop, h->E1.p);
+  heat_kernel<kLanes><<<sweep_blocks(h), 256, 0, st>>>(sa, h->hk.p, h->E.p, dt_loop, h->E1.p);
   EPHA_LAUNCH_CHECK(h);
   EPHA_CUDA(h, cudaMemcpyAsync(h->E.p, h->E1.p, (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, st));   // :783-785
   return EPH_B200_OK;
@@ -1079,8 +1060,7 @@ int eph_b200_atomic_get_peratom(eph_b200_atomic_handle *h, double *array12, int 
   const int nl = h->nlocal;
   if (nl == 0) return EPH_B200_OK;
   double *dst = memspace == EPH_B200_DEVICE ? array12 : h->array12.p;
-  EPHA_LAUNCH(peratom_kernel, blocks_for(nl, 256), 256, h->stream, nl, h->type_p, h->mask_p, h->d_tmb.p, h->cfg.groupbit, h->t, h->rho.p,
-                                                             h->f_eph.p, h->f_rng.p, h->rho_a.p, h->E.p, h->dE.p, h->T_a.p, dst);
+  peratom_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->type_p, h->mask_p, h->d_tmb.p, h->cfg.groupbit, h->t, h->rho.p, h->f_eph.p, h->f_rng.p, h->rho_a.p, h->E.p, h->dE.p, h->T_a.p, dst);
   EPHA_LAUNCH_CHECK(h);
   if (memspace == EPH_B200_HOST) {
     EPHA_CUDA(h, cudaMemcpyAsync(array12, dst, 12 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
