@@ -74,3 +74,37 @@ def test_emulated_builtin_gaussian_stream(make_engine, kappa_tables):
 
 def test_emulated_size_independent_properties(make_engine, kappa_tables):
     cases.properties_case(make_engine, kappa_tables, 4)
+
+
+def test_emulated_device_memspace(make_engine, kappa_tables):
+    """memspace EPH_B200_DEVICE on the host build (device memory is host memory there): caller-owned type / mask / tag /
+    list arrays are aliased, x, v are read and f is updated in place, without staging copies"""
+    import numpy as np
+    from eph_b200 import harness as H
+    from oracle import oracle as O
+    import traj
+    from test_engine_emulated import dev
+    s = H.make_system(3)
+    nl = s["nlocal"]
+    eng = make_engine([0], [0], 7, inner_loops=2)
+    from eph_b200 import host
+    eng.set_tables_from(host.BetaTables(path=cases.BETA), kappa_tables)
+    eng.set_dt(1e-4)
+    keep = [dev(s["type"], np.int32), dev(s["mask"], np.int32), dev(s["tag"], np.int64), dev(s["ghost_owner"], np.int32),
+            dev(s["offsets"], np.int64), dev(s["neigh"], np.int32)]
+    eng.set_atoms(nl, s["nghost"], *keep[:4])
+    eng.set_neighbors(*keep[4:])
+    eng.init_energy(300.0)
+    fx = O.AtomicFix(s, O.Beta(path=cases.BETA), O.Kappa(cases.KAPPA), 7, inner_loops=2)
+    x, v = dev(s["x"].copy()), dev(s["v"].copy())
+    for step in (1, 2):
+        xi = np.random.default_rng(step).normal(size=(nl, 3))
+        f = dev(np.zeros((nl, 3)))
+        eng.post_force(x, v, f, dev(xi), step)
+        Ee, Te = eng.end_of_step()
+        fx.f[:] = 0.0
+        fx.post_force(xi)
+        fx.end_of_step()
+        assert H.error_metrics(np.asarray(f), fx.f[:nl]) < cases.TOL
+        assert H.error_metrics(eng.probe(6)[:nl], np.array(fx.ptr(6)[:nl])) < cases.TOL
+        assert abs(Ee - fx.Ee()) <= cases.TOL * fx.Ee() and abs(Te - fx.Te()) <= cases.TOL * fx.Te()

@@ -170,3 +170,62 @@ def test_emulated_sharded_grid_solve(synth_beta_1, shape, world, kind, monkeypat
     """the plane range of the plain stencil kernel and the plan / sub-step / external-finish calls of the sharded solve"""
     monkeypatch.setattr(GZ, "_views", _host_views)
     GZ.test_sharded_grid_solve_matches_replicated_solve_and_oracle(synth_beta_1, shape, world, kind)
+
+
+class DevArr(np.ndarray):
+    """numpy array that the Python binding takes for a device tensor (memspace EPH_B200_DEVICE): on the host build device
+    memory is host memory, so this drives the pointer-aliasing branches of the C ABI (no staging copies, f updated in
+    place, caller-owned type / mask / tag / list arrays) that GPU-resident callers use"""
+    is_cuda = True
+
+    def data_ptr(self):
+        return self.ctypes.data
+
+    def is_contiguous(self):
+        return bool(self.flags["C_CONTIGUOUS"])
+
+
+def dev(a, dtype=None):
+    return np.ascontiguousarray(a, dtype=dtype).view(DevArr)
+
+
+@pytest.mark.parametrize("flags", [7, 3, 7 | 16 | 32])
+def test_emulated_engine_device_memspace(sys500, synth_beta_1, flags):
+    s = sys500
+    nl = s["nlocal"]
+    rng = np.random.default_rng(41)
+    xis = [rng.normal(size=(nl, 3)) for _ in range(3)]
+    fx = O.Fix(s, O.Beta(path=synth_beta_1), O.FDM(3, 2, 2, G.box6(s), 300.0, 3.5e-6, 1.0, 0.1248), flags, dt=1e-4)
+    refs = traj.run_oracle(fx, s, xis, [58.71])
+    eng = G.make_engine(synth_beta_1, flags, (3, 2, 2), G.box6(s))
+    keep = [dev(s["type"], np.int32), dev(s["mask"], np.int32), dev(s["tag"], np.int64), dev(s["ghost_owner"], np.int32),
+            dev(s["offsets"], np.int64), dev(s["neigh"], np.int32)]
+    eng.set_atoms(nl, s["nghost"], *keep[:4])
+    eng.set_neighbors(*keep[4:])
+    sync = traj.GhostSync(s)
+    x, v, f = dev(s["x"].copy()), dev(s["v"].copy()), dev(np.zeros((nl, 3)))
+    m = np.array([0.0, 58.71])
+    Ee = 0.0
+    for step, (xi, ref) in enumerate(zip(xis, refs), start=1):
+        f[...] = 0.0
+        eng.initial_integrate(x, v, f, m, 1e-4, 0.5 * 1e-4 * H.FTM2V)
+        sync(x, v)
+        eng.post_force(x, v, f, dev(xi), step)
+        eng.final_integrate(v, f, m, 0.5 * 1e-4 * H.FTM2V)
+        sync(x, v)
+        Ee += eng.end_of_step(x, v)
+        for key, got in (("x", x[:nl]), ("v", v[:nl]), ("f", f), ("T", eng.get_grid(0)), ("array", eng.peratom()), ("w", eng.probe(1))):
+            assert H.error_metrics(np.asarray(got), ref[key]) < G.TOL, (step, key)
+        assert abs(Ee - ref["Ee"]) <= G.TOL * max(abs(ref["Ee"]), 1e-300)
+
+
+def test_simt_stand_in_selftest():
+    """the lock-step stand-in itself: closed-form results for block barriers with early-exiting threads, sub-warp
+    shuffles with different trip counts per group, ballots, 3-D launches and dynamic shared memory -- and a collective
+    whose mask names a lane that never arrives must be reported as a dead-lock, not pass"""
+    subprocess.check_call(["make", "-C", EMUL, "selftest"], stdout=subprocess.DEVNULL)
+    exe = os.path.join(EMUL, "selftest")
+    ok = subprocess.run([exe, "ok"], capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "selftest ok" in ok.stdout, ok.stdout + ok.stderr
+    bad = subprocess.run([exe, "deadlock"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and "dead-lock" in bad.stderr and "not reached" not in bad.stdout
