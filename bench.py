@@ -479,14 +479,17 @@ def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):
     k_ms = kt[0] / max(kt[1], 1)
     ach = 60.0 * cells / (k_ms * 1e-3) / 1e9
     eng.close()
-    # the grid of this benchmark has constant coefficients, so the engine takes its constant-coefficient TMA kernel, which
-    # really moves 24 B per cell-update (T_e in/out, dT_e in); `achieved` uses the 60 B of the general path
+    # the grid of this benchmark has constant coefficients, so the engine takes its constant-coefficient TMA kernel, whose
+    # algorithmic traffic is 24 B per cell-update (T_e in/out, dT_e in): that is what `achieved` / `frac` are measured on.
+    # The 60 B per cell-update of the general variable-coefficient path is reported next to it as a
+    # convention only (it exceeds the peak because this kernel does not move those bytes).
     actual = 24.0 * cells / (k_ms * 1e-3) / 1e9
     return {"metric": "FDM Mcell-updates/s", "value": rate / 1e6, "unit": "Mcell-updates/s", "grid": [n] * 3, "substeps": sub,
             "solves": solves, "ms_per_solve": ms / solves,
-            "roofline": {"bound": "hbm", "kernel": "fdm_substep (constant-coefficient TMA path)", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_cell_update": 60, "kernel_ms": k_ms,
-                         "actual_bytes_per_cell_update": 24, "actual_gbs": actual, "actual_frac": actual / peak}}
+            "roofline": {"bound": "hbm", "kernel": "fdm_substep (constant-coefficient TMA path)", "achieved": actual, "peak": peak,
+                         "unit": "GB/s", "frac": actual / peak, "algorithmic_bytes_per_cell_update": 24, "kernel_ms": k_ms,
+                         "survey_convention": {"bytes_per_cell_update": 60, "gbs": ach, "frac": ach / peak,
+                                               "note": "general-path byte count applied to the constant-coefficient kernel"}}}
 
 
 def main():
