@@ -108,3 +108,20 @@ def test_emulated_device_memspace(make_engine, kappa_tables):
         assert H.error_metrics(np.asarray(f), fx.f[:nl]) < cases.TOL
         assert H.error_metrics(eng.probe(6)[:nl], np.array(fx.ptr(6)[:nl])) < cases.TOL
         assert abs(Ee - fx.Ee()) <= cases.TOL * fx.Ee() and abs(Te - fx.Te()) <= cases.TOL * fx.Te()
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_fuzz_atomic_configurations(seed, make_engine, kappa_tables, tmp_path):
+    import numpy as np
+    from eph_b200 import harness as H
+    rng = np.random.default_rng(seed)
+    beta2 = str(H.write_beta_file(tmp_path / "synth2.beta", H.synthetic_knots(2, n_beta=5001, drho=0.01)))
+    for it in range(10):
+        flags = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 7 | 8, 7 | 16, 7 | 32, 7 | 16 | 32]))
+        loops = int(rng.integers(0, 4))
+        gf = None if rng.random() < 0.5 else float(rng.uniform(0.2, 0.9))
+        n = int(rng.integers(2, 5))
+        if rng.random() < 0.4:
+            cases.trajectory_case(make_engine, kappa_tables, flags, loops, gf, n=n, steps=2, ntypes=2, beta=beta2, names=("Ni", "Co"))
+        else:
+            cases.trajectory_case(make_engine, kappa_tables, flags, loops, gf, n=n, steps=int(rng.integers(1, 4)))
