@@ -494,7 +494,7 @@ struct eph_b200_atomic_handle {
   const int *type_p = nullptr, *mask_p = nullptr;
   const long long *tag_p = nullptr, *off_p = nullptr;
   const int *neigh_p = nullptr;
-  DevBuf<double> x, v, f, xi_in, stage;
+  DevBuf<double> x, v, f, xi_in;
   // external ghost transport (LAMMPS' Comm::forward_comm(Fix*) with host buffers): no owner map, phase-split calls
   bool external_comm = false;
   int phase = 0;                 // 0 idle, 1 after post_force_begin, 2 after post_force_mid
@@ -650,7 +650,7 @@ int eph_b200_atomic_destroy(eph_b200_atomic_handle *h) {
   cudaStreamSynchronize(h->stream);
   h->rho_tab.release(); h->alpha_tab.release(); h->beta_tab.release(); h->rhoa_tab.release(); h->E_T.release(); h->K_T.release();
   h->type.release(); h->mask.release(); h->owner.release(); h->d_tmb.release(); h->d_tmk.release(); h->tag.release();
-  h->off.release(); h->neigh.release(); h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->stage.release(); h->comm_idx.release(); h->comm_buf.release();
+  h->off.release(); h->neigh.release(); h->x.release(); h->v.release(); h->f.release(); h->xi_in.release(); h->comm_idx.release(); h->comm_buf.release();
   h->rec.release(); h->cp.release(); h->q.release(); h->hk.release();
   h->rho.release(); h->rho_a.release(); h->E.release(); h->E1.release(); h->dE.release(); h->T_a.release(); h->w.release();
   h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array12.release(); h->scal.release();
