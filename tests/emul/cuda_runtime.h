@@ -5,14 +5,16 @@
 // cu2cpp.py rewrites the launch syntax, this directory comes first on the include path so that <cuda_runtime.h> and
 // <cub/cub.cuh> resolve here) and check kernels and orchestration against the oracle in a container without a GPU.
 // Device memory is host memory, streams and events are immediate, kernels run under the lock-step SIMT stand-in of
-// simt.h (real sub-warp shuffles, ballots, block barriers, shared memory).  Not modelled: TMA / mbarrier (the tensor-map
-// encoder reports failure, so the engine takes its plain stencil path), memory ordering, timing.  What this cannot
+// simt.h (real sub-warp shuffles, ballots, block barriers, shared memory).  TMA box loads are synchronous copies described by
+// a tensor map kept in the clear and mbarrier waits are already satisfied (cu2cpp.py maps the two PTX statements).  Not
+// modelled: memory ordering, asynchrony, timing.  What this cannot
 // check is covered by the `-m gpu` tests on a B200.
 #pragma once
 
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -104,12 +106,6 @@ inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
-// no driver behind this: the engine falls back where it asks for an entry point (tensor maps, stream memory operations)
-inline cudaError_t cudaGetDriverEntryPoint(const char *, void **p, unsigned long long, cudaDriverEntryPointQueryResult *q = nullptr) {
-  *p = nullptr;
-  if (q) *q = cudaDriverEntryPointSymbolNotFound;
-  return cudaErrorNotSupported;
-}
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) {
   // fresh storage is poisoned so that reads of unwritten device memory show up as NaNs / wild indices in the tests
   *p = static_cast<T *>(std::aligned_alloc(256, (n + 255) / 256 * 256 + 256));
@@ -128,17 +124,61 @@ inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
 
-// ---- driver types named by the engine (never used: no entry point is ever handed out) ----
+// ---- the two driver entry points the engine asks for ----
 typedef int CUresult;
 enum { CUDA_SUCCESS = 0 };
 typedef void *CUstream;
 typedef unsigned long long CUdeviceptr;
 typedef uint32_t cuuint32_t;
 typedef uint64_t cuuint64_t;
-struct alignas(64) CUtensorMap { unsigned char opaque[128]; };
 enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT64 = 10 };
 enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
 enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0 };
 enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
 enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
 enum { CU_STREAM_WAIT_VALUE_GEQ = 0 };
+// a tiled tensor map: what cuTensorMapEncodeTiled is told, kept in the clear (the real one is an opaque 128-byte blob)
+struct alignas(64) CUtensorMap {
+  unsigned char *base;
+  uint64_t dims[3], strides[2];   // elements; bytes between rows / planes
+  uint32_t box[3];
+  uint32_t elem_bytes, rank;
+  unsigned char pad[128 - 8 - 24 - 16 - 12 - 8];
+};
+inline CUresult emul_cuTensorMapEncodeTiled(CUtensorMap *map, CUtensorMapDataType dt, cuuint32_t rank, void *base, const cuuint64_t *dims,
+                                            const cuuint64_t *strides, const cuuint32_t *box, const cuuint32_t *, CUtensorMapInterleave,
+                                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  if (rank != 3 || dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15) || (strides[1] & 15)) return 1;   // the real encoder's alignment rules
+  std::memset(map, 0, sizeof *map);
+  map->base = static_cast<unsigned char *>(base);
+  for (int d = 0; d < 3; ++d) { map->dims[d] = dims[d]; map->box[d] = box[d]; }
+  map->strides[0] = strides[0]; map->strides[1] = strides[1];
+  map->elem_bytes = 8; map->rank = 3;
+  return CUDA_SUCCESS;
+}
+// cp.async.bulk.tensor.3d: the box starting at (c0, c1, c2), row-major in shared memory, elements outside the tensor zero
+inline long long g_emul_tma_loads = 0;   // read by the tests through emul_tma_load_count() (emul_probe.cpp)
+inline void emul_tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2) {
+  ++g_emul_tma_loads;
+  if (c0 & 1) { std::fprintf(stderr, "emulated TMA: fp64 box starts at odd x = %d (16-byte rule)\n", c0); std::abort(); }
+  double *out = static_cast<double *>(dst);
+  for (uint32_t z = 0; z < map->box[2]; ++z)
+    for (uint32_t y = 0; y < map->box[1]; ++y)
+      for (uint32_t x = 0; x < map->box[0]; ++x) {
+        const long long gx = (long long)c0 + x, gy = (long long)c1 + y, gz = (long long)c2 + z;
+        double v = 0.0;
+        if (gx >= 0 && gy >= 0 && gz >= 0 && gx < (long long)map->dims[0] && gy < (long long)map->dims[1] && gz < (long long)map->dims[2])
+          std::memcpy(&v, map->base + gx * 8 + gy * map->strides[0] + gz * map->strides[1], 8);
+        *out++ = v;
+      }
+}
+// streams are immediate: whatever a wait would wait for has already happened
+inline CUresult emul_cuStreamWaitValue32(CUstream, CUdeviceptr, cuuint32_t, unsigned) { return CUDA_SUCCESS; }
+inline cudaError_t cudaGetDriverEntryPoint(const char *name, void **p, unsigned long long, cudaDriverEntryPointQueryResult *q = nullptr) {
+  *p = nullptr;
+  if (std::strcmp(name, "cuTensorMapEncodeTiled") == 0 && !std::getenv("EPH_EMUL_NO_TMA")) *p = reinterpret_cast<void *>(&emul_cuTensorMapEncodeTiled);
+  if (std::strcmp(name, "cuStreamWaitValue32") == 0) *p = reinterpret_cast<void *>(&emul_cuStreamWaitValue32);
+  if (q) *q = *p ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return *p ? cudaSuccess : cudaErrorNotSupported;
+}

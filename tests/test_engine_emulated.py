@@ -4,8 +4,9 @@ a lock-step SIMT stand-in (tests/emul: every CUDA thread a fiber, real sub-warp 
 shared memory) and driven through the same C ABI, Python binding and FixEPHB200 host class as on the device.  The test
 bodies are the ones of the `-m gpu` suite (tests/test_gpu_parity.py, test_zy_gpu_coloured.py,
 test_zz_gpu_late_additions.py), called here with the emulated library swapped in, against the oracle at the 1e-10 bar.
-Not covered here: the TMA stencil kernels (no tensor maps on the host: the engine takes its plain stencil path), device
-pointers, stream overlap, anything about speed.  Test infrastructure only: the product has no CPU fallback."""
+The TMA stencil kernels run too (a tensor map kept in the clear, box loads as synchronous copies with zero fill outside the
+tensor, mbarrier waits already satisfied).  Not covered here: asynchrony and memory ordering, stream overlap, anything
+about speed.  Test infrastructure only: the product has no CPU fallback."""
 import ctypes as C
 import os
 import subprocess
@@ -38,6 +39,7 @@ def emulated_engine():
     for n in ("ephh_beta_load", "ephh_beta_from_knots", "ephh_grid_load"):
         getattr(L, n).restype = C.c_void_p
     L.ephh_grid_tables.restype = C.c_double
+    L.emul_tma_load_count.restype = C.c_longlong
     saved = (lib._lib, host._fix)
     lib._lib, host._fix = L, L
     yield L
@@ -103,8 +105,10 @@ def test_emulated_grid_solve(synth_beta_1, shape, walls, constant):
 
 
 @pytest.mark.parametrize("shape", [(32, 16, 8), (16, 4, 5)])
-def test_emulated_grid_uniform_parameters(synth_beta_1, shape):
+def test_emulated_grid_uniform_parameters(synth_beta_1, shape, emulated_engine):
+    before = emulated_engine.emul_tma_load_count()
     G.test_grid_uniform_fast_path_matches_oracle(synth_beta_1, shape)
+    assert emulated_engine.emul_tma_load_count() > before     # the constant-coefficient TMA kernel did the work
 
 
 @pytest.mark.parametrize("shape", [(6, 5, 4), (32, 5, 4)])
@@ -166,10 +170,13 @@ def _host_views(engs, nz, plane):
 
 @pytest.mark.parametrize("shape,world,kind", [((32, 6, 8), 2, "walls"), ((32, 6, 8), 4, "walls"), ((33, 9, 6), 3, "walls"),
                                               ((32, 16, 8), 2, "uniform"), ((16, 4, 4), 4, "general")])
-def test_emulated_sharded_grid_solve(synth_beta_1, shape, world, kind, monkeypatch):
-    """the plane range of the plain stencil kernel and the plan / sub-step / external-finish calls of the sharded solve"""
+def test_emulated_sharded_grid_solve(synth_beta_1, shape, world, kind, monkeypatch, emulated_engine):
+    """the plane range of the three stencil kernels and the plan / sub-step / external-finish calls of the sharded solve"""
     monkeypatch.setattr(GZ, "_views", _host_views)
+    before = emulated_engine.emul_tma_load_count()
     GZ.test_sharded_grid_solve_matches_replicated_solve_and_oracle(synth_beta_1, shape, world, kind)
+    # even nx: the plane range of the two TMA kernels; odd nx (33, 9, 6): that of the plain kernel
+    assert (emulated_engine.emul_tma_load_count() > before) == (shape[0] % 2 == 0)
 
 
 class DevArr(np.ndarray):
