@@ -68,7 +68,12 @@ def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first):
         eng.set_neighbors(*keep[4:])
         src = torch.zeros(int(np.prod(gshape)), dtype=torch.float64)
         eng.bind_grid_source(src)
-        if boundary_first:   # the density pass sweeps the tiles other ranks wait for first (tile_mark / tile_split)
+        if boundary_first:
+            # the density pass sweeps the tiles other ranks wait for first (tile_mark / tile_split), and with a
+            # communication stream registered the pack waits on the finished-tile counter (cuStreamWaitValue32) and
+            # post_force_end on the unpack event; streams are immediate on the host build, so this checks the
+            # bookkeeping of that path, not its overlap
+            eng.set_comm_stream(0x10)
             eng.set_boundary_atoms(np.ascontiguousarray(plan.flat_send_index(), dtype=np.int32))
         x, v = torch.as_tensor(s["x"].copy()), torch.as_tensor(s["v"].copy())
         f = torch.zeros((nl, 3), dtype=torch.float64)
