@@ -20,6 +20,10 @@
 
 #include "simt.h"
 
+#ifdef EPHA_EMUL_EXACT_ALLOC
+#include <sanitizer/asan_interface.h>
+#endif
+
 #define EPHA_HOST_EMULATION 1
 
 #define __global__
@@ -108,7 +112,12 @@ template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute,
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) {
   // fresh storage is poisoned so that reads of unwritten device memory show up as NaNs / wild indices in the tests
+#ifdef EPHA_EMUL_EXACT_ALLOC   // AddressSanitizer build: the poisoned zone starts right behind the last byte asked for
+  *p = static_cast<T *>(std::aligned_alloc(32, (n + 31) / 32 * 32));
+  if (*p && n % 32) ASAN_POISON_MEMORY_REGION(reinterpret_cast<char *>(*p) + n, 32 - n % 32);
+#else
   *p = static_cast<T *>(std::aligned_alloc(256, (n + 255) / 256 * 256 + 256));
+#endif
   if (!*p) return cudaErrorMemoryAllocation;
   std::memset(*p, 0xFF, n);
   return cudaSuccess;

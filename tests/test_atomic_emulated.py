@@ -20,7 +20,7 @@ EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
 def emul():
     subprocess.check_call(["make", "-C", EMUL, "libeph_atomic_emul.so"], stdout=subprocess.DEVNULL)
     # one self-contained library (engine + host class), loaded privately: see tests/emul/Makefile
-    L = A.declare(C.CDLL(os.path.join(EMUL, "libeph_atomic_emul.so")))
+    L = A.declare(C.CDLL(os.path.join(EMUL, "libeph_atomic_emul%s.so" % os.environ.get("EPH_EMUL_SUFFIX", ""))))
     return L, L
 
 
@@ -105,7 +105,7 @@ def test_emulated_device_memspace(make_engine, kappa_tables):
         fx.f[:] = 0.0
         fx.post_force(xi)
         fx.end_of_step()
-        assert H.error_metrics(np.asarray(f), fx.f[:nl]) < cases.TOL
+        assert H.error_metrics(f.a, fx.f[:nl]) < cases.TOL
         assert H.error_metrics(eng.probe(6)[:nl], np.array(fx.ptr(6)[:nl])) < cases.TOL
         assert abs(Ee - fx.Ee()) <= cases.TOL * fx.Ee() and abs(Te - fx.Te()) <= cases.TOL * fx.Te()
 

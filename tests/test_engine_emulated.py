@@ -30,7 +30,7 @@ EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
 def emulated_engine():
     """swap the emulated library in for the product's two (engine + host side) while this module runs"""
     subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
-    L = C.CDLL(os.path.join(EMUL, "libeph_b200_emul.so"))   # private: no RTLD_GLOBAL, linked -Bsymbolic
+    L = C.CDLL(os.path.join(EMUL, "libeph_b200_emul%s.so" % os.environ.get("EPH_EMUL_SUFFIX", "")))   # private: no RTLD_GLOBAL, linked -Bsymbolic
     for name, (res, args) in lib.SYMBOLS.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -179,21 +179,28 @@ def test_emulated_sharded_grid_solve(synth_beta_1, shape, world, kind, monkeypat
     assert (emulated_engine.emul_tma_load_count() > before) == (shape[0] % 2 == 0)
 
 
-class DevArr(np.ndarray):
-    """numpy array that the Python binding takes for a device tensor (memspace EPH_B200_DEVICE): on the host build device
-    memory is host memory, so this drives the pointer-aliasing branches of the C ABI (no staging copies, f updated in
-    place, caller-owned type / mask / tag / list arrays) that GPU-resident callers use"""
+class DevArr:
+    """what the Python binding takes for a device tensor (memspace EPH_B200_DEVICE), wrapped around a numpy array: on the
+    host build device memory is host memory, so this drives the pointer-aliasing branches of the C ABI (no staging
+    copies, f updated in place, caller-owned type / mask / tag / list arrays) that GPU-resident callers use.  `.a` is
+    the array itself, for the harness' own arithmetic."""
     is_cuda = True
 
+    def __init__(self, a, dtype=None):
+        self.a = np.ascontiguousarray(a, dtype=dtype)
+
     def data_ptr(self):
-        return self.ctypes.data
+        return self.a.ctypes.data
 
     def is_contiguous(self):
-        return bool(self.flags["C_CONTIGUOUS"])
+        return True
+
+    def __len__(self):
+        return len(self.a)
 
 
 def dev(a, dtype=None):
-    return np.ascontiguousarray(a, dtype=dtype).view(DevArr)
+    return DevArr(a, dtype)
 
 
 @pytest.mark.parametrize("flags", [7, 3, 7 | 16 | 32])
@@ -214,14 +221,14 @@ def test_emulated_engine_device_memspace(sys500, synth_beta_1, flags):
     m = np.array([0.0, 58.71])
     Ee = 0.0
     for step, (xi, ref) in enumerate(zip(xis, refs), start=1):
-        f[...] = 0.0
+        f.a[...] = 0.0
         eng.initial_integrate(x, v, f, m, 1e-4, 0.5 * 1e-4 * H.FTM2V)
-        sync(x, v)
+        sync(x.a, v.a)
         eng.post_force(x, v, f, dev(xi), step)
         eng.final_integrate(v, f, m, 0.5 * 1e-4 * H.FTM2V)
-        sync(x, v)
+        sync(x.a, v.a)
         Ee += eng.end_of_step(x, v)
-        for key, got in (("x", x[:nl]), ("v", v[:nl]), ("f", f), ("T", eng.get_grid(0)), ("array", eng.peratom()), ("w", eng.probe(1))):
+        for key, got in (("x", x.a[:nl]), ("v", v.a[:nl]), ("f", f.a), ("T", eng.get_grid(0)), ("array", eng.peratom()), ("w", eng.probe(1))):
             assert H.error_metrics(np.asarray(got), ref[key]) < G.TOL, (step, key)
         assert abs(Ee - ref["Ee"]) <= G.TOL * max(abs(ref["Ee"]), 1e-300)
 

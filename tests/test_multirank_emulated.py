@@ -27,7 +27,7 @@ CELLS, SEED, DT = 6, 4711, 1e-4
 
 
 def _swap_in_emulated_engine():
-    L = C.CDLL(os.path.join(EMUL, "libeph_b200_emul.so"))
+    L = C.CDLL(os.path.join(EMUL, "libeph_b200_emul%s.so" % os.environ.get("EPH_EMUL_SUFFIX", "")))
     for name, (res, args) in lib.SYMBOLS.items():
         fn = getattr(L, name)
         fn.restype = res
