@@ -2,7 +2,8 @@
 // sources.  `selftest ok` runs kernels whose results are known in closed form (block reduction through shared memory and
 // __syncthreads with early-exiting threads, sub-warp shuffles under group masks with different trip counts per group,
 // ballots, a 3-D launch, dynamic shared memory); `selftest deadlock` runs a kernel whose lanes name a mask that one of
-// them never joins and must be stopped by the dead-lock report (exit through abort).
+// them never joins and must be stopped by the dead-lock report (exit through abort); `selftest race` runs a kernel that
+// misses a barrier: its checksum must differ between SIMT_ORDER settings, which is how the host build exposes races.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -47,6 +48,16 @@ __global__ void dyn_smem_3d_kernel(int nx, int ny, int nz, int *out) {
   if (x < nx && y < ny && z < nz) out[x + nx * (y + ny * z)] = tile[n - 1 - t] + 1000 * (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
 }
 
+// a missing barrier: thread t reads its neighbour's slot without waiting for the neighbour to write it
+__global__ void racy_kernel(int *out) {
+  __shared__ int slot[64];
+  slot[threadIdx.x] = 0;
+  __syncthreads();
+  slot[threadIdx.x] = 100 + threadIdx.x;
+  // __syncthreads() belongs here
+  out[threadIdx.x] = slot[(threadIdx.x + 1) % 64];
+}
+
 __global__ void bad_mask_kernel(int *out) {
   const int lane = threadIdx.x & 31;
   int v = lane;
@@ -59,6 +70,14 @@ int main(int argc, char **argv) {
     std::vector<int> out(32);
     bad_mask_kernel<<<1, 32>>>(out.data());
     std::printf("not reached\n");
+    return 0;
+  }
+  if (argc > 1 && std::strcmp(argv[1], "race") == 0) {   // the sum depends on the order the fibers are resumed in (SIMT_ORDER)
+    std::vector<int> out(64);
+    racy_kernel<<<1, 64>>>(out.data());
+    long long sum = 0;
+    for (int v : out) sum += v;
+    std::printf("race checksum %lld\n", sum);
     return 0;
   }
   int bad = 0;

@@ -172,11 +172,26 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F &&body) {
           makecontext(&f.ctx, trampoline, 0);
           f.done = false;
         }
+        // SIMT_ORDER=reverse | random: the order in which parked fibers are resumed.  Results must not depend on it
+        // (beyond the rounding of atomic sums): a kernel that misses a barrier between a shared-memory or global write
+        // and another thread's read gives different answers under different orders -- the host build's racecheck.
+        static const int order_mode = [] {
+          const char *e = std::getenv("SIMT_ORDER");
+          return !e ? 0 : std::strcmp(e, "reverse") == 0 ? 1 : std::strcmp(e, "random") == 0 ? 2 : 0;
+        }();
+        static unsigned long long lcg = 0x9E3779B97F4A7C15ULL;
         int remaining = n;
         while (remaining > 0) {
           const long long before = s.progress;
           remaining = 0;
-          for (int t = 0; t < n; ++t) {
+          int start = 0, step = 1;
+          if (order_mode == 1) { start = n - 1; step = -1; }
+          if (order_mode == 2) {
+            lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+            start = (int)((lcg >> 33) % (unsigned long long)n);
+            step = ((lcg >> 20) & 1) ? 1 : -1;
+          }
+          for (int k = 0, t = start; k < n; ++k, t = (t + step + n) % n) {
             if (s.fibers[t].done) continue;
             set_thread(t);
             swapcontext(&s.sched, &s.fibers[t].ctx);

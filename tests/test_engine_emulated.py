@@ -243,3 +243,8 @@ def test_simt_stand_in_selftest():
     assert ok.returncode == 0 and "selftest ok" in ok.stdout, ok.stdout + ok.stderr
     bad = subprocess.run([exe, "deadlock"], capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and "dead-lock" in bad.stderr and "not reached" not in bad.stdout
+    # a kernel that misses a barrier answers differently when the fibers are resumed in another order: running the
+    # suites under SIMT_ORDER=reverse / random is the host build's racecheck (all product kernels are order-independent)
+    sums = {mode: subprocess.run([exe, "race"], capture_output=True, text=True, timeout=120,
+                                 env=dict(os.environ, SIMT_ORDER=mode)).stdout for mode in ("forward", "reverse")}
+    assert "race checksum" in sums["forward"] and sums["forward"] != sums["reverse"], sums
