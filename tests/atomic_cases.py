@@ -177,3 +177,12 @@ def properties_case(make_engine, kappa_tables, n, steps=2, loops=2):
         v[:nl] += 0.5 * dt * H.FTM2V / 58.71 * f       # keep the state moving between the steps
         x[:nl] += dt * v[:nl]
         sync(x, v)
+
+
+def reordering_case(make_fix, comm="device"):
+    """LAMMPS re-orders the local atoms (spatial sort): FixEPHAtomicB200 carries E_a_i along through copy_arrays and
+    re-registers it on the device, so the trajectory continues as if nothing had happened"""
+    s = H.make_system(3)
+    xi = [np.random.default_rng(40 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
+    args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2, style="eph/atomic/b200") + ["rng", "mars", "comm", comm]
+    traj.assert_reordering_is_transparent(lambda system: make_fix(system, args), s, xi, permute_after=2, tol=TOL)

@@ -9,7 +9,9 @@
 // the bottom (p_rho, p_w, p_xi, p_feph, p_frng, grid_size, grid_T).
 #pragma once
 
+#include <algorithm>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -152,6 +154,76 @@ int world_set_xi(World<FixT> *w, const double *xi) {
   });
 }
 
+// What LAMMPS' spatial sort (atom_modify sort, every 1000 steps by default) does to a fix: the local atoms are
+// re-ordered -- the atom at index i moves to new_of_old[i] -- and the fix is told through copy_arrays(i, j, 0) calls
+// that walk the cycles of the permutation with one scratch slot, exactly like AtomVec / Modify::copy_arrays in
+// Atom::sort().  The harness' own arrays, the ghost->owner map and the neighbour list are relabelled accordingly, so
+// the physics is unchanged and a fix that migrates its per-atom state correctly continues the same trajectory.
+template <class FixT>
+int world_permute(World<FixT> *w, const int *new_of_old) {
+  return guarded(w, [&] {
+    Atom *a = w->lmp.atom;
+    const int nl = a->nlocal, nt = nl + a->nghost;
+    std::vector<int> old_of_new(nl, -1);
+    for (int i = 0; i < nl; ++i) {
+      if (new_of_old[i] < 0 || new_of_old[i] >= nl || old_of_new[new_of_old[i]] != -1) throw std::runtime_error("permute: not a permutation");
+      old_of_new[new_of_old[i]] = i;
+    }
+    if (w->nmax_fix < nt + 1) {   // one scratch slot behind the ghosts
+      w->fix->grow_arrays(nt + 1);
+      w->nmax_fix = nt + 1;
+    }
+    a->nmax = std::max(a->nmax, nt + 1);
+    const int scratch = nt;
+    std::vector<char> done(nl, 0);
+    for (int j0 = 0; j0 < nl; ++j0) {
+      if (done[j0] || old_of_new[j0] == j0) continue;
+      w->fix->copy_arrays(j0, scratch, 0);
+      int j = j0;
+      for (;;) {
+        done[j] = 1;
+        const int src = old_of_new[j];
+        if (src == j0) { w->fix->copy_arrays(scratch, j, 0); break; }
+        w->fix->copy_arrays(src, j, 0);
+        j = src;
+      }
+    }
+    auto perm3 = [&](std::vector<double> &v) {
+      std::vector<double> t(v.begin(), v.begin() + 3 * (size_t)nl);
+      for (int i = 0; i < nl; ++i) for (int d = 0; d < 3; ++d) v[3 * (size_t)new_of_old[i] + d] = t[3 * (size_t)i + d];
+    };
+    perm3(w->xs); perm3(w->vs); perm3(w->fs);
+    auto perm1 = [&](auto &v) {
+      auto t = v;
+      for (int i = 0; i < nl; ++i) v[new_of_old[i]] = t[i];
+    };
+    perm1(w->type); perm1(w->mask); perm1(w->tag);
+    for (auto &o : w->lmp.comm->ghost_owner) o = new_of_old[o];
+    // neighbour list: row j of the new order is the old row of old_of_new[j], entries relabelled
+    std::vector<int> flat;
+    std::vector<int> num(nl);
+    flat.reserve(w->flat.size());
+    std::vector<size_t> start(nl);
+    for (int j = 0; j < nl; ++j) {
+      const int i = old_of_new[j];
+      start[j] = flat.size();
+      num[j] = w->numneigh[i];
+      for (int k = 0; k < w->numneigh[i]; ++k) {
+        const int e = w->firstneigh[i][k];
+        const int idx = e & NEIGHMASK, hi = e & ~NEIGHMASK;
+        flat.push_back(hi | (idx < nl ? new_of_old[idx] : idx));
+      }
+    }
+    w->flat.swap(flat);
+    w->numneigh = num;
+    for (int j = 0; j < nl; ++j) w->firstneigh[j] = w->flat.data() + start[j];
+    w->list.numneigh = w->numneigh.data();
+    w->list.firstneigh = w->firstneigh.data();
+    w->lmp.neighbor->ago = 0;
+    w->fix->init_list(0, &w->list);
+  });
+}
+
 }  // namespace shim_driver
 
 #define SHIM_DRIVER_DEFINE(P, FixT)                                                                            \
@@ -179,6 +251,9 @@ int world_set_xi(World<FixT> *w, const double *xi) {
   }                                                                                                            \
   int P##_set_neighbors(void *w, int nlocal, const long long *off, const int *flat) {                          \
     return shim_driver::world_set_neighbors(static_cast<P##_world *>(w), nlocal, off, flat);                   \
+  }                                                                                                            \
+  int P##_permute(void *w, const int *new_of_old) {                                                           \
+    return shim_driver::world_permute(static_cast<P##_world *>(w), new_of_old);                               \
   }                                                                                                            \
   int P##_set_xi(void *w, const double *xi) {                                                                  \
     return shim_driver::world_set_xi(static_cast<P##_world *>(w), xi);                                         \

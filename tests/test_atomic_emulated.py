@@ -125,3 +125,8 @@ def test_fuzz_atomic_configurations(seed, make_engine, kappa_tables, tmp_path):
             cases.trajectory_case(make_engine, kappa_tables, flags, loops, gf, n=n, steps=2, ntypes=2, beta=beta2, names=("Ni", "Co"))
         else:
             cases.trajectory_case(make_engine, kappa_tables, flags, loops, gf, n=n, steps=int(rng.integers(1, 4)))
+
+
+@pytest.mark.parametrize("comm", ["device", "lammps"])
+def test_emulated_fix_survives_atom_reordering(make_fix, comm):
+    cases.reordering_case(make_fix, comm)

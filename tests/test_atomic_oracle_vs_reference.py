@@ -95,3 +95,13 @@ def test_atomic_oracle_matches_committed_golden_vectors(name):
     for k in KEYS:
         got = np.array([r[k] for r in recs])
         assert np.array_equal(got, g["out_" + k]), k
+
+
+def test_reference_atomic_survives_atom_reordering(refa):
+    """the stand-in's re-ordering (LAMMPS' spatial sort: copy_arrays along the permutation's cycles) is transparent to
+    the reference fix, which carries E_a_i along (fix_eph_atomic.cpp:951-955) -- this pins the harness side of the
+    migration tests of the product (test_atomic_emulated.py, test_zx_gpu_atomic.py)"""
+    s = H.make_system(3)
+    xi = [np.random.default_rng(40 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
+    mk = lambda system: refa.atomic_fix_driver(system, H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2))
+    traj.assert_reordering_is_transparent(mk, s, xi, permute_after=2)

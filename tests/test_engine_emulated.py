@@ -153,6 +153,10 @@ def test_emulated_coloured_fix_golden_vectors():
     GC.test_fix_coloured_b200_matches_committed_golden_vectors()
 
 
+def test_emulated_coloured_fix_survives_atom_reordering(ni_trunc_beta):
+    GC.test_fix_coloured_b200_survives_atom_reordering(ni_trunc_beta)
+
+
 def test_emulated_fix_peratom_cadence():
     GZ.test_fix_b200_peratom_cadence()
 

@@ -322,3 +322,12 @@ def test_coloured_oracle_matches_committed_golden_vectors(ni_trunc_beta):
     recs = traj.run_oracle(fx, s, list(g["xi"]), [58.71])
     for k in ("f", "array", "T", "Ee", "Tmean", "w", "rho", "x", "v", "f_dis", "f_sto"):
         assert np.array_equal(np.array([r[k] for r in recs]), g["out_" + k]), k
+
+
+def test_reference_coloured_survives_atom_reordering(refc, ni_trunc_beta):
+    """the reference fork migrates f_sto_i / f_dis_i with the atoms (fix_eph_coloured_exp.cpp:793-825): the stand-in's
+    re-ordering is transparent to it, bit for bit"""
+    s = H.make_system(3)
+    xi = [np.random.default_rng(60 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
+    args = H.fix_args(7, ni_trunc_beta, ["Ni"], model="5e-4", grid=(2, 2, 2), style="eph/coloured/exp")
+    traj.assert_reordering_is_transparent(lambda system: refc.coloured_fix_driver(system, args), s, xi, permute_after=2)

@@ -62,3 +62,7 @@ def test_atomic_engine_builtin_gaussian_stream(make_engine, kappa_tables):
 def test_atomic_engine_properties_at_scale(make_engine, kappa_tables):
     """108 000 atoms (no oracle run needed): momentum, ledger = work, diffusion conserves, ghosts equal owners"""
     cases.properties_case(make_engine, kappa_tables, 30)
+
+
+def test_fix_atomic_b200_survives_atom_reordering():
+    cases.reordering_case(lambda s, args: A.fix_driver(s, args))

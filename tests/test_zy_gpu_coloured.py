@@ -90,3 +90,12 @@ def test_fix_coloured_b200_matches_committed_golden_vectors():
     for k in ("Ee", "Tmean"):
         got = np.array([r[k] for r in recs])
         assert np.all(np.abs(got - g["out_" + k]) <= TOL * np.abs(g["out_" + k])), k
+
+
+def test_fix_coloured_b200_survives_atom_reordering(ni_trunc_beta):
+    """LAMMPS re-orders the local atoms (spatial sort): the filter state migrates through copy_arrays and is registered
+    again on the device, the trajectory continues unchanged"""
+    s = H.make_system(3)
+    xi = [np.random.default_rng(60 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
+    args = H.fix_args(7, ni_trunc_beta, ["Ni"], model="5e-4", grid=(2, 2, 2), style="eph/coloured/exp/b200", extra=["rng", "mars"])
+    traj.assert_reordering_is_transparent(lambda system: host.FixDriver(system, args), s, xi, permute_after=2, tol=TOL)

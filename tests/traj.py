@@ -205,3 +205,67 @@ def run_atomic_engine(eng, system, xis, mass, dt, groupbit=1, noint=False, ftm2v
                         w=eng.probe(1), f_eph=eng.probe(3), f_rng=eng.probe(4), rho_a=eng.probe(5), E=eng.probe(6)[:nl],
                         dE=eng.probe(7), T=eng.probe(8), xi=eng.probe(2)))
     return out
+
+
+# ---------------------------------------------------------------------------
+# atom re-ordering (LAMMPS' spatial sort): a fix must carry its per-atom state along through copy_arrays
+# ---------------------------------------------------------------------------
+def run_with_reordering(make_driver, system, xi_by_tag, permute_after=None, seed=5):
+    """Runs len(xi_by_tag) Verlet steps of a fix living in the LAMMPS stand-in; after `permute_after` steps the local
+    atoms are re-ordered at random (FixDriver.permute).  xi_by_tag[k]: Gaussians of step k+1 per atom TAG [natoms][3]
+    (or None).  Returns per-step records with the per-atom quantities sorted by tag, so that runs with and without the
+    re-ordering can be compared directly."""
+    drv = make_driver(system)
+    nl = system["nlocal"]
+    tags = np.asarray(system["tag"][:nl]).copy()
+    owner = np.asarray(system["ghost_owner"]).copy()
+    x0 = np.asarray(system["x"])
+    shift = x0[nl:] - x0[owner]
+    out = []
+    for k, xi_tag in enumerate(xi_by_tag):
+        if permute_after is not None and k == permute_after:
+            perm = np.random.default_rng(seed).permutation(nl).astype(np.int32)   # atom i moves to perm[i]
+            drv.permute(perm)
+            new_tags = np.empty_like(tags)
+            new_tags[perm] = tags
+            tags = new_tags
+            owner = perm[owner]
+        drv.set_step(k + 1)
+        x, v, f = drv.xvf()
+        f[:] = 0.0
+        drv.update(f=f)
+        drv.initial_integrate()
+        x, v, f = drv.xvf()
+        x[nl:] = x[owner] + shift
+        v[nl:] = v[owner]
+        drv.update(x=x, v=v)
+        if xi_tag is not None:
+            drv.set_xi(np.ascontiguousarray(xi_tag[tags - 1]))
+        drv.post_force()
+        drv.final_integrate()
+        x, v, f = drv.xvf()
+        v[nl:] = v[owner]
+        drv.update(v=v)
+        drv.end_of_step()
+        x, v, f = drv.xvf()
+        order = np.argsort(tags)
+        out.append(dict(x=x[:nl][order].copy(), v=v[:nl][order].copy(), f=f[:nl][order].copy(), array=drv.array()[order].copy(),
+                        Ee=drv.compute_vector(0), T=drv.compute_vector(1)))
+    return out
+
+
+def assert_reordering_is_transparent(make_driver, system, xi_by_tag, permute_after, tol=0.0):
+    """the trajectory with a re-ordering after `permute_after` steps equals the one without (tol 0: bit for bit)"""
+    from eph_b200 import harness as H
+    a = run_with_reordering(make_driver, system, xi_by_tag, None)
+    b = run_with_reordering(make_driver, system, xi_by_tag, permute_after)
+    for step, (ra, rb) in enumerate(zip(a, b), start=1):
+        for key in ("x", "v", "f", "array"):
+            if tol == 0.0:
+                assert np.array_equal(ra[key], rb[key]), (step, key)
+            else:
+                assert H.error_metrics(rb[key], ra[key]) < tol, (step, key)
+        for key in ("Ee", "T"):
+            assert abs(ra[key] - rb[key]) <= max(tol, 1e-14) * abs(ra[key]), (step, key)
+    # the state really mattered: without it the later steps would differ from a fresh start
+    assert not np.array_equal(a[-1]["array"], a[0]["array"])

@@ -194,6 +194,13 @@ class FixDriver:
         a = [None if t is None else np.ascontiguousarray(t, dtype=np.float64) for t in (x, v, f)]
         self._ck(self._fn("update_xvf")(C.c_void_p(self.w), *[None if t is None else C.c_void_p(t.ctypes.data) for t in a]))
 
+    def permute(self, new_of_old):
+        """re-order the local atoms like LAMMPS' spatial sort does (atom i moves to new_of_old[i]); the fix is told through
+        copy_arrays, the harness' arrays, ghost owners and neighbour list are relabelled"""
+        p = np.ascontiguousarray(new_of_old, dtype=np.int32)
+        assert len(p) == self.nlocal
+        self._ck(self._fn("permute")(C.c_void_p(self.w), C.c_void_p(p.ctypes.data)))
+
     def set_xi(self, xi):
         xi = np.ascontiguousarray(xi, dtype=np.float64)
         self._ck(self._fn("set_xi")(C.c_void_p(self.w), C.c_void_p(xi.ctypes.data)))
