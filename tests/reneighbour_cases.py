@@ -1,0 +1,49 @@
+"""Re-neighbouring with a changing number of ghosts (what LAMMPS does every few steps: ghosts and list rebuilt from the
+current positions, atoms wrapped back into the box, per-atom arrays grown), product fix against the compiled reference
+fix, both inside the LAMMPS stand-in.  Shared by the host-build tests and their `-m gpu` twins."""
+import os
+
+import numpy as np
+import pytest
+
+from eph_b200 import harness as H
+from eph_b200 import host
+
+import traj
+from conftest import GOLDEN
+
+SCHEDULE = {2: 6.0, 4: 7.5, 5: 6.5}    # ghost shell / list cut-off before these steps: fewer, more, fewer ghosts
+BETA = os.path.join(GOLDEN, "Ni_trunc.beta")
+KAPPA = os.path.join(GOLDEN, "synth1.kappa")
+TOL = 1e-10
+
+
+def fix_case(style, extra):
+    """style "eph" or "eph/coloured/exp": FixEPHB200 continues exactly like the reference (grid, filter state, energies)"""
+    from oracle import reference as R
+    if not (R.available() and R.coloured_available()):
+        pytest.skip("compiled reference not present")
+    s = H.make_system(3, skin=2.0)
+    xis = [np.random.default_rng(80 + k).normal(size=(s["nlocal"], 3)) for k in range(6)]
+    ref_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2), style=style, **extra)
+    our_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2), style=style + "/b200", extra=["rng", "mars"], **extra)
+    mk_ref = (lambda sy: R.coloured_fix_driver(sy, ref_args)) if "coloured" in style else (lambda sy: R.fix_driver(sy, ref_args))
+    a = traj.run_with_reneighbouring(mk_ref, s, xis, SCHEDULE)
+    b = traj.run_with_reneighbouring(lambda sy: host.FixDriver(sy, our_args), s, xis, SCHEDULE)
+    assert len({r["nghost"] for r in a}) >= 3
+    traj.assert_same_trajectory(a, b, TOL)
+
+
+def atomic_case(make_fix, comm):
+    """the per-atom energies stay with their atoms: FixEPHAtomicB200 continues like the reference fix"""
+    from oracle import reference as R
+    if not R.atomic_available():
+        pytest.skip("compiled reference not present")
+    s = H.make_system(3, skin=2.0)
+    xis = [np.random.default_rng(90 + k).normal(size=(s["nlocal"], 3)) for k in range(6)]
+    ref_args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2)
+    our_args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2, style="eph/atomic/b200") + ["rng", "mars", "comm", comm]
+    a = traj.run_with_reneighbouring(lambda sy: R.atomic_fix_driver(sy, ref_args), s, xis, SCHEDULE)
+    b = traj.run_with_reneighbouring(lambda sy: make_fix(sy, our_args), s, xis, SCHEDULE)
+    assert len({r["nghost"] for r in a}) >= 3
+    traj.assert_same_trajectory(a, b, TOL)

@@ -130,3 +130,9 @@ def test_fuzz_atomic_configurations(seed, make_engine, kappa_tables, tmp_path):
 @pytest.mark.parametrize("comm", ["device", "lammps"])
 def test_emulated_fix_survives_atom_reordering(make_fix, comm):
     cases.reordering_case(make_fix, comm)
+
+
+@pytest.mark.parametrize("comm", ["device", "lammps"])
+def test_emulated_fix_through_reneighbouring_matches_reference(make_fix, comm):
+    import reneighbour_cases
+    reneighbour_cases.atomic_case(make_fix, comm)

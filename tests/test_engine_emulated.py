@@ -252,3 +252,10 @@ def test_simt_stand_in_selftest():
     sums = {mode: subprocess.run([exe, "race"], capture_output=True, text=True, timeout=120,
                                  env=dict(os.environ, SIMT_ORDER=mode)).stdout for mode in ("forward", "reverse")}
     assert "race checksum" in sums["forward"] and sums["forward"] != sums["reverse"], sums
+
+
+# ---- re-neighbouring with a changing ghost count, product against the compiled reference, both in the stand-in ----
+@pytest.mark.parametrize("style,extra", [("eph", {}), ("eph/coloured/exp", dict(model="5e-4"))])
+def test_emulated_fix_through_reneighbouring_matches_reference(style, extra):
+    import reneighbour_cases
+    reneighbour_cases.fix_case(style, extra)

@@ -66,3 +66,9 @@ def test_atomic_engine_properties_at_scale(make_engine, kappa_tables):
 
 def test_fix_atomic_b200_survives_atom_reordering():
     cases.reordering_case(lambda s, args: A.fix_driver(s, args))
+
+
+@pytest.mark.parametrize("comm", ["device", "lammps"])
+def test_fix_atomic_b200_through_reneighbouring_matches_reference(comm):
+    import reneighbour_cases
+    reneighbour_cases.atomic_case(lambda s, args: A.fix_driver(s, args), comm)

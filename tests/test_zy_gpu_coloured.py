@@ -99,3 +99,11 @@ def test_fix_coloured_b200_survives_atom_reordering(ni_trunc_beta):
     xi = [np.random.default_rng(60 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
     args = H.fix_args(7, ni_trunc_beta, ["Ni"], model="5e-4", grid=(2, 2, 2), style="eph/coloured/exp/b200", extra=["rng", "mars"])
     traj.assert_reordering_is_transparent(lambda system: host.FixDriver(system, args), s, xi, permute_after=2, tol=TOL)
+
+
+@pytest.mark.parametrize("style,extra", [("eph", {}), ("eph/coloured/exp", dict(model="5e-4"))])
+def test_fix_b200_through_reneighbouring_matches_reference(style, extra):
+    """ghosts and list rebuilt from the current positions with a changing ghost count: FixEPHB200 (plain and coloured)
+    continues exactly like the compiled reference fix"""
+    import reneighbour_cases
+    reneighbour_cases.fix_case(style, extra)

@@ -269,3 +269,75 @@ def assert_reordering_is_transparent(make_driver, system, xi_by_tag, permute_aft
             assert abs(ra[key] - rb[key]) <= max(tol, 1e-14) * abs(ra[key]), (step, key)
     # the state really mattered: without it the later steps would differ from a fresh start
     assert not np.array_equal(a[-1]["array"], a[0]["array"])
+
+
+# ---------------------------------------------------------------------------
+# re-neighbouring with a changing number of ghosts (what LAMMPS does every few steps)
+# ---------------------------------------------------------------------------
+def reneighbour(drv, system, shell):
+    """Rebuilds ghosts and the full list from the CURRENT positions of the local atoms with a ghost shell / list cut-off
+    of `shell`, and hands them to the fix in the stand-in the way LAMMPS does after re-neighbouring (the number of ghosts
+    changes, per-atom arrays may have to grow).  Returns the new system dict."""
+    from eph_b200 import harness as H
+    nl = system["nlocal"]
+    x, v, f = drv.xvf()
+    L = np.asarray(system["box"], dtype=np.float64)
+    x[:nl] = np.mod(x[:nl], L)          # atoms that left the box are wrapped back first (Domain::remap)
+    x[:nl][x[:nl] >= L] = 0.0
+    xg, owner = H.ghosts(np.ascontiguousarray(x[:nl]), L, np.zeros(3), L.copy(), shell)
+    owner = owner.astype(np.int32)
+    s = dict(system)
+    s["x"] = np.ascontiguousarray(np.concatenate([x[:nl], xg]))
+    s["v"] = np.ascontiguousarray(np.concatenate([v[:nl], v[:nl][owner]]))
+    s["f"] = np.ascontiguousarray(np.concatenate([f[:nl], np.zeros((len(xg), 3))]))
+    for k in ("type", "mask", "tag"):
+        loc = np.asarray(system[k][:nl])
+        s[k] = np.ascontiguousarray(np.concatenate([loc, loc[owner]]))
+    s["ghost_owner"], s["nghost"] = owner, len(xg)
+    s["offsets"], s["neigh"] = H.neighbor_list(s["x"], nl, shell)
+    drv.nghost = s["nghost"]
+    drv._set_atoms(s)
+    drv.set_neighbors(s["offsets"], s["neigh"])
+    return s
+
+
+def run_with_reneighbouring(make_driver, system, xis, schedule):
+    """schedule: {step index: ghost shell} -- before that step the ghosts and the list are rebuilt with that shell"""
+    drv = make_driver(system)
+    s = system
+    out = []
+    for k, xi in enumerate(xis):
+        if k in schedule:
+            s = reneighbour(drv, s, schedule[k])
+        nl = s["nlocal"]
+        sync = GhostSync(s)
+        drv.set_step(k + 1)
+        x, v, f = drv.xvf()
+        f[:] = 0.0
+        drv.update(f=f)
+        drv.initial_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(x=x, v=v)
+        if xi is not None:
+            drv.set_xi(xi)
+        drv.post_force()
+        drv.final_integrate()
+        x, v, f = drv.xvf()
+        sync(x, v)
+        drv.update(v=v)
+        drv.end_of_step()
+        x, v, f = drv.xvf()
+        out.append(dict(x=x[:nl].copy(), v=v[:nl].copy(), f=f[:nl].copy(), array=drv.array().copy(), Ee=drv.compute_vector(0),
+                        T=drv.compute_vector(1), nghost=s["nghost"]))
+    return out
+
+
+def assert_same_trajectory(a, b, tol):
+    from eph_b200 import harness as H
+    for step, (ra, rb) in enumerate(zip(a, b), start=1):
+        assert ra["nghost"] == rb["nghost"]
+        for key in ("x", "v", "f", "array"):
+            assert H.error_metrics(rb[key], ra[key]) < tol, (step, key)
+        for key in ("Ee", "T"):
+            assert abs(ra[key] - rb[key]) <= tol * max(abs(ra[key]), 1e-300), (step, key)
