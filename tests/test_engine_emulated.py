@@ -259,3 +259,44 @@ def test_simt_stand_in_selftest():
 def test_emulated_fix_through_reneighbouring_matches_reference(style, extra):
     import reneighbour_cases
     reneighbour_cases.fix_case(style, extra)
+
+
+def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
+    """200 velocity-Verlet steps of hot atoms under the fix's own forces, LAMMPS' list never rebuilt: the inner list is
+    rebuilt several times as the atoms drift, then (once 2 D + inner skin > skin) the engine stays on LAMMPS' list --
+    and the forces, positions and grid follow the oracle to 1e-10 all the way"""
+    s = H.make_system(4, T=6000.0)
+    dt, nl = 1.5e-4, s["nlocal"]
+    rng = np.random.default_rng(3)
+    fx = O.Fix(s, O.Beta(path=ni_trunc_beta), O.FDM(2, 2, 2, G.box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=dt)
+    eng = G.make_engine(ni_trunc_beta, 7, (2, 2, 2), G.box6(s), dt=dt)
+    eng.set_skin(2.0, 0.4)
+    G.attach(eng, s)
+    sync = traj.GhostSync(s)
+    x, v = s["x"].copy(), s["v"].copy()
+    f = np.zeros((nl, 3))
+    m, dtf = np.array([0.0, 58.71]), 0.5 * dt * H.FTM2V
+    fx.f[:] = 0.0
+    worst = 0.0
+    for step in range(1, 201):
+        xi = rng.normal(size=(nl, 3))
+        eng.initial_integrate(x, v, f, m, dt, dtf)
+        sync(x, v)
+        f = np.zeros((nl, 3))
+        eng.post_force(x, v, f, xi, step)
+        eng.final_integrate(v, f, m, dtf)
+        sync(x, v)
+        eng.end_of_step(x, v)
+        fx.initial_integrate([58.71])
+        sync(fx.x, fx.v)
+        fx.f[:] = 0.0
+        fx.post_force(xi)
+        fx.final_integrate([58.71])
+        sync(fx.x, fx.v)
+        fx.end_of_step()
+        worst = max(worst, H.error_metrics(f, fx.f[:nl]), H.error_metrics(x[:nl], fx.x[:nl]),
+                    H.error_metrics(eng.get_grid(0), fx.fdm.field(0)))
+    st = eng.list_stats()
+    assert worst < G.TOL, worst
+    assert st["inner_builds"] >= 4 and st["fallback_steps"] >= 10, st
+    assert 0.8 < np.abs(x[:nl] - s["x"][:nl]).max() < 1.2
