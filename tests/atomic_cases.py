@@ -47,13 +47,14 @@ def compare(recs, refs, in_group=None):
 
 
 def trajectory_case(make_engine, kappa_tables, flags, loops, group_fraction=None, n=3, steps=3, ntypes=1, beta=BETA,
-                    names=("Ni",)):
+                    names=("Ni",), kappa=KAPPA, tk=None):
     s = H.make_system(n, group_fraction=group_fraction, ntypes=ntypes)
     gb = 2 if group_fraction else 1
     tm = list(range(ntypes)) if len(names) > 1 else [0] * ntypes
-    eng = setup_engine(make_engine(tm, [0] * ntypes, flags, groupbit=gb, inner_loops=loops), s, beta, kappa_tables)
-    fx = O.AtomicFix(s, O.Beta(path=beta), O.Kappa(KAPPA), flags, groupbit=gb, inner_loops=loops, type_map_beta=tm,
-                     type_map_kappa=[0] * ntypes)
+    tk = list(tk) if tk is not None else [0] * ntypes    # element of the .kappa file per atom type
+    eng = setup_engine(make_engine(tm, tk, flags, groupbit=gb, inner_loops=loops), s, beta, kappa_tables)
+    fx = O.AtomicFix(s, O.Beta(path=beta), O.Kappa(kappa), flags, groupbit=gb, inner_loops=loops, type_map_beta=tm,
+                     type_map_kappa=tk)
     # the constructor's sums (fix_eph_atomic.cpp:223-253)
     Ee0, Te0 = eng.summary()
     assert abs(Ee0 - fx.Ee()) <= TOL * abs(fx.Ee()) and abs(Te0 - fx.Te()) <= TOL * abs(fx.Te())

@@ -136,3 +136,25 @@ def test_emulated_fix_survives_atom_reordering(make_fix, comm):
 def test_emulated_fix_through_reneighbouring_matches_reference(make_fix, comm):
     import reneighbour_cases
     reneighbour_cases.atomic_case(make_fix, comm)
+
+
+def test_emulated_three_elements_in_both_files(make_engine, tmp_path):
+    """three atom types on three elements of the .beta AND of the .kappa file: per-element locality densities, E(T) and
+    K(T) tables (three elements give n_pairs = 4 >= 3, the smallest multi-element file the reference indexes in bounds,
+    eph_kappa.h:69); a two-element .kappa file (n_pairs = 1) is refused"""
+    from eph_b200 import harness as H
+    from eph_b200 import lib
+    beta3 = str(H.write_beta_file(tmp_path / "synth3.beta", H.synthetic_knots(3, n_beta=5001, drho=0.01)))
+    kappa3 = str(H.write_kappa_file(tmp_path / "synth3.kappa", H.synthetic_kappa(3, n_r=501, n_T=401, dT=2.5)))
+    kt = A.KappaTables(kappa3)
+    assert (kt.n_elements, kt.n_pairs) == (3, 4)
+    cases.trajectory_case(make_engine, kt, 7, 2, 0.8, ntypes=3, beta=beta3, names=("Ni", "Co", "Cr"), kappa=kappa3, tk=[2, 0, 1])
+    kappa2 = str(H.write_kappa_file(tmp_path / "synth2.kappa", H.synthetic_kappa(2, n_r=501, n_T=401, dT=2.5)))
+    eng = make_engine([0, 1], [0, 1], 7)
+    with pytest.raises(lib.EphError, match="indexed by element"):
+        eng.set_tables_from(host_beta(beta3), A.KappaTables(kappa2))
+
+
+def host_beta(path):
+    from eph_b200 import host
+    return host.BetaTables(path=path)

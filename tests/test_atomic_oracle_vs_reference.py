@@ -105,3 +105,31 @@ def test_reference_atomic_survives_atom_reordering(refa):
     xi = [np.random.default_rng(40 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
     mk = lambda system: refa.atomic_fix_driver(system, H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2))
     traj.assert_reordering_is_transparent(mk, s, xi, permute_after=2)
+
+
+def test_atomic_three_elements_bit_exact(refa, tmp_path):
+    """three atom types on three elements of both files (the smallest multi-element .kappa file the reference indexes in
+    bounds: n_pairs = 4 >= 3, eph_kappa.h:69), element names given out of file order"""
+    beta3 = str(H.write_beta_file(tmp_path / "synth3.beta", H.synthetic_knots(3, n_beta=5001, drho=0.01)))
+    kappa3 = str(H.write_kappa_file(tmp_path / "synth3.kappa", H.synthetic_kappa(3, n_r=501, n_T=401, dT=2.5)))
+    kr, ko = refa.Kappa(kappa3), O.Kappa(kappa3)
+    assert (kr.n_elements, kr.n_pairs) == (3, 4) == (ko.n_elements, ko.n_pairs)
+    for e in range(3):
+        for kind in (0, 1, 2):
+            assert np.array_equal(kr.table(kind, e), ko.table(kind, e)), (kind, e)
+    for p in range(4):
+        assert np.array_equal(kr.table(3, p), ko.table(3, p)), p
+    s = H.make_system(3, ntypes=3, group_fraction=0.8)
+    mass = [58.71, 58.93, 52.0]
+    drv = refa.atomic_fix_driver(s, H.atomic_fix_args(7, beta3, kappa3, ["Cr", "Ni", "Co"], inner_loops=2, group="bit1"), mass=mass)
+    fx = O.AtomicFix(s, O.Beta(path=beta3), ko, 7, groupbit=2, inner_loops=2, type_map_beta=[2, 0, 1], type_map_kappa=[2, 0, 1])
+    xis = [np.random.default_rng(i).normal(size=(s["nlocal"], 3)) for i in range(3)]
+    a = traj.run_atomic_fix_driver(drv, s, xis)
+    b = traj.run_atomic_oracle(fx, s, xis, mass)
+    in_group = (s["mask"][: s["nlocal"]] & 2) != 0
+    for step, (ra, rb) in enumerate(zip(a, b)):
+        for k in ra:
+            if k == "T":
+                assert np.array_equal(ra[k][in_group], rb[k][in_group]), (step, k)
+            else:
+                assert np.array_equal(np.asarray(ra[k]), np.asarray(rb[k])), (step, k)

@@ -72,3 +72,11 @@ def test_fix_atomic_b200_survives_atom_reordering():
 def test_fix_atomic_b200_through_reneighbouring_matches_reference(comm):
     import reneighbour_cases
     reneighbour_cases.atomic_case(lambda s, args: A.fix_driver(s, args), comm)
+
+
+def test_atomic_engine_three_elements_in_both_files(make_engine, tmp_path):
+    """three atom types on three elements of the .beta and of the .kappa file (n_pairs = 4 >= 3, eph_kappa.h:69)"""
+    beta3 = str(H.write_beta_file(tmp_path / "synth3.beta", H.synthetic_knots(3, n_beta=5001, drho=0.01)))
+    kappa3 = str(H.write_kappa_file(tmp_path / "synth3.kappa", H.synthetic_kappa(3, n_r=501, n_T=401, dT=2.5)))
+    cases.trajectory_case(make_engine, A.KappaTables(kappa3), 7, 2, 0.8, ntypes=3, beta=beta3, names=("Ni", "Co", "Cr"),
+                          kappa=kappa3, tk=[2, 0, 1])
