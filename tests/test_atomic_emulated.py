@@ -158,3 +158,51 @@ def test_emulated_three_elements_in_both_files(make_engine, tmp_path):
 def host_beta(path):
     from eph_b200 import host
     return host.BetaTables(path=path)
+
+
+def test_emulated_call_order_errors_are_reported(make_engine, kappa_tables):
+    """misuse of the C ABI comes back as an error code with a message, never as a crash or a silent no-op"""
+    import numpy as np
+    from eph_b200 import harness as H
+    from eph_b200 import host, lib
+    s = H.make_system(2)
+    nl = s["nlocal"]
+    x, v, f = s["x"], s["v"], np.zeros((nl, 3))
+    eng = make_engine([0], [0], 7, inner_loops=1)
+    with pytest.raises(lib.EphError, match="tables not set"):
+        eng.post_force(x, v, f, None, 1)
+    eng.set_tables_from(host.BetaTables(path=cases.BETA), kappa_tables)
+    with pytest.raises(lib.EphError, match="set_dt"):
+        eng.post_force(x, v, f, None, 1)
+    eng.set_dt(1e-4)
+    with pytest.raises(lib.EphError, match="set_atoms"):
+        eng.post_force(x, v, f, None, 1)
+    ints = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    with pytest.raises(lib.EphError, match="type"):
+        eng.set_atoms(nl, s["nghost"], ints(s["type"]) + 5, ints(s["mask"]), np.ascontiguousarray(s["tag"], dtype=np.int64), ints(s["ghost_owner"]))
+    with pytest.raises(lib.EphError, match="owner"):
+        eng.set_atoms(nl, s["nghost"], ints(s["type"]), ints(s["mask"]), np.ascontiguousarray(s["tag"], dtype=np.int64), ints(s["ghost_owner"]) + nl)
+    eng.set_atoms(nl, s["nghost"], ints(s["type"]), ints(s["mask"]), np.ascontiguousarray(s["tag"], dtype=np.int64), ints(s["ghost_owner"]))
+    with pytest.raises(lib.EphError, match="set_neighbors"):
+        eng.post_force(x, v, f, None, 1)
+    bad = ints(s["neigh"]).copy()
+    bad[3] = nl + s["nghost"] + 7
+    with pytest.raises(lib.EphError, match="out of range"):
+        eng.set_neighbors(np.ascontiguousarray(s["offsets"], dtype=np.int64), bad)
+    eng.set_neighbors(np.ascontiguousarray(s["offsets"], dtype=np.int64), ints(s["neigh"]))
+    eng.init_energy(300.0)
+    with pytest.raises(lib.EphError, match="no post_force"):
+        eng.end_of_step()                       # heat diffusion needs the positions of a post_force
+    with pytest.raises(lib.EphError, match="without post_force_begin"):
+        eng._check(eng.lib.eph_b200_atomic_post_force_mid(eng.h))
+    eng.post_force(x, v, f, None, 1)
+    Ee, Te = eng.end_of_step()
+    assert Ee > 0 and 250 < Te < 350
+    # the phase-split calls belong to the external-transport mode, the one-call ones to the internal one
+    eng._check(eng.lib.eph_b200_atomic_set_comm_mode(eng.h, 1))
+    with pytest.raises(lib.EphError, match="external comm mode"):
+        eng.post_force(x, v, f, None, 2)
+    with pytest.raises(lib.EphError, match="external comm mode"):
+        eng.end_of_step()
+    with pytest.raises(lib.EphError, match="unknown probe"):
+        eng.probe(42)
