@@ -29,7 +29,7 @@ struct World {
   std::vector<double> xs, vs, fs, mass;
   std::vector<double *> xr, vr, fr;
   std::vector<int> type, mask;
-  std::vector<long long> tag;
+  std::vector<tagint> tag;
   std::vector<int> numneigh, flat;
   std::vector<int *> firstneigh;
   std::vector<double> xi;
@@ -79,7 +79,7 @@ int world_set_atoms(World<FixT> *w, int nlocal, int nghost, const double *x, con
     w->type.assign(type, type + n);
     w->mask.assign(mask, mask + n);
     w->tag.resize(n);
-    for (size_t i = 0; i < n; ++i) w->tag[i] = tag ? tag[i] : static_cast<long long>(i + 1);
+    for (size_t i = 0; i < n; ++i) w->tag[i] = static_cast<tagint>(tag ? tag[i] : static_cast<long long>(i + 1));
     w->xr.resize(n); w->vr.resize(n); w->fr.resize(n);
     for (size_t i = 0; i < n; ++i) {
       w->xr[i] = &w->xs[3 * i]; w->vr[i] = &w->vs[3 * i]; w->fr[i] = &w->fs[3 * i];

@@ -25,6 +25,15 @@
 
 namespace LAMMPS_NS {
 
+// LAMMPS' integer widths depend on the build: -DLAMMPS_SMALLBIG (the default) has 32-bit atom tags and 64-bit atom counts
+// and time steps, -DLAMMPS_BIGBIG 64-bit tags.  The stand-in follows BIGBIG unless built with -DSHIM_TAGINT32.
+#ifdef SHIM_TAGINT32
+typedef int tagint;
+#else
+typedef long long tagint;
+#endif
+typedef long long bigint;
+
 class Fix;
 class LAMMPS;
 
@@ -52,7 +61,7 @@ class Atom {
   double *mass = nullptr;   // indexed by type, 1-based
   int *type = nullptr;
   int *mask = nullptr;
-  long long *tag = nullptr;
+  tagint *tag = nullptr;
   int ncallbacks = 0;
   void add_callback(int) { ++ncallbacks; }
   void delete_callback(const char *, int) { --ncallbacks; }

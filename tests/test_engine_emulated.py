@@ -300,3 +300,32 @@ def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
     assert worst < G.TOL, worst
     assert st["inner_builds"] >= 4 and st["fallback_steps"] >= 10, st
     assert 0.8 < np.abs(x[:nl] - s["x"][:nl]).max() < 1.2
+
+
+def test_emulated_fixes_with_32_bit_atom_tags(ni_trunc_beta, emulated_engine):
+    """LAMMPS' default build (-DLAMMPS_SMALLBIG) has 32-bit atom tags: the host classes, compiled against a stand-in with
+    `typedef int tagint`, widen the tags for the C ABI and give the same forces -- with the built-in Gaussian stream too,
+    which is keyed on the tags"""
+    from conftest import GOLDEN
+    from eph_b200 import atomic as A
+    subprocess.check_call(["make", "-C", EMUL, "TAG32=1", "SUFFIX=_tag32", "libeph_b200_emul_tag32.so", "libeph_atomic_emul_tag32.so"],
+                          stdout=subprocess.DEVNULL)
+    L32 = C.CDLL(os.path.join(EMUL, "libeph_b200_emul_tag32.so"))
+    g = np.load(os.path.join(GOLDEN, "caseA_example1.npz"))
+    s = traj.system_from_golden(g)
+    s["natoms"] = s["nlocal"]
+    s["tag"] = np.ascontiguousarray(np.random.default_rng(7).permutation(s["nlocal"])[np.r_[np.arange(s["nlocal"]), s["ghost_owner"]]] + 1)
+    args = H.fix_args(3, ni_trunc_beta, ["Ni"], grid=(1, 1, 1), style="eph/b200")     # rng philox: xi from (seed, tag, step)
+    xis = [None] * 3
+    a = traj.run_fix_driver(host.FixDriver(s, args, lib=L32), s, xis)
+    b = traj.run_fix_driver(host.FixDriver(s, args), s, xis)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra["f"], rb["f"]) and np.abs(ra["f"]).max() > 0
+    import atomic_cases as cases
+    La32 = C.CDLL(os.path.join(EMUL, "libeph_atomic_emul_tag32.so"))
+    La = C.CDLL(os.path.join(EMUL, "libeph_atomic_emul.so"))
+    aargs = H.atomic_fix_args(7, cases.BETA, cases.KAPPA, ["Ni"], inner_loops=1, style="eph/atomic/b200")
+    a = traj.run_atomic_fix_driver(A.fix_driver(s, aargs, lib=La32), s, xis)
+    b = traj.run_atomic_fix_driver(A.fix_driver(s, aargs, lib=La), s, xis)
+    for ra, rb in zip(a, b):
+        assert np.array_equal(ra["f"], rb["f"]) and np.array_equal(ra["E"], rb["E"]) and np.abs(ra["f_rng"]).max() > 0

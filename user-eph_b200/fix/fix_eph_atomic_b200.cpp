@@ -255,7 +255,10 @@ void FixEPHAtomicB200::upload_topology() {
     for (int g = 0; g < nghost; ++g)
       if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/atomic/b200: ghost atom without a local owner");
   }
-  check(eph_b200_atomic_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, reinterpret_cast<const int64_t *>(atom->tag),
+  // LAMMPS' tagint is 32 or 64 bits wide depending on the build (-DLAMMPS_SMALLBIG, the default, has 32): widen here
+  tag64.resize((size_t)nlocal + nghost);
+  for (size_t i = 0; i < tag64.size(); ++i) tag64[i] = static_cast<int64_t>(atom->tag[i]);
+  check(eph_b200_atomic_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, tag64.data(),
                                   comm_lammps ? nullptr : ghost_owner.data(), EPH_B200_HOST),
         "set_atoms");
   if (!list) error->all(FLERR, "fix eph/atomic/b200: no neighbour list");

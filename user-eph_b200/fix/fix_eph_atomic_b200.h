@@ -95,6 +95,7 @@ class FixEPHAtomicB200 : public Fix {
   double *E_a_i;    // [nmax] per-atom electronic energy, migrates with the atoms; the device copy is refreshed from it
                     // whenever LAMMPS may have re-ordered the atoms (re-neighbouring) and written back every step
   std::vector<double> xi_host;
+  std::vector<int64_t> tag64;   // atom->tag widened to 64 bits for the C ABI (tagint may be 32 bits wide)
   std::vector<int> ghost_owner;
   std::vector<int64_t> csr_offsets;
   std::vector<int> csr_neigh;

@@ -33,6 +33,7 @@ FixStyle(eph/coloured/exp/b200,FixEPHB200)
 #ifndef LMP_FIX_EPH_B200_H
 #define LMP_FIX_EPH_B200_H
 
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -111,6 +112,7 @@ class FixEPHB200 : public Fix {
   double **f_sto_i, **f_dis_i;  // coloured: filtered random / friction force of the last step, [nmax][3], migrate with the atoms
   double **array;               // [nmax][8] per-atom output (array_atom)
   std::vector<double> xi_host;  // rng mars: Gaussians of this step
+  std::vector<int64_t> tag64;   // atom->tag widened to 64 bits for the C ABI (tagint may be 32 bits wide)
   std::vector<int> ghost_owner; // local owner of each ghost (single rank)
   std::vector<double> owner_buf;
   long long atoms_epoch;        // (nlocal,nghost) signature of the last upload
