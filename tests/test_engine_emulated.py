@@ -261,6 +261,14 @@ def test_emulated_fix_through_reneighbouring_matches_reference(style, extra):
     reneighbour_cases.fix_case(style, extra)
 
 
+@pytest.mark.parametrize("keywords", [("neigh", "device"), ("comm", "lammps"), ("neigh", "device", "comm", "lammps")])
+def test_emulated_fix_keywords_through_reneighbouring(keywords):
+    """the list built on the device from the positions and / or the ghost values through LAMMPS' forward comm, across
+    re-neighbourings"""
+    import reneighbour_cases
+    reneighbour_cases.fix_case("eph", {}, keywords, schedule={2: 7.0, 4: 7.0})
+
+
 def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
     """200 velocity-Verlet steps of hot atoms under the fix's own forces, LAMMPS' list never rebuilt: the inner list is
     rebuilt several times as the atoms drift, then (once 2 D + inner skin > skin) the engine stays on LAMMPS' list --
