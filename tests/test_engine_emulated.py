@@ -337,3 +337,57 @@ def test_emulated_fixes_with_32_bit_atom_tags(ni_trunc_beta, emulated_engine):
     b = traj.run_atomic_fix_driver(A.fix_driver(s, aargs, lib=La), s, xis)
     for ra, rb in zip(a, b):
         assert np.array_equal(ra["f"], rb["f"]) and np.array_equal(ra["E"], rb["E"]) and np.abs(ra["f_rng"]).max() > 0
+
+
+def test_emulated_fix_output_files_match_reference(ni_trunc_beta, tmp_path):
+    """the files the fix writes: heat maps `T_out_%06d` every `freq` steps (fix_eph.cpp:397-399) and the restart file of
+    post_run (fix_eph.cpp:1019-1021; `<T_infile>.restart` when the grid came from a file) -- product against the
+    compiled reference, both inside the stand-in, each in its own working directory; the restart is then read back as
+    T_infile of a continuation run"""
+    from oracle import reference as R
+    if not R.available():
+        pytest.skip("compiled reference not present")
+    s = H.make_system(3)
+    xis = [np.random.default_rng(70 + k).normal(size=(s["nlocal"], 3)) for k in range(4)]
+    nc = 4 * 3 * 2
+    T0 = 300 + 50 * np.random.default_rng(10).random(nc)
+    fl = np.ones(nc, dtype=np.int64)
+    fl[::5] = 2
+    fl[7] = 0
+    out = {}
+    for who in ("ref", "b200"):
+        d = tmp_path / who
+        d.mkdir()
+        H.write_grid_file(d / "T.in", 4, 3, 2, G.box6(s), T0, 0.0, 1.0, 3.5e-6, 0.1248, fl, 0, steps=1)
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            style = "eph" if who == "ref" else "eph/b200"
+            extra = [] if who == "ref" else ["rng", "mars"]
+            args = H.fix_args(7, ni_trunc_beta, ["Ni"], T_infile="T.in", T_freq=2, T_out="T_out", style=style, extra=extra)
+            drv = R.fix_driver(s, args) if who == "ref" else host.FixDriver(s, args)
+            recs = traj.run_fix_driver(drv, s, xis)
+            drv.post_run()
+            out[who] = dict(files=sorted(os.listdir(d)), recs=recs,
+                            content={f: open(d / f).read() for f in os.listdir(d) if f != "T.in"})
+        finally:
+            os.chdir(cwd)
+    assert out["ref"]["files"] == out["b200"]["files"] == ["T.in", "T.in.restart", "T_out_000001", "T_out_000002"]
+    for name, text in out["ref"]["content"].items():
+        ours = out["b200"]["content"][name]
+        if ours != text:   # %e formatting of values that agree to 1e-14 can differ in the last printed digit
+            a = np.array([float(t) for t in text.split() if t[0].isdigit() or t[0] in "+-."], dtype=float)
+            b = np.array([float(t) for t in ours.split() if t[0].isdigit() or t[0] in "+-."], dtype=float)
+            assert a.shape == b.shape and np.allclose(a, b, rtol=2e-6, atol=0), name
+        assert text.splitlines()[:7] == ours.splitlines()[:7], name           # headers identical
+    # continuation from the product's restart file equals continuation from the reference's
+    for who in ("ref", "b200"):
+        cwd = os.getcwd()
+        os.chdir(tmp_path / who)
+        try:
+            args = H.fix_args(7, ni_trunc_beta, ["Ni"], T_infile="T.in.restart", style="eph/b200", extra=["rng", "mars"])
+            out[who + "2"] = traj.run_fix_driver(host.FixDriver(s, args), s, xis[:2])
+        finally:
+            os.chdir(cwd)
+    for ra, rb in zip(out["ref2"], out["b2002"]):
+        assert H.error_metrics(rb["T"], ra["T"]) < 1e-6 and H.error_metrics(rb["f"], ra["f"]) < 1e-6
