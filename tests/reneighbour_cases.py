@@ -50,3 +50,30 @@ def atomic_case(make_fix, comm):
     b = traj.run_with_reneighbouring(lambda sy: make_fix(sy, our_args), s, xis, SCHEDULE)
     assert len({r["nghost"] for r in a}) >= 3
     traj.assert_same_trajectory(a, b, TOL)
+
+
+def adaptive_dt_case(kind, make_fix=None):
+    """the cascade configuration runs with an adaptive time step (`Tests/MD_Run/run.lmp:94-97`): reset_dt
+    at every change, product against the compiled reference (eta factor, grid dt and sub-stepping, memory-kernel zeta,
+    ledger dt)"""
+    from oracle import reference as R
+    s = H.make_system(3, skin=2.0)
+    xis = [np.random.default_rng(95 + k).normal(size=(s["nlocal"], 3)) for k in range(6)]
+    dts = [5.5e-7, 5.5e-7, 2.0e-6, 1.0e-5, 1.0e-4, 1.0e-4]
+    if kind == "atomic":
+        if not R.atomic_available():
+            pytest.skip("compiled reference not present")
+        ref_args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2)
+        our_args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2, style="eph/atomic/b200") + ["rng", "mars"]
+        mk_ref, mk_our = (lambda sy: R.atomic_fix_driver(sy, ref_args)), (lambda sy: make_fix(sy, our_args))
+    else:
+        if not (R.available() and R.coloured_available()):
+            pytest.skip("compiled reference not present")
+        style, extra = ("eph/coloured/exp", dict(model="5e-4")) if kind == "coloured" else ("eph", {})
+        ref_args = H.fix_args(7, BETA, ["Ni"], grid=(4, 4, 4), style=style, **extra)
+        our_args = H.fix_args(7, BETA, ["Ni"], grid=(4, 4, 4), style=style + "/b200", extra=["rng", "mars"], **extra)
+        mk_ref = (lambda sy: R.coloured_fix_driver(sy, ref_args)) if kind == "coloured" else (lambda sy: R.fix_driver(sy, ref_args))
+        mk_our = lambda sy: host.FixDriver(sy, our_args)
+    a = traj.run_with_reneighbouring(mk_ref, s, xis, {}, dts=dts)
+    b = traj.run_with_reneighbouring(mk_our, s, xis, {}, dts=dts)
+    traj.assert_same_trajectory(a, b, TOL)

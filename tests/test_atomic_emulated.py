@@ -206,3 +206,8 @@ def test_emulated_call_order_errors_are_reported(make_engine, kappa_tables):
         eng.end_of_step()
     with pytest.raises(lib.EphError, match="unknown probe"):
         eng.probe(42)
+
+
+def test_emulated_fix_adaptive_time_step_matches_reference(make_fix):
+    import reneighbour_cases
+    reneighbour_cases.adaptive_dt_case("atomic", make_fix)

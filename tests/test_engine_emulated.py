@@ -391,3 +391,9 @@ def test_emulated_fix_output_files_match_reference(ni_trunc_beta, tmp_path):
             os.chdir(cwd)
     for ra, rb in zip(out["ref2"], out["b2002"]):
         assert H.error_metrics(rb["T"], ra["T"]) < 1e-6 and H.error_metrics(rb["f"], ra["f"]) < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["plain", "coloured"])
+def test_emulated_fix_adaptive_time_step_matches_reference(kind):
+    import reneighbour_cases
+    reneighbour_cases.adaptive_dt_case(kind)

@@ -80,3 +80,8 @@ def test_atomic_engine_three_elements_in_both_files(make_engine, tmp_path):
     kappa3 = str(H.write_kappa_file(tmp_path / "synth3.kappa", H.synthetic_kappa(3, n_r=501, n_T=401, dT=2.5)))
     cases.trajectory_case(make_engine, A.KappaTables(kappa3), 7, 2, 0.8, ntypes=3, beta=beta3, names=("Ni", "Co", "Cr"),
                           kappa=kappa3, tk=[2, 0, 1])
+
+
+def test_fix_atomic_b200_adaptive_time_step_matches_reference():
+    import reneighbour_cases
+    reneighbour_cases.adaptive_dt_case("atomic", lambda s, args: A.fix_driver(s, args))

@@ -107,3 +107,11 @@ def test_fix_b200_through_reneighbouring_matches_reference(style, extra):
     continues exactly like the compiled reference fix"""
     import reneighbour_cases
     reneighbour_cases.fix_case(style, extra)
+
+
+@pytest.mark.parametrize("kind", ["plain", "coloured"])
+def test_fix_b200_adaptive_time_step_matches_reference(kind):
+    """the cascade configuration's adaptive time step: reset_dt at every change (eta factor, grid dt and sub-step count,
+    memory-kernel zeta), FixEPHB200 against the compiled reference fix"""
+    import reneighbour_cases
+    reneighbour_cases.adaptive_dt_case(kind)

@@ -301,12 +301,15 @@ def reneighbour(drv, system, shell):
     return s
 
 
-def run_with_reneighbouring(make_driver, system, xis, schedule):
-    """schedule: {step index: ghost shell} -- before that step the ghosts and the list are rebuilt with that shell"""
+def run_with_reneighbouring(make_driver, system, xis, schedule, dts=None):
+    """schedule: {step index: ghost shell} -- before that step the ghosts and the list are rebuilt with that shell;
+    dts: time step of every step (LAMMPS' `fix dt/reset`: Fix::reset_dt is called whenever it changes)"""
     drv = make_driver(system)
     s = system
     out = []
     for k, xi in enumerate(xis):
+        if dts is not None and (k == 0 or dts[k] != dts[k - 1]):
+            drv.set_dt(dts[k])
         if k in schedule:
             s = reneighbour(drv, s, schedule[k])
         nl = s["nlocal"]
