@@ -46,7 +46,7 @@ def _swap_in_emulated_engine():
     lib.Engine.grid_tensor = grid_tensor
 
 
-def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first):
+def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -61,6 +61,8 @@ def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first):
         eng.set_tables_from(host.BetaTables(path=beta))
         eng.set_grid(*gshape, box, 300.0, 1.0, 3.5e-6, 0.1248)
         eng.set_dt(DT)
+        if tau0 > 0:
+            eng.set_colour(tau0)          # fix eph/coloured/exp: the memory kernel filters each rank's own atoms
         keep = [np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
                 np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(plan.self_owner, dtype=np.int32),
                 np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32)]
@@ -88,14 +90,15 @@ def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,gshape,sharded,boundary_first", [(2, (3, 2, 2), False, False), (2, (3, 2, 2), False, True),
-                                                                 (2, (8, 8, 8), True, False), (4, (8, 8, 8), True, True)])
-def test_distributed_step_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first):
+@pytest.mark.parametrize("world,gshape,sharded,boundary_first,tau0", [(2, (3, 2, 2), False, False, 0.0), (2, (3, 2, 2), False, True, 0.0),
+                                                                      (2, (8, 8, 8), True, False, 0.0), (4, (8, 8, 8), True, True, 0.0),
+                                                                      (2, (3, 2, 2), False, True, 5e-4)])
+def test_distributed_step_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first, tau0):
     subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first, tau0)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
@@ -105,6 +108,8 @@ def test_distributed_step_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, w
     nlw = whole["nlocal"]
     box = [0, whole["box"][0], 0, whole["box"][1], 0, whole["box"][2]]
     fx = O.Fix(whole, O.Beta(path=synth_beta_1), O.FDM(*gshape, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=DT)
+    if tau0 > 0:
+        fx.set_colour(tau0)
     order = np.argsort(whole["tag"][:nlw])
     E_prev = 0.0
     assert sum(len(tags) for _, tags, _, _ in res) == nlw
