@@ -187,3 +187,33 @@ def reordering_case(make_fix, comm="device"):
     xi = [np.random.default_rng(40 + k).normal(size=(s["natoms"], 3)) for k in range(4)]
     args = H.atomic_fix_args(7, BETA, KAPPA, ["Ni"], inner_loops=2, style="eph/atomic/b200") + ["rng", "mars", "comm", comm]
     traj.assert_reordering_is_transparent(lambda system: make_fix(system, args), s, xi, permute_after=2, tol=TOL)
+
+
+def ragged_case(make_engine, kappa_tables):
+    """empty and ragged inputs: no atoms at all; then an isolated cluster without ghosts in which one atom has no
+    neighbour (rho = 0: skipped everywhere, fix_eph_atomic.cpp:515) and one lies outside the fix group"""
+    eng = make_engine([0], [0], 7, inner_loops=2)
+    eng.set_tables_from(host.BetaTables(path=BETA), kappa_tables)
+    eng.set_dt(1e-4)
+    z = np.zeros((0, 3))
+    eng.set_atoms(0, 0, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64), None)
+    eng.set_neighbors(np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int32))
+    eng.post_force(z, z, z.copy(), None, 1)       # nothing to do, no error
+    rng = np.random.default_rng(5)
+    nl = 20
+    x = np.ascontiguousarray(rng.uniform(0, 9, (nl, 3)))
+    x[7] = [40.0, 40.0, 40.0]
+    v = rng.normal(size=(nl, 3))
+    off, ne = H.neighbor_list(x, nl, 7.0)
+    mask = np.ones(nl, dtype=np.int32)
+    mask[3] = 0
+    s = dict(nlocal=nl, nghost=0, x=x, v=v, f=np.zeros_like(x), type=np.ones(nl, dtype=np.int32), mask=mask, tag=np.arange(1, nl + 1),
+             ghost_owner=np.zeros(0, dtype=np.int32), offsets=off, neigh=ne, box=np.array([50.0, 50.0, 50.0]), ntypes=1)
+    eng.set_atoms(nl, 0, s["type"], mask, np.ascontiguousarray(s["tag"], dtype=np.int64), None)
+    eng.set_neighbors(np.ascontiguousarray(off, dtype=np.int64), np.ascontiguousarray(ne, dtype=np.int32))
+    eng.init_energy(300.0)
+    fx = O.AtomicFix(s, O.Beta(path=BETA), O.Kappa(KAPPA), 7, inner_loops=2)
+    xis = [rng.normal(size=(nl, 3)) for _ in range(3)]
+    recs = traj.run_atomic_engine(eng, s, xis, [58.71], 1e-4)
+    compare(recs, traj.run_atomic_oracle(fx, s, xis, [58.71]), in_group=mask != 0)
+    assert recs[-1]["rho"][7] == 0.0 and not recs[-1]["f"][7].any() and not recs[-1]["array"][3].any()

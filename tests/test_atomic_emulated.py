@@ -211,3 +211,7 @@ def test_emulated_call_order_errors_are_reported(make_engine, kappa_tables):
 def test_emulated_fix_adaptive_time_step_matches_reference(make_fix):
     import reneighbour_cases
     reneighbour_cases.adaptive_dt_case("atomic", make_fix)
+
+
+def test_emulated_empty_and_ragged_inputs(make_engine, kappa_tables):
+    cases.ragged_case(make_engine, kappa_tables)

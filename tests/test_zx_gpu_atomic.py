@@ -85,3 +85,7 @@ def test_atomic_engine_three_elements_in_both_files(make_engine, tmp_path):
 def test_fix_atomic_b200_adaptive_time_step_matches_reference():
     import reneighbour_cases
     reneighbour_cases.adaptive_dt_case("atomic", lambda s, args: A.fix_driver(s, args))
+
+
+def test_atomic_engine_empty_and_ragged_inputs(make_engine, kappa_tables):
+    cases.ragged_case(make_engine, kappa_tables)
