@@ -128,6 +128,17 @@ int eph_b200_set_colour(eph_b200_handle *h, double tau0);
 int eph_b200_get_colour_state(eph_b200_handle *h, double *f_dis, double *f_sto, int memspace);
 int eph_b200_set_colour_state(eph_b200_handle *h, const double *f_dis, const double *f_sto, int memspace);
 
+/* Gather records of the two list sweeps.  packed_records = 1 (default; EPH_B200_RECORDS=packed): steps that walk the
+ * inner list read 16-byte fixed-point positions (42-bit fractions of a period P, a power of two > 2 (r_c + 2 inner_skin);
+ * quantum P / 2^42 = 3.6e-12 A at the defaults) and 16-byte block-floating-point vectors (v, u, z: 40-bit mantissas,
+ * <= 1.8e-12 of the largest component) -- half the 32-byte sectors per list slot of the fp64 records.  The error this
+ * adds to rho_i, w_i, f_EPH, f_RNG stays below ~1e-11 of the largest value (the bar is 1e-10).
+ * packed_records = 0 (EPH_B200_RECORDS=exact): fp64 records everywhere (agreement with the reference ~1e-14).
+ * Packed records need model 4, at most four elements and the inner list; otherwise the fp64 records are used.
+ * get_precision reports what the next step will use (period and position quantum in A, 0 when fp64). */
+int eph_b200_set_precision(eph_b200_handle *h, int packed_records);
+int eph_b200_get_precision(eph_b200_handle *h, int *packed_records, double *period, double *position_quantum);
+
 /* LAMMPS' neighbor->skin and the skin of the device-side inner list (two-level Verlet list: the sweeps walk a
  * list cut at r_c + inner_skin that the device rebuilds from LAMMPS' list; a device-side displacement check falls
  * back to LAMMPS' list whenever the inner one could be incomplete, so results never depend on this setting).

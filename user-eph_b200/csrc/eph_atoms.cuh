@@ -4,6 +4,7 @@
 #pragma once
 
 #include "eph_device.cuh"
+#include "eph_packed.cuh"
 
 namespace ephb {
 
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
                                   const int *__restrict__ type, const int *__restrict__ mask,
                                   const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
                                   double4 *__restrict__ pv, int track, int track0, const double4 *__restrict__ xref,
-                                  const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st) {
+                                  const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st,
+                                  Packed32 *__restrict__ recD, double inv_period, unsigned *__restrict__ status) {
   __shared__ double s_max[8];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   double d0 = 0.0;
@@ -33,8 +35,17 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
     const double px = x[3 * (size_t)a], py = x[3 * (size_t)a + 1], pz = x[3 * (size_t)a + 2];
     const double4 p4 = make_double4(px, py, pz, bits_to_double(bits));
     pos4[a] = p4;
-    pv[2 * (size_t)a] = p4;
-    pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+    const double vx = v[3 * (size_t)a], vy = v[3 * (size_t)a + 1], vz = v[3 * (size_t)a + 2];
+    if (pv != nullptr) {   // fp64 records: steps that walk LAMMPS' list (always, without packed records)
+      pv[2 * (size_t)a] = p4;
+      pv[2 * (size_t)a + 1] = make_double4(vx, vy, vz, 0.0);
+    }
+    if (recD != nullptr) {   // packed density-pass record (eph_packed.cuh); flags: element index
+      Packed32 r;
+      r.p = pack_position(px, py, pz, inv_period, bits & 3u);
+      r.b = pack_vector(vx, vy, vz, status);
+      recD[a] = r;
+    }
     if (track) {
       const double4 r = xref[a];
       const double dx = px - r.x, dy = py - r.y, dz = pz - r.z;
@@ -57,6 +68,18 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
       atomicMax(&st->disp0_sq_bits, (unsigned long long)__double_as_longlong(m));
     }
   }
+}
+
+// fp64 density-pass records for a step that turns out to need them: the packed density pass returns at once when the
+// displacement guard of pack_atoms has invalidated the inner list, and the fp64 pass that walks LAMMPS' list instead
+// gathers from pv.  Launched behind pack_atoms in every packed step; does nothing while the inner list is valid.
+__global__ void __launch_bounds__(256) pv_fill_kernel(int ntotal, const double *__restrict__ v, const double4 *__restrict__ pos4,
+                                                      double4 *__restrict__ pv, const ListState *__restrict__ st) {
+  if (st->inner_invalid == 0u) return;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= ntotal) return;
+  pv[2 * (size_t)a] = pos4[a];
+  pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
 }
 
 struct PrepArgs {
@@ -85,6 +108,13 @@ struct PrepArgs {
   int built_inner;
   double skin, inner_skin;
   ListState *__restrict__ list_state;
+  // packed force-pass records (eph_packed.cuh), nullptr without them: A = {position + valid/group flags | u}, B = {z},
+  // var = eta_factor sqrt(T_e(cell)) per local atom
+  Packed32 *__restrict__ recA;
+  Block16 *__restrict__ recB;
+  double *__restrict__ var;
+  double inv_period;
+  int puz_mode;   // fp64 record puz: 2 always, 1 only if the inner list is invalid (the fp64 force pass will run), 0 never
 };
 
 // Between the two passes, for locals and ghosts alike: ghost rho and W come from the owner (the reference's
@@ -142,10 +172,21 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
     cell = grid_index(p.grid, pa.x, pa.y, pa.z);
     if (p.do_random) var = p.eta_factor * sqrt(p.T_e[cell]);
   }
-  double4 *rec = p.puz + 3 * (size_t)a;
-  rec[0] = pa;
-  rec[1] = make_double4(s * wx, s * wy, s * wz, s * xi[0]);
-  rec[2] = make_double4(s * xi[1], s * xi[2], var, bits_to_double(static_cast<unsigned>(cell)));
+  const double ux = s * wx, uy = s * wy, uz = s * wz, zx = s * xi[0], zy = s * xi[1], zz = s * xi[2];
+  if (p.puz_mode == 2 || (p.puz_mode == 1 && p.list_state->inner_invalid != 0u)) {
+    double4 *rec = p.puz + 3 * (size_t)a;
+    rec[0] = pa;
+    rec[1] = make_double4(ux, uy, uz, zx);
+    rec[2] = make_double4(zy, zz, var, bits_to_double(static_cast<unsigned>(cell)));
+  }
+  if (p.recA != nullptr) {
+    Packed32 r;
+    r.p = pack_position(pa.x, pa.y, pa.z, p.inv_period, ((bits & kBitValid) ? 1u : 0u) | ((bits & kBitGroup) ? 2u : 0u));
+    r.b = pack_vector(ux, uy, uz, p.status);
+    p.recA[a] = r;
+    if (p.do_random) p.recB[a] = pack_vector(zx, zy, zz, p.status);
+    if (a < p.nlocal) p.var[a] = var;
+  }
   if (a < p.nlocal) {
     p.xi[3 * (size_t)a] = xi[0]; p.xi[3 * (size_t)a + 1] = xi[1]; p.xi[3 * (size_t)a + 2] = xi[2];
   }

@@ -97,6 +97,12 @@ struct eph_b200_handle {
   // internal per-atom records
   DevBuf<double4> pos4, pv, puz, W4;
   DevBuf<double> rho, w, xi, f_eph, f_rng, array8, gpair, gpair_i;
+  // packed gather records (eph_packed.cuh): half the sectors per list slot of the fp64 records pv / puz
+  DevBuf<Packed32> recD, recA;
+  DevBuf<Block16> recB;
+  DevBuf<double> var;
+  int precision = 1;            // 1: packed records where they apply (default), 0: fp64 records everywhere
+  bool step_packed = false;     // this step's density pass ran on packed records (the fp64 pass stands by as fall-back)
   // `fix eph/coloured/exp` (fix_eph_coloured_exp.cpp): exponential memory kernel on both forces; the filtered forces of
   // the previous step are per-atom state (f_dis, f_sto [nlocal][3])
   bool coloured = false;
@@ -346,6 +352,22 @@ bool encode_grid_map(CUtensorMap *map, double *base, int nx, int ny, int nz, int
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- packed records (eph_packed.cuh) ----
+// Period of the packed positions: a power of two comfortably above twice the largest pair distance a walk of the inner
+// list can meet (r_c + inner_skin when the list is built, plus inner_skin of relative drift before the displacement
+// guard of pack_atoms trips).
+double packed_period(const eph_b200_handle *h) {
+  const double reach = std::sqrt(h->rc2) + 2.0 * h->inner_skin;
+  double P = 1.0;
+  while (P < 2.2 * reach) P *= 2.0;
+  return P;
+}
+// Packed records serve model PRL with at most four elements (two flag bits) and need the inner list; a period above
+// 64 A would make the position quantum too coarse for the 1e-10 bar.
+bool packed_possible(const eph_b200_handle *h) {
+  return h->precision == 1 && h->tables_set && h->cfg.model == EPH_B200_MODEL_PRL && h->n_el <= 4 && h->inner_enabled &&
+         packed_period(h) <= 64.0;
+}
 }  // namespace
 
 extern "C" {
@@ -388,6 +410,10 @@ int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out) {
   if (const char *e = std::getenv("EPH_B200_INNER_SKIN")) {
     h->inner_skin = std::atof(e);
     h->inner_enabled = h->inner_wanted = h->inner_skin > 0.0;
+  }
+  if (const char *e = std::getenv("EPH_B200_RECORDS")) {   // gather records: "exact" (fp64) or "packed" (default)
+    if (std::strcmp(e, "exact") == 0) h->precision = 0;
+    else if (std::strcmp(e, "packed") == 0) h->precision = 1;
   }
   if (const char *e = std::getenv("EPH_B200_LANES")) {   // tuning knob: lanes per atom in the sweeps
     const int v = std::atoi(e);
@@ -438,6 +464,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->pos4.release(); h->pv.release(); h->puz.release(); h->W4.release(); h->gpair.release(); h->gpair_i.release();
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
   h->f_dis.release(); h->f_sto.release();
+  h->recD.release(); h->recA.release(); h->recB.release(); h->var.release();
   h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -725,6 +752,22 @@ int eph_b200_set_colour_state(eph_b200_handle *h, const double *f_dis, const dou
   return EPH_B200_OK;
 }
 
+int eph_b200_set_precision(eph_b200_handle *h, int packed_records) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (h->pf_open) return fail(h, EPH_B200_ERR_ARG, "set_precision: not between post_force_begin and post_force_end");
+  h->precision = packed_records ? 1 : 0;
+  return EPH_B200_OK;
+}
+
+int eph_b200_get_precision(eph_b200_handle *h, int *packed_records, double *period, double *position_quantum) {
+  if (!h) return EPH_B200_ERR_ARG;
+  const bool on = packed_possible(h);
+  if (packed_records) *packed_records = on ? 1 : 0;
+  if (period) *period = on ? packed_period(h) : 0.0;
+  if (position_quantum) *position_quantum = on ? packed_period(h) / kQScale : 0.0;
+  return EPH_B200_OK;
+}
+
 int eph_b200_set_skin(eph_b200_handle *h, double skin, double inner_skin) {
   if (!h) return EPH_B200_ERR_ARG;
   if (skin < 0.0) return fail(h, EPH_B200_ERR_ARG, "set_skin: negative skin");
@@ -768,6 +811,8 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   }
   EPH_CUDA(h, h->pos4.reserve(nt)); EPH_CUDA(h, h->pv.reserve(2 * nt)); EPH_CUDA(h, h->puz.reserve(3 * nt));
   EPH_CUDA(h, h->rho.reserve(nt)); EPH_CUDA(h, h->W4.reserve(nt));
+  EPH_CUDA(h, h->recD.reserve(nt)); EPH_CUDA(h, h->recA.reserve(nt)); EPH_CUDA(h, h->recB.reserve(nt));
+  EPH_CUDA(h, h->var.reserve(std::max<size_t>(nlocal, 1)));
   EPH_CUDA(h, h->xref.reserve(nt)); EPH_CUDA(h, h->xref0.reserve(nt)); EPH_CUDA(h, h->icount.reserve(std::max<size_t>(nlocal, 1)));
   h->have_inner = false;
   const size_t nl = std::max<size_t>(nlocal, 1);
@@ -996,7 +1041,7 @@ int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool bui
 template <int LANES, bool MULTI>
 int launch_force(eph_b200_handle *h, const SweepArgs &a) {
   const int threads = EPH_THREADS_FORCE;
-  KernelTimer kt(h, "force_sweep");
+  KernelTimer kt(h, a.only_fallback ? "force_sweep_fallback" : "force_sweep");
   auto k = force_sweep_kernel<LANES, MULTI>;
   k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a);
   EPH_LAUNCH_CHECK(h);
@@ -1014,9 +1059,70 @@ int launch_density_lanes(eph_b200_handle *h, const SweepArgs &a, size_t smem, in
   }
 }
 
+// ---- packed records (eph_packed.cuh) ----
+PackedArgs packed_args(const eph_b200_handle *h) {
+  PackedArgs q{};
+  q.D = h->recD.p; q.A = h->recA.p; q.B = h->recB.p; q.pos4 = h->pos4.p; q.var = h->var.p;
+  const double quantum = packed_period(h) / kQScale;
+  q.quantum_sq = quantum * quantum;
+  return q;
+}
+
+template <int LANES, bool MULTI>
+int launch_density_packed(eph_b200_handle *h, const SweepArgs &a, const char *name) {
+  const int threads = 256;
+  KernelTimer kt(h, name ? name : "density_sweep");
+  auto k = density_packed_kernel<LANES, MULTI>;
+  k<<<sweep_grid(h, k, threads, 0, a.n_work, threads / LANES), threads, 0, h->stream>>>(a, packed_args(h));
+  EPH_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+template <int LANES, bool MULTI>
+int launch_force_packed(eph_b200_handle *h, const SweepArgs &a) {
+  const int threads = EPH_THREADS_FORCE;
+  KernelTimer kt(h, "force_sweep");
+  auto k = force_packed_kernel<LANES, MULTI>;
+  k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a, packed_args(h));
+  EPH_LAUNCH_CHECK(h);
+  return EPH_B200_OK;
+}
+// which: 0 density, 1 force
+int launch_packed(eph_b200_handle *h, const SweepArgs &a, int which, const char *name = nullptr) {
+  const bool multi = a.n_elements > 1;
+#define EPH_PACKED_CASE(L)                                                                                       \
+  case L:                                                                                                        \
+    if (which == 0) return multi ? launch_density_packed<L, true>(h, a, name) : launch_density_packed<L, false>(h, a, name); \
+    return multi ? launch_force_packed<L, true>(h, a) : launch_force_packed<L, false>(h, a);
+  switch (h->lanes) {
+    EPH_PACKED_CASE(1)
+    EPH_PACKED_CASE(2)
+    EPH_PACKED_CASE(8)
+    EPH_PACKED_CASE(16)
+    default: break;
+  }
+  if (which == 0) return multi ? launch_density_packed<4, true>(h, a, name) : launch_density_packed<4, false>(h, a, name);
+  return multi ? launch_force_packed<4, true>(h, a) : launch_force_packed<4, false>(h, a);
+#undef EPH_PACKED_CASE
+}
+
+int launch_sweep_exact(eph_b200_handle *h, const SweepArgs &a, int which, bool build, const char *name);
+
 // which: 0 density pass (optionally rebuilding the inner list), 1 force pass.  Both passes use the same number of
-// lanes per atom: it fixes the tile shape of the inner list and of the pair weights.
-int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false, const char *name = nullptr) {
+// lanes per atom: it fixes the tile shape of the inner list and of the pair weights.  `packed`: the pass runs on the
+// packed records; where the inner list may turn out invalid on the device (density pass, force pass in walk mode 1)
+// the fp64 kernel is launched behind it as a fall-back that returns at once in the normal case.
+int launch_sweep(eph_b200_handle *h, const SweepArgs &a, int which, bool build = false, const char *name = nullptr,
+                 bool packed = false) {
+  if (!packed) return launch_sweep_exact(h, a, which, build, name);
+  int rc = launch_packed(h, a, which, name);
+  if (rc) return rc;
+  if (which == 1 && a.walk_mode == 2) return EPH_B200_OK;   // list built in this very step: nothing to fall back from
+  SweepArgs b = a;
+  b.only_fallback = 1;
+  return launch_sweep_exact(h, b, which, false, which == 0 ? "density_sweep_fallback" : "force_sweep_fallback");
+}
+
+int launch_sweep_exact(eph_b200_handle *h, const SweepArgs &a, int which, bool build, const char *name) {
   const bool multi = a.n_elements > 1;
   if (which == 1) {
     switch (h->lanes) {
@@ -1105,17 +1211,27 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   const bool track0 = track && build && !h->fresh_neighbors;
   if (track0)
     EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->disp0_sq_bits, 0, sizeof(unsigned long long), h->stream));
+  // packed records serve every step that walks the inner list; a step that builds it (or has none) walks LAMMPS' list
+  // on the fp64 records
+  const bool use_inner = h->inner_enabled && h->have_inner && !build;
+  const bool packed = packed_possible(h) && use_inner;
+  h->step_packed = packed;
   {
     KernelTimer kt(h, "pack_atoms");
     const double half = 0.5 * h->inner_skin;
     pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
-                                                                   h->cfg.groupbit, h->pos4.p, h->pv.p, track ? 1 : 0,
-                                                                   track0 ? 1 : 0, h->xref.p, h->xref0.p, half * half, h->lstate.p);
+                                                                   h->cfg.groupbit, h->pos4.p, packed ? nullptr : h->pv.p, track ? 1 : 0,
+                                                                   track0 ? 1 : 0, h->xref.p, h->xref0.p, half * half, h->lstate.p,
+                                                                   packed ? h->recD.p : nullptr, 1.0 / packed_period(h), h->d_status.p);
   }
   EPH_LAUNCH_CHECK(h);
+  if (packed) {   // fp64 records only if the guard just tripped (the kernel returns at once otherwise)
+    pv_fill_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dv, h->pos4.p, h->pv.p, h->lstate.p);
+    EPH_LAUNCH_CHECK(h);
+  }
 
   SweepArgs a = sweep_args(h);
-  a.use_inner = (h->inner_enabled && h->have_inner && !build) ? 1 : 0;
+  a.use_inner = use_inner ? 1 : 0;
   const int tile_atoms = 32 / h->lanes;
   a.work = nullptr; a.n_work = nl; a.n_boundary = 0; a.done_counter = nullptr;
   h->boundary_by_counter = false;
@@ -1127,18 +1243,18 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
     a.n_boundary = h->n_first * tile_atoms; a.done_counter = h->done_counter.p;
     h->boundary_target += (unsigned)h->n_first;
     h->boundary_by_counter = true;
-    if ((rc = launch_sweep(h, a, 0, build))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
   } else if (h->comm_stream && h->split_ready && h->n_first > 0) {
     // no stream memory operations: two launches with an event between them
     a.work = h->work_all.p; a.n_work = h->n_first * tile_atoms;
-    if ((rc = launch_sweep(h, a, 0, build, "density_sweep_boundary"))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build, "density_sweep_boundary", packed))) return rc;
     EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
     if (h->n_rest > 0) {
       a.work = h->work_all.p + h->n_first; a.n_work = h->n_rest * tile_atoms;
-      if ((rc = launch_sweep(h, a, 0, build))) return rc;
+      if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
     }
   } else {
-    if ((rc = launch_sweep(h, a, 0, build))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
     if (h->comm_stream) EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
   }
   h->boundary_recorded = h->comm_stream != nullptr;
@@ -1195,6 +1311,13 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   p.w = h->w.p; p.xi = h->xi.p; p.status = h->d_status.p;
   p.built_inner = build ? 1 : 0; p.skin = h->skin >= 0.0 ? h->skin : h->inner_skin; p.inner_skin = h->inner_skin;
   p.list_state = h->lstate.p;
+  // which list the force pass walks: the one whose slots this step's density pass filled with pair weights
+  const int walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
+  // ... and on which records: packed whenever that is the inner list (its pairs are within reach of the packed
+  // positions by construction); the fp64 record is then only written if the guard tripped this step
+  const bool force_packed = packed_possible(h) && walk_mode != 0;
+  p.recA = force_packed ? h->recA.p : nullptr; p.recB = h->recB.p; p.var = h->var.p; p.inv_period = 1.0 / packed_period(h);
+  p.puz_mode = !force_packed ? 2 : (walk_mode == 1 ? 1 : 0);
   {
     KernelTimer kt(h, "prep_coupling");
     prep_coupling_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(p);
@@ -1242,8 +1365,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
     }
   } else if (h->cfg.model == EPH_B200_MODEL_PRL && (a.do_friction || a.do_random)) {
     a.f = (add_fric || add_rand) ? df : nullptr;
-    // walk the list whose slots this step's density pass filled with pair weights
-    a.walk_mode = build ? 2 : ((h->inner_enabled && h->have_inner) ? 1 : 0);
+    a.walk_mode = walk_mode;
     a.add_friction = add_fric ? 1 : 0;
     a.add_random = add_rand ? 1 : 0;
     if (h->coloured) {
@@ -1251,7 +1373,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
       // forces are what goes into f (fix_eph_coloured_exp.cpp:563-569, :619-625, :664-678)
       a.f = nullptr;
       a.i_begin = 0; a.i_end = nl;
-      if ((rc = launch_sweep(h, a, 1))) return rc;
+      if ((rc = launch_sweep(h, a, 1, false, nullptr, force_packed))) return rc;
       ColourArgs c{};
       c.nlocal = nl; c.pos4 = h->pos4.p; c.rho = h->rho.p; c.zeta = h->zeta;
       c.do_friction = a.do_friction; c.do_random = a.do_random;
@@ -1276,7 +1398,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
       for (int i0 = 0; i0 < nl; i0 += per) {
         const int i1 = std::min(nl, i0 + per);
         a.i_begin = i0; a.i_end = i1;
-        if ((rc = launch_sweep(h, a, 1))) return rc;
+        if ((rc = launch_sweep(h, a, 1, false, nullptr, force_packed))) return rc;
         EPH_CUDA(h, cudaEventRecord(h->f_event, h->stream));
         EPH_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->f_event, 0));
         EPH_CUDA(h, cudaMemcpyAsync(f + 3 * (size_t)i0, h->f.p + 3 * (size_t)i0, 3 * (size_t)(i1 - i0) * sizeof(double),
@@ -1286,7 +1408,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
       EPH_CUDA(h, cudaStreamSynchronize(h->stream));
     } else {
       a.i_begin = 0; a.i_end = nl;
-      if ((rc = launch_sweep(h, a, 1))) return rc;
+      if ((rc = launch_sweep(h, a, 1, false, nullptr, force_packed))) return rc;
     }
   }
   h->forces_valid = true;

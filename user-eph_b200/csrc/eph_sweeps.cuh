@@ -96,6 +96,8 @@ struct SweepArgs {
   double *__restrict__ f_eph;             // [nlocal][3]
   double *__restrict__ f_rng;             // [nlocal][3]
   int do_friction, do_random, add_friction, add_random;
+  int only_fallback;                      // this launch follows a packed sweep (eph_packed.cuh): run only if that one stood
+                                          // down because the inner list is invalid
 };
 
 // rho(r^2) table access.  TAB = 1: both halves of every record staged in shared
@@ -156,6 +158,7 @@ __device__ __forceinline__ RowWalk walk_tile(const SweepArgs &a, int i, int lane
 template <int LANES, int TAB, bool BUILD, bool MULTI>
 __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(SweepArgs a) {
   extern __shared__ double2 s_tab[];
+  if (a.only_fallback && *a.inner_invalid == 0u) return;
   const RhoTable<TAB> tab = stage_tables<TAB>(a, s_tab);
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES - 1);
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_sweep
   const unsigned gmask = group_mask<LANES>(lane);
   const int groups_per_block = blockDim.x / LANES;
   const int group_in_block = threadIdx.x / LANES;
+  if (a.only_fallback && *a.inner_invalid == 0u) return;
   // the list whose slots the density pass of this step filled
   const bool inner = a.walk_mode == 2 || (a.walk_mode == 1 && *a.inner_invalid == 0u);
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;

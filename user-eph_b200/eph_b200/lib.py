@@ -44,6 +44,8 @@ SYMBOLS = {
     "eph_b200_set_colour": (C.c_int, [C.c_void_p, C.c_double]),
     "eph_b200_get_colour_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_set_colour_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "eph_b200_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "eph_b200_get_precision": (C.c_int, [C.c_void_p, c_int_p, c_double_p, c_double_p]),
     "eph_b200_set_skin": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "eph_b200_list_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "eph_b200_set_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -237,6 +239,15 @@ class Engine:
     def set_colour_state(self, f_dis, f_sto):
         ps = [_ptr(f_dis), _ptr(f_sto)]
         self._check(self.lib.eph_b200_set_colour_state(self.h, ps[0][0], ps[1][0], _space(*ps)))
+
+    def set_precision(self, packed=True):
+        """gather records of the sweeps: packed (16-byte positions / vectors, default) or fp64"""
+        self._check(self.lib.eph_b200_set_precision(self.h, int(bool(packed))))
+
+    def precision(self):
+        on, period, quantum = C.c_int(), C.c_double(), C.c_double()
+        self._check(self.lib.eph_b200_get_precision(self.h, C.byref(on), C.byref(period), C.byref(quantum)))
+        return {"packed": bool(on.value), "period": period.value, "position_quantum": quantum.value}
 
     def set_skin(self, skin, inner_skin=-1.0):
         self._check(self.lib.eph_b200_set_skin(self.h, skin, inner_skin))
