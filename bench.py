@@ -285,14 +285,16 @@ def run_b200(a):
         if not a.no_overlap:   # ghost exchange on a third stream, behind the boundary tiles of the density pass
             cstream = torch.cuda.Stream(device=dev, priority=a.side_stream_priority)
             eng.set_comm_stream(cstream.cuda_stream)
-    exch = P.GhostExchange(plan, D, dev, comm_stream=cstream)
-    if cstream is not None:
-        eng.set_boundary_atoms(exch.send_idx)
-
     sharded = bool(D) and a.sharded_grid and P.grid_slab(gridn[2], rank, world) is not None
+    if D:
+        # the engine's own data plane: NCCL communicator (its 128-byte id travels over torch.distributed), ghost map,
+        # and from then on plain post_force / end_of_step do the exchange, the source all-reduce and the grid solve
+        P.attach_comm(eng, D, rank, world)
+        eng.set_grid_sharding(sharded)
+        eng.set_ghost_map(plan)
 
     def step_resident(k):
-        P.distributed_step(eng, exch, D, d_x, d_v, d_f, k, d_src, grid_stream=gstream, sharded_grid=sharded)
+        P.distributed_step(eng, d_x, d_v, d_f, k)
 
     def timed(fn, steps, first):
         """barrier + synchronize on both sides, device time via CUDA events, max over ranks"""
@@ -389,22 +391,14 @@ def run_b200(a):
                     eng.build_neighbors(nx, 7.0)                    # list built on the device from the uploaded positions
                 else:
                     eng.set_neighbors(h_off.numpy(), h_neigh.numpy())   # LAMMPS' list uploaded
-                if cstream is not None:
-                    eng.set_boundary_atoms(exch.send_idx)
+                if D:
+                    eng.set_ghost_map(plan)
 
             def step_e2e(k):
                 if k % REBUILD_EVERY == 0:
                     reneighbor()
-                if D:
-                    eng.post_force_begin(nx, nv, None, k)   # x, v up
-                    exch(eng)
-                    eng.post_force_end(nf)                  # f up, f down
-                    eng.end_of_step_begin(None, nv)         # v (locals) up; positions are those of post_force
-                    with torch.cuda.stream(gstream):
-                        D.all_reduce(d_src)
-                    return eng.end_of_step_end(True)        # E_local down
-                eng.post_force(nx, nv, nf, None, k)         # x, v, f up (f behind the density pass), f down
-                return eng.end_of_step(None, nv)            # v up, E_local down
+                eng.post_force(nx, nv, nf, None, k)         # x, v, f up (f behind the density pass), ghost exchange, f down
+                return eng.end_of_step(None, nv)            # v up, source all-reduce + solve, E_local down
 
             reneighbor()
             for k in range(1, min(a.warmup, 3) + 1):
@@ -426,8 +420,8 @@ def run_b200(a):
         e2e["with_uploaded_list"]["note"] = "same, but LAMMPS' list (int32 CSR) uploaded every %d steps" % REBUILD_EVERY
         eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
         eng.set_neighbors(d_off, d_neigh)
-        if cstream is not None:
-            eng.set_boundary_atoms(exch.send_idx)
+        if D:
+            eng.set_ghost_map(plan)
 
     # ---- FDM micro-benchmark: Mcell-updates/s of the stencil on a 256^3 grid with 13 sub-steps (TB_Bench fine grid) ----
     fdm = None
@@ -439,7 +433,7 @@ def run_b200(a):
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if a.weak else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid), grid_solve="z-slabs + halo planes + all-gather" if sharded else "whole grid on every rank",
-                              exchange_bytes_per_step_rank0=exch.bytes_per_step(), list_stats=eng.list_stats()),
+                              exchange_bytes_per_step_rank0=(eng.exchange_bytes if D else 0), list_stats=eng.list_stats()),
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.cpu_steps)

@@ -39,7 +39,8 @@ enum eph_b200_status {
   EPH_B200_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail)  */
   EPH_B200_ERR_NODEVICE = -3, /* no usable sm_100 device                       */
   EPH_B200_ERR_MODEL = -4,    /* friction model not available on the device   */
-  EPH_B200_ERR_STATE = -5     /* numerical guard tripped (see status word)    */
+  EPH_B200_ERR_STATE = -5,    /* numerical guard tripped (see status word)    */
+  EPH_B200_ERR_COMM = -6      /* NCCL missing or an NCCL call failed           */
 };
 
 enum eph_b200_memspace { EPH_B200_HOST = 0, EPH_B200_DEVICE = 1 };
@@ -79,6 +80,8 @@ typedef struct eph_b200_config {
 } eph_b200_config;
 
 int eph_b200_version(void);
+/* number of CUDA devices this process sees (the host classes map ranks to devices with it) */
+int eph_b200_device_count(int *out);
 int eph_b200_create(const eph_b200_config *cfg, eph_b200_handle **out);
 int eph_b200_destroy(eph_b200_handle *h);
 const char *eph_b200_last_error(const eph_b200_handle *h);
@@ -213,6 +216,34 @@ int eph_b200_grid_plan_substeps(eph_b200_handle *h, int *n_substeps);
 int eph_b200_grid_substep(eph_b200_handle *h, int z_begin, int z_end);
 int eph_b200_end_of_step_end_external(eph_b200_handle *h, double *E_local);
 int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr);
+/* ---- Multi-rank data plane inside the engine (NCCL over NVLink / NVSwitch) --------------------------------------------
+ * One rank per GPU along LAMMPS' spatial decomposition.  With a communicator attached and a ghost map registered the
+ * plain entry points do the whole multi-rank step themselves:
+ *   eph_b200_post_force    density pass -> ghost exchange -> coupling -> force pass.  The exchange replaces the
+ *                          reference's forward comms RHO and WI (fix_eph.cpp:870-871, :743-744) by ONE grouped
+ *                          ncclSend/ncclRecv of {rho, Wx, Wy, Wz} per peer; XI (:863-864) travels only when the caller
+ *                          injects Gaussians (the built-in stream is keyed on atom tags: ghosts regenerate it).
+ *   eph_b200_end_of_step   deposit -> ncclAllReduce of the source term (MPI_Allreduce, eph_fdm.h:481) -> solve on every
+ *                          rank (no MPI_Bcast, eph_fdm.h:490), or with set_grid_sharding the z-slab solve with halo
+ *                          planes by ncclSend/ncclRecv between sub-steps and one ncclAllGather.
+ *   E_local stays this rank's contribution (the fix sums it over ranks like fix_eph.cpp:402).
+ * comm_get_id: on rank 0, 128 bytes (ncclUniqueId) for the caller to broadcast (MPI_Bcast in the fix);
+ * comm_init: collective over all ranks, on the handle's device.  NCCL is bound at run time (libnccl.so.2); without it
+ * these calls fail with EPH_B200_ERR_COMM -- there is no host fall-back.
+ * set_ghost_map (host arrays; call after every set_atoms): for each peer rank the owned atoms it holds as ghosts
+ * (send_index: local indices, concatenated in peer order, in the order the peer expects them) and the ghost slots
+ * (recv_slot: nlocal + g) that peer fills, in the order it sends them.  Ghosts that are images of the rank's own atoms
+ * stay with ghost_owner >= 0 in set_atoms.  exchange_ghosts / reduce_and_solve are the two collective halves for
+ * callers that drive post_force_begin/_end and end_of_step_begin themselves. */
+#define EPH_B200_COMM_ID_BYTES 128
+int eph_b200_comm_get_id(void *id128);
+int eph_b200_comm_init(eph_b200_handle *h, const void *id128, int rank, int nranks);
+int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank, const int *send_count, const int *send_index,
+                           const int *recv_count, const int *recv_slot);
+int eph_b200_exchange_ghosts(eph_b200_handle *h);
+int eph_b200_set_grid_sharding(eph_b200_handle *h, int on);
+int eph_b200_reduce_and_solve(eph_b200_handle *h, double *E_local);
+
 /* Optional second CUDA stream for the grid.  When set, end_of_step_begin makes that stream wait for the deposit,
  * end_of_step_end enqueues the solve on it, and the engine's main stream waits for the solve only where it needs
  * T_e or dT_e again (the force pass, the next deposit, grid read-backs).  A caller that issues its all-reduce of the

@@ -62,6 +62,8 @@ World<FixT> *world_new(long long natoms, int ntypes, const double *boxlo, const 
     w->lmp.domain->boxhi[d] = boxhi[d];
   }
   w->lmp.update->dt = dt;
+  w->lmp.comm->me = shim_mpi().rank;      // several ranks: the test has plugged its transport in before (P_set_mpi)
+  w->lmp.comm->nprocs = shim_mpi().size;
   w->mass.assign(ntypes + 1, 1.0);
   for (int t = 1; t <= ntypes; ++t) w->mass[t] = mass_by_type ? mass_by_type[t - 1] : 1.0;
   w->lmp.atom->mass = w->mass.data();
@@ -116,6 +118,28 @@ int world_make_fix(World<FixT> *w, int narg, const char **arg) {
     w->nmax_fix = w->lmp.atom->nmax;
     w->fix->init();
     w->fix->init_list(0, &w->list);
+  });
+}
+
+// Several ranks: the swaps of Comm::forward_comm(Fix*) (lammps_shim.h) -- per peer (this rank included, for its own
+// periodic images) the local atoms it holds as ghosts and the contiguous ghost range it fills -- and the transport.
+template <class FixT>
+int world_set_swaps(World<FixT> *w, int nswaps, const int *peer, const int *send_count, const int *sendlist, const int *first,
+                    const int *n, void (*exchange)(int, const int *, double *const *, const int *, double *const *, const int *)) {
+  return guarded(w, [&] {
+    Comm *c = w->lmp.comm;
+    c->swaps.clear();
+    size_t o = 0;
+    for (int k = 0; k < nswaps; ++k) {
+      Comm::Swap s;
+      s.peer = peer[k];
+      s.sendlist.assign(sendlist + o, sendlist + o + send_count[k]);
+      o += send_count[k];
+      s.first = first[k];
+      s.n = n[k];
+      c->swaps.push_back(s);
+    }
+    c->exchange = exchange;
   });
 }
 
@@ -237,6 +261,19 @@ int world_permute(World<FixT> *w, const int *new_of_old) {
     return shim_driver::world_new<FixT>(natoms, ntypes, lo, hi, dt, mass);                                     \
   }                                                                                                            \
   void P##_world_free(void *w) { delete static_cast<P##_world *>(w); }                                         \
+  void P##_set_mpi(int rank, int size, void (*allreduce)(void *, int, int, int), void (*bcast)(void *, int, int),   \
+                   void (*alltoallv)(const int *, const int *, const int *, int *, const int *, const int *),  \
+                   void (*barrier)()) {                                                                        \
+    ShimMpiBackend &b = shim_mpi();                                                                            \
+    b.rank = rank; b.size = size; b.allreduce = allreduce; b.bcast = bcast; b.alltoallv_int = alltoallv;       \
+    b.barrier = barrier;                                                                                       \
+  }                                                                                                            \
+  int P##_set_swaps(void *w, int nswaps, const int *peer, const int *send_count, const int *sendlist,          \
+                    const int *first, const int *n,                                                            \
+                    void (*exchange)(int, const int *, double *const *, const int *, double *const *, const int *)) { \
+    return shim_driver::world_set_swaps(static_cast<P##_world *>(w), nswaps, peer, send_count, sendlist, first, n, \
+                                        exchange);                                                             \
+  }                                                                                                            \
   const char *P##_last_error(void *w) { return static_cast<P##_world *>(w)->err.c_str(); }                     \
   int P##_set_atoms(void *w, int nlocal, int nghost, const double *x, const double *v, const double *f,        \
                     const int *type, const int *mask, const long long *tag, const int *owner) {                \

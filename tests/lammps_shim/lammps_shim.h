@@ -155,8 +155,18 @@ class Comm {
   int ghost_velocity = 0;
   int me = 0;
   int nprocs = 1;
-  // ghost g (array index nlocal+g) is an image of local atom ghost_owner[g]
+  // one rank: ghost g (array index nlocal+g) is an image of local atom ghost_owner[g]
   std::vector<int> ghost_owner;
+  // several ranks: one swap per rank that holds atoms of this one as ghosts or owns ghosts of this one (this rank itself
+  // included, for its own periodic images).  The ghosts a rank fills are one contiguous range of the atom arrays.
+  struct Swap {
+    int peer;
+    std::vector<int> sendlist;   // local atoms the peer holds as ghosts, in the peer's ghost order
+    int first, n;                // ghost range [first, first + n) the peer fills
+  };
+  std::vector<Swap> swaps;
+  // moves the packed buffers of all swaps with other ranks at once (the test plugs torch.distributed in)
+  void (*exchange)(int nswaps, const int *peer, double *const *sbuf, const int *sn, double *const *rbuf, const int *rn) = nullptr;
   Atom *atom = nullptr;
   long long n_forward = 0;
   inline void forward_comm(Fix *fix);
@@ -298,6 +308,42 @@ class Fix : protected Pointers {
 // pack/unpack callbacks, exactly the path LAMMPS' Comm::forward_comm(Fix*) takes.
 inline void Comm::forward_comm(Fix *fix) {
   ++n_forward;
+  if (!swaps.empty()) {
+    const int width = fix->comm_forward > 0 ? fix->comm_forward : 1;
+    std::vector<std::vector<double>> sb(swaps.size()), rb(swaps.size());
+    std::vector<int> peer, sn, rn;
+    std::vector<double *> sp, rp;
+    std::vector<int> per(swaps.size(), 0);
+    for (size_t k = 0; k < swaps.size(); ++k) {
+      Swap &w = swaps[k];
+      sb[k].resize(w.sendlist.size() * width + 1);
+      const int m = w.sendlist.empty() ? 0 : fix->pack_forward_comm((int)w.sendlist.size(), w.sendlist.data(), sb[k].data(), 0, nullptr);
+      per[k] = w.sendlist.empty() ? 0 : m / (int)w.sendlist.size();
+      if (w.peer == me) continue;
+      peer.push_back(w.peer); sn.push_back(m); sp.push_back(sb[k].data());
+    }
+    // every rank packs the same state, so the doubles per atom agree between the two sides; a rank that sends nothing
+    // to anybody learns the width from whoever sends to it by receiving at full width and using what arrives
+    int wid = 0;
+    for (int p : per) wid = p > wid ? p : wid;
+    MPI_Allreduce(MPI_IN_PLACE, &wid, 1, MPI_INT, MPI_MAX, 0);
+    for (size_t k = 0; k < swaps.size(); ++k) {
+      Swap &w = swaps[k];
+      rb[k].resize((size_t)w.n * wid + 1);
+      if (w.peer == me) continue;
+      rn.push_back(w.n * wid); rp.push_back(rb[k].data());
+    }
+    if (!peer.empty()) {
+      if (!exchange) throw ShimError("Comm shim: several ranks but no transport plugged in");
+      exchange((int)peer.size(), peer.data(), sp.data(), sn.data(), rp.data(), rn.data());
+    }
+    for (size_t k = 0; k < swaps.size(); ++k) {
+      Swap &w = swaps[k];
+      if (w.n == 0) continue;
+      fix->unpack_forward_comm(w.n, w.first, w.peer == me ? sb[k].data() : rb[k].data());
+    }
+    return;
+  }
   int n = static_cast<int>(ghost_owner.size());
   if (n == 0) return;
   std::vector<double> buf(static_cast<size_t>(n) * (fix->comm_forward > 0 ? fix->comm_forward : 1));

@@ -82,7 +82,7 @@ def test_fuzz_grid_files_and_memory_kernel(seed, synth_beta_4, tmp_path):
         refs = traj.run_oracle(fx, s, xis, [58.71])
         G.attach(eng, s)
         recs = traj.run_engine(eng, s, xis, [58.71], dt, coloured=tau0 > 0)
-        G.compare(recs, refs, s["nlocal"])
+        G.compare(recs, refs, s["nlocal"], dt=dt)
         assert np.all(np.isfinite(recs[-1]["T"]))
         if tau0 > 0:
             for a, b in zip(recs, refs):

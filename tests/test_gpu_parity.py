@@ -44,13 +44,17 @@ def attach(eng, s, device=False):
         eng.set_neighbors(np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32))
 
 
-def compare(recs, refs, nl, keys=("f", "array", "T", "w", "x", "v")):
+def compare(recs, refs, nl, keys=("f", "array", "T", "w", "x", "v"), dt=1e-4):
+    e_scale = 0.0
     for k, (a, b) in enumerate(zip(recs, refs)):
         for key in keys:
             err = H.error_metrics(a[key], b[key])
             assert err < TOL, (key, k, err)
         assert H.error_metrics(a["rho"][:nl], b["rho"][:nl]) < TOL
-        assert abs(a["Ee"] - b["Ee"]) <= TOL * max(abs(b["Ee"]), 1e-300), (a["Ee"], b["Ee"])
+        # Ee accumulates -(f_EPH + f_RNG) . v dt over atoms and steps: a cancelling sum (the random force heats, the friction
+        # cools), so like the forces it is measured against the size of its terms, not against what is left of them
+        e_scale += float(np.abs(b["array"][:, 2:5] * b["v"]).sum() + np.abs(b["array"][:, 5:8] * b["v"]).sum()) * dt
+        assert abs(a["Ee"] - b["Ee"]) <= TOL * max(abs(b["Ee"]), e_scale, 1e-300), (a["Ee"], b["Ee"])
         assert abs(a["Tmean"] - b["Tmean"]) <= TOL * abs(b["Tmean"])
 
 
@@ -537,6 +541,7 @@ def test_size_independent_properties_at_scale(synth_beta_1):
     xi = rng.normal(size=(nl, 3))
     x, v = s["x"], s["v"]
     f = np.zeros((nl, 3))
+    eng.post_force(x, v, f, xi, 0)    # the step that builds the inner list runs on the fp64 records; the ones below on one kind
     eng.post_force(x, v, f, xi, 1)
     assert np.all(f == 0.0)
     fe, fr, rho = eng.probe(3), eng.probe(4), eng.probe(0)
@@ -546,7 +551,8 @@ def test_size_independent_properties_at_scale(synth_beta_1):
     assert np.max(np.abs(fr.sum(axis=0))) < 1e-9 * np.abs(fr).max() * np.sqrt(nl)
     # friction is linear in v, the random force linear in xi
     eng.post_force(x, 2.0 * v, f, -3.0 * xi, 1)
-    assert H.error_metrics(eng.probe(3), 2.0 * fe) < 1e-12 and H.error_metrics(eng.probe(4), -3.0 * fr) < 1e-12
+    # (a factor 2 commutes with the block-floating-point records; a factor -3 re-rounds 40-bit mantissas: <= 2^-39 per vector)
+    assert H.error_metrics(eng.probe(3), 2.0 * fe) < 1e-12 and H.error_metrics(eng.probe(4), -3.0 * fr) < 2e-11
     # friction dissipates: -f_EPH . v >= 0 summed over atoms; energy bookkeeping matches the deposited source
     eng.post_force(x, v, f, xi, 1)
     T0 = eng.get_grid(0)

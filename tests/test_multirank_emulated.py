@@ -1,9 +1,11 @@
 """The multi-GPU path of the product, end to end on the CPU: `world` gloo ranks, each with the host build of the engine
-(tests/emul, see test_engine_emulated.py) and its brick of the box, run eph_b200.parallel.distributed_step -- the very
-function bench.py runs over NCCL: post_force_begin, ghost payload all-to-all (GhostExchange), post_force_end, deposit,
-all-reduce of the grid source term, replicated or sharded grid solve with halo planes -- and the forces, densities,
-grid temperatures and energies must equal the single-rank oracle on the whole box at 1e-10.  On the host build device
-memory is host memory, so CPU tensors stand where device tensors stand on a B200.  Test infrastructure only."""
+(tests/emul, see test_engine_emulated.py) and its brick of the box, run what bench.py runs on B200s: plain
+eph_b200_post_force / eph_b200_end_of_step on an engine with a communicator attached (eph_b200_comm_init) and a ghost
+map registered (eph_b200_set_ghost_map).  The ENGINE issues the ghost exchange (grouped ncclSend / ncclRecv of {rho, W}),
+the all-reduce of the grid source term and, with grid sharding, the halo planes and the all-gather of the slab solve;
+on the host build a stand-in NCCL (tests/emul/fake_nccl.cpp) hands the bytes to torch.distributed over gloo.  Forces,
+densities, grid temperatures and energies must equal the single-rank oracle on the whole box at 1e-10.
+Test infrastructure only."""
 import ctypes as C
 import os
 import subprocess
@@ -25,6 +27,40 @@ EMUL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
 TOL = 1e-10
 CELLS, SEED, DT = 6, 4711, 1e-4
 
+P2P_FN = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t)
+ALLGATHER_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+def _bytes_view(ptr, n):
+    return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)))
+
+
+def gloo_transport(L):
+    """the stand-in NCCL of the host build moves its bytes through these callbacks: torch.distributed over gloo"""
+    def p2p(nops, is_send, peer, buf, nbytes):
+        ops = [dist.P2POp(dist.isend if is_send[k] else dist.irecv, _bytes_view(buf[k], nbytes[k]), peer[k]) for k in range(nops)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def allreduce(buf, count):
+        t = torch.from_numpy(np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(count,)))
+        dist.all_reduce(t)
+
+    def allgather(send, recv, nbytes):
+        world = dist.get_world_size()
+        mine = _bytes_view(send, nbytes).clone()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        out = _bytes_view(recv, nbytes * world)
+        for r, p in enumerate(parts):
+            out[r * nbytes:(r + 1) * nbytes] = p
+
+    cbs = (P2P_FN(p2p), ALLREDUCE_FN(allreduce), ALLGATHER_FN(allgather))
+    L.emul_nccl_set_transport(*cbs)
+    L.emul_nccl_calls.restype = C.c_longlong
+    return cbs   # keep alive
+
 
 def _swap_in_emulated_engine():
     L = C.CDLL(os.path.join(EMUL, "libeph_b200_emul%s.so" % os.environ.get("EPH_EMUL_SUFFIX", "")))
@@ -37,68 +73,66 @@ def _swap_in_emulated_engine():
         getattr(L, n).restype = C.c_void_p
     L.ephh_grid_tables.restype = C.c_double
     lib._lib, host._fix = L, L
-
-    def grid_tensor(self, which=0):   # a CPU view of the engine's field: device memory is host memory here
-        p = C.c_void_p()
-        self._check(self.lib.eph_b200_grid_device_ptr(self.h, which, C.byref(p)))
-        return torch.from_numpy(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(self.ncell,)))
-
-    lib.Engine.grid_tensor = grid_tensor
+    return L
 
 
-def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.0):
+def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.0, inject_xi=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        _swap_in_emulated_engine()
+        L = _swap_in_emulated_engine()
+        keep_cbs = gloo_transport(L)
         grid = P.brick_grid(world)
         s = H.make_system(CELLS, brick=(rank, grid))
         nl = s["nlocal"]
         box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
         plan = P.ExchangePlan(s, rank, world, dist)
-        exch = P.GhostExchange(plan, dist, torch.device("cpu"))
         eng = lib.Engine([0], flags=7, seed=SEED, rank=rank, nranks=world)
         eng.set_tables_from(host.BetaTables(path=beta))
         eng.set_grid(*gshape, box, 300.0, 1.0, 3.5e-6, 0.1248)
         eng.set_dt(DT)
         if tau0 > 0:
             eng.set_colour(tau0)          # fix eph/coloured/exp: the memory kernel filters each rank's own atoms
-        keep = [np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
-                np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(plan.self_owner, dtype=np.int32),
-                np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32)]
-        eng.set_atoms(nl, s["nghost"], *keep[:4])
-        eng.set_neighbors(*keep[4:])
-        src = torch.zeros(int(np.prod(gshape)), dtype=torch.float64)
-        eng.bind_grid_source(src)
+        P.attach_comm(eng, dist, rank, world)
+        eng.set_grid_sharding(sharded)
         if boundary_first:
             # the density pass sweeps the tiles other ranks wait for first (tile_mark / tile_split), and with a
             # communication stream registered the pack waits on the finished-tile counter (cuStreamWaitValue32) and
             # post_force_end on the unpack event; streams are immediate on the host build, so this checks the
             # bookkeeping of that path, not its overlap
             eng.set_comm_stream(0x10)
-            eng.set_boundary_atoms(np.ascontiguousarray(plan.flat_send_index(), dtype=np.int32))
-        x, v = torch.as_tensor(s["x"].copy()), torch.as_tensor(s["v"].copy())
-        f = torch.zeros((nl, 3), dtype=torch.float64)
+        keep = [np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
+                np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(plan.self_owner, dtype=np.int32),
+                np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32)]
+        eng.set_atoms(nl, s["nghost"], *keep[:4])
+        eng.set_neighbors(*keep[4:])
+        eng.set_ghost_map(plan)
+        x, v = s["x"].copy(), s["v"].copy()
+        f = np.zeros((nl, 3))
         out = []
-        for step in (1, 2):
-            f.zero_()
-            E = P.distributed_step(eng, exch, dist, x, v, f, step, src, want_energy=True, sharded_grid=sharded)
-            out.append(dict(f=f.numpy().copy(), rho=eng.probe(0)[:nl].copy(), T=eng.get_grid(0).copy(), E=E,
+        for step in (1, 2, 3):
+            f[:] = 0.0
+            xi = O.xi_stream(SEED + 17, step, s["tag"][:nl]) if inject_xi else None   # caller-supplied Gaussians: the XI exchange runs too
+            E = P.distributed_step(eng, x, v, f, step, xi=xi, want_energy=True)
+            out.append(dict(f=f.copy(), rho=eng.probe(0)[:nl].copy(), T=eng.get_grid(0).copy(), E=E,
                             substeps=eng.last_substeps()))
-        q.put((rank, s["tag"][:nl].copy(), out, exch.bytes_per_step()))
+        calls = [L.emul_nccl_calls(k) for k in range(4)]
+        q.put((rank, s["tag"][:nl].copy(), out, eng.exchange_bytes, calls))
+        del keep_cbs
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,gshape,sharded,boundary_first,tau0", [(2, (3, 2, 2), False, False, 0.0), (2, (3, 2, 2), False, True, 0.0),
-                                                                      (2, (8, 8, 8), True, False, 0.0), (4, (8, 8, 8), True, True, 0.0),
-                                                                      (2, (3, 2, 2), False, True, 5e-4)])
-def test_distributed_step_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first, tau0):
+@pytest.mark.parametrize("world,gshape,sharded,boundary_first,tau0,inject_xi",
+                         [(2, (3, 2, 2), False, False, 0.0, False), (2, (3, 2, 2), False, True, 0.0, True),
+                          (2, (8, 8, 8), True, False, 0.0, False), (4, (8, 8, 8), True, True, 0.0, False),
+                          (3, (6, 6, 9), True, False, 0.0, True), (2, (3, 2, 2), False, True, 5e-4, False)])
+def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first, tau0, inject_xi):
     subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first, tau0)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first, tau0, inject_xi)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
@@ -112,20 +146,23 @@ def test_distributed_step_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, w
         fx.set_colour(tau0)
     order = np.argsort(whole["tag"][:nlw])
     E_prev = 0.0
-    assert sum(len(tags) for _, tags, _, _ in res) == nlw
-    for k, step in enumerate((1, 2)):
-        xi = O.xi_stream(SEED, step, whole["tag"][:nlw])   # the ranks generate the same Gaussians from the atom tags
+    assert sum(len(r[1]) for r in res) == nlw
+    for k, step in enumerate((1, 2, 3)):
+        # the ranks generate the same Gaussians from the atom tags, or are handed them and exchange the ghosts' share
+        xi = O.xi_stream(SEED + 17 if inject_xi else SEED, step, whole["tag"][:nlw])
         fx.f[:] = 0.0
         fx.post_force(xi)
         fx.end_of_step()
         ref_f, ref_rho = fx.f[:nlw], np.array(fx.ptr(0))[:nlw]
         E = 0.0
-        for rank, tags, out, nbytes in res:
+        for rank, tags, out, nbytes, calls in res:
             idx = order[np.searchsorted(whole["tag"][:nlw][order], tags)]
             assert H.error_metrics(out[k]["f"], ref_f[idx], floor=np.abs(ref_f).max()) < TOL, (rank, step)
             assert H.error_metrics(out[k]["rho"], ref_rho[idx]) < TOL, (rank, step)
             assert H.error_metrics(out[k]["T"], fx.fdm.field(0)) < TOL, (rank, step)
             assert nbytes > 0
+            # the engine itself issued the collectives: one grouped exchange and one all-reduce per step (+ halo groups / all-gathers)
+            assert calls[0] >= 3 and calls[2] == 3 and (calls[3] == 3) == bool(sharded), calls
             if sharded:   # fine grid: the solve takes several sub-steps, so halo planes were exchanged between them
                 assert out[k]["substeps"] >= 3
             E += out[k]["E"]

@@ -21,6 +21,7 @@
 #include "eph_neigh.cuh"
 #include "eph_sweeps.cuh"
 #include "eph_legacy.cuh"
+#include "eph_nccl.h"
 
 using namespace ephb;
 
@@ -37,7 +38,7 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    size_t want = n + n / 8 + 64;
+    size_t want = n + n / 8 + 512;   // slack: the list streams of the sweeps are prefetched a few iterations past the end
     cudaError_t e = cudaMalloc(&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
@@ -131,6 +132,18 @@ struct eph_b200_handle {
   bool boundary_by_counter = false;     // this step's pack waits on the counter (one launch) instead of an event (two)
   bool split_ready = false;
   double *dT_e_ext = nullptr;   // caller-owned grid source term (multi-rank: all-reduced between the two end_of_step halves)
+
+  // multi-rank data plane inside the engine (NCCL over NVLink; eph_b200_comm_init / set_ghost_map): the ghost exchange
+  // of post_force, the all-reduce of the grid source term and the halo planes of the sharded grid solve
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  bool ghost_map_set = false;
+  std::vector<int> gm_peer, gm_send_count, gm_recv_count;   // per peer rank
+  DevBuf<int> gm_send_idx, gm_recv_slot;                    // concatenated over the peers, in peer order
+  int gm_nsend = 0, gm_nrecv = 0;
+  DevBuf<double> gm_send_buf, gm_recv_buf, gm_send_xi, gm_recv_xi;   // {rho, Wx, Wy, Wz} per atom; xi only when injected
+  bool grid_sharded = false;    // every rank advances only its z-slab of the grid (halo planes + all-gather)
+  DevBuf<double> slab_tmp;
 
   // neighbours
   DevBuf<long long> off;
@@ -373,6 +386,11 @@ bool packed_possible(const eph_b200_handle *h) {
 extern "C" {
 
 int eph_b200_version(void) { return EPH_B200_VERSION; }
+int eph_b200_device_count(int *out) {
+  if (!out) return EPH_B200_ERR_ARG;
+  *out = 0;
+  return cudaGetDeviceCount(out) == cudaSuccess ? EPH_B200_OK : EPH_B200_ERR_NODEVICE;
+}
 const char *eph_b200_create_error(void) { return g_create_error.c_str(); }
 const char *eph_b200_last_error(const eph_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 long long eph_b200_launch_count(const eph_b200_handle *h) { return h ? h->launches : 0; }
@@ -465,6 +483,9 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
   h->f_dis.release(); h->f_sto.release();
   h->recD.release(); h->recA.release(); h->recB.release(); h->var.release();
+  if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
+  h->gm_send_idx.release(); h->gm_recv_slot.release(); h->gm_send_buf.release(); h->gm_recv_buf.release();
+  h->gm_send_xi.release(); h->gm_recv_xi.release(); h->slab_tmp.release();
   h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -836,6 +857,7 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   h->atoms_set = true;
   h->peratom_valid = false;
   h->split_ready = false;   // the boundary work lists name atoms of the previous registration
+  h->ghost_map_set = false; // ... and so does the ghost map
   h->neigh_set = false;
   h->forces_valid = false;
   return EPH_B200_OK;
@@ -1068,41 +1090,41 @@ PackedArgs packed_args(const eph_b200_handle *h) {
   return q;
 }
 
-template <int LANES, bool MULTI>
+template <int LANES, bool MULTI, bool FRIC>
 int launch_density_packed(eph_b200_handle *h, const SweepArgs &a, const char *name) {
   const int threads = 256;
   KernelTimer kt(h, name ? name : "density_sweep");
-  auto k = density_packed_kernel<LANES, MULTI>;
+  auto k = density_packed_kernel<LANES, MULTI, FRIC>;
   k<<<sweep_grid(h, k, threads, 0, a.n_work, threads / LANES), threads, 0, h->stream>>>(a, packed_args(h));
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
-template <int LANES, bool MULTI>
+template <int LANES, bool MULTI, bool FRIC, bool RAND>
 int launch_force_packed(eph_b200_handle *h, const SweepArgs &a) {
   const int threads = EPH_THREADS_FORCE;
   KernelTimer kt(h, "force_sweep");
-  auto k = force_packed_kernel<LANES, MULTI>;
+  auto k = force_packed_kernel<LANES, MULTI, FRIC, RAND>;
   k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a, packed_args(h));
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
+template <int LANES, bool MULTI>
+int launch_packed_flags(eph_b200_handle *h, const SweepArgs &a, int which, const char *name) {
+  if (which == 0) return a.do_friction ? launch_density_packed<LANES, MULTI, true>(h, a, name) : launch_density_packed<LANES, MULTI, false>(h, a, name);
+  if (a.do_friction && a.do_random) return launch_force_packed<LANES, MULTI, true, true>(h, a);
+  if (a.do_friction) return launch_force_packed<LANES, MULTI, true, false>(h, a);
+  return launch_force_packed<LANES, MULTI, false, true>(h, a);
+}
 // which: 0 density, 1 force
 int launch_packed(eph_b200_handle *h, const SweepArgs &a, int which, const char *name = nullptr) {
   const bool multi = a.n_elements > 1;
-#define EPH_PACKED_CASE(L)                                                                                       \
-  case L:                                                                                                        \
-    if (which == 0) return multi ? launch_density_packed<L, true>(h, a, name) : launch_density_packed<L, false>(h, a, name); \
-    return multi ? launch_force_packed<L, true>(h, a) : launch_force_packed<L, false>(h, a);
   switch (h->lanes) {
-    EPH_PACKED_CASE(1)
-    EPH_PACKED_CASE(2)
-    EPH_PACKED_CASE(8)
-    EPH_PACKED_CASE(16)
-    default: break;
+    case 1: return multi ? launch_packed_flags<1, true>(h, a, which, name) : launch_packed_flags<1, false>(h, a, which, name);
+    case 2: return multi ? launch_packed_flags<2, true>(h, a, which, name) : launch_packed_flags<2, false>(h, a, which, name);
+    case 8: return multi ? launch_packed_flags<8, true>(h, a, which, name) : launch_packed_flags<8, false>(h, a, which, name);
+    case 16: return multi ? launch_packed_flags<16, true>(h, a, which, name) : launch_packed_flags<16, false>(h, a, which, name);
+    default: return multi ? launch_packed_flags<4, true>(h, a, which, name) : launch_packed_flags<4, false>(h, a, which, name);
   }
-  if (which == 0) return multi ? launch_density_packed<4, true>(h, a, name) : launch_density_packed<4, false>(h, a, name);
-  return multi ? launch_force_packed<4, true>(h, a) : launch_force_packed<4, false>(h, a);
-#undef EPH_PACKED_CASE
 }
 
 int launch_sweep_exact(eph_b200_handle *h, const SweepArgs &a, int which, bool build, const char *name);
@@ -1281,7 +1303,7 @@ int eph_b200_post_force_end(eph_b200_handle *h, double *f, int memspace) {
   h->pf_open = false;
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal, nt = h->nlocal + h->nghost;
-  if (nl == 0) return EPH_B200_OK;
+  if (nl == 0) { h->forces_valid = true; return EPH_B200_OK; }   // a rank without atoms still takes part in end_of_step
   if (!f) return fail(h, EPH_B200_ERR_ARG, "post_force: null f");
   int rc;
   const bool add_fric = (h->cfg.flags & EPH_B200_FRICTION) && !(h->cfg.flags & EPH_B200_NOFRICTION);
@@ -1431,6 +1453,8 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
       h->f_prefetched = true;
     }
   }
+  // several ranks with the engine's own transport: the one ghost exchange of the step happens here
+  if (h->comm && h->comm_size > 1 && (rc = eph_b200_exchange_ghosts(h))) return rc;
   return eph_b200_post_force_end(h, f, memspace);
 }
 
@@ -1583,17 +1607,17 @@ extern "C" {
 
 int eph_b200_end_of_step_begin(eph_b200_handle *h, const double *x, const double *v, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
-  if (!h->forces_valid) return fail(h, EPH_B200_ERR_ARG, "end_of_step: post_force has not run");
+  if (!h->forces_valid && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "end_of_step: post_force has not run");
   if (!h->grid_set) return fail(h, EPH_B200_ERR_ARG, "end_of_step: set_grid not called");
-  if (!v) return fail(h, EPH_B200_ERR_ARG, "end_of_step: null v");
+  if (!v && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "end_of_step: null v");
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal;
   const double *dx = nullptr, *dv = nullptr;
   int rc;
   // only the local part is read here; x == NULL: positions are those of the last post_force (Verlet does not move
   // atoms between post_force and end_of_step), so nothing is uploaded for them
-  if (x && (rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
-  if ((rc = stage_in(h, h->v, v, 3 * (size_t)nl, memspace, &dv))) return rc;
+  if (x && nl > 0 && (rc = stage_in(h, h->x, x, 3 * (size_t)nl, memspace, &dx))) return rc;
+  if (nl > 0 && (rc = stage_in(h, h->v, v, 3 * (size_t)nl, memspace, &dv))) return rc;
   join_grid_stream(h);   // the previous solve clears dT_e
   EPH_CUDA(h, cudaMemsetAsync(h->d_scal.p, 0, sizeof(double), h->stream));
   if (nl > 0) {
@@ -1695,6 +1719,9 @@ int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr) {
 int eph_b200_end_of_step(eph_b200_handle *h, const double *x, const double *v, double *E_local, int memspace) {
   int rc = eph_b200_end_of_step_begin(h, x, v, memspace);
   if (rc) return rc;
+  // several ranks with the engine's own transport: the source term is summed over ranks (eph_fdm.h:481) and every rank
+  // solves the whole grid, or its slab of it (eph_b200_set_grid_sharding)
+  if (h->comm && h->comm_size > 1) return eph_b200_reduce_and_solve(h, E_local);
   return eph_b200_end_of_step_end(h, E_local);
 }
 
@@ -1911,6 +1938,213 @@ int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, con
   EPH_LAUNCH_CHECK(h);
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));   // the caller may reuse its buffer
   return EPH_B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Multi-rank data plane inside the engine: NCCL over NVLink carries the ghost exchange of post_force
+// (reference: the forward comms RHO, WI, XI, fix_eph.cpp:743-744, :863-871), the all-reduce of the grid source term
+// (eph_fdm.h:481) and the halo planes of the sharded grid solve (which replaces rank-0 solve + MPI_Bcast, eph_fdm.h:271, :490).
+// ---------------------------------------------------------------------------
+namespace {
+
+#define EPH_NCCL(h, call)                                                                                         \
+  do {                                                                                                            \
+    const int r_ = (call);                                                                                        \
+    if (r_ != kNcclSuccess)                                                                                       \
+      return fail(h, EPH_B200_ERR_COMM, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+// rows of `width` doubles from a receive buffer into the listed slots of a [n][stride] array
+__global__ void scatter_rows_kernel(int n, const int *__restrict__ slot, double *__restrict__ dst, int width, int stride,
+                                    const double *__restrict__ buf, int nrows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const int k = t / width, c = t - k * width;
+  const int a = slot[k];
+  if (a >= 0 && a < nrows) dst[(size_t)a * stride + c] = buf[t];
+}
+
+// z-planes [z0, z1) this rank advances in a sharded solve; false if the grid does not divide
+bool grid_slab(const eph_b200_handle *h, int *z0, int *z1) {
+  if (h->comm_size < 1 || h->nz % h->comm_size) return false;
+  const int per = h->nz / h->comm_size;
+  *z0 = h->comm_rank * per;
+  *z1 = *z0 + per;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eph_b200_comm_get_id(void *id128) {
+  if (!id128) return EPH_B200_ERR_ARG;
+  NcclApi &api = nccl_api();
+  if (!api.ok) { g_create_error = "eph_b200_comm_get_id: " + api.error; return EPH_B200_ERR_COMM; }
+  NcclUniqueId id;
+  const int r = api.GetUniqueId(&id);
+  if (r != kNcclSuccess) { g_create_error = std::string("ncclGetUniqueId failed: ") + api.GetErrorString(r); return EPH_B200_ERR_COMM; }
+  std::memcpy(id128, &id, sizeof id);
+  return EPH_B200_OK;
+}
+
+int eph_b200_comm_init(eph_b200_handle *h, const void *id128, int rank, int nranks) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, EPH_B200_ERR_ARG, "comm_init: bad rank %d of %d or null id", rank, nranks);
+  NcclApi &api = nccl_api();
+  if (!api.ok) return fail(h, EPH_B200_ERR_COMM, "comm_init: %s (the multi-rank data plane needs NCCL; there is no host fall-back)", api.error.c_str());
+  cudaSetDevice(h->cfg.device);
+  if (h->comm) { api.CommDestroy(h->comm); h->comm = nullptr; }
+  NcclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  EPH_NCCL(h, api.CommInitRank(&h->comm, nranks, id, rank));
+  h->comm_rank = rank;
+  h->comm_size = nranks;
+  h->ghost_map_set = false;
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank, const int *send_count, const int *send_index,
+                           const int *recv_count, const int *recv_slot) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: call set_atoms first");
+  if (npeers < 0 || (npeers > 0 && (!peer_rank || !send_count || !recv_count))) return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: bad arguments");
+  cudaSetDevice(h->cfg.device);
+  long long ns = 0, nr = 0;
+  for (int p = 0; p < npeers; ++p) {
+    if (peer_rank[p] < 0 || peer_rank[p] >= h->comm_size || peer_rank[p] == h->comm_rank || send_count[p] < 0 || recv_count[p] < 0)
+      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: peer %d: rank %d, %d to send, %d to receive", p, peer_rank[p], send_count[p], recv_count[p]);
+    ns += send_count[p]; nr += recv_count[p];
+  }
+  if ((ns > 0 && !send_index) || (nr > 0 && !recv_slot)) return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: null index lists");
+  for (long long k = 0; k < ns; ++k)
+    if (send_index[k] < 0 || send_index[k] >= h->nlocal) return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: send index %d is not an owned atom", send_index[k]);
+  for (long long k = 0; k < nr; ++k)
+    if (recv_slot[k] < h->nlocal || recv_slot[k] >= h->nlocal + h->nghost) return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: receive slot %d is not a ghost", recv_slot[k]);
+  h->gm_peer.assign(peer_rank, peer_rank + npeers);
+  h->gm_send_count.assign(send_count, send_count + npeers);
+  h->gm_recv_count.assign(recv_count, recv_count + npeers);
+  h->gm_nsend = (int)ns; h->gm_nrecv = (int)nr;
+  EPH_CUDA(h, h->gm_send_idx.reserve(std::max<size_t>(ns, 1))); EPH_CUDA(h, h->gm_recv_slot.reserve(std::max<size_t>(nr, 1)));
+  EPH_CUDA(h, h->gm_send_buf.reserve(4 * std::max<size_t>(ns, 1))); EPH_CUDA(h, h->gm_recv_buf.reserve(4 * std::max<size_t>(nr, 1)));
+  EPH_CUDA(h, h->gm_send_xi.reserve(3 * std::max<size_t>(ns, 1))); EPH_CUDA(h, h->gm_recv_xi.reserve(3 * std::max<size_t>(nr, 1)));
+  if (ns) EPH_CUDA(h, cudaMemcpyAsync(h->gm_send_idx.p, send_index, ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (nr) EPH_CUDA(h, cudaMemcpyAsync(h->gm_recv_slot.p, recv_slot, nr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ghost_map_set = true;
+  // with a communication stream registered the density pass sweeps the tiles these atoms live in first
+  if (h->comm_stream && ns > 0) return eph_b200_set_boundary_atoms(h, (int)ns, h->gm_send_idx.p, EPH_B200_DEVICE);
+  return EPH_B200_OK;
+}
+
+// The one ghost exchange of a step: {rho, W} of the owned atoms other ranks hold as ghosts (and the injected xi, when the
+// caller supplies the Gaussians instead of the tag-keyed stream), one grouped ncclSend / ncclRecv per peer.
+int eph_b200_exchange_ghosts(eph_b200_handle *h) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->pf_open) return fail(h, EPH_B200_ERR_ARG, "exchange_ghosts: only valid between post_force_begin and post_force_end");
+  if (!h->comm) return fail(h, EPH_B200_ERR_ARG, "exchange_ghosts: eph_b200_comm_init has not been called");
+  if (!h->ghost_map_set) return fail(h, EPH_B200_ERR_ARG, "exchange_ghosts: eph_b200_set_ghost_map must follow every set_atoms");
+  cudaSetDevice(h->cfg.device);
+  NcclApi &api = nccl_api();
+  const bool with_xi = h->pf_xi != nullptr && (h->cfg.flags & EPH_B200_RANDOM);
+  cudaStream_t st = h->comm_stream ? h->comm_stream : h->stream;
+  int rc;
+  if (h->gm_nsend) {
+    if ((rc = eph_b200_pack_ghost_payload(h, h->gm_nsend, h->gm_send_idx.p, h->gm_send_buf.p))) return rc;
+    if (with_xi) {
+      pack_forward_kernel<<<blocks_for(3LL * h->gm_nsend, 256), 256, 0, st>>>(h->gm_nsend, h->gm_send_idx.p, h->xi.p, 3, 3, h->gm_send_xi.p);
+      EPH_LAUNCH_CHECK(h);
+    }
+  } else if (h->comm_stream && h->boundary_recorded) {
+    EPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_boundary, 0));
+  }
+  {
+    KernelTimer kt(h, "ghost_exchange", st);
+    EPH_NCCL(h, api.GroupStart());
+    size_t so = 0, ro = 0;
+    for (size_t p = 0; p < h->gm_peer.size(); ++p) {
+      const size_t sc = h->gm_send_count[p], rcn = h->gm_recv_count[p];
+      if (sc) {
+        EPH_NCCL(h, api.Send(h->gm_send_buf.p + 4 * so, 4 * sc, kNcclFloat64, h->gm_peer[p], h->comm, st));
+        if (with_xi) EPH_NCCL(h, api.Send(h->gm_send_xi.p + 3 * so, 3 * sc, kNcclFloat64, h->gm_peer[p], h->comm, st));
+      }
+      if (rcn) {
+        EPH_NCCL(h, api.Recv(h->gm_recv_buf.p + 4 * ro, 4 * rcn, kNcclFloat64, h->gm_peer[p], h->comm, st));
+        if (with_xi) EPH_NCCL(h, api.Recv(h->gm_recv_xi.p + 3 * ro, 3 * rcn, kNcclFloat64, h->gm_peer[p], h->comm, st));
+      }
+      so += sc; ro += rcn;
+    }
+    EPH_NCCL(h, api.GroupEnd());
+  }
+  if (h->gm_nrecv) {
+    if (with_xi) {   // the XI forward comm of the reference (fix_eph.cpp:863-864): the ghost's slot of xi
+      scatter_rows_kernel<<<blocks_for(3LL * h->gm_nrecv, 256), 256, 0, st>>>(h->gm_nrecv, h->gm_recv_slot.p, h->xi.p, 3, 3, h->gm_recv_xi.p,
+                                                                              h->nlocal + h->nghost);
+      EPH_LAUNCH_CHECK(h);
+    }
+    if ((rc = eph_b200_unpack_ghost_payload(h, h->gm_nrecv, h->gm_recv_slot.p, h->gm_recv_buf.p))) return rc;
+  } else if (h->comm_stream) {
+    EPH_CUDA(h, cudaEventRecord(h->ev_unpacked, st));
+    h->unpack_pending = true;
+  }
+  return EPH_B200_OK;
+}
+
+int eph_b200_set_grid_sharding(eph_b200_handle *h, int on) {
+  if (!h) return EPH_B200_ERR_ARG;
+  h->grid_sharded = on != 0;
+  return EPH_B200_OK;
+}
+
+// Second half of end_of_step on several ranks: ncclAllReduce of the source term (the reference's MPI_Allreduce,
+// eph_fdm.h:481), then the solve -- the whole grid on every rank, or with sharding this rank's z-slab with one plane pair
+// exchanged between sub-steps (periodic in z, written in place at their global position) and one all-gather of the
+// slabs at the end, which replaces the reference's MPI_Bcast (eph_fdm.h:490).
+int eph_b200_reduce_and_solve(eph_b200_handle *h, double *E_local) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->eos_open) return fail(h, EPH_B200_ERR_ARG, "reduce_and_solve without end_of_step_begin");
+  if (!h->comm) return fail(h, EPH_B200_ERR_ARG, "reduce_and_solve: eph_b200_comm_init has not been called");
+  cudaSetDevice(h->cfg.device);
+  NcclApi &api = nccl_api();
+  cudaStream_t st = h->grid_stream ? h->grid_stream : h->stream;
+  double *src = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p;
+  {
+    KernelTimer kt(h, "source_allreduce", st);
+    EPH_NCCL(h, api.AllReduce(src, src, (size_t)h->ncell, kNcclFloat64, kNcclSum, h->comm, st));
+  }
+  int z0 = 0, z1 = 0;
+  if (!(h->grid_sharded && (h->cfg.flags & EPH_B200_FDM) && grid_slab(h, &z0, &z1))) return eph_b200_end_of_step_end(h, E_local);
+  int rc = grid_plan(h, st);
+  if (rc) return rc;
+  const int n = h->last_substeps;
+  const size_t plane = (size_t)h->nx * h->ny;
+  const int prev = (h->comm_rank + h->comm_size - 1) % h->comm_size, next = (h->comm_rank + 1) % h->comm_size;
+  for (int sstep = 0; sstep < n; ++sstep) {
+    if ((rc = grid_substep(h, st, z0, z1, sstep + 1 == n))) return rc;
+    if (sstep + 1 == n) break;
+    // halo planes for the next sub-step.  Posting order matters when prev == next (two ranks): sends go "bottom plane to
+    // prev, top plane to next", receives "from next into the plane above the slab, from prev into the plane below"
+    double *T = h->T[h->cur].p;
+    const int zlo = (z0 + h->nz - 1) % h->nz, zhi = z1 % h->nz;
+    KernelTimer kt(h, "grid_halo", st);
+    EPH_NCCL(h, api.GroupStart());
+    EPH_NCCL(h, api.Send(T + (size_t)z0 * plane, plane, kNcclFloat64, prev, h->comm, st));
+    EPH_NCCL(h, api.Send(T + (size_t)(z1 - 1) * plane, plane, kNcclFloat64, next, h->comm, st));
+    EPH_NCCL(h, api.Recv(T + (size_t)zhi * plane, plane, kNcclFloat64, next, h->comm, st));
+    EPH_NCCL(h, api.Recv(T + (size_t)zlo * plane, plane, kNcclFloat64, prev, h->comm, st));
+    EPH_NCCL(h, api.GroupEnd());
+  }
+  if (n > 0) {
+    // the kernel cleared the source term on this rank's slab only
+    if (z0 > 0) EPH_CUDA(h, cudaMemsetAsync(src, 0, (size_t)z0 * plane * sizeof(double), st));
+    if (z1 < h->nz) EPH_CUDA(h, cudaMemsetAsync(src + (size_t)z1 * plane, 0, (size_t)(h->nz - z1) * plane * sizeof(double), st));
+    double *T = h->T[h->cur].p;
+    KernelTimer kt(h, "grid_allgather", st);
+    EPH_NCCL(h, api.AllGather(T + (size_t)z0 * plane, T, (size_t)(z1 - z0) * plane, kNcclFloat64, h->comm, st));   // in place
+  }
+  return end_of_step_finish(h, E_local, false);
 }
 
 }  // extern "C"

@@ -17,7 +17,8 @@
 //   A[a] = {position + valid | u}, B[a] = {z}  force pass: 2 sectors per slot (was 3), 1 without the random force
 //
 // Both decodes avoid integer <-> fp64 conversions: a 42-bit integer t is read as the double 1.5 * 2^52 + t by OR-ing
-// it into a constant bit pattern, and one DADD removes the constant.  The error these records add to rho_i, w_i,
+// it into a constant bit pattern, and one DADD removes the constant.  Both records keep the low 32 bits of their three
+// numbers in words 0, 2, 3 and all high bits in word 1, so a field costs one shift to reach.  The error these records add to rho_i, w_i,
 // f_EPH and f_RNG is bounded in DESIGN.md section 4 (<= ~1e-11 of the largest value, against the 1e-10 bar) and
 // measured in every parity test; EPH_B200_RECORDS=exact (or eph_b200_set_precision) selects the fp64 records instead.
 //
@@ -32,66 +33,70 @@ namespace ephb {
 
 constexpr unsigned long long kQMask = (1ull << 42) - 1ull;
 constexpr unsigned long long kQHalf = 1ull << 41;
-constexpr double kQScale = 4398046511104.0;                 // 2^42
-constexpr unsigned long long kMagic = 0x4338000000000000ull;   // bit pattern of 1.5 * 2^52
+constexpr double kQScale = 4398046511104.0;   // 2^42
+constexpr unsigned kMagicHi = 0x43380000u;     // high word of 1.5 * 2^52: as_double(kMagicHi : t) = 1.5 * 2^52 + t for t < 2^51
 
-struct __align__(16) Packed16 { unsigned long long w0, w1; };
-struct __align__(16) Block16 { unsigned w0, w1, w2, w3; };
-struct __align__(32) Packed32 { Packed16 p; Block16 b; };
+// One 16-byte record, used for positions and for vectors alike:
+//   position  w0 = x[31:0], w2 = y[31:0], w3 = z[31:0], w1 = x[41:32] | y[41:32] << 10 | z[41:32] << 20 | flags << 30
+//   vector    w0 = m0[31:0], w2 = m1[31:0], w3 = m2[31:0], w1 = m0[39:32] | m1[39:32] << 8 | m2[39:32] << 16 | (E + 127) << 24
+//             (m_k = rint(a_k 2^(39 - E)) + 2^39, E the exponent with max |a_k| < 2^E)
+struct __align__(16) Words16 { unsigned w0, w1, w2, w3; };
+struct __align__(32) Packed32 { Words16 p, b; };
+typedef Words16 Block16;
 
-// ---- position: x | y | z as 42-bit fractions of the period ----
-//   w0 = x (bits 0..41) | y[41:20] (bits 42..63)
-//   w1 = flags (bits 0..1) | y[19:0] (bits 2..21) | z (bits 22..63)
+// ---- position ----
 __device__ __forceinline__ unsigned long long quantise_coord(double x, double inv_period) {
   double t = x * inv_period;
   t -= floor(t);   // [0, 1)
   return static_cast<unsigned long long>(t * kQScale + 0.5) & kQMask;   // a fraction that rounds up to 1 wraps to 0
 }
-__device__ __forceinline__ Packed16 pack_position(double x, double y, double z, double inv_period, unsigned flags) {
+__device__ __forceinline__ Words16 pack_position(double x, double y, double z, double inv_period, unsigned flags) {
   const unsigned long long qx = quantise_coord(x, inv_period), qy = quantise_coord(y, inv_period), qz = quantise_coord(z, inv_period);
-  Packed16 p;
-  p.w0 = qx | ((qy >> 20) << 42);
-  p.w1 = (unsigned long long)(flags & 3u) | ((qy & 0xFFFFFull) << 2) | (qz << 22);
+  Words16 p;
+  p.w0 = static_cast<unsigned>(qx); p.w2 = static_cast<unsigned>(qy); p.w3 = static_cast<unsigned>(qz);
+  p.w1 = static_cast<unsigned>(qx >> 32) | (static_cast<unsigned>(qy >> 32) << 10) | (static_cast<unsigned>(qz >> 32) << 20) | ((flags & 3u) << 30);
   return p;
 }
-__device__ __forceinline__ unsigned packed_flags(const Packed16 &p) { return static_cast<unsigned>(p.w1) & 3u; }
+__device__ __forceinline__ unsigned packed_flags(const Words16 &p) { return p.w1 >> 30; }
 
-// The centre atom of a sweep: its coordinates shifted by half a period, so that (q_j - o) mod 2^42 is the unsigned
-// displacement + 2^41 and the signed displacement needs no sign extension.
+// The centre atom of a sweep: its coordinates shifted by half a period, so that (q_j - o) mod 2^42 is the displacement
+// + 2^41, an unsigned number that needs no sign extension.
 struct Centre {
-  unsigned long long ox, oy, ozs;   // ozs: o_z << 22 (z sits in the top 42 bits of w1)
+  unsigned long long ox, oy, oz;
 };
-__device__ __forceinline__ Centre make_centre(const Packed16 &p) {
-  const unsigned long long qx = p.w0 & kQMask;
-  const unsigned long long qy = ((p.w0 >> 42) << 20) | ((p.w1 >> 2) & 0xFFFFFull);
-  const unsigned long long qz = p.w1 >> 22;
+__device__ __forceinline__ Centre make_centre(const Words16 &p) {
+  const unsigned long long qx = p.w0 | (static_cast<unsigned long long>(p.w1 & 0x3FFu) << 32);
+  const unsigned long long qy = p.w2 | (static_cast<unsigned long long>((p.w1 >> 10) & 0x3FFu) << 32);
+  const unsigned long long qz = p.w3 | (static_cast<unsigned long long>((p.w1 >> 20) & 0x3FFu) << 32);
   Centre c;
   c.ox = (qx - kQHalf) & kQMask;
   c.oy = (qy - kQHalf) & kQMask;
-  c.ozs = ((qz - kQHalf) & kQMask) << 22;
+  c.oz = (qz - kQHalf) & kQMask;
   return c;
 }
+// one coordinate: (hi : lo) - o, reduced modulo 2^42, read as a double, minus 2^41.  Bits of `hi` above the field do not
+// matter: borrows travel upwards and the mask removes what is left of them.
+__device__ __forceinline__ double coord_delta(unsigned lo, unsigned hi, unsigned long long o) {
+  const unsigned long long t = ((static_cast<unsigned long long>(hi) << 32) | lo) - o;
+  const unsigned th = (static_cast<unsigned>(t >> 32) & 0x3FFu) | kMagicHi;
+  return __hiloint2double(static_cast<int>(th), static_cast<int>(static_cast<unsigned>(t))) -
+         __hiloint2double(static_cast<int>(kMagicHi | 0x200u), 0);   // 1.5 * 2^52 + 2^41
+}
 // displacement j - i in quanta, exact, in [-2^41, 2^41)
-__device__ __forceinline__ void displacement(const Centre &c, const Packed16 &pj, double &dx, double &dy, double &dz) {
-  const double half = __longlong_as_double(static_cast<long long>(kMagic | kQHalf));
-  const unsigned long long tx = (pj.w0 - c.ox) & kQMask;
-  const unsigned long long qy = ((pj.w0 >> 42) << 20) | ((pj.w1 >> 2) & 0xFFFFFull);
-  const unsigned long long ty = (qy - c.oy) & kQMask;
-  const unsigned long long tz = (pj.w1 - c.ozs) >> 22;   // the low 22 bits of ozs are zero: no borrow out of the flag / y bits
-  dx = __longlong_as_double(static_cast<long long>(kMagic | tx)) - half;
-  dy = __longlong_as_double(static_cast<long long>(kMagic | ty)) - half;
-  dz = __longlong_as_double(static_cast<long long>(kMagic | tz)) - half;
+__device__ __forceinline__ void displacement(const Centre &c, const Words16 &pj, double &dx, double &dy, double &dz) {
+  dx = coord_delta(pj.w0, pj.w1, c.ox);
+  dy = coord_delta(pj.w2, pj.w1 >> 10, c.oy);
+  dz = coord_delta(pj.w3, pj.w1 >> 20, c.oz);
 }
 
-// ---- 3-vector: mantissas m_k = rint(a_k 2^(39 - E)) stored biased by 2^39, E the exponent with max |a_k| < 2^E ----
-//   w0, w1, w2 = low 32 bits of the three biased mantissas; w3 = their high bytes (bytes 0..2) | (E + 127) << 24
-__device__ __forceinline__ Block16 pack_vector(double a, double b, double c, unsigned *status) {
-  Block16 r;
-  r.w0 = r.w1 = r.w2 = 0u;
-  r.w3 = 0x00808080u;   // zero vector: mantissas 0 (biased 2^39), smallest exponent
+// ---- 3-vector ----
+__device__ __forceinline__ Words16 pack_vector(double a, double b, double c, unsigned *status) {
+  Words16 r;
+  r.w0 = r.w2 = r.w3 = 0u;
+  r.w1 = 0x00808080u;   // zero vector: mantissas 0 (biased 2^39), smallest exponent
   const double m = fmax(fabs(a), fmax(fabs(b), fabs(c)));
   const unsigned long long mb = static_cast<unsigned long long>(__double_as_longlong(m));
-  int ef = static_cast<int>((mb >> 52) & 0x7FFull);
+  const int ef = static_cast<int>((mb >> 52) & 0x7FFull);
   if (ef == 0x7FF || a != a || b != b || c != c) {   // non-finite input: flagged, encoded as zero
     if (status) atomicOr(status, 4u);
     return r;
@@ -109,20 +114,28 @@ __device__ __forceinline__ Block16 pack_vector(double a, double b, double c, uns
     const long long ia = static_cast<long long>(fmin(fmax(ma, -lim), lim)) + (1ll << 39);
     const long long ib = static_cast<long long>(fmin(fmax(mbv, -lim), lim)) + (1ll << 39);
     const long long ic = static_cast<long long>(fmin(fmax(mc, -lim), lim)) + (1ll << 39);
-    r.w0 = static_cast<unsigned>(ia); r.w1 = static_cast<unsigned>(ib); r.w2 = static_cast<unsigned>(ic);
-    r.w3 = static_cast<unsigned>((ia >> 32) & 0xFF) | (static_cast<unsigned>((ib >> 32) & 0xFF) << 8) |
+    r.w0 = static_cast<unsigned>(ia); r.w2 = static_cast<unsigned>(ib); r.w3 = static_cast<unsigned>(ic);
+    r.w1 = static_cast<unsigned>((ia >> 32) & 0xFF) | (static_cast<unsigned>((ib >> 32) & 0xFF) << 8) |
            (static_cast<unsigned>((ic >> 32) & 0xFF) << 16) | (static_cast<unsigned>(E + 127) << 24);
     break;
   }
   return r;
 }
-__device__ __forceinline__ void unpack_vector(const Block16 &r, double &a, double &b, double &c) {
+// byte k of `bytes` into the low byte of `base` (whose own low byte is zero): one PRMT on the device
+__device__ __forceinline__ unsigned splice_byte(unsigned bytes, unsigned base, int k) {
+#ifdef EPHA_HOST_EMULATION
+  return base | ((bytes >> (8 * k)) & 0xFFu);
+#else
+  return __byte_perm(bytes, base, 0x7650u + static_cast<unsigned>(k));
+#endif
+}
+__device__ __forceinline__ void unpack_vector(const Words16 &r, double &a, double &b, double &c) {
   // exponent field E + 13 + 1023 = (E + 127) + 909, mantissa bit 51 set: the double 2^(E+13) (1.5 + m_biased / 2^52)
-  const unsigned base_hi = ((r.w3 >> 4) & 0x0FF00000u) + ((909u << 20) | 0x00080000u);
+  const unsigned base_hi = ((r.w1 >> 4) & 0x0FF00000u) + ((909u << 20) | 0x00080000u);
   const double centre = __hiloint2double(static_cast<int>(base_hi | 0x80u), 0);
-  a = __hiloint2double(static_cast<int>(base_hi | (r.w3 & 0xFFu)), static_cast<int>(r.w0)) - centre;
-  b = __hiloint2double(static_cast<int>(base_hi | ((r.w3 >> 8) & 0xFFu)), static_cast<int>(r.w1)) - centre;
-  c = __hiloint2double(static_cast<int>(base_hi | ((r.w3 >> 16) & 0xFFu)), static_cast<int>(r.w2)) - centre;
+  a = __hiloint2double(static_cast<int>(splice_byte(r.w1, base_hi, 0)), static_cast<int>(r.w0)) - centre;
+  b = __hiloint2double(static_cast<int>(splice_byte(r.w1, base_hi, 1)), static_cast<int>(r.w2)) - centre;
+  c = __hiloint2double(static_cast<int>(splice_byte(r.w1, base_hi, 2)), static_cast<int>(r.w3)) - centre;
 }
 
 // ---- record loads through the read-only path ----
@@ -130,37 +143,47 @@ __device__ __forceinline__ Packed32 ld_packed32(const Packed32 *p) {
 #ifdef EPHA_HOST_EMULATION
   return *p;
 #else
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
   Packed32 r;
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(r.p.w0), "=l"(r.p.w1), "=l"(*reinterpret_cast<unsigned long long *>(&r.b.w0)),
-                 "=l"(*reinterpret_cast<unsigned long long *>(&r.b.w2))
-               : "l"(p));
+  r.p.w0 = static_cast<unsigned>(a); r.p.w1 = static_cast<unsigned>(a >> 32); r.p.w2 = static_cast<unsigned>(b); r.p.w3 = static_cast<unsigned>(b >> 32);
+  r.b.w0 = static_cast<unsigned>(c); r.b.w1 = static_cast<unsigned>(c >> 32); r.b.w2 = static_cast<unsigned>(d); r.b.w3 = static_cast<unsigned>(d >> 32);
   return r;
 #endif
 }
-__device__ __forceinline__ Block16 ld_block16(const Block16 *p) {
+__device__ __forceinline__ Words16 ld_block16(const Words16 *p) {
 #ifdef EPHA_HOST_EMULATION
   return *p;
 #else
-  Block16 r;
+  Words16 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w0), "=r"(r.w1), "=r"(r.w2), "=r"(r.w3) : "l"(p));
   return r;
 #endif
 }
 
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
 struct PackedArgs {
   const Packed32 *__restrict__ D;   // [ntotal] {position (flags: element index) | v}
   const Packed32 *__restrict__ A;   // [ntotal] {position (flags: bit0 rho > 0, bit1 in group) | u}
-  const Block16 *__restrict__ B;    // [ntotal] z
+  const Words16 *__restrict__ B;    // [ntotal] z
   const double4 *__restrict__ pos4; // [ntotal] fp64 positions + bits of pack_atoms (group bit of the centre atom)
   const double *__restrict__ var;   // [nlocal] eta_factor sqrt(T_e(cell)) of prep_coupling
   double quantum_sq;                // (P / 2^42)^2: squared length of one position quantum
 };
 
-// Density pass on packed records.  Walks the inner list only; when the device-side guard has invalidated it the
-// launch returns at once and the fp64 kernel that follows does the step on LAMMPS' list.
-// Two list slots per lane are in flight: both records are requested before either is used.
-template <int LANES, bool MULTI>
+// The packed sweeps walk the tiles of the inner list with ONE trip count per warp: the step that builds the list pads
+// every atom's slots up to the longest list of its tile (rounded up to two iterations) with the atom's own index and a
+// zero pair weight, so index and weight streams are prefetched without bounds tests and the tail needs no predicates.
+//
+// Density pass on packed records.  When the device-side guard has invalidated the inner list the launch returns at once
+// and the fp64 kernel that follows does the step on LAMMPS' list.  Two list slots per lane are in flight: both records
+// are requested before either is used.
+template <int LANES, bool MULTI, bool FRIC>
 __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(SweepArgs a, PackedArgs q) {
   if (*a.inner_invalid != 0u) return;
   const RhoTable<0> tab{a.rho_tab4, nullptr, nullptr};
@@ -169,71 +192,70 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
   const unsigned gmask = group_mask<LANES>(lane);
   const int groups_per_block = blockDim.x / LANES;
   const int group_in_block = threadIdx.x / LANES;
+  constexpr int TILE = 32 / LANES;
+  const int n_work_pad = (a.n_work + TILE - 1) / TILE * TILE;   // whole warps: the trip count is a warp-wide maximum
 
-  for (int w = blockIdx.x * groups_per_block + group_in_block; w < a.n_work; w += gridDim.x * groups_per_block) {
-    const int i = a.work ? a.work[w / (32 / LANES)] * (32 / LANES) + (w & (32 / LANES - 1)) : w;
-    const bool real = i < a.nlocal;
+  for (int w = blockIdx.x * groups_per_block + group_in_block; w < n_work_pad; w += gridDim.x * groups_per_block) {
+    const int i = a.work ? a.work[w / TILE] * TILE + (w & (TILE - 1)) : w;
+    const bool real = w < a.n_work && i < a.nlocal;
     double rho = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
     bool active = false;
     Packed32 ri;
+    ri.p = Words16{0u, 0u, 0u, 0u}; ri.b = ri.p;
     int nn = 0;
-    long long first = 0;
     if (real) {
       ri = ld_packed32(q.D + i);
       active = (double_to_bits(q.pos4[i].w) & kBitGroup) != 0u;   // atoms outside the group: rho = 0, w = 0 (fix_eph.cpp:442-445, :704)
-      nn = a.icount[i];
-      first = a.tile_off[i / (32 / LANES)] + lane;
+      nn = active ? a.icount[i] : 0;
     }
-    if (active) {
-      const Centre c = make_centre(ri.p);
-      const int off_i = MULTI ? (int)packed_flags(ri.p) * a.n_rho : 0;
-      double vix = 0.0, viy = 0.0, viz = 0.0;
-      if (a.do_friction) unpack_vector(ri.b, vix, viy, viz);
-      const int *__restrict__ lp = a.ineigh + first;
-      double *__restrict__ gp = a.gpair + first;
-      double *__restrict__ gip = MULTI ? a.gpair_i + first : nullptr;
-      // slots k (this lane) and k + LANES; the tile holds them 32 entries apart
-      int ja = sub < nn ? ld_stream(lp) : i;
-      int jb = sub + LANES < nn ? ld_stream(lp + 32) : i;
-      for (int k = sub, slot = 0; k < nn; k += 2 * LANES, slot += 64) {
-        const bool have_b = k + LANES < nn;
-        const Packed32 ra = ld_packed32(q.D + (ja & kNeighMask));
-        const Packed32 rb = ld_packed32(q.D + (jb & kNeighMask));
-        if (k + 2 * LANES < nn) ja = ld_stream(lp + slot + 64);
-        if (k + 3 * LANES < nn) jb = ld_stream(lp + slot + 96);
+    const int niter = (warp_max_int(nn) + 2 * LANES - 1) / (2 * LANES);   // double iterations of the whole warp
+    const long long first = a.tile_off[(a.work ? i : w) / TILE] + lane;
+    const Centre c = make_centre(ri.p);
+    const int off_i = MULTI ? (int)packed_flags(ri.p) * a.n_rho : 0;
+    double vix = 0.0, viy = 0.0, viz = 0.0;
+    if (FRIC) unpack_vector(ri.b, vix, viy, viz);
+    const int *__restrict__ lp = a.ineigh + first;
+    double *__restrict__ gp = a.gpair + first;
+    double *__restrict__ gip = MULTI ? a.gpair_i + first : nullptr;
+    // slots k (this lane) and k + LANES; the tile holds them 32 entries apart
+    unsigned ja = (unsigned)ld_stream(lp), jb = (unsigned)ld_stream(lp + 32);
+    for (int m = 0, k = sub; m < niter; ++m, k += 2 * LANES) {
+      const Packed32 ra = ld_packed32(q.D + ja);
+      const Packed32 rb = ld_packed32(q.D + jb);
+      ja = (unsigned)ld_stream(lp + 64 * (m + 1));
+      jb = (unsigned)ld_stream(lp + 64 * (m + 1) + 32);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const Packed32 &rj = h ? rb : ra;
-          if (h && !have_b) break;
-          double dx, dy, dz;
-          displacement(c, rj.p, dx, dy, dz);
-          const double r2 = (dx * dx + dy * dy + dz * dz) * q.quantum_sq;
-          double g = 0.0, gi = 0.0;
-          if (r2 < a.r_cutoff_sq) {   // strict '<' as in fix_eph.cpp:457, :724
-            const int off_j = MULTI ? (int)packed_flags(rj.p) * a.n_rho : 0;
-            const double rho_j = tab.eval(off_j, a.inv_dr_sq, r2);
-            const double rinv = fast_rcp(r2);
-            g = rho_j * rinv;
-            rho += rho_j;
-            if (MULTI) gi = (off_j == off_i) ? g : tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
-            if (a.do_friction) {   // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
-              double vjx, vjy, vjz;
-              unpack_vector(rj.b, vjx, vjy, vjz);
-              const double d = g * (dx * (vix - vjx) + dy * (viy - vjy) + dz * (viz - vjz));
-              wx += d * dx; wy += d * dy; wz += d * dz;
-            }
+      for (int h = 0; h < 2; ++h) {
+        const Packed32 &rj = h ? rb : ra;
+        if (k + h * LANES >= nn) break;
+        double dx, dy, dz;
+        displacement(c, rj.p, dx, dy, dz);
+        const double r2 = (dx * dx + dy * dy + dz * dz) * q.quantum_sq;
+        double g = 0.0, gi = 0.0;
+        if (r2 < a.r_cutoff_sq) {   // strict '<' as in fix_eph.cpp:457, :724
+          const int off_j = MULTI ? (int)packed_flags(rj.p) * a.n_rho : 0;
+          const double rho_j = tab.eval(off_j, a.inv_dr_sq, r2);
+          const double rinv = fast_rcp(r2);
+          g = rho_j * rinv;
+          rho += rho_j;
+          if (MULTI) gi = (off_j == off_i) ? g : tab.eval(off_i, a.inv_dr_sq, r2) * rinv;
+          if (FRIC) {   // fix_eph.cpp:726-738 without the per-atom prefactor alpha_i/rho_i; no test on rho_j
+            double vjx, vjy, vjz;
+            unpack_vector(rj.b, vjx, vjy, vjz);
+            const double d = g * (dx * (vix - vjx) + dy * (viy - vjy) + dz * (viz - vjz));
+            wx += d * dx; wy += d * dy; wz += d * dz;
           }
-          st_stream(gp + slot + 32 * h, g);
-          if (MULTI) st_stream(gip + slot + 32 * h, gi);
         }
+        st_stream(gp + 64 * m + 32 * h, g);
+        if (MULTI) st_stream(gip + 64 * m + 32 * h, gi);
       }
-      rho = group_sum<LANES>(rho, gmask);
-      if (a.do_friction) {
-        // W accumulated with displacements in quanta: two factors of the quantum bring it to A^2
-        wx = group_sum<LANES>(wx, gmask) * q.quantum_sq;
-        wy = group_sum<LANES>(wy, gmask) * q.quantum_sq;
-        wz = group_sum<LANES>(wz, gmask) * q.quantum_sq;
-      }
+    }
+    rho = group_sum<LANES>(rho, gmask);
+    if (FRIC) {
+      // W accumulated with displacements in quanta: two factors of the quantum bring it to A^2
+      wx = group_sum<LANES>(wx, gmask) * q.quantum_sq;
+      wy = group_sum<LANES>(wy, gmask) * q.quantum_sq;
+      wz = group_sum<LANES>(wz, gmask) * q.quantum_sq;
     }
     if (real && sub == 0) {
       a.rho[i] = rho;
@@ -251,88 +273,110 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
 
 // Force pass on packed records (inner list; the caller launches it only when this step's pair weights are stored in
 // the inner list's tiles -- walk_mode 2, or 1 with the guard intact, which is re-checked here).
-template <int LANES, bool MULTI>
-__global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE) force_packed_kernel(SweepArgs a, PackedArgs q) {
+#ifndef EPH_MINB_FORCE_PACKED
+#define EPH_MINB_FORCE_PACKED 6
+#endif
+
+template <int LANES, bool MULTI, bool FRIC, bool RAND>
+__global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE_PACKED) force_packed_kernel(SweepArgs a, PackedArgs q) {
   if (a.walk_mode == 1 && *a.inner_invalid != 0u) return;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES - 1);
   const unsigned gmask = group_mask<LANES>(lane);
   const int groups_per_block = blockDim.x / LANES;
   const int group_in_block = threadIdx.x / LANES;
+  constexpr int TILE = 32 / LANES;
+  const int i_end_pad = a.i_begin + (a.i_end - a.i_begin + TILE - 1) / TILE * TILE;   // i_begin is a multiple of 32
 
-  for (int i = a.i_begin + blockIdx.x * groups_per_block + group_in_block; i < a.i_end; i += gridDim.x * groups_per_block) {
-    const Packed32 ri = ld_packed32(q.A + i);
-    const int nn = a.icount[i];
-    const long long first = a.tile_off[i / (32 / LANES)] + lane;
+  for (int i = a.i_begin + blockIdx.x * groups_per_block + group_in_block; i < i_end_pad; i += gridDim.x * groups_per_block) {
+    const bool real = i < a.i_end;
+    Packed32 ri;
+    ri.p = Words16{0u, 0u, 0u, 0u}; ri.b = ri.p;
+    int nn = 0;
+    if (real) ri = ld_packed32(q.A + i);
+    const bool active = real && packed_flags(ri.p) == 3u;   // in the group and rho_i > 0 (fix_eph.cpp:749-754, :793-798)
+    if (active) nn = a.icount[i];
+    const int niter = (warp_max_int(nn) + LANES - 1) / LANES;
+    const long long first = a.tile_off[i / TILE] + lane;
     double fx = 0, fy = 0, fz = 0, rx = 0, ry = 0, rz = 0;
-    const bool active = packed_flags(ri.p) == 3u;   // in the group and rho_i > 0 (fix_eph.cpp:749-754, :793-798)
-    if (active) {
-      const Centre c = make_centre(ri.p);
-      double uix = 0, uiy = 0, uiz = 0, zix = 0, ziy = 0, ziz = 0;
-      if (a.do_friction) unpack_vector(ri.b, uix, uiy, uiz);
-      if (a.do_random) unpack_vector(ld_block16(q.B + i), zix, ziy, ziz);
-      const int *__restrict__ lp = a.ineigh + first;
-      const double *__restrict__ gp = a.gpair + first;
-      const double *__restrict__ gip = MULTI ? a.gpair_i + first : nullptr;
-      int jn = 0;
-      double gjn = 0.0, gin = 0.0;
-      if (sub < nn) {
-        jn = ld_stream(lp);
-        gjn = ld_stream(gp);
-        if (MULTI) gin = ld_stream(gip);
+    const Centre c = make_centre(ri.p);
+    double uix = 0, uiy = 0, uiz = 0, zix = 0, ziy = 0, ziz = 0;
+    if (FRIC) unpack_vector(ri.b, uix, uiy, uiz);
+    if (RAND && active) unpack_vector(ld_block16(q.B + i), zix, ziy, ziz);
+    const int *__restrict__ lp = a.ineigh + first;
+    const double *__restrict__ gp = a.gpair + first;
+    const double *__restrict__ gip = MULTI ? a.gpair_i + first : nullptr;
+    // One list slot: both force terms of the pair from its records (nothing happens behind the list, beyond the cut-off --
+    // fix_eph.cpp:768, :811 -- or for a neighbour with rho_j <= 0).
+    auto pair_terms = [&](int k, double gj, double gi, const Packed32 &rj, const Words16 &bj) {
+      if (k >= nn || (gj == 0.0 && gi == 0.0) || !(packed_flags(rj.p) & 1u)) return;
+      double dx, dy, dz;
+      displacement(c, rj.p, dx, dy, dz);
+      if (FRIC) {
+        double ux, uy, uz;
+        unpack_vector(rj.b, ux, uy, uz);
+        const double di = dx * uix + dy * uiy + dz * uiz;
+        const double dj = dx * ux + dy * uy + dz * uz;
+        const double g = gj * di - gi * dj;
+        fx -= g * dx; fy -= g * dy; fz -= g * dz;   // friction is negative, fix_eph.cpp:781-784
       }
-#pragma unroll 1
-      for (int k = sub, slot = 0; k < nn; k += LANES, slot += 32) {
-        const int j = jn & kNeighMask;
-        const double gj = gjn;
-        const double gi = MULTI ? gin : gjn;
-        if (k + LANES < nn) {
-          jn = ld_stream(lp + slot + 32);
-          gjn = ld_stream(gp + slot + 32);
-          if (MULTI) gin = ld_stream(gip + slot + 32);
-        }
-        if (gj == 0.0 && gi == 0.0) continue;   // beyond the cut-off (fix_eph.cpp:768, :811) or a vanishing pair weight
-        const Packed32 rj = ld_packed32(q.A + j);
-        Block16 bj;
-        if (a.do_random) bj = ld_block16(q.B + j);
-        if (!(packed_flags(rj.p) & 1u)) continue;   // rho_j > 0 required, fix_eph.cpp:768, :811
-        double dx, dy, dz;
-        displacement(c, rj.p, dx, dy, dz);
-        if (a.do_friction) {
-          double ux, uy, uz;
-          unpack_vector(rj.b, ux, uy, uz);
-          const double di = dx * uix + dy * uiy + dz * uiz;
-          const double dj = dx * ux + dy * uy + dz * uz;
-          const double g = gj * di - gi * dj;
-          fx -= g * dx; fy -= g * dy; fz -= g * dz;   // friction is negative, fix_eph.cpp:781-784
-        }
-        if (a.do_random) {
-          double zx, zy, zz;
-          unpack_vector(bj, zx, zy, zz);
-          const double di = dx * zix + dy * ziy + dz * ziz;
-          const double dj = dx * zx + dy * zy + dz * zz;
-          const double g = gj * di - gi * dj;
-          rx += g * dx; ry += g * dy; rz += g * dz;   // fix_eph.cpp:823-826
-        }
+      if (RAND) {
+        double zx, zy, zz;
+        unpack_vector(bj, zx, zy, zz);
+        const double di = dx * zix + dy * ziy + dz * ziz;
+        const double dj = dx * zx + dy * zy + dz * zz;
+        const double g = gj * di - gi * dj;
+        rx += g * dx; ry += g * dy; rz += g * dz;   // fix_eph.cpp:823-826
       }
-      fx = group_sum<LANES>(fx, gmask); fy = group_sum<LANES>(fy, gmask); fz = group_sum<LANES>(fz, gmask);
-      rx = group_sum<LANES>(rx, gmask); ry = group_sum<LANES>(ry, gmask); rz = group_sum<LANES>(rz, gmask);
+    };
+    // Per warp and iteration the pass waits for the slowest of 32 gathers (usually one that went to DRAM) and then runs a
+    // long dependent chain of fp64 work; with a single slot in flight the two add up (ncu: issue slots 39 % busy, L1 data
+    // pipe 54 %, nothing saturated).  So the records of one slot are requested while the previous slot is evaluated:
+    // two record buffers used in turn (no copies between them), the index / pair-weight streams one pair of slots ahead.
+    // The padding of the tiles makes every gather of the (even, warp-wide) trip count legal without a test.
+    const int npair = (niter + 1) / 2;
+    unsigned j0 = (unsigned)ld_stream(lp), j1 = (unsigned)ld_stream(lp + 32);
+    double g0 = ld_stream(gp), g1 = ld_stream(gp + 32);
+    double gi0 = MULTI ? ld_stream(gip) : 0.0, gi1 = MULTI ? ld_stream(gip + 32) : 0.0;
+    Packed32 ra = ri, rb = ri;
+    Words16 ba = ri.b, bb = ri.b;
+    if (npair > 0) {
+      ra = ld_packed32(q.A + j0);
+      if (RAND) ba = ld_block16(q.B + j0);
     }
-    if (sub == 0) {
+#pragma unroll 1
+    for (int m = 0; m < npair; ++m) {
+      const int k = sub + 2 * m * LANES;
+      rb = ld_packed32(q.A + j1);                       // slot 2m + 1, evaluated after slot 2m
+      if (RAND) bb = ld_block16(q.B + j1);
+      const double ga = g0, gia = MULTI ? gi0 : g0, gb = g1, gib = MULTI ? gi1 : g1;
+      j0 = (unsigned)ld_stream(lp + 64 * (m + 1)); j1 = (unsigned)ld_stream(lp + 64 * (m + 1) + 32);
+      g0 = ld_stream(gp + 64 * (m + 1)); g1 = ld_stream(gp + 64 * (m + 1) + 32);
+      if (MULTI) { gi0 = ld_stream(gip + 64 * (m + 1)); gi1 = ld_stream(gip + 64 * (m + 1) + 32); }
+      pair_terms(k, ga, gia, ra, ba);
+      if (m + 1 < npair) {                               // slot 2m + 2, evaluated in the next iteration
+        ra = ld_packed32(q.A + j0);
+        if (RAND) ba = ld_block16(q.B + j0);
+      }
+      pair_terms(k + LANES, gb, gib, rb, bb);
+    }
+    if (FRIC) { fx = group_sum<LANES>(fx, gmask); fy = group_sum<LANES>(fy, gmask); fz = group_sum<LANES>(fz, gmask); }
+    if (RAND) { rx = group_sum<LANES>(rx, gmask); ry = group_sum<LANES>(ry, gmask); rz = group_sum<LANES>(rz, gmask); }
+    if (real && sub == 0) {
       // displacements were in quanta: two factors of the quantum; the random force also takes
       // eta_factor sqrt(T_e(nearest cell)) (fix_eph.cpp:829-833), worked out once per atom by prep_coupling
       double var = 0.0;
-      if (active && a.do_random) var = q.var[i] * q.quantum_sq;
+      if (RAND && active) var = q.var[i] * q.quantum_sq;
       fx *= q.quantum_sq; fy *= q.quantum_sq; fz *= q.quantum_sq;
       rx *= var; ry *= var; rz *= var;
       const size_t o = 3 * (size_t)i;
-      if (a.do_friction) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
-      if (a.do_random) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
+      if (FRIC) { a.f_eph[o] = fx; a.f_eph[o + 1] = fy; a.f_eph[o + 2] = fz; }
+      if (RAND) { a.f_rng[o] = rx; a.f_rng[o + 1] = ry; a.f_rng[o + 2] = rz; }
       // f += f_EPH (+ f_RNG) for every local atom, grouped or not (fix_eph.cpp:892-906)
       if (a.f != nullptr) {
         double ax = 0, ay = 0, az = 0;
-        if (a.add_friction) { ax += fx; ay += fy; az += fz; }
-        if (a.add_random) { ax += rx; ay += ry; az += rz; }
+        if (FRIC && a.add_friction) { ax += fx; ay += fy; az += fz; }
+        if (RAND && a.add_random) { ax += rx; ay += ry; az += rz; }
         a.f[o] += ax; a.f[o + 1] += ay; a.f[o + 2] += az;
       }
     }

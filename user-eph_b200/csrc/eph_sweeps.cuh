@@ -171,10 +171,12 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
   const bool spec = inner && a.spec_v;
   const int *__restrict__ list = inner ? a.ineigh : a.neigh;
 
-  for (int w = blockIdx.x * groups_per_block + group_in_block; w < a.n_work; w += gridDim.x * groups_per_block) {
+  // whole warps run the loop (the last tile may be partial): the padding of a freshly built tile needs a warp-wide maximum
+  const int n_work_pad = (a.n_work + 32 / LANES - 1) / (32 / LANES) * (32 / LANES);
+  for (int w = blockIdx.x * groups_per_block + group_in_block; w < n_work_pad; w += gridDim.x * groups_per_block) {
     // a work list names whole tiles (the warp's 32/LANES atoms), so the lane <-> tile-slot mapping is unchanged
     const int i = a.work ? a.work[w / (32 / LANES)] * (32 / LANES) + (w & (32 / LANES - 1)) : w;
-    const bool real = i < a.nlocal;   // the last tile may be partial
+    const bool real = w < a.n_work && i < a.nlocal;
     // the whole header of the atom is requested at once, not behind the record that says whether it is in the group
     double4 pi = make_double4(0, 0, 0, 0), vi = pi;
     RowWalk rw{0, 0};
@@ -254,6 +256,23 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
       a.rho[i] = rho;
       a.W4[i] = make_double4(wx, wy, wz, 0.0);
       if (BUILD) a.icount[i] = icnt;
+    }
+    if (BUILD) {
+      // Padding for the packed sweeps (eph_packed.cuh), which run ONE trip count per warp and prefetch without bounds
+      // tests: every atom's slots up to the longest list of the tile, rounded up to two iterations, hold the atom's own
+      // index and a zero pair weight.
+      __syncwarp();
+      int tmax = icnt;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xFFFFFFFFu, tmax, o));
+      const int padded = (tmax + 2 * LANES - 1) / (2 * LANES) * (2 * LANES);
+      const long long t0 = a.tile_off[(a.work ? i : w) / (32 / LANES)] + gshift;
+      for (int c = icnt + sub; c < padded; c += LANES) {
+        const long long dst = t0 + (long long)(c / LANES) * 32 + (c & (LANES - 1));
+        a.ineigh[dst] = real ? i : 0;
+        st_stream(a.gpair + dst, 0.0);
+        if (MULTI) st_stream(a.gpair_i + dst, 0.0);
+      }
     }
     // boundary tiles come first in the work list; when the last of them is done the ghost exchange may start
     // (the communication stream waits for the counter with a stream memory operation)

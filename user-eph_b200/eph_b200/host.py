@@ -185,6 +185,78 @@ class FixDriver:
         self._ck(self._fn("set_atoms")(C.c_void_p(self.w), s["nlocal"], s["nghost"],
                                        *[C.c_void_p(a.ctypes.data) if a is not None else None for a in arrs]))
 
+    # -- several ranks (tests): the stand-in's MPI and Comm::forward_comm(Fix*) get a transport ------------------
+    MPI_ALLREDUCE = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int)
+    MPI_BCAST = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)
+    MPI_ALLTOALLV = C.CFUNCTYPE(None, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int), C.POINTER(C.c_int))
+    MPI_BARRIER = C.CFUNCTYPE(None)
+    EXCHANGE = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int),
+                           C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int))
+
+    @classmethod
+    def plug_mpi(cls, lib, dist, prefix="b200"):
+        """Route the MPI stand-in of `lib` (tests/lammps_shim/mpi.h) through torch.distributed `dist`.  Call before the fix
+        is constructed; returns the callbacks, which the caller keeps alive."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        def view(ptr, n, ctype, dtype):
+            return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).view(dtype))
+
+        def allreduce(buf, n, dtype, op):
+            t = view(buf, n, C.c_double if dtype == 1 else C.c_int, np.float64 if dtype == 1 else np.int32)
+            dist.all_reduce(t, op={1: dist.ReduceOp.SUM, 2: dist.ReduceOp.MAX, 3: dist.ReduceOp.MIN}[op])
+
+        def bcast(buf, nbytes, root):
+            dist.broadcast(view(buf, nbytes, C.c_uint8, np.uint8), src=root)
+
+        def alltoallv(send, scount, sdisp, recv, rcount, rdisp):
+            outs = [torch.from_numpy(np.array([send[sdisp[r] + k] for k in range(scount[r])], dtype=np.int32)) for r in range(world)]
+            ins = [torch.empty(rcount[r], dtype=torch.int32) for r in range(world)]
+            ops = [dist.P2POp(dist.isend, outs[r], r) for r in range(world) if r != rank and scount[r]]
+            ops += [dist.P2POp(dist.irecv, ins[r], r) for r in range(world) if r != rank and rcount[r]]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            ins[rank] = outs[rank]
+            for r in range(world):
+                for k in range(rcount[r]):
+                    recv[rdisp[r] + k] = int(ins[r][k])
+
+        def barrier():
+            dist.barrier()
+
+        cbs = (cls.MPI_ALLREDUCE(allreduce), cls.MPI_BCAST(bcast), cls.MPI_ALLTOALLV(alltoallv), cls.MPI_BARRIER(barrier))
+        getattr(lib, prefix + "_set_mpi")(rank, world, *cbs)
+        return cbs
+
+    def set_swaps(self, swaps, dist):
+        """swaps: [(peer, sendlist (local indices, the peer's ghost order), first ghost index, count)], this rank included for
+        its own periodic images.  Comm::forward_comm(Fix*) of the stand-in then moves the packed buffers over `dist`."""
+        import torch
+
+        def exchange(nswaps, peer, sbuf, sn, rbuf, rn):
+            ops = []
+            for k in range(nswaps):
+                if sn[k]:
+                    ops.append(dist.P2POp(dist.isend, torch.from_numpy(np.ctypeslib.as_array(sbuf[k], shape=(sn[k],))), peer[k]))
+            for k in range(nswaps):
+                if rn[k]:
+                    ops.append(dist.P2POp(dist.irecv, torch.from_numpy(np.ctypeslib.as_array(rbuf[k], shape=(rn[k],))), peer[k]))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+
+        self._exchange_cb = self.EXCHANGE(exchange)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        peer, cnt = i32([w[0] for w in swaps]), i32([len(w[1]) for w in swaps])
+        flat = i32(np.concatenate([np.asarray(w[1], dtype=np.int32) for w in swaps]) if swaps else [])
+        first, n = i32([w[2] for w in swaps]), i32([w[3] for w in swaps])
+        self._ck(self._fn("set_swaps")(C.c_void_p(self.w), len(swaps), C.c_void_p(peer.ctypes.data), C.c_void_p(cnt.ctypes.data),
+                                       C.c_void_p(flat.ctypes.data), C.c_void_p(first.ctypes.data), C.c_void_p(n.ctypes.data),
+                                       self._exchange_cb))
+
     def set_neighbors(self, offsets, neigh):
         o = np.ascontiguousarray(offsets, dtype=np.int64)
         n = np.ascontiguousarray(neigh, dtype=np.int32)

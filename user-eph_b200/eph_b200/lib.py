@@ -26,6 +26,7 @@ class Config(C.Structure):
 # every symbol include/eph_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "eph_b200_version": (C.c_int, []),
+    "eph_b200_device_count": (C.c_int, [c_int_p]),
     "eph_b200_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "eph_b200_destroy": (C.c_int, [C.c_void_p]),
     "eph_b200_last_error": (C.c_char_p, [C.c_void_p]),
@@ -66,6 +67,12 @@ SYMBOLS = {
     "eph_b200_grid_substep": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "eph_b200_end_of_step_end_external": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_grid_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "eph_b200_comm_get_id": (C.c_int, [C.c_void_p]),
+    "eph_b200_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "eph_b200_set_ghost_map": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eph_b200_exchange_ghosts": (C.c_int, [C.c_void_p]),
+    "eph_b200_set_grid_sharding": (C.c_int, [C.c_void_p, C.c_int]),
+    "eph_b200_reduce_and_solve": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_set_grid_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_set_comm_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "eph_b200_set_boundary_atoms": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -332,6 +339,42 @@ class Engine:
         if p.value not in views:
             views[p.value] = torch.as_tensor(_DeviceArray(p.value, self.ncell), device=torch.device("cuda", torch.cuda.current_device()))
         return views[p.value]
+
+    # -- multi-rank data plane inside the engine (NCCL) ------------------------
+    @staticmethod
+    def comm_get_id():
+        """128 bytes (ncclUniqueId) created on the calling rank, for the caller to broadcast"""
+        buf = (C.c_char * 128)()
+        rc = load().eph_b200_comm_get_id(buf)
+        if rc != 0:
+            raise EphError("eph_b200_comm_get_id failed (%d): %s" % (rc, load().eph_b200_create_error().decode()))
+        return bytes(buf)
+
+    def comm_init(self, id_bytes, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
+        self._check(self.lib.eph_b200_comm_init(self.h, buf, rank, nranks))
+
+    def set_ghost_map(self, plan):
+        """plan: eph_b200.parallel.ExchangePlan (who holds which of my atoms as ghosts, who fills which of my ghost slots)"""
+        peers = [r for r in range(plan.world) if r != plan.rank and (plan.send_counts[r] or plan.recv_counts[r])]
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        pr, sc, rc = i32(peers), i32([plan.send_counts[r] for r in peers]), i32([plan.recv_counts[r] for r in peers])
+        si = i32(np.concatenate([plan.send_index[r] for r in peers]) if peers else [])
+        rs = i32(np.concatenate([plan.recv_index[r] for r in peers]) if peers else [])
+        self._check(self.lib.eph_b200_set_ghost_map(self.h, len(peers), pr.ctypes.data, sc.ctypes.data, si.ctypes.data,
+                                                    rc.ctypes.data, rs.ctypes.data))
+        self.exchange_bytes = 32 * (len(si) + len(rs))
+
+    def exchange_ghosts(self):
+        self._check(self.lib.eph_b200_exchange_ghosts(self.h))
+
+    def set_grid_sharding(self, on=True):
+        self._check(self.lib.eph_b200_set_grid_sharding(self.h, int(bool(on))))
+
+    def reduce_and_solve(self, want_energy=True):
+        e = C.c_double()
+        self._check(self.lib.eph_b200_reduce_and_solve(self.h, C.byref(e) if want_energy else None))
+        return e.value if want_energy else None
 
     def bind_grid_source(self, tensor):
         self._check(self.lib.eph_b200_bind_grid_source(self.h, tensor.data_ptr() if tensor is not None else None))

@@ -5,6 +5,8 @@
 
 #include <mpi.h>
 
+#include "eph_device_select.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -131,6 +133,8 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   // optional keyword pairs after the element names
   rng_mars = false;
   comm_lammps = nrPS > 1;
+  comm_nccl = false;
+  grid_sharded = false;
   neigh_device = false;
   peratom_every = 1;
   int device = -1;
@@ -138,7 +142,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   // reference those extras are skipped, and a keyword is recognised wherever it stands
   for (int k = 17 + types; k < narg; ++k) {
     const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "neigh") == 0 ||
-                            strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0;
+                            strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0 || strcmp(arg[k], "grid") == 0;
     if (!is_keyword) continue;   // an extra element name
     if (k + 1 >= narg) error->all(FLERR, "fix eph/b200: keyword without a value");
     const char *val = arg[k + 1];
@@ -157,10 +161,15 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
       // the cadence is the user's: every N-th step (default 1 = the reference's behaviour, 0 = never)
       peratom_every = atoi(val);
       if (peratom_every < 0) error->all(FLERR, "fix eph/b200: peratom must be >= 0");
+    } else if (strcmp(arg[k], "grid") == 0) {
+      if (strcmp(val, "sharded") == 0) grid_sharded = true;
+      else if (strcmp(val, "replicated") == 0) grid_sharded = false;
+      else error->all(FLERR, "fix eph/b200: grid must be replicated or sharded");
     } else {   // comm
-      if (strcmp(val, "lammps") == 0) comm_lammps = true;
-      else if (strcmp(val, "device") == 0) comm_lammps = false;
-      else error->all(FLERR, "fix eph/b200: comm must be device or lammps");
+      if (strcmp(val, "lammps") == 0) { comm_lammps = true; comm_nccl = false; }
+      else if (strcmp(val, "device") == 0) { comm_lammps = false; comm_nccl = false; }
+      else if (strcmp(val, "nccl") == 0) { comm_lammps = false; comm_nccl = true; }
+      else error->all(FLERR, "fix eph/b200: comm must be device, lammps or nccl");
     }
     ++k;
   }
@@ -172,11 +181,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   // the device engine
   eph_b200_config cfg;
   memset(&cfg, 0, sizeof cfg);
-  if (device < 0) {
-    const char *vis = getenv("EPH_B200_DEVICES_PER_NODE");
-    int per_node = vis ? atoi(vis) : 1;
-    device = per_node > 0 ? myID % per_node : 0;
-  }
+  if (device < 0) device = eph_b200::default_device(myID);   // node-local rank modulo the visible devices
   cfg.device = device;
   cfg.ntypes = types;
   cfg.type_map = type_map.data();
@@ -188,6 +193,18 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   cfg.nranks = nrPS;
   cfg.stream = nullptr;
   if (eph_b200_create(&cfg, &dev) != EPH_B200_OK) error->all(FLERR, eph_b200_create_error());
+  if (comm_nccl && nrPS > 1) {
+    // the engine's own transport (NCCL over NVLink): rank 0 creates the communicator id, MPI carries its 128 bytes
+    char id[EPH_B200_COMM_ID_BYTES];
+    memset(id, 0, sizeof id);
+    int ok = 1;
+    if (myID == 0) ok = eph_b200_comm_get_id(id) == EPH_B200_OK ? 1 : 0;
+    MPI_Bcast(&ok, 1, MPI_INT, 0, world);
+    if (!ok) error->all(FLERR, std::string("fix eph/b200: comm nccl: ") + eph_b200_create_error());
+    MPI_Bcast(id, EPH_B200_COMM_ID_BYTES, MPI_CHAR, 0, world);
+    check(eph_b200_comm_init(dev, id, myID, nrPS), "comm_init");
+    check(eph_b200_set_grid_sharding(dev, grid_sharded ? 1 : 0), "set_grid_sharding");
+  }
 
   {
     std::vector<double> t_rho = eph_b200::BetaTables::flatten(beta.rho_r_sq);
@@ -260,6 +277,11 @@ void FixEPHB200::init() {
     req->set_cutoff(r_cutoff);
   }
 
+  // a `neighbor` / `neigh_modify` command may have changed the skin since the fix line or between runs; the engine's
+  // inner list is validated against it on the device, so it must know the current value before every run
+  check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
+  need_upload = true;
+
   reset_dt();
 }
 
@@ -312,16 +334,51 @@ void FixEPHB200::final_integrate() {
 // rebuild, never per step.
 void FixEPHB200::upload_topology() {
   const int nlocal = atom->nlocal, nghost = atom->nghost;
-  if (nrPS > 1 && !comm_lammps)
-    error->all(FLERR, "fix eph/b200: comm device needs a single rank; use comm lammps (or the NCCL halves, INTEGRATION.md)");
+  if (nrPS > 1 && !comm_lammps && !comm_nccl)
+    error->all(FLERR, "fix eph/b200: comm device needs a single rank; use comm nccl (one rank per GPU) or comm lammps");
   ghost_owner.assign(nghost, -1);
+  ghost_rank.assign(nghost, -1);
+  std::vector<int> peers, send_count, send_index, recv_count, recv_slot;
   if (!comm_lammps) {
-    // ghost -> owner: one forward comm of the owner's local index through our own pack/unpack
+    // ghost -> (owner rank, owner's local index): one forward comm through our own pack/unpack
     state = FixState::OWNER;
     comm->forward_comm(this);
     state = FixState::NONE;
     for (int g = 0; g < nghost; ++g)
-      if (ghost_owner[g] < 0 || ghost_owner[g] >= nlocal) error->all(FLERR, "fix eph/b200: ghost atom without a local owner");
+      if (ghost_rank[g] < 0 || ghost_rank[g] >= nrPS || ghost_owner[g] < 0 || (ghost_rank[g] == myID && ghost_owner[g] >= nlocal))
+        error->one(FLERR, "fix eph/b200: ghost atom without an owner");
+  }
+  if (comm_nccl && nrPS > 1) {
+    // The ghost map of the engine's NCCL exchange.  Ghosts owned elsewhere are grouped by owner; every owner is told
+    // which of its atoms this rank holds, in this rank's ghost order (the receive order), and answers in kind.
+    std::vector<std::vector<int>> want(nrPS), slot(nrPS);
+    for (int g = 0; g < nghost; ++g) {
+      const int r = ghost_rank[g];
+      if (r == myID) continue;             // an image of one of this rank's own atoms: filled inside the engine
+      want[r].push_back(ghost_owner[g]);
+      slot[r].push_back(nlocal + g);
+      ghost_owner[g] = -1;
+    }
+    std::vector<int> n_want(nrPS), n_asked(nrPS), d_want(nrPS), d_asked(nrPS), flat_want;
+    for (int r = 0; r < nrPS; ++r) n_want[r] = (int)want[r].size();
+    MPI_Alltoall(n_want.data(), 1, MPI_INT, n_asked.data(), 1, MPI_INT, world);
+    int tw = 0, ta = 0;
+    for (int r = 0; r < nrPS; ++r) {
+      d_want[r] = tw; d_asked[r] = ta;
+      tw += n_want[r]; ta += n_asked[r];
+      flat_want.insert(flat_want.end(), want[r].begin(), want[r].end());
+    }
+    std::vector<int> asked(ta > 0 ? ta : 1);
+    if (flat_want.empty()) flat_want.push_back(0);
+    MPI_Alltoallv(flat_want.data(), n_want.data(), d_want.data(), MPI_INT, asked.data(), n_asked.data(), d_asked.data(), MPI_INT, world);
+    for (int r = 0; r < nrPS; ++r) {
+      if (r == myID || (n_want[r] == 0 && n_asked[r] == 0)) continue;
+      peers.push_back(r);
+      send_count.push_back(n_asked[r]);
+      send_index.insert(send_index.end(), asked.begin() + d_asked[r], asked.begin() + d_asked[r] + n_asked[r]);
+      recv_count.push_back(n_want[r]);
+      recv_slot.insert(recv_slot.end(), slot[r].begin(), slot[r].end());
+    }
   }
   // LAMMPS' tagint is 32 or 64 bits wide depending on the build (-DLAMMPS_SMALLBIG, the default, has 32): widen here
   tag64.resize((size_t)nlocal + nghost);
@@ -329,6 +386,10 @@ void FixEPHB200::upload_topology() {
   check(eph_b200_set_atoms(dev, nlocal, nghost, atom->type, atom->mask, tag64.data(),
                            ghost_owner.data(), EPH_B200_HOST),
         "set_atoms");
+  if (comm_nccl && nrPS > 1)
+    check(eph_b200_set_ghost_map(dev, (int)peers.size(), peers.data(), send_count.data(), send_index.data(), recv_count.data(),
+                                 recv_slot.data()),
+          "set_ghost_map");
   if (neigh_device) check(eph_b200_build_neighbors(dev, &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
   else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
   // the memory kernel's state in the atoms' present order (LAMMPS may have sorted or migrated them)
@@ -355,8 +416,8 @@ void FixEPHB200::post_force(int) {
       }
     xi = xi_host.data();
   }
-  if (nlocal + nghost == 0) return;
-  if (!comm_lammps) {
+  if (nlocal + nghost == 0) return;   // no atoms, no ghosts: nobody exchanges anything with this rank
+  if (!comm_lammps) {   // one rank, or the engine's NCCL exchange between the two halves of post_force
     check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
                               EPH_B200_HOST),
           "post_force");
@@ -376,17 +437,31 @@ void FixEPHB200::post_force(int) {
 void FixEPHB200::end_of_step() {
   const int nlocal = atom->nlocal;
   double E_local = 0.0;
-  if (nlocal > 0)
-    check(eph_b200_end_of_step(dev, &atom->x[0][0], &atom->v[0][0], &E_local, EPH_B200_HOST), "end_of_step");
+  const double *xp = nlocal > 0 ? &atom->x[0][0] : nullptr, *vp = nlocal > 0 ? &atom->v[0][0] : nullptr;
+  if (nrPS == 1) {
+    if (nlocal > 0) check(eph_b200_end_of_step(dev, xp, vp, &E_local, EPH_B200_HOST), "end_of_step");
+  } else if (comm_nccl) {
+    // every rank, with or without atoms: the engine sums the source term over ranks (ncclAllReduce) and solves
+    check(eph_b200_end_of_step(dev, xp, vp, &E_local, EPH_B200_HOST), "end_of_step");
+  } else {
+    // LAMMPS' transport: every rank deposits its own atoms, the source term is summed over ranks like the reference's
+    // sync_before does (eph_fdm.h:479-482), and every rank then solves the same grid (no broadcast needed, :484-491)
+    check(eph_b200_end_of_step_begin(dev, xp, vp, EPH_B200_HOST), "end_of_step");
+    source_buf.resize(grid.ncell());
+    check(eph_b200_get_grid(dev, 5, source_buf.data()), "get_grid");
+    MPI_Allreduce(MPI_IN_PLACE, source_buf.data(), (int)source_buf.size(), MPI_DOUBLE, MPI_SUM, world);
+    check(eph_b200_put_grid(dev, 5, source_buf.data()), "put_grid");
+    check(eph_b200_end_of_step_end(dev, &E_local), "end_of_step");
+  }
 
-  // heat map (fix_eph.cpp:397-399)
+  // heat map (fix_eph.cpp:397-399); rank 0 only, so failures there must not wait for the other ranks
   if (myID == 0 && T_freq > 0 && (update->ntimestep % T_freq) == 0) {
     std::vector<double> T(grid.ncell());
-    check(eph_b200_get_grid(dev, 0, T.data()), "get_grid");
+    if (eph_b200_get_grid(dev, 0, T.data()) != EPH_B200_OK) error->one(FLERR, std::string("fix eph/b200: get_grid: ") + eph_b200_last_error(dev));
     try {
       eph_b200::write_heat_map(grid, T, T_out, (int)(update->ntimestep / T_freq));
     } catch (const std::exception &e) {
-      error->all(FLERR, e.what());
+      error->one(FLERR, e.what());
     }
   }
 
@@ -455,6 +530,7 @@ int FixEPHB200::pack_forward_comm(int n, int *list, double *data, int, int *) {
     // LAMMPS forwards ghosts of ghosts in later swaps: resolve through the part already known
     for (int i = 0; i < n; ++i) {
       const int src = list[i];
+      data[m++] = static_cast<double>(src < nlocal ? myID : ghost_rank[src - nlocal]);
       data[m++] = static_cast<double>(src < nlocal ? src : ghost_owner[src - nlocal]);
     }
     return m;
@@ -471,7 +547,10 @@ int FixEPHB200::pack_forward_comm(int n, int *list, double *data, int, int *) {
 void FixEPHB200::unpack_forward_comm(int n, int first, double *data) {
   if (state == FixState::OWNER) {
     const int nlocal = atom->nlocal;
-    for (int i = 0; i < n; ++i) ghost_owner[first + i - nlocal] = static_cast<int>(data[i]);
+    for (int i = 0; i < n; ++i) {
+      ghost_rank[first + i - nlocal] = static_cast<int>(data[2 * i]);
+      ghost_owner[first + i - nlocal] = static_cast<int>(data[2 * i + 1]);
+    }
     return;
   }
   const int st = state == FixState::RHO ? EPH_B200_STATE_RHO : state == FixState::WI ? EPH_B200_STATE_WI
@@ -485,16 +564,16 @@ double FixEPHB200::memory_usage() {
 
 // final grid state, readable as T_infile of a later run (fix_eph.cpp:1019-1021)
 void FixEPHB200::post_run() {
-  if (myID != 0) return;
+  if (myID != 0) return;   // rank 0 only: errors in here are error->one, error->all would wait for ranks that never come
   std::vector<double> T(grid.ncell());
-  check(eph_b200_get_grid(dev, 0, T.data()), "get_grid");
   // temperature-dependent cells carry their last C_e / kappa_e in the reference's restart
-  check(eph_b200_get_grid(dev, 3, grid.C_e.data()), "get_grid");
-  check(eph_b200_get_grid(dev, 4, grid.kappa_e.data()), "get_grid");
+  if (eph_b200_get_grid(dev, 0, T.data()) != EPH_B200_OK || eph_b200_get_grid(dev, 3, grid.C_e.data()) != EPH_B200_OK ||
+      eph_b200_get_grid(dev, 4, grid.kappa_e.data()) != EPH_B200_OK)
+    error->one(FLERR, std::string("fix eph/b200: get_grid: ") + eph_b200_last_error(dev));
   try {
     eph_b200::write_restart(grid, T, T_state);
   } catch (const std::exception &e) {
-    error->all(FLERR, e.what());
+    error->one(FLERR, e.what());
   }
 }
 

@@ -9,8 +9,12 @@
  *   device N          CUDA device ordinal (default: rank modulo visible devices)
  *   neigh lammps|device the full neighbour list comes from LAMMPS (uploaded when it is rebuilt; default) or is built
  *                     on the device from the positions (LAMMPS then builds no list for this fix)
- *   comm device|lammps ghost values through the engine's own owner map (single rank, default) or through LAMMPS'
- *                     Comm::forward_comm(Fix*) with host buffers, as the reference does (default for several ranks)
+ *   comm device|lammps|nccl  ghost values through the engine's own owner map (single rank, default), through LAMMPS'
+ *                     Comm::forward_comm(Fix*) with host buffers and MPI_Allreduce of the grid source term, as the
+ *                     reference does (default for several ranks), or -- one rank per GPU -- through the engine's own
+ *                     NCCL data plane (one grouped send/recv of {rho, W} per peer, ncclAllReduce of the source term)
+ *   grid replicated|sharded  with comm nccl: every rank solves the whole grid (default) or only its z-slab, with halo
+ *                     planes between sub-steps and one all-gather (replaces the reference's MPI_Bcast, eph_fdm.h:490)
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
  * (f_ID[1], f_ID[2], 8 per-atom columns); all per-timestep work is done by libeph_b200 (include/eph_b200.h).
  * Build with -DEPH_B200_REPLACE_FIX_EPH to register under the name `eph` itself.
@@ -101,6 +105,8 @@ class FixEPHB200 : public Fix {
   class RanMars *random;
   bool rng_mars;
   bool comm_lammps;
+  bool comm_nccl;               // keyword `comm nccl`: the engine exchanges ghosts / sums the grid source over NCCL itself
+  bool grid_sharded;            // keyword `grid sharded`: with comm nccl every rank advances only its z-slab of the grid
   bool neigh_device;
   int peratom_every;            // keyword `peratom N`: array_atom is refreshed every N-th step (0: never)
   class NeighList *list;
@@ -113,7 +119,9 @@ class FixEPHB200 : public Fix {
   double **array;               // [nmax][8] per-atom output (array_atom)
   std::vector<double> xi_host;  // rng mars: Gaussians of this step
   std::vector<int64_t> tag64;   // atom->tag widened to 64 bits for the C ABI (tagint may be 32 bits wide)
-  std::vector<int> ghost_owner; // local owner of each ghost (single rank)
+  std::vector<int> ghost_owner; // owner's local index of each ghost ...
+  std::vector<int> ghost_rank;  // ... and the rank that owns it
+  std::vector<double> source_buf; // comm lammps on several ranks: the grid source term on its way through MPI_Allreduce
   std::vector<double> owner_buf;
   long long atoms_epoch;        // (nlocal,nghost) signature of the last upload
   bool need_upload;
