@@ -5,11 +5,18 @@
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's own CPU fix
 
 Workload: fcc Ni, n^3 unit cells (n = 100 -> 4 000 000 atoms), a = 3.52 A, N(0, 0.05 A)
-displacements, Maxwell velocities at 600 K plus one 10 keV primary knock-on atom, dt = 1e-4 ps, flags 7
-(friction + random + FDM), model 4, FDM grid 64^3, full neighbour list at r_c + 2 A = 7 A.  One step = post_force
-+ end_of_step.  `value` is timed with all inputs resident in HBM; `e2e` goes through the same C ABI with pinned
-HOST buffers (x, v, f up and f down every step, the neighbour list re-uploaded every 10 steps as a re-neighbouring
-LAMMPS run would).  Prints ONE JSON line.
+displacements, Maxwell velocities at 600 K plus one 10 keV primary knock-on atom, flags 7 (friction + random + FDM),
+model 4, `Data/Ni/Ni_PRB2019.beta` (shipped copy), FDM grid 64^3, full neighbour list at r_c + 2 A = 7 A, time step of
+the cascade's adaptive rule while the PKA is fast (1e-3 A / v_max = 5.5e-7 ps).
+
+One step is what LAMMPS' Verlet loop makes the fix do: initial_integrate -> (LAMMPS: ghost refresh; every 10th step
+re-neighbouring: the fix registers its atoms again and the full list is rebuilt from the positions, on the device) ->
+post_force -> final_integrate -> end_of_step.  The atoms move, the device-side inner list is rebuilt with the full list,
+and all of it is inside the timed region (`--mode static` times post_force + end_of_step on frozen atoms instead, the
+round-1 measurement).  `value` has everything resident in HBM; `e2e` goes through the same C ABI with pinned HOST
+buffers.  On N > 1 GPUs the engine's own NCCL data plane runs the ghost exchange, the source all-reduce and the grid
+solve, and after the timed steps the result is checked atom by atom against the whole box on one GPU (`parity_vs_n1`).
+Prints ONE JSON line.
 """
 import argparse
 import json
@@ -25,11 +32,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
 sys.path.insert(0, ROOT)
 
-BETA_FILE = os.path.join(ROOT, "tests", "golden", "Ni_trunc.beta")
 METRIC = "fix eph atom-steps/s (Ni 4M atoms)"
 UNIT = "atom-steps/s"
 REBUILD_EVERY = 10
-DT = 1e-4
+V_PKA = 1813.0                      # A/ps: 10 keV Ni (Tests/MD_Run/run.lmp:69-73)
+DT = 1e-3 / V_PKA                   # ps: the adaptive rule's step while the PKA is fast (Tests/MD_Run/run.lmp:94-97, :177-189)
+MASS = 58.71
+FTM2V = 1.0 / 1.0364269e-4
+CUTOFF = 7.0                        # r_c + skin
 
 
 def parse_args():
@@ -38,38 +48,43 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="trajectory", choices=["trajectory", "static"],
+                    help="trajectory (default): integrator hooks + re-neighbouring every 10 steps inside the timed region; "
+                         "static: post_force + end_of_step on frozen atoms (steady state of the two sweeps)")
     ap.add_argument("--cells", type=int, default=100, help="fcc unit cells per box edge (100 -> 4M atoms)")
     ap.add_argument("--grid", type=int, default=64, help="FDM grid points per edge")
+    ap.add_argument("--dt", type=float, default=DT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: keep the ghost exchange on the main stream")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C4 (4-element) leg and the small-box check against the reference")
+    ap.add_argument("--no-check", action="store_true", help="multi-GPU: skip the atom-by-atom comparison with the whole box on one GPU")
+    ap.add_argument("--overlap", action="store_true", help="multi-GPU: ghost exchange on a second stream behind a boundary-first density pass")
     ap.add_argument("--sharded-grid", action="store_true", help="multi-GPU: every rank advances only its z-slab of the FDM grid "
                     "(halo planes between sub-steps, all-gather at the end) instead of solving the whole grid redundantly; "
                     "needs --grid divisible by --gpus")
-    ap.add_argument("--side-stream-priority", type=int, default=0, help="CUDA priority of the grid/communication streams "
-                    "and of NCCL's stream (0 default; -1 high was measured 12 %% slower at 2 GPUs: the all-reduce kernel "
-                    "then takes SM slots from the density pass while it waits for its peer)")
     ap.add_argument("--weak", action="store_true", help="weak scaling (supplementary): --cells^3 unit cells and --grid^3 grid "
                     "cells PER GPU (config C5 at 8 GPUs: 32 M atoms); the default is strong scaling of the named 4 M-atom box")
-    ap.add_argument("--elements", type=int, default=1, help="config C4: this many elements (types uniform random), synthetic "
-                    "multi-element .beta file written on the fly; the default 1 is the Ni workload of the headline metric")
-    ap.add_argument("--cpu-cells", type=int, default=16, help="edge of each CPU-baseline replica (16 -> 16 384 atoms)")
-    ap.add_argument("--cpu-steps", type=int, default=100, help="timed steps of every CPU-baseline replica (about 10 s of work per core)")
+    ap.add_argument("--elements", type=int, default=1, help="config C4: 4 = the NiCoCrFe table with types uniform random")
+    ap.add_argument("--cpu-cells", type=int, default=32, help="edge of each CPU replica (32 -> 131 072 atoms)")
+    ap.add_argument("--cpu-steps", type=int, default=8, help="timed steps of every CPU-baseline replica (about 12 s of work per core)")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
-def build_workload(cells, brick=None, elements=1):
+def beta_file(elements):
     from eph_b200 import harness as H
-    s = H.make_system(cells, brick=brick, ntypes=elements)
-    # the primary knock-on atom of config C3: 10 keV along (0.835, 0.544, 0.082) (Tests/MD_Run/run.lmp:69-73)
-    if brick is None or brick[0] == 0:
-        pka = 0
-        s["v"][pka] = 1813.0 * np.array([0.835115, 0.543981, 0.081652])
-        s["v"][s["nlocal"]:][s["ghost_owner"] == pka] = s["v"][pka]
+    return H.shipped_beta("Ni_PRB2019" if elements == 1 else "NiCoCrFe_PRB2019")
+
+
+def build_workload(cells, brick=None, elements=1, with_list=False):
+    from eph_b200 import harness as H
+    s = H.make_system(cells, brick=brick, ntypes=elements, with_list=with_list)
+    # the primary knock-on atom of config C3: 10 keV along (0.835, 0.544, 0.082) (Tests/MD_Run/run.lmp:69-73); tag 1
+    pka = np.nonzero(s["tag"] == 1)[0]
+    s["v"][pka] = V_PKA * np.array([0.835115, 0.543981, 0.081652])
     return s
 
 
@@ -83,6 +98,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.rows = []
         self.stop_flag = False
+        self.proc = None
 
     def run(self):
         try:
@@ -124,70 +140,93 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's own fix (compiled, unmodified) or the oracle port, as independent replicas
 # ---------------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    cells, steps, seed, use_ref = args
+_cpu_state = {}
+
+
+def _cpu_init(cells, grid, dt, seed_base):
+    """one replica per worker process, built once: the unmodified reference fix on its own periodic box"""
+    import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
     sys.path.insert(0, ROOT)
     from eph_b200 import harness as H
-    s = H.make_system(cells, pos_seed=1234 + seed, vel_seed=101 + seed)
-    xi = np.random.default_rng(seed).normal(size=(s["nlocal"], 3))
+    k = mp.current_process()._identity[0] if mp.current_process()._identity else 0
+    s = H.make_system(cells, pos_seed=1234 + k, vel_seed=101 + k)
+    s["v"][0] = V_PKA * np.array([0.835115, 0.543981, 0.081652])
+    s["v"][s["nlocal"]:][s["ghost_owner"] == 0] = s["v"][0]
+    xi = np.random.default_rng(seed_base + k).normal(size=(s["nlocal"], 3))
     box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
-    g = 4
-    if use_ref:
-        from oracle import reference as R
+    from oracle import reference as R
+    if R.available():
         devnull = os.open(os.devnull, os.O_WRONLY)   # the reference prints a banner per fix
         saved = os.dup(1)
         os.dup2(devnull, 1)
         try:
-            drv = R.fix_driver(s, H.fix_args(7, BETA_FILE, ["Ni"], grid=(g, g, g)), dt=DT)
+            drv = R.fix_driver(s, H.fix_args(7, beta_file(1), ["Ni"], grid=(grid,) * 3), dt=dt)
         finally:
             os.dup2(saved, 1)
-        drv.set_xi(xi); drv.post_force(); drv.end_of_step()          # untimed first step
-        t0 = time.perf_counter()
-        for _ in range(steps):
+
+        def step():
             drv.set_xi(xi)
             drv.post_force()
             drv.end_of_step()
-        return s["nlocal"] * steps, time.perf_counter() - t0
-    from oracle import oracle as O
-    fx = O.Fix(s, O.Beta(path=BETA_FILE), O.FDM(g, g, g, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=DT)
-    fx.post_force(xi); fx.end_of_step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fx.post_force(xi)
-        fx.end_of_step()
-    return s["nlocal"] * steps, time.perf_counter() - t0
+        kind = "reference"
+    else:
+        from oracle import oracle as O
+        fx = O.Fix(s, O.Beta(path=beta_file(1)), O.FDM(grid, grid, grid, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=dt)
+
+        def step():
+            fx.post_force(xi)
+            fx.end_of_step()
+        kind = "port"
+    step()                                           # untimed first step
+    _cpu_state.update(step=step, natoms=s["nlocal"], kind=kind)
 
 
-def cpu_baseline(cells, steps, procs=None):
-    """Aggregate atom-steps/s of `procs` concurrent single-rank replicas (the reference has no threads and MPI is
-    not installed, so replicas stand in for ranks)."""
-    import multiprocessing as mp
-    from oracle import reference as R
-    use_ref = R.available()
-    procs = procs or max(1, (os.cpu_count() or 1))
-    ctx = mp.get_context("spawn")
+def _cpu_run(nsteps):
     t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(cells, steps, k, use_ref) for k in range(procs)])
-    wall = time.perf_counter() - t0
-    work = sum(r[0] for r in res)
-    tmax = max(r[1] for r in res)
-    return {"value": work / tmax, "unit": UNIT, "cores": procs, "kind": "reference" if use_ref else "port",
-            "sample": "%d concurrent single-rank replicas of %d Ni atoms (n=%d), %d timed steps each, grid 4^3, flags 7, "
-                      "model 4; slowest replica %.2f s, wall %.1f s" % (procs, 4 * cells ** 3, cells, steps, tmax, wall)}
+    for _ in range(nsteps):
+        _cpu_state["step"]()
+    return _cpu_state["natoms"] * nsteps, time.perf_counter() - t0, _cpu_state["kind"]
+
+
+class CpuReplicas:
+    """`procs` concurrent single-rank replicas of the reference fix (it has no threads and MPI is not installed, so
+    replicas stand in for ranks), each on its own 4 * cells^3-atom periodic box with the
+    workload's grid, parametrisation, PKA and time step."""
+
+    def __init__(self, cells, grid, dt, procs=None):
+        import multiprocessing as mp
+        self.procs = procs or max(1, (os.cpu_count() or 1))
+        self.cells, self.grid = cells, grid
+        self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_init, initargs=(cells, grid, dt, 777))
+        self.pool.map(_cpu_run, [0] * self.procs)   # every worker has built its replica
+
+    def sample(self, nsteps):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_run, [nsteps] * self.procs, chunksize=1)
+        wall = time.perf_counter() - t0
+        work, tmax = sum(r[0] for r in res), max(r[1] for r in res)
+        return {"value": work / tmax, "unit": UNIT, "cores": self.procs, "kind": res[0][2],
+                "sample": "%d concurrent single-rank replicas of %d Ni atoms (n=%d) with a %d^3 grid, %d timed steps each, "
+                          "flags 7, model 4, Ni_PRB2019; slowest replica %.2f s, wall %.1f s"
+                          % (self.procs, 4 * self.cells ** 3, self.cells, self.grid, nsteps, tmax, wall)}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = []
-    base = None
+    rep = CpuReplicas(a.cpu_cells, a.grid, a.dt)
+    per_step, base = [], None
     for k in range(a.warmup + a.steps):
-        base = cpu_baseline(a.cpu_cells, 10)
+        base = rep.sample(1)
         if k >= a.warmup:
             per_step.append(base["value"])
+    rep.close()
     value = float(np.mean(per_step))
     natoms = 4 * a.cells ** 3
     base["value"] = value
@@ -196,31 +235,121 @@ def run_reference_arm(a):
            "dtype": "f64", "data": "synthetic", "impl": "reference",
            "config": workload_config(a, natoms), "cpu_baseline": base,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "reference CPU fix on the host cores; each step is a bounded sample (all cores, one replica of "
-                   "%d atoms per core); ms_per_step is the time the full %d-atom workload would need at that rate"
-                   % (4 * a.cpu_cells ** 3, natoms)}
+           "note": "the unmodified reference fix (post_force + end_of_step) on all host cores; every step is a bounded sample "
+                   "(one replica of %d atoms with the workload's %d^3 grid per core, one fix step each); ms_per_step is the "
+                   "time the %d-atom workload would need at that rate" % (4 * a.cpu_cells ** 3, a.grid, natoms)}
     print(json.dumps(out))
 
 
 def workload_config(a, natoms):
     multi = getattr(a, "elements", 1) > 1
+    beta = "Data/NiCoCrFe/NiCoCrFe_PRB2019.beta" if multi else "Data/Ni/Ni_PRB2019.beta"
+    steps = ("trajectory: initial_integrate, post_force, final_integrate, end_of_step on moving atoms, re-neighbouring (atoms "
+             "registered again, full list and inner list rebuilt on the device) every %d steps, all inside the timed region"
+             % REBUILD_EVERY) if a.mode == "trajectory" else "static: post_force + end_of_step on frozen atoms"
     if getattr(a, "weak", False) and a.gpus > 1:
         return {"workload": "C5-style weak scaling: Ni fcc, %d^3 cells (= %d atoms) and a %d^3 grid per GPU, %d atoms in all, "
-                            "flags 7, model 4, dt 1e-4 ps, full list at 7 A" % (a.cells, 4 * a.cells ** 3, a.grid, natoms),
-                "atoms": natoms, "fdm_grid_per_gpu": [a.grid] * 3, "beta_file": "tests/golden/Ni_trunc.beta",
+                            "flags 7, model 4, dt %.3g ps, full list at 7 A" % (a.cells, 4 * a.cells ** 3, a.grid, natoms, a.dt),
+                "atoms": natoms, "fdm_grid_per_gpu": [a.grid] * 3, "beta_file": beta, "step": steps,
                 "l2": "inputs far larger than the 126 MB L2; no flush needed", "parallelism": "spatial bricks, one rank per GPU"}
-    name = ("C4: %d-element fcc alloy (types uniform random, synthetic .beta tables)" % a.elements) if multi else "C3: Ni fcc"
+    name = "C4: NiCoCrFe fcc alloy (types uniform random)" if multi else "C3: Ni fcc"
     return {"workload": "%s %d^3 cells = %d atoms, one 10 keV PKA, flags 7 (friction+random+FDM), model 4, "
-                        "FDM grid %d^3, dt 1e-4 ps, full list at 7 A" % (name, a.cells, natoms, a.grid),
-            "atoms": natoms, "fdm_grid": [a.grid] * 3,
-            "beta_file": "synthetic (eph_b200.harness.synthetic_knots)" if multi else "tests/golden/Ni_trunc.beta",
+                        "FDM grid %d^3, dt %.3g ps, full list at 7 A" % (name, a.cells, natoms, a.grid, a.dt),
+            "atoms": natoms, "fdm_grid": [a.grid] * 3, "beta_file": beta + " (shipped copy, tests/golden/data)", "step": steps,
             "l2": "inputs (neighbour list + per-atom arrays) far larger than the 126 MB L2; no flush needed",
-            "parallelism": "spatial bricks, one rank per GPU"}
+            "parallelism": "spatial bricks, one rank per GPU; ghost exchange, source all-reduce and grid solve by the engine over NCCL"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
+class Verlet:
+    """Plays LAMMPS' Verlet loop around the fix for one rank, everything on the device: the fix hooks are the engine's
+    C-ABI calls, LAMMPS' own part (ghost positions and velocities follow their owners, force_clear, re-neighbouring
+    cadence) is done here with torch.  On several ranks the ghosts owned elsewhere are refreshed by an all-to-all over
+    torch.distributed, like LAMMPS' Comm::forward_comm() with ghost_velocity does."""
+
+    def __init__(self, eng, s, plan, dist, dev, a, torch):
+        self.eng, self.s, self.plan, self.dist, self.torch, self.a = eng, s, plan, dist, torch, a
+        nl, ng = s["nlocal"], s["nghost"]
+        t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
+        self.nl, self.ng = nl, ng
+        self.x, self.v = t(s["x"], torch.float64), t(s["v"], torch.float64)
+        self.f = torch.zeros((nl, 3), dtype=torch.float64, device=dev)
+        self.type, self.mask, self.tag = t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64)
+        self.owner = t(plan.self_owner, torch.int32)
+        self.mass = np.array([0.0] + [MASS] * s["ntypes"])
+        self.dtv, self.dtf = a.dt, 0.5 * a.dt * FTM2V
+        # ghosts that are images of this rank's own atoms: position = owner + shift
+        own = np.nonzero(plan.self_owner >= 0)[0]
+        self.own_g = t(nl + own, torch.long)
+        self.own_o = t(plan.self_owner[own], torch.long)
+        self.own_shift = self.x[self.own_g] - self.x[self.own_o]
+        # ghosts owned by other ranks: x, v of my atoms they hold go out, theirs come in (set-up: the shifts)
+        self.world = dist.get_world_size() if dist else 1
+        if self.world > 1:
+            self.send_idx = t(plan.flat_send_index(), torch.long)
+            self.recv_idx = t(plan.flat_recv_index(), torch.long)
+            self.out_splits = [6 * c for c in plan.send_counts]
+            self.in_splits = [6 * c for c in plan.recv_counts]
+            self.sbuf = torch.empty((max(len(self.send_idx), 1), 6), dtype=torch.float64, device=dev)
+            self.rbuf = torch.empty((max(len(self.recv_idx), 1), 6), dtype=torch.float64, device=dev)
+            self._exchange()
+            self.rem_shift = self.x[self.recv_idx] - self.rbuf[: len(self.recv_idx), :3]
+        self.register(first=True)
+
+    def _exchange(self):
+        ns, nr = len(self.send_idx), len(self.recv_idx)
+        self.sbuf[:ns, :3] = self.x[self.send_idx]
+        self.sbuf[:ns, 3:] = self.v[self.send_idx]
+        self.dist.all_to_all_single(self.rbuf.view(-1)[: 6 * nr], self.sbuf.view(-1)[: 6 * ns], output_split_sizes=self.in_splits,
+                                    input_split_sizes=self.out_splits)
+
+    def refresh_ghosts(self):
+        """LAMMPS' forward comm of x and v (comm->ghost_velocity is set by the fix, fix_eph.cpp:82)"""
+        self.x[self.own_g] = self.x[self.own_o] + self.own_shift
+        self.v[self.own_g] = self.v[self.own_o]
+        if self.world > 1:
+            self._exchange()
+            nr = len(self.recv_idx)
+            self.x[self.recv_idx] = self.rbuf[:nr, :3] + self.rem_shift
+            self.v[self.recv_idx] = self.rbuf[:nr, 3:]
+
+    def register(self, first=False):
+        """what FixEPHB200::upload_topology does when LAMMPS has re-neighboured: atoms, full list (built on the device from
+        the positions: `neigh device`), ghost map"""
+        eng = self.eng
+        eng.set_atoms(self.nl, self.ng, self.type, self.mask, self.tag, self.owner)
+        eng.build_neighbors(self.x, CUTOFF)
+        if self.world > 1:
+            eng.set_ghost_map(self.plan)
+
+    def step(self, k):
+        eng = self.eng
+        if self.a.mode == "static":
+            eng.post_force(self.x, self.v, self.f, None, k)
+            eng.end_of_step(None, self.v, want_energy=False)
+            return
+        eng.initial_integrate(self.x, self.v, self.f, self.mass, self.dtv, self.dtf)
+        self.refresh_ghosts()
+        if k % REBUILD_EVERY == 0:
+            self.register()
+        self.f.zero_()                      # LAMMPS: force_clear; there is no pair style in this workload
+        eng.post_force(self.x, self.v, self.f, None, k)
+        eng.final_integrate(self.v, self.f, self.mass, self.dtf)
+        eng.end_of_step(None, self.v, want_energy=False)
+
+
+def make_engine(lib, host, a, s, gridn, box, local, rank, world, stream, elements=None):
+    elements = elements or a.elements
+    eng = lib.Engine(list(range(elements)), flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
+    eng.set_tables_from(host.BetaTables(path=beta_file(elements)))
+    eng.set_grid(gridn[0], gridn[1], gridn[2], box, 300.0, 1.0, 3.5e-6, 0.1248)
+    eng.set_dt(a.dt)
+    eng.set_skin(2.0)
+    return eng
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -235,9 +364,7 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = a.side_stream_priority < 0    # NCCL's own stream: like the side streams below
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        dist.init_process_group("nccl", device_id=dev)
     D = dist if world > 1 else None
 
     grid = P.brick_grid(world)
@@ -248,7 +375,6 @@ def run_b200(a):
         s["grid"] = (1, 1, 1)
     nl, ng = s["nlocal"], s["nghost"]
     natoms = s["natoms"]
-    n_nb = float(s["offsets"][-1]) / nl
     box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
     plan = P.ExchangePlan(s, rank, world, D)
 
@@ -257,44 +383,21 @@ def run_b200(a):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    beta_file = BETA_FILE
-    if a.elements > 1:   # C4: multi-element tables (two look-ups per pair, second pair-weight stream)
-        import tempfile
-        from eph_b200 import harness as H
-        beta_file = os.path.join(tempfile.mkdtemp(prefix="eph_bench_"), "synthetic_%d.beta" % a.elements)
-        H.write_beta_file(beta_file, H.synthetic_knots(n_elements=a.elements))
-    eng = lib.Engine(list(range(a.elements)), flags=7, seed=12345, device=local, rank=rank, nranks=world, stream=stream)
-    eng.set_tables_from(host.BetaTables(path=beta_file))
-    eng.set_grid(gridn[0], gridn[1], gridn[2], box, 300.0, 1.0, 3.5e-6, 0.1248)
-    eng.set_dt(DT)
-    eng.set_skin(2.0)
-    t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
-    d_type, d_mask, d_tag, d_owner = t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64), t(plan.self_owner, torch.int32)
-    d_off, d_neigh = t(s["offsets"], torch.int64), t(s["neigh"], torch.int32)
-    d_x, d_v = t(s["x"], torch.float64), t(s["v"], torch.float64)
-    d_f = torch.zeros((nl, 3), dtype=torch.float64, device=dev)
-    d_src = torch.zeros(gridn[0] * gridn[1] * gridn[2], dtype=torch.float64, device=dev)
-    eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
-    eng.set_neighbors(d_off, d_neigh)
-    eng.bind_grid_source(d_src)
-    gstream = cstream = None
-    if D:   # grid all-reduce + solve on a second stream: they overlap the next step's density pass
-        # side streams at default priority (see --side-stream-priority)
-        gstream = torch.cuda.Stream(device=dev, priority=a.side_stream_priority)
-        eng.set_grid_stream(gstream.cuda_stream)
-        if not a.no_overlap:   # ghost exchange on a third stream, behind the boundary tiles of the density pass
-            cstream = torch.cuda.Stream(device=dev, priority=a.side_stream_priority)
-            eng.set_comm_stream(cstream.cuda_stream)
+    eng = make_engine(lib, host, a, s, gridn, box, local, rank, world, stream)
     sharded = bool(D) and a.sharded_grid and P.grid_slab(gridn[2], rank, world) is not None
+    gstream = cstream = None
     if D:
-        # the engine's own data plane: NCCL communicator (its 128-byte id travels over torch.distributed), ghost map,
-        # and from then on plain post_force / end_of_step do the exchange, the source all-reduce and the grid solve
+        # the engine's own data plane: NCCL communicator (its 128-byte id travels over torch.distributed), then plain
+        # post_force / end_of_step do the ghost exchange, the source all-reduce and the grid solve
         P.attach_comm(eng, D, rank, world)
         eng.set_grid_sharding(sharded)
-        eng.set_ghost_map(plan)
-
-    def step_resident(k):
-        P.distributed_step(eng, d_x, d_v, d_f, k)
+        gstream = torch.cuda.Stream(device=dev)      # source all-reduce + solve overlap the next step's density pass
+        eng.set_grid_stream(gstream.cuda_stream)
+        if a.overlap:
+            cstream = torch.cuda.Stream(device=dev)
+            eng.set_comm_stream(cstream.cuda_stream)
+    md = Verlet(eng, s, plan, D, dev, a, torch)
+    n_nb = float(eng.get_neighbors_count()) / max(nl, 1)
 
     def timed(fn, steps, first):
         """barrier + synchronize on both sides, device time via CUDA events, max over ranks"""
@@ -318,8 +421,9 @@ def run_b200(a):
             ms, wall = float(tt[0]), float(tt[1])
         return ms, wall
 
-    for k in range(a.warmup):
-        step_resident(k)
+    # warm-up steps 1 .. W, timed steps W+1 .. W+K: the re-neighbouring steps (multiples of 10) fall where they fall
+    for k in range(1, a.warmup + 1):
+        md.step(k)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -327,13 +431,16 @@ def run_b200(a):
         time.sleep(0.3)
     eng.set_profiling(True)
     l0 = eng.launch_count()
-    ms, _ = timed(step_resident, a.steps, a.warmup)
+    stats0 = eng.list_stats()
+    ms, _ = timed(md.step, a.steps, a.warmup + 1)
     launches = eng.launch_count() - l0
     ktimes = eng.kernel_times()
     eng.set_profiling(False)
+    stats1 = eng.list_stats()
     clocks = sampler.summary() if rank == 0 else None
     ms_per_step = ms / a.steps
     value = natoms * a.steps / (ms * 1e-3)
+    rebuilds = len([k for k in range(a.warmup + 1, a.warmup + a.steps + 1) if k % REBUILD_EVERY == 0]) if a.mode == "trajectory" else 0
 
     # ---- roofline of the dominant kernel (SURVEY.md 8d per-sweep algorithmic bytes) ----
     peaks = {}
@@ -346,10 +453,7 @@ def run_b200(a):
     # rho sweep 36+4N, w sweep 84+4N, f sweep 180+4N bytes per atom.  density_sweep does the work of the
     # reference's rho AND w sweeps, force_sweep that of its f sweep (friction + random).
     alg = {"density_sweep": (36 + 4 * n_nb) + (84 + 4 * n_nb), "force_sweep": 180 + 4 * n_nb}
-    per_kernel = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in ktimes.items()}
-    if "density_sweep_boundary" in per_kernel and "density_sweep" in per_kernel:
-        # multi-rank overlap: the density pass is two launches (boundary tiles, interior tiles) over the same nl atoms
-        per_kernel["density_sweep"]["ms_avg"] += per_kernel.pop("density_sweep_boundary")["ms_avg"]
+    per_kernel = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1], "ms_per_step": v[0] / a.steps} for k, v in ktimes.items()}
     dom = max((k for k in per_kernel if k in alg), key=lambda k: per_kernel[k]["ms_avg"], default=None)
     roofline = None
     if dom:
@@ -358,9 +462,9 @@ def run_b200(a):
         # DRAM bytes per launch of the same kernel on the same workload from the committed ncu capture (tools/ncu_traffic.py)
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic_4M.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic_4M.json")))
             if tj["atoms"] == nl and dom in tj["kernels"]:
-                traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], "profiles/r1_traffic_4M.json (%s)" % tj["report"]
+                traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], "profiles/r2_traffic_4M.json (%s)" % tj["report"]
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -368,122 +472,274 @@ def run_b200(a):
                     "algorithmic_bytes_per_launch": alg[dom] * nl, "peak_source": peak_src,
                     "algorithmic_bytes_per_atom": alg[dom], "kernel_ms": per_kernel[dom]["ms_avg"],
                     "step": {"algorithmic_bytes_per_atom_step": b_step, "achieved": b_step * value / 1e9 / world,
-                             "frac": b_step * value / 1e9 / world / peak, "note": "whole step, per GPU"},
-                    "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in per_kernel.items()}}
+                             "frac": b_step * value / 1e9 / world / peak, "note": "whole step as timed (incl. integrator hooks and list maintenance), per GPU"},
+                    "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in per_kernel.items()},
+                    "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()}}
+
+    # ---- multi-GPU: the same steps on the whole box on one GPU, atom by atom ----
+    parity = None
+    if D and not a.no_check:
+        parity = check_against_one_gpu(a, torch, dist, lib, host, P, eng, md, s, gridn, box, cells, local, rank, world, dev, stream)
 
     # ---- end to end through the C ABI with pinned host buffers ----
     e2e = None
     if not a.no_e2e:
-        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
-        h_x, h_v = pin(s["x"]), pin(s["v"])
-        h_f = torch.zeros((nl, 3), dtype=torch.float64).pin_memory()
-        h_off, h_neigh = pin(s["offsets"]), pin(s["neigh"])
-        h_type, h_mask, h_tag, h_owner = pin(s["type"]), pin(s["mask"]), pin(s["tag"]), pin(plan.self_owner)
-        nx, nv, nf = h_x.numpy(), h_v.numpy(), h_f.numpy()
+        e2e = run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world)
+        md.register()
 
-        nt = nl + ng
-        rebuilds = len([k for k in range(a.steps) if k % REBUILD_EVERY == 0])
-
-        def run_e2e(device_list):
-            def reneighbor():
-                eng.set_atoms(nl, ng, h_type.numpy(), h_mask.numpy(), h_tag.numpy(), h_owner.numpy())
-                if device_list:
-                    eng.build_neighbors(nx, 7.0)                    # list built on the device from the uploaded positions
-                else:
-                    eng.set_neighbors(h_off.numpy(), h_neigh.numpy())   # LAMMPS' list uploaded
-                if D:
-                    eng.set_ghost_map(plan)
-
-            def step_e2e(k):
-                if k % REBUILD_EVERY == 0:
-                    reneighbor()
-                eng.post_force(nx, nv, nf, None, k)         # x, v, f up (f behind the density pass), ghost exchange, f down
-                return eng.end_of_step(None, nv)            # v up, source all-reduce + solve, E_local down
-
-            reneighbor()
-            for k in range(1, min(a.warmup, 3) + 1):
-                step_e2e(k)
-            ms_dev, ms_wall = timed(step_e2e, a.steps, 0)
-            ms_e = max(ms_dev, ms_wall)
-            topo = nt * (4 + 4 + 8) + ng * 4
-            list_bytes = (topo + (nt * 24 if device_list else h_off.numel() * 8 + h_neigh.numel() * 4)) * rebuilds / a.steps
-            h2d = 2 * nt * 24 + nl * 24 + nl * 24 + list_bytes
-            d2h = nl * 24 + 8
-            return {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
-                    "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps}
-
-        e2e = run_e2e(True)
-        e2e["note"] = ("pinned host x, v, f through the C ABI (HOST memspace): x, v, f up and f, E down every step; every %d steps "
-                       "the atom arrays are re-registered and the neighbour list is rebuilt on the device from the positions "
-                       "(eph_b200_build_neighbors); bytes summed over ranks" % REBUILD_EVERY)
-        e2e["with_uploaded_list"] = run_e2e(False)
-        e2e["with_uploaded_list"]["note"] = "same, but LAMMPS' list (int32 CSR) uploaded every %d steps" % REBUILD_EVERY
-        eng.set_atoms(nl, ng, d_type, d_mask, d_tag, d_owner)
-        eng.set_neighbors(d_off, d_neigh)
-        if D:
-            eng.set_ghost_map(plan)
-
-    # ---- FDM micro-benchmark: Mcell-updates/s of the stencil on a 256^3 grid with 13 sub-steps (TB_Bench fine grid) ----
-    fdm = None
-    if not a.no_fdm_bench and rank == 0 and world == 1:
-        fdm = fdm_bench(lib, host, stream, local, peak)
+    # ---- extras on one GPU: FDM micro-benchmarks, the 4-element configuration, a small box against the reference ----
+    fdm = extras = None
+    if rank == 0 and world == 1:
+        if not a.no_fdm_bench:
+            fdm = fdm_bench(lib, host, stream, local, peak)
+        if not a.no_extras:
+            extras = {"C4_NiCoCrFe": c4_leg(a, torch, lib, host, P, s, gridn, box, local, stream, dev, natoms),
+                      "parity_vs_reference": small_box_check(a, torch, lib, host, local, stream, dev)}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if a.weak else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid), grid_solve="z-slabs + halo planes + all-gather" if sharded else "whole grid on every rank",
-                              exchange_bytes_per_step_rank0=(eng.exchange_bytes if D else 0), list_stats=eng.list_stats()),
+               "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid),
+                              grid_solve="z-slabs + halo planes + all-gather" if sharded else "whole grid on every rank",
+                              exchange_bytes_per_step_rank0=(eng.exchange_bytes if D else 0), records=eng.precision(),
+                              reneighbourings_in_timed_region=rebuilds,
+                              list_stats={k: stats1[k] - stats0[k] for k in stats1}),
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
+        if parity is not None:
+            out["parity_vs_n1"] = parity
+        if extras is not None:
+            out["extras"] = extras
         if not a.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.cpu_steps)
+            rep = CpuReplicas(a.cpu_cells, a.grid, a.dt)
+            out["cpu_baseline"] = rep.sample(a.cpu_steps)
+            rep.close()
         print(json.dumps(out), flush=True)
     if D:
         D.barrier()
         dist.destroy_process_group()
 
 
-def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):
-    import torch
-    L = 56.32 * n / 128.0
-    eng = lib.Engine([0], flags=7, device=local, stream=stream)
-    eng.set_tables_from(host.BetaTables(path=BETA_FILE))
-    eng.set_grid(n, n, n, [0, L, 0, L, 0, L], 300.0, 1.0, 3.5e-6, 0.01248)    # TB_Bench 03_Grid_Fine parameters
-    eng.set_dt(DT)
-    x = np.array([[1.0, 1.0, 1.0]]); z = np.zeros((1, 3))
-    eng.set_atoms(1, 0, np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1], dtype=np.int64))
-    eng.set_neighbors(np.array([0, 0], dtype=np.int64), np.array([0], dtype=np.int32))
-    dx, dv, df = (torch.as_tensor(t, device=torch.device("cuda", local)) for t in (x, z, z.copy()))
-    eng.post_force(dx, dv, df, None, 0)
-    for _ in range(2):
-        eng.end_of_step(dx, dv, want_energy=False)
-    sub = eng.last_substeps()
+def check_against_one_gpu(a, torch, dist, lib, host, P, eng, md, s, gridn, box, cells, local, rank, world, dev, stream, nsteps=3):
+    """`nsteps` further trajectory steps on the bricks, then the same steps from the same state on the WHOLE box on rank
+    0's GPU alone; forces, densities, positions and the grid are compared atom by atom / cell by cell."""
+    natoms = s["natoms"]
+    nl = s["nlocal"]
+    tag0 = md.tag[:nl].long() - 1
+    # state of all atoms before the checked steps, gathered by tag on rank 0
+    def gather(t3):
+        g = torch.zeros((natoms, t3.shape[1]), dtype=torch.float64, device=dev)
+        g[tag0] = t3[:nl]
+        dist.reduce(g, dst=0)
+        return g
+    x0, v0, f0 = gather(md.x), gather(md.v), gather(md.f)
+    T0 = torch.as_tensor(eng.get_grid(0))
+    k0 = 100000
+    for k in range(nsteps):
+        md.step(k0 + 1 + k)       # no re-neighbouring inside (k0 + 1 .. k0 + 3)
+    rho_b = torch.as_tensor(eng.probe(0)[:nl], device=dev).reshape(-1, 1)
+    xb, fb, rb = gather(md.x), gather(md.f), gather(rho_b)
+    Tb = eng.get_grid(0)
+    res = None
+    if rank == 0:
+        from eph_b200 import harness as H
+        w = H.make_system(cells, ntypes=a.elements, with_list=False)
+        order = torch.as_tensor(w["tag"][: w["nlocal"]] - 1, device=dev)
+        w["x"][: w["nlocal"]] = x0[order].cpu().numpy()
+        w["v"][: w["nlocal"]] = v0[order].cpu().numpy()
+        own = w["ghost_owner"]
+        shift = H.make_system.__globals__["np"].zeros(0)
+        plan1 = P.ExchangePlan(w, 0, 1)
+        a1 = argparse.Namespace(**vars(a))
+        e1 = make_engine(lib, host, a1, w, gridn, box, local, 0, 1, stream)
+        e1.put_grid(0, T0.numpy())
+        # ghosts of the whole box: images of its own atoms (positions follow from the unperturbed lattice's shifts)
+        wl = H.make_system(cells, ntypes=a.elements, with_list=False)
+        gshift = wl["x"][wl["nlocal"]:] - wl["x"][own]
+        w["x"][w["nlocal"]:] = w["x"][own] + gshift
+        w["v"][w["nlocal"]:] = w["v"][own]
+        m1 = Verlet(e1, w, plan1, None, dev, a1, torch)
+        m1.f[:] = f0[order]
+        for k in range(nsteps):
+            m1.step(k0 + 1 + k)
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(len(order), device=dev)
+        def dev_rel(b, r):
+            r = r[inv] if r.shape[0] == natoms else r
+            return float((b - r).abs().max() / r.abs().max())
+        rho1 = torch.as_tensor(e1.probe(0)[: w["nlocal"]], device=dev).reshape(-1, 1)
+        T1 = e1.get_grid(0)
+        res = {"steps": nsteps, "max_rel_dev_f": dev_rel(fb, m1.f), "max_rel_dev_rho": dev_rel(rb, rho1),
+               "max_rel_dev_x": dev_rel(xb, m1.x[: w["nlocal"]]), "max_rel_dev_T_e": float(np.abs(Tb - T1).max() / np.abs(T1).max()),
+               "mean_T_e": float(T1.mean()), "sum_abs_f": float(m1.f.abs().sum()),
+               "note": "bricks on %d GPUs (engine's NCCL data plane) against the whole box on one GPU, all atoms and grid cells, "
+                       "after %d trajectory steps from the same state; scaled by the largest magnitude" % (world, nsteps)}
+        res["max_rel_dev"] = max(res["max_rel_dev_f"], res["max_rel_dev_rho"], res["max_rel_dev_x"], res["max_rel_dev_T_e"])
+        e1.close()
+    dist.barrier()
+    return res
+
+
+def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
+    """the same metric through the C ABI with pinned HOST buffers (what FixEPHB200 does with LAMMPS' host arrays):
+    x, v, f up and f, E down every step, atoms registered and the list rebuilt on the device every 10 steps"""
+    nl, ng = s["nlocal"], s["nghost"]
+    nt = nl + ng
+    pin = lambda t: t.cpu().pin_memory()
+    h_x, h_v = pin(md.x), pin(md.v)
+    h_f = torch.zeros((nl, 3), dtype=torch.float64).pin_memory()
+    h_type, h_mask, h_tag, h_owner = pin(md.type), pin(md.mask), pin(md.tag), pin(md.owner)
+    nx, nv, nf = h_x.numpy(), h_v.numpy(), h_f.numpy()
+
+    def reneighbor():
+        eng.set_atoms(nl, ng, h_type.numpy(), h_mask.numpy(), h_tag.numpy(), h_owner.numpy())
+        eng.build_neighbors(nx, CUTOFF)                    # list built on the device from the uploaded positions
+        if D:
+            eng.set_ghost_map(plan)
+
+    def step_e2e(k):
+        if k % REBUILD_EVERY == 0:
+            reneighbor()
+        eng.post_force(nx, nv, nf, None, k)         # x, v, f up (f behind the density pass), ghost exchange, f down
+        return eng.end_of_step(None, nv)            # v up, source all-reduce + solve, E_local down
+
+    reneighbor()
+    for k in range(1, min(a.warmup, 3) + 1):
+        step_e2e(k)
+    ms_dev, ms_wall = timed(step_e2e, a.steps, a.warmup + 1)
+    ms_e = max(ms_dev, ms_wall)
+    rebuilds = len([k for k in range(a.warmup + 1, a.warmup + a.steps + 1) if k % REBUILD_EVERY == 0])
+    topo = nt * (4 + 4 + 8) + ng * 4
+    list_bytes = (topo + nt * 24) * rebuilds / a.steps
+    h2d = 2 * nt * 24 + nl * 24 + nl * 24 + list_bytes
+    d2h = nl * 24 + 8
+    return {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
+            "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps,
+            "note": "pinned host x, v, f through the C ABI (HOST memspace): x, v, f up and f, E down every step; every %d steps "
+                    "the atom arrays are re-registered and the neighbour list is rebuilt on the device from the positions "
+                    "(eph_b200_build_neighbors); post_force + end_of_step (the integrator hooks of FixEPHB200 are host loops "
+                    "in this mode); bytes summed over ranks" % REBUILD_EVERY}
+
+
+def c4_leg(a, torch, lib, host, P, s, gridn, box, local, stream, dev, natoms, steps=10):
+    """config C4 on the same positions and list: four elements (types uniform random), the NiCoCrFe table: two table
+    look-ups per pair and a second pair-weight stream"""
+    a4 = argparse.Namespace(**vars(a))
+    a4.elements = 4
+    s4 = dict(s)
+    s4["ntypes"] = 4
+    s4["type"] = np.random.default_rng(7).integers(1, 5, len(s["type"])).astype(np.int32)
+    s4["type"][s["nlocal"]:] = s4["type"][s["ghost_owner"]]
+    eng = make_engine(lib, host, a4, s4, gridn, box, local, 0, 1, stream, elements=4)
+    md = Verlet(eng, s4, P.ExchangePlan(s4, 0, 1), None, dev, a4, torch)
+    for k in range(1, 4):
+        md.step(k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     eng.set_profiling(True)
     e0.record()
-    for _ in range(solves):
-        eng.end_of_step(dx, dv, want_energy=False)
+    for k in range(4, 4 + steps):
+        md.step(k)
     e1.record()
     torch.cuda.synchronize()
-    kt = eng.kernel_times().get("fdm_substep", (0.0, 1))
-    ms = e0.elapsed_time(e1)
-    cells = n ** 3
-    rate = cells * sub * solves / (ms * 1e-3)
-    k_ms = kt[0] / max(kt[1], 1)
-    ach = 60.0 * cells / (k_ms * 1e-3) / 1e9
+    kt = eng.kernel_times()
+    ms = e0.elapsed_time(e1) / steps
     eng.close()
-    # the grid of this benchmark has constant coefficients, so the engine takes its constant-coefficient TMA kernel, whose
-    # algorithmic traffic is 24 B per cell-update (T_e in/out, dT_e in): that is what `achieved` / `frac` are measured on.
-    # The 60 B per cell-update of the general variable-coefficient path is reported next to it as a
-    # convention only (it exceeds the peak because this kernel does not move those bytes).
-    actual = 24.0 * cells / (k_ms * 1e-3) / 1e9
-    return {"metric": "FDM Mcell-updates/s", "value": rate / 1e6, "unit": "Mcell-updates/s", "grid": [n] * 3, "substeps": sub,
-            "solves": solves, "ms_per_solve": ms / solves,
-            "roofline": {"bound": "hbm", "kernel": "fdm_substep (constant-coefficient TMA path)", "achieved": actual, "peak": peak,
-                         "unit": "GB/s", "frac": actual / peak, "algorithmic_bytes_per_cell_update": 24, "kernel_ms": k_ms,
-                         "survey_convention": {"bytes_per_cell_update": 60, "gbs": ach, "frac": ach / peak,
-                                               "note": "general-path byte count applied to the constant-coefficient kernel"}}}
+    return {"value": natoms / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "kernels_ms": {k: round(v[0] / max(v[1], 1), 4) for k, v in kt.items()},
+            "note": "same box and list, 4 elements (NiCoCrFe_PRB2019), %s mode, one re-neighbouring inside" % a.mode}
+
+
+def small_box_check(a, torch, lib, host, local, stream, dev, cells=16, nsteps=3):
+    """a 16 384-atom box with the PKA through the same engine build, against the unmodified reference fix on the host
+    (oracle/_ref; the oracle port if it is not there): all atoms, forces / densities / grid"""
+    from eph_b200 import harness as H
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import traj
+    s = H.make_system(cells)
+    s["v"][0] = V_PKA * np.array([0.835115, 0.543981, 0.081652])
+    s["v"][s["nlocal"]:][s["ghost_owner"] == 0] = s["v"][0]
+    box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+    xis = [np.random.default_rng(40 + k).normal(size=(s["nlocal"], 3)) for k in range(nsteps)]
+    eng = lib.Engine([0], flags=7, device=local, stream=stream)
+    eng.set_tables_from(host.BetaTables(path=beta_file(1)))
+    eng.set_grid(8, 8, 8, box, 300.0, 1.0, 3.5e-6, 0.1248)
+    eng.set_dt(a.dt)
+    eng.set_skin(2.0)
+    t = lambda arr, dt: torch.as_tensor(np.ascontiguousarray(arr), dtype=dt, device=dev)
+    eng.set_atoms(s["nlocal"], s["nghost"], t(s["type"], torch.int32), t(s["mask"], torch.int32), t(s["tag"], torch.int64),
+                  t(s["ghost_owner"], torch.int32))
+    eng.set_neighbors(t(s["offsets"], torch.int64), t(s["neigh"], torch.int32))
+    recs = traj.run_engine(eng, s, xis, [MASS], a.dt, device=True)
+    from oracle import reference as R
+    if R.available():
+        devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            drv = R.fix_driver(s, H.fix_args(7, beta_file(1), ["Ni"], grid=(8, 8, 8)), dt=a.dt)
+            refs = traj.run_fix_driver(drv, s, xis)
+        finally:
+            os.dup2(saved, 1)
+        kind = "reference (oracle/_ref)"
+    else:
+        from oracle import oracle as O
+        fx = O.Fix(s, O.Beta(path=beta_file(1)), O.FDM(8, 8, 8, box, 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=a.dt)
+        refs = traj.run_oracle(fx, s, xis, [MASS])
+        kind = "oracle port"
+    worst = {}
+    for ra, rb in zip(recs, refs):
+        for key in ("f", "array", "T", "x", "v"):
+            worst[key] = max(worst.get(key, 0.0), H.error_metrics(ra[key], rb[key]))
+    eng.close()
+    return {"atoms": s["nlocal"], "steps": nsteps, "against": kind, "max_rel_dev": max(worst.values()), "by_quantity": worst,
+            "records": "packed from step 2 on (step 1 builds the inner list on the fp64 records)"}
+
+
+def fdm_bench(lib, host, stream, local, peak, n=256, solves=5):
+    """FDM Mcell-updates/s on a 256^3 grid with 13 sub-steps per solve (TB_Bench fine-grid parameters): the
+    constant-coefficient path (the grid `fix eph` creates without a grid file) and the general variable-coefficient path"""
+    import torch
+    L = 56.32 * n / 128.0
+    out = {}
+    for kind in ("uniform", "general"):
+        eng = lib.Engine([0], flags=7, device=local, stream=stream)
+        eng.set_tables_from(host.BetaTables(path=beta_file(1)))
+        kap = 0.01248 if kind == "uniform" else 0.01248 * (0.9 + 0.1 * np.random.default_rng(1).random(n ** 3))
+        eng.set_grid(n, n, n, [0, L, 0, L, 0, L], 300.0, 1.0, 3.5e-6, kap)    # TB_Bench 03_Grid_Fine parameters
+        eng.set_dt(1e-4)
+        x = np.array([[1.0, 1.0, 1.0]]); z = np.zeros((1, 3))
+        eng.set_atoms(1, 0, np.array([1], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1], dtype=np.int64))
+        eng.set_neighbors(np.array([0, 0], dtype=np.int64), np.array([0], dtype=np.int32))
+        dx, dv, df = (torch.as_tensor(t, device=torch.device("cuda", local)) for t in (x, z, z.copy()))
+        eng.post_force(dx, dv, df, None, 0)
+        for _ in range(2):
+            eng.end_of_step(dx, dv, want_energy=False)
+        sub = eng.last_substeps()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        eng.set_profiling(True)
+        e0.record()
+        for _ in range(solves):
+            eng.end_of_step(dx, dv, want_energy=False)
+        e1.record()
+        torch.cuda.synchronize()
+        kt = eng.kernel_times().get("fdm_substep", (0.0, 1))
+        ms = e0.elapsed_time(e1)
+        cells = n ** 3
+        k_ms = kt[0] / max(kt[1], 1)
+        eng.close()
+        # the constant-coefficient kernel moves 24 B per cell-update (T_e in/out, dT_e in), the general one SURVEY's 60 B
+        nbytes = 24.0 if kind == "uniform" else 60.0
+        gbs = nbytes * cells / (k_ms * 1e-3) / 1e9
+        out[kind] = {"value": cells * sub * solves / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s", "substeps": sub, "solves": solves,
+                     "ms_per_solve": ms / solves,
+                     "roofline": {"bound": "hbm", "kernel": "fdm_substep (%s TMA path)" % ("constant-coefficient" if kind == "uniform" else "general"),
+                                  "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "algorithmic_bytes_per_cell_update": nbytes, "kernel_ms": k_ms}}
+    return {"metric": "FDM Mcell-updates/s", "value": out["general"]["value"], "unit": "Mcell-updates/s", "grid": [n] * 3,
+            "general_path": out["general"], "constant_coefficient_path": out["uniform"],
+            "note": "value = the general variable-coefficient path (60 B per cell-update, SURVEY 8d); the constant-coefficient "
+                    "path is what `fix eph ... NX NY NZ NULL` runs"}
 
 
 def main():

@@ -76,4 +76,4 @@ def adaptive_dt_case(kind, make_fix=None):
         mk_our = lambda sy: host.FixDriver(sy, our_args)
     a = traj.run_with_reneighbouring(mk_ref, s, xis, {}, dts=dts)
     b = traj.run_with_reneighbouring(mk_our, s, xis, {}, dts=dts)
-    traj.assert_same_trajectory(a, b, TOL)
+    traj.assert_same_trajectory(a, b, TOL, dts=dts)

@@ -144,7 +144,8 @@ def test_fix_b200_without_gpu_reports_through_lammps_error(sys500, synth_beta_1)
     with pytest.raises(host.FixError, match="non-positive grid"):
         host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], grid=(0, 1, 1)))
     for extra, msg in ((["peratom", -1], "peratom must be >= 0"), (["rng", "mt"], "rng must be mars or philox"),
-                       (["neigh", "host"], "neigh must be device or lammps"), (["comm", "mpi"], "comm must be device or lammps")):
+                       (["neigh", "host"], "neigh must be device or lammps"), (["comm", "mpi"], "comm must be device, lammps or nccl"),
+                       (["grid", "split"], "grid must be replicated or sharded")):
         with pytest.raises(host.FixError, match=msg):
             host.FixDriver(s, H.fix_args(7, synth_beta_1, ["Ni"], style="eph/b200", extra=extra))
     # decks list more element names than atom types (`Ni.beta Ni Ni`): a keyword is found behind any number of extras

@@ -96,107 +96,8 @@ def test_exchange_plan_two_gloo_ranks(cells):
         assert remote > 0 and own > 0     # 2 x 1 x 1 bricks: x-ghosts are remote, y/z images are the rank's own atoms
 
 
-# ---- sharded grid solve: the orchestration of eph_b200.parallel.sharded_grid_solve (slabs, halo planes, all-gather) ----
-class NumpySlabEngine:
-    """Stands in for eph_b200.lib.Engine (same four members the orchestration uses) with a numpy form of the
-    reference's explicit sub-step (eph_fdm.h:319-395, all cells dynamic).  Planes outside the slab are poisoned with
-    NaN in the buffer a sub-step writes, so a missing or misplaced halo plane cannot go unnoticed."""
-
-    def __init__(self, shape, box, c, dt, src):
-        self.grid_shape = shape
-        nx, ny, nz = shape
-        r3 = lambda a: np.asarray(a, dtype=np.float64).reshape(nz, ny, nx).copy()
-        self.T = [torch.as_tensor(r3(c["T"]).reshape(-1)), torch.full((nx * ny * nz,), float("nan"), dtype=torch.float64)]
-        self.cur = 0
-        self.K, self.C, self.rho, self.S, self.src = r3(c["kap"]), r3(c["Ce"]), r3(c["rho"]), r3(c["S"]), r3(src)
-        d = [(box[1] - box[0]) / nx, (box[3] - box[2]) / ny, (box[5] - box[4]) / nz]
-        self.inv = [1.0 / (q * q) for q in d]
-        # sub-step count of the reference (eph_fdm.h:290-313), steps = 1
-        r = dt * sum(self.inv) / self.C.min() / self.rho.min() * self.K.max()
-        self.n = 1
-        if r > 0.4:
-            self.n = max(int(dt / (0.4 * dt / r)), 1)
-        self.inner_dt = dt / self.n
-
-    def grid_plan_substeps(self):
-        return self.n
-
-    def grid_tensor(self, which=0):
-        return self.T[self.cur]
-
-    def grid_substep(self, z0, z1):
-        nx, ny, nz = self.grid_shape
-        Tin = self.T[self.cur].numpy().reshape(nz, ny, nx)
-        Tout = self.T[1 - self.cur].numpy().reshape(nz, ny, nx)
-        Tout[...] = np.nan
-        for k in range(z0, z1):
-            T, kr = Tin[k], self.K[k]
-            dd = np.zeros_like(T)
-            for axis, inv in ((1, self.inv[0]), (0, self.inv[1])):
-                Tq, Tp = np.roll(T, -1, axis), np.roll(T, 1, axis)
-                dd += (np.roll(kr, -1, axis) - np.roll(kr, 1, axis)) * (Tq - Tp) * inv * 0.25
-                dd += kr * ((Tq + Tp - 2.0 * T) * inv)
-            Tq, Tp = Tin[(k + 1) % nz], Tin[(k - 1) % nz]
-            dd += (self.K[(k + 1) % nz] - self.K[(k - 1) % nz]) * (Tq - Tp) * self.inv[2] * 0.25
-            dd += kr * ((Tq + Tp - 2.0 * T) * self.inv[2])
-            Tout[k] = np.maximum(T + (dd + self.src[k] + self.S[k]) / (self.rho[k] * self.C[k]) * self.inner_dt, 0.0)
-        self.cur = 1 - self.cur
-
-
-def _slab_case(shape, seed=71):
-    rng = np.random.default_rng(seed)
-    n = int(np.prod(shape))
-    c = dict(T=300 + 100 * rng.random(n), kap=0.1248 * (0.5 + rng.random(n)), Ce=3.5e-6 * (0.5 + rng.random(n)),
-             S=1e-3 * rng.random(n), rho=1.0 + 0.2 * rng.random(n))
-    return c, 1e-2 * rng.normal(size=n)
-
-
-SLAB_BOX = [0.0, 17.6, -1.0, 16.6, 2.0, 19.6]
-
-
-def _slab_worker(rank, world, port, q, shape, dt):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        c, src = _slab_case(shape)
-        eng = NumpySlabEngine(shape, SLAB_BOX, c, dt, src)
-        n = P.sharded_grid_solve(eng, dist, rank, world)
-        q.put((rank, n, eng.grid_tensor(0).numpy().copy()))
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize("world,shape,dt", [(2, (6, 5, 4), 5e-3), (2, (5, 3, 2), 5e-3), (3, (4, 4, 6), 2e-3), (2, (6, 5, 4), 1e-4)])
-def test_sharded_grid_solve_matches_the_whole_grid_solve(world, shape, dt):
-    """slab sub-steps + halo planes + all-gather over gloo ranks == one rank solving the whole grid == the oracle's
-    EPH_FDM::solve; two ranks exercise the prev == next pairing of the halo exchange, one-plane slabs the wrap"""
-    from oracle import oracle as O
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, q, shape, dt)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(60)
-    c, src = _slab_case(shape)
-    one = NumpySlabEngine(shape, SLAB_BOX, c, dt, src)
-    assert P.sharded_grid_solve(one, None, 0, 1) == one.n
-    whole = one.grid_tensor(0).numpy()
-    o = O.FDM(*shape, SLAB_BOX, 300.0, 3.5e-6, 1.0, 0.1248)
-    for which, key in ((0, "T"), (1, "S"), (2, "rho"), (3, "Ce"), (4, "kap")):
-        o.field(which)[:] = c[key]
-    o.field(5)[:] = src
-    o.set_dt(dt)
-    o.solve()
-    assert H.error_metrics(whole, o.field(0)) < 1e-12
-    for rank, n, T in res:
-        assert n == one.n and (n > 1 or dt < 1e-3)
-        assert np.all(np.isfinite(T)), "rank %d read a plane nobody sent" % rank
-        assert np.array_equal(T, whole), "rank %d" % rank
-
-
+# The sharded grid solve itself (slab sub-steps, halo planes in place, all-gather) is driven by the engine
+# (eph_b200_reduce_and_solve); tests/test_multirank_emulated.py and tests/test_multirank_fix.py run it on 2, 3 and 4 ranks.
 def test_grid_slabs_partition_the_planes():
     assert P.grid_slab(64, 3, 8) == (24, 32) and P.grid_slab(6, 0, 1) == (0, 6)
     assert P.grid_slab(10, 0, 4) is None

@@ -8,13 +8,6 @@
 
 namespace ephb {
 
-// Device-side bookkeeping of the two-level Verlet list (see eph_sweeps.cuh).
-struct ListState {
-  unsigned inner_invalid;   // != 0: the inner list must not be used (some atom moved more than inner_skin/2)
-  unsigned pad;
-  unsigned long long disp0_sq_bits;  // max squared displacement since LAMMPS built its list (double bits, >= 0)
-};
-
 // x, v ([n][3], LAMMPS layout) -> pos4 {x,y,z,bits} and the density-pass record pv {x,y,z,bits | vx,vy,vz,0}
 // (eph_sweeps.cuh); with track != 0 also the displacement check that guards the inner list (against xref, the
 // positions when the inner list was built) and, with track0 != 0 -- only in a step that rebuilds the inner list from

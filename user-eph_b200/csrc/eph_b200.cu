@@ -163,7 +163,7 @@ struct eph_b200_handle {
   // two-level Verlet list: inner list with a small skin, rebuilt on the device from LAMMPS' list
   DevBuf<int> ineigh, icount;
   DevBuf<long long> tile_caps, tile_off;  // warp-tiled layout of the inner list (eph_sweeps.cuh)
-  int lanes = 4;                          // lanes per atom in both sweeps (fixes the tile shape)
+  int lanes = 2;                          // lanes per atom in both sweeps (fixes the tile shape); 2 measured best with packed records
   DevBuf<double4> xref, xref0;          // positions at the last inner build / at LAMMPS' build
   DevBuf<ListState> lstate;
   double skin = -1.0;                    // LAMMPS' neighbor->skin (unknown: inner list only valid from LAMMPS' build)
@@ -1101,7 +1101,7 @@ int launch_density_packed(eph_b200_handle *h, const SweepArgs &a, const char *na
 }
 template <int LANES, bool MULTI, bool FRIC, bool RAND>
 int launch_force_packed(eph_b200_handle *h, const SweepArgs &a) {
-  const int threads = EPH_THREADS_FORCE;
+  const int threads = EPH_THREADS_FORCE_PACKED;
   KernelTimer kt(h, "force_sweep");
   auto k = force_packed_kernel<LANES, MULTI, FRIC, RAND>;
   k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a, packed_args(h));

@@ -43,6 +43,13 @@ __device__ __forceinline__ double2 ld128(const double4 *p) {
 #endif
 }
 
+// Device-side bookkeeping of the two-level Verlet list (see eph_sweeps.cuh).
+struct ListState {
+  unsigned inner_invalid;   // != 0: the inner list must not be used (some atom moved more than inner_skin/2)
+  unsigned pad;
+  unsigned long long disp0_sq_bits;  // max squared displacement since LAMMPS built its list (double bits, >= 0)
+};
+
 // Streams that are read or written exactly once per pass (list indices, pair weights): evict-first hints keep
 // them from displacing the gathered per-atom records in L1/L2.
 __device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }

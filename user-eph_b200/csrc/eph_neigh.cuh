@@ -8,7 +8,7 @@
 namespace ephb {
 
 // Capacity of every warp tile of the inner list (eph_sweeps.cuh): 32 entries per iteration, as many iterations as
-// the longest LAMMPS row of the tile needs (the inner list is a subset of LAMMPS' list), rounded up to an even number.
+// the longest LAMMPS row of the tile needs (the inner list is a subset of LAMMPS' list), rounded up to a multiple of four.
 // caps[ntiles] = 0 closes the scan.
 __global__ void tile_caps_kernel(int nlocal, const long long *__restrict__ offsets, int tile_atoms, int lanes,
                                  int ntiles, long long *__restrict__ caps) {
@@ -20,8 +20,8 @@ __global__ void tile_caps_kernel(int nlocal, const long long *__restrict__ offse
       const int i = w * tile_atoms + a;
       if (i < nlocal) longest = max(longest, offsets[i + 1] - offsets[i]);
     }
-  // an even number of iterations: the packed sweeps pad every list to a whole double iteration (eph_packed.cuh)
-  caps[w] = 32 * (((longest + lanes - 1) / lanes + 1) / 2 * 2);
+  // a multiple of four iterations: the packed sweeps pad every list to whole blocks of up to four (eph_packed.cuh)
+  caps[w] = 32 * (((longest + lanes - 1) / lanes + 3) / 4 * 4);
 }
 
 // Boundary-first ordering of the density pass (multi-rank overlap): tiles that hold an atom some other rank needs as a

@@ -167,6 +167,23 @@ __device__ __forceinline__ int warp_max_int(int v) {
   return v;
 }
 
+// Launch shapes, measured on B200 at 4 M atoms (profiles/r2_force_variants.txt): two list slots in flight per lane in both
+// passes; density 256 threads x 4 CTAs (63 registers), force 256 threads x 3 CTAs (80 registers).
+#ifndef EPH_THREADS_FORCE_PACKED
+#define EPH_THREADS_FORCE_PACKED 256
+#endif
+#ifndef EPH_MINB_FORCE_PACKED
+#define EPH_MINB_FORCE_PACKED 3
+#endif
+#ifndef EPH_FORCE_SLOTS
+#define EPH_FORCE_SLOTS 2
+#endif
+#ifndef EPH_DENSITY_SLOTS
+#define EPH_DENSITY_SLOTS 2
+#endif
+#ifndef EPH_MINB_DENSITY_PACKED
+#define EPH_MINB_DENSITY_PACKED 4
+#endif
 struct PackedArgs {
   const Packed32 *__restrict__ D;   // [ntotal] {position (flags: element index) | v}
   const Packed32 *__restrict__ A;   // [ntotal] {position (flags: bit0 rho > 0, bit1 in group) | u}
@@ -178,13 +195,14 @@ struct PackedArgs {
 
 // The packed sweeps walk the tiles of the inner list with ONE trip count per warp: the step that builds the list pads
 // every atom's slots up to the longest list of its tile (rounded up to two iterations) with the atom's own index and a
-// zero pair weight, so index and weight streams are prefetched without bounds tests and the tail needs no predicates.
+// zero pair weight, so the index and weight streams run ahead without bounds tests and every gather of the (warp-wide)
+// trip count is legal.
 //
 // Density pass on packed records.  When the device-side guard has invalidated the inner list the launch returns at once
 // and the fp64 kernel that follows does the step on LAMMPS' list.  Two list slots per lane are in flight: both records
 // are requested before either is used.
 template <int LANES, bool MULTI, bool FRIC>
-__global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(SweepArgs a, PackedArgs q) {
+__global__ void __launch_bounds__(256, EPH_MINB_DENSITY_PACKED) density_packed_kernel(SweepArgs a, PackedArgs q) {
   if (*a.inner_invalid != 0u) return;
   const RhoTable<0> tab{a.rho_tab4, nullptr, nullptr};
   const int lane = threadIdx.x & 31;
@@ -208,7 +226,9 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
       active = (double_to_bits(q.pos4[i].w) & kBitGroup) != 0u;   // atoms outside the group: rho = 0, w = 0 (fix_eph.cpp:442-445, :704)
       nn = active ? a.icount[i] : 0;
     }
-    const int niter = (warp_max_int(nn) + 2 * LANES - 1) / (2 * LANES);   // double iterations of the whole warp
+    constexpr int S = EPH_DENSITY_SLOTS;   // list slots per lane and iteration: all records are requested before any is used
+    static_assert(kPadIters % S == 0, "the padding of the tiles covers whole iterations only for divisors of kPadIters");
+    const int niter = (warp_max_int(nn) + S * LANES - 1) / (S * LANES);
     const long long first = a.tile_off[(a.work ? i : w) / TILE] + lane;
     const Centre c = make_centre(ri.p);
     const int off_i = MULTI ? (int)packed_flags(ri.p) * a.n_rho : 0;
@@ -217,16 +237,19 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
     const int *__restrict__ lp = a.ineigh + first;
     double *__restrict__ gp = a.gpair + first;
     double *__restrict__ gip = MULTI ? a.gpair_i + first : nullptr;
-    // slots k (this lane) and k + LANES; the tile holds them 32 entries apart
-    unsigned ja = (unsigned)ld_stream(lp), jb = (unsigned)ld_stream(lp + 32);
-    for (int m = 0, k = sub; m < niter; ++m, k += 2 * LANES) {
-      const Packed32 ra = ld_packed32(q.D + ja);
-      const Packed32 rb = ld_packed32(q.D + jb);
-      ja = (unsigned)ld_stream(lp + 64 * (m + 1));
-      jb = (unsigned)ld_stream(lp + 64 * (m + 1) + 32);
+    // slots k, k + LANES, ...; the tile holds them 32 entries apart
+    unsigned jq[S];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const Packed32 &rj = h ? rb : ra;
+    for (int t = 0; t < S; ++t) jq[t] = (unsigned)ld_stream(lp + 32 * t);
+    for (int m = 0, k = sub; m < niter; ++m, k += S * LANES) {
+      Packed32 rq[S];
+#pragma unroll
+      for (int t = 0; t < S; ++t) rq[t] = ld_packed32(q.D + jq[t]);
+#pragma unroll
+      for (int t = 0; t < S; ++t) jq[t] = (unsigned)ld_stream(lp + 32 * (S * (m + 1) + t));
+#pragma unroll
+      for (int h = 0; h < S; ++h) {
+        const Packed32 &rj = rq[h];
         if (k + h * LANES >= nn) break;
         double dx, dy, dz;
         displacement(c, rj.p, dx, dy, dz);
@@ -246,8 +269,8 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
             wx += d * dx; wy += d * dy; wz += d * dz;
           }
         }
-        st_stream(gp + 64 * m + 32 * h, g);
-        if (MULTI) st_stream(gip + 64 * m + 32 * h, gi);
+        st_stream(gp + 32 * (S * m + h), g);
+        if (MULTI) st_stream(gip + 32 * (S * m + h), gi);
       }
     }
     rho = group_sum<LANES>(rho, gmask);
@@ -273,12 +296,8 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_packed_kernel(S
 
 // Force pass on packed records (inner list; the caller launches it only when this step's pair weights are stored in
 // the inner list's tiles -- walk_mode 2, or 1 with the guard intact, which is re-checked here).
-#ifndef EPH_MINB_FORCE_PACKED
-#define EPH_MINB_FORCE_PACKED 6
-#endif
-
 template <int LANES, bool MULTI, bool FRIC, bool RAND>
-__global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE_PACKED) force_packed_kernel(SweepArgs a, PackedArgs q) {
+__global__ void __launch_bounds__(EPH_THREADS_FORCE_PACKED, EPH_MINB_FORCE_PACKED) force_packed_kernel(SweepArgs a, PackedArgs q) {
   if (a.walk_mode == 1 && *a.inner_invalid != 0u) return;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES - 1);
@@ -329,36 +348,44 @@ __global__ void __launch_bounds__(EPH_THREADS_FORCE, EPH_MINB_FORCE_PACKED) forc
         rx += g * dx; ry += g * dy; rz += g * dz;   // fix_eph.cpp:823-826
       }
     };
-    // Per warp and iteration the pass waits for the slowest of 32 gathers (usually one that went to DRAM) and then runs a
-    // long dependent chain of fp64 work; with a single slot in flight the two add up (ncu: issue slots 39 % busy, L1 data
-    // pipe 54 %, nothing saturated).  So the records of one slot are requested while the previous slot is evaluated:
-    // two record buffers used in turn (no copies between them), the index / pair-weight streams one pair of slots ahead.
-    // The padding of the tiles makes every gather of the (even, warp-wide) trip count legal without a test.
-    const int npair = (niter + 1) / 2;
-    unsigned j0 = (unsigned)ld_stream(lp), j1 = (unsigned)ld_stream(lp + 32);
-    double g0 = ld_stream(gp), g1 = ld_stream(gp + 32);
-    double gi0 = MULTI ? ld_stream(gip) : 0.0, gi1 = MULTI ? ld_stream(gip + 32) : 0.0;
-    Packed32 ra = ri, rb = ri;
-    Words16 ba = ri.b, bb = ri.b;
-    if (npair > 0) {
-      ra = ld_packed32(q.A + j0);
-      if (RAND) ba = ld_block16(q.B + j0);
+    // EPH_FORCE_SLOTS list slots per lane and iteration, all their records requested before any is evaluated.  Per warp and
+    // iteration the pass waits for the slowest of its gathers and then runs a long dependent chain of fp64 work; measured
+    // on B200 (profiles/r2_force_variants.txt): one slot in flight 1.53-1.64 ms at 28-32 warps per SM, two slots 1.23 ms
+    // at 24 warps (80 registers), four slots 1.32 ms at 16; register-held software pipelines and deeper index queues
+    // lose to the occupancy they cost.
+    constexpr int S = EPH_FORCE_SLOTS;
+    static_assert(kPadIters % S == 0, "the padding of the tiles covers whole iterations only for divisors of kPadIters");
+    const int nblk = (niter + S - 1) / S;
+    unsigned jq[S];
+    double gq[S], giq[S];
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      jq[t] = (unsigned)ld_stream(lp + 32 * t);
+      gq[t] = ld_stream(gp + 32 * t);
+      giq[t] = MULTI ? ld_stream(gip + 32 * t) : 0.0;
     }
 #pragma unroll 1
-    for (int m = 0; m < npair; ++m) {
-      const int k = sub + 2 * m * LANES;
-      rb = ld_packed32(q.A + j1);                       // slot 2m + 1, evaluated after slot 2m
-      if (RAND) bb = ld_block16(q.B + j1);
-      const double ga = g0, gia = MULTI ? gi0 : g0, gb = g1, gib = MULTI ? gi1 : g1;
-      j0 = (unsigned)ld_stream(lp + 64 * (m + 1)); j1 = (unsigned)ld_stream(lp + 64 * (m + 1) + 32);
-      g0 = ld_stream(gp + 64 * (m + 1)); g1 = ld_stream(gp + 64 * (m + 1) + 32);
-      if (MULTI) { gi0 = ld_stream(gip + 64 * (m + 1)); gi1 = ld_stream(gip + 64 * (m + 1) + 32); }
-      pair_terms(k, ga, gia, ra, ba);
-      if (m + 1 < npair) {                               // slot 2m + 2, evaluated in the next iteration
-        ra = ld_packed32(q.A + j0);
-        if (RAND) ba = ld_block16(q.B + j0);
+    for (int m = 0; m < nblk; ++m) {
+      const int k = sub + S * m * LANES;
+      Packed32 ra[S];
+      Words16 rb[S];
+      double ga[S], gia[S];
+#pragma unroll
+      for (int t = 0; t < S; ++t) {
+        ra[t] = ld_packed32(q.A + jq[t]);
+        rb[t] = ri.b;
+        if (RAND) rb[t] = ld_block16(q.B + jq[t]);
+        ga[t] = gq[t];
+        gia[t] = MULTI ? giq[t] : gq[t];
       }
-      pair_terms(k + LANES, gb, gib, rb, bb);
+#pragma unroll
+      for (int t = 0; t < S; ++t) {
+        jq[t] = (unsigned)ld_stream(lp + 32 * (S * (m + 1) + t));
+        gq[t] = ld_stream(gp + 32 * (S * (m + 1) + t));
+        if (MULTI) giq[t] = ld_stream(gip + 32 * (S * (m + 1) + t));
+      }
+#pragma unroll
+      for (int t = 0; t < S; ++t) pair_terms(k + t * LANES, ga[t], gia[t], ra[t], rb[t]);
     }
     if (FRIC) { fx = group_sum<LANES>(fx, gmask); fy = group_sum<LANES>(fy, gmask); fz = group_sum<LANES>(fz, gmask); }
     if (RAND) { rx = group_sum<LANES>(rx, gmask); ry = group_sum<LANES>(ry, gmask); rz = group_sum<LANES>(rz, gmask); }

@@ -61,6 +61,7 @@ namespace ephb {
 //   density pass: pv[2a] = {x, y, z, bits}, pv[2a+1] = {vx, vy, vz, 0}
 //   force pass:   puz[3a] = {x, y, z, bits}, puz[3a+1] = {ux, uy, uz, zx}, puz[3a+2] = {zy, zz, var, cell}
 //                 (var = eta_factor sqrt(T_e(cell of a)) and the cell index, local atoms only, from prep_coupling)
+constexpr int kPadIters = 4;   // a freshly built tile is padded to a multiple of this many iterations (eph_packed.cuh)
 constexpr int kPvStride = 2;
 constexpr int kPuzStride = 3;
 
@@ -259,13 +260,13 @@ __global__ void __launch_bounds__(256, EPH_MINB_DENSITY) density_sweep_kernel(Sw
     }
     if (BUILD) {
       // Padding for the packed sweeps (eph_packed.cuh), which run ONE trip count per warp and prefetch without bounds
-      // tests: every atom's slots up to the longest list of the tile, rounded up to two iterations, hold the atom's own
+      // tests: every atom's slots up to the longest list of the tile, rounded up to kPadIters iterations, hold the atom's own
       // index and a zero pair weight.
       __syncwarp();
       int tmax = icnt;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xFFFFFFFFu, tmax, o));
-      const int padded = (tmax + 2 * LANES - 1) / (2 * LANES) * (2 * LANES);
+      const int padded = (tmax + kPadIters * LANES - 1) / (kPadIters * LANES) * (kPadIters * LANES);
       const long long t0 = a.tile_off[(a.work ? i : w) / (32 / LANES)] + gshift;
       for (int c = icnt + sub; c < padded; c += LANES) {
         const long long dst = t0 + (long long)(c / LANES) * 32 + (c & (LANES - 1));

@@ -26,6 +26,22 @@ def _hlib():
     return _h
 
 
+def shipped_beta(name):
+    """Path of a shipped parametrisation (tests/golden/data/<name>.beta.gz, e.g. "Ni_PRB2019", "NiCoCrFe_PRB2019"),
+    unpacked once per process into a temporary directory."""
+    import gzip
+    import tempfile
+    cache = shipped_beta.__dict__.setdefault("cache", {})
+    if name not in cache:
+        from ._paths import REPO_ROOT
+        src = os.path.join(REPO_ROOT, "tests", "golden", "data", name + ".beta.gz")
+        dst = os.path.join(tempfile.mkdtemp(prefix="eph_beta_"), name + ".beta")
+        with gzip.open(src, "rb") as f, open(dst, "wb") as g:
+            g.write(f.read())
+        cache[name] = dst
+    return cache[name]
+
+
 def fcc_positions(n, a=NI_A, sigma=0.05, seed=1234, sort_bin=3.5):
     """n^3 fcc unit cells (4 n^3 atoms) in a periodic box of side n*a, with N(0, sigma) displacements,
     wrapped into [0, L) and ordered by spatial bins like LAMMPS' `atom_modify sort`."""
@@ -85,7 +101,7 @@ def neighbor_list(x, nlocal, cut):
 
 
 def make_system(n, a=NI_A, sigma=0.05, T=600.0, r_cut=5.0, skin=2.0, ntypes=1, type_seed=7, group_fraction=None,
-                pos_seed=1234, vel_seed=101, brick=None, mass=NI_MASS):
+                pos_seed=1234, vel_seed=101, brick=None, mass=NI_MASS, with_list=True):
     """A periodic fcc system as one rank of a LAMMPS run would see it.
 
     brick = (rank, (px,py,pz)) cuts the rank's sub-domain out of the global box (spatial decomposition);
@@ -120,7 +136,10 @@ def make_system(n, a=NI_A, sigma=0.05, T=600.0, r_cut=5.0, skin=2.0, ntypes=1, t
     sel = np.concatenate([loc, owner_g])
     glob2loc = np.full(natoms, -1, dtype=np.int64)
     glob2loc[loc] = np.arange(nlocal)
-    offsets, neigh = neighbor_list(x, nlocal, r_cut + skin)
+    if with_list:
+        offsets, neigh = neighbor_list(x, nlocal, r_cut + skin)
+    else:   # the caller builds the list on the device (eph_b200_build_neighbors)
+        offsets, neigh = np.zeros(nlocal + 1, dtype=np.int64), np.zeros(1, dtype=np.int32)
     return dict(n=n, natoms=natoms, box=L, lo=lo, hi=hi, nlocal=nlocal, nghost=nghost, ntypes=ntypes, x=x, v=v,
                 f=np.zeros_like(x), type=np.ascontiguousarray(types_all[sel]), mask=np.ascontiguousarray(mask_all[sel]),
                 tag=np.ascontiguousarray(tags[sel]), ghost_owner=glob2loc[owner_g].astype(np.int32),

@@ -280,6 +280,12 @@ class Engine:
         p = _ptr(x)
         self._check(self.lib.eph_b200_build_neighbors(self.h, p[0], cutoff, p[1]))
 
+    def get_neighbors_count(self):
+        """entries of the full list in use"""
+        n = C.c_longlong()
+        self._check(self.lib.eph_b200_get_neighbors(self.h, None, None, C.byref(n)))
+        return n.value
+
     def get_neighbors(self):
         n = C.c_longlong()
         self._check(self.lib.eph_b200_get_neighbors(self.h, None, None, C.byref(n)))

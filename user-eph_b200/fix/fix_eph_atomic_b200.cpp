@@ -5,6 +5,8 @@
 
 #include <mpi.h>
 
+#include "eph_device_select.h"
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -92,7 +94,7 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
 
   rng_mars = false;
   comm_lammps = nrPS > 1;
-  int device = 0;
+  int device = -1;
   for (int k = n_elem + types; k < narg; ++k) {
     const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "comm") == 0;
     if (!is_keyword) continue;   // an extra element name (the reference's decks list more names than types)
@@ -143,13 +145,19 @@ FixEPHAtomicB200::FixEPHAtomicB200(LAMMPS *lmp, int narg, char **arg)
       array[i][11] = T;
       array[i][1] = eph_b200::CubicTable(beta.beta[type_map_beta[atom->type[i] - 1]])(0.0);   // beta(rho_i = 0), :408
     }
+  // over all ranks like the reference: the energies add up, the temperature is the mean over the ranks that hold atoms of
+  // the group of their local means (fix_eph_atomic.cpp:236-260)
   if (atom_counter > 0) Te /= static_cast<double>(atom_counter);
-  Te /= static_cast<double>(atom_counter > 0 ? 1 : 0);
+  int proc_counter = atom_counter > 0 ? 1 : 0;
+  MPI_Allreduce(MPI_IN_PLACE, &Ee, 1, MPI_DOUBLE, MPI_SUM, world);
+  MPI_Allreduce(MPI_IN_PLACE, &Te, 1, MPI_DOUBLE, MPI_SUM, world);
+  MPI_Allreduce(MPI_IN_PLACE, &proc_counter, 1, MPI_INT, MPI_SUM, world);
+  Te /= static_cast<double>(proc_counter);
 
   // the device engine
   eph_b200_atomic_config cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.device = device;
+  cfg.device = device >= 0 ? device : eph_b200::default_device(myID);   // node-local rank modulo the visible devices
   cfg.ntypes = types;
   cfg.type_map_beta = type_map_beta.data();
   cfg.type_map_kappa = type_map_kappa.data();
