@@ -64,6 +64,7 @@ inline double __longlong_as_double(long long u) { double d; std::memcpy(&d, &u, 
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> inline T __ldcs(const T *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, T v) { *p = v; }

@@ -53,7 +53,7 @@ def compare(recs, refs, nl, keys=("f", "array", "T", "w", "x", "v"), dt=1e-4):
         assert H.error_metrics(a["rho"][:nl], b["rho"][:nl]) < TOL
         # Ee accumulates -(f_EPH + f_RNG) . v dt over atoms and steps: a cancelling sum (the random force heats, the friction
         # cools), so like the forces it is measured against the size of its terms, not against what is left of them
-        e_scale += float(np.abs(b["array"][:, 2:5] * b["v"]).sum() + np.abs(b["array"][:, 5:8] * b["v"]).sum()) * dt
+        e_scale += traj.energy_scale(b, dt)
         assert abs(a["Ee"] - b["Ee"]) <= TOL * max(abs(b["Ee"]), e_scale, 1e-300), (a["Ee"], b["Ee"])
         assert abs(a["Tmean"] - b["Tmean"]) <= TOL * abs(b["Tmean"])
 

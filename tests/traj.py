@@ -6,6 +6,15 @@ final_integrate, ghost v refresh, end_of_step."""
 import numpy as np
 
 
+def energy_scale(rec, dt=1e-4):
+    """Size of the terms of one step's energy transfer, sum_i (|f_EPH_i . v_i| + |f_RNG_i . v_i|) dt.  The cumulative energy
+    `Ee` is a cancelling sum of such terms over atoms and steps (friction cools, the random force heats), so -- like the
+    forces, SURVEY.md 8c -- it is compared against the size of its terms and not against what is left of them.
+    rec: a record with the per-atom output `array` (columns 2..4 f_EPH, 5..7 f_RNG) and the local velocities `v`."""
+    arr, v = np.asarray(rec["array"]), np.asarray(rec["v"])
+    return float(np.abs(arr[:, 2:5] * v).sum() + np.abs(arr[:, 5:8] * v).sum()) * dt
+
+
 class GhostSync:
     def __init__(self, system):
         self.nl = system["nlocal"]
@@ -348,5 +357,5 @@ def assert_same_trajectory(a, b, tol, dts=None):
         # the forces it is measured against the size of its terms; `fix eph` keeps f_EPH, f_RNG in columns 2..7
         if ra["array"].shape[1] == 8:
             dt = 1e-4 if dts is None else dts[step - 1]
-            e_scale += float(np.abs(ra["array"][:, 2:5] * ra["v"]).sum() + np.abs(ra["array"][:, 5:8] * ra["v"]).sum()) * dt
+            e_scale += energy_scale(ra, dt)
         assert abs(ra["Ee"] - rb["Ee"]) <= tol * max(abs(ra["Ee"]), e_scale, 1e-300), (step, "Ee")

@@ -973,8 +973,16 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
   cell_ranges_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, h->nb_cell_s.p, h->nb_atom_s.p, dx, h->nb_xs.p, h->nb_start.p, h->nb_end.p);
   EPH_LAUNCH_CHECK(h);
   EPH_CUDA(h, cudaMemsetAsync(h->nb_counts.p + nl, 0, sizeof(long long), h->stream));
-  neighbor_pass_kernel<false><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
-                                                                          h->nb_counts.p, nullptr, nullptr);
+  // count and fill passes: one CTA per row of cells, candidates staged through shared memory (EPH_B200_NEIGH_KERNEL=atom
+  // selects the per-atom kernels instead)
+  static const bool per_atom = std::getenv("EPH_B200_NEIGH_KERNEL") && std::strcmp(std::getenv("EPH_B200_NEIGH_KERNEL"), "atom") == 0;
+  const int nrows = g.nb[1] * g.nb[2];
+  if (per_atom)
+    neighbor_pass_kernel<false><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                            h->nb_counts.p, nullptr, nullptr);
+  else
+    neighbor_tile_kernel<false><<<nrows, 32 * kNeighWarps, 0, h->stream>>>(nl, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                           h->nb_counts.p, nullptr, nullptr);
   EPH_LAUNCH_CHECK(h);
   EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->nb_counts.p, h->off.p, nl + 1, h->stream));
   ++h->launches;
@@ -982,8 +990,12 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
   EPH_CUDA(h, cudaMemcpyAsync(&total, h->off.p + nl, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
   EPH_CUDA(h, h->neigh.reserve((size_t)std::max<long long>(total, 1)));
-  neighbor_pass_kernel<true><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
-                                                                         nullptr, h->off.p, h->neigh.p);
+  if (per_atom)
+    neighbor_pass_kernel<true><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                           nullptr, h->off.p, h->neigh.p);
+  else
+    neighbor_tile_kernel<true><<<nrows, 32 * kNeighWarps, 0, h->stream>>>(nl, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
+                                                                          nullptr, h->off.p, h->neigh.p);
   EPH_LAUNCH_CHECK(h);
   // hand the device-resident CSR to the common path (aliases our own buffers: no copy)
   return eph_b200_set_neighbors_csr(h, nl, reinterpret_cast<const int64_t *>(h->off.p), h->neigh.p, EPH_B200_DEVICE);
@@ -1233,9 +1245,11 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   const bool track0 = track && build && !h->fresh_neighbors;
   if (track0)
     EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->disp0_sq_bits, 0, sizeof(unsigned long long), h->stream));
-  // packed records serve every step that walks the inner list; a step that builds it (or has none) walks LAMMPS' list
-  // on the fp64 records
-  const bool use_inner = h->inner_enabled && h->have_inner && !build;
+  // packed records serve every step that walks the inner list.  A step that has to (re)build it does that first, with
+  // a kernel of its own, and then runs the packed passes like any other step; with fp64 records the density pass
+  // builds the list while it walks LAMMPS' list.
+  const bool build_first = build && packed_possible(h);
+  const bool use_inner = h->inner_enabled && (build_first || (h->have_inner && !build));
   const bool packed = packed_possible(h) && use_inner;
   h->step_packed = packed;
   {
@@ -1247,12 +1261,27 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
                                                                    packed ? h->recD.p : nullptr, 1.0 / packed_period(h), h->d_status.p);
   }
   EPH_LAUNCH_CHECK(h);
-  if (packed) {   // fp64 records only if the guard just tripped (the kernel returns at once otherwise)
+  SweepArgs a = sweep_args(h);
+  if (build_first) {
+    KernelTimer kt(h, "inner_list_build");
+    const int ntiles = (nl + 32 / h->lanes - 1) / (32 / h->lanes);
+    const int grid = (int)std::min<long long>(blocks_for(ntiles, 8), (long long)h->sm_count * 8);
+    const bool multi = h->n_el > 1;
+    switch (h->lanes) {
+#define EPH_BUILD_CASE(L) case L: if (multi) inner_build_kernel<L, true><<<grid, 256, 0, h->stream>>>(a, h->pos4.p); \
+                                  else inner_build_kernel<L, false><<<grid, 256, 0, h->stream>>>(a, h->pos4.p); break;
+      EPH_BUILD_CASE(1) EPH_BUILD_CASE(2) EPH_BUILD_CASE(8) EPH_BUILD_CASE(16)
+      default: EPH_BUILD_CASE(4)
+#undef EPH_BUILD_CASE
+    }
+    EPH_LAUNCH_CHECK(h);
+    // the list is new: whatever the displacement guard said about the old one no longer applies
+    EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->inner_invalid, 0, sizeof(unsigned), h->stream));
+  } else if (packed) {   // fp64 records only if the guard just tripped (the kernel returns at once otherwise)
     pv_fill_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dv, h->pos4.p, h->pv.p, h->lstate.p);
     EPH_LAUNCH_CHECK(h);
   }
-
-  SweepArgs a = sweep_args(h);
+  const bool build_in_pass = build && !build_first;
   a.use_inner = use_inner ? 1 : 0;
   const int tile_atoms = 32 / h->lanes;
   a.work = nullptr; a.n_work = nl; a.n_boundary = 0; a.done_counter = nullptr;
@@ -1265,18 +1294,18 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
     a.n_boundary = h->n_first * tile_atoms; a.done_counter = h->done_counter.p;
     h->boundary_target += (unsigned)h->n_first;
     h->boundary_by_counter = true;
-    if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build_in_pass, nullptr, packed))) return rc;
   } else if (h->comm_stream && h->split_ready && h->n_first > 0) {
     // no stream memory operations: two launches with an event between them
     a.work = h->work_all.p; a.n_work = h->n_first * tile_atoms;
-    if ((rc = launch_sweep(h, a, 0, build, "density_sweep_boundary", packed))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build_in_pass, "density_sweep_boundary", packed))) return rc;
     EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
     if (h->n_rest > 0) {
       a.work = h->work_all.p + h->n_first; a.n_work = h->n_rest * tile_atoms;
-      if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
+      if ((rc = launch_sweep(h, a, 0, build_in_pass, nullptr, packed))) return rc;
     }
   } else {
-    if ((rc = launch_sweep(h, a, 0, build, nullptr, packed))) return rc;
+    if ((rc = launch_sweep(h, a, 0, build_in_pass, nullptr, packed))) return rc;
     if (h->comm_stream) EPH_CUDA(h, cudaEventRecord(h->ev_boundary, h->stream));
   }
   h->boundary_recorded = h->comm_stream != nullptr;

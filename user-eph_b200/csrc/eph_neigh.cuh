@@ -152,4 +152,96 @@ __global__ void __launch_bounds__(128) neighbor_pass_kernel(int nlocal, const do
   if (!FILL) counts[i] = n;
 }
 
+// The same two passes, cooperatively: one CTA per row of cells (fixed y, z), its warps take chunks of 32 consecutive
+// atoms of the row in cell order.  The atoms of a chunk share one candidate set -- the cells from two left of the
+// chunk's first atom to two right of its last one, in the 25 rows around -- which the warp stages through shared memory
+// 32 positions at a time (one coalesced 1 KB load) and every lane then reads as broadcasts.  The per-atom kernel above
+// gathers ~1000 sectors per atom and pass (25 x 10 cell-range look-ups + ~490 candidates); this one ~75 wavefronts.
+// Neighbours come out in the same order (rows by dz, dy; ascending cell order within a row), so both kernels produce
+// the same list.  Rows of ghost atoms are not built (the list has rows for local atoms only).
+constexpr int kNeighWarps = 4;
+template <bool FILL>
+__global__ void __launch_bounds__(32 * kNeighWarps) neighbor_tile_kernel(int nlocal, CellGrid g, double cut_sq, const double4 *__restrict__ xs,
+                                                                         const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                                         long long *__restrict__ counts, const long long *__restrict__ offsets,
+                                                                         int *__restrict__ neigh) {
+  __shared__ double4 s_cand[kNeighWarps][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int row = blockIdx.x;   // y + nb[1] * z
+  const int ry = row % g.nb[1], rz = row / g.nb[1];
+  // the row's atoms: one contiguous run of the cell-sorted array (empty cells have start = end = 0)
+  int r0 = -1, r1 = -1;
+  for (int c = row * g.nb[0] + lane; c < (row + 1) * g.nb[0]; c += 32) {
+    const int b = cell_start[c], e = cell_end[c];
+    if (e > b) { r0 = (r0 < 0 || b < r0) ? b : r0; r1 = e > r1 ? e : r1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int q0 = __shfl_xor_sync(0xFFFFFFFFu, r0, o), q1 = __shfl_xor_sync(0xFFFFFFFFu, r1, o);
+    r0 = (r0 < 0) ? q0 : ((q0 >= 0 && q0 < r0) ? q0 : r0);
+    r1 = q1 > r1 ? q1 : r1;
+  }
+  if (r0 < 0) return;
+  for (int base = r0 + 32 * wib; base < r1; base += 32 * kNeighWarps) {
+    const int sme = base + lane;
+    const bool have = sme < r1;
+    double4 me = make_double4(0, 0, 0, 0);
+    int id = -1, cx = 0;
+    if (have) {
+      me = xs[sme];
+      id = (int)double_to_bits(me.w);
+      cx = cell_coord(me.x, g.lo[0], g.inv[0], g.nb[0]);
+    }
+    const bool mine = have && id < nlocal;   // ghosts have no row
+    // x-cell range of the chunk (atoms are in cell order: first and last valid lane)
+    const unsigned vmask = __ballot_sync(0xFFFFFFFFu, have);
+    const int cxa = __shfl_sync(0xFFFFFFFFu, cx, 0), cxb = __shfl_sync(0xFFFFFFFFu, cx, 31 - __clz(vmask));
+    const int x0 = max(cxa - 2, 0), x1 = min(cxb + 2, g.nb[0] - 1);
+    long long n = 0;
+    int *out = (FILL && mine) ? neigh + offsets[id] : nullptr;
+    for (int dz = -2; dz <= 2; ++dz) {
+      const int z = rz + dz;
+      if (z < 0 || z >= g.nb[2]) continue;
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int y = ry + dy;
+        if (y < 0 || y >= g.nb[1]) continue;
+        const int crow = (z * g.nb[1] + y) * g.nb[0];
+        // the run of the cells [x0, x1] of that row
+        int s0 = -1, s1 = -1;
+        for (int c = crow + x0 + lane; c <= crow + x1; c += 32) {
+          const int b = cell_start[c], e = cell_end[c];
+          if (e > b) { s0 = (s0 < 0 || b < s0) ? b : s0; s1 = e > s1 ? e : s1; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const int q0 = __shfl_xor_sync(0xFFFFFFFFu, s0, o), q1 = __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+          s0 = (s0 < 0) ? q0 : ((q0 >= 0 && q0 < s0) ? q0 : s0);
+          s1 = q1 > s1 ? q1 : s1;
+        }
+        if (s0 < 0) continue;
+        // per-atom window inside the run: cells [cx - 2, cx + 2] only (what the per-atom kernel walks); outside it the
+        // distance test fails anyway (cells are at least cut-off / 2 wide), so testing the whole run gives the same rows
+        for (int cb = s0; cb < s1; cb += 32) {
+          __syncwarp();
+          if (cb + lane < s1) s_cand[wib][lane] = xs[cb + lane];
+          __syncwarp();
+          const int m = min(32, s1 - cb);
+          if (mine) {
+            for (int c = 0; c < m; ++c) {
+              const double4 p = s_cand[wib][c];
+              const double ddx = p.x - me.x, ddy = p.y - me.y, ddz = p.z - me.z;
+              const int j = (int)double_to_bits(p.w);
+              if (j != id && ddx * ddx + ddy * ddy + ddz * ddz < cut_sq) {
+                if (FILL) out[n] = j;
+                ++n;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (!FILL && mine) counts[id] = n;
+  }
+}
+
 }  // namespace ephb

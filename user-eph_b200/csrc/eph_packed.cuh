@@ -193,6 +193,68 @@ struct PackedArgs {
   double quantum_sq;                // (P / 2^42)^2: squared length of one position quantum
 };
 
+// The inner list on its own, for steps that rebuild it and then run the packed sweeps on it: one WARP per atom walks the
+// atom's row of LAMMPS' list (136 entries at r_c + 2 A: index loads of 128 bytes, one gathered fp64 position per lane),
+// keeps the neighbours closer than r_c + inner_skin in list order (ballot + popc) and writes them into the atom's slots
+// of its tile; a warp does the atoms of one tile in turn so that it can pad all of them to the tile's longest list
+// (see below).  Exact fp64 positions decide membership, like in density_sweep_kernel<BUILD>.
+template <int LANES, bool MULTI>
+__global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const double4 *__restrict__ pos4) {
+  constexpr int TILE = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  const int warps_per_block = blockDim.x >> 5;
+  const int ntiles = (a.nlocal + TILE - 1) / TILE;
+  for (int tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * warps_per_block) {
+    const long long t0 = a.tile_off[tile];
+    int cnt_mine = 0, tmax = 0;   // lane t keeps the list length of the tile's atom t
+    for (int t = 0; t < TILE; ++t) {
+      const int i = tile * TILE + t;
+      int cnt = 0;
+      if (i < a.nlocal) {
+        const double4 pi = pos4[i];
+        if (double_to_bits(pi.w) & kBitGroup) {   // atoms outside the group have no list (their rho and w stay zero)
+          const long long row = a.offsets[i];
+          const int n = static_cast<int>(a.offsets[i + 1] - row);
+          for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            bool in = false;
+            int j = 0;
+            if (k < n) {
+              j = ld_stream(a.neigh + row + k) & kNeighMask;
+              const double4 pj = ld256(pos4 + j);
+              const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+              in = ex * ex + ey * ey + ez * ez < a.r_inner_sq;
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) {
+              const int c = cnt + __popc(bal & below);
+              a.ineigh[t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1))] = j;
+            }
+            cnt += __popc(bal);
+          }
+        }
+        if (lane == 0) a.icount[i] = cnt;
+      }
+      if (lane == t) cnt_mine = cnt;
+      tmax = max(tmax, cnt);
+    }
+    // padding: every atom's slots up to the tile's longest list, rounded up to kPadIters iterations, hold the atom's own
+    // index and a zero pair weight
+    const int padded = (tmax + kPadIters * LANES - 1) / (kPadIters * LANES) * (kPadIters * LANES);
+    for (int t = 0; t < TILE; ++t) {
+      const int i = tile * TILE + t;
+      const int cnt = __shfl_sync(0xFFFFFFFFu, cnt_mine, t);
+      for (int c = cnt + lane; c < padded; c += 32) {
+        const long long dst = t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1));
+        a.ineigh[dst] = i < a.nlocal ? i : 0;
+        st_stream(a.gpair + dst, 0.0);
+        if (MULTI) st_stream(a.gpair_i + dst, 0.0);
+      }
+    }
+  }
+}
+
 // The packed sweeps walk the tiles of the inner list with ONE trip count per warp: the step that builds the list pads
 // every atom's slots up to the longest list of its tile (rounded up to two iterations) with the atom's own index and a
 // zero pair weight, so the index and weight streams run ahead without bounds tests and every gather of the (warp-wide)
