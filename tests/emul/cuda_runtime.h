@@ -37,6 +37,10 @@
 
 struct double2 { double x, y; };
 struct alignas(32) double4 { double x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }

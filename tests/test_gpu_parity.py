@@ -570,6 +570,35 @@ def test_size_independent_properties_at_scale(synth_beta_1):
     assert np.array_equal(arr[:, 0], rho[:nl]) and np.array_equal(arr[:, 2:5], fe) and np.array_equal(arr[:, 5:8], fr)
 
 
+@pytest.mark.parametrize("case", ["Ni_cascade", "NiCoCrFe_partial_group"])
+def test_all_atoms_against_compiled_reference_at_131k_atoms(case, ref):
+    """The unmodified reference fix (oracle/_ref, about half a second per step on the host) and FixEPHB200 on the device
+    on a 131 072-atom box: the shipped parametrisations (Ni_PRB2019: 50 001 beta knots; NiCoCrFe_PRB2019: four elements),
+    the 10 keV primary knock-on atom, a partial fix group, six Verlet steps with one re-neighbouring in the middle (ghosts
+    and list rebuilt from the current positions).  ALL atoms are compared: rho_i, w_i, the per-atom output (rho, beta,
+    f_EPH, f_RNG), f, x, v, and the whole T_e grid, at 1e-10."""
+    from eph_b200 import host
+    s = H.make_system(32, ntypes=4 if case != "Ni_cascade" else 1, group_fraction=None if case == "Ni_cascade" else 0.7)
+    s["v"][0] = 1813.0 * np.array([0.835115, 0.543981, 0.081652])
+    s["v"][s["nlocal"]:][s["ghost_owner"] == 0] = s["v"][0]
+    elems, beta = (["Ni"], H.shipped_beta("Ni_PRB2019")) if case == "Ni_cascade" else (["Ni", "Co", "Cr", "Fe"], H.shipped_beta("NiCoCrFe_PRB2019"))
+    group = "all" if case == "Ni_cascade" else "bit1"
+    dt = 1e-4 if case != "Ni_cascade" else 5.5e-7     # the cascade's adaptive step while the PKA is fast
+    xis = [np.random.default_rng(300 + k).normal(size=(s["nlocal"], 3)) for k in range(6)]
+    ref_args = H.fix_args(7, beta, elems, grid=(16, 16, 16), group=group)
+    # the alloy case lets the engine build the full list itself (`neigh device`: the fill pass also writes the inner list)
+    our_args = H.fix_args(7, beta, elems, grid=(16, 16, 16), group=group, style="eph/b200",
+                          extra=["rng", "mars"] + ([] if case == "Ni_cascade" else ["neigh", "device"]))
+    dts = [dt] * len(xis)
+    a = traj.run_with_reneighbouring(lambda sy: ref.fix_driver(sy, ref_args, dt=dt), s, xis, {3: 7.0}, dts=dts, probes=True)
+    b = traj.run_with_reneighbouring(lambda sy: host.FixDriver(sy, our_args, dt=dt), s, xis, {3: 7.0}, dts=dts, probes=True)
+    traj.assert_same_trajectory(a, b, TOL, dts=dts)
+    for step, (ra, rb) in enumerate(zip(a, b), start=1):
+        for key in ("rho", "w", "grid"):
+            assert H.error_metrics(rb[key], ra[key]) < TOL, (step, key)
+        assert np.abs(ra["array"][:, 2:8]).max() > 0 and np.all(ra["rho"][(np.asarray(s["mask"][: s["nlocal"]]) & (2 if group == "bit1" else 1)) != 0] > 0)
+
+
 def test_full_size_box_properties_and_sampled_parity(ni_trunc_beta):
     """BASELINE's full size (config C3: n = 100, 4 000 000 atoms, 5.4e8 list entries, the bench's .beta file).  The C
     oracle needs minutes per step there, so parity is checked two ways: size-independent properties over all atoms

@@ -310,9 +310,10 @@ def reneighbour(drv, system, shell):
     return s
 
 
-def run_with_reneighbouring(make_driver, system, xis, schedule, dts=None):
+def run_with_reneighbouring(make_driver, system, xis, schedule, dts=None, probes=False):
     """schedule: {step index: ghost shell} -- before that step the ghosts and the list are rebuilt with that shell;
-    dts: time step of every step (LAMMPS' `fix dt/reset`: Fix::reset_dt is called whenever it changes)"""
+    dts: time step of every step (LAMMPS' `fix dt/reset`: Fix::reset_dt is called whenever it changes);
+    probes: also record rho_i (locals), w_i and the whole T_e grid of every step"""
     drv = make_driver(system)
     s = system
     out = []
@@ -342,6 +343,8 @@ def run_with_reneighbouring(make_driver, system, xis, schedule, dts=None):
         x, v, f = drv.xvf()
         out.append(dict(x=x[:nl].copy(), v=v[:nl].copy(), f=f[:nl].copy(), array=drv.array().copy(), Ee=drv.compute_vector(0),
                         T=drv.compute_vector(1), nghost=s["nghost"]))
+        if probes:
+            out[-1].update(rho=drv.probe(0)[:nl].copy(), w=drv.probe(1).copy(), grid=drv.grid_T().copy())
     return out
 
 

@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
 __global__ void __launch_bounds__(256) pv_fill_kernel(int ntotal, const double *__restrict__ v, const double4 *__restrict__ pos4,
                                                       double4 *__restrict__ pv, const ListState *__restrict__ st) {
   if (st->inner_invalid == 0u) return;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= ntotal) return;
-  pv[2 * (size_t)a] = pos4[a];
-  pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < ntotal; a += gridDim.x * blockDim.x) {
+    pv[2 * (size_t)a] = pos4[a];
+    pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
+  }
 }
 
 struct PrepArgs {

@@ -171,6 +171,7 @@ struct eph_b200_handle {
   bool inner_enabled = true;
   bool inner_wanted = true;              // the setting the next set_neighbors applies (set_skin with a list registered)
   bool fresh_neighbors = false;          // set_neighbors since the last post_force
+  bool inner_prebuilt = false;           // eph_b200_build_neighbors filled the inner list's tiles while it wrote the full list
   bool have_inner = false;               // an inner list (and xref) exists
   bool inner_gave_up = false;            // rebuild was refused by the device-side check: use LAMMPS' list until it changes
   bool rebuilt_last_step = false;
@@ -382,6 +383,9 @@ bool packed_possible(const eph_b200_handle *h) {
          packed_period(h) <= 64.0;
 }
 }  // namespace
+
+static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total);
+static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready);
 
 extern "C" {
 
@@ -886,6 +890,30 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
     h->neigh_ptr = h->neigh.p;
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
+  return register_list(h, nlocal, total, false);
+}
+
+}  // extern "C"
+
+// Common tail of the ways a full list reaches the engine: tile storage of the inner list sized from the rows, pair-weight
+// slots, list state.  tiles_ready: eph_b200_build_neighbors has sized the tiles already (and filled them).
+static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready) {
+  if (!tiles_ready) {
+    int rc = prepare_tiles(h, nlocal, total);
+    if (rc) return rc;
+  }
+  EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
+  h->fresh_neighbors = true;
+  h->have_inner = false;
+  h->inner_gave_up = false;
+  h->flag_pending = false;
+  h->inner_prebuilt = tiles_ready && h->inner_enabled;
+  h->n_entries = total;
+  h->neigh_set = true;
+  return EPH_B200_OK;
+}
+
+static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total) {
   h->inner_enabled = h->inner_wanted;
   long long slots = total;   // pair-weight slots: CSR rows of LAMMPS' list or, usually larger, the tiles of the inner list
   if (h->inner_enabled && nlocal > 0) {
@@ -908,15 +936,10 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
   }
   EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(slots, 1)));
   if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(slots, 1)));
-  EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
-  h->fresh_neighbors = true;
-  h->have_inner = false;
-  h->inner_gave_up = false;
-  h->flag_pending = false;
-  h->n_entries = total;
-  h->neigh_set = true;
   return EPH_B200_OK;
 }
+
+extern "C" {
 
 // Builds the full list on the device from the positions: rows of local atoms over all atoms closer than `cutoff`
 // (r_c + skin).  Same pair set as LAMMPS' REQ_FULL list, so the fix need not request (and LAMMPS need not build and
@@ -982,7 +1005,7 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
                                                                             h->nb_counts.p, nullptr, nullptr);
   else
     neighbor_tile_kernel<false><<<nrows, 32 * kNeighWarps, 0, h->stream>>>(nl, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
-                                                                           h->nb_counts.p, nullptr, nullptr);
+                                                                           h->nb_counts.p, nullptr, nullptr, InnerOut{});
   EPH_LAUNCH_CHECK(h);
   EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->nb_counts.p, h->off.p, nl + 1, h->stream));
   ++h->launches;
@@ -993,9 +1016,31 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
   if (per_atom)
     neighbor_pass_kernel<true><<<blocks_for(nl, 128), 128, 0, h->stream>>>(nl, dx, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
                                                                            nullptr, h->off.p, h->neigh.p);
-  else
+  else {
+    // With packed records the step after a re-neighbouring runs on the inner list straight away, so the fill pass also
+    // writes the inner list (same rows, cut at r_c + inner_skin) into its tiles and no second walk of the new list is needed.
+    h->off_ptr = h->off.p;
+    h->neigh_ptr = h->neigh.p;
+    int rc = prepare_tiles(h, nl, total);
+    if (rc) return rc;
+    InnerOut io{};
+    const bool prebuild = h->inner_enabled && packed_possible(h);
+    if (prebuild) {
+      const double r_in = std::sqrt(h->rc2) + h->inner_skin;
+      io.ineigh = h->ineigh.p; io.icount = h->icount.p; io.tile_off = h->tile_off.p; io.mask = h->mask.p;
+      io.groupbit = h->cfg.groupbit; io.r_inner_sq = r_in * r_in; io.lanes = h->lanes;
+    }
     neighbor_tile_kernel<true><<<nrows, 32 * kNeighWarps, 0, h->stream>>>(nl, g, cutoff * cutoff, h->nb_xs.p, h->nb_start.p, h->nb_end.p,
-                                                                          nullptr, h->off.p, h->neigh.p);
+                                                                          nullptr, h->off.p, h->neigh.p, io);
+    EPH_LAUNCH_CHECK(h);
+    if (prebuild) {
+      const int ntiles = (nl + 32 / h->lanes - 1) / (32 / h->lanes);
+      tile_pad_kernel<<<(int)std::min<long long>(blocks_for(ntiles, 8), (long long)h->sm_count * 8), 256, 0, h->stream>>>(
+          nl, h->lanes, h->tile_off.p, h->icount.p, h->ineigh.p, h->gpair.p, h->n_el > 1 ? h->gpair_i.p : nullptr);
+      EPH_LAUNCH_CHECK(h);
+    }
+    return register_list(h, nl, total, prebuild);
+  }
   EPH_LAUNCH_CHECK(h);
   // hand the device-resident CSR to the common path (aliases our own buffers: no copy)
   return eph_b200_set_neighbors_csr(h, nl, reinterpret_cast<const int64_t *>(h->off.p), h->neigh.p, EPH_B200_DEVICE);
@@ -1262,7 +1307,10 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   }
   EPH_LAUNCH_CHECK(h);
   SweepArgs a = sweep_args(h);
-  if (build_first) {
+  if (build_first && h->inner_prebuilt && h->fresh_neighbors) {
+    // eph_b200_build_neighbors wrote the inner list together with the full one
+    EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->inner_invalid, 0, sizeof(unsigned), h->stream));
+  } else if (build_first) {
     KernelTimer kt(h, "inner_list_build");
     const int ntiles = (nl + 32 / h->lanes - 1) / (32 / h->lanes);
     const int grid = (int)std::min<long long>(blocks_for(ntiles, 8), (long long)h->sm_count * 8);
@@ -1278,7 +1326,7 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
     // the list is new: whatever the displacement guard said about the old one no longer applies
     EPH_CUDA(h, cudaMemsetAsync(&h->lstate.p->inner_invalid, 0, sizeof(unsigned), h->stream));
   } else if (packed) {   // fp64 records only if the guard just tripped (the kernel returns at once otherwise)
-    pv_fill_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dv, h->pos4.p, h->pv.p, h->lstate.p);
+    pv_fill_kernel<<<std::min(blocks_for(nt, 256), 8 * h->sm_count), 256, 0, h->stream>>>(nt, dv, h->pos4.p, h->pv.p, h->lstate.p);
     EPH_LAUNCH_CHECK(h);
   }
   const bool build_in_pass = build && !build_first;
@@ -1318,6 +1366,7 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   }
   h->rebuilt_last_step = build && !h->fresh_neighbors;
   h->fresh_neighbors = false;
+  h->inner_prebuilt = false;
   if (dxi) EPH_CUDA(h, cudaMemcpyAsync(h->xi.p, dxi, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   h->pf_build = build;
   h->pf_xi = dxi;

@@ -156,19 +156,38 @@ __global__ void __launch_bounds__(128) neighbor_pass_kernel(int nlocal, const do
 // atoms of the row in cell order.  The atoms of a chunk share one candidate set -- the cells from two left of the
 // chunk's first atom to two right of its last one, in the 25 rows around -- which the warp stages through shared memory
 // 32 positions at a time (one coalesced 1 KB load) and every lane then reads as broadcasts.  The per-atom kernel above
-// gathers ~1000 sectors per atom and pass (25 x 10 cell-range look-ups + ~490 candidates); this one ~75 wavefronts.
-// Neighbours come out in the same order (rows by dz, dy; ascending cell order within a row), so both kernels produce
-// the same list.  Rows of ghost atoms are not built (the list has rows for local atoms only).
+// gathers ~1000 sectors per atom and pass (25 x 10 cell-range look-ups + ~490 candidates); here the memory side is ~75
+// wavefronts per atom and the pair tests themselves (2.4 x as many, the price of the shared candidate set) set the pace,
+// so they run in fp32 on coordinates relative to the chunk (error of r^2 below 3e-4 A^2) and only a pair inside a band
+// of 1e-3 A^2 around a cut-off is decided again in fp64: the lists are exactly those of the fp64 test.
+// Neighbours come out in the same order as from the per-atom kernel (rows by dz, dy; ascending cell order within a
+// row).  Rows of ghost atoms are not built (the list has rows for local atoms only).
+// INNER (fill pass only): the entries closer than r_c + inner_skin also go straight into the atom's slots of the inner
+// list (warp-tiled layout of eph_sweeps.cuh, LANES lanes per atom), so a re-neighbouring needs no second walk of the
+// new list; tile_pad_kernel completes the tiles afterwards.
 constexpr int kNeighWarps = 4;
+struct InnerOut {
+  int *ineigh;                 // nullptr: no inner list
+  int *icount;
+  const long long *tile_off;
+  const int *mask;             // atom->mask; atoms outside the fix group (mask & groupbit == 0) have no inner list
+  int groupbit;
+  double r_inner_sq;
+  int lanes;
+};
 template <bool FILL>
 __global__ void __launch_bounds__(32 * kNeighWarps) neighbor_tile_kernel(int nlocal, CellGrid g, double cut_sq, const double4 *__restrict__ xs,
                                                                          const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                                                                          long long *__restrict__ counts, const long long *__restrict__ offsets,
-                                                                         int *__restrict__ neigh) {
+                                                                         int *__restrict__ neigh, InnerOut io) {
   __shared__ double4 s_cand[kNeighWarps][32];
+  __shared__ float4 s_rel[kNeighWarps][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int row = blockIdx.x;   // y + nb[1] * z
   const int ry = row % g.nb[1], rz = row / g.nb[1];
+  const float band = 1e-3f;
+  const float cut_lo = (float)cut_sq - band, cut_hi = (float)cut_sq + band;
+  const float in_lo = (float)io.r_inner_sq - band, in_hi = (float)io.r_inner_sq + band;
   // the row's atoms: one contiguous run of the cell-sorted array (empty cells have start = end = 0)
   int r0 = -1, r1 = -1;
   for (int c = row * g.nb[0] + lane; c < (row + 1) * g.nb[0]; c += 32) {
@@ -193,12 +212,21 @@ __global__ void __launch_bounds__(32 * kNeighWarps) neighbor_tile_kernel(int nlo
       cx = cell_coord(me.x, g.lo[0], g.inv[0], g.nb[0]);
     }
     const bool mine = have && id < nlocal;   // ghosts have no row
-    // x-cell range of the chunk (atoms are in cell order: first and last valid lane)
+    // x-cell range of the chunk (atoms are in cell order: first and last valid lane) and its origin for the fp32 tests
     const unsigned vmask = __ballot_sync(0xFFFFFFFFu, have);
     const int cxa = __shfl_sync(0xFFFFFFFFu, cx, 0), cxb = __shfl_sync(0xFFFFFFFFu, cx, 31 - __clz(vmask));
+    const double ox = __shfl_sync(0xFFFFFFFFu, me.x, 0), oy = __shfl_sync(0xFFFFFFFFu, me.y, 0), oz = __shfl_sync(0xFFFFFFFFu, me.z, 0);
+    const float mx = (float)(me.x - ox), my = (float)(me.y - oy), mz = (float)(me.z - oz);
     const int x0 = max(cxa - 2, 0), x1 = min(cxb + 2, g.nb[0] - 1);
     long long n = 0;
     int *out = (FILL && mine) ? neigh + offsets[id] : nullptr;
+    const bool inner = FILL && mine && io.ineigh != nullptr && (io.mask[id] & io.groupbit) != 0;
+    int ni = 0;
+    long long it0 = 0;
+    if (inner) {
+      const int tile_atoms = 32 / io.lanes;
+      it0 = io.tile_off[id / tile_atoms] + (long long)(id % tile_atoms) * io.lanes;
+    }
     for (int dz = -2; dz <= 2; ++dz) {
       const int z = rz + dz;
       if (z < 0 || z >= g.nb[2]) continue;
@@ -219,21 +247,39 @@ __global__ void __launch_bounds__(32 * kNeighWarps) neighbor_tile_kernel(int nlo
           s1 = q1 > s1 ? q1 : s1;
         }
         if (s0 < 0) continue;
-        // per-atom window inside the run: cells [cx - 2, cx + 2] only (what the per-atom kernel walks); outside it the
-        // distance test fails anyway (cells are at least cut-off / 2 wide), so testing the whole run gives the same rows
+        // the whole run is tested against every atom of the chunk: outside an atom's own window of cells [cx - 2, cx + 2]
+        // the distance test fails anyway (cells are at least cut-off / 2 wide), so the rows equal the per-atom kernel's
         for (int cb = s0; cb < s1; cb += 32) {
           __syncwarp();
-          if (cb + lane < s1) s_cand[wib][lane] = xs[cb + lane];
+          if (cb + lane < s1) {
+            const double4 p = xs[cb + lane];
+            s_cand[wib][lane] = p;
+            s_rel[wib][lane] = make_float4((float)(p.x - ox), (float)(p.y - oy), (float)(p.z - oz), __int_as_float((int)double_to_bits(p.w)));
+          }
           __syncwarp();
           const int m = min(32, s1 - cb);
           if (mine) {
             for (int c = 0; c < m; ++c) {
-              const double4 p = s_cand[wib][c];
-              const double ddx = p.x - me.x, ddy = p.y - me.y, ddz = p.z - me.z;
-              const int j = (int)double_to_bits(p.w);
-              if (j != id && ddx * ddx + ddy * ddy + ddz * ddz < cut_sq) {
-                if (FILL) out[n] = j;
-                ++n;
+              const float4 q = s_rel[wib][c];
+              const float fx = q.x - mx, fy = q.y - my, fz = q.z - mz;
+              const float d2 = fx * fx + fy * fy + fz * fz;
+              if (d2 >= cut_hi) continue;
+              const int j = __float_as_int(q.w);
+              if (j == id) continue;
+              bool in_cut = d2 < cut_lo, in_inner = d2 < in_lo;
+              if (!in_cut || (!in_inner && d2 < in_hi)) {   // inside a band: the fp64 test decides
+                const double4 p = s_cand[wib][c];
+                const double ddx = p.x - me.x, ddy = p.y - me.y, ddz = p.z - me.z;
+                const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                in_cut = r2 < cut_sq;
+                in_inner = r2 < io.r_inner_sq;
+              }
+              if (!in_cut) continue;
+              if (FILL) out[n] = j;
+              ++n;
+              if (inner && in_inner) {
+                io.ineigh[it0 + (long long)(ni / io.lanes) * 32 + (ni % io.lanes)] = j;
+                ++ni;
               }
             }
           }
@@ -241,6 +287,37 @@ __global__ void __launch_bounds__(32 * kNeighWarps) neighbor_tile_kernel(int nlo
       }
     }
     if (!FILL && mine) counts[id] = n;
+    if (FILL && mine && io.ineigh != nullptr) io.icount[id] = ni;
+  }
+}
+
+// Completes freshly written tiles of the inner list: every atom's slots from its list length up to the longest list of
+// the tile, rounded up to kPadIters iterations, get the atom's own index and a zero pair weight (see eph_packed.cuh).
+// One warp per tile.
+__global__ void __launch_bounds__(256) tile_pad_kernel(int nlocal, int lanes, const long long *__restrict__ tile_off,
+                                                       const int *__restrict__ icount, int *__restrict__ ineigh,
+                                                       double *__restrict__ gpair, double *__restrict__ gpair_i) {
+  const int lane = threadIdx.x & 31;
+  const int tile_atoms = 32 / lanes;
+  const int ntiles = (nlocal + tile_atoms - 1) / tile_atoms;
+  for (int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * (blockDim.x >> 5)) {
+    const int i_mine = tile * tile_atoms + lane;
+    const int cnt_mine = (lane < tile_atoms && i_mine < nlocal) ? icount[i_mine] : 0;
+    int tmax = cnt_mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = max(tmax, __shfl_xor_sync(0xFFFFFFFFu, tmax, o));
+    const int padded = (tmax + 4 * lanes - 1) / (4 * lanes) * (4 * lanes);   // kPadIters = 4 iterations (eph_sweeps.cuh)
+    const long long t0 = tile_off[tile];
+    for (int t = 0; t < tile_atoms; ++t) {
+      const int i = tile * tile_atoms + t;
+      const int cnt = __shfl_sync(0xFFFFFFFFu, cnt_mine, t);
+      for (int c = cnt + lane; c < padded; c += 32) {
+        const long long dst = t0 + (long long)(c / lanes) * 32 + t * lanes + (c % lanes);
+        ineigh[dst] = i < nlocal ? i : 0;
+        gpair[dst] = 0.0;
+        if (gpair_i != nullptr) gpair_i[dst] = 0.0;
+      }
+    }
   }
 }
 
