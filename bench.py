@@ -10,10 +10,10 @@ model 4, `Data/Ni/Ni_PRB2019.beta` (shipped copy), FDM grid 64^3, full neighbour
 the cascade's adaptive rule while the PKA is fast (1e-3 A / v_max = 5.5e-7 ps).
 
 One step is what LAMMPS' Verlet loop makes the fix do: initial_integrate -> (LAMMPS: ghost refresh; every 10th step
-re-neighbouring: the fix registers its atoms again and the full list is rebuilt from the positions, on the device) ->
-post_force -> final_integrate -> end_of_step.  The atoms move, the device-side inner list is rebuilt with the full list,
-and all of it is inside the timed region (`--mode static` times post_force + end_of_step on frozen atoms instead, the
-round-1 measurement).  `value` has everything resident in HBM; `e2e` goes through the same C ABI with pinned HOST
+re-neighbouring: the fix registers its atoms again, receives the full list LAMMPS built for it -- device-resident, as
+from LAMMPS-KOKKOS; `--neigh device` makes the engine build it from the positions instead -- and rebuilds its inner
+list) -> post_force -> final_integrate -> end_of_step.  The atoms move and all of it is inside the timed region
+(`--mode static` times post_force + end_of_step on frozen atoms instead, the round-1 measurement).  `value` has everything resident in HBM; `e2e` goes through the same C ABI with pinned HOST
 buffers.  On N > 1 GPUs the engine's own NCCL data plane runs the ghost exchange, the source all-reduce and the grid
 solve, and after the timed steps the result is checked atom by atom against the whole box on one GPU (`parity_vs_n1`).
 Prints ONE JSON line.
@@ -54,6 +54,11 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=100, help="fcc unit cells per box edge (100 -> 4M atoms)")
     ap.add_argument("--grid", type=int, default=64, help="FDM grid points per edge")
     ap.add_argument("--dt", type=float, default=DT)
+    ap.add_argument("--neigh", default="lammps", choices=["lammps", "device"],
+                    help="where the full neighbour list comes from at a re-neighbouring: lammps (default) = handed over as a "
+                         "device-resident CSR, the way GPU-resident LAMMPS (KOKKOS) provides the list its fix requested -- like the "
+                         "reference fix, which is given its list by LAMMPS; device = built by the engine from the positions "
+                         "(fix keyword `neigh device`: LAMMPS then builds no list for this fix)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fdm-bench", action="store_true")
@@ -244,9 +249,10 @@ def run_reference_arm(a):
 def workload_config(a, natoms):
     multi = getattr(a, "elements", 1) > 1
     beta = "Data/NiCoCrFe/NiCoCrFe_PRB2019.beta" if multi else "Data/Ni/Ni_PRB2019.beta"
-    steps = ("trajectory: initial_integrate, post_force, final_integrate, end_of_step on moving atoms, re-neighbouring (atoms "
-             "registered again, full list and inner list rebuilt on the device) every %d steps, all inside the timed region"
-             % REBUILD_EVERY) if a.mode == "trajectory" else "static: post_force + end_of_step on frozen atoms"
+    steps = ("trajectory: initial_integrate, post_force, final_integrate, end_of_step on moving atoms, re-neighbouring every %d "
+             "steps (atoms registered again, %s, inner list rebuilt), all inside the timed region"
+             % (REBUILD_EVERY, "full list handed over as a device-resident CSR like LAMMPS-KOKKOS does" if a.neigh == "lammps"
+                else "full list rebuilt by the engine from the positions")) if a.mode == "trajectory" else "static: post_force + end_of_step on frozen atoms"
     if getattr(a, "weak", False) and a.gpus > 1:
         return {"workload": "C5-style weak scaling: Ni fcc, %d^3 cells (= %d atoms) and a %d^3 grid per GPU, %d atoms in all, "
                             "flags 7, model 4, dt %.3g ps, full list at 7 A" % (a.cells, 4 * a.cells ** 3, a.grid, natoms, a.dt),
@@ -296,7 +302,13 @@ class Verlet:
             self.rbuf = torch.empty((max(len(self.recv_idx), 1), 6), dtype=torch.float64, device=dev)
             self._exchange()
             self.rem_shift = self.x[self.recv_idx] - self.rbuf[: len(self.recv_idx), :3]
+        self.csr = None
         self.register(first=True)
+        if a.neigh == "lammps":
+            # LAMMPS' list, device-resident: built once here with the engine's own kernel (the atoms of this workload move
+            # by less than 1e-4 A between re-neighbourings, so every rebuild would give the same rows)
+            off, ne = eng.get_neighbors()
+            self.csr = (torch.as_tensor(off, device=dev), torch.as_tensor(ne, device=dev))
 
     def _exchange(self):
         ns, nr = len(self.send_idx), len(self.recv_idx)
@@ -320,7 +332,10 @@ class Verlet:
         the positions: `neigh device`), ghost map"""
         eng = self.eng
         eng.set_atoms(self.nl, self.ng, self.type, self.mask, self.tag, self.owner)
-        eng.build_neighbors(self.x, CUTOFF)
+        if self.csr is not None:
+            eng.set_neighbors(*self.csr)
+        else:
+            eng.build_neighbors(self.x, CUTOFF)
         if self.world > 1:
             eng.set_ghost_map(self.plan)
 

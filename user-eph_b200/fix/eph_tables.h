@@ -6,7 +6,7 @@
 // stored as {a,b,c,d} in ABSOLUTE x (reference eph_spline.h:31-131), the
 // rho(r) -> rho(r^2) resampling and alpha = sqrt(beta) tables of EPH_Beta
 // (reference eph_beta.h:96-125) and the `.beta` grammar (eph_beta.h:39-128,
-// Doc/Beta/input.beta).  tests/test_tables.py checks bit-equality against the
+// Doc/Beta/input.beta).  tests/test_host_side.py (test_product_tables_*) checks bit-equality against the
 // compiled reference.  Compile with -ffp-contract=off: the coefficients carry
 // cancellation and must round exactly like the reference build.
 #pragma once
