@@ -272,8 +272,8 @@ def workload_config(a, natoms):
 class Verlet:
     """Plays LAMMPS' Verlet loop around the fix for one rank, everything on the device: the fix hooks are the engine's
     C-ABI calls, LAMMPS' own part (ghost positions and velocities follow their owners, force_clear, re-neighbouring
-    cadence) is done here with torch.  On several ranks the ghosts owned elsewhere are refreshed by an all-to-all over
-    torch.distributed, like LAMMPS' Comm::forward_comm() with ghost_velocity does."""
+    cadence) is done here; the ghost refresh itself is the engine's eph_b200_refresh_ghosts (what Comm::forward_comm() with
+    ghost_velocity does, for x and v that live on the device; over NCCL between ranks)."""
 
     def __init__(self, eng, s, plan, dist, dev, a, torch):
         self.eng, self.s, self.plan, self.dist, self.torch, self.a = eng, s, plan, dist, torch, a
@@ -286,22 +286,7 @@ class Verlet:
         self.owner = t(plan.self_owner, torch.int32)
         self.mass = np.array([0.0] + [MASS] * s["ntypes"])
         self.dtv, self.dtf = a.dt, 0.5 * a.dt * FTM2V
-        # ghosts that are images of this rank's own atoms: position = owner + shift
-        own = np.nonzero(plan.self_owner >= 0)[0]
-        self.own_g = t(nl + own, torch.long)
-        self.own_o = t(plan.self_owner[own], torch.long)
-        self.own_shift = self.x[self.own_g] - self.x[self.own_o]
-        # ghosts owned by other ranks: x, v of my atoms they hold go out, theirs come in (set-up: the shifts)
         self.world = dist.get_world_size() if dist else 1
-        if self.world > 1:
-            self.send_idx = t(plan.flat_send_index(), torch.long)
-            self.recv_idx = t(plan.flat_recv_index(), torch.long)
-            self.out_splits = [6 * c for c in plan.send_counts]
-            self.in_splits = [6 * c for c in plan.recv_counts]
-            self.sbuf = torch.empty((max(len(self.send_idx), 1), 6), dtype=torch.float64, device=dev)
-            self.rbuf = torch.empty((max(len(self.recv_idx), 1), 6), dtype=torch.float64, device=dev)
-            self._exchange()
-            self.rem_shift = self.x[self.recv_idx] - self.rbuf[: len(self.recv_idx), :3]
         self.csr = None
         self.register(first=True)
         if a.neigh == "lammps":
@@ -310,22 +295,10 @@ class Verlet:
             off, ne = eng.get_neighbors()
             self.csr = (torch.as_tensor(off, device=dev), torch.as_tensor(ne, device=dev))
 
-    def _exchange(self):
-        ns, nr = len(self.send_idx), len(self.recv_idx)
-        self.sbuf[:ns, :3] = self.x[self.send_idx]
-        self.sbuf[:ns, 3:] = self.v[self.send_idx]
-        self.dist.all_to_all_single(self.rbuf.view(-1)[: 6 * nr], self.sbuf.view(-1)[: 6 * ns], output_split_sizes=self.in_splits,
-                                    input_split_sizes=self.out_splits)
-
     def refresh_ghosts(self):
-        """LAMMPS' forward comm of x and v (comm->ghost_velocity is set by the fix, fix_eph.cpp:82)"""
-        self.x[self.own_g] = self.x[self.own_o] + self.own_shift
-        self.v[self.own_g] = self.v[self.own_o]
-        if self.world > 1:
-            self._exchange()
-            nr = len(self.recv_idx)
-            self.x[self.recv_idx] = self.rbuf[:nr, :3] + self.rem_shift
-            self.v[self.recv_idx] = self.rbuf[:nr, 3:]
+        """LAMMPS' forward comm of x and v (comm->ghost_velocity is set by the fix, fix_eph.cpp:82), on the device: images of
+        the rank's own atoms are shifted copies, ghosts owned by other ranks arrive over the engine's NCCL ghost map"""
+        self.eng.refresh_ghosts(self.x, self.v)
 
     def register(self, first=False):
         """what FixEPHB200::upload_topology does when LAMMPS has re-neighboured: atoms, full list (built on the device from
@@ -338,6 +311,7 @@ class Verlet:
             eng.build_neighbors(self.x, CUTOFF)
         if self.world > 1:
             eng.set_ghost_map(self.plan)
+        eng.refresh_ghosts(self.x, self.v)     # first call after set_atoms: records the image shifts of the fresh ghosts
 
     def step(self, k):
         eng = self.eng
@@ -628,8 +602,40 @@ def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
     list_bytes = (topo + nt * 24) * rebuilds / a.steps
     h2d = 2 * nt * 24 + nl * 24 + nl * 24 + list_bytes
     d2h = nl * 24 + 8
+    # ---- the same through the device-resident integration mode (fix keyword `integrate device`): x, v, f stay on the
+    # device between the hooks; per step the pair forces go up, x, f and v come down; all four hooks are inside ----
+    resident = None
+    if world == 1:
+        mass = np.array([0.0] + [MASS] * s["ntypes"])
+        dtv, dtf = a.dt, 0.5 * a.dt * FTM2V
+        nxl, nvl = nx[:nl], nv[:nl]
+
+        def reneighbor_res():
+            reneighbor()
+            eng.resident_upload(nx, nv)
+
+        def step_res(k):
+            eng.resident_initial_integrate(nf, mass, dtv, dtf, nxl)      # x down
+            if k % REBUILD_EVERY == 0:
+                nvl[...] = eng.resident_get(1)                           # LAMMPS re-neighbours from its host arrays: v down too
+                reneighbor_res()
+            eng.resident_post_force(nf, None, k)                         # pair forces up, total forces down
+            eng.resident_final_integrate(mass, dtf, nvl)                 # v down
+            return eng.resident_end_of_step(True)                        # E_local down
+
+        reneighbor_res()
+        for k in range(1, min(a.warmup, 3) + 1):
+            step_res(k)
+        r_dev, r_wall = timed(step_res, a.steps, a.warmup + 1)
+        ms_r = max(r_dev, r_wall)
+        resident = {"value": natoms * a.steps / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r / a.steps,
+                    "h2d_bytes_per_step": int(nl * 24 + (topo + 2 * nt * 24 + nt * 24) * rebuilds / a.steps),
+                    "d2h_bytes_per_step": int(3 * nl * 24 + 8 + nl * 24 * rebuilds / a.steps),
+                    "note": "device-resident integration (eph_b200_resident_*; FixEPHB200 keyword `integrate device`): all four "
+                            "hooks, x / v / f stay on the device; per step f up, x, f, v down; every %d steps v down once more, "
+                            "atoms registered, list rebuilt on the device, x and v uploaded" % REBUILD_EVERY}
     return {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
-            "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps,
+            "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps, "resident_mode": resident,
             "note": "pinned host x, v, f through the C ABI (HOST memspace): x, v, f up and f, E down every step; every %d steps "
                     "the atom arrays are re-registered and the neighbour list is rebuilt on the device from the positions "
                     "(eph_b200_build_neighbors); post_force + end_of_step (the integrator hooks of FixEPHB200 are host loops "

@@ -272,6 +272,34 @@ int eph_b200_initial_integrate(eph_b200_handle *h, double *x, double *v, const d
 int eph_b200_final_integrate(eph_b200_handle *h, double *v, const double *f, const double *mass_by_type, double dtf,
                              int memspace);
 
+/* Ghost atoms following their owners on the device: what LAMMPS' Comm::forward_comm() does for x and v (the fix sets
+ * comm->ghost_velocity, fix_eph.cpp:82) when those arrays live on the GPU.  Images of the rank's own atoms are shifted
+ * copies (set_atoms' ghost_owner >= 0); ghosts owned by other ranks arrive over the NCCL ghost map.  The first call after
+ * set_atoms, while the ghost coordinates are still LAMMPS' own, records the image shifts; later calls apply them.
+ * x, v: DEVICE arrays [nlocal + nghost][3]. */
+int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v);
+
+/* Device-resident integration (replaces the host round trips around FixEPH::initial_integrate /
+ * post_force / final_integrate / end_of_step, fix_eph.cpp:305-429, when LAMMPS' own arrays are host arrays).  The engine
+ * keeps x, v of all atoms and f of the local ones between the hooks.  Per step only the pair forces go up; x (after the
+ * drift: the pair style and the neighbour check need it), f (after post_force) and v (after the second kick, optional)
+ * come down.  Valid while this fix is the integrator of all atoms it is given and the last fix to change f.
+ *   resident_upload             after every set_atoms (re-neighbouring): x, v [nlocal + nghost][3] from the host once
+ *   resident_initial_integrate  kick + drift on the device with the forces of the last resident_post_force (f: host
+ *                               forces for the very first step, else may be NULL); ghosts follow; x_out <- x[nlocal][3]
+ *   resident_post_force         f: host forces of the other contributors in, the same plus f_EPH (+ f_RNG) out
+ *   resident_final_integrate    second kick; v_out <- v[nlocal][3] (NULL: not needed on the host this step)
+ *   resident_end_of_step        end_of_step on the resident velocities */
+int eph_b200_resident_upload(eph_b200_handle *h, const double *x, const double *v);
+int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf,
+                                        double *x_out);
+int eph_b200_resident_post_force(eph_b200_handle *h, double *f, const double *xi_inject, long long ntimestep);
+int eph_b200_resident_final_integrate(eph_b200_handle *h, const double *mass_by_type, double dtf, double *v_out);
+int eph_b200_resident_end_of_step(eph_b200_handle *h, double *E_local);
+/* which: 0 x, 1 v, 2 f of the local atoms -> HOST out [nlocal][3] (e.g. v after the first kick on a step in which LAMMPS
+ * re-neighbours: it migrates and re-orders the atoms from its host arrays) */
+int eph_b200_resident_get(eph_b200_handle *h, int which, double *out);
+
 /* FixEPH::array (fix_eph.cpp:406-428): [nlocal][8] = rho, beta(rho), f_EPH xyz, f_RNG xyz */
 int eph_b200_get_peratom(eph_b200_handle *h, double *array8, int memspace);
 /* probes for parity tests; LAMMPS order.

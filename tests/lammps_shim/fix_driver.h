@@ -300,6 +300,12 @@ int world_permute(World<FixT> *w, const int *new_of_old) {
     return shim_driver::guarded(w, [&] { w->lmp.update->dt = dt; w->fix->reset_dt(); });                       \
   }                                                                                                            \
   void P##_set_step(void *w, long long step) { static_cast<P##_world *>(w)->lmp.update->ntimestep = step; }    \
+  /* Neighbor::decide() of a step without re-neighbouring: the list ages */                                    \
+  void P##_neigh_tick(void *w_) { ++static_cast<P##_world *>(w_)->lmp.neighbor->ago; }                         \
+  void P##_neigh_modify(void *w_, int every, int delay, int check) {                                           \
+    auto *w = static_cast<P##_world *>(w_);                                                                    \
+    w->lmp.neighbor->every = every; w->lmp.neighbor->delay = delay; w->lmp.neighbor->dist_check = check;       \
+  }                                                                                                            \
   int P##_initial_integrate(void *w_) {                                                                        \
     auto *w = static_cast<P##_world *>(w_);                                                                    \
     return shim_driver::guarded(w, [&] { w->fix->initial_integrate(0); });                                     \

@@ -144,6 +144,7 @@ class Neighbor {
   NeighRequest last_request;
   double skin = 2.0;
   int ago = 0;
+  int every = 1, delay = 0, dist_check = 1;   // neigh_modify every / delay / check (LAMMPS defaults: 1, 0, yes)
   NeighRequest *add_request(Fix *, int style) {
     last_request.style = style;
     return &last_request;

@@ -77,3 +77,20 @@ def adaptive_dt_case(kind, make_fix=None):
     a = traj.run_with_reneighbouring(mk_ref, s, xis, {}, dts=dts)
     b = traj.run_with_reneighbouring(mk_our, s, xis, {}, dts=dts)
     traj.assert_same_trajectory(a, b, TOL, dts=dts)
+
+
+def resident_case(cells=3, steps=7, every=3):
+    """`integrate device`: x, v, f stay on the device between the hooks; FixEPHB200 in that mode continues exactly like the
+    reference fix through re-neighbourings that happen, as in LAMMPS, between initial_integrate and post_force"""
+    from oracle import reference as R
+    if not R.available():
+        pytest.skip("compiled reference not present")
+    s = H.make_system(cells, skin=2.0)
+    s["v"][0] = 300.0 * np.array([0.835115, 0.543981, 0.081652])     # one fast atom
+    s["v"][s["nlocal"]:][s["ghost_owner"] == 0] = s["v"][0]
+    xis = [np.random.default_rng(120 + k).normal(size=(s["nlocal"], 3)) for k in range(steps)]
+    ref_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2))
+    our_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2), style="eph/b200", extra=["rng", "mars", "integrate", "device"])
+    a = traj.run_in_lammps_order(lambda sy: R.fix_driver(sy, ref_args), s, xis, every)
+    b = traj.run_in_lammps_order(lambda sy: host.FixDriver(sy, our_args, neigh_modify=(every, 0, False)), s, xis, every)
+    traj.assert_same_trajectory(a, b, TOL)

@@ -238,6 +238,12 @@ def test_emulated_engine_device_memspace(sys500, synth_beta_1, flags):
         assert abs(Ee - ref["Ee"]) <= G.TOL * max(abs(ref["Ee"]), e_scale, 1e-300)
 
 
+def test_emulated_fix_integrate_device_matches_reference(emulated_engine):
+    """keyword `integrate device`: the velocity-Verlet half steps run on the device and x, v, f stay there between the hooks"""
+    import reneighbour_cases
+    reneighbour_cases.resident_case()
+
+
 def test_simt_stand_in_selftest():
     """the lock-step stand-in itself: closed-form results for block barriers with early-exiting threads, sub-warp
     shuffles with different trip counts per group, ballots, 3-D launches and dynamic shared memory -- and a collective

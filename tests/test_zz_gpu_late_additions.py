@@ -167,3 +167,11 @@ def test_sharded_grid_solve_matches_replicated_solve_and_oracle(synth_beta_1, sh
                 assert np.array_equal(e.get_grid(0), whole), "rank %d of %d" % (r, world)
                 assert np.all(e.get_grid(5) == 0.0)
     assert engs[0].last_substeps() > 1
+
+
+def test_fix_integrate_device_matches_reference():
+    """keyword `integrate device` of FixEPHB200: the velocity-Verlet half steps run on the device, x, v, f stay there between
+    the hooks; against the compiled reference fix through re-neighbourings in LAMMPS' order (between initial_integrate and
+    post_force)"""
+    import reneighbour_cases
+    reneighbour_cases.resident_case(cells=6, steps=8, every=3)

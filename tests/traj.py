@@ -362,3 +362,39 @@ def assert_same_trajectory(a, b, tol, dts=None):
             dt = 1e-4 if dts is None else dts[step - 1]
             e_scale += energy_scale(ra, dt)
         assert abs(ra["Ee"] - rb["Ee"]) <= tol * max(abs(ra["Ee"]), e_scale, 1e-300), (step, "Ee")
+
+
+def run_in_lammps_order(make_driver, system, xis, every, shell=7.0):
+    """The Verlet loop in LAMMPS' own order -- initial_integrate, THEN (every `every`-th step) re-neighbouring from the host
+    arrays, else the list ages and the ghosts are refreshed, post_force, final_integrate, end_of_step -- which is what a
+    fix that keeps x, v, f on the device between the hooks (`integrate device`) has to cope with: LAMMPS migrates and
+    re-orders atoms from its host arrays in the middle of a step."""
+    drv = make_driver(system)     # (built with neigh_modify=(every, 0, False))
+    s = system
+    out = []
+    for k, xi in enumerate(xis, start=1):
+        nl = s["nlocal"]
+        drv.set_step(k)
+        drv.initial_integrate()     # first kick with last step's total force (zero before the first step), as in LAMMPS
+        if k % every == 0:
+            s = reneighbour(drv, s, shell)
+        else:
+            drv.neigh_tick()
+            x, v, f = drv.xvf()
+            GhostSync(s)(x, v)
+            drv.update(x=x, v=v)
+        x, v, f = drv.xvf()
+        f[:] = 0.0
+        drv.update(f=f)
+        if xi is not None:
+            drv.set_xi(xi)
+        drv.post_force()
+        drv.final_integrate()
+        x, v, f = drv.xvf()
+        GhostSync(s)(x, v)
+        drv.update(v=v)
+        drv.end_of_step()
+        x, v, f = drv.xvf()
+        out.append(dict(x=x[:nl].copy(), v=v[:nl].copy(), f=f[:nl].copy(), array=drv.array().copy(), Ee=drv.compute_vector(0),
+                        T=drv.compute_vector(1), nghost=s["nghost"]))
+    return out

@@ -142,6 +142,14 @@ struct eph_b200_handle {
   DevBuf<int> gm_send_idx, gm_recv_slot;                    // concatenated over the peers, in peer order
   int gm_nsend = 0, gm_nrecv = 0;
   DevBuf<double> gm_send_buf, gm_recv_buf, gm_send_xi, gm_recv_xi;   // {rho, Wx, Wy, Wz} per atom; xi only when injected
+  // ghost positions and velocities following their owners on the device (eph_b200_refresh_ghosts): shifts recorded at
+  // the first call after set_atoms, when the caller's ghost coordinates are LAMMPS' own
+  DevBuf<double> gshift;        // [nghost][3] x_ghost - x_owner
+  bool gshift_valid = false;
+  DevBuf<double> gm_send_xv, gm_recv_xv;   // {x, v} of the atoms other ranks hold as ghosts
+  // device-resident integration (eph_b200_resident_*): x, v of all atoms and f of the local ones stay here between hooks
+  DevBuf<double> res_x, res_v, res_f;
+  bool resident = false, res_f_valid = false;
   bool grid_sharded = false;    // every rank advances only its z-slab of the grid (halo planes + all-gather)
   DevBuf<double> slab_tmp;
 
@@ -490,6 +498,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   h->gm_send_idx.release(); h->gm_recv_slot.release(); h->gm_send_buf.release(); h->gm_recv_buf.release();
   h->gm_send_xi.release(); h->gm_recv_xi.release(); h->slab_tmp.release();
+  h->gshift.release(); h->gm_send_xv.release(); h->gm_recv_xv.release(); h->res_x.release(); h->res_v.release(); h->res_f.release();
   h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -862,6 +871,8 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   h->peratom_valid = false;
   h->split_ready = false;   // the boundary work lists name atoms of the previous registration
   h->ghost_map_set = false; // ... and so does the ghost map
+  h->gshift_valid = false;
+  h->resident = false; h->res_f_valid = false;
   h->neigh_set = false;
   h->forces_valid = false;
   return EPH_B200_OK;
@@ -2223,6 +2234,214 @@ int eph_b200_reduce_and_solve(eph_b200_handle *h, double *E_local) {
     EPH_NCCL(h, api.AllGather(T + (size_t)z0 * plane, T, (size_t)(z1 - z0) * plane, kNcclFloat64, h->comm, st));   // in place
   }
   return end_of_step_finish(h, E_local, false);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Ghost atoms following their owners on the device, and device-resident integration
+// ---------------------------------------------------------------------------
+namespace {
+
+// own periodic images: x_ghost = x_owner + shift, v_ghost = v_owner; record = 1 stores the shifts instead
+__global__ void ghost_images_kernel(int nlocal, int nghost, const int *__restrict__ owner, double *__restrict__ x, double *__restrict__ v,
+                                    double *__restrict__ shift, int record) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const int o = owner[g];
+  if (o < 0) return;   // owned by another rank: filled from the exchange
+  const size_t a = 3 * (size_t)(nlocal + g), b = 3 * (size_t)o, c = 3 * (size_t)g;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (record) shift[c + d] = x[a + d] - x[b + d];
+    else { x[a + d] = x[b + d] + shift[c + d]; v[a + d] = v[b + d]; }
+  }
+}
+__global__ void pack_xv_kernel(int n, const int *__restrict__ index, const double *__restrict__ x, const double *__restrict__ v, double *__restrict__ buf) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const size_t a = 3 * (size_t)index[t];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { buf[6 * (size_t)t + d] = x[a + d]; buf[6 * (size_t)t + 3 + d] = v[a + d]; }
+}
+__global__ void unpack_xv_kernel(int n, const int *__restrict__ slot, int nlocal, double *__restrict__ x, double *__restrict__ v, const double *__restrict__ buf,
+                                 double *__restrict__ shift, int record) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const size_t a = 3 * (size_t)slot[t], c = 3 * (size_t)(slot[t] - nlocal);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (record) shift[c + d] = x[a + d] - buf[6 * (size_t)t + d];
+    else { x[a + d] = buf[6 * (size_t)t + d] + shift[c + d]; v[a + d] = buf[6 * (size_t)t + 3 + d]; }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// What LAMMPS' Comm::forward_comm() does for positions and velocities (comm->ghost_velocity, fix_eph.cpp:82), for callers
+// whose x and v live on the device: images of this rank's own atoms are shifted copies, ghosts owned by other ranks
+// arrive over the engine's NCCL ghost map.  The first call after set_atoms (when the ghost coordinates are still the
+// ones LAMMPS produced) records the image shifts, later calls apply them.  x, v: DEVICE arrays [nlocal + nghost][3].
+int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: set_atoms not called");
+  if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: null x or v");
+  const int nl = h->nlocal, ng = h->nghost;
+  if (ng == 0) return EPH_B200_OK;
+  if (!h->has_owner) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: set_atoms was given no ghost owners");
+  const bool remote = h->comm && h->comm_size > 1;
+  if (remote && !h->ghost_map_set) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: eph_b200_set_ghost_map must follow every set_atoms");
+  cudaSetDevice(h->cfg.device);
+  const int record = h->gshift_valid ? 0 : 1;
+  EPH_CUDA(h, h->gshift.reserve(3 * (size_t)ng));
+  if (remote && (h->gm_nsend || h->gm_nrecv)) {
+    NcclApi &api = nccl_api();
+    EPH_CUDA(h, h->gm_send_xv.reserve(6 * std::max<size_t>(h->gm_nsend, 1))); EPH_CUDA(h, h->gm_recv_xv.reserve(6 * std::max<size_t>(h->gm_nrecv, 1)));
+    if (h->gm_nsend) {
+      pack_xv_kernel<<<blocks_for(h->gm_nsend, 256), 256, 0, h->stream>>>(h->gm_nsend, h->gm_send_idx.p, x, v, h->gm_send_xv.p);
+      EPH_LAUNCH_CHECK(h);
+    }
+    EPH_NCCL(h, api.GroupStart());
+    size_t so = 0, ro = 0;
+    for (size_t p = 0; p < h->gm_peer.size(); ++p) {
+      const size_t sc = h->gm_send_count[p], rcn = h->gm_recv_count[p];
+      if (sc) EPH_NCCL(h, api.Send(h->gm_send_xv.p + 6 * so, 6 * sc, kNcclFloat64, h->gm_peer[p], h->comm, h->stream));
+      if (rcn) EPH_NCCL(h, api.Recv(h->gm_recv_xv.p + 6 * ro, 6 * rcn, kNcclFloat64, h->gm_peer[p], h->comm, h->stream));
+      so += sc; ro += rcn;
+    }
+    EPH_NCCL(h, api.GroupEnd());
+    if (h->gm_nrecv) {
+      unpack_xv_kernel<<<blocks_for(h->gm_nrecv, 256), 256, 0, h->stream>>>(h->gm_nrecv, h->gm_recv_slot.p, nl, x, v, h->gm_recv_xv.p, h->gshift.p, record);
+      EPH_LAUNCH_CHECK(h);
+    }
+  }
+  ghost_images_kernel<<<blocks_for(ng, 256), 256, 0, h->stream>>>(nl, ng, h->owner.p, x, v, h->gshift.p, record);
+  EPH_LAUNCH_CHECK(h);
+  h->gshift_valid = true;
+  return EPH_B200_OK;
+}
+
+// ---- device-resident integration --------------------------------------------------------------------------------------
+// x, v of all atoms (and f of the local ones) stay on the device between the fix hooks; per step only the pair forces go
+// up and x (after the drift), f (after post_force) and v (after the second kick) come down for LAMMPS' own use.
+
+int eph_b200_resident_upload(eph_b200_handle *h, const double *x, const double *v) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "resident_upload: set_atoms not called");
+  if (h->cfg.flags & EPH_B200_NOINT) return fail(h, EPH_B200_ERR_ARG, "resident_upload: flag 8 (no integration) leaves the atoms to another integrator");
+  if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "resident_upload: null x or v");
+  cudaSetDevice(h->cfg.device);
+  const size_t nt = (size_t)h->nlocal + h->nghost, nl = h->nlocal;
+  EPH_CUDA(h, h->res_x.reserve(3 * std::max<size_t>(nt, 1))); EPH_CUDA(h, h->res_v.reserve(3 * std::max<size_t>(nt, 1)));
+  EPH_CUDA(h, h->res_f.reserve(3 * std::max<size_t>(nl, 1)));
+  if (nt) {
+    EPH_CUDA(h, cudaMemcpyAsync(h->res_x.p, x, 3 * nt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(h->res_v.p, v, 3 * nt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->resident = true;
+  h->gshift_valid = false;
+  if (h->nghost > 0) {   // the ghost coordinates just uploaded are LAMMPS' own: record the image shifts
+    int rc = eph_b200_refresh_ghosts(h, h->res_x.p, h->res_v.p);
+    if (rc) return rc;
+  }
+  return EPH_B200_OK;
+}
+
+// f: HOST total forces of the local atoms, needed only while the engine holds none itself (first step after an upload
+// without a preceding resident_post_force; may be NULL otherwise).  x_out: HOST [nlocal][3], receives the new positions.
+int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf, double *x_out) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_initial_integrate: resident_upload not called since set_atoms");
+  if (!mass_by_type) return fail(h, EPH_B200_ERR_ARG, "resident_initial_integrate: null masses");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  if (!h->res_f_valid) {
+    if (!f) return fail(h, EPH_B200_ERR_ARG, "resident_initial_integrate: the engine holds no forces yet and none were passed");
+    EPH_CUDA(h, cudaMemcpyAsync(h->res_f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->res_f_valid = true;
+  }
+  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
+  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->res_x.p, h->res_v.p, h->res_f.p, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
+  EPH_LAUNCH_CHECK(h);
+  if (x_out) EPH_CUDA(h, cudaMemcpyAsync(x_out, h->res_x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  int rc = eph_b200_refresh_ghosts(h, h->res_x.p, h->res_v.p);
+  if (rc) return rc;
+  if (x_out) EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  return EPH_B200_OK;
+}
+
+// f: HOST [nlocal][3] forces of the other force contributors (the pair style): go up behind the density pass, come back
+// with f_EPH (+ f_RNG) added; the engine keeps the sum for the two kicks.
+int eph_b200_resident_post_force(eph_b200_handle *h, double *f, const double *xi_inject, long long ntimestep) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_post_force: resident_upload not called since set_atoms");
+  if (!f && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "resident_post_force: null f");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  const double *dxi = nullptr;
+  int rc;
+  if (xi_inject && nl > 0) {
+    if ((rc = stage_in(h, h->xi_in, xi_inject, 3 * (size_t)nl, EPH_B200_HOST, &dxi))) return rc;
+  }
+  if (nl > 0) {   // the pair forces travel while the density pass runs
+    EPH_CUDA(h, cudaMemcpyAsync(h->res_f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    EPH_CUDA(h, cudaEventRecord(h->f_event, h->copy_stream));
+  }
+  if ((rc = eph_b200_post_force_begin(h, h->res_x.p, h->res_v.p, dxi, ntimestep, EPH_B200_DEVICE))) return rc;
+  if (h->comm && h->comm_size > 1 && (rc = eph_b200_exchange_ghosts(h))) return rc;
+  if (nl > 0) EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));
+  if ((rc = eph_b200_post_force_end(h, h->res_f.p, EPH_B200_DEVICE))) return rc;
+  h->res_f_valid = true;
+  if (nl > 0) {
+    EPH_CUDA(h, cudaMemcpyAsync(f, h->res_f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+// v_out: HOST [nlocal][3] or NULL (a caller that does not need the velocities on the host this step saves the copy)
+int eph_b200_resident_final_integrate(eph_b200_handle *h, const double *mass_by_type, double dtf, double *v_out) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->resident || !h->res_f_valid) return fail(h, EPH_B200_ERR_ARG, "resident_final_integrate: no resident forces (resident_post_force first)");
+  if (!mass_by_type) return fail(h, EPH_B200_ERR_ARG, "resident_final_integrate: null masses");
+  cudaSetDevice(h->cfg.device);
+  const int nl = h->nlocal;
+  if (nl == 0) return EPH_B200_OK;
+  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
+  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, nullptr, h->res_v.p, h->res_f.p, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, 0.0, dtf, 0);
+  EPH_LAUNCH_CHECK(h);
+  if (v_out) {
+    EPH_CUDA(h, cudaMemcpyAsync(v_out, h->res_v.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+// which: 0 x, 1 v, 2 f of the local atoms -> HOST out [nlocal][3]
+int eph_b200_resident_get(eph_b200_handle *h, int which, double *out) {
+  if (!h || !out) return EPH_B200_ERR_ARG;
+  if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_get: resident_upload not called since set_atoms");
+  const double *src = which == 0 ? h->res_x.p : which == 1 ? h->res_v.p : which == 2 ? h->res_f.p : nullptr;
+  if (!src) return fail(h, EPH_B200_ERR_ARG, "resident_get: bad id %d", which);
+  cudaSetDevice(h->cfg.device);
+  if (h->nlocal > 0) {
+    EPH_CUDA(h, cudaMemcpyAsync(out, src, 3 * (size_t)h->nlocal * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return EPH_B200_OK;
+}
+
+// end_of_step on the resident velocities
+int eph_b200_resident_end_of_step(eph_b200_handle *h, double *E_local) {
+  if (!h) return EPH_B200_ERR_ARG;
+  if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_end_of_step: resident_upload not called since set_atoms");
+  return eph_b200_end_of_step(h, nullptr, h->res_v.p, E_local, EPH_B200_DEVICE);
 }
 
 }  // extern "C"

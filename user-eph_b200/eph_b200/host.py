@@ -146,7 +146,7 @@ class FixDriver:
     prefix "b200" drives FixEPHB200 (this library); the test suite passes the
     reference library with prefix "ref" to drive the unmodified FixEPH."""
 
-    def __init__(self, system, fix_args, dt=1e-4, lib=None, prefix="b200", mass=None):
+    def __init__(self, system, fix_args, dt=1e-4, lib=None, prefix="b200", mass=None, neigh_modify=None):
         self.lib = lib or load_fix_lib()
         self.p = prefix
         self.sys = system
@@ -164,6 +164,8 @@ class FixDriver:
                                        C.c_void_p(hi.ctypes.data), C.c_double(dt), C.c_void_p(m.ctypes.data))
         self.nlocal, self.nghost = system["nlocal"], system["nghost"]
         self._set_atoms(system)
+        if neigh_modify is not None:          # (every, delay, check): a `neigh_modify` command ahead of the fix's init()
+            self.neigh_modify(*neigh_modify)
         args = [str(a).encode() for a in fix_args]
         arr = (C.c_char_p * len(args))(*args)
         self._ck(self._fn("make_fix")(C.c_void_p(self.w), len(args), arr))
@@ -279,6 +281,14 @@ class FixDriver:
 
     def set_dt(self, dt):
         self._ck(self._fn("set_dt")(C.c_void_p(self.w), C.c_double(dt)))
+
+    def neigh_tick(self):
+        """a step in which LAMMPS does not re-neighbour: the list ages (Neighbor::decide)"""
+        self._fn("neigh_tick")(C.c_void_p(self.w))
+
+    def neigh_modify(self, every=1, delay=0, check=True):
+        """LAMMPS' `neigh_modify every N delay M check yes|no` in the stand-in"""
+        self._fn("neigh_modify")(C.c_void_p(self.w), int(every), int(delay), int(bool(check)))
 
     def set_step(self, step):
         self._fn("set_step")(C.c_void_p(self.w), C.c_longlong(step))

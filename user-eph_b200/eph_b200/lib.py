@@ -79,6 +79,13 @@ SYMBOLS = {
     "eph_b200_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                              C.c_double, C.c_int]),
     "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
+    "eph_b200_refresh_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eph_b200_resident_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "eph_b200_resident_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    "eph_b200_resident_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
+    "eph_b200_resident_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "eph_b200_resident_end_of_step": (C.c_int, [C.c_void_p, c_double_p]),
+    "eph_b200_resident_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "eph_b200_get_peratom": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "eph_b200_get_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "eph_b200_pack_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -413,6 +420,36 @@ class Engine:
         m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
         ps = [_ptr(v), _ptr(f)]
         self._check(self.lib.eph_b200_final_integrate(self.h, ps[0][0], ps[1][0], m.ctypes.data, dtf, _space(*ps)))
+
+    def refresh_ghosts(self, x, v):
+        """ghost x, v follow their owners on the device (device tensors); the first call after set_atoms records the shifts"""
+        self._check(self.lib.eph_b200_refresh_ghosts(self.h, x.data_ptr(), v.data_ptr()))
+
+    # device-resident integration: host arrays in and out, x / v / f stay on the device between the hooks
+    def resident_upload(self, x, v):
+        self._check(self.lib.eph_b200_resident_upload(self.h, x.ctypes.data, v.ctypes.data))
+
+    def resident_initial_integrate(self, f, mass_by_type, dtv, dtf, x_out):
+        m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
+        self._check(self.lib.eph_b200_resident_initial_integrate(self.h, None if f is None else f.ctypes.data, m.ctypes.data, dtv, dtf,
+                                                                 None if x_out is None else x_out.ctypes.data))
+
+    def resident_post_force(self, f, xi=None, step=0):
+        self._check(self.lib.eph_b200_resident_post_force(self.h, f.ctypes.data, None if xi is None else xi.ctypes.data, step))
+
+    def resident_final_integrate(self, mass_by_type, dtf, v_out=None):
+        m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
+        self._check(self.lib.eph_b200_resident_final_integrate(self.h, m.ctypes.data, dtf, None if v_out is None else v_out.ctypes.data))
+
+    def resident_get(self, which):
+        out = np.empty((self.nlocal, 3))
+        self._check(self.lib.eph_b200_resident_get(self.h, which, out.ctypes.data))
+        return out
+
+    def resident_end_of_step(self, want_energy=True):
+        e = C.c_double()
+        self._check(self.lib.eph_b200_resident_end_of_step(self.h, C.byref(e) if want_energy else None))
+        return e.value if want_energy else None
 
     def peratom(self):
         out = np.empty((self.nlocal, 8), dtype=np.float64)

@@ -136,13 +136,15 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   comm_nccl = false;
   grid_sharded = false;
   neigh_device = false;
+  integrate_device = false;
   peratom_every = 1;
   int device = -1;
   // token by token: decks list more element names than atom types (e.g. `Ni.beta Ni Ni` with one type); like the
   // reference those extras are skipped, and a keyword is recognised wherever it stands
   for (int k = 17 + types; k < narg; ++k) {
     const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "neigh") == 0 ||
-                            strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0 || strcmp(arg[k], "grid") == 0;
+                            strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0 || strcmp(arg[k], "grid") == 0 ||
+                            strcmp(arg[k], "integrate") == 0;
     if (!is_keyword) continue;   // an extra element name
     if (k + 1 >= narg) error->all(FLERR, "fix eph/b200: keyword without a value");
     const char *val = arg[k + 1];
@@ -161,6 +163,10 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
       // the cadence is the user's: every N-th step (default 1 = the reference's behaviour, 0 = never)
       peratom_every = atoi(val);
       if (peratom_every < 0) error->all(FLERR, "fix eph/b200: peratom must be >= 0");
+    } else if (strcmp(arg[k], "integrate") == 0) {
+      if (strcmp(val, "device") == 0) integrate_device = true;
+      else if (strcmp(val, "host") == 0) integrate_device = false;
+      else error->all(FLERR, "fix eph/b200: integrate must be host or device");
     } else if (strcmp(arg[k], "grid") == 0) {
       if (strcmp(val, "sharded") == 0) grid_sharded = true;
       else if (strcmp(val, "replicated") == 0) grid_sharded = false;
@@ -173,6 +179,9 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
     }
     ++k;
   }
+
+  if (integrate_device && (eph_flag & Flag::NOINT)) error->all(FLERR, "fix eph/b200: integrate device contradicts flag 8 (no integration)");
+  if (integrate_device && comm_lammps) error->all(FLERR, "fix eph/b200: integrate device needs comm device (one rank) or comm nccl");
 
   eta_factor = sqrt(2.0 * force->boltz / update->dt);
   dtv = update->dt;
@@ -236,6 +245,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   n = 0;
   atoms_epoch = -1;
   need_upload = true;
+  v_synced_step = -1;
 
   grow_arrays(atom->nmax);
   atom->add_callback(0);
@@ -281,6 +291,8 @@ void FixEPHB200::init() {
   // inner list is validated against it on the device, so it must know the current value before every run
   check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
   need_upload = true;
+  if (integrate_device && neighbor->dist_check)
+    error->all(FLERR, "fix eph/b200: integrate device needs a re-neighbouring schedule known in advance (neigh_modify every N delay 0 check no)");
 
   reset_dt();
 }
@@ -304,6 +316,19 @@ int FixEPHB200::setmask() {
 // variants (eph_b200_initial_integrate / final_integrate) serve GPU-resident atoms.
 void FixEPHB200::initial_integrate(int) {
   if (eph_flag & Flag::NOINT) return;
+  if (integrate_device && !need_upload) {
+    const int nlocal = atom->nlocal;
+    if (nlocal == 0) return;
+    check(eph_b200_resident_initial_integrate(dev, &atom->f[0][0], atom->mass, dtv, dtf, &atom->x[0][0]), "initial_integrate");
+    // LAMMPS re-neighbours from its host arrays (migration, sorting): on those steps it needs the half-kicked v as well
+    // (Neighbor::decide(), which runs next: ago + 1 reaches a multiple of `every` that is not below `delay`)
+    const int ago = neighbor->ago + 1;
+    const bool reneigh = neighbor->every > 0 && ago >= neighbor->delay && ago % neighbor->every == 0;
+    if (reneigh) check(eph_b200_resident_get(dev, 1, &atom->v[0][0]), "resident_get");
+    v_synced_step = reneigh ? update->ntimestep : -1;
+    return;
+  }
+  v_synced_step = update->ntimestep;   // host loop: LAMMPS' arrays are the authoritative ones this step
   double **x = atom->x, **v = atom->v, **f = atom->f;
   const double *mass = atom->mass;
   const int *type = atom->type, *mask = atom->mask;
@@ -318,6 +343,10 @@ void FixEPHB200::initial_integrate(int) {
 
 void FixEPHB200::final_integrate() {
   if (eph_flag & Flag::NOINT) return;
+  if (integrate_device) {
+    if (atom->nlocal > 0) check(eph_b200_resident_final_integrate(dev, atom->mass, dtf, &atom->v[0][0]), "final_integrate");
+    return;
+  }
   double **v = atom->v, **f = atom->f;
   const double *mass = atom->mass;
   const int *type = atom->type, *mask = atom->mask;
@@ -394,6 +423,13 @@ void FixEPHB200::upload_topology() {
   else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
   // the memory kernel's state in the atoms' present order (LAMMPS may have sorted or migrated them)
   if (coloured && nlocal > 0) check(eph_b200_set_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "set_colour_state");
+  if (integrate_device) {
+    if (atoms_epoch >= 0 && v_synced_step != update->ntimestep)
+      error->all(FLERR, "fix eph/b200: integrate device: LAMMPS re-neighboured on a step the fix did not expect (neigh_modify every N delay 0 check no)");
+    for (int i = 0; i < nlocal; ++i)
+      if (!(atom->mask[i] & groupbit)) error->one(FLERR, "fix eph/b200: integrate device needs every atom in the fix group");
+    if (nlocal + nghost > 0) check(eph_b200_resident_upload(dev, &atom->x[0][0], &atom->v[0][0]), "resident_upload");
+  }
   atoms_epoch = ((long long)nlocal << 32) | (unsigned)nghost;
   need_upload = false;
 }
@@ -417,6 +453,10 @@ void FixEPHB200::post_force(int) {
     xi = xi_host.data();
   }
   if (nlocal + nghost == 0) return;   // no atoms, no ghosts: nobody exchanges anything with this rank
+  if (integrate_device) {
+    check(eph_b200_resident_post_force(dev, nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep), "post_force");
+    return;
+  }
   if (!comm_lammps) {   // one rank, or the engine's NCCL exchange between the two halves of post_force
     check(eph_b200_post_force(dev, &atom->x[0][0], &atom->v[0][0], nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep,
                               EPH_B200_HOST),
@@ -438,7 +478,9 @@ void FixEPHB200::end_of_step() {
   const int nlocal = atom->nlocal;
   double E_local = 0.0;
   const double *xp = nlocal > 0 ? &atom->x[0][0] : nullptr, *vp = nlocal > 0 ? &atom->v[0][0] : nullptr;
-  if (nrPS == 1) {
+  if (integrate_device) {
+    if (nlocal > 0 || nrPS > 1) check(eph_b200_resident_end_of_step(dev, &E_local), "end_of_step");
+  } else if (nrPS == 1) {
     if (nlocal > 0) check(eph_b200_end_of_step(dev, xp, vp, &E_local, EPH_B200_HOST), "end_of_step");
   } else if (comm_nccl) {
     // every rank, with or without atoms: the engine sums the source term over ranks (ncclAllReduce) and solves

@@ -13,6 +13,12 @@
  *                     Comm::forward_comm(Fix*) with host buffers and MPI_Allreduce of the grid source term, as the
  *                     reference does (default for several ranks), or -- one rank per GPU -- through the engine's own
  *                     NCCL data plane (one grouped send/recv of {rho, W} per peer, ncclAllReduce of the source term)
+ *   integrate host|device  the velocity-Verlet half steps of the fix run on LAMMPS' host arrays (default) or on the
+ *                     device, where x, v, f then stay between the hooks: per step only the pair forces go up, and x
+ *                     (after the drift), f (after post_force) and v (after the second kick) come down.  Needs the fix
+ *                     group to be all atoms, this fix to be the last one that changes f, and a re-neighbouring schedule
+ *                     known in advance (neigh_modify ... check no): on those steps v is brought down after the first
+ *                     kick as well, because LAMMPS migrates and re-orders the atoms from its host arrays
  *   grid replicated|sharded  with comm nccl: every rank solves the whole grid (default) or only its z-slab, with halo
  *                     planes between sub-steps and one all-gather (replaces the reference's MPI_Bcast, eph_fdm.h:490)
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
@@ -108,6 +114,7 @@ class FixEPHB200 : public Fix {
   bool comm_nccl;               // keyword `comm nccl`: the engine exchanges ghosts / sums the grid source over NCCL itself
   bool grid_sharded;            // keyword `grid sharded`: with comm nccl every rank advances only its z-slab of the grid
   bool neigh_device;
+  bool integrate_device;        // keyword `integrate device`: x, v, f of the atoms stay on the device between the hooks
   int peratom_every;            // keyword `peratom N`: array_atom is refreshed every N-th step (0: never)
   class NeighList *list;
   double Ee;
@@ -125,6 +132,7 @@ class FixEPHB200 : public Fix {
   std::vector<double> owner_buf;
   long long atoms_epoch;        // (nlocal,nghost) signature of the last upload
   bool need_upload;
+  long long v_synced_step;      // integrate device: the step whose half-kicked v went down to the host (a re-neighbouring step)
 
   void upload_topology();
   void check(int rc, const char *what);
