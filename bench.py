@@ -619,8 +619,9 @@ def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
             if k % REBUILD_EVERY == 0:
                 nvl[...] = eng.resident_get(1)                           # LAMMPS re-neighbours from its host arrays: v down too
                 reneighbor_res()
-            eng.resident_post_force(nf, None, k)                         # pair forces up, total forces down
-            eng.resident_final_integrate(mass, dtf, nvl)                 # v down
+            sync = k % REBUILD_EVERY == 0                               # `sync 10`: LAMMPS' own f and v every 10th step
+            eng.resident_post_force(nf, None, k, f_out=nf if sync else None)    # pair forces up (total forces down)
+            eng.resident_final_integrate(mass, dtf, nvl if sync else None)      # (v down)
             return eng.resident_end_of_step(True)                        # E_local down
 
         reneighbor_res()
@@ -630,10 +631,11 @@ def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
         ms_r = max(r_dev, r_wall)
         resident = {"value": natoms * a.steps / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r / a.steps,
                     "h2d_bytes_per_step": int(nl * 24 + (topo + 2 * nt * 24 + nt * 24) * rebuilds / a.steps),
-                    "d2h_bytes_per_step": int(3 * nl * 24 + 8 + nl * 24 * rebuilds / a.steps),
-                    "note": "device-resident integration (eph_b200_resident_*; FixEPHB200 keyword `integrate device`): all four "
-                            "hooks, x / v / f stay on the device; per step f up, x, f, v down; every %d steps v down once more, "
-                            "atoms registered, list rebuilt on the device, x and v uploaded" % REBUILD_EVERY}
+                    "d2h_bytes_per_step": int(nl * 24 + 8 + 3 * nl * 24 * rebuilds / a.steps),
+                    "note": "device-resident integration (eph_b200_resident_*; FixEPHB200 keywords `integrate device sync %d`): all "
+                            "four hooks, x / v / f stay on the device; per step the pair forces go up and x comes down; every %d "
+                            "steps f and v come down too (thermo / dump cadence), v once more for the re-neighbouring, atoms are "
+                            "registered, the list is rebuilt on the device and x, v are uploaded" % (REBUILD_EVERY, REBUILD_EVERY)}
     return {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
             "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps, "resident_mode": resident,
             "note": "pinned host x, v, f through the C ABI (HOST memspace): x, v, f up and f, E down every step; every %d steps "

@@ -287,13 +287,14 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v);
  *   resident_upload             after every set_atoms (re-neighbouring): x, v [nlocal + nghost][3] from the host once
  *   resident_initial_integrate  kick + drift on the device with the forces of the last resident_post_force (f: host
  *                               forces for the very first step, else may be NULL); ghosts follow; x_out <- x[nlocal][3]
- *   resident_post_force         f: host forces of the other contributors in, the same plus f_EPH (+ f_RNG) out
+ *   resident_post_force         f: host forces of the other contributors in; f_out <- the same plus f_EPH (+ f_RNG)
+ *                               (may be f itself; NULL: not needed on the host this step)
  *   resident_final_integrate    second kick; v_out <- v[nlocal][3] (NULL: not needed on the host this step)
  *   resident_end_of_step        end_of_step on the resident velocities */
 int eph_b200_resident_upload(eph_b200_handle *h, const double *x, const double *v);
 int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf,
                                         double *x_out);
-int eph_b200_resident_post_force(eph_b200_handle *h, double *f, const double *xi_inject, long long ntimestep);
+int eph_b200_resident_post_force(eph_b200_handle *h, const double *f, double *f_out, const double *xi_inject, long long ntimestep);
 int eph_b200_resident_final_integrate(eph_b200_handle *h, const double *mass_by_type, double dtf, double *v_out);
 int eph_b200_resident_end_of_step(eph_b200_handle *h, double *E_local);
 /* which: 0 x, 1 v, 2 f of the local atoms -> HOST out [nlocal][3] (e.g. v after the first kick on a step in which LAMMPS

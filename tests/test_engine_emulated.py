@@ -242,6 +242,7 @@ def test_emulated_fix_integrate_device_matches_reference(emulated_engine):
     """keyword `integrate device`: the velocity-Verlet half steps run on the device and x, v, f stay there between the hooks"""
     import reneighbour_cases
     reneighbour_cases.resident_case()
+    reneighbour_cases.resident_case(sync=2)
 
 
 def test_simt_stand_in_selftest():

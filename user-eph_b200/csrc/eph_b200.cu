@@ -2375,9 +2375,10 @@ int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, con
   return EPH_B200_OK;
 }
 
-// f: HOST [nlocal][3] forces of the other force contributors (the pair style): go up behind the density pass, come back
-// with f_EPH (+ f_RNG) added; the engine keeps the sum for the two kicks.
-int eph_b200_resident_post_force(eph_b200_handle *h, double *f, const double *xi_inject, long long ntimestep) {
+// f: HOST [nlocal][3] forces of the other force contributors (the pair style): go up behind the density pass; the engine
+// keeps f + f_EPH (+ f_RNG) for the two kicks and copies it to f_out (HOST, may be f itself; NULL: not needed on the
+// host this step).
+int eph_b200_resident_post_force(eph_b200_handle *h, const double *f, double *f_out, const double *xi_inject, long long ntimestep) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_post_force: resident_upload not called since set_atoms");
   if (!f && h->nlocal > 0) return fail(h, EPH_B200_ERR_ARG, "resident_post_force: null f");
@@ -2397,8 +2398,8 @@ int eph_b200_resident_post_force(eph_b200_handle *h, double *f, const double *xi
   if (nl > 0) EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));
   if ((rc = eph_b200_post_force_end(h, h->res_f.p, EPH_B200_DEVICE))) return rc;
   h->res_f_valid = true;
-  if (nl > 0) {
-    EPH_CUDA(h, cudaMemcpyAsync(f, h->res_f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (nl > 0 && f_out) {
+    EPH_CUDA(h, cudaMemcpyAsync(f_out, h->res_f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     EPH_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   return EPH_B200_OK;

@@ -82,7 +82,7 @@ SYMBOLS = {
     "eph_b200_refresh_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "eph_b200_resident_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "eph_b200_resident_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
-    "eph_b200_resident_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
+    "eph_b200_resident_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
     "eph_b200_resident_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "eph_b200_resident_end_of_step": (C.c_int, [C.c_void_p, c_double_p]),
     "eph_b200_resident_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -434,8 +434,9 @@ class Engine:
         self._check(self.lib.eph_b200_resident_initial_integrate(self.h, None if f is None else f.ctypes.data, m.ctypes.data, dtv, dtf,
                                                                  None if x_out is None else x_out.ctypes.data))
 
-    def resident_post_force(self, f, xi=None, step=0):
-        self._check(self.lib.eph_b200_resident_post_force(self.h, f.ctypes.data, None if xi is None else xi.ctypes.data, step))
+    def resident_post_force(self, f, xi=None, step=0, f_out=None):
+        self._check(self.lib.eph_b200_resident_post_force(self.h, f.ctypes.data, None if f_out is None else f_out.ctypes.data,
+                                                          None if xi is None else xi.ctypes.data, step))
 
     def resident_final_integrate(self, mass_by_type, dtf, v_out=None):
         m = np.ascontiguousarray(mass_by_type, dtype=np.float64)

@@ -137,6 +137,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   grid_sharded = false;
   neigh_device = false;
   integrate_device = false;
+  sync_every = 1;
   peratom_every = 1;
   int device = -1;
   // token by token: decks list more element names than atom types (e.g. `Ni.beta Ni Ni` with one type); like the
@@ -144,7 +145,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   for (int k = 17 + types; k < narg; ++k) {
     const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "neigh") == 0 ||
                             strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0 || strcmp(arg[k], "grid") == 0 ||
-                            strcmp(arg[k], "integrate") == 0;
+                            strcmp(arg[k], "integrate") == 0 || strcmp(arg[k], "sync") == 0;
     if (!is_keyword) continue;   // an extra element name
     if (k + 1 >= narg) error->all(FLERR, "fix eph/b200: keyword without a value");
     const char *val = arg[k + 1];
@@ -167,6 +168,9 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
       if (strcmp(val, "device") == 0) integrate_device = true;
       else if (strcmp(val, "host") == 0) integrate_device = false;
       else error->all(FLERR, "fix eph/b200: integrate must be host or device");
+    } else if (strcmp(arg[k], "sync") == 0) {
+      sync_every = atoi(val);
+      if (sync_every < 1) error->all(FLERR, "fix eph/b200: sync must be >= 1");
     } else if (strcmp(arg[k], "grid") == 0) {
       if (strcmp(val, "sharded") == 0) grid_sharded = true;
       else if (strcmp(val, "replicated") == 0) grid_sharded = false;
@@ -344,7 +348,8 @@ void FixEPHB200::initial_integrate(int) {
 void FixEPHB200::final_integrate() {
   if (eph_flag & Flag::NOINT) return;
   if (integrate_device) {
-    if (atom->nlocal > 0) check(eph_b200_resident_final_integrate(dev, atom->mass, dtf, &atom->v[0][0]), "final_integrate");
+    if (atom->nlocal > 0)
+      check(eph_b200_resident_final_integrate(dev, atom->mass, dtf, update->ntimestep % sync_every == 0 ? &atom->v[0][0] : nullptr), "final_integrate");
     return;
   }
   double **v = atom->v, **f = atom->f;
@@ -454,7 +459,9 @@ void FixEPHB200::post_force(int) {
   }
   if (nlocal + nghost == 0) return;   // no atoms, no ghosts: nobody exchanges anything with this rank
   if (integrate_device) {
-    check(eph_b200_resident_post_force(dev, nlocal ? &atom->f[0][0] : nullptr, xi, update->ntimestep), "post_force");
+    // LAMMPS' own f and v are brought up to date every `sync`-th step (thermo / dump steps); x every step
+    double *fp = nlocal ? &atom->f[0][0] : nullptr;
+    check(eph_b200_resident_post_force(dev, fp, update->ntimestep % sync_every == 0 ? fp : nullptr, xi, update->ntimestep), "post_force");
     return;
   }
   if (!comm_lammps) {   // one rank, or the engine's NCCL exchange between the two halves of post_force

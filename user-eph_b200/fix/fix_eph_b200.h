@@ -19,6 +19,8 @@
  *                     group to be all atoms, this fix to be the last one that changes f, and a re-neighbouring schedule
  *                     known in advance (neigh_modify ... check no): on those steps v is brought down after the first
  *                     kick as well, because LAMMPS migrates and re-orders the atoms from its host arrays
+ *   sync N            with integrate device: atom->f and atom->v on the host are brought up to date every N-th step only
+ *                     (default 1; set it to the thermo / dump interval), x every step
  *   grid replicated|sharded  with comm nccl: every rank solves the whole grid (default) or only its z-slab, with halo
  *                     planes between sub-steps and one all-gather (replaces the reference's MPI_Bcast, eph_fdm.h:490)
  * The same hooks are registered (fix_eph.cpp:293-302) and the same outputs are produced
@@ -115,6 +117,7 @@ class FixEPHB200 : public Fix {
   bool grid_sharded;            // keyword `grid sharded`: with comm nccl every rank advances only its z-slab of the grid
   bool neigh_device;
   bool integrate_device;        // keyword `integrate device`: x, v, f of the atoms stay on the device between the hooks
+  int sync_every;               // keyword `sync N`: with integrate device, LAMMPS' host f and v are refreshed every N-th step
   int peratom_every;            // keyword `peratom N`: array_atom is refreshed every N-th step (0: never)
   class NeighList *list;
   double Ee;
