@@ -611,13 +611,16 @@ def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
         nxl, nvl = nx[:nl], nv[:nl]
 
         def reneighbor_res():
-            reneighbor()
-            eng.resident_upload(nx, nv)
+            eng.set_atoms(nl, ng, h_type.numpy(), h_mask.numpy(), h_tag.numpy(), h_owner.numpy())
+            eng.resident_upload(nx, nv)                                  # x, v up once ...
+            eng.build_neighbors(None, CUTOFF)                            # ... and the list is built from the resident copy
 
         def step_res(k):
-            eng.resident_initial_integrate(nf, mass, dtv, dtf, nxl)      # x down
-            if k % REBUILD_EVERY == 0:
-                nvl[...] = eng.resident_get(1)                           # LAMMPS re-neighbours from its host arrays: v down too
+            rebuild = k % REBUILD_EVERY == 0
+            # x down; without a re-neighbouring ahead the density pass of this step starts while x travels
+            eng.resident_initial_integrate(nf, mass, dtv, dtf, nxl, start_post_force_step=-1 if rebuild else k)
+            if rebuild:
+                eng.resident_get(1, out=nvl)                             # LAMMPS re-neighbours from its host arrays: v down too
                 reneighbor_res()
             sync = k % REBUILD_EVERY == 0                               # `sync 10`: LAMMPS' own f and v every 10th step
             eng.resident_post_force(nf, None, k, f_out=nf if sync else None)    # pair forces up (total forces down)

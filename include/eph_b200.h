@@ -167,7 +167,8 @@ int eph_b200_set_neighbors_lammps(eph_b200_handle *h, int nlocal, const int *num
 
 /* Alternative to uploading LAMMPS' list: build the same full list (rows of local atoms over locals and ghosts,
  * pairs closer than cutoff = r_c + neighbor->skin) on the device from the positions x [nlocal+nghost][3].  Call when
- * neighbor->ago == 0, after set_atoms.  get_neighbors reads the list in use back (offsets [nlocal+1], neigh). */
+ * neighbor->ago == 0, after set_atoms.  x == NULL: the positions the engine keeps itself (after eph_b200_resident_upload).
+ * get_neighbors reads the list in use back (offsets [nlocal+1], neigh). */
 int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff, int memspace);
 int eph_b200_get_neighbors(eph_b200_handle *h, int64_t *offsets, int *neigh, long long *n_entries);
 
@@ -286,14 +287,18 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v);
  * come down.  Valid while this fix is the integrator of all atoms it is given and the last fix to change f.
  *   resident_upload             after every set_atoms (re-neighbouring): x, v [nlocal + nghost][3] from the host once
  *   resident_initial_integrate  kick + drift on the device with the forces of the last resident_post_force (f: host
- *                               forces for the very first step, else may be NULL); ghosts follow; x_out <- x[nlocal][3]
+ *                               forces for the very first step, else may be NULL); ghosts follow; x_out <- x[nlocal][3].
+ *                               start_post_force_step >= 0 (the time step; only when LAMMPS will not re-neighbour in this
+ *                               step and the Gaussians are the built-in stream): the first half of post_force -- records
+ *                               and density pass, which need x and v only -- is started at once and runs while x travels
+ *                               and the host computes its pair forces; resident_post_force then continues from there
  *   resident_post_force         f: host forces of the other contributors in; f_out <- the same plus f_EPH (+ f_RNG)
  *                               (may be f itself; NULL: not needed on the host this step)
  *   resident_final_integrate    second kick; v_out <- v[nlocal][3] (NULL: not needed on the host this step)
  *   resident_end_of_step        end_of_step on the resident velocities */
 int eph_b200_resident_upload(eph_b200_handle *h, const double *x, const double *v);
 int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf,
-                                        double *x_out);
+                                        double *x_out, long long start_post_force_step);
 int eph_b200_resident_post_force(eph_b200_handle *h, const double *f, double *f_out, const double *xi_inject, long long ntimestep);
 int eph_b200_resident_final_integrate(eph_b200_handle *h, const double *mass_by_type, double dtf, double *v_out);
 int eph_b200_resident_end_of_step(eph_b200_handle *h, double *E_local);

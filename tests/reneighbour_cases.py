@@ -79,7 +79,7 @@ def adaptive_dt_case(kind, make_fix=None):
     traj.assert_same_trajectory(a, b, TOL, dts=dts)
 
 
-def resident_case(cells=3, steps=7, every=3, sync=1):
+def resident_case(cells=3, steps=7, every=3, sync=1, rng="mars"):
     """`integrate device`: x, v, f stay on the device between the hooks; FixEPHB200 in that mode continues exactly like the
     reference fix through re-neighbourings that happen, as in LAMMPS, between initial_integrate and post_force"""
     from oracle import reference as R
@@ -88,10 +88,16 @@ def resident_case(cells=3, steps=7, every=3, sync=1):
     s = H.make_system(cells, skin=2.0)
     s["v"][0] = 300.0 * np.array([0.835115, 0.543981, 0.081652])     # one fast atom
     s["v"][s["nlocal"]:][s["ghost_owner"] == 0] = s["v"][0]
-    xis = [np.random.default_rng(120 + k).normal(size=(s["nlocal"], 3)) for k in range(steps)]
+    if rng == "mars":
+        xis = [np.random.default_rng(120 + k).normal(size=(s["nlocal"], 3)) for k in range(steps)]
+    else:
+        # the product's own counter-based stream (keyed on seed, step, atom tag): the reference is handed the same numbers.
+        # Without injected Gaussians the fix starts the density pass of a step inside initial_integrate.
+        from oracle import oracle as O
+        xis = [O.xi_stream(12345, k + 1, s["tag"][: s["nlocal"]]) for k in range(steps)]
     ref_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2))
     our_args = H.fix_args(7, BETA, ["Ni"], grid=(2, 2, 2), style="eph/b200",
-                          extra=["rng", "mars", "integrate", "device", "sync", sync])
+                          extra=["rng", rng, "integrate", "device", "sync", sync])
     a = traj.run_in_lammps_order(lambda sy: R.fix_driver(sy, ref_args), s, xis, every)
     b = traj.run_in_lammps_order(lambda sy: host.FixDriver(sy, our_args, neigh_modify=(every, 0, False)), s, xis, every)
     if sync == 1:

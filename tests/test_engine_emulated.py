@@ -243,6 +243,7 @@ def test_emulated_fix_integrate_device_matches_reference(emulated_engine):
     import reneighbour_cases
     reneighbour_cases.resident_case()
     reneighbour_cases.resident_case(sync=2)
+    reneighbour_cases.resident_case(rng="philox")
 
 
 def test_simt_stand_in_selftest():

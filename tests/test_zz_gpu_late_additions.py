@@ -175,3 +175,4 @@ def test_fix_integrate_device_matches_reference():
     post_force)"""
     import reneighbour_cases
     reneighbour_cases.resident_case(cells=6, steps=8, every=3)
+    reneighbour_cases.resident_case(cells=6, steps=8, every=3, rng="philox", sync=2)

@@ -149,7 +149,7 @@ struct eph_b200_handle {
   DevBuf<double> gm_send_xv, gm_recv_xv;   // {x, v} of the atoms other ranks hold as ghosts
   // device-resident integration (eph_b200_resident_*): x, v of all atoms and f of the local ones stay here between hooks
   DevBuf<double> res_x, res_v, res_f;
-  bool resident = false, res_f_valid = false;
+  bool resident = false, res_f_valid = false, res_pf_started = false;
   bool grid_sharded = false;    // every rank advances only its z-slab of the grid (halo planes + all-gather)
   DevBuf<double> slab_tmp;
 
@@ -872,7 +872,7 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
   h->split_ready = false;   // the boundary work lists name atoms of the previous registration
   h->ghost_map_set = false; // ... and so does the ghost map
   h->gshift_valid = false;
-  h->resident = false; h->res_f_valid = false;
+  h->resident = false; h->res_f_valid = false; h->res_pf_started = false;
   h->neigh_set = false;
   h->forces_valid = false;
   return EPH_B200_OK;
@@ -958,7 +958,8 @@ extern "C" {
 int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff, int memspace) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: call set_atoms first");
-  if (!x || !(cutoff > 0.0)) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: null positions or bad cut-off");
+  if ((!x && !h->resident) || !(cutoff > 0.0)) return fail(h, EPH_B200_ERR_ARG, "build_neighbors: null positions or bad cut-off");
+  if (!x) { x = h->res_x.p; memspace = EPH_B200_DEVICE; }   // the positions the engine keeps (eph_b200_resident_upload)
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal, nt = h->nlocal + h->nghost;
   if (nl == 0) {
@@ -2352,7 +2353,8 @@ int eph_b200_resident_upload(eph_b200_handle *h, const double *x, const double *
 
 // f: HOST total forces of the local atoms, needed only while the engine holds none itself (first step after an upload
 // without a preceding resident_post_force; may be NULL otherwise).  x_out: HOST [nlocal][3], receives the new positions.
-int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf, double *x_out) {
+int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, const double *mass_by_type, double dtv, double dtf, double *x_out,
+                                        long long start_post_force_step) {
   if (!h) return EPH_B200_ERR_ARG;
   if (!h->resident) return fail(h, EPH_B200_ERR_ARG, "resident_initial_integrate: resident_upload not called since set_atoms");
   if (!mass_by_type) return fail(h, EPH_B200_ERR_ARG, "resident_initial_integrate: null masses");
@@ -2368,10 +2370,21 @@ int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, con
   EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->res_x.p, h->res_v.p, h->res_f.p, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
   EPH_LAUNCH_CHECK(h);
-  if (x_out) EPH_CUDA(h, cudaMemcpyAsync(x_out, h->res_x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  // x travels to the host on the copy stream while the main stream goes on: ghosts follow their owners and, if the caller
+  // knows that LAMMPS will not re-neighbour in this step, the first half of post_force (records, density pass) starts
+  // right away -- it needs x and v only, so it runs while the host computes its pair forces
+  if (x_out) {
+    EPH_CUDA(h, cudaEventRecord(h->f_event, h->stream));
+    EPH_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->f_event, 0));
+    EPH_CUDA(h, cudaMemcpyAsync(x_out, h->res_x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+  }
   int rc = eph_b200_refresh_ghosts(h, h->res_x.p, h->res_v.p);
   if (rc) return rc;
-  if (x_out) EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (start_post_force_step >= 0 && h->neigh_set) {
+    if ((rc = eph_b200_post_force_begin(h, h->res_x.p, h->res_v.p, nullptr, start_post_force_step, EPH_B200_DEVICE))) return rc;
+    h->res_pf_started = true;
+  }
+  if (x_out) EPH_CUDA(h, cudaStreamSynchronize(h->copy_stream));
   return EPH_B200_OK;
 }
 
@@ -2393,7 +2406,10 @@ int eph_b200_resident_post_force(eph_b200_handle *h, const double *f, double *f_
     EPH_CUDA(h, cudaMemcpyAsync(h->res_f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
     EPH_CUDA(h, cudaEventRecord(h->f_event, h->copy_stream));
   }
-  if ((rc = eph_b200_post_force_begin(h, h->res_x.p, h->res_v.p, dxi, ntimestep, EPH_B200_DEVICE))) return rc;
+  if (h->res_pf_started && h->pf_open && !dxi && h->pf_step == ntimestep) {
+    // resident_initial_integrate has started this step's density pass already
+  } else if ((rc = eph_b200_post_force_begin(h, h->res_x.p, h->res_v.p, dxi, ntimestep, EPH_B200_DEVICE))) return rc;
+  h->res_pf_started = false;
   if (h->comm && h->comm_size > 1 && (rc = eph_b200_exchange_ghosts(h))) return rc;
   if (nl > 0) EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));
   if ((rc = eph_b200_post_force_end(h, h->res_f.p, EPH_B200_DEVICE))) return rc;

@@ -81,7 +81,7 @@ SYMBOLS = {
     "eph_b200_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "eph_b200_refresh_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "eph_b200_resident_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "eph_b200_resident_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    "eph_b200_resident_initial_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_longlong]),
     "eph_b200_resident_post_force": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
     "eph_b200_resident_final_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "eph_b200_resident_end_of_step": (C.c_int, [C.c_void_p, c_double_p]),
@@ -283,8 +283,9 @@ class Engine:
         self._keep = (offsets, neigh)  # device memspace aliases the caller's buffers
 
     def build_neighbors(self, x, cutoff):
-        """full list built on the device from positions (instead of uploading LAMMPS' list)"""
-        p = _ptr(x)
+        """full list built on the device from positions (instead of uploading LAMMPS' list); x = None: the positions the
+        engine keeps itself (resident mode)"""
+        p = _ptr(x) if x is not None else (None, HOST)
         self._check(self.lib.eph_b200_build_neighbors(self.h, p[0], cutoff, p[1]))
 
     def get_neighbors_count(self):
@@ -429,10 +430,10 @@ class Engine:
     def resident_upload(self, x, v):
         self._check(self.lib.eph_b200_resident_upload(self.h, x.ctypes.data, v.ctypes.data))
 
-    def resident_initial_integrate(self, f, mass_by_type, dtv, dtf, x_out):
+    def resident_initial_integrate(self, f, mass_by_type, dtv, dtf, x_out, start_post_force_step=-1):
         m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
         self._check(self.lib.eph_b200_resident_initial_integrate(self.h, None if f is None else f.ctypes.data, m.ctypes.data, dtv, dtf,
-                                                                 None if x_out is None else x_out.ctypes.data))
+                                                                 None if x_out is None else x_out.ctypes.data, start_post_force_step))
 
     def resident_post_force(self, f, xi=None, step=0, f_out=None):
         self._check(self.lib.eph_b200_resident_post_force(self.h, f.ctypes.data, None if f_out is None else f_out.ctypes.data,
@@ -442,8 +443,9 @@ class Engine:
         m = np.ascontiguousarray(mass_by_type, dtype=np.float64)
         self._check(self.lib.eph_b200_resident_final_integrate(self.h, m.ctypes.data, dtf, None if v_out is None else v_out.ctypes.data))
 
-    def resident_get(self, which):
-        out = np.empty((self.nlocal, 3))
+    def resident_get(self, which, out=None):
+        if out is None:
+            out = np.empty((self.nlocal, 3))
         self._check(self.lib.eph_b200_resident_get(self.h, which, out.ctypes.data))
         return out
 

@@ -323,11 +323,15 @@ void FixEPHB200::initial_integrate(int) {
   if (integrate_device && !need_upload) {
     const int nlocal = atom->nlocal;
     if (nlocal == 0) return;
-    check(eph_b200_resident_initial_integrate(dev, &atom->f[0][0], atom->mass, dtv, dtf, &atom->x[0][0]), "initial_integrate");
-    // LAMMPS re-neighbours from its host arrays (migration, sorting): on those steps it needs the half-kicked v as well
-    // (Neighbor::decide(), which runs next: ago + 1 reaches a multiple of `every` that is not below `delay`)
+    // Neighbor::decide(), which runs next: ago + 1 reaches a multiple of `every` that is not below `delay`
     const int ago = neighbor->ago + 1;
     const bool reneigh = neighbor->every > 0 && ago >= neighbor->delay && ago % neighbor->every == 0;
+    // without a re-neighbouring ahead (and with the built-in Gaussians) the density pass of this step's post_force starts
+    // now and runs while the host computes its pair forces
+    const bool early = !reneigh && !((eph_flag & Flag::RANDOM) && rng_mars);
+    check(eph_b200_resident_initial_integrate(dev, &atom->f[0][0], atom->mass, dtv, dtf, &atom->x[0][0], early ? (long long)update->ntimestep : -1),
+          "initial_integrate");
+    // LAMMPS re-neighbours from its host arrays (migration, sorting): on those steps it needs the half-kicked v as well
     if (reneigh) check(eph_b200_resident_get(dev, 1, &atom->v[0][0]), "resident_get");
     v_synced_step = reneigh ? update->ntimestep : -1;
     return;
@@ -424,7 +428,14 @@ void FixEPHB200::upload_topology() {
     check(eph_b200_set_ghost_map(dev, (int)peers.size(), peers.data(), send_count.data(), send_index.data(), recv_count.data(),
                                  recv_slot.data()),
           "set_ghost_map");
-  if (neigh_device) check(eph_b200_build_neighbors(dev, &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
+  bool uploaded = false;
+  if (integrate_device && neigh_device && nlocal + nghost > 0) {   // x goes up once: the list is built from the resident copy
+    for (int i = 0; i < nlocal; ++i)
+      if (!(atom->mask[i] & groupbit)) error->one(FLERR, "fix eph/b200: integrate device needs every atom in the fix group");
+    check(eph_b200_resident_upload(dev, &atom->x[0][0], &atom->v[0][0]), "resident_upload");
+    uploaded = true;
+  }
+  if (neigh_device) check(eph_b200_build_neighbors(dev, uploaded ? nullptr : &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
   else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
   // the memory kernel's state in the atoms' present order (LAMMPS may have sorted or migrated them)
   if (coloured && nlocal > 0) check(eph_b200_set_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "set_colour_state");
@@ -433,7 +444,7 @@ void FixEPHB200::upload_topology() {
       error->all(FLERR, "fix eph/b200: integrate device: LAMMPS re-neighboured on a step the fix did not expect (neigh_modify every N delay 0 check no)");
     for (int i = 0; i < nlocal; ++i)
       if (!(atom->mask[i] & groupbit)) error->one(FLERR, "fix eph/b200: integrate device needs every atom in the fix group");
-    if (nlocal + nghost > 0) check(eph_b200_resident_upload(dev, &atom->x[0][0], &atom->v[0][0]), "resident_upload");
+    if (nlocal + nghost > 0 && !uploaded) check(eph_b200_resident_upload(dev, &atom->x[0][0], &atom->v[0][0]), "resident_upload");
   }
   atoms_epoch = ((long long)nlocal << 32) | (unsigned)nghost;
   need_upload = false;
