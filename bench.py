@@ -639,12 +639,16 @@ def run_e2e(a, torch, eng, md, s, plan, D, timed, natoms, world):
                             "four hooks, x / v / f stay on the device; per step the pair forces go up and x comes down; every %d "
                             "steps f and v come down too (thermo / dump cadence), v once more for the re-neighbouring, atoms are "
                             "registered, the list is rebuilt on the device and x, v are uploaded" % (REBUILD_EVERY, REBUILD_EVERY)}
-    return {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
-            "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps, "resident_mode": resident,
+    host_mode = {"value": natoms * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
+                 "d2h_bytes_per_step": int(d2h * world), "ms_per_step": ms_e / a.steps,
             "note": "pinned host x, v, f through the C ABI (HOST memspace): x, v, f up and f, E down every step; every %d steps "
                     "the atom arrays are re-registered and the neighbour list is rebuilt on the device from the positions "
                     "(eph_b200_build_neighbors); post_force + end_of_step (the integrator hooks of FixEPHB200 are host loops "
                     "in this mode); bytes summed over ranks" % REBUILD_EVERY}
+    if resident is None:
+        return host_mode
+    # one GPU: the headline is the mode that keeps x, v, f on the device (all four hooks); the plain host mode next to it
+    return dict(resident, mode="integrate device (resident x, v, f)", host_mode=host_mode)
 
 
 def c4_leg(a, torch, lib, host, P, s, gridn, box, local, stream, dev, natoms, steps=10):

@@ -13,6 +13,6 @@ python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/m_bench_default.json").read().strip().splitlines()[-1])
 print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["step"]["frac"], d["roofline"]["kernels_ms_per_step"])
-e=d["e2e"]; print("e2e", e["value"], e["ms_per_step"], "resident", e["resident_mode"]["value"], e["resident_mode"]["ms_per_step"])
+e=d["e2e"]; print("e2e", e["value"], e["ms_per_step"], e.get("mode"), "host mode", e.get("host_mode",{}).get("value"))
 print(d["extras"]["C4_NiCoCrFe"]["value"], d["extras"]["parity_vs_reference"]["max_rel_dev"], d["cpu_baseline"]["value"])
 PY

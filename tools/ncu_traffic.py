@@ -19,7 +19,7 @@ def main():
     dur_i = hdr.index("gpu__time_duration.sum")
     kernels = {}
     for r in data:
-        key = "density_sweep" if "density_sweep" in r[name_i] else "force_sweep" if "force_sweep" in r[name_i] else None
+        key = "density_sweep" if "density_" in r[name_i] else "force_sweep" if "force_" in r[name_i] else None
         if key is None or key in kernels:
             continue
         rd = float(r[rd_i]) * UNIT[units[rd_i]]
