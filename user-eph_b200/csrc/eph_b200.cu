@@ -1096,15 +1096,18 @@ int env_int(const char *name, int dflt);
 // the communication and grid streams -- pack/unpack, NCCL, the grid solve -- can take SM slots while a sweep is
 // running instead of waiting for its tail): 3 % slower on one GPU and 2.5 % slower on 8 GPUs, where the NCCL kernels
 // then spin on SMs the sweep could use (profiles/r1_v10_bench_4M_8gpu*.json).  Kept as a switch, not the default.
+// A launch that only stands by for a packed sweep (SweepArgs::only_fallback) is empty in all but the steps in which the
+// displacement guard trips: one CTA per SM keeps the empty launch at ~3 us (a full resident wave costs ~6) and the rare
+// real one merely runs at reduced occupancy.
 template <class K>
-int sweep_grid(eph_b200_handle *h, K kernel, int threads, size_t smem, long long items, int per_cta) {
+int sweep_grid(eph_b200_handle *h, K kernel, int threads, size_t smem, long long items, int per_cta, bool standby = false) {
   static const int forced = env_int("EPH_B200_PERSISTENT", -1);
   const bool persistent = forced >= 0 ? forced != 0 : true;
   const long long passes = std::max<long long>(1, (items + per_cta - 1) / per_cta);
   if (!persistent) return (int)std::min<long long>((passes + 3) / 4, 1 << 22);   // four passes per CTA: short-lived CTAs
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  return (int)std::min<long long>(passes, (long long)h->sm_count * per_sm);
+  return (int)std::min<long long>(passes, (long long)h->sm_count * (standby ? 1 : per_sm));
 }
 
 int env_int(const char *name, int dflt) {
@@ -1123,7 +1126,7 @@ int launch_density(eph_b200_handle *h, const SweepArgs &a, size_t smem, bool bui
   } else {
     auto k = density_sweep_kernel<LANES, TAB, false, MULTI>;
     if (TAB) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<sweep_grid(h, k, threads, smem, a.n_work, threads / LANES), threads, smem, h->stream>>>(a);
+    k<<<sweep_grid(h, k, threads, smem, a.n_work, threads / LANES, a.only_fallback != 0), threads, smem, h->stream>>>(a);
   }
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
@@ -1134,7 +1137,7 @@ int launch_force(eph_b200_handle *h, const SweepArgs &a) {
   const int threads = EPH_THREADS_FORCE;
   KernelTimer kt(h, a.only_fallback ? "force_sweep_fallback" : "force_sweep");
   auto k = force_sweep_kernel<LANES, MULTI>;
-  k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES), threads, 0, h->stream>>>(a);
+  k<<<sweep_grid(h, k, threads, 0, a.i_end - a.i_begin, threads / LANES, a.only_fallback != 0), threads, 0, h->stream>>>(a);
   EPH_LAUNCH_CHECK(h);
   return EPH_B200_OK;
 }
@@ -2200,12 +2203,22 @@ int eph_b200_reduce_and_solve(eph_b200_handle *h, double *E_local) {
   NcclApi &api = nccl_api();
   cudaStream_t st = h->grid_stream ? h->grid_stream : h->stream;
   double *src = h->dT_e_ext ? h->dT_e_ext : h->dT_e.p;
-  {
-    KernelTimer kt(h, "source_allreduce", st);
-    EPH_NCCL(h, api.AllReduce(src, src, (size_t)h->ncell, kNcclFloat64, kNcclSum, h->comm, st));
-  }
   int z0 = 0, z1 = 0;
-  if (!(h->grid_sharded && (h->cfg.flags & EPH_B200_FDM) && grid_slab(h, &z0, &z1))) return eph_b200_end_of_step_end(h, E_local);
+  const bool slabs = h->grid_sharded && (h->cfg.flags & EPH_B200_FDM) && grid_slab(h, &z0, &z1);
+  if (!slabs) {
+    {
+      KernelTimer kt(h, "source_allreduce", st);
+      EPH_NCCL(h, api.AllReduce(src, src, (size_t)h->ncell, kNcclFloat64, kNcclSum, h->comm, st));
+    }
+    return eph_b200_end_of_step_end(h, E_local);
+  }
+  {
+    // a slab solve needs the summed source term of its own planes only: reduce-scatter (in place: the slab sits where it
+    // belongs), half the traffic of the all-reduce whose other half the all-gather of T_e below makes up for
+    KernelTimer kt(h, "source_reduce_scatter", st);
+    const size_t slab = (size_t)(z1 - z0) * h->nx * h->ny;
+    EPH_NCCL(h, api.ReduceScatter(src, src + (size_t)z0 * h->nx * h->ny, slab, kNcclFloat64, kNcclSum, h->comm, st));
+  }
   int rc = grid_plan(h, st);
   if (rc) return rc;
   const int n = h->last_substeps;

@@ -146,7 +146,13 @@ struct GridGeom {
 };
 
 __device__ __forceinline__ int wrap_cell(double x, double x0, double dx, int n) {
-  const int l = static_cast<int>(floor((x - x0) / dx));
+  // floor((x - x0) / dx) as the reference computes it.  The quotient comes from a reciprocal (a quarter of the fp64
+  // division's instructions); it can differ from the correctly rounded one by an ulp, which matters only within 1e-9 of a
+  // cell boundary -- there the division itself decides.
+  const double t = x - x0;
+  double q = t * fast_rcp(dx);
+  if (fabs(q - rint(q)) < 1e-9 * fmax(1.0, fabs(q))) q = t / dx;
+  const int l = static_cast<int>(floor(q));
   if (l >= 0 && l < n) return l;   // inside the grid: the second floor is zero
   // l - floor(double(l) / n) * n of the reference is the non-negative remainder; in integers, without a second
   // fp64 division

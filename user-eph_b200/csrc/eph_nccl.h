@@ -31,6 +31,7 @@ struct NcclApi {
   int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   std::string error;   // why loading failed
   bool ok = false;
@@ -48,6 +49,7 @@ int ncclSend(const void *, size_t, int, int, NcclComm, cudaStream_t);
 int ncclRecv(void *, size_t, int, int, NcclComm, cudaStream_t);
 int ncclAllReduce(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
 int ncclAllGather(const void *, void *, size_t, int, NcclComm, cudaStream_t);
+int ncclReduceScatter(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
 const char *ncclGetErrorString(int);
 }
 #endif
@@ -60,7 +62,7 @@ inline NcclApi &nccl_api() {
 #ifdef EPHA_HOST_EMULATION
   api.GetUniqueId = ncclGetUniqueId; api.CommInitRank = ncclCommInitRank; api.CommDestroy = ncclCommDestroy;
   api.GroupStart = ncclGroupStart; api.GroupEnd = ncclGroupEnd; api.Send = ncclSend; api.Recv = ncclRecv;
-  api.AllReduce = ncclAllReduce; api.AllGather = ncclAllGather; api.GetErrorString = ncclGetErrorString;
+  api.AllReduce = ncclAllReduce; api.AllGather = ncclAllGather; api.ReduceScatter = ncclReduceScatter; api.GetErrorString = ncclGetErrorString;
   api.ok = true;
 #else
   void *lib = nullptr;
@@ -80,7 +82,8 @@ inline NcclApi &nccl_api() {
   };
   bind(api.GetUniqueId, "ncclGetUniqueId"); bind(api.CommInitRank, "ncclCommInitRank"); bind(api.CommDestroy, "ncclCommDestroy");
   bind(api.GroupStart, "ncclGroupStart"); bind(api.GroupEnd, "ncclGroupEnd"); bind(api.Send, "ncclSend"); bind(api.Recv, "ncclRecv");
-  bind(api.AllReduce, "ncclAllReduce"); bind(api.AllGather, "ncclAllGather"); bind(api.GetErrorString, "ncclGetErrorString");
+  bind(api.AllReduce, "ncclAllReduce"); bind(api.AllGather, "ncclAllGather"); bind(api.ReduceScatter, "ncclReduceScatter");
+  bind(api.GetErrorString, "ncclGetErrorString");
   api.ok = all;
 #endif
   return api;
