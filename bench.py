@@ -418,15 +418,24 @@ def run_b200(a):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    eng.set_profiling(True)
+    # CUDA events around the two list sweeps only inside the timed region (the roofline's kernel durations): a pair of
+    # events costs about 3 us of stream time, which for all 13 kernels of a step is 9 % of a 500 k-atom brick's step
+    eng.set_profiling(2)
     l0 = eng.launch_count()
     stats0 = eng.list_stats()
     ms, _ = timed(md.step, a.steps, a.warmup + 1)
     launches = eng.launch_count() - l0
     ktimes = eng.kernel_times()
-    eng.set_profiling(False)
     stats1 = eng.list_stats()
     clocks = sampler.summary() if rank == 0 else None
+    if eng.status_word() & 0x100:
+        raise SystemExit("bench.py: a peer-memory ghost exchange timed out on rank %d (results invalid)" % rank)
+    # the other kernels: the same number of further steps with every launch bracketed, outside the timed region
+    eng.set_profiling(1)
+    ms_all, _ = timed(md.step, a.steps, a.warmup + a.steps + 1)
+    ktimes_all = eng.kernel_times()
+    eng.set_profiling(0)
+    ktimes = dict(ktimes_all, **ktimes)
     ms_per_step = ms / a.steps
     value = natoms * a.steps / (ms * 1e-3)
     rebuilds = len([k for k in range(a.warmup + 1, a.warmup + a.steps + 1) if k % REBUILD_EVERY == 0]) if a.mode == "trajectory" else 0
@@ -463,7 +472,9 @@ def run_b200(a):
                     "step": {"algorithmic_bytes_per_atom_step": b_step, "achieved": b_step * value / 1e9 / world,
                              "frac": b_step * value / 1e9 / world / peak, "note": "whole step as timed (incl. integrator hooks and list maintenance), per GPU"},
                     "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in per_kernel.items()},
-                    "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()}}
+                    "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()},
+                    "kernels_note": "the two sweeps: CUDA events on the launch stream inside the timed region; the other kernels: the %d steps "
+                                    "that follow it, every launch bracketed (%.4f ms per step with all those events)" % (a.steps, ms_all / a.steps)}
 
     # ---- multi-GPU: the same steps on the whole box on one GPU, atom by atom ----
     parity = None
@@ -492,6 +503,7 @@ def run_b200(a):
                "config": dict(workload_config(a, natoms), mean_list_length=n_nb, ghosts_rank0=ng, brick_grid=list(grid),
                               grid_solve="z-slabs + halo planes + all-gather" if sharded else "whole grid on every rank",
                               exchange_bytes_per_step_rank0=(eng.exchange_bytes if D else 0), records=eng.precision(),
+                              ghost_exchange_transport={0: None, 1: "grouped ncclSend/ncclRecv", 2: "NVLink peer memory (one kernel stores the rows into the receivers' windows)"}[eng.comm_transport()],
                               reneighbourings_in_timed_region=rebuilds,
                               list_stats={k: stats1[k] - stats0[k] for k in stats1}),
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}

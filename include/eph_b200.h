@@ -235,10 +235,18 @@ int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr);
  * (send_index: local indices, concatenated in peer order, in the order the peer expects them) and the ghost slots
  * (recv_slot: nlocal + g) that peer fills, in the order it sends them.  Ghosts that are images of the rank's own atoms
  * stay with ghost_owner >= 0 in set_atoms.  exchange_ghosts / reduce_and_solve are the two collective halves for
- * callers that drive post_force_begin/_end and end_of_step_begin themselves. */
+ * callers that drive post_force_begin/_end and end_of_step_begin themselves.
+ * Transport of the two per-step ghost exchanges ({rho, W} here, {x, v} in eph_b200_refresh_ghosts): when every rank of
+ * the communicator can map every other rank's memory (one node, NVLink / PCIe peer access) comm_init sets up windows
+ * (cudaIpc) and the exchanges become one kernel that stores the rows straight into the receivers' memory plus one that
+ * scatters them (csrc/eph_p2p.cuh); otherwise grouped ncclSend / ncclRecv.  The choice is made once, by all ranks
+ * together; EPH_B200_EXCHANGE=nccl forces send / receive, EPH_B200_P2P_WINDOW_MB (default 256) sizes the window.
+ * comm_transport: 0 no communicator, 1 NCCL send / receive, 2 peer memory.  A peer that fails to arrive within 5 s sets
+ * bit 8 of the status word instead of hanging the device. */
 #define EPH_B200_COMM_ID_BYTES 128
 int eph_b200_comm_get_id(void *id128);
 int eph_b200_comm_init(eph_b200_handle *h, const void *id128, int rank, int nranks);
+int eph_b200_comm_transport(const eph_b200_handle *h);
 int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank, const int *send_count, const int *send_index,
                            const int *recv_count, const int *recv_slot);
 int eph_b200_exchange_ghosts(eph_b200_handle *h);
@@ -322,7 +330,8 @@ int eph_b200_pack_forward(eph_b200_handle *h, int state, int n, const int *list,
 int eph_b200_unpack_forward(eph_b200_handle *h, int state, int n, int first, const double *buf);
 
 /* Per-kernel device timing with CUDA events on the launch stream (benchmarks).  kernel_times returns the number of
- * distinct kernels seen since profiling was switched on and fills up to `max` entries (total ms, launches). */
+ * distinct kernels seen since profiling was switched on and fills up to `max` entries (total ms, launches).
+ * on: 0 off, 1 every kernel (two events per launch: about 3 us of stream time each), 2 only the two list sweeps. */
 int eph_b200_set_profiling(eph_b200_handle *h, int on);
 int eph_b200_kernel_times(eph_b200_handle *h, int max, const char **names, double *ms, long long *counts);
 
@@ -331,7 +340,7 @@ int eph_b200_synchronize(eph_b200_handle *h);
 /* number of kernels this handle has launched since creation */
 long long eph_b200_launch_count(const eph_b200_handle *h);
 /* device status word: bit0 rho_i > rho_cutoff seen (eph_beta.h:174-180), bit1 T_e clamped at 0 (eph_fdm.h:391-394),
- * bit2 non-finite force */
+ * bit2 non-finite force, bit8 a peer-memory ghost exchange timed out */
 int eph_b200_status_word(eph_b200_handle *h, unsigned *out);
 
 #ifdef __cplusplus

@@ -22,6 +22,7 @@
 #include "eph_sweeps.cuh"
 #include "eph_legacy.cuh"
 #include "eph_nccl.h"
+#include "eph_p2p.cuh"
 
 using namespace ephb;
 
@@ -63,7 +64,7 @@ struct eph_b200_handle {
   long long launches = 0;
 
   // optional per-kernel timing with CUDA events on the launch stream
-  bool profiling = false;
+  int profiling = 0;   // 0 off, 1 every kernel, 2 the two list sweeps only
   struct KernelStat { const char *name; double ms = 0; long long count = 0; };
   std::vector<KernelStat> kstats;
   struct Pending { int stat; cudaEvent_t beg, end; };
@@ -147,6 +148,16 @@ struct eph_b200_handle {
   DevBuf<double> gshift;        // [nghost][3] x_ghost - x_owner
   bool gshift_valid = false;
   DevBuf<double> gm_send_xv, gm_recv_xv;   // {x, v} of the atoms other ranks hold as ghosts
+  // the same two exchanges through NVLink peer memory (eph_p2p.cuh) when every rank of the communicator can map every
+  // other rank's window (one node); NCCL send/receive otherwise
+  bool p2p_ok = false;
+  char *p2p_window = nullptr;
+  size_t p2p_window_bytes = 0, p2p_region_bytes = 0;
+  std::vector<char *> p2p_peer_window;     // by rank; own entry = p2p_window
+  P2PMap p2p_map{};
+  unsigned long long p2p_epoch[2] = {0, 0};
+  DevBuf<unsigned> p2p_done;               // finished blocks of the sending kernels, per kind
+  DevBuf<double> p2p_scratch;
   // device-resident integration (eph_b200_resident_*): x, v of all atoms and f of the local ones stay here between hooks
   DevBuf<double> res_x, res_v, res_f;
   bool resident = false, res_f_valid = false, res_pf_started = false;
@@ -265,6 +276,7 @@ struct KernelTimer {
   cudaStream_t st;
   KernelTimer(eph_b200_handle *h_, const char *name, cudaStream_t st_ = nullptr) : h(h_), st(st_ ? st_ : h_->stream) {
     if (!h->profiling) return;
+    if (h->profiling == 2 && std::strcmp(name, "density_sweep") != 0 && std::strcmp(name, "force_sweep") != 0) return;
     idx = stat_index(h, name);
     beg = take_event(h);
     cudaEventRecord(beg, st);
@@ -305,6 +317,20 @@ void drain_timers(eph_b200_handle *h) {
     if (e_ != cudaSuccess)                                                                               \
       return fail(h, EPH_B200_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// unmaps the peers' windows and frees the own one (eph_p2p.cuh)
+void p2p_teardown(eph_b200_handle *h) {
+#ifndef EPHA_HOST_EMULATION
+  for (size_t r = 0; r < h->p2p_peer_window.size(); ++r)
+    if (h->p2p_peer_window[r] && h->p2p_peer_window[r] != h->p2p_window) cudaIpcCloseMemHandle(h->p2p_peer_window[r]);
+#endif
+  h->p2p_peer_window.clear();
+  if (h->p2p_window) cudaFree(h->p2p_window);
+  h->p2p_window = nullptr;
+  h->p2p_ok = false;
+  h->p2p_done.release(); h->p2p_scratch.release();
+  cudaGetLastError();
+}
 
 // the main stream must not read T_e / write dT_e before a solve running on the grid stream has finished
 inline void join_grid_stream(eph_b200_handle *h) {
@@ -495,6 +521,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   h->rho.release(); h->w.release(); h->xi.release(); h->f_eph.release(); h->f_rng.release(); h->array8.release();
   h->f_dis.release(); h->f_sto.release();
   h->recD.release(); h->recA.release(); h->recB.release(); h->var.release();
+  p2p_teardown(h);
   if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   h->gm_send_idx.release(); h->gm_recv_slot.release(); h->gm_send_buf.release(); h->gm_recv_buf.release();
   h->gm_send_xi.release(); h->gm_recv_xi.release(); h->slab_tmp.release();
@@ -526,7 +553,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
 int eph_b200_set_profiling(eph_b200_handle *h, int on) {
   if (!h) return EPH_B200_ERR_ARG;
   drain_timers(h);
-  h->profiling = on != 0;
+  h->profiling = on < 0 ? 0 : (on > 2 ? 1 : on);
   if (on) for (auto &k : h->kstats) { k.ms = 0; k.count = 0; }
   return EPH_B200_OK;
 }
@@ -1551,6 +1578,21 @@ int eph_b200_post_force(eph_b200_handle *h, const double *x, const double *v, do
   return eph_b200_post_force_end(h, f, memspace);
 }
 
+// The stream a step's ghost exchange runs on: the main stream, or the communication stream made to wait for the boundary
+// tiles of the density pass (a counter the launch bumps, or an event behind a launch of its own).
+static int exchange_stream(eph_b200_handle *h, cudaStream_t *st) {
+  *st = h->stream;
+  if (!h->comm_stream) return EPH_B200_OK;
+  *st = h->comm_stream;
+  if (h->boundary_recorded && h->boundary_by_counter) {
+    if (stream_wait_value()(*st, (CUdeviceptr)h->done_counter.p, h->boundary_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+      return fail(h, EPH_B200_ERR_CUDA, "ghost exchange: cuStreamWaitValue32 failed");
+  } else if (h->boundary_recorded) {
+    EPH_CUDA(h, cudaStreamWaitEvent(*st, h->ev_boundary, 0));
+  }
+  return EPH_B200_OK;
+}
+
 // Ghost payload of the one exchange a step needs: {rho, Wx, Wy, Wz} per atom, device buffers.
 int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index_dev, double *buf_dev) {
   if (!h) return EPH_B200_ERR_ARG;
@@ -1558,15 +1600,8 @@ int eph_b200_pack_ghost_payload(eph_b200_handle *h, int n, const int *send_index
   if (n == 0) return EPH_B200_OK;
   cudaSetDevice(h->cfg.device);
   cudaStream_t st = h->stream;
-  if (h->comm_stream) {   // starts as soon as the boundary tiles of the density pass are done
-    st = h->comm_stream;
-    if (h->boundary_recorded && h->boundary_by_counter) {
-      if (stream_wait_value()(st, (CUdeviceptr)h->done_counter.p, h->boundary_target, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-        return fail(h, EPH_B200_ERR_CUDA, "pack_ghost_payload: cuStreamWaitValue32 failed");
-    } else if (h->boundary_recorded) {
-      EPH_CUDA(h, cudaStreamWaitEvent(st, h->ev_boundary, 0));
-    }
-  }
+  int rc = exchange_stream(h, &st);
+  if (rc) return rc;
   {
     KernelTimer kt(h, "pack_payload", st);
     pack_payload_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, send_index_dev, h->rho.p, h->W4.p, reinterpret_cast<double4 *>(buf_dev));
@@ -2059,6 +2094,74 @@ __global__ void scatter_rows_kernel(int n, const int *__restrict__ slot, double 
   if (a >= 0 && a < nrows) dst[(size_t)a * stride + c] = buf[t];
 }
 
+// Peer-memory exchange (eph_p2p.cuh): allocate and export this rank's window, learn everybody's handle through the
+// communicator itself, map them, and agree -- all ranks or none -- that the exchanges go that way.  Failing to map a
+// peer (another node, no peer access) is not an error: the NCCL send / receive path stays.
+int p2p_setup(eph_b200_handle *h) {
+  p2p_teardown(h);
+#ifndef EPHA_HOST_EMULATION
+  NcclApi &api = nccl_api();
+  struct Record { cudaIpcMemHandle_t handle; unsigned long long bytes; int want; int pad; };
+  const char *mode = std::getenv("EPH_B200_EXCHANGE");
+  const char *mb = std::getenv("EPH_B200_P2P_WINDOW_MB");
+  Record mine{};
+  mine.bytes = (unsigned long long)std::max(8LL, mb ? std::atoll(mb) : 256LL) << 20;
+  mine.want = !(mode && std::strcmp(mode, "nccl") == 0) && h->comm_size > 1 && h->comm_size <= kP2PMaxRanks;
+  if (mine.want) {
+    void *w = nullptr;
+    if (cudaMalloc(&w, mine.bytes) != cudaSuccess || cudaMemset(w, 0, kP2PHeaderBytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.handle, w) != cudaSuccess) {
+      cudaGetLastError();
+      if (w) cudaFree(w);
+      mine.want = 0;
+    } else {
+      h->p2p_window = static_cast<char *>(w);
+      h->p2p_window_bytes = mine.bytes;
+    }
+  }
+  const int n = h->comm_size;
+  DevBuf<unsigned char> rec;
+  EPH_CUDA(h, rec.reserve(sizeof(Record) * (size_t)n));
+  EPH_CUDA(h, cudaMemcpy(rec.p + sizeof(Record) * (size_t)h->comm_rank, &mine, sizeof(Record), cudaMemcpyHostToDevice));
+  EPH_CUDA(h, cudaDeviceSynchronize());   // the window's cleared header and the record precede the collective on h->stream
+  EPH_NCCL(h, api.AllGather(rec.p + sizeof(Record) * (size_t)h->comm_rank, rec.p, sizeof(Record), kNcclInt8, h->comm, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<Record> all((size_t)n);
+  EPH_CUDA(h, cudaMemcpy(all.data(), rec.p, sizeof(Record) * (size_t)n, cudaMemcpyDeviceToHost));
+  rec.release();
+  int ok = mine.want;
+  for (int r = 0; r < n; ++r)
+    if (!all[r].want || all[r].bytes != mine.bytes) ok = 0;
+  h->p2p_peer_window.assign((size_t)n, nullptr);
+  if (ok) {
+    for (int r = 0; r < n && ok; ++r) {
+      if (r == h->comm_rank) { h->p2p_peer_window[r] = h->p2p_window; continue; }
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+      else h->p2p_peer_window[r] = static_cast<char *>(ptr);
+    }
+  }
+  EPH_CUDA(h, h->p2p_scratch.reserve(2));
+  EPH_CUDA(h, h->p2p_done.reserve(2));
+  EPH_CUDA(h, cudaMemset(h->p2p_done.p, 0, 2 * sizeof(unsigned)));
+  const double okd = ok;
+  double sum = 0.0;
+  EPH_CUDA(h, cudaMemcpy(h->p2p_scratch.p, &okd, sizeof(double), cudaMemcpyHostToDevice));
+  EPH_CUDA(h, cudaDeviceSynchronize());
+  EPH_NCCL(h, api.AllReduce(h->p2p_scratch.p, h->p2p_scratch.p, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  EPH_CUDA(h, cudaMemcpy(&sum, h->p2p_scratch.p, sizeof(double), cudaMemcpyDeviceToHost));
+  if (sum == (double)n) {
+    h->p2p_ok = true;
+    h->p2p_region_bytes = (h->p2p_window_bytes - kP2PHeaderBytes) / (size_t)n / 512 * 512;
+    h->p2p_epoch[0] = h->p2p_epoch[1] = 0;
+  } else {
+    p2p_teardown(h);
+  }
+#endif
+  return EPH_B200_OK;
+}
+
 // z-planes [z0, z1) this rank advances in a sharded solve; false if the grid does not divide
 bool grid_slab(const eph_b200_handle *h, int *z0, int *z1) {
   if (h->comm_size < 1 || h->nz % h->comm_size) return false;
@@ -2096,7 +2199,12 @@ int eph_b200_comm_init(eph_b200_handle *h, const void *id128, int rank, int nran
   h->comm_rank = rank;
   h->comm_size = nranks;
   h->ghost_map_set = false;
-  return EPH_B200_OK;
+  return p2p_setup(h);
+}
+
+int eph_b200_comm_transport(const eph_b200_handle *h) {
+  if (!h || !h->comm || h->comm_size < 2) return 0;
+  return h->p2p_ok ? 2 : 1;
 }
 
 int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank, const int *send_count, const int *send_index,
@@ -2126,6 +2234,29 @@ int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank,
   if (ns) EPH_CUDA(h, cudaMemcpyAsync(h->gm_send_idx.p, send_index, ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (nr) EPH_CUDA(h, cudaMemcpyAsync(h->gm_recv_slot.p, recv_slot, nr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+#ifndef EPHA_HOST_EMULATION
+  if (h->p2p_ok) {
+    if (npeers > kP2PMaxPeers)
+      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d peers, the peer-memory exchange takes %d (EPH_B200_EXCHANGE=nccl selects send/receive)", npeers, kP2PMaxPeers);
+    P2PMap &m = h->p2p_map;
+    m = P2PMap{};
+    m.n = npeers; m.my_rank = h->comm_rank; m.local = h->p2p_window; m.region_bytes = h->p2p_region_bytes;
+    for (int p = 0; p < npeers; ++p) {
+      m.rank[p] = peer_rank[p];
+      m.send_off[p + 1] = m.send_off[p] + send_count[p];
+      m.recv_off[p + 1] = m.recv_off[p] + recv_count[p];
+      m.remote[p] = h->p2p_peer_window[peer_rank[p]];
+      const size_t need = p2p_half_bytes_needed(std::max(send_count[p], recv_count[p]));
+      if (need > m.region_bytes / 2)
+        return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d ghost rows for rank %d need %zu bytes of its window, a rank's share is %zu "
+                    "(raise EPH_B200_P2P_WINDOW_MB on all ranks, or EPH_B200_EXCHANGE=nccl)", std::max(send_count[p], recv_count[p]),
+                    peer_rank[p], need, m.region_bytes / 2);
+    }
+    // re-registration is collective: nobody writes rows of the new map into a window whose owner may still be reading
+    // rows of the old one (with an unchanged set of peers the exchanges themselves guarantee that)
+    EPH_NCCL(h, nccl_api().AllReduce(h->p2p_scratch.p + 1, h->p2p_scratch.p + 1, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+  }
+#endif
   h->ghost_map_set = true;
   // with a communication stream registered the density pass sweeps the tiles these atoms live in first
   if (h->comm_stream && ns > 0) return eph_b200_set_boundary_atoms(h, (int)ns, h->gm_send_idx.p, EPH_B200_DEVICE);
@@ -2144,6 +2275,34 @@ int eph_b200_exchange_ghosts(eph_b200_handle *h) {
   const bool with_xi = h->pf_xi != nullptr && (h->cfg.flags & EPH_B200_RANDOM);
   cudaStream_t st = h->comm_stream ? h->comm_stream : h->stream;
   int rc;
+#ifndef EPHA_HOST_EMULATION
+  if (h->p2p_ok) {
+    // peer memory: the sending kernel stores the rows into the receivers' windows and raises its flag there
+    if ((rc = exchange_stream(h, &st))) return rc;
+    const P2PMap &m = h->p2p_map;
+    if (m.n > 0) {
+      const unsigned long long epoch = ++h->p2p_epoch[0];
+      const int cap = 2 * h->sm_count;   // all blocks resident: the receiving blocks poll
+      {
+        KernelTimer kt(h, "pack_payload", st);
+        p2p_send_payload_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nsend, 256))), 256, 0, st>>>(
+            m, h->gm_nsend, h->gm_send_idx.p, h->rho.p, h->W4.p, with_xi ? h->xi.p : nullptr, epoch, h->p2p_done.p);
+      }
+      EPH_LAUNCH_CHECK(h);
+      {
+        KernelTimer kt(h, "unpack_payload", st);
+        p2p_recv_payload_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nrecv, 256))), 256, 0, st>>>(
+            m, h->gm_nrecv, h->gm_recv_slot.p, h->rho.p, h->W4.p, with_xi ? h->xi.p : nullptr, h->nlocal + h->nghost, epoch, h->d_status.p);
+      }
+      EPH_LAUNCH_CHECK(h);
+    }
+    if (h->comm_stream) {   // post_force_end waits for the ghosts' {rho, W}
+      EPH_CUDA(h, cudaEventRecord(h->ev_unpacked, st));
+      h->unpack_pending = true;
+    }
+    return EPH_B200_OK;
+  }
+#endif
   if (h->gm_nsend) {
     if ((rc = eph_b200_pack_ghost_payload(h, h->gm_nsend, h->gm_send_idx.p, h->gm_send_buf.p))) return rc;
     if (with_xi) {
@@ -2303,13 +2462,28 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
   if (!h->atoms_set) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: set_atoms not called");
   if (!x || !v) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: null x or v");
   const int nl = h->nlocal, ng = h->nghost;
-  if (ng == 0) return EPH_B200_OK;
-  if (!h->has_owner) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: set_atoms was given no ghost owners");
   const bool remote = h->comm && h->comm_size > 1;
+  if (ng == 0 && !(remote && h->ghost_map_set && (h->gm_nsend || h->gm_nrecv || h->p2p_map.n > 0))) return EPH_B200_OK;
+  if (ng > 0 && !h->has_owner) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: set_atoms was given no ghost owners");
   if (remote && !h->ghost_map_set) return fail(h, EPH_B200_ERR_ARG, "refresh_ghosts: eph_b200_set_ghost_map must follow every set_atoms");
   cudaSetDevice(h->cfg.device);
   const int record = h->gshift_valid ? 0 : 1;
-  EPH_CUDA(h, h->gshift.reserve(3 * (size_t)ng));
+  EPH_CUDA(h, h->gshift.reserve(3 * (size_t)std::max(ng, 1)));
+#ifndef EPHA_HOST_EMULATION
+  if (remote && h->p2p_ok) {
+    const P2PMap &m = h->p2p_map;
+    if (m.n > 0) {
+      const unsigned long long epoch = ++h->p2p_epoch[1];
+      const int cap = 2 * h->sm_count;
+      p2p_send_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nsend, 256))), 256, 0, h->stream>>>(m, h->gm_nsend, h->gm_send_idx.p, x, v, epoch,
+                                                                                                        h->p2p_done.p + 1);
+      EPH_LAUNCH_CHECK(h);
+      p2p_recv_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nrecv, 256))), 256, 0, h->stream>>>(m, h->gm_nrecv, h->gm_recv_slot.p, nl, x, v,
+                                                                                                        h->gshift.p, record, epoch, h->d_status.p);
+      EPH_LAUNCH_CHECK(h);
+    }
+  } else
+#endif
   if (remote && (h->gm_nsend || h->gm_nrecv)) {
     NcclApi &api = nccl_api();
     EPH_CUDA(h, h->gm_send_xv.reserve(6 * std::max<size_t>(h->gm_nsend, 1))); EPH_CUDA(h, h->gm_recv_xv.reserve(6 * std::max<size_t>(h->gm_nrecv, 1)));
@@ -2331,8 +2505,10 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
       EPH_LAUNCH_CHECK(h);
     }
   }
-  ghost_images_kernel<<<blocks_for(ng, 256), 256, 0, h->stream>>>(nl, ng, h->owner.p, x, v, h->gshift.p, record);
-  EPH_LAUNCH_CHECK(h);
+  if (ng > 0) {
+    ghost_images_kernel<<<blocks_for(ng, 256), 256, 0, h->stream>>>(nl, ng, h->owner.p, x, v, h->gshift.p, record);
+    EPH_LAUNCH_CHECK(h);
+  }
   h->gshift_valid = true;
   return EPH_B200_OK;
 }

@@ -198,6 +198,8 @@ struct PackedArgs {
 // keeps the neighbours closer than r_c + inner_skin in list order (ballot + popc) and writes them into the atom's slots
 // of its tile; a warp does the atoms of one tile in turn so that it can pad all of them to the tile's longest list
 // (see below).  Exact fp64 positions decide membership, like in density_sweep_kernel<BUILD>.
+constexpr int kBuildChunks = 5;
+
 template <int LANES, bool MULTI>
 __global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const double4 *__restrict__ pos4) {
   constexpr int TILE = 32 / LANES;
@@ -216,22 +218,35 @@ __global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const dou
         if (double_to_bits(pi.w) & kBitGroup) {   // atoms outside the group have no list (their rho and w stay zero)
           const long long row = a.offsets[i];
           const int n = static_cast<int>(a.offsets[i + 1] - row);
-          for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            bool in = false;
-            int j = 0;
-            if (k < n) {
-              j = ld_stream(a.neigh + row + k) & kNeighMask;
-              const double4 pj = ld256(pos4 + j);
-              const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
-              in = ex * ex + ey * ey + ez * ez < a.r_inner_sq;
+          // kBuildChunks runs of 32 entries per trip: all their indices, then all their positions are requested before
+          // the first one is tested, so a lane has that many gathers in flight (a 136-entry row is one trip)
+          for (int k0 = 0; k0 < n; k0 += 32 * kBuildChunks) {
+            int j[kBuildChunks];
+            bool in[kBuildChunks];
+#pragma unroll
+            for (int u = 0; u < kBuildChunks; ++u) {
+              const int k = k0 + 32 * u + lane;
+              j[u] = k < n ? (ld_stream(a.neigh + row + k) & kNeighMask) : -1;
             }
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, in);
-            if (in) {
-              const int c = cnt + __popc(bal & below);
-              a.ineigh[t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1))] = j;
+#pragma unroll
+            for (int u = 0; u < kBuildChunks; ++u) {
+              in[u] = false;
+              if (j[u] >= 0) {
+                const double4 pj = ld256(pos4 + j[u]);
+                const double ex = pj.x - pi.x, ey = pj.y - pi.y, ez = pj.z - pi.z;
+                in[u] = ex * ex + ey * ey + ez * ez < a.r_inner_sq;
+              }
             }
-            cnt += __popc(bal);
+#pragma unroll
+            for (int u = 0; u < kBuildChunks; ++u) {
+              if (k0 + 32 * u >= n) break;   // warp-uniform
+              const unsigned bal = __ballot_sync(0xFFFFFFFFu, in[u]);
+              if (in[u]) {
+                const int c = cnt + __popc(bal & below);
+                a.ineigh[t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1))] = j[u];
+              }
+              cnt += __popc(bal);
+            }
           }
         }
         if (lane == 0) a.icount[i] = cnt;

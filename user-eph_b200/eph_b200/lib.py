@@ -69,6 +69,7 @@ SYMBOLS = {
     "eph_b200_grid_device_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "eph_b200_comm_get_id": (C.c_int, [C.c_void_p]),
     "eph_b200_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "eph_b200_comm_transport": (C.c_int, [C.c_void_p]),
     "eph_b200_set_ghost_map": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "eph_b200_exchange_ghosts": (C.c_int, [C.c_void_p]),
     "eph_b200_set_grid_sharding": (C.c_int, [C.c_void_p, C.c_int]),
@@ -367,6 +368,10 @@ class Engine:
     def comm_init(self, id_bytes, rank, nranks):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
         self._check(self.lib.eph_b200_comm_init(self.h, buf, rank, nranks))
+
+    def comm_transport(self):
+        """0 no communicator, 1 NCCL send / receive, 2 NVLink peer memory (eph_p2p.cuh)"""
+        return int(self.lib.eph_b200_comm_transport(self.h))
 
     def set_ghost_map(self, plan):
         """plan: eph_b200.parallel.ExchangePlan (who holds which of my atoms as ghosts, who fills which of my ghost slots)"""
