@@ -160,6 +160,7 @@ struct eph_b200_handle {
   DevBuf<double> p2p_scratch;
   // device-resident integration (eph_b200_resident_*): x, v of all atoms and f of the local ones stay here between hooks
   DevBuf<double> res_x, res_v, res_f;
+  DevBuf<double> res_fe;        // this step's f_EPH + f_RNG, formed while the pair forces are still on their way up
   bool resident = false, res_f_valid = false, res_pf_started = false;
   bool grid_sharded = false;    // every rank advances only its z-slab of the grid (halo planes + all-gather)
   DevBuf<double> slab_tmp;
@@ -525,7 +526,7 @@ int eph_b200_destroy(eph_b200_handle *h) {
   if (h->comm) { nccl_api().CommDestroy(h->comm); h->comm = nullptr; }
   h->gm_send_idx.release(); h->gm_recv_slot.release(); h->gm_send_buf.release(); h->gm_recv_buf.release();
   h->gm_send_xi.release(); h->gm_recv_xi.release(); h->slab_tmp.release();
-  h->gshift.release(); h->gm_send_xv.release(); h->gm_recv_xv.release(); h->res_x.release(); h->res_v.release(); h->res_f.release();
+  h->gshift.release(); h->gm_send_xv.release(); h->gm_recv_xv.release(); h->res_x.release(); h->res_v.release(); h->res_f.release(); h->res_fe.release();
   h->off.release(); h->neigh.release();
   h->T[0].release(); h->T[1].release(); h->dT_e.release(); h->S_e.release(); h->rho_e.release(); h->C_e.release();
   h->kappa_e.release(); h->flag.release(); h->t_dyn.release(); h->C_T_tab.release(); h->K_T_tab.release(); h->E_T_tab.release();
@@ -2416,6 +2417,10 @@ int eph_b200_reduce_and_solve(eph_b200_handle *h, double *E_local) {
 // ---------------------------------------------------------------------------
 namespace {
 
+__global__ void add_rows_kernel(long long n, double *__restrict__ dst, const double *__restrict__ src) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) dst[t] += src[t];
+}
+
 // own periodic images: x_ghost = x_owner + shift, v_ghost = v_owner; record = 1 stores the shifts instead
 __global__ void ghost_images_kernel(int nlocal, int nghost, const int *__restrict__ owner, double *__restrict__ x, double *__restrict__ v,
                                     double *__restrict__ shift, int record) {
@@ -2562,11 +2567,11 @@ int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, con
   // x travels to the host on the copy stream while the main stream goes on: ghosts follow their owners and, if the caller
   // knows that LAMMPS will not re-neighbour in this step, the first half of post_force (records, density pass) starts
   // right away -- it needs x and v only, so it runs while the host computes its pair forces
-  if (x_out) {
-    EPH_CUDA(h, cudaEventRecord(h->f_event, h->stream));
-    EPH_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->f_event, 0));
-    EPH_CUDA(h, cudaMemcpyAsync(x_out, h->res_x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
-  }
+  // whatever the copy stream does next (x down; this step's pair forces up, into the array the kick has just read) comes
+  // after the kick
+  EPH_CUDA(h, cudaEventRecord(h->f_event, h->stream));
+  EPH_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->f_event, 0));
+  if (x_out) EPH_CUDA(h, cudaMemcpyAsync(x_out, h->res_x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
   int rc = eph_b200_refresh_ghosts(h, h->res_x.p, h->res_v.p);
   if (rc) return rc;
   if (start_post_force_step >= 0 && h->neigh_set) {
@@ -2600,8 +2605,16 @@ int eph_b200_resident_post_force(eph_b200_handle *h, const double *f, double *f_
   } else if ((rc = eph_b200_post_force_begin(h, h->res_x.p, h->res_v.p, dxi, ntimestep, EPH_B200_DEVICE))) return rc;
   h->res_pf_started = false;
   if (h->comm && h->comm_size > 1 && (rc = eph_b200_exchange_ghosts(h))) return rc;
-  if (nl > 0) EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));
-  if ((rc = eph_b200_post_force_end(h, h->res_f.p, EPH_B200_DEVICE))) return rc;
+  // the force pass does not wait for the pair forces: it adds into a cleared array of its own, which joins the uploaded
+  // forces once both are there (f = f_pair + (f_EPH + f_RNG))
+  EPH_CUDA(h, h->res_fe.reserve(3 * std::max<size_t>(nl, 1)));
+  if (nl > 0) EPH_CUDA(h, cudaMemsetAsync(h->res_fe.p, 0, 3 * (size_t)nl * sizeof(double), h->stream));
+  if ((rc = eph_b200_post_force_end(h, h->res_fe.p, EPH_B200_DEVICE))) return rc;
+  if (nl > 0) {
+    EPH_CUDA(h, cudaStreamWaitEvent(h->stream, h->f_event, 0));
+    add_rows_kernel<<<std::min(blocks_for(3LL * nl, 256), 16 * h->sm_count), 256, 0, h->stream>>>(3LL * nl, h->res_f.p, h->res_fe.p);
+    EPH_LAUNCH_CHECK(h);
+  }
   h->res_f_valid = true;
   if (nl > 0 && f_out) {
     EPH_CUDA(h, cudaMemcpyAsync(f_out, h->res_f.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
