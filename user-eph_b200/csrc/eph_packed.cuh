@@ -198,11 +198,22 @@ struct PackedArgs {
 // keeps the neighbours closer than r_c + inner_skin in list order (ballot + popc) and writes them into the atom's slots
 // of its tile; a warp does the atoms of one tile in turn so that it can pad all of them to the tile's longest list
 // (see below).  Exact fp64 positions decide membership, like in density_sweep_kernel<BUILD>.
-constexpr int kBuildChunks = 5;
+#ifndef EPH_BUILD_CHUNKS
+#define EPH_BUILD_CHUNKS 5
+#endif
+#ifndef EPH_STAGE_ENTRIES
+#define EPH_STAGE_ENTRIES 1536
+#endif
+constexpr int kBuildChunks = EPH_BUILD_CHUNKS;
+constexpr int kStageEntries = EPH_STAGE_ENTRIES;   // list slots of a tile staged in shared memory per warp (6 KB): 96 per atom at 2 lanes
 
 template <int LANES, bool MULTI>
 __global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const double4 *__restrict__ pos4) {
   constexpr int TILE = 32 / LANES;
+  // The kept neighbours of an atom land 8 bytes per 128-byte line of the tile layout: written straight to global memory
+  // they cost as many L1 wavefronts as the gathers.  The warp assembles its tile here and copies it out in whole lines.
+  __shared__ int s_stage[8][kStageEntries];
+  int *stage = s_stage[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned below = (1u << lane) - 1u;
   const int warps_per_block = blockDim.x >> 5;
@@ -243,7 +254,9 @@ __global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const dou
               const unsigned bal = __ballot_sync(0xFFFFFFFFu, in[u]);
               if (in[u]) {
                 const int c = cnt + __popc(bal & below);
-                a.ineigh[t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1))] = j[u];
+                const int pos = (c / LANES) * 32 + t * LANES + (c & (LANES - 1));
+                if (pos < kStageEntries) stage[pos] = j[u];
+                else a.ineigh[t0 + pos] = j[u];
               }
               cnt += __popc(bal);
             }
@@ -255,18 +268,28 @@ __global__ void __launch_bounds__(256) inner_build_kernel(SweepArgs a, const dou
       tmax = max(tmax, cnt);
     }
     // padding: every atom's slots up to the tile's longest list, rounded up to kPadIters iterations, hold the atom's own
-    // index and a zero pair weight
+    // index and a zero pair weight.  Lane l owns column l of the tile: atom l / LANES, every LANES-th list position.
     const int padded = (tmax + kPadIters * LANES - 1) / (kPadIters * LANES) * (kPadIters * LANES);
-    for (int t = 0; t < TILE; ++t) {
-      const int i = tile * TILE + t;
-      const int cnt = __shfl_sync(0xFFFFFFFFu, cnt_mine, t);
-      for (int c = cnt + lane; c < padded; c += 32) {
-        const long long dst = t0 + (long long)(c / LANES) * 32 + t * LANES + (c & (LANES - 1));
-        a.ineigh[dst] = i < a.nlocal ? i : 0;
-        st_stream(a.gpair + dst, 0.0);
-        if (MULTI) st_stream(a.gpair_i + dst, 0.0);
+    const int rows = padded / LANES;                      // warp iterations of the sweeps over this tile
+    const int t_mine = lane / LANES;
+    const int i_mine = tile * TILE + t_mine;
+    const int self = i_mine < a.nlocal ? i_mine : 0;
+    const int cnt_col = __shfl_sync(0xFFFFFFFFu, cnt_mine, t_mine);
+    __syncwarp();
+    for (int r = 0; r < rows; ++r) {
+      const int pos = r * 32 + lane;
+      const int c = r * LANES + (lane & (LANES - 1));
+      const bool pad = c >= cnt_col;
+      int v;
+      if (pos < kStageEntries) v = pad ? self : stage[pos];
+      else v = pad ? self : a.ineigh[t0 + pos];
+      a.ineigh[t0 + pos] = v;                              // whole 128-byte lines
+      if (pad) {
+        st_stream(a.gpair + t0 + pos, 0.0);
+        if (MULTI) st_stream(a.gpair_i + t0 + pos, 0.0);
       }
     }
+    __syncwarp();
   }
 }
 
