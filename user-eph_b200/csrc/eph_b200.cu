@@ -419,8 +419,8 @@ bool packed_possible(const eph_b200_handle *h) {
 }
 }  // namespace
 
-static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total);
-static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready);
+static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total, const long long *total_pending);
+static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready, bool inner_filled);
 
 extern "C" {
 
@@ -893,7 +893,7 @@ int eph_b200_set_atoms(eph_b200_handle *h, int nlocal, int nghost, const int *ty
     EPH_CUDA(h, cudaMemsetAsync(h->f_dis.p, 0, h->f_dis.cap * sizeof(double), h->stream));
     EPH_CUDA(h, cudaMemsetAsync(h->f_sto.p, 0, h->f_sto.cap * sizeof(double), h->stream));
   }
-  EPH_CUDA(h, cudaStreamSynchronize(h->stream));  // host source buffers may be reused by the caller
+  if (memspace != EPH_B200_DEVICE) EPH_CUDA(h, cudaStreamSynchronize(h->stream));  // host source buffers may be reused by the caller
   h->nlocal = nlocal; h->nghost = nghost;
   h->atoms_set = true;
   h->peratom_valid = false;
@@ -914,10 +914,15 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
   cudaSetDevice(h->cfg.device);
   long long total = 0;
   if (memspace == EPH_B200_DEVICE) {
-    EPH_CUDA(h, cudaMemcpyAsync(&total, offsets + nlocal, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
-    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    // the list length comes down together with the size of the tile storage: one synchronisation for both
+    long long *pinned_total = reinterpret_cast<long long *>(h->h_pinned + 6);
+    EPH_CUDA(h, cudaMemcpyAsync(pinned_total, offsets + nlocal, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     h->off_ptr = reinterpret_cast<const long long *>(offsets);
     h->neigh_ptr = neigh;
+    int rc = prepare_tiles(h, nlocal, 0, pinned_total);
+    if (rc) return rc;
+    if (*pinned_total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
+    return register_list(h, nlocal, *pinned_total, true, false);
   } else {
     total = offsets[nlocal];
     EPH_CUDA(h, h->off.reserve((size_t)nlocal + 1));
@@ -929,16 +934,17 @@ int eph_b200_set_neighbors_csr(eph_b200_handle *h, int nlocal, const int64_t *of
     h->neigh_ptr = h->neigh.p;
   }
   if (total < 0) return fail(h, EPH_B200_ERR_ARG, "set_neighbors: negative list length");
-  return register_list(h, nlocal, total, false);
+  return register_list(h, nlocal, total, false, false);
 }
 
 }  // extern "C"
 
 // Common tail of the ways a full list reaches the engine: tile storage of the inner list sized from the rows, pair-weight
-// slots, list state.  tiles_ready: eph_b200_build_neighbors has sized the tiles already (and filled them).
-static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready) {
+// slots, list state.  tiles_ready: the caller has sized the tiles already; inner_filled: eph_b200_build_neighbors has
+// written the inner list into them as well.
+static int register_list(eph_b200_handle *h, int nlocal, long long total, bool tiles_ready, bool inner_filled) {
   if (!tiles_ready) {
-    int rc = prepare_tiles(h, nlocal, total);
+    int rc = prepare_tiles(h, nlocal, total, nullptr);
     if (rc) return rc;
   }
   EPH_CUDA(h, cudaMemsetAsync(h->lstate.p, 0, sizeof(ListState), h->stream));
@@ -946,15 +952,18 @@ static int register_list(eph_b200_handle *h, int nlocal, long long total, bool t
   h->have_inner = false;
   h->inner_gave_up = false;
   h->flag_pending = false;
-  h->inner_prebuilt = tiles_ready && h->inner_enabled;
+  h->inner_prebuilt = inner_filled && h->inner_enabled;
   h->n_entries = total;
   h->neigh_set = true;
   return EPH_B200_OK;
 }
 
-static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total) {
+// total_pending: the list length is still on its way to the host (pinned); it is there after this function's own
+// synchronisation, or after the one done here if the tiles need none
+static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total, const long long *total_pending) {
   h->inner_enabled = h->inner_wanted;
   long long slots = total;   // pair-weight slots: CSR rows of LAMMPS' list or, usually larger, the tiles of the inner list
+  bool synced = false;
   if (h->inner_enabled && nlocal > 0) {
     const int tile_atoms = 32 / h->lanes;
     const int ntiles = (nlocal + tile_atoms - 1) / tile_atoms;
@@ -967,11 +976,17 @@ static int prepare_tiles(eph_b200_handle *h, int nlocal, long long total) {
     EPH_CUDA(h, h->nb_tmp.reserve(scan_bytes));
     EPH_CUDA(h, cub::DeviceScan::ExclusiveSum(h->nb_tmp.p, scan_bytes, h->tile_caps.p, h->tile_off.p, ntiles + 1, h->stream));
     ++h->launches;
-    long long tiled = 0;
-    EPH_CUDA(h, cudaMemcpyAsync(&tiled, h->tile_off.p + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    long long *tiled = reinterpret_cast<long long *>(h->h_pinned + 7);
+    EPH_CUDA(h, cudaMemcpyAsync(tiled, h->tile_off.p + ntiles, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
     EPH_CUDA(h, cudaStreamSynchronize(h->stream));
-    EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(tiled, 1)));
-    slots = std::max(slots, tiled);
+    synced = true;
+    if (total_pending) slots = *total_pending;
+    EPH_CUDA(h, h->ineigh.reserve((size_t)std::max<long long>(*tiled, 1)));
+    slots = std::max(slots, *tiled);
+  }
+  if (total_pending && !synced) {
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    slots = *total_pending;
   }
   EPH_CUDA(h, h->gpair.reserve((size_t)std::max<long long>(slots, 1)));
   if (h->n_el > 1) EPH_CUDA(h, h->gpair_i.reserve((size_t)std::max<long long>(slots, 1)));
@@ -1061,7 +1076,7 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
     // writes the inner list (same rows, cut at r_c + inner_skin) into its tiles and no second walk of the new list is needed.
     h->off_ptr = h->off.p;
     h->neigh_ptr = h->neigh.p;
-    int rc = prepare_tiles(h, nl, total);
+    int rc = prepare_tiles(h, nl, total, nullptr);
     if (rc) return rc;
     InnerOut io{};
     const bool prebuild = h->inner_enabled && packed_possible(h);
@@ -1079,7 +1094,7 @@ int eph_b200_build_neighbors(eph_b200_handle *h, const double *x, double cutoff,
           nl, h->lanes, h->tile_off.p, h->icount.p, h->ineigh.p, h->gpair.p, h->n_el > 1 ? h->gpair_i.p : nullptr);
       EPH_LAUNCH_CHECK(h);
     }
-    return register_list(h, nl, total, prebuild);
+    return register_list(h, nl, total, true, prebuild);
   }
   EPH_LAUNCH_CHECK(h);
   // hand the device-resident CSR to the common path (aliases our own buffers: no copy)

@@ -375,12 +375,16 @@ class Engine:
 
     def set_ghost_map(self, plan):
         """plan: eph_b200.parallel.ExchangePlan (who holds which of my atoms as ghosts, who fills which of my ghost slots)"""
-        peers = [r for r in range(plan.world) if r != plan.rank and (plan.send_counts[r] or plan.recv_counts[r])]
-        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
-        pr, sc, rc = i32(peers), i32([plan.send_counts[r] for r in peers]), i32([plan.recv_counts[r] for r in peers])
-        si = i32(np.concatenate([plan.send_index[r] for r in peers]) if peers else [])
-        rs = i32(np.concatenate([plan.recv_index[r] for r in peers]) if peers else [])
-        self._check(self.lib.eph_b200_set_ghost_map(self.h, len(peers), pr.ctypes.data, sc.ctypes.data, si.ctypes.data,
+        cached = getattr(plan, "_ghost_map_arrays", None)   # a plan does not change: flatten it once
+        if cached is None:
+            peers = [r for r in range(plan.world) if r != plan.rank and (plan.send_counts[r] or plan.recv_counts[r])]
+            i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+            pr, sc, rc = i32(peers), i32([plan.send_counts[r] for r in peers]), i32([plan.recv_counts[r] for r in peers])
+            si = i32(np.concatenate([plan.send_index[r] for r in peers]) if peers else [])
+            rs = i32(np.concatenate([plan.recv_index[r] for r in peers]) if peers else [])
+            cached = plan._ghost_map_arrays = (len(peers), pr, sc, si, rc, rs)
+        n, pr, sc, si, rc, rs = cached
+        self._check(self.lib.eph_b200_set_ghost_map(self.h, n, pr.ctypes.data, sc.ctypes.data, si.ctypes.data,
                                                     rc.ctypes.data, rs.ctypes.data))
         self.exchange_bytes = 32 * (len(si) + len(rs))
 
