@@ -17,6 +17,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
+
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "simt.h"
 
@@ -71,6 +79,7 @@ inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 template <class T> inline T __ldcs(const T *p) { return *p; }
 template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
 inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
@@ -131,7 +140,67 @@ template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) {
   *p = static_cast<T *>(std::malloc(n ? n : 1));
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+// ---- memory another process can map (cudaIpc*): POSIX shared-memory objects, so that the peer-memory ghost exchange
+// (csrc/eph_p2p.cuh) runs between the CPU ranks of the multi-process tests.  emul_ipc_malloc stands in for the cudaMalloc
+// of an exported allocation; the handle carries the object's name and size.
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+struct EmulIpcRegion { std::string name; size_t bytes; bool owner; };
+inline std::map<void *, EmulIpcRegion> &emul_ipc_regions() { static std::map<void *, EmulIpcRegion> m; return m; }
+inline cudaError_t emul_ipc_malloc(void **p, size_t n) {
+  static int counter = 0;
+  char name[64];
+  std::snprintf(name, sizeof name, "/ephb_emul_%d_%d", (int)getpid(), counter++);
+  const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return cudaErrorMemoryAllocation;
+  if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); return cudaErrorMemoryAllocation; }
+  void *q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) { shm_unlink(name); return cudaErrorMemoryAllocation; }
+  emul_ipc_regions()[q] = EmulIpcRegion{name, n, true};
+  *p = q;
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  auto it = emul_ipc_regions().find(p);
+  if (it == emul_ipc_regions().end() || !it->second.owner) return cudaErrorNotSupported;
+  std::memset(h, 0, sizeof *h);
+  std::strncpy(h->reserved, it->second.name.c_str(), 47);
+  const unsigned long long n = it->second.bytes;
+  std::memcpy(h->reserved + 48, &n, 8);
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  unsigned long long n = 0;
+  std::memcpy(&n, h.reserved + 48, 8);
+  h.reserved[47] = 0;
+  const int fd = shm_open(h.reserved, O_RDWR, 0600);
+  if (fd < 0) return cudaErrorNotSupported;
+  void *q = mmap(nullptr, (size_t)n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) return cudaErrorNotSupported;
+  emul_ipc_regions()[q] = EmulIpcRegion{h.reserved, (size_t)n, false};
+  *p = q;
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void *p) {
+  auto it = emul_ipc_regions().find(p);
+  if (it == emul_ipc_regions().end() || it->second.owner) return cudaErrorNotSupported;
+  munmap(p, it->second.bytes);
+  emul_ipc_regions().erase(it);
+  return cudaSuccess;
+}
+inline cudaError_t cudaFree(void *p) {
+  auto it = emul_ipc_regions().find(p);
+  if (it != emul_ipc_regions().end()) {
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    emul_ipc_regions().erase(it);
+    return cudaSuccess;
+  }
+  std::free(p);
+  return cudaSuccess;
+}
 inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t n) { std::memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }

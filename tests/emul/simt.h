@@ -7,6 +7,7 @@
 // hardware requires, so mismatched masks or divergent barriers show up as a reported dead-lock instead of passing
 // silently.  Single host thread: atomics are plain read-modify-writes, results are deterministic.
 #pragma once
+#include <sched.h>
 
 #include <ucontext.h>
 
@@ -236,6 +237,8 @@ inline T from_bits(uint64_t u) {
 inline void __syncthreads() { simt::syncthreads(); }
 inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { simt::collective(mask, 0); }
 inline void __threadfence() {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }   // other PROCESSES read the peer-memory windows
+inline void __nanosleep(unsigned) { sched_yield(); }
 template <class T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
   const int lane = simt::S().cur & 31;

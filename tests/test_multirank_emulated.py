@@ -76,8 +76,12 @@ def _swap_in_emulated_engine():
     return L
 
 
-def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.0, inject_xi=False):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.0, inject_xi=False, transport="p2p"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EPH_B200_P2P_WINDOW_MB="8")
+    if transport == "nccl":
+        os.environ["EPH_B200_EXCHANGE"] = "nccl"
+    else:
+        os.environ.pop("EPH_B200_EXCHANGE", None)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         L = _swap_in_emulated_engine()
@@ -117,22 +121,26 @@ def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.
             out.append(dict(f=f.copy(), rho=eng.probe(0)[:nl].copy(), T=eng.get_grid(0).copy(), E=E,
                             substeps=eng.last_substeps()))
         calls = [L.emul_nccl_calls(k) for k in range(4)]
-        q.put((rank, s["tag"][:nl].copy(), out, eng.exchange_bytes, calls))
+        q.put((rank, s["tag"][:nl].copy(), out, eng.exchange_bytes, calls, eng.comm_transport()))
         del keep_cbs
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,gshape,sharded,boundary_first,tau0,inject_xi",
-                         [(2, (3, 2, 2), False, False, 0.0, False), (2, (3, 2, 2), False, True, 0.0, True),
-                          (2, (8, 8, 8), True, False, 0.0, False), (4, (8, 8, 8), True, True, 0.0, False),
-                          (3, (6, 6, 9), True, False, 0.0, True), (2, (3, 2, 2), False, True, 5e-4, False)])
-def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first, tau0, inject_xi):
+# transport of the two ghost exchanges: "p2p" = the peer-memory windows of csrc/eph_p2p.cuh (shared-memory objects between
+# the ranks' processes on the host build: the same kernels, flags, epochs and double-buffered halves as over NVLink),
+# "nccl" = grouped send / receive through the stand-in library
+@pytest.mark.parametrize("world,gshape,sharded,boundary_first,tau0,inject_xi,transport",
+                         [(2, (3, 2, 2), False, False, 0.0, False, "p2p"), (2, (3, 2, 2), False, True, 0.0, True, "p2p"),
+                          (2, (8, 8, 8), True, False, 0.0, False, "nccl"), (4, (8, 8, 8), True, True, 0.0, False, "p2p"),
+                          (3, (6, 6, 9), True, False, 0.0, True, "p2p"), (2, (3, 2, 2), False, True, 5e-4, False, "nccl"),
+                          (4, (3, 2, 2), False, False, 0.0, True, "nccl")])
+def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, world, gshape, sharded, boundary_first, tau0, inject_xi, transport):
     subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first, tau0, inject_xi)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, synth_beta_1, gshape, sharded, boundary_first, tau0, inject_xi, transport)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
@@ -155,14 +163,21 @@ def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, 
         fx.end_of_step()
         ref_f, ref_rho = fx.f[:nlw], np.array(fx.ptr(0))[:nlw]
         E = 0.0
-        for rank, tags, out, nbytes, calls in res:
+        for rank, tags, out, nbytes, calls, used in res:
             idx = order[np.searchsorted(whole["tag"][:nlw][order], tags)]
             assert H.error_metrics(out[k]["f"], ref_f[idx], floor=np.abs(ref_f).max()) < TOL, (rank, step)
             assert H.error_metrics(out[k]["rho"], ref_rho[idx]) < TOL, (rank, step)
             assert H.error_metrics(out[k]["T"], fx.fdm.field(0)) < TOL, (rank, step)
             assert nbytes > 0
-            # the engine itself issued the collectives: one grouped exchange and one all-reduce per step (+ halo groups / all-gathers)
-            assert calls[0] >= 3 and calls[2] == 3 and (calls[3] == 3) == bool(sharded), calls
+            # the engine itself issued the collectives.  Per step: one all-reduce of the source term (or reduce-scatter +
+            # all-gather), and with send / receive one grouped exchange; setting up the transport costs one all-gather (the
+            # window handles) and one all-reduce (the agreement), every set_ghost_map over peer memory one more all-reduce
+            assert used == (2 if transport == "p2p" else 1), used
+            assert calls[2] == 3 + (2 if transport == "p2p" else 1) and calls[3] == 1 + (3 if sharded else 0), calls
+            if transport == "nccl":
+                assert calls[0] >= 3, calls
+            elif not sharded:
+                assert calls[0] == 0, calls     # no send / receive at all: the rows went through the windows
             if sharded:   # fine grid: the solve takes several sub-steps, so halo planes were exchanged between them
                 assert out[k]["substeps"] >= 3
             E += out[k]["E"]

@@ -321,10 +321,8 @@ void drain_timers(eph_b200_handle *h) {
 
 // unmaps the peers' windows and frees the own one (eph_p2p.cuh)
 void p2p_teardown(eph_b200_handle *h) {
-#ifndef EPHA_HOST_EMULATION
   for (size_t r = 0; r < h->p2p_peer_window.size(); ++r)
     if (h->p2p_peer_window[r] && h->p2p_peer_window[r] != h->p2p_window) cudaIpcCloseMemHandle(h->p2p_peer_window[r]);
-#endif
   h->p2p_peer_window.clear();
   if (h->p2p_window) cudaFree(h->p2p_window);
   h->p2p_window = nullptr;
@@ -2115,7 +2113,6 @@ __global__ void scatter_rows_kernel(int n, const int *__restrict__ slot, double 
 // peer (another node, no peer access) is not an error: the NCCL send / receive path stays.
 int p2p_setup(eph_b200_handle *h) {
   p2p_teardown(h);
-#ifndef EPHA_HOST_EMULATION
   NcclApi &api = nccl_api();
   struct Record { cudaIpcMemHandle_t handle; unsigned long long bytes; int want; int pad; };
   const char *mode = std::getenv("EPH_B200_EXCHANGE");
@@ -2125,7 +2122,11 @@ int p2p_setup(eph_b200_handle *h) {
   mine.want = !(mode && std::strcmp(mode, "nccl") == 0) && h->comm_size > 1 && h->comm_size <= kP2PMaxRanks;
   if (mine.want) {
     void *w = nullptr;
-    if (cudaMalloc(&w, mine.bytes) != cudaSuccess || cudaMemset(w, 0, kP2PHeaderBytes) != cudaSuccess ||
+#ifdef EPHA_HOST_EMULATION
+    if (emul_ipc_malloc(&w, mine.bytes) != cudaSuccess ||   // tests/emul: a shared-memory object the other ranks can map
+#else
+    if (cudaMalloc(&w, mine.bytes) != cudaSuccess ||
+#endif cudaMemset(w, 0, kP2PHeaderBytes) != cudaSuccess ||
         cudaIpcGetMemHandle(&mine.handle, w) != cudaSuccess) {
       cudaGetLastError();
       if (w) cudaFree(w);
@@ -2174,7 +2175,6 @@ int p2p_setup(eph_b200_handle *h) {
   } else {
     p2p_teardown(h);
   }
-#endif
   return EPH_B200_OK;
 }
 
@@ -2250,7 +2250,6 @@ int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank,
   if (ns) EPH_CUDA(h, cudaMemcpyAsync(h->gm_send_idx.p, send_index, ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (nr) EPH_CUDA(h, cudaMemcpyAsync(h->gm_recv_slot.p, recv_slot, nr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   EPH_CUDA(h, cudaStreamSynchronize(h->stream));
-#ifndef EPHA_HOST_EMULATION
   if (h->p2p_ok) {
     if (npeers > kP2PMaxPeers)
       return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d peers, the peer-memory exchange takes %d (EPH_B200_EXCHANGE=nccl selects send/receive)", npeers, kP2PMaxPeers);
@@ -2272,7 +2271,6 @@ int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank,
     // rows of the old one (with an unchanged set of peers the exchanges themselves guarantee that)
     EPH_NCCL(h, nccl_api().AllReduce(h->p2p_scratch.p + 1, h->p2p_scratch.p + 1, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
   }
-#endif
   h->ghost_map_set = true;
   // with a communication stream registered the density pass sweeps the tiles these atoms live in first
   if (h->comm_stream && ns > 0) return eph_b200_set_boundary_atoms(h, (int)ns, h->gm_send_idx.p, EPH_B200_DEVICE);
@@ -2291,7 +2289,6 @@ int eph_b200_exchange_ghosts(eph_b200_handle *h) {
   const bool with_xi = h->pf_xi != nullptr && (h->cfg.flags & EPH_B200_RANDOM);
   cudaStream_t st = h->comm_stream ? h->comm_stream : h->stream;
   int rc;
-#ifndef EPHA_HOST_EMULATION
   if (h->p2p_ok) {
     // peer memory: the sending kernel stores the rows into the receivers' windows and raises its flag there
     if ((rc = exchange_stream(h, &st))) return rc;
@@ -2318,7 +2315,6 @@ int eph_b200_exchange_ghosts(eph_b200_handle *h) {
     }
     return EPH_B200_OK;
   }
-#endif
   if (h->gm_nsend) {
     if ((rc = eph_b200_pack_ghost_payload(h, h->gm_nsend, h->gm_send_idx.p, h->gm_send_buf.p))) return rc;
     if (with_xi) {
@@ -2489,7 +2485,6 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
   cudaSetDevice(h->cfg.device);
   const int record = h->gshift_valid ? 0 : 1;
   EPH_CUDA(h, h->gshift.reserve(3 * (size_t)std::max(ng, 1)));
-#ifndef EPHA_HOST_EMULATION
   if (remote && h->p2p_ok) {
     const P2PMap &m = h->p2p_map;
     if (m.n > 0) {
@@ -2502,9 +2497,7 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
                                                                                                         h->gshift.p, record, epoch, h->d_status.p);
       EPH_LAUNCH_CHECK(h);
     }
-  } else
-#endif
-  if (remote && (h->gm_nsend || h->gm_nrecv)) {
+  } else if (remote && (h->gm_nsend || h->gm_nrecv)) {
     NcclApi &api = nccl_api();
     EPH_CUDA(h, h->gm_send_xv.reserve(6 * std::max<size_t>(h->gm_nsend, 1))); EPH_CUDA(h, h->gm_recv_xv.reserve(6 * std::max<size_t>(h->gm_nrecv, 1)));
     if (h->gm_nsend) {

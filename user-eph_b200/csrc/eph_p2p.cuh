@@ -44,7 +44,6 @@ __host__ __device__ inline size_t p2p_kind1_offset(int rows) { return ((size_t)r
 __host__ __device__ inline size_t p2p_half_bytes_needed(int rows) { return p2p_kind1_offset(rows) + (size_t)rows * 48; }
 
 #ifndef EPHA_HOST_EMULATION
-
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -58,6 +57,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+constexpr unsigned long long kP2PTimeoutNs = 5000000000ull;
+#else
+// host build of the tests: the windows are shared-memory objects of the ranks' processes
+inline unsigned long long ld_acquire_sys_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long global_timer_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+constexpr unsigned long long kP2PTimeoutNs = 120000000000ull;
+#endif
 
 __device__ __forceinline__ int p2p_peer_of(const int *off, int n, int t) {
   int p = 0;
@@ -92,7 +103,7 @@ __device__ __forceinline__ void p2p_wait(const P2PMap &m, int kind, unsigned lon
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys_u64(flag) < epoch) {
       __nanosleep(64);
-      if (global_timer_ns() - t0 > 5000000000ull) { atomicOr(status, kStatusP2PTimeout); break; }
+      if (global_timer_ns() - t0 > kP2PTimeoutNs) { atomicOr(status, kStatusP2PTimeout); break; }
     }
   }
   __syncthreads();
@@ -175,6 +186,5 @@ __global__ void __launch_bounds__(256) p2p_recv_xv_kernel(P2PMap m, int nr, cons
   }
 }
 
-#endif  // EPHA_HOST_EMULATION
 
 }  // namespace ephb
