@@ -80,12 +80,12 @@ def parse_args():
 # workload
 # ---------------------------------------------------------------------------------------------------------------
 def beta_file(elements):
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     return H.shipped_beta("Ni_PRB2019" if elements == 1 else "NiCoCrFe_PRB2019")
 
 
 def build_workload(cells, brick=None, elements=1, with_list=False):
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     s = H.make_system(cells, brick=brick, ntypes=elements, with_list=with_list)
     # the primary knock-on atom of config C3: 10 keV along (0.835, 0.544, 0.082) (Tests/MD_Run/run.lmp:69-73); tag 1
     pka = np.nonzero(s["tag"] == 1)[0]
@@ -153,7 +153,7 @@ def _cpu_init(cells, grid, dt, seed_base):
     import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
     sys.path.insert(0, ROOT)
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     k = mp.current_process()._identity[0] if mp.current_process()._identity else 0
     s = H.make_system(cells, pos_seed=1234 + k, vel_seed=101 + k)
     s["v"][0] = V_PKA * np.array([0.835115, 0.543981, 0.081652])
@@ -343,7 +343,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     from eph_b200 import host, lib
-    from eph_b200 import parallel as P
+    from eph_harness import parallel as P
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -543,7 +543,7 @@ def check_against_one_gpu(a, torch, dist, lib, host, P, eng, md, s, gridn, box, 
     Tb = eng.get_grid(0)
     res = None
     if rank == 0:
-        from eph_b200 import harness as H
+        from eph_harness import harness as H
         w = H.make_system(cells, ntypes=a.elements, with_list=False)
         order = torch.as_tensor(w["tag"][: w["nlocal"]] - 1, device=dev)
         w["x"][: w["nlocal"]] = x0[order].cpu().numpy()
@@ -695,7 +695,7 @@ def c4_leg(a, torch, lib, host, P, s, gridn, box, local, stream, dev, natoms, st
 def small_box_check(a, torch, lib, host, local, stream, dev, cells=16, nsteps=3):
     """a 16 384-atom box with the PKA through the same engine build, against the unmodified reference fix on the host
     (oracle/_ref; the oracle port if it is not there): all atoms, forces / densities / grid"""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import traj
     s = H.make_system(cells)

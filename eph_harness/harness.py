@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from ._paths import lib_path
+from . import LIB, REPO_ROOT
 
 KB = 8.617343e-5          # eV/K  (LAMMPS metal units, force->boltz)
 MVV2E = 1.0364269e-4      # eV per amu (A/ps)^2
@@ -21,7 +21,7 @@ _h = None
 def _hlib():
     global _h
     if _h is None:
-        _h = C.CDLL(lib_path("harness"))
+        _h = C.CDLL(LIB)
         _h.eph_harness_ghosts.restype = C.c_longlong
     return _h
 
@@ -33,7 +33,6 @@ def shipped_beta(name):
     import tempfile
     cache = shipped_beta.__dict__.setdefault("cache", {})
     if name not in cache:
-        from ._paths import REPO_ROOT
         src = os.path.join(REPO_ROOT, "tests", "golden", "data", name + ".beta.gz")
         dst = os.path.join(tempfile.mkdtemp(prefix="eph_beta_"), name + ".beta")
         with gzip.open(src, "rb") as f, open(dst, "wb") as g:
@@ -176,7 +175,7 @@ def write_beta_file(path, knots, names=None, Z=None):
     names = names or ["Ni", "Co", "Cr", "Fe", "Al", "Cu"][:n_el]
     Z = Z or [28, 27, 24, 26, 13, 29][:n_el]
     with open(path, "w") as f:
-        f.write("# synthetic electronic density and coupling, written by eph_b200.harness\n# rho(r) [1/A^3], beta(rho) [eV ps/A^2]\n#\n")
+        f.write("# synthetic electronic density and coupling, written by eph_harness\n# rho(r) [1/A^3], beta(rho) [eV ps/A^2]\n#\n")
         f.write("%d %s\n" % (n_el, " ".join(names)))
         f.write("%d %.17g %d %.17g %.17g\n" % (n_rho, dr, n_beta, drho, rc))
         for e in range(n_el):
@@ -200,7 +199,7 @@ def write_grid_file(path, nx, ny, nz, box, T_e, S_e, rho_e, C_e, kappa_e, flag, 
     T_e, S_e, rho_e, C_e, kappa_e = (fld(v) for v in (T_e, S_e, rho_e, C_e, kappa_e))
     flag, t_dyn = fld(flag, np.int64), fld(t_dyn, np.int64)
     with open(path, "w") as f:
-        f.write("# grid written by eph_b200.harness\n#\n#\n")
+        f.write("# grid written by eph_harness\n#\n#\n")
         f.write("%d %d %d %d\n" % (nx, ny, nz, steps))
         f.write("%.17e %.17e\n%.17e %.17e\n%.17e %.17e\n" % tuple(box))
         f.write("%s\n" % parameter_file)
@@ -215,7 +214,7 @@ def write_grid_file(path, nx, ny, nz, box, T_e, S_e, rho_e, C_e, kappa_e, flag, 
 
 def write_parameter_file(path, dT, C_e_T, kappa_e_T):
     with open(path, "w") as f:
-        f.write("# C_e(T) kappa_e(T) written by eph_b200.harness\n#\n#\n")
+        f.write("# C_e(T) kappa_e(T) written by eph_harness\n#\n#\n")
         f.write("%d %.17g\n" % (len(C_e_T), dT))
         for c, k in zip(C_e_T, kappa_e_T):
             f.write("%.17e %.17e\n" % (c, k))
@@ -257,7 +256,7 @@ def write_kappa_file(path, knots, names=None, Z=None):
     names = names or ["Ni", "Co", "Cr", "Fe", "Al", "Cu"][:n_el]
     Z = Z or [28, 27, 24, 26, 13, 29][:n_el]
     with open(path, "w") as f:
-        f.write("# synthetic per-atom electronic properties, written by eph_b200.harness\n# rho_a(r), C(T), K(T)\n#\n")
+        f.write("# synthetic per-atom electronic properties, written by eph_harness\n# rho_a(r), C(T), K(T)\n#\n")
         f.write("%d %s\n" % (n_el, " ".join(names)))
         f.write("%d %.17g %.17g %d %.17g %.17g\n" % (n_r, dr, rc, n_T, dT, T_max))
         for e in range(n_el):

@@ -6,7 +6,7 @@ import os
 
 import numpy as np
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host
 from oracle import oracle as O
 

@@ -21,9 +21,12 @@ def pytest_configure(config):
 def _built_libraries():
     """CPU-side libraries (oracle, host side, harness) are built on demand; the CUDA library is cross-compiled too."""
     from eph_b200 import _paths
-    need = [p for p in (_paths.lib_path("engine"), _paths.lib_path("fix"), _paths.lib_path("harness")) if not os.path.exists(p)]
+    need = [p for p in (_paths.lib_path("engine"), _paths.lib_path("fix")) if not os.path.exists(p)]
     if need:
         _paths.build_all()
+    import eph_harness
+    if not os.path.exists(eph_harness.LIB):
+        eph_harness.build()
     from oracle import oracle
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         oracle.build()
@@ -44,14 +47,14 @@ def ref():
 
 @pytest.fixture(scope="session")
 def synth_beta_1(tmp_path_factory):
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     p = tmp_path_factory.mktemp("beta") / "synth1.beta"
     return str(H.write_beta_file(p, H.synthetic_knots(1, n_beta=5001, drho=0.01)))
 
 
 @pytest.fixture(scope="session")
 def synth_beta_4(tmp_path_factory):
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     p = tmp_path_factory.mktemp("beta") / "synth4.beta"
     return str(H.write_beta_file(p, H.synthetic_knots(4, n_beta=5001, drho=0.01)))
 
@@ -63,7 +66,7 @@ def ni_trunc_beta():
 
 @pytest.fixture(scope="session")
 def sys500():
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     return H.make_system(5)
 
 

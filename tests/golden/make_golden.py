@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from eph_b200 import harness as H  # noqa: E402
+from eph_harness import harness as H  # noqa: E402
 from oracle import reference as R  # noqa: E402
 import traj  # noqa: E402
 

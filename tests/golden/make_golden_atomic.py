@@ -3,7 +3,7 @@
 
     python tests/golden/make_golden_atomic.py
 
-synth1.kappa is a synthetic per-atom parametrisation (eph_b200.harness.synthetic_kappa) in the reference's `.kappa`
+synth1.kappa is a synthetic per-atom parametrisation (eph_harness.harness.synthetic_kappa) in the reference's `.kappa`
 grammar; inputs are stored next to the outputs."""
 import os
 import sys
@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "user-eph_b200"))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from eph_b200 import harness as H  # noqa: E402
+from eph_harness import harness as H  # noqa: E402
 from oracle import reference as R  # noqa: E402
 import traj  # noqa: E402
 

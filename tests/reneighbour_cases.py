@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host
 
 import traj

@@ -48,7 +48,7 @@ def test_emulated_trajectory_matches_oracle(make_engine, kappa_tables, flags, lo
 
 def test_emulated_two_elements_in_the_beta_file(make_engine, kappa_tables, tmp_path):
     """two atom types on two .beta elements (g_ij != g_ji), both on the single .kappa element"""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     beta2 = str(H.write_beta_file(tmp_path / "synth2.beta", H.synthetic_knots(2, n_beta=5001, drho=0.01)))
     cases.trajectory_case(make_engine, kappa_tables, 7, 2, None, ntypes=2, beta=beta2, names=("Ni", "Co"))
 
@@ -80,7 +80,7 @@ def test_emulated_device_memspace(make_engine, kappa_tables):
     """memspace EPH_B200_DEVICE on the host build (device memory is host memory there): caller-owned type / mask / tag /
     list arrays are aliased, x, v are read and f is updated in place, without staging copies"""
     import numpy as np
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     from oracle import oracle as O
     import traj
     from test_engine_emulated import dev
@@ -113,7 +113,7 @@ def test_emulated_device_memspace(make_engine, kappa_tables):
 @pytest.mark.parametrize("seed", [31, 32])
 def test_fuzz_atomic_configurations(seed, make_engine, kappa_tables, tmp_path):
     import numpy as np
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     rng = np.random.default_rng(seed)
     beta2 = str(H.write_beta_file(tmp_path / "synth2.beta", H.synthetic_knots(2, n_beta=5001, drho=0.01)))
     for it in range(10):
@@ -142,7 +142,7 @@ def test_emulated_three_elements_in_both_files(make_engine, tmp_path):
     """three atom types on three elements of the .beta AND of the .kappa file: per-element locality densities, E(T) and
     K(T) tables (three elements give n_pairs = 4 >= 3, the smallest multi-element file the reference indexes in bounds,
     eph_kappa.h:69); a two-element .kappa file (n_pairs = 1) is refused"""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     from eph_b200 import lib
     beta3 = str(H.write_beta_file(tmp_path / "synth3.beta", H.synthetic_knots(3, n_beta=5001, drho=0.01)))
     kappa3 = str(H.write_kappa_file(tmp_path / "synth3.kappa", H.synthetic_kappa(3, n_r=501, n_T=401, dT=2.5)))
@@ -163,7 +163,7 @@ def host_beta(path):
 def test_emulated_call_order_errors_are_reported(make_engine, kappa_tables):
     """misuse of the C ABI comes back as an error code with a message, never as a crash or a silent no-op"""
     import numpy as np
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     from eph_b200 import host, lib
     s = H.make_system(2)
     nl = s["nlocal"]

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from oracle import oracle as O
 
 import test_gpu_parity as G

@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host, lib
 from oracle import oracle as O
 

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host, lib
 from oracle import oracle as O
 
@@ -87,7 +87,7 @@ def test_engine_lane_widths(sys500, synth_beta_1, lanes, monkeypatch):
         import sys, os, numpy as np
         sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
         import test_gpu_parity as T, traj
-        from eph_b200 import harness as H
+        from eph_harness import harness as H
         from oracle import oracle as O
         s = H.make_system(5)
         xis = [np.random.default_rng(3).normal(size=(s["nlocal"], 3))]
@@ -377,9 +377,9 @@ def test_inner_list_invalidation_and_rebuild(synth_beta_1, skin):
 def test_bricks_with_ghost_exchange_match_whole_box_oracle(synth_beta_1, world, overlap):
     """The multi-rank path on one GPU: `world` engines, one per spatial brick, driven through the two halves of
     post_force / end_of_step with the ghost payload and the grid source term moved between them exactly as
-    torch.distributed would (eph_b200.parallel); the result must equal the single-rank oracle on the whole box."""
+    torch.distributed would (eph_harness.parallel); the result must equal the single-rank oracle on the whole box."""
     import torch
-    from eph_b200 import parallel as P
+    from eph_harness import parallel as P
     dev = torch.device("cuda", 0)
     # one stream for torch and all engines, so the copies that stand in for NCCL are ordered with the kernels
     tstream = torch.cuda.Stream(device=dev)

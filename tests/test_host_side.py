@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host, lib
 from oracle import oracle as O
 
@@ -244,7 +244,7 @@ def test_atomic_library_exports_every_declared_symbol():
 
 def test_atomic_no_cpu_fallback_and_argument_errors():
     from eph_b200 import atomic as A
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     if not gpu_available():
         with pytest.raises(lib.EphError) as e:
             A.AtomicEngine([0], [0], 7)

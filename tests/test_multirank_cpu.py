@@ -10,8 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from eph_b200 import harness as H
-from eph_b200 import parallel as P
+from eph_harness import harness as H
+from eph_harness import parallel as P
 
 
 def test_brick_grid_shapes():

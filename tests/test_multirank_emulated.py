@@ -16,9 +16,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host, lib
-from eph_b200 import parallel as P
+from eph_harness import parallel as P
 from oracle import oracle as O
 
 from test_multirank_cpu import _free_port

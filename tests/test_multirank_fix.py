@@ -19,9 +19,9 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host
-from eph_b200 import parallel as P
+from eph_harness import parallel as P
 
 from test_multirank_cpu import _free_port
 from test_multirank_emulated import EMUL, _swap_in_emulated_engine, gloo_transport

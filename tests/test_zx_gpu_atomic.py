@@ -6,7 +6,7 @@ import numpy as np  # noqa: F401
 import pytest
 
 from eph_b200 import atomic as A
-from eph_b200 import harness as H
+from eph_harness import harness as H
 
 import atomic_cases as cases
 

@@ -6,9 +6,9 @@ import os
 import numpy as np
 import pytest
 
-from eph_b200 import harness as H
+from eph_harness import harness as H
 from eph_b200 import host, lib
-from eph_b200 import parallel as P
+from eph_harness import parallel as P
 from oracle import oracle as O
 
 import traj
@@ -65,7 +65,7 @@ def _copy(dst, src):
 
 
 def _solve_sharded(engs, xz, shape):
-    """what eph_b200.parallel.sharded_grid_solve does over NCCL, with the ranks' engines in one process: slab sub-steps,
+    """what eph_harness.parallel.sharded_grid_solve does over NCCL, with the ranks' engines in one process: slab sub-steps,
     halo planes copied between the engines' T_e arrays, slabs gathered at the end"""
     W = len(engs)
     nx, ny, nz = shape

@@ -61,7 +61,7 @@ def run_fix_driver(drv, system, xis, dt=None, vec3_probes=None):
 
 def system_from_golden(g):
     """Rebuild the harness system dict (incl. the neighbour list) from a golden file's stored inputs."""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     nl, ng = int(g["nlocal"]), int(g["nghost"])
     x = np.ascontiguousarray(g["x"])
     offsets, neigh = H.neighbor_list(x, nl, 7.0)
@@ -265,7 +265,7 @@ def run_with_reordering(make_driver, system, xi_by_tag, permute_after=None, seed
 
 def assert_reordering_is_transparent(make_driver, system, xi_by_tag, permute_after, tol=0.0):
     """the trajectory with a re-ordering after `permute_after` steps equals the one without (tol 0: bit for bit)"""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     a = run_with_reordering(make_driver, system, xi_by_tag, None)
     b = run_with_reordering(make_driver, system, xi_by_tag, permute_after)
     for step, (ra, rb) in enumerate(zip(a, b), start=1):
@@ -287,7 +287,7 @@ def reneighbour(drv, system, shell):
     """Rebuilds ghosts and the full list from the CURRENT positions of the local atoms with a ghost shell / list cut-off
     of `shell`, and hands them to the fix in the stand-in the way LAMMPS does after re-neighbouring (the number of ghosts
     changes, per-atom arrays may have to grow).  Returns the new system dict."""
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     nl = system["nlocal"]
     x, v, f = drv.xvf()
     L = np.asarray(system["box"], dtype=np.float64)
@@ -349,7 +349,7 @@ def run_with_reneighbouring(make_driver, system, xis, schedule, dts=None, probes
 
 
 def assert_same_trajectory(a, b, tol, dts=None):
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     e_scale = 0.0
     for step, (ra, rb) in enumerate(zip(a, b), start=1):
         assert ra["nghost"] == rb["nghost"]

@@ -27,7 +27,7 @@ def main():
     a = ap.parse_args()
     import torch
     from eph_b200 import atomic as A
-    from eph_b200 import harness as H
+    from eph_harness import harness as H
     from eph_b200 import host
     assert torch.cuda.is_available(), "needs a GPU: there is no CPU fallback"
     dev = torch.device("cuda", 0)

@@ -28,7 +28,7 @@ def main():
     import torch
     import torch.distributed as dist
     from eph_b200 import host, lib
-    from eph_b200 import parallel as P
+    from eph_harness import parallel as P
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     sys.argv = [sys.argv[0], "--gpus", str(world), "--cells", str(b.cells), "--neigh", b.neigh] + (["--overlap"] if b.overlap else [])

@@ -8,7 +8,6 @@ REPO_ROOT = os.path.dirname(os.path.dirname(PKG_DIR))
 _LIBS = {
     "engine": os.path.join(PKG_DIR, "libeph_b200.so"),
     "fix": os.path.join(PKG_DIR, "libeph_b200_fix.so"),
-    "harness": os.path.join(PKG_DIR, "libeph_harness.so"),
     "atomic_fix": os.path.join(PKG_DIR, "libeph_b200_atomic_fix.so"),
 }
 

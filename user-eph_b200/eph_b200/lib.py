@@ -334,7 +334,7 @@ class Engine:
         self._check(fn(self.h, C.byref(e) if want_energy else None))
         return e.value if want_energy else None
 
-    # sharded grid solve (eph_b200.parallel.sharded_grid_solve drives these between end_of_step_begin and
+    # sharded grid solve (eph_harness.parallel.sharded_grid_solve drives these between end_of_step_begin and
     # end_of_step_end(external=True))
     def grid_plan_substeps(self):
         n = C.c_int()
@@ -374,7 +374,7 @@ class Engine:
         return int(self.lib.eph_b200_comm_transport(self.h))
 
     def set_ghost_map(self, plan):
-        """plan: eph_b200.parallel.ExchangePlan (who holds which of my atoms as ghosts, who fills which of my ghost slots)"""
+        """plan: eph_harness.parallel.ExchangePlan (who holds which of my atoms as ghosts, who fills which of my ghost slots)"""
         cached = getattr(plan, "_ghost_map_arrays", None)   # a plan does not change: flatten it once
         if cached is None:
             peers = [r for r in range(plan.world) if r != plan.rank and (plan.send_counts[r] or plan.recv_counts[r])]
