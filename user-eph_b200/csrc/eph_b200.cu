@@ -95,6 +95,7 @@ struct eph_b200_handle {
   DevBuf<int> comm_idx;           // forward-comm scratch (host transport)
   DevBuf<double> comm_buf;
   DevBuf<double> mass;
+  std::vector<double> mass_host;   // what h->mass holds: the masses go up again only when they change
 
   // internal per-atom records
   DevBuf<double4> pos4, pv, puz, W4;
@@ -329,6 +330,17 @@ void p2p_teardown(eph_b200_handle *h) {
   h->p2p_ok = false;
   h->p2p_done.release(); h->p2p_scratch.release();
   cudaGetLastError();
+}
+
+// masses by type on the device; uploaded only when they differ from what is there (a copy per hook otherwise)
+int upload_masses(eph_b200_handle *h, const double *mass_by_type) {
+  const size_t n = (size_t)h->cfg.ntypes + 1;
+  if (h->mass_host.size() == n && std::memcmp(h->mass_host.data(), mass_by_type, n * sizeof(double)) == 0) return EPH_B200_OK;
+  EPH_CUDA(h, h->mass.reserve(n));
+  h->mass_host.assign(mass_by_type, mass_by_type + n);
+  // the vector outlives the copy: a pageable source is staged before cudaMemcpyAsync returns anyway
+  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, h->mass_host.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return EPH_B200_OK;
 }
 
 // the main stream must not read T_e / write dT_e before a solve running on the grid stream has finished
@@ -1945,8 +1957,7 @@ int eph_b200_initial_integrate(eph_b200_handle *h, double *x, double *v, const d
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal;
   if (nl == 0) return EPH_B200_OK;
-  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
-  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  { const int rc_m = upload_masses(h, mass_by_type); if (rc_m) return rc_m; }
   double *dx = x, *dv = v;
   const double *df = f;
   if (memspace != EPH_B200_DEVICE) {
@@ -1956,7 +1967,10 @@ int eph_b200_initial_integrate(eph_b200_handle *h, double *x, double *v, const d
     EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     dx = h->x.p; dv = h->v.p; df = h->f.p;
   }
-  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, dx, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
+  {
+    KernelTimer kt(h, "initial_integrate");
+    integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, dx, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
+  }
   EPH_LAUNCH_CHECK(h);
   if (memspace != EPH_B200_DEVICE) {
     EPH_CUDA(h, cudaMemcpyAsync(x, h->x.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1975,8 +1989,7 @@ int eph_b200_final_integrate(eph_b200_handle *h, double *v, const double *f, con
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal;
   if (nl == 0) return EPH_B200_OK;
-  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
-  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  { const int rc_m = upload_masses(h, mass_by_type); if (rc_m) return rc_m; }
   double *dv = v;
   const double *df = f;
   if (memspace != EPH_B200_DEVICE) {
@@ -1985,7 +1998,10 @@ int eph_b200_final_integrate(eph_b200_handle *h, double *v, const double *f, con
     EPH_CUDA(h, cudaMemcpyAsync(h->f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     dv = h->v.p; df = h->f.p;
   }
-  integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, nullptr, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, 0.0, dtf, 0);
+  {
+    KernelTimer kt(h, "final_integrate");
+    integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, nullptr, dv, df, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, 0.0, dtf, 0);
+  }
   EPH_LAUNCH_CHECK(h);
   if (memspace != EPH_B200_DEVICE) {
     EPH_CUDA(h, cudaMemcpyAsync(v, h->v.p, 3 * (size_t)nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -2490,11 +2506,17 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
     if (m.n > 0) {
       const unsigned long long epoch = ++h->p2p_epoch[1];
       const int cap = 2 * h->sm_count;
-      p2p_send_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nsend, 256))), 256, 0, h->stream>>>(m, h->gm_nsend, h->gm_send_idx.p, x, v, epoch,
-                                                                                                        h->p2p_done.p + 1);
+      {
+        KernelTimer kt(h, "refresh_send");
+        p2p_send_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nsend, 256))), 256, 0, h->stream>>>(m, h->gm_nsend, h->gm_send_idx.p, x, v, epoch,
+                                                                                                          h->p2p_done.p + 1);
+      }
       EPH_LAUNCH_CHECK(h);
-      p2p_recv_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nrecv, 256))), 256, 0, h->stream>>>(m, h->gm_nrecv, h->gm_recv_slot.p, nl, x, v,
-                                                                                                        h->gshift.p, record, epoch, h->d_status.p);
+      {
+        KernelTimer kt(h, "refresh_recv");
+        p2p_recv_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nrecv, 256))), 256, 0, h->stream>>>(m, h->gm_nrecv, h->gm_recv_slot.p, nl, x, v,
+                                                                                                          h->gshift.p, record, epoch, h->d_status.p);
+      }
       EPH_LAUNCH_CHECK(h);
     }
   } else if (remote && (h->gm_nsend || h->gm_nrecv)) {
@@ -2519,9 +2541,10 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
     }
   }
   if (ng > 0) {
+    KernelTimer kt(h, "ghost_images");
     ghost_images_kernel<<<blocks_for(ng, 256), 256, 0, h->stream>>>(nl, ng, h->owner.p, x, v, h->gshift.p, record);
-    EPH_LAUNCH_CHECK(h);
   }
+  EPH_LAUNCH_CHECK(h);
   h->gshift_valid = true;
   return EPH_B200_OK;
 }
@@ -2568,8 +2591,7 @@ int eph_b200_resident_initial_integrate(eph_b200_handle *h, const double *f, con
     EPH_CUDA(h, cudaMemcpyAsync(h->res_f.p, f, 3 * (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->res_f_valid = true;
   }
-  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
-  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  { const int rc_m = upload_masses(h, mass_by_type); if (rc_m) return rc_m; }
   integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, h->res_x.p, h->res_v.p, h->res_f.p, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, dtv, dtf, 1);
   EPH_LAUNCH_CHECK(h);
   // x travels to the host on the copy stream while the main stream goes on: ghosts follow their owners and, if the caller
@@ -2639,8 +2661,7 @@ int eph_b200_resident_final_integrate(eph_b200_handle *h, const double *mass_by_
   cudaSetDevice(h->cfg.device);
   const int nl = h->nlocal;
   if (nl == 0) return EPH_B200_OK;
-  EPH_CUDA(h, h->mass.reserve(h->cfg.ntypes + 1));
-  EPH_CUDA(h, cudaMemcpyAsync(h->mass.p, mass_by_type, (h->cfg.ntypes + 1) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  { const int rc_m = upload_masses(h, mass_by_type); if (rc_m) return rc_m; }
   integrate_kernel<<<blocks_for(nl, 256), 256, 0, h->stream>>>(nl, nullptr, h->res_v.p, h->res_f.p, h->type.p, h->mask.p, h->mass.p, h->cfg.groupbit, 0.0, dtf, 0);
   EPH_LAUNCH_CHECK(h);
   if (v_out) {
