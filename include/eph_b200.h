@@ -240,7 +240,9 @@ int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr);
  * the communicator can map every other rank's memory (one node, NVLink / PCIe peer access) comm_init sets up windows
  * (cudaIpc) and the exchanges become one kernel that stores the rows straight into the receivers' memory plus one that
  * scatters them (csrc/eph_p2p.cuh); otherwise grouped ncclSend / ncclRecv.  The choice is made once, by all ranks
- * together; EPH_B200_EXCHANGE=nccl forces send / receive, EPH_B200_P2P_WINDOW_MB (default 256) sizes the window.
+ * together; EPH_B200_EXCHANGE=nccl forces send / receive, EPH_B200_P2P_WINDOW_MB (default 256) sizes the window.  With
+ * peer memory set_ghost_map is collective (one small all-reduce): ghost rows that do not fit a rank's share of a
+ * window make it fail on every rank together, with the size it needs.
  * comm_transport: 0 no communicator, 1 NCCL send / receive, 2 peer memory.  A peer that fails to arrive within 5 s sets
  * bit 8 of the status word instead of hanging the device. */
 #define EPH_B200_COMM_ID_BYTES 128

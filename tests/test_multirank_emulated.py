@@ -183,3 +183,50 @@ def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, 
             E += out[k]["E"]
         assert abs(E - (fx.Ee() - E_prev)) < 1e-9 * abs(E)
         E_prev = fx.Ee()
+
+
+def _small_window_worker(rank, world, port, q, beta):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EPH_B200_P2P_WINDOW_MB="0.0625")
+    os.environ.pop("EPH_B200_EXCHANGE", None)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = _swap_in_emulated_engine()
+        keep_cbs = gloo_transport(L)
+        grid = P.brick_grid(world)
+        s = H.make_system(CELLS, brick=(rank, grid))
+        plan = P.ExchangePlan(s, rank, world, dist)
+        eng = lib.Engine([0], flags=7, seed=SEED, rank=rank, nranks=world)
+        eng.set_tables_from(host.BetaTables(path=beta))
+        P.attach_comm(eng, dist, rank, world)
+        keep = [np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
+                np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(plan.self_owner, dtype=np.int32)]
+        eng.set_atoms(s["nlocal"], s["nghost"], *keep)
+        msg = None
+        try:
+            eng.set_ghost_map(plan)
+        except lib.EphError as e:
+            msg = str(e)
+        q.put((rank, eng.comm_transport(), msg, int(max(max(plan.send_counts), max(plan.recv_counts)))))
+        del keep_cbs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ghost_rows_that_do_not_fit_the_window_fail_on_every_rank(synth_beta_1):
+    """64 KB windows: the ghost rows of this box do not fit a rank's share.  set_ghost_map must say so with the size it
+    needs -- on ALL ranks (the verdict travels with the collective of the registration), not leave the others waiting."""
+    subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_small_window_worker, args=(r, world, port, q, synth_beta_1)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    for rank, used, msg, rows in res:
+        assert used == 2, used                      # the windows themselves were set up
+        assert rows * 104 > (65536 - 8192) // world // 2, rows   # the premise of the test
+        assert msg is not None and "EPH_B200_P2P_WINDOW_MB" in msg and "EPH_B200_EXCHANGE=nccl" in msg, msg

@@ -2134,7 +2134,7 @@ int p2p_setup(eph_b200_handle *h) {
   const char *mode = std::getenv("EPH_B200_EXCHANGE");
   const char *mb = std::getenv("EPH_B200_P2P_WINDOW_MB");
   Record mine{};
-  mine.bytes = (unsigned long long)std::max(8LL, mb ? std::atoll(mb) : 256LL) << 20;
+  mine.bytes = (unsigned long long)(std::max(0.0625, mb ? std::atof(mb) : 256.0) * 1048576.0) / 4096 * 4096;
   mine.want = !(mode && std::strcmp(mode, "nccl") == 0) && h->comm_size > 1 && h->comm_size <= kP2PMaxRanks;
   if (mine.want) {
     void *w = nullptr;
@@ -2265,27 +2265,40 @@ int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank,
   EPH_CUDA(h, h->gm_send_xi.reserve(3 * std::max<size_t>(ns, 1))); EPH_CUDA(h, h->gm_recv_xi.reserve(3 * std::max<size_t>(nr, 1)));
   if (ns) EPH_CUDA(h, cudaMemcpyAsync(h->gm_send_idx.p, send_index, ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (nr) EPH_CUDA(h, cudaMemcpyAsync(h->gm_recv_slot.p, recv_slot, nr * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (!h->p2p_ok) EPH_CUDA(h, cudaStreamSynchronize(h->stream));   // (with peer memory the synchronisation below covers the copies)
   if (h->p2p_ok) {
-    if (npeers > kP2PMaxPeers)
-      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d peers, the peer-memory exchange takes %d (EPH_B200_EXCHANGE=nccl selects send/receive)", npeers, kP2PMaxPeers);
     P2PMap &m = h->p2p_map;
     m = P2PMap{};
-    m.n = npeers; m.my_rank = h->comm_rank; m.local = h->p2p_window; m.region_bytes = h->p2p_region_bytes;
-    for (int p = 0; p < npeers; ++p) {
+    const bool too_many = npeers > kP2PMaxPeers;
+    m.n = too_many ? 0 : npeers; m.my_rank = h->comm_rank; m.local = h->p2p_window; m.region_bytes = h->p2p_region_bytes;
+    size_t worst = 0;
+    int worst_rows = 0, worst_rank = -1;
+    for (int p = 0; p < m.n; ++p) {
       m.rank[p] = peer_rank[p];
       m.send_off[p + 1] = m.send_off[p] + send_count[p];
       m.recv_off[p + 1] = m.recv_off[p] + recv_count[p];
       m.remote[p] = h->p2p_peer_window[peer_rank[p]];
       const size_t need = p2p_half_bytes_needed(std::max(send_count[p], recv_count[p]));
-      if (need > m.region_bytes / 2)
-        return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d ghost rows for rank %d need %zu bytes of its window, a rank's share is %zu "
-                    "(raise EPH_B200_P2P_WINDOW_MB on all ranks, or EPH_B200_EXCHANGE=nccl)", std::max(send_count[p], recv_count[p]),
-                    peer_rank[p], need, m.region_bytes / 2);
+      if (need > worst) { worst = need; worst_rows = std::max(send_count[p], recv_count[p]); worst_rank = peer_rank[p]; }
     }
-    // re-registration is collective: nobody writes rows of the new map into a window whose owner may still be reading
-    // rows of the old one (with an unchanged set of peers the exchanges themselves guarantee that)
+    // Re-registration is collective: nobody writes rows of the new map into a window whose owner may still be reading
+    // rows of the old one (with an unchanged set of peers the exchanges themselves guarantee that).  The same
+    // all-reduce carries "my rows do not fit", so that every rank fails together instead of one leaving the others
+    // waiting in the next collective.
+    const double mine = (too_many || worst > m.region_bytes / 2) ? 1.0 : 0.0;
+    double failed = 0.0;
+    EPH_CUDA(h, cudaMemcpyAsync(h->p2p_scratch.p + 1, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     EPH_NCCL(h, nccl_api().AllReduce(h->p2p_scratch.p + 1, h->p2p_scratch.p + 1, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+    EPH_CUDA(h, cudaMemcpyAsync(&failed, h->p2p_scratch.p + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EPH_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (too_many)
+      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d peers, the peer-memory exchange takes %d (EPH_B200_EXCHANGE=nccl selects send/receive)", npeers, kP2PMaxPeers);
+    if (mine > 0.0)
+      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: %d ghost rows exchanged with rank %d need %zu bytes of a peer-memory window, a rank's share "
+                  "is %zu (raise EPH_B200_P2P_WINDOW_MB on all ranks, or EPH_B200_EXCHANGE=nccl)", worst_rows, worst_rank, worst, m.region_bytes / 2);
+    if (failed > 0.0)
+      return fail(h, EPH_B200_ERR_ARG, "set_ghost_map: the ghost rows of %d other rank(s) do not fit their peer-memory windows "
+                  "(raise EPH_B200_P2P_WINDOW_MB on all ranks, or EPH_B200_EXCHANGE=nccl)", (int)failed);
   }
   h->ghost_map_set = true;
   // with a communication stream registered the density pass sweeps the tiles these atoms live in first
