@@ -476,6 +476,25 @@ def run_b200(a):
                     "kernels_note": "the two sweeps: CUDA events on the launch stream inside the timed region; the other kernels: the %d steps "
                                     "that follow it, every launch bracketed (%.4f ms per step with all those events)" % (a.steps, ms_all / a.steps)}
 
+    # ---- where the step goes (rank 0's kernels; what the kernels on the main stream do not account for is launch gaps,
+    # registration and waiting for neighbours) ----
+    breakdown = None
+    if roofline:
+        kps = roofline["kernels_ms_per_step"]
+        side = ("source_allreduce", "source_reduce_scatter", "grid_allgather", "grid_halo", "fdm_substep") if D else ()
+        groups = {"sweeps": ("density_sweep", "force_sweep", "density_sweep_boundary"),
+                  "ghost_exchanges": ("pack_payload", "ghost_exchange", "unpack_payload", "refresh_send", "refresh_recv", "ghost_images"),
+                  "list_maintenance": ("inner_list_build", "build_neighbors"),
+                  "stand_by_launches": ("density_sweep_fallback", "force_sweep_fallback")}
+        named = set(sum(groups.values(), ())) | set(side)
+        parts = {g: round(sum(kps.get(k, 0.0) for k in ks), 4) for g, ks in groups.items()}
+        parts["streaming_kernels"] = round(sum(v for k, v in kps.items() if k not in named), 4)
+        parts["gaps_registration_and_waiting"] = round(ms_per_step - sum(parts.values()), 4)
+        non_sweep = {k: v for k, v in parts.items() if k != "sweeps"}
+        breakdown = {"ms_per_step": parts, "largest_non_sweep_part": max(non_sweep, key=non_sweep.get),
+                     "on_the_grid_stream_ms_per_step": {k: kps[k] for k in side if k in kps},
+                     "note": "rank 0, main stream; the all-reduce of the source term and the grid solve run on a second stream under the next step's density pass"}
+
     # ---- multi-GPU: the same steps on the whole box on one GPU, atom by atom ----
     parity = None
     if D and not a.no_check:
@@ -506,7 +525,7 @@ def run_b200(a):
                               ghost_exchange_transport={0: None, 1: "grouped ncclSend/ncclRecv", 2: "NVLink peer memory (one kernel stores the rows into the receivers' windows)"}[eng.comm_transport()],
                               reneighbourings_in_timed_region=rebuilds,
                               list_stats={k: stats1[k] - stats0[k] for k in stats1}),
-               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "fdm": fdm}
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "step_breakdown": breakdown, "e2e": e2e, "fdm": fdm}
         if parity is not None:
             out["parity_vs_n1"] = parity
         if extras is not None:
