@@ -319,6 +319,62 @@ def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
     assert 0.8 < np.abs(x[:nl] - s["x"][:nl]).max() < 1.2
 
 
+def test_emulated_long_trajectory_with_a_longer_list(ni_trunc_beta):
+    """The same 170 hot steps with LAMMPS' list 0.4 A longer (fix keyword `extra_skin 0.4`: cut-off r_c + 2.4 A while LAMMPS
+    still re-neighbours at half of ITS 2 A skin, i.e. before any atom has moved 1 A): the inner list can be rebuilt from
+    the aged list for the whole life of the list -- the engine never gives up and stays on the full list -- and
+    the results follow the oracle as before."""
+    s = H.make_system(4, T=6000.0, skin=2.4)
+    dt, nl = 1.5e-4, s["nlocal"]
+    rng = np.random.default_rng(3)
+    fx = O.Fix(s, O.Beta(path=ni_trunc_beta), O.FDM(2, 2, 2, G.box6(s), 300.0, 3.5e-6, 1.0, 0.1248), 7, dt=dt)
+    eng = G.make_engine(ni_trunc_beta, 7, (2, 2, 2), G.box6(s), dt=dt)
+    eng.set_skin(2.4, 0.4)      # what FixEPHB200::init() passes: neighbor->skin + extra_skin
+    G.attach(eng, s)
+    sync = traj.GhostSync(s)
+    x, v = s["x"].copy(), s["v"].copy()
+    f = np.zeros((nl, 3))
+    m, dtf = np.array([0.0, 58.71]), 0.5 * dt * H.FTM2V
+    fx.f[:] = 0.0
+    worst, trips = 0.0, 0
+    for step in range(1, 171):
+        xi = rng.normal(size=(nl, 3))
+        eng.initial_integrate(x, v, f, m, dt, dtf)
+        sync(x, v)
+        f = np.zeros((nl, 3))
+        eng.post_force(x, v, f, xi, step)
+        eng.final_integrate(v, f, m, dtf)
+        sync(x, v)
+        eng.end_of_step(x, v)
+        fx.initial_integrate([58.71])
+        sync(fx.x, fx.v)
+        fx.f[:] = 0.0
+        fx.post_force(xi)
+        fx.final_integrate([58.71])
+        sync(fx.x, fx.v)
+        fx.end_of_step()
+        worst = max(worst, H.error_metrics(f, fx.f[:nl]), H.error_metrics(x[:nl], fx.x[:nl]),
+                    H.error_metrics(eng.get_grid(0), fx.fdm.field(0)))
+    st = eng.list_stats()
+    moved = np.abs(x[:nl] - s["x"][:nl]).max()
+    assert worst < G.TOL, worst
+    assert 0.7 < moved < 1.0, moved          # within the life of a LAMMPS list (re-neighbouring at 1 A)
+    # every guard trip costs one step on the full list and is answered by a rebuild: no run of fall-back steps
+    assert st["inner_builds"] >= 4 and st["fallback_steps"] <= st["inner_builds"], st
+
+
+def test_emulated_fix_extra_skin_keyword():
+    """`extra_skin 0.4`: the fix asks LAMMPS for a list 0.4 A longer and tells the engine so; forces, grid and energies are
+    those of the reference on the standard list (r_c decides the pair set), across re-neighbourings; a negative value is
+    refused"""
+    import reneighbour_cases
+    reneighbour_cases.fix_case("eph", {}, ("extra_skin", "0.4"), schedule={2: 7.4, 4: 7.4})
+    s = H.make_system(2, skin=2.4)
+    bad = H.fix_args(7, reneighbour_cases.BETA, ["Ni"], grid=(1, 1, 1), style="eph/b200", extra=["extra_skin", "-0.1"])
+    with pytest.raises(Exception, match="extra_skin must be >= 0"):
+        host.FixDriver(s, bad)
+
+
 def test_emulated_fixes_with_32_bit_atom_tags(ni_trunc_beta, emulated_engine):
     """LAMMPS' default build (-DLAMMPS_SMALLBIG) has 32-bit atom tags: the host classes, compiled against a stand-in with
     `typedef int tagint`, widen the tags for the C ABI and give the same forces -- with the built-in Gaussian stream too,

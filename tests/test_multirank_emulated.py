@@ -121,7 +121,19 @@ def _worker(rank, world, port, q, beta, gshape, sharded, boundary_first, tau0=0.
             out.append(dict(f=f.copy(), rho=eng.probe(0)[:nl].copy(), T=eng.get_grid(0).copy(), E=E,
                             substeps=eng.last_substeps()))
         calls = [L.emul_nccl_calls(k) for k in range(4)]
-        q.put((rank, s["tag"][:nl].copy(), out, eng.exchange_bytes, calls, eng.comm_transport()))
+        # LAMMPS' forward comm of x and v on the "device" (eph_b200_refresh_ghosts, the second per-step exchange of a run
+        # whose atoms live there): the first call records the image shifts, then the owners move and the ghosts must follow
+        import torch
+        tag = s["tag"].astype(np.float64)
+        move = lambda t: 1e-3 * np.stack([np.sin(t), np.cos(2 * t), np.sin(3 * t)], axis=1)
+        vel = lambda t: np.stack([1e-3 * t, -2e-3 * t, 5e-4 * t], axis=1)
+        xt, vt = torch.from_numpy(s["x"].copy()), torch.from_numpy(s["v"].copy())
+        eng.refresh_ghosts(xt, vt)
+        xt[:nl] += torch.from_numpy(move(tag[:nl]))
+        vt[:nl] = torch.from_numpy(vel(tag[:nl]))
+        eng.refresh_ghosts(xt, vt)
+        refresh_err = max(np.abs(xt.numpy()[nl:] - (s["x"][nl:] + move(tag[nl:]))).max(), np.abs(vt.numpy()[nl:] - vel(tag[nl:])).max())
+        q.put((rank, s["tag"][:nl].copy(), out, eng.exchange_bytes, calls, eng.comm_transport(), float(refresh_err)))
         del keep_cbs
     finally:
         dist.destroy_process_group()
@@ -163,7 +175,8 @@ def test_engine_data_plane_on_gloo_ranks_matches_whole_box_oracle(synth_beta_1, 
         fx.end_of_step()
         ref_f, ref_rho = fx.f[:nlw], np.array(fx.ptr(0))[:nlw]
         E = 0.0
-        for rank, tags, out, nbytes, calls, used in res:
+        for rank, tags, out, nbytes, calls, used, refresh_err in res:
+            assert refresh_err < 1e-12, (rank, refresh_err)
             idx = order[np.searchsorted(whole["tag"][:nlw][order], tags)]
             assert H.error_metrics(out[k]["f"], ref_f[idx], floor=np.abs(ref_f).max()) < TOL, (rank, step)
             assert H.error_metrics(out[k]["rho"], ref_rho[idx]) < TOL, (rank, step)

@@ -2521,7 +2521,7 @@ int eph_b200_refresh_ghosts(eph_b200_handle *h, double *x, double *v) {
       const int cap = 2 * h->sm_count;
       {
         KernelTimer kt(h, "refresh_send");
-        p2p_send_xv_kernel<<<std::min(cap, std::max(1, blocks_for(h->gm_nsend, 256))), 256, 0, h->stream>>>(m, h->gm_nsend, h->gm_send_idx.p, x, v, epoch,
+        p2p_send_xv_kernel<<<std::min(cap, std::max(1, blocks_for(3LL * h->gm_nsend, 256))), 256, 0, h->stream>>>(m, h->gm_nsend, h->gm_send_idx.p, x, v, epoch,
                                                                                                           h->p2p_done.p + 1);
       }
       EPH_LAUNCH_CHECK(h);

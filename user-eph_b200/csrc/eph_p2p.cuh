@@ -128,18 +128,20 @@ __global__ void __launch_bounds__(256) p2p_send_payload_kernel(P2PMap m, int ns,
   p2p_signal(m, 0, epoch, done_blocks);
 }
 
-// kind 1: {x, v} of the atoms other ranks hold as ghosts
+// kind 1: {x, v} of the atoms other ranks hold as ghosts.  A row is three 16-byte pieces {x0 x1 | x2 v0 | v1 v2}; one
+// thread per PIECE, so that consecutive threads store consecutive 16 bytes of the receiver's window (a thread per row
+// would store 16 bytes at a stride of 48)
 __global__ void __launch_bounds__(256) p2p_send_xv_kernel(P2PMap m, int ns, const int *__restrict__ index, const double *__restrict__ x,
                                                           const double *__restrict__ v, unsigned long long epoch, unsigned *done_blocks) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
+  const long long pieces = 3LL * ns;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < pieces; c += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(c / 3), part = (int)(c - 3LL * t);
     const int p = p2p_peer_of(m.send_off, m.n, t);
     const int rows = m.send_off[p + 1] - m.send_off[p], r = t - m.send_off[p];
     char *half = m.remote[p] + kP2PHeaderBytes + (size_t)m.my_rank * m.region_bytes + (size_t)(epoch & 1ull) * (m.region_bytes / 2);
-    double2 *q = reinterpret_cast<double2 *>(half + p2p_kind1_offset(rows)) + 3 * (size_t)r;
+    double2 *q = reinterpret_cast<double2 *>(half + p2p_kind1_offset(rows)) + 3 * (size_t)r + part;
     const size_t a = 3 * (size_t)index[t];
-    q[0] = make_double2(x[a], x[a + 1]);
-    q[1] = make_double2(x[a + 2], v[a]);
-    q[2] = make_double2(v[a + 1], v[a + 2]);
+    *q = part == 0 ? make_double2(x[a], x[a + 1]) : part == 1 ? make_double2(x[a + 2], v[a]) : make_double2(v[a + 1], v[a + 2]);
   }
   p2p_signal(m, 1, epoch, done_blocks);
 }

@@ -138,6 +138,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   neigh_device = false;
   integrate_device = false;
   sync_every = 1;
+  extra_skin = 0.0;
   peratom_every = 1;
   int device = -1;
   // token by token: decks list more element names than atom types (e.g. `Ni.beta Ni Ni` with one type); like the
@@ -145,7 +146,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
   for (int k = 17 + types; k < narg; ++k) {
     const bool is_keyword = strcmp(arg[k], "rng") == 0 || strcmp(arg[k], "device") == 0 || strcmp(arg[k], "neigh") == 0 ||
                             strcmp(arg[k], "peratom") == 0 || strcmp(arg[k], "comm") == 0 || strcmp(arg[k], "grid") == 0 ||
-                            strcmp(arg[k], "integrate") == 0 || strcmp(arg[k], "sync") == 0;
+                            strcmp(arg[k], "integrate") == 0 || strcmp(arg[k], "sync") == 0 || strcmp(arg[k], "extra_skin") == 0;
     if (!is_keyword) continue;   // an extra element name
     if (k + 1 >= narg) error->all(FLERR, "fix eph/b200: keyword without a value");
     const char *val = arg[k + 1];
@@ -171,6 +172,9 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
     } else if (strcmp(arg[k], "sync") == 0) {
       sync_every = atoi(val);
       if (sync_every < 1) error->all(FLERR, "fix eph/b200: sync must be >= 1");
+    } else if (strcmp(arg[k], "extra_skin") == 0) {
+      extra_skin = atof(val);
+      if (!(extra_skin >= 0.0)) error->all(FLERR, "fix eph/b200: extra_skin must be >= 0");
     } else if (strcmp(arg[k], "grid") == 0) {
       if (strcmp(val, "sharded") == 0) grid_sharded = true;
       else if (strcmp(val, "replicated") == 0) grid_sharded = false;
@@ -241,7 +245,7 @@ FixEPHB200::FixEPHB200(LAMMPS *lmp, int narg, char **arg)
                                    grid.E_e_T.y.data()),
           "set_grid_tables");
   check(eph_b200_set_dt(dev, update->dt, force->boltz), "set_dt");
-  check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
+  check(eph_b200_set_skin(dev, neighbor->skin + extra_skin, -1.0), "set_skin");
   if (coloured) check(eph_b200_set_colour(dev, tau0), "set_colour");
 
   array = nullptr;
@@ -288,12 +292,16 @@ void FixEPHB200::init() {
   if (!neigh_device) {
     int request_style = NeighConst::REQ_FULL | NeighConst::REQ_GHOST;
     auto req = neighbor->add_request(this, request_style);
-    req->set_cutoff(r_cutoff);
+    // `extra_skin X`: the engine's inner list (skin 0.4 A) can be rebuilt from LAMMPS' aged list only while twice the
+    // displacement since LAMMPS' build plus the inner skin still fits into the list's skin; LAMMPS re-neighbours at
+    // half ITS skin, so for the last fifth of a list's life the sweeps would have to walk the full list.  A list
+    // requested X = 0.4 A longer closes that gap; the pair set the forces see is unchanged (r_c decides).
+    req->set_cutoff(r_cutoff + extra_skin);
   }
 
   // a `neighbor` / `neigh_modify` command may have changed the skin since the fix line or between runs; the engine's
   // inner list is validated against it on the device, so it must know the current value before every run
-  check(eph_b200_set_skin(dev, neighbor->skin, -1.0), "set_skin");
+  check(eph_b200_set_skin(dev, neighbor->skin + extra_skin, -1.0), "set_skin");
   need_upload = true;
   if (integrate_device && neighbor->dist_check)
     error->all(FLERR, "fix eph/b200: integrate device needs a re-neighbouring schedule known in advance (neigh_modify every N delay 0 check no)");
@@ -435,7 +443,7 @@ void FixEPHB200::upload_topology() {
     check(eph_b200_resident_upload(dev, &atom->x[0][0], &atom->v[0][0]), "resident_upload");
     uploaded = true;
   }
-  if (neigh_device) check(eph_b200_build_neighbors(dev, uploaded ? nullptr : &atom->x[0][0], r_cutoff + neighbor->skin, EPH_B200_HOST), "build_neighbors");
+  if (neigh_device) check(eph_b200_build_neighbors(dev, uploaded ? nullptr : &atom->x[0][0], r_cutoff + neighbor->skin + extra_skin, EPH_B200_HOST), "build_neighbors");
   else check(eph_b200_set_neighbors_lammps(dev, nlocal, list->numneigh, list->firstneigh), "set_neighbors");
   // the memory kernel's state in the atoms' present order (LAMMPS may have sorted or migrated them)
   if (coloured && nlocal > 0) check(eph_b200_set_colour_state(dev, &f_dis_i[0][0], &f_sto_i[0][0], EPH_B200_HOST), "set_colour_state");

@@ -118,6 +118,7 @@ class FixEPHB200 : public Fix {
   bool neigh_device;
   bool integrate_device;        // keyword `integrate device`: x, v, f of the atoms stay on the device between the hooks
   int sync_every;               // keyword `sync N`: with integrate device, LAMMPS' host f and v are refreshed every N-th step
+  double extra_skin;            // keyword `extra_skin X`: the list is requested X A longer than r_c + neighbor->skin (see init())
   int peratom_every;            // keyword `peratom N`: array_atom is refreshed every N-th step (0: never)
   class NeighList *list;
   double Ee;
