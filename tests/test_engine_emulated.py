@@ -280,8 +280,9 @@ def test_emulated_fix_keywords_through_reneighbouring(keywords):
 
 def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
     """200 velocity-Verlet steps of hot atoms under the fix's own forces, LAMMPS' list never rebuilt: the inner list is
-    rebuilt several times as the atoms drift, then (once 2 D + inner skin > skin) the engine stays on LAMMPS' list --
-    and the forces, positions and grid follow the oracle to 1e-10 all the way"""
+    rebuilt several times as the atoms drift; late rebuilds stand for a shorter skin (skin - 2 D: the guard trips sooner)
+    and only when that falls below 0.1 A does the engine stay on LAMMPS' list -- 20 fall-back steps here, 51 when a late
+    rebuild had to carry the full inner skin -- and the forces, positions and grid follow the oracle to 1e-10 all the way"""
     s = H.make_system(4, T=6000.0)
     dt, nl = 1.5e-4, s["nlocal"]
     rng = np.random.default_rng(3)
@@ -315,7 +316,7 @@ def test_emulated_long_trajectory_list_state_machine(ni_trunc_beta):
                     H.error_metrics(eng.get_grid(0), fx.fdm.field(0)))
     st = eng.list_stats()
     assert worst < G.TOL, worst
-    assert st["inner_builds"] >= 4 and st["fallback_steps"] >= 10, st
+    assert st["inner_builds"] >= 5 and 8 <= st["fallback_steps"] <= 35, st
     assert 0.8 < np.abs(x[:nl] - s["x"][:nl]).max() < 1.2
 
 

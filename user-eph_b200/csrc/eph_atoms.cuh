@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
                                   const int *__restrict__ type, const int *__restrict__ mask,
                                   const int *__restrict__ type_map, int groupbit, double4 *__restrict__ pos4,
                                   double4 *__restrict__ pv, int track, int track0, const double4 *__restrict__ xref,
-                                  const double4 *__restrict__ xref0, double half_skin_sq, ListState *__restrict__ st,
+                                  const double4 *__restrict__ xref0, ListState *__restrict__ st,
                                   Packed32 *__restrict__ recD, double inv_period, unsigned *__restrict__ status) {
   __shared__ double s_max[8];
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) pack_atoms_kernel(int ntotal, const doubl
     if (track) {
       const double4 r = xref[a];
       const double dx = px - r.x, dy = py - r.y, dz = pz - r.z;
-      if (dx * dx + dy * dy + dz * dz > half_skin_sq) st->inner_invalid = 1u;
+      if (dx * dx + dy * dy + dz * dz > st->guard_sq) st->inner_invalid = 1u;
     }
     if (track0) {
       const double4 r0 = xref0[a];
@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) pv_fill_kernel(int ntotal, const double *
     pv[2 * (size_t)a + 1] = make_double4(v[3 * (size_t)a], v[3 * (size_t)a + 1], v[3 * (size_t)a + 2], 0.0);
   }
 }
+
+constexpr double kMinInnerSkin = 0.1;   // A
 
 struct PrepArgs {
   int nlocal, ntotal;
@@ -118,10 +120,16 @@ __global__ void prep_coupling_kernel(PrepArgs p) {
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.ntotal) return;
   if (a == 0 && p.built_inner) {
-    // an inner list built now from LAMMPS' list is complete only if r_c + inner_skin + 2 D <= r_c + skin,
-    // D = largest displacement since LAMMPS built its list
+    // An inner list built now from LAMMPS' list holds every pair that is closer than r_c + s, s = min(inner_skin,
+    // skin - 2 D), D = largest displacement since LAMMPS built its list (LAMMPS' list is complete up to r_c + skin at ITS
+    // build time).  It therefore stands until some atom has moved s / 2 since this build: late in the life of LAMMPS'
+    // list the guard simply trips sooner, instead of the engine having to walk the full list.  Below kMinInnerSkin the
+    // rebuilds would come every few steps: the list is declared invalid and the engine stays on LAMMPS' list.
     const double d0 = sqrt(__longlong_as_double((long long)p.list_state->disp0_sq_bits));
-    p.list_state->inner_invalid = (2.0 * d0 + p.inner_skin <= p.skin) ? 0u : 1u;
+    const double s = fmin(p.inner_skin, p.skin - 2.0 * d0);
+    const bool ok = s >= fmin(kMinInnerSkin, p.inner_skin);
+    p.list_state->inner_invalid = ok ? 0u : 1u;
+    p.list_state->guard_sq = ok ? 0.25 * s * s : 0.0;
   }
   // ghosts: owner >= 0 is a local atom of this rank (periodic image); owner < 0 means the owner lives on another
   // rank and the exchange already wrote {rho, W} into the ghost's own slot

@@ -1367,10 +1367,9 @@ int eph_b200_post_force_begin(eph_b200_handle *h, const double *x, const double 
   h->step_packed = packed;
   {
     KernelTimer kt(h, "pack_atoms");
-    const double half = 0.5 * h->inner_skin;
     pack_atoms_kernel<<<blocks_for(nt, 256), 256, 0, h->stream>>>(nt, dx, dv, h->type.p, h->mask.p, h->d_type_map.p,
                                                                    h->cfg.groupbit, h->pos4.p, packed ? nullptr : h->pv.p, track ? 1 : 0,
-                                                                   track0 ? 1 : 0, h->xref.p, h->xref0.p, half * half, h->lstate.p,
+                                                                   track0 ? 1 : 0, h->xref.p, h->xref0.p, h->lstate.p,
                                                                    packed ? h->recD.p : nullptr, 1.0 / packed_period(h), h->d_status.p);
   }
   EPH_LAUNCH_CHECK(h);

@@ -48,6 +48,8 @@ struct ListState {
   unsigned inner_invalid;   // != 0: the inner list must not be used (some atom moved more than inner_skin/2)
   unsigned pad;
   unsigned long long disp0_sq_bits;  // max squared displacement since LAMMPS built its list (double bits, >= 0)
+  double guard_sq;          // the inner list stands while no atom has moved further than this (squared) since its build:
+                            // half of the skin the list is COMPLETE for, set by prep_coupling in the step that builds it
 };
 
 // Streams that are read or written exactly once per pass (list indices, pair weights): evict-first hints keep
