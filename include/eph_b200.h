@@ -243,8 +243,9 @@ int eph_b200_grid_device_ptr(eph_b200_handle *h, int which, double **ptr);
  * together; EPH_B200_EXCHANGE=nccl forces send / receive, EPH_B200_P2P_WINDOW_MB (default 256) sizes the window.  With
  * peer memory set_ghost_map is collective (one small all-reduce): ghost rows that do not fit a rank's share of a
  * window make it fail on every rank together, with the size it needs.
- * comm_transport: 0 no communicator, 1 NCCL send / receive, 2 peer memory.  A peer that fails to arrive within 5 s sets
- * bit 8 of the status word instead of hanging the device. */
+ * comm_transport: 0 no communicator, 1 NCCL send / receive, 2 peer memory.  A peer that fails to arrive within 5 s
+ * (EPH_B200_P2P_TIMEOUT_MS) sets bit 8 of the status word instead of hanging the device, and the next end_of_step
+ * that returns the energy fails with EPH_B200_ERR_COMM. */
 #define EPH_B200_COMM_ID_BYTES 128
 int eph_b200_comm_get_id(void *id128);
 int eph_b200_comm_init(eph_b200_handle *h, const void *id128, int rank, int nranks);

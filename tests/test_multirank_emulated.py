@@ -243,3 +243,62 @@ def test_ghost_rows_that_do_not_fit_the_window_fail_on_every_rank(synth_beta_1):
         assert used == 2, used                      # the windows themselves were set up
         assert rows * 104 > (65536 - 8192) // world // 2, rows   # the premise of the test
         assert msg is not None and "EPH_B200_P2P_WINDOW_MB" in msg and "EPH_B200_EXCHANGE=nccl" in msg, msg
+
+
+def _timeout_worker(rank, world, port, q, beta):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EPH_B200_P2P_WINDOW_MB="8", EPH_B200_P2P_TIMEOUT_MS="300")
+    os.environ.pop("EPH_B200_EXCHANGE", None)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = _swap_in_emulated_engine()
+        keep_cbs = gloo_transport(L)
+        grid = P.brick_grid(world)
+        s = H.make_system(CELLS, brick=(rank, grid))
+        nl = s["nlocal"]
+        box = [0, s["box"][0], 0, s["box"][1], 0, s["box"][2]]
+        plan = P.ExchangePlan(s, rank, world, dist)
+        eng = lib.Engine([0], flags=7, seed=SEED, rank=rank, nranks=world)
+        eng.set_tables_from(host.BetaTables(path=beta))
+        eng.set_grid(2, 2, 2, box, 300.0, 1.0, 3.5e-6, 0.1248)
+        eng.set_dt(DT)
+        P.attach_comm(eng, dist, rank, world)
+        keep = [np.ascontiguousarray(s["type"], dtype=np.int32), np.ascontiguousarray(s["mask"], dtype=np.int32),
+                np.ascontiguousarray(s["tag"], dtype=np.int64), np.ascontiguousarray(plan.self_owner, dtype=np.int32),
+                np.ascontiguousarray(s["offsets"], dtype=np.int64), np.ascontiguousarray(s["neigh"], dtype=np.int32)]
+        eng.set_atoms(nl, s["nghost"], *keep[:4])
+        eng.set_neighbors(*keep[4:])
+        eng.set_ghost_map(plan)
+        x, v, f = s["x"].copy(), s["v"].copy(), np.zeros((nl, 3))
+        msg = None
+        try:
+            if rank == 0:
+                eng.post_force(x, v, f, None, 1)          # exchanges: rank 1 never sends its rows
+            else:
+                eng.post_force_begin(x, v, None, 1)       # a rank that skips the exchange (a bug, a crash ...)
+                eng.post_force_end(f)
+            eng.end_of_step(x, v, want_energy=True)       # the all-reduce of the source term still matches on both
+        except lib.EphError as e:
+            msg = str(e)
+        q.put((rank, msg, eng.status_word()))
+        del keep_cbs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_peer_that_never_delivers_is_an_error_not_a_hang(synth_beta_1):
+    """rank 1 skips the ghost exchange of a step: rank 0's receiving kernel gives up after the time-out (300 ms here),
+    sets bit 8 of the status word, and the step's host synchronisation in end_of_step turns it into an error"""
+    subprocess.check_call(["make", "-C", EMUL, "libeph_b200_emul.so"], stdout=subprocess.DEVNULL)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, q, synth_beta_1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    (r0, msg0, st0), (r1, msg1, st1) = res
+    assert msg0 is not None and "timed out" in msg0, msg0
+    assert st0 & 0x100 and not (st1 & 0x100), (st0, st1)
+    assert msg1 is None, msg1

@@ -1811,9 +1811,14 @@ static int end_of_step_finish(eph_b200_handle *h, double *E_local, bool solve) {
     h->solve_pending = true;
   }
   if (E_local) {
+    unsigned *status = reinterpret_cast<unsigned *>(h->h_pinned + 5);
     EPH_CUDA(h, cudaMemcpyAsync(h->h_pinned, h->d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->p2p_ok) EPH_CUDA(h, cudaMemcpyAsync(status, h->d_status.p, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
     EPH_CUDA(h, cudaStreamSynchronize(h->stream));
     *E_local = h->h_pinned[0];
+    // the step's one host synchronisation is where a peer that never delivered its ghost rows becomes an error
+    if (h->p2p_ok && (*status & kStatusP2PTimeout))
+      return fail(h, EPH_B200_ERR_COMM, "a peer-memory ghost exchange timed out: a peer rank did not deliver its rows (results of this step are invalid)");
   }
   return EPH_B200_OK;
 }
@@ -2270,6 +2275,8 @@ int eph_b200_set_ghost_map(eph_b200_handle *h, int npeers, const int *peer_rank,
     m = P2PMap{};
     const bool too_many = npeers > kP2PMaxPeers;
     m.n = too_many ? 0 : npeers; m.my_rank = h->comm_rank; m.local = h->p2p_window; m.region_bytes = h->p2p_region_bytes;
+    const char *tmo = std::getenv("EPH_B200_P2P_TIMEOUT_MS");
+    m.timeout_ns = tmo && std::atof(tmo) > 0.0 ? (unsigned long long)(std::atof(tmo) * 1e6) : kP2PTimeoutNs;
     size_t worst = 0;
     int worst_rows = 0, worst_rank = -1;
     for (int p = 0; p < m.n; ++p) {

@@ -38,6 +38,7 @@ struct P2PMap {
   char *remote[kP2PMaxPeers];         // peer p's window, mapped into this process
   char *local;                        // own window
   size_t region_bytes;
+  unsigned long long timeout_ns;      // how long the receiving side polls for a peer's flag before it gives up
 };
 
 __host__ __device__ inline size_t p2p_kind1_offset(int rows) { return ((size_t)rows * 56 + 255) / 256 * 256; }
@@ -57,7 +58,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long kP2PTimeoutNs = 5000000000ull;
+constexpr unsigned long long kP2PTimeoutNs = 5000000000ull;      // default; EPH_B200_P2P_TIMEOUT_MS
 #else
 // host build of the tests: the windows are shared-memory objects of the ranks' processes
 inline unsigned long long ld_acquire_sys_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
@@ -67,7 +68,7 @@ inline unsigned long long global_timer_ns() {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
-constexpr unsigned long long kP2PTimeoutNs = 120000000000ull;
+constexpr unsigned long long kP2PTimeoutNs = 120000000000ull;   // default on the (slow) host build
 #endif
 
 __device__ __forceinline__ int p2p_peer_of(const int *off, int n, int t) {
@@ -103,7 +104,7 @@ __device__ __forceinline__ void p2p_wait(const P2PMap &m, int kind, unsigned lon
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys_u64(flag) < epoch) {
       __nanosleep(64);
-      if (global_timer_ns() - t0 > kP2PTimeoutNs) { atomicOr(status, kStatusP2PTimeout); break; }
+      if (global_timer_ns() - t0 > m.timeout_ns) { atomicOr(status, kStatusP2PTimeout); break; }
     }
   }
   __syncthreads();
