@@ -52,7 +52,7 @@ def group_ghosts_by_owner_rank(s, rank):
 
 
 def _worker(rank, world, port, q, beta, gshape, comm_mode, extra):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EPH_B200_P2P_WINDOW_MB="8")   # small shared-memory windows
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         L = _swap_in_emulated_engine()
