@@ -14,8 +14,9 @@ re-neighbouring: the fix registers its atoms again, receives the full list LAMMP
 from LAMMPS-KOKKOS; `--neigh device` makes the engine build it from the positions instead -- and rebuilds its inner
 list) -> post_force -> final_integrate -> end_of_step.  The atoms move and all of it is inside the timed region
 (`--mode static` times post_force + end_of_step on frozen atoms instead, the round-1 measurement).  `value` has everything resident in HBM; `e2e` goes through the same C ABI with pinned HOST
-buffers.  On N > 1 GPUs the engine's own NCCL data plane runs the ghost exchange, the source all-reduce and the grid
-solve, and after the timed steps the result is checked atom by atom against the whole box on one GPU (`parity_vs_n1`).
+buffers.  On N > 1 GPUs the engine's own data plane runs the ghost exchanges (NVLink peer memory, or NCCL send/receive),
+the source all-reduce (NCCL) and the grid solve, and after the timed steps the result is checked atom by atom against
+the whole box on one GPU (`parity_vs_n1`); `step_breakdown` says where the step goes.
 Prints ONE JSON line.
 """
 import argparse
@@ -263,7 +264,7 @@ def workload_config(a, natoms):
                         "FDM grid %d^3, dt %.3g ps, full list at 7 A" % (name, a.cells, natoms, a.grid, a.dt),
             "atoms": natoms, "fdm_grid": [a.grid] * 3, "beta_file": beta + " (shipped copy, tests/golden/data)", "step": steps,
             "l2": "inputs (neighbour list + per-atom arrays) far larger than the 126 MB L2; no flush needed",
-            "parallelism": "spatial bricks, one rank per GPU; ghost exchange, source all-reduce and grid solve by the engine over NCCL"}
+            "parallelism": "spatial bricks, one rank per GPU; ghost exchanges (peer memory or NCCL send/receive), source all-reduce (NCCL) and grid solve by the engine"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
